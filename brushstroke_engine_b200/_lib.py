@@ -1,0 +1,100 @@
+"""ctypes binding of libnbe_b200.so (the C ABI declared in include/nbe_b200.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is
+missing or a call fails, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libnbe_b200.so')
+
+F32, F16, BF16, F64 = 0, 1, 2, 3
+DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.float64: F64}
+
+_P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
+
+# name -> argtypes  (order = include/nbe_b200.h)
+_SIGNATURES = {
+    'nbe_bias_act': [_P, _P, _P, _L, _L, _L, _I, _F, _F, _F, _I, _P],
+    'nbe_upfirdn2d': [_P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _L, _I, _I, _L, _L, _L, _L,
+                      _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'nbe_conv2d_f32': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _L, _F, _P, _I, _F, _F, _F, _P],
+    'nbe_weight_sqsum_f32': [_P, _P, _I, _I, _I, _P],
+    'nbe_demod_coefs_f32': [_P, _P, _P, _I, _I, _I, _P],
+    'nbe_fc_f32': [_P, _I, _P, _P, _P, _I, _I, _I, _L, _L, _F, _F, _I, _F, _F, _I, _P],
+    'nbe_shifted_noise_f32': [_P, _P, _P, _P, _I, _I, _I, _P],
+    'nbe_pack_nhwc_bf16': [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    'nbe_unpack_nchw_f32': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'nbe_upsample2x_nhwc_bf16': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'nbe_prepare_weights_bf16': [_P, _P, _I, _I, _I, _I, _P],
+    'nbe_conv_tc_bf16': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _F, _P, _F, _F, _F, _P, _P],
+    'nbe_torgb_triad': [_P, _I, _I, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P],
+    'nbe_triad_composite': [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    'nbe_gather_geom_patches': [_P, _I, _I, _P, _P, _I, _I, _P],
+    'nbe_tile_owner_map': [_P, _I, _I, _P, _I, _I, _P],
+    'nbe_place_tiles': [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P],
+    'nbe_blend_features': [_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} is missing: build it with `python -m brushstroke_engine_b200.build` '
+            '(there is no CPU / PyTorch fallback for the NeuBE hot path).')
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.nbe_abi_version.restype = c_int
+    lib.nbe_last_error.restype = c_char_p
+    lib.nbe_launch_count.restype = c_int64
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    if lib.nbe_abi_version() != 1:
+        raise RuntimeError(f'libnbe_b200.so ABI version {lib.nbe_abi_version()} != 1; rebuild it')
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return ['nbe_abi_version', 'nbe_last_error', 'nbe_launch_count'] + list(_SIGNATURES.keys())
+
+
+def launch_count() -> int:
+    return int(load().nbe_launch_count())
+
+
+def call(name: str, *args) -> None:
+    """Invoke one entry point; non-zero status -> RuntimeError with the library's message."""
+    lib = load()
+    status = getattr(lib, name)(*args)
+    if status != 0:
+        msg = lib.nbe_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'{name} failed ({status}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not isinstance(t, torch.Tensor) or t.device.type != 'cuda':
+        raise RuntimeError(f'{what}: expected a CUDA tensor, got {type(t).__name__} on '
+                           f'{getattr(t, "device", None)} (no CPU fallback on this path)')

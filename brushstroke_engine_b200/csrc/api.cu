@@ -1,0 +1,11 @@
+// Library-wide state of libnbe_b200.so: error string, launch counter, ABI version.
+#include "common.cuh"
+
+namespace nbe {
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+}  // namespace nbe
+
+extern "C" int nbe_abi_version(void) { return NBE_ABI_VERSION; }
+extern "C" const char* nbe_last_error(void) { return nbe::g_err; }
+extern "C" int64_t nbe_launch_count(void) { return nbe::g_launches.load(std::memory_order_relaxed); }

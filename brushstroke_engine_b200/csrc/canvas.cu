@@ -1,0 +1,139 @@
+// Engine composite + canvas-side integer work of the patch scheduler (bit-exact index arithmetic).
+#include "common.cuh"
+
+namespace nbe {
+
+// rgba from uvs/colors (+ optional UVS remap), float and/or cropped uint8 HWC tile.
+__global__ void __launch_bounds__(256)
+triad_composite_kernel(const float* __restrict__ uvs, const float* __restrict__ colors01, const float* __restrict__ sfactor,
+                       int mode, float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, int N, int H, int W, int m) {
+    const int HW = H * W;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * HW) return;
+    const int n = idx / HW, pix = idx - n * HW;
+    const int y = pix / W, x = pix - y * W;
+    float U = uvs[((int64_t)n * 3 + 0) * HW + pix];
+    float V = uvs[((int64_t)n * 3 + 1) * HW + pix];
+    float S = uvs[((int64_t)n * 3 + 2) * HW + pix];
+    if (sfactor) {
+        // StyleUVSMapper._map_style_s (mapper.py:53-72), same op order in fp32
+        float Sp = sfactor[n] * S;
+        if (Sp > 1.0f) Sp = 1.0f;
+        const float delta = 1.f - Sp;
+        const float uvf = (delta <= 0.000001f) ? 0.f : __fdiv_rn(delta, __fadd_rn(U, V));
+        U = uvf * U; V = uvf * V; S = Sp;
+    }
+    const float* c = colors01 + n * 9;
+    float rgba[4];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)                                // torch.sum over k of uvs_k * colors[ch,k]: ((u*c0 + v*c1) + s*c2)
+        rgba[ch] = __fadd_rn(__fadd_rn(__fmul_rn(U, c[ch * 3 + 0]), __fmul_rn(V, c[ch * 3 + 1])), __fmul_rn(S, c[ch * 3 + 2]));
+    rgba[3] = (mode == 0) ? __fadd_rn(U, V) : 1.f;
+    if (out_f32) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) out_f32[((int64_t)n * 4 + ch) * HW + pix] = rgba[ch];
+    }
+    if (out_u8 && y >= m && y < H - m && x >= m && x < W - m) {
+        const int T = W - 2 * m, TH = H - 2 * m;
+        uchar4 px;
+        uint8_t* o = reinterpret_cast<uint8_t*>(&px);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            float v = __fmul_rn(rgba[ch], 255.f);
+            v = fminf(fmaxf(v, 0.f), 255.f);
+            o[ch] = (uint8_t)v;                                    // truncation, as tensor.to(torch.uint8)
+        }
+        reinterpret_cast<uchar4*>(out_u8)[((int64_t)n * TH + (y - m)) * T + (x - m)] = px;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gather_geom_kernel(const uint8_t* __restrict__ canvas, int canvas_h, int canvas_w, const int32_t* __restrict__ crops,
+                   float* __restrict__ geom, int N, int P) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * P * P) return;
+    const int n = idx / (P * P), r = idx - n * P * P;
+    const int y = r / P, x = r - y * P;
+    const int cy = crops[2 * n] + y, cx = crops[2 * n + 1] + x;
+    uint8_t g = 255;
+    if (cy >= 0 && cy < canvas_h && cx >= 0 && cx < canvas_w) g = canvas[(int64_t)cy * canvas_w + cx];
+    const uint8_t inv = (uint8_t)(255 - g);                        // paint_image_main.py:167
+    geom[idx] = __fsub_rn(1.f, __fdiv_rn((float)inv, 255.0f));     // brush.py:679
+}
+
+// owner[y,x] = max raster index of a tile covering the pixel, -1 if none (last writer wins in raster order).
+// Scatter formulation: one thread per (tile, tile pixel) does an atomicMax of the tile index -- O(tiles * T^2)
+// instead of O(pixels * tiles); `owner` is pre-filled with -1 by the host wrapper.
+__global__ void __launch_bounds__(256)
+tile_owner_kernel(const int32_t* __restrict__ tile_yx, int n_tiles, int T, int32_t* __restrict__ owner, int h, int w) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_tiles * T * T) return;
+    const int t = (int)(idx / (T * T));
+    const int r = (int)(idx - (int64_t)t * T * T);
+    const int y = tile_yx[2 * t] + r / T, x = tile_yx[2 * t + 1] + r % T;
+    if (y < 0 || y >= h || x < 0 || x >= w) return;
+    atomicMax(&owner[(int64_t)y * w + x], t);
+}
+
+__global__ void __launch_bounds__(256)
+place_tiles_kernel(const uint8_t* __restrict__ tiles, const int32_t* __restrict__ tile_yx, const int32_t* __restrict__ order,
+                   int N, int T, const int32_t* __restrict__ owner, uint8_t* __restrict__ canvas, int h, int w) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)N * T * T) return;
+    const int n = (int)(idx / (T * T));
+    const int r = (int)(idx - (int64_t)n * T * T);
+    const int ly = r / T, lx = r - ly * T;
+    const int y = tile_yx[2 * n] + ly, x = tile_yx[2 * n + 1] + lx;
+    if (y < 0 || y >= h || x < 0 || x >= w) return;
+    if (owner && owner[(int64_t)y * w + x] != order[n]) return;
+    reinterpret_cast<uchar4*>(canvas)[(int64_t)y * w + x] = reinterpret_cast<const uchar4*>(tiles)[idx];
+}
+
+}  // namespace nbe
+
+using namespace nbe;
+
+extern "C" int nbe_triad_composite(const float* uvs, const float* colors01, const float* sfactor, int mode,
+                                   float* out_f32, uint8_t* out_u8, int N, int H, int W, int crop_margin,
+                                   nbe_stream_t stream) {
+    NBE_REQUIRE(uvs && colors01 && (out_f32 || out_u8), "triad_composite: null tensor");
+    NBE_REQUIRE(mode == 0 || mode == 1, "triad_composite: unknown render mode %d", mode);
+    NBE_REQUIRE(N >= 0 && H >= 1 && W >= 1 && crop_margin >= 0 && 2 * crop_margin < H && 2 * crop_margin < W, "triad_composite: bad shape");
+    if (N == 0) return NBE_OK;
+    const int64_t total = (int64_t)N * H * W;
+    NBE_REQUIRE(total <= INT32_MAX, "triad_composite: too large");
+    triad_composite_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        uvs, colors01, sfactor, mode, out_f32, out_u8, N, H, W, crop_margin);
+    return launched("triad_composite_kernel");
+}
+
+extern "C" int nbe_gather_geom_patches(const uint8_t* canvas, int canvas_h, int canvas_w, const int32_t* crops, float* geom,
+                                       int N, int P, nbe_stream_t stream) {
+    NBE_REQUIRE(canvas && crops && geom && N >= 0 && P >= 1 && canvas_h >= 1 && canvas_w >= 1, "gather_geom_patches: bad arguments");
+    if (N == 0) return NBE_OK;
+    const int64_t total = (int64_t)N * P * P;
+    NBE_REQUIRE(total <= INT32_MAX, "gather_geom_patches: too large");
+    gather_geom_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(canvas, canvas_h, canvas_w, crops, geom, N, P);
+    return launched("gather_geom_kernel");
+}
+
+extern "C" int nbe_tile_owner_map(const int32_t* tile_yx, int n_tiles, int T, int32_t* owner, int canvas_h, int canvas_w,
+                                  nbe_stream_t stream) {
+    NBE_REQUIRE(tile_yx && owner && n_tiles >= 0 && T >= 1 && canvas_h >= 1 && canvas_w >= 1, "tile_owner_map: bad arguments");
+    cudaError_t e = cudaMemsetAsync(owner, 0xFF, (size_t)canvas_h * canvas_w * sizeof(int32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(NBE_ECUDA, "tile_owner_map: memset: %s", cudaGetErrorString(e));
+    if (n_tiles == 0) return NBE_OK;
+    const int64_t total = (int64_t)n_tiles * T * T;
+    tile_owner_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tile_yx, n_tiles, T, owner, canvas_h, canvas_w);
+    return launched("tile_owner_kernel");
+}
+
+extern "C" int nbe_place_tiles(const uint8_t* tiles, const int32_t* tile_yx, const int32_t* order, int N, int T,
+                               const int32_t* owner, uint8_t* canvas, int canvas_h, int canvas_w, nbe_stream_t stream) {
+    NBE_REQUIRE(tiles && tile_yx && canvas && N >= 0 && T >= 1, "place_tiles: bad arguments");
+    NBE_REQUIRE(!owner || order, "place_tiles: owner map given without tile order");
+    if (N == 0) return NBE_OK;
+    const int64_t total = (int64_t)N * T * T;
+    place_tiles_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tiles, tile_yx, order, N, T, owner, canvas, canvas_h, canvas_w);
+    return launched("place_tiles_kernel");
+}

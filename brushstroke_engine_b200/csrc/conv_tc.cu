@@ -1,0 +1,342 @@
+// modulated_conv2d as an implicit GEMM on 5th-gen tensor cores (tcgen05), BF16 operands, FP32 accumulate.
+//
+//   D[m, o] = sum_{tap, c} A_tap[m, c] * Wq[tap][o][c]           m = pixel (n, oy, ox), o = out channel
+//
+// * Activations are NHWC bf16.  For filter tap (kh, kw) the A tile of a 128-pixel block is exactly one 4-D TMA box
+//   {64 channels, bw, bh, bn} of the activation tensor shifted by (kw - pad, kh - pad): no im2col buffer, and TMA's
+//   out-of-bounds zero fill implements the convolution's zero padding (and the channel padding 144 -> 192).
+//   The box lands in shared memory as 128 rows x 128 bytes with the 128-byte swizzle = the canonical K-major UMMA
+//   operand layout, so the smem descriptor is built once per stage and advanced 32 bytes per K=16 step.
+// * Weights are pre-laid out [tap][Cout][Cin_pad] bf16 (nbe_prepare_weights_bf16); one 3-D TMA box per k-block.
+//   "Each patch carries its own style": modulation is applied on the *input* side by the producer of x (previous
+//   epilogue / upsample kernel) and demodulation in this epilogue, so the B operand is shared by the whole batch.
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//   warps 2..5 = epilogue (tcgen05.ld 32 lanes x 32 columns at a time -> demod, noise, bias, lrelu, gain, clamp,
+//   next-layer modulation -> bf16 -> 16-byte stores).  smem ring of STAGES {A 16 KiB, B Cout*128 B} with
+//   full/empty mbarriers; tcgen05.commit releases a stage when the MMAs that read it retire.
+// * Two CTAs fit per SM (<= 113 KiB smem, 128 TMEM columns each) so one CTA's epilogue overlaps the other's MMAs.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace nbe {
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) {                       // ~2 s at 2 GHz
+            printf("nbe conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO), LBO unused (=1), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct ConvTcParams {
+    __nv_bfloat16* y;
+    int N, OH, OW, Cout, y_cs;
+    int bw, bh, bn;                 // pixel box of one M tile (bw * bh * bn == 128)
+    int tiles_x, tiles_y;           // tiles per image in x / y
+    int KK, K, pad_off;             // taps, kernel size, coordinate offset (= -pad for 'same', 0 for 'valid')
+    int k_chunks;                   // Cin_pad / 64
+    const float* dcoef; const float* noise; long long noise_sn; float noise_gain;
+    const float* bias; float alpha, gain, clamp; const float* next_scale;
+    uint32_t idesc; uint32_t tmem_cols;
+};
+
+constexpr int TC_STAGES = 3;
+constexpr int TC_A_BYTES = 128 * 128;                               // 128 pixels x 64 bf16
+constexpr int TC_THREADS = 192;
+
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = p.Cout * 128;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + TC_STAGES * TC_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + TC_STAGES * b_bytes);
+    // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full ; then the TMEM base address
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile -> (n0, y0, x0)
+    int tile = blockIdx.x;
+    const int txi = tile % p.tiles_x; tile /= p.tiles_x;
+    const int tyi = tile % p.tiles_y; tile /= p.tiles_y;
+    const int n0 = tile * p.bn, y0 = tyi * p.bh, x0 = txi * p.bw;
+    const int num_kb = p.KK * p.k_chunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&bars[TC_STAGES + s]), 1); }
+        mbar_init(smem_u32(&bars[2 * TC_STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int tap = kb / p.k_chunks, cc = kb - tap * p.k_chunks;
+                const int kh = tap / p.K, kw = tap - kh * p.K;
+                mbar_wait(smem_u32(&bars[TC_STAGES + stage]), phase ^ 1);
+                const uint32_t full = smem_u32(&bars[stage]);
+                mbar_expect_tx(full, TC_A_BYTES + b_bytes);
+                tma_load_4d(smem_u32(smem_a + stage * TC_A_BYTES), &tmap_a, full, cc * 64, x0 + kw + p.pad_off, y0 + kh + p.pad_off, n0);
+                tma_load_3d(smem_u32(smem_b + stage * b_bytes), &tmap_b, full, cc * 64, 0, tap);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(smem_u32(&bars[stage]), phase);
+                tcgen05_fence_after();
+                const uint64_t a_desc = umma_smem_desc(smem_u32(smem_a + stage * TC_A_BYTES));
+                const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b + stage * b_bytes));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)                         // 4 x (K = 16) per 64-channel block: +32 B inside the swizzle atom
+                    umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+                umma_commit(smem_u32(&bars[TC_STAGES + stage]));    // frees the smem stage when these MMAs retire
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(smem_u32(&bars[2 * TC_STAGES]));            // accumulator complete
+        }
+    } else {
+        // ============================== epilogue (warps 2..5) ==============================
+        const int q = warp & 3;                                     // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;                                // accumulator row = pixel within the tile
+        const int wi = m % p.bw;
+        const int hi = (m / p.bw) % p.bh;
+        const int ni = m / (p.bw * p.bh);
+        const int n = n0 + ni, oy = y0 + hi, ox = x0 + wi;
+        const bool valid = n < p.N;
+        mbar_wait(smem_u32(&bars[2 * TC_STAGES]), 0);
+        tcgen05_fence_after();
+        float nz = 0.f;
+        if (valid && p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
+        const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
+        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (valid) {
+                __nv_bfloat16* yp = p.y + (((long long)n * p.OH + oy) * p.OW + ox) * p.y_cs + c0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    int4 out;
+                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float r[2];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int o = c0 + g * 8 + e * 2 + h;
+                            float a = __uint_as_float(v[g * 8 + e * 2 + h]);
+                            if (p.dcoef) a *= __ldg(p.dcoef + (long long)n * p.Cout + o);
+                            a += nz;
+                            if (p.bias) a += __ldg(p.bias + o);
+                            a *= (a > 0.f) ? pos_gain : neg_gain;
+                            if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
+                            if (p.next_scale) a *= __ldg(p.next_scale + (long long)n * p.Cout + o);
+                            r[h] = a;
+                        }
+                        o2[e] = __floats2bfloat162_rn(r[0], r[1]);
+                    }
+                    *reinterpret_cast<int4*>(yp + g * 8) = out;
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// [Cout][Cin][K][K] f32 -> [KK][Cout][Cin_pad] bf16 (flip = true convolution)
+__global__ void prepare_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wq, int Cout, int Cin, int Cin_pad, int KK, int flip) {
+    const int64_t total = (int64_t)KK * Cout * Cin_pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cin_pad);
+        const int o = (int)((i / Cin_pad) % Cout);
+        const int t = (int)(i / ((int64_t)Cin_pad * Cout));
+        float v = 0.f;
+        if (c < Cin) v = w[((int64_t)o * Cin + c) * KK + (flip ? KK - 1 - t : t)];
+        wq[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+static int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, const char* what) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(NBE_ECUDA, "conv_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NBE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return NBE_OK;
+}
+
+}  // namespace nbe
+
+using namespace nbe;
+
+extern "C" int nbe_prepare_weights_bf16(const float* w, void* wq, int Cout, int Cin, int K, int flip, nbe_stream_t stream) {
+    NBE_REQUIRE(w && wq && Cout >= 1 && Cin >= 1 && K >= 1, "prepare_weights: bad arguments");
+    const int Cin_pad = (Cin + 63) / 64 * 64;
+    const int64_t total = (int64_t)K * K * Cout * Cin_pad;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    prepare_weights_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wq, Cout, Cin, Cin_pad, K * K, flip);
+    return launched("prepare_weights_kernel");
+}
+
+extern "C" int nbe_conv_tc_bf16(const void* x, const void* wq, void* y,
+                                int N, int OH, int OW, int Cin, int x_cs, int Cout, int y_cs, int K, int valid,
+                                const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                                const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                                nbe_stream_t stream) {
+    NBE_REQUIRE(x && wq && y, "conv_tc: null tensor");
+    NBE_REQUIRE(N >= 0 && OH >= 1 && OW >= 1 && Cin >= 1, "conv_tc: bad shape");
+    NBE_REQUIRE(K == 1 || K == 3, "conv_tc: kernel size %d not supported (1 or 3)", K);
+    NBE_REQUIRE(Cout >= 16 && Cout <= 256 && Cout % 16 == 0, "conv_tc: Cout must be a multiple of 16 in [16, 256]");
+    NBE_REQUIRE(x_cs % 8 == 0 && x_cs >= Cin && y_cs % 8 == 0 && y_cs >= Cout, "conv_tc: channel strides must be multiples of 8");
+    NBE_REQUIRE((((uintptr_t)x | (uintptr_t)wq | (uintptr_t)y) & 15) == 0, "conv_tc: tensors must be 16-byte aligned");
+    NBE_REQUIRE((OW & (OW - 1)) == 0 && (OH & (OH - 1)) == 0, "conv_tc: output size must be a power of two");
+    if (N == 0) return NBE_OK;
+
+    ConvTcParams p;
+    p.y = (__nv_bfloat16*)y; p.N = N; p.OH = OH; p.OW = OW; p.Cout = Cout; p.y_cs = y_cs;
+    p.bw = OW < 128 ? OW : 128;
+    p.bh = (128 / p.bw) < OH ? (128 / p.bw) : OH;
+    p.bn = 128 / (p.bw * p.bh);
+    p.tiles_x = OW / p.bw; p.tiles_y = OH / p.bh;
+    p.K = K; p.KK = K * K;
+    const int pad = K / 2;
+    p.pad_off = valid ? 0 : -pad;
+    const int IH = valid ? OH + 2 * pad : OH, IW = valid ? OW + 2 * pad : OW;
+    const int Cin_pad = (Cin + 63) / 64 * 64;
+    p.k_chunks = Cin_pad / 64;
+    p.dcoef = dcoef; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain;
+    p.bias = bias; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.next_scale = next_scale;
+    // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), K-major A and B, N >> 3 at 17, M >> 4 at 24
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.tmem_cols = Cout <= 32 ? 32 : Cout <= 64 ? 64 : Cout <= 128 ? 128 : 256;
+
+    CUtensorMap tmap_a, tmap_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)x_cs * 2, (cuuint64_t)IW * x_cs * 2, (cuuint64_t)IH * IW * x_cs * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
+        int st = make_tmap(&tmap_a, x, 4, dims, strides, box, "activations");
+        if (st) return st;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, (cuuint64_t)Cout, (cuuint64_t)p.KK};
+        cuuint64_t strides[2] = {(cuuint64_t)Cin_pad * 2, (cuuint64_t)Cout * Cin_pad * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)Cout, 1};
+        int st = make_tmap(&tmap_b, wq, 3, dims, strides, box, "weights");
+        if (st) return st;
+    }
+    const int64_t tiles = (int64_t)p.tiles_x * p.tiles_y * ((N + p.bn - 1) / p.bn);
+    NBE_REQUIRE(tiles <= INT32_MAX, "conv_tc: too many tiles");
+    const size_t smem = 1024 + (size_t)TC_STAGES * (TC_A_BYTES + Cout * 128) + 128;
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    if (attr_err != cudaSuccess) return fail(NBE_ECUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+    conv_tc_kernel<<<(int)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, p);
+    return launched("conv_tc_kernel");
+}

@@ -1,0 +1,384 @@
+// Small / memory-bound operators of the generator forward: fully-connected layers (mapping + affines),
+// shifted noise, NCHW<->NHWC packing, the FIR-first x2 upsample feeding the tensor-core conv, the
+// fused ToRGB + triad composite, and feature blending.
+#include "common.cuh"
+
+namespace nbe {
+
+// ---------------------------------------------------------------------------------------------
+// Fully connected: one warp per output element (n, o); x row optionally 2nd-moment normalised.
+// ---------------------------------------------------------------------------------------------
+template <class XT>
+__global__ void __launch_bounds__(256)
+fc_kernel(const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y,
+          int N, int In, int Out, int64_t xs_n, int64_t ys_n, float wgain, float bgain, int act, float alpha,
+          float act_gain, int normalize) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= N * Out) return;
+    const int n = warp / Out, o = warp - n * Out;
+    const XT* xr = x + n * xs_n;
+    const float* wr = w + (int64_t)o * In;
+    float dot = 0.f, sq = 0.f;
+    for (int i = lane; i < In; i += 32) {
+        float xv = (float)xr[i];
+        dot = fmaf(xv, wr[i] * wgain, dot);
+        sq = fmaf(xv, xv, sq);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    }
+    if (lane == 0) {
+        if (normalize) dot *= rsqrtf(sq / (float)In + 1e-8f);      // x * rsqrt(mean(x^2) + eps), networks.py:24-26
+        if (b) dot += b[o] * bgain;
+        y[n * ys_n + o] = apply_act(dot, act, alpha) * act_gain;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shifted noise (grid_sample restated; op order mirrors ATen's fp32 arithmetic so that the wrap
+// discontinuity at frac == 0 falls on the same element).
+// ---------------------------------------------------------------------------------------------
+__global__ void shifted_noise_kernel(const float* __restrict__ nc, const float* __restrict__ lin,
+                                     const int64_t* __restrict__ positions, float* __restrict__ out, int N, int R, int mod) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * R * R) return;
+    const int j = idx % R, i = (idx / R) % R, n = idx / (R * R);
+    int64_t py = positions[2 * n] % mod, px = positions[2 * n + 1] % mod;
+    if (py < 0) py += mod;                                         // python % semantics
+    if (px < 0) px += mod;
+    const float p0 = __fdiv_rn((float)py, (float)(mod - 1));
+    const float p1 = __fdiv_rn((float)px, (float)(mod - 1));
+    // grid x (-> input column) comes from the output ROW i, grid y (-> input row) from the output COLUMN j
+    float sx = __fadd_rn(lin[i], p0); sx = __fsub_rn(sx, floorf(sx));
+    float sy = __fadd_rn(lin[j], p1); sy = __fsub_rn(sy, floorf(sy));
+    const float gx = __fsub_rn(__fmul_rn(sx, 2.f), 1.f), gy = __fsub_rn(__fmul_rn(sy, 2.f), 1.f);
+    const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(R - 1));
+    const float cy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(R - 1));
+    const float fx0 = floorf(cx), fy0 = floorf(cy);
+    const float tx = cx - fx0, ty = cy - fy0;
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    auto at = [&](int yy, int xx) -> float { return (yy >= 0 && yy < R && xx >= 0 && xx < R) ? nc[yy * R + xx] : 0.f; };
+    out[idx] = at(y0, x0) * (1.f - tx) * (1.f - ty) + at(y0, x1) * tx * (1.f - ty) +
+               at(y1, x0) * (1.f - tx) * ty + at(y1, x1) * tx * ty;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW f32 -> NHWC bf16 through a 32(c) x 32(pixel) shared-memory transpose; and back.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW, int dst_cs, int c_off,
+                 const float* __restrict__ scale) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        int c = c0 + r, p = p0 + tx;
+        float v = 0.f;
+        if (c < C && p < HW) {
+            v = src[((int64_t)n * C + c) * HW + p];
+            if (scale) v *= scale[(int64_t)n * C + c];
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int p = p0 + r, c = c0 + tx;
+        if (c < C && p < HW) dst[((int64_t)n * HW + p) * dst_cs + c_off + c] = __float2bfloat16_rn(tile[tx][r]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, int HW, int src_cs) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        int p = p0 + r, c = c0 + tx;
+        tile[r][tx] = (c < C && p < HW) ? __bfloat162float(src[((int64_t)n * HW + p) * src_cs + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int c = c0 + r, p = p0 + tx;
+        if (c < C && p < HW) dst[((int64_t)n * C + c) * HW + p] = tile[tx][r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FIR-first x2 upsample on NHWC bf16:  U[n, uy, ux, c] = sum over the (<=2)x(<=2) taps with even parity of
+//   g[a,b] * x[n, (uy+a-3)/2, (ux+b-3)/2, c] * scale[n,c],   g = f flipped * 4,  U is (2H+2) x (2W+2).
+// One thread = one output pixel x 8 channels (16-byte vector); consecutive threads walk the channel
+// dimension so both the loads (4 neighbouring input pixels) and the store are fully coalesced.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+upsample2x_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ f, const float* __restrict__ scale,
+                       __nv_bfloat16* __restrict__ u, int N, int H, int W, int C, int xs_c) {
+    __shared__ float s_g[16];
+    if (threadIdx.x < 16) {
+        int a = threadIdx.x >> 2, b = threadIdx.x & 3;
+        s_g[threadIdx.x] = f[(3 - a) * 4 + (3 - b)] * 4.f;          // flip_filter = False, gain = up^2
+    }
+    __syncthreads();
+    const int CV = C / 8;
+    const int UH = 2 * H + 2, UW = 2 * W + 2;
+    const int64_t total = (int64_t)N * UH * UW * CV;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        int64_t t = idx / CV;
+        const int ux = (int)(t % UW); t /= UW;
+        const int uy = (int)(t % UH);
+        const int n = (int)(t / UH);
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        // taps a with (uy + a - 3) even: a0 = (uy + 1) & 1, a0 + 2
+#pragma unroll
+        for (int da = 0; da < 2; ++da) {
+            const int a = ((uy + 1) & 1) + 2 * da;
+            const int iy = (uy + a - 3) >> 1;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int db = 0; db < 2; ++db) {
+                const int b = ((ux + 1) & 1) + 2 * db;
+                const int ix = (ux + b - 3) >> 1;
+                if (ix < 0 || ix >= W) continue;
+                const float g = s_g[a * 4 + b];
+                const int4 raw = *reinterpret_cast<const int4*>(x + (((int64_t)n * H + iy) * W + ix) * xs_c + cv * 8);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float2 v = __bfloat1622float2(h2[k]);
+                    acc[2 * k] = fmaf(g, v.x, acc[2 * k]);
+                    acc[2 * k + 1] = fmaf(g, v.y, acc[2 * k + 1]);
+                }
+            }
+        }
+        if (scale) {
+            const float4 s0 = *reinterpret_cast<const float4*>(scale + (int64_t)n * C + cv * 8);
+            const float4 s1 = *reinterpret_cast<const float4*>(scale + (int64_t)n * C + cv * 8 + 4);
+            acc[0] *= s0.x; acc[1] *= s0.y; acc[2] *= s0.z; acc[3] *= s0.w;
+            acc[4] *= s1.x; acc[5] *= s1.y; acc[6] *= s1.z; acc[7] *= s1.w;
+        }
+        int4 outv;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o2[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+        *reinterpret_cast<int4*>(u + (((int64_t)n * UH + uy) * UW + ux) * C + cv * 8) = outv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ToRGB (1x1 modconv, no demod) + bias + clamp + softmax(3) + triad colour mix.
+// NHWC bf16 input: one warp per 32 pixels?  No -- one thread per pixel would stride 256 B between lanes.
+// Instead a warp cooperates on 8 pixels at a time: 4 lanes per pixel, each lane reads 32 channels
+// (4 x 16-byte vectors, the 4 lanes of a pixel cover its 256 contiguous bytes), partial dot products are
+// combined with two shuffles.  Reads are fully coalesced; writes are per-plane NCHW rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+torgb_triad_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const float* __restrict__ w,
+                        const float* __restrict__ styles, const float* __restrict__ bias,
+                        const float* __restrict__ colors, float clamp, float* __restrict__ img, float* __restrict__ uvs,
+                        int N, int C, int HW) {
+    extern __shared__ float s_w[];                                 // [3][C] modulated weights of this image
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_w[i] = w[i] * styles[(int64_t)n * C + (i % C)];
+    __syncthreads();
+    const int sub = threadIdx.x & 3;                               // quarter of the channel range
+    const int cpl = C / 4;                                         // channels per lane
+    float col[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) col[i] = colors[n * 9 + i];
+    const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
+    for (int pix = blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2); pix < HW; pix += gridDim.x * (blockDim.x / 4)) {
+        const __nv_bfloat16* xp = x + ((int64_t)n * HW + pix) * x_cs + sub * cpl;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+        for (int c = 0; c < cpl; c += 8) {
+            const int4 raw = *reinterpret_cast<const int4*>(xp + c);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 v = __bfloat1622float2(h2[k]);
+                const int cc = sub * cpl + c + 2 * k;
+                t0 = fmaf(v.x, s_w[cc], t0);          t0 = fmaf(v.y, s_w[cc + 1], t0);
+                t1 = fmaf(v.x, s_w[C + cc], t1);      t1 = fmaf(v.y, s_w[C + cc + 1], t1);
+                t2 = fmaf(v.x, s_w[2 * C + cc], t2);  t2 = fmaf(v.y, s_w[2 * C + cc + 1], t2);
+            }
+        }
+        t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 1); t2 += __shfl_xor_sync(0xffffffffu, t2, 1);
+        t0 += __shfl_xor_sync(0xffffffffu, t0, 2); t1 += __shfl_xor_sync(0xffffffffu, t1, 2); t2 += __shfl_xor_sync(0xffffffffu, t2, 2);
+        t0 += b0; t1 += b1; t2 += b2;
+        if (clamp >= 0.f) {
+            t0 = fminf(fmaxf(t0, -clamp), clamp); t1 = fminf(fmaxf(t1, -clamp), clamp); t2 = fminf(fmaxf(t2, -clamp), clamp);
+        }
+        const float m = fmaxf(t0, fmaxf(t1, t2));
+        const float e0 = expf(t0 - m), e1 = expf(t1 - m), e2 = expf(t2 - m);
+        const float inv = 1.f / (e0 + e1 + e2);
+        const float u[3] = {e0 * inv, e1 * inv, e2 * inv};
+        if (sub < 3) {                                              // lane `sub` writes channel `sub`
+            const int64_t o = ((int64_t)n * 3 + sub) * HW + pix;
+            if (uvs) uvs[o] = u[sub];
+            if (img) img[o] = u[0] * col[sub * 3 + 0] + u[1] * col[sub * 3 + 1] + u[2] * col[sub * 3 + 2];
+        }
+    }
+}
+
+// NCHW float32 variant (FP32 mode): one thread per pixel, channel loop with coalesced plane reads.
+__global__ void __launch_bounds__(256)
+torgb_triad_nchw_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ styles,
+                        const float* __restrict__ bias, const float* __restrict__ colors, float clamp,
+                        float* __restrict__ img, float* __restrict__ uvs, int N, int C, int HW) {
+    extern __shared__ float s_w[];
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_w[i] = w[i] * styles[(int64_t)n * C + (i % C)];
+    __syncthreads();
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    const float* xp = x + (int64_t)n * C * HW + pix;
+    for (int c = 0; c < C; ++c) {
+        const float v = xp[(int64_t)c * HW];
+        t0 = fmaf(v, s_w[c], t0); t1 = fmaf(v, s_w[C + c], t1); t2 = fmaf(v, s_w[2 * C + c], t2);
+    }
+    t0 += bias[0]; t1 += bias[1]; t2 += bias[2];
+    if (clamp >= 0.f) {
+        t0 = fminf(fmaxf(t0, -clamp), clamp); t1 = fminf(fmaxf(t1, -clamp), clamp); t2 = fminf(fmaxf(t2, -clamp), clamp);
+    }
+    const float m = fmaxf(t0, fmaxf(t1, t2));
+    const float e0 = expf(t0 - m), e1 = expf(t1 - m), e2 = expf(t2 - m);
+    const float inv = 1.f / (e0 + e1 + e2);
+    const float u[3] = {e0 * inv, e1 * inv, e2 * inv};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int64_t o = ((int64_t)n * 3 + c) * HW + pix;
+        if (uvs) uvs[o] = u[c];
+        if (img) img[o] = u[0] * colors[n * 9 + c * 3 + 0] + u[1] * colors[n * 9 + c * 3 + 1] + u[2] * colors[n * 9 + c * 3 + 2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BlendedFeatures.blend: x = alpha * saved + (1 - alpha) * x
+// ---------------------------------------------------------------------------------------------
+__global__ void blend_nchw_kernel(float* __restrict__ x, const float* __restrict__ saved, const float* __restrict__ alpha,
+                                  int64_t alpha_sn, int C, int HW, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % HW);
+        const int n = (int)(i / ((int64_t)C * HW));
+        const float a = alpha[n * alpha_sn + pix];
+        x[i] = a * saved[i] + (1.f - a) * x[i];
+    }
+}
+__global__ void blend_nhwc_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ saved,
+                                  const float* __restrict__ alpha, int64_t alpha_sn, int C, int HW, int cs, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t pixn = i / C;
+        const int pix = (int)(pixn % HW);
+        const int n = (int)(pixn / HW);
+        const float a = alpha[n * alpha_sn + pix];
+        const int64_t o = pixn * cs + c;
+        x[o] = __float2bfloat16_rn(a * __bfloat162float(saved[o]) + (1.f - a) * __bfloat162float(x[o]));
+    }
+}
+
+}  // namespace nbe
+
+using namespace nbe;
+
+extern "C" int nbe_fc_f32(const void* x, int x_is_f64, const float* w, const float* b, float* y, int N, int In, int Out,
+                          int64_t xs_n, int64_t ys_n, float wgain, float bgain, int act, float alpha, float act_gain,
+                          int normalize, nbe_stream_t stream) {
+    NBE_REQUIRE(x && w && y && N >= 0 && In >= 1 && Out >= 1, "fc: bad arguments");
+    NBE_REQUIRE(act >= NBE_ACT_LINEAR && act <= NBE_ACT_SWISH, "fc: bad activation");
+    if (N == 0) return NBE_OK;
+    const int64_t threads = (int64_t)N * Out * 32;
+    const int blocks = (int)((threads + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (x_is_f64) fc_kernel<double><<<blocks, 256, 0, s>>>((const double*)x, w, b, y, N, In, Out, xs_n, ys_n, wgain, bgain, act, alpha, act_gain, normalize);
+    else          fc_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, w, b, y, N, In, Out, xs_n, ys_n, wgain, bgain, act, alpha, act_gain, normalize);
+    return launched("fc_kernel");
+}
+
+extern "C" int nbe_shifted_noise_f32(const float* noise_const, const float* lin, const int64_t* positions, float* out,
+                                     int N, int R, int mod, nbe_stream_t stream) {
+    NBE_REQUIRE(noise_const && lin && positions && out && N >= 0 && R >= 2 && mod >= 2, "shifted_noise: bad arguments");
+    if (N == 0) return NBE_OK;
+    const int total = N * R * R;
+    shifted_noise_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(noise_const, lin, positions, out, N, R, mod);
+    return launched("shifted_noise_kernel");
+}
+
+extern "C" int nbe_pack_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int dst_cs, int c_off,
+                                  const float* scale, nbe_stream_t stream) {
+    NBE_REQUIRE(src && dst && N >= 0 && C >= 1 && H >= 1 && W >= 1 && c_off >= 0 && c_off + C <= dst_cs, "pack_nhwc: bad arguments");
+    if (N == 0) return NBE_OK;
+    NBE_REQUIRE(N <= 65535, "pack_nhwc: batch too large for one launch");
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, N);
+    pack_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, H * W, dst_cs, c_off, scale);
+    return launched("pack_nhwc_kernel");
+}
+
+extern "C" int nbe_unpack_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int src_cs, nbe_stream_t stream) {
+    NBE_REQUIRE(src && dst && N >= 0 && C >= 1 && H >= 1 && W >= 1 && C <= src_cs, "unpack_nchw: bad arguments");
+    if (N == 0) return NBE_OK;
+    NBE_REQUIRE(N <= 65535, "unpack_nchw: batch too large for one launch");
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, N);
+    unpack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, C, H * W, src_cs);
+    return launched("unpack_nchw_kernel");
+}
+
+extern "C" int nbe_upsample2x_nhwc_bf16(const void* x, const float* f, const float* scale, void* u,
+                                        int N, int H, int W, int C, int xs_c, nbe_stream_t stream) {
+    NBE_REQUIRE(x && f && u && N >= 0 && H >= 1 && W >= 1 && C >= 8, "upsample2x: bad arguments");
+    NBE_REQUIRE(C % 8 == 0 && xs_c % 8 == 0 && xs_c >= C, "upsample2x: channels must be a multiple of 8");
+    NBE_REQUIRE((((uintptr_t)x | (uintptr_t)u) & 15) == 0, "upsample2x: tensors must be 16-byte aligned");
+    if (N == 0) return NBE_OK;
+    const int64_t total = (int64_t)N * (2 * H + 2) * (2 * W + 2) * (C / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+    upsample2x_nhwc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, f, scale, (__nv_bfloat16*)u, N, H, W, C, xs_c);
+    return launched("upsample2x_nhwc_kernel");
+}
+
+extern "C" int nbe_torgb_triad(const void* x, int x_is_bf16, int x_cs, const float* w, const float* styles, const float* bias,
+                               const float* colors, float clamp, float* img, float* uvs, int N, int C, int H, int W,
+                               nbe_stream_t stream) {
+    NBE_REQUIRE(x && w && styles && bias && colors && (img || uvs), "torgb_triad: null tensor");
+    NBE_REQUIRE(N >= 0 && C >= 1 && H >= 1 && W >= 1, "torgb_triad: bad shape");
+    if (N == 0) return NBE_OK;
+    NBE_REQUIRE(N <= 65535, "torgb_triad: batch too large for one launch");
+    const int HW = H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)3 * C * sizeof(float);
+    NBE_REQUIRE(smem <= 48 * 1024, "torgb_triad: too many channels");
+    if (x_is_bf16) {
+        NBE_REQUIRE(C % 32 == 0 && x_cs % 8 == 0 && x_cs >= C && ((uintptr_t)x & 15) == 0, "torgb_triad: NHWC input needs C %% 32 == 0");
+        int bx = (HW + 63) / 64;
+        if (bx > 64) bx = 64;
+        dim3 grid(bx, N);
+        torgb_triad_nhwc_kernel<<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, x_cs, w, styles, bias, colors, clamp, img, uvs, N, C, HW);
+        return launched("torgb_triad_nhwc_kernel");
+    }
+    dim3 grid((HW + 255) / 256, N);
+    torgb_triad_nchw_kernel<<<grid, 256, smem, s>>>((const float*)x, w, styles, bias, colors, clamp, img, uvs, N, C, HW);
+    return launched("torgb_triad_nchw_kernel");
+}
+
+extern "C" int nbe_blend_features(void* x, const void* saved, const float* alpha, int64_t alpha_sn, int N, int C, int H, int W,
+                                  int is_nhwc_bf16, int cs, nbe_stream_t stream) {
+    NBE_REQUIRE(x && saved && alpha && N >= 0 && C >= 1 && H >= 1 && W >= 1, "blend_features: bad arguments");
+    if (N == 0) return NBE_OK;
+    const int64_t total = (int64_t)N * C * H * W;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (is_nhwc_bf16) {
+        NBE_REQUIRE(cs >= C, "blend_features: bad channel stride");
+        blend_nhwc_kernel<<<(int)blocks, 256, 0, s>>>((__nv_bfloat16*)x, (const __nv_bfloat16*)saved, alpha, alpha_sn, C, H * W, cs, total);
+    } else {
+        blend_nchw_kernel<<<(int)blocks, 256, 0, s>>>((float*)x, (const float*)saved, alpha, alpha_sn, C, H * W, total);
+    }
+    return launched("blend_features_kernel");
+}

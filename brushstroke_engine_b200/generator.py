@@ -1,0 +1,392 @@
+"""NeuBE generator forward on B200: mapping -> modulated-conv synthesis with geometry injection -> triad ToRGB.
+
+Host-side mirror of the reference wrapper
+(thirdparty/stylegan2_ada_pytorch/training/networks_modified.py:228-400 ``Generator``,
+:28-223 ``SynthesisNetwork``; layers from training/networks.py:303-391, 416-485, 540-680):
+same call surface -- ``G(z, c, geom_feature, positions=..., noise_buffers=..., truncation_psi=...,
+return_debug_data=..., return_features=..., blended_features=..., **synthesis_kwargs)``,
+``G.forward_pre_mapped(ws, geom_feature, ...)``, ``G.mapping(z, c, ...)``, ``G.synthesis(ws, geom_feature, ...)``,
+attributes ``z_dim, c_dim, w_dim, img_resolution, img_channels, num_ws`` and the debug dict keys
+``'uvs','colors','ws','features{res}','features{res}_preblend'``.
+
+Two execution modes, selected like the reference selects precision (``force_fp32`` kwarg):
+* ``'bf16'`` (default, = the reference's mixed-fp16 default): NHWC bf16 activations, every modulated conv
+  is one tcgen05 implicit-GEMM launch (``nbe_conv_tc_bf16``) with demod/noise/bias/lrelu/clamp and the next
+  layer's modulation fused in its epilogue; up-sampling layers are FIR-first (``nbe_upsample2x_nhwc_bf16``).
+* ``'fp32'`` (``force_fp32=True``): NCHW float32 on CUDA cores (``nbe_conv2d_f32``), for <= 1e-4 parity.
+
+Forward only.  All compute is in libnbe_b200.so; torch provides memory, streams and RNG.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from . import upfirdn2d as _up
+from .conv2d_resample import conv2d_f32
+from .modconv import demod_coefs, weight_sqsum
+from .params import Bundle, GeneratorConfig
+
+SQRT2 = math.sqrt(2.0)
+ACT_LINEAR, ACT_LRELU, ACT_TANH = 1, 3, 4
+
+
+def fully_connected(x, weight, bias, activation=ACT_LINEAR, lr_multiplier=1.0, act_gain=1.0, alpha=0.0,
+                    normalize=False, out=None):
+    """``FullyConnectedLayer.forward`` (networks.py:109-122) on ``nbe_fc_f32``."""
+    _lib.require_cuda(x, 'fully_connected')
+    assert x.ndim == 2 and x.stride(1) == 1
+    N, In = x.shape
+    Out = weight.shape[0]
+    if out is None:
+        out = torch.empty((N, Out), dtype=torch.float32, device=x.device)
+    is64 = x.dtype == torch.float64
+    assert is64 or x.dtype == torch.float32
+    with torch.cuda.device(x.device):
+        _lib.call('nbe_fc_f32', _lib.ptr(x), int(is64), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(out), N, In, Out,
+                  x.stride(0), out.stride(0), float(lr_multiplier / math.sqrt(In)), float(lr_multiplier),
+                  int(activation), float(alpha), float(act_gain), int(bool(normalize)), _lib.stream())
+    return out
+
+
+class _Layer:
+    """Device-side constants of one SynthesisLayer."""
+    __slots__ = ('name', 'res', 'up', 'cin', 'cout', 'w32', 'wq', 'wsq', 'bias', 'noise_const', 'noise_strength',
+                 'affine_w', 'affine_b')
+
+
+class MappingNetwork:
+    """``MappingNetwork.forward`` (networks.py:255-290), c_dim == 0."""
+    def __init__(self, G: 'Generator'):
+        self._G = G
+        self.z_dim, self.c_dim, self.w_dim, self.num_ws = G.z_dim, 0, G.w_dim, G.num_ws
+        self.num_layers = G.cfg.mapping_layers
+
+    def __call__(self, z, c=None, truncation_psi=1, truncation_cutoff=None, skip_w_avg_update=False):
+        G = self._G
+        _lib.require_cuda(z, 'mapping')
+        assert z.ndim == 2 and z.shape[1] == self.z_dim
+        x = z if z.dtype in (torch.float32, torch.float64) else z.to(torch.float32)
+        x = x.contiguous()
+        for i in range(self.num_layers):
+            x = fully_connected(x, G._map_w[i], G._map_b[i], ACT_LRELU, G.cfg.mapping_lr_multiplier, SQRT2, 0.2,
+                                normalize=(i == 0))
+        ws = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        if truncation_psi != 1:
+            if truncation_cutoff is None:
+                ws = G._w_avg.lerp(ws, truncation_psi)
+            else:
+                ws[:, :truncation_cutoff] = G._w_avg.lerp(ws[:, :truncation_cutoff], truncation_psi)
+        return ws
+
+
+class SynthesisNetwork:
+    """``SynthesisNetwork.forward`` (networks_modified.py:123-223), architecture 'orig', colour format 'triad'."""
+    def __init__(self, G: 'Generator'):
+        self._G = G
+        self.w_dim = G.w_dim
+        self.img_resolution = G.img_resolution
+        self.img_channels = G.img_channels
+        self.block_resolutions = G.cfg.block_resolutions
+        self.num_ws = G.num_ws
+        self.geom_feature_resolutions = list(G.cfg.geom_feature_resolutions)
+        self.geom_feature_channels = list(G.cfg.geom_feature_channels)
+
+    def named_buffers(self):
+        for L in self._G._layers:
+            yield f'{L.name}.noise_const', L.noise_const
+
+    def __call__(self, ws, geom_feature, pos_encoding=None, return_debug_data=False, return_features=None,
+                 blended_features=None, noise_buffers=None, **block_kwargs):
+        return self._G._synthesis(ws, geom_feature, pos_encoding=pos_encoding, return_debug_data=return_debug_data,
+                                  return_features=return_features, blended_features=blended_features,
+                                  noise_buffers=noise_buffers, **block_kwargs)
+
+    forward = __call__
+
+
+class Generator:
+    """Drop-in for the reference ``Generator`` on the forward path (see module docstring)."""
+
+    def __init__(self, params: Bundle, cfg: GeneratorConfig = GeneratorConfig(), device='cuda', mode: str = 'bf16'):
+        assert mode in ('bf16', 'fp32')
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('Generator: a CUDA device is required (no CPU fallback on this path)')
+        _lib.load()
+        self.mode = mode
+        self.z_dim, self.c_dim, self.w_dim = cfg.z_dim, 0, cfg.w_dim
+        self.img_resolution, self.img_channels = cfg.img_resolution, cfg.img_channels
+        self.num_ws = cfg.num_ws
+        self._build(params)
+        self.mapping = MappingNetwork(self)
+        self.synthesis = SynthesisNetwork(self)
+        self._ws_cache = {}
+
+    # ------------------------------------------------------------------------------------------ plan
+    def _build(self, p: Bundle) -> None:
+        dev = self.device
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        cfg = self.cfg
+        self._map_w = [f32(p[f'mapping.fc{i}.weight']) for i in range(cfg.mapping_layers)]
+        self._map_b = [f32(p[f'mapping.fc{i}.bias']) for i in range(cfg.mapping_layers)]
+        self._w_avg = f32(p['mapping.w_avg'])
+        self._filter = _up.setup_filter([1, 3, 3, 1], device=dev)                 # networks.py:350
+        self._const = f32(p['synthesis.b4.const'])                               # [C,4,4]
+        self._const_nhwc = self._const.permute(1, 2, 0).contiguous()              # [4,4,C]
+        self._lin = {}
+        self._layers: List[_Layer] = []
+        with torch.cuda.device(dev):
+            for res in cfg.block_resolutions:
+                for conv in (['conv0'] if res > 4 else []) + ['conv1']:
+                    k = f'synthesis.b{res}.{conv}'
+                    L = _Layer()
+                    L.name, L.res, L.up = f'b{res}.{conv}', res, (2 if conv == 'conv0' else 1)
+                    L.w32 = f32(p[f'{k}.weight'])
+                    L.cout, L.cin = L.w32.shape[0], L.w32.shape[1]
+                    L.wsq = weight_sqsum(L.w32)
+                    cin_pad = (L.cin + 63) // 64 * 64
+                    L.wq = torch.empty((9, L.cout, cin_pad), dtype=torch.bfloat16, device=dev)
+                    # up layers are true convolutions (flip_weight = (up == 1), networks.py:384): pre-flip
+                    _lib.call('nbe_prepare_weights_bf16', _lib.ptr(L.w32), _lib.ptr(L.wq), L.cout, L.cin, 3,
+                              int(L.up == 2), _lib.stream())
+                    L.bias = f32(p[f'{k}.bias'])
+                    L.noise_const = f32(p[f'{k}.noise_const'])
+                    L.noise_strength = float(p[f'{k}.noise_strength'])
+                    L.affine_w = f32(p[f'{k}.affine.weight'])
+                    L.affine_b = f32(p[f'{k}.affine.bias'])
+                    self._layers.append(L)
+                self._lin[res] = torch.linspace(0, 1, res).to(dev)                # networks.py:295-299 (CPU linspace)
+            k = f'synthesis.b{cfg.img_resolution}.torgb'
+            self._rgb_w = f32(p[f'{k}.weight']).reshape(cfg.img_channels, -1)
+            self._rgb_b = f32(p[f'{k}.bias'])
+            self._rgb_color_bias = f32(p[f'{k}.color_bias'])
+            self._rgb_affine_w = f32(p[f'{k}.affine.weight'])
+            self._rgb_affine_b = f32(p[f'{k}.affine.bias'])
+        self._layer_by_name = {L.name: L for L in self._layers}
+
+    # ------------------------------------------------------------------------------------------ API
+    def __call__(self, *args, **kwargs):
+        return self.forward(*args, **kwargs)
+
+    def forward(self, z, c=None, geom_feature=None, positions=None, noise_buffers=None, truncation_psi=1,
+                truncation_cutoff=None, return_debug_data=False, return_features=None, blended_features=None,
+                style_mixing_prob=0, **synthesis_kwargs):
+        """networks_modified.py:367-400 (style mixing is training-only and rejected)."""
+        if style_mixing_prob and style_mixing_prob > 0:
+            raise RuntimeError('Generator.forward: style mixing is a training-time feature (out of scope)')
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff)
+        return self.forward_pre_mapped(ws, geom_feature, positions=positions, return_debug_data=return_debug_data,
+                                       return_features=return_features, blended_features=blended_features,
+                                       noise_buffers=noise_buffers, **synthesis_kwargs)
+
+    def forward_pre_mapped(self, ws, geom_feature, positions=None, return_debug_data=False, return_features=None,
+                           blended_features=None, noise_buffers=None, **synthesis_kwargs):
+        """networks_modified.py:346-365."""
+        res = self._synthesis(ws, geom_feature, return_debug_data=return_debug_data, return_features=return_features,
+                              blended_features=blended_features, noise_buffers=noise_buffers, positions=positions,
+                              **synthesis_kwargs)
+        if return_debug_data or return_features:
+            img, debug = res
+            if return_debug_data:
+                debug['ws'] = ws
+            return img, debug
+        return res
+
+    # ------------------------------------------------------------------------------------------ synthesis
+    def _noise_for(self, L: _Layer, B: int, noise_mode: str, positions, norm_noise_positions, input_noise):
+        """-> (noise tensor or None, batch stride in elements, gain); networks.py:365-382."""
+        if noise_mode == 'none':
+            return None, 0, 0.0
+        R = L.res
+        if noise_mode == 'random':
+            n = torch.randn([B, 1, R, R], device=self.device)                    # RNG stays in torch (same stream as the reference)
+            return n, R * R, L.noise_strength
+        assert noise_mode == 'const'
+        nc = L.noise_const if input_noise is None else input_noise.to(self.device, torch.float32).contiguous()
+        if positions is not None:
+            out = torch.empty((B, R, R), dtype=torch.float32, device=self.device)
+            pos = positions.to(self.device, torch.int64).contiguous()
+            assert pos.shape == (B, 2)
+            _lib.call('nbe_shifted_noise_f32', _lib.ptr(nc), _lib.ptr(self._lin[R]), _lib.ptr(pos), _lib.ptr(out),
+                      B, R, self.img_resolution, _lib.stream())
+            return out, R * R, L.noise_strength
+        if norm_noise_positions is not None:
+            raise RuntimeError('synthesis: pass integer `positions` (Generator.forward_pre_mapped derives '
+                               'norm_noise_positions itself, networks_modified.py:351-353)')
+        return nc, 0, L.noise_strength
+
+    def _styles(self, ws: torch.Tensor):
+        """All affine layers + demodulation coefficients up front (they depend on ws only)."""
+        styles, dcoefs = {}, {}
+        w_idx = 0
+        for res in self.cfg.block_resolutions:
+            names = ([f'b{res}.conv0'] if res > 4 else []) + [f'b{res}.conv1']
+            for j, name in enumerate(names):
+                L = self._layer_by_name[name]
+                s = fully_connected(ws[:, w_idx + j].contiguous(), L.affine_w, L.affine_b)
+                styles[name] = s
+                dcoefs[name] = demod_coefs(s, L.wsq)
+            w_idx += len(names)
+        # ToRGB: affine -> [colors(9) | styles(C)] (networks.py:455-462); w index = last conv + 1
+        scaled = fully_connected(ws[:, w_idx].contiguous(), self._rgb_affine_w, self._rgb_affine_b)
+        cin = self._rgb_w.shape[1]
+        from .bias_act import bias_act
+        colors = bias_act(scaled[:, :9].contiguous(), self._rgb_color_bias, dim=1, act='tanh').reshape(-1, 3, 3)
+        rgb_styles = (scaled[:, 9:] * (1.0 / math.sqrt(cin))).contiguous()
+        return styles, dcoefs, colors, rgb_styles
+
+    def _synthesis(self, ws, geom_feature, pos_encoding=None, return_debug_data=False, return_features=None,
+                   blended_features=None, noise_buffers=None, positions=None, noise_mode='random', force_fp32=False,
+                   fused_modconv=None, norm_noise_positions=None, **unused):
+        if pos_encoding is not None:
+            raise RuntimeError('synthesis: positional-encoding injection is not part of the style1/2 architecture')
+        _lib.require_cuda(ws, 'synthesis')
+        assert noise_mode in ('random', 'const', 'none')
+        return_features = list(return_features or [])
+        blended_features = blended_features or {}
+        noise_buffers = noise_buffers or {}
+        cfg = self.cfg
+        B = ws.shape[0]
+        assert ws.shape[1:] == (self.num_ws, self.w_dim)
+        ws = ws.to(torch.float32)
+        mode = 'fp32' if (force_fp32 or self.mode == 'fp32') else 'bf16'
+        with torch.cuda.device(self.device):
+            styles, dcoefs, colors, rgb_styles = self._styles(ws)
+            run = self._run_fp32 if mode == 'fp32' else self._run_bf16
+            img, uvs, feats = run(B, styles, dcoefs, colors, rgb_styles, geom_feature, positions, norm_noise_positions,
+                                  noise_mode, noise_buffers, return_features, blended_features)
+        debug = dict(feats)
+        if return_debug_data:
+            debug['colors'] = colors
+            debug['uvs'] = uvs
+        if len(debug) > 0:
+            return img, debug
+        return img
+
+    # ---- FP32 mode ---------------------------------------------------------------------------
+    def _run_fp32(self, B, styles, dcoefs, colors, rgb_styles, geom_feature, positions, nnp, noise_mode, noise_buffers,
+                  return_features, blended_features):
+        cfg = self.cfg
+        feats = {}
+        x = self._const.unsqueeze(0).expand(B, -1, -1, -1).contiguous()
+        geo_idx = 0
+        for res in cfg.block_resolutions:
+            for conv in (['conv0'] if res > 4 else []) + ['conv1']:
+                L = self._layer_by_name[f'b{res}.{conv}']
+                noise, nsn, ngain = self._noise_for(L, B, noise_mode, positions, nnp, noise_buffers.get(f'{L.name}.noise_const'))
+                if L.up == 2:
+                    # FIR-first form of conv2d_resample's up path: pad = 1 + (fw+up-1)//2, 1 + (fw-up)//2 = (3, 2)
+                    x = _up.upfirdn2d(x, self._filter, up=2, padding=[3, 2, 3, 2], gain=4)
+                    pad, flip = 0, True
+                else:
+                    pad, flip = 1, False
+                x = conv2d_f32(x, L.w32, padding=pad, flip=flip, xscale=styles[L.name], dcoef=dcoefs[L.name],
+                               noise=noise, noise_gain=ngain, bias=L.bias, act=ACT_LRELU, alpha=0.2, gain=SQRT2,
+                               clamp=cfg.conv_clamp if cfg.conv_clamp is not None else -1)
+            if res in return_features:
+                feats[f'features{res}_preblend'] = x
+            if res in blended_features:
+                x = self._blend_nchw(x, blended_features[res])
+            if res in return_features:
+                feats[f'features{res}'] = x
+            if res == cfg.img_resolution:
+                img, uvs = self._torgb(x, False, x.shape[1], rgb_styles, colors, B)
+            if res in cfg.geom_feature_resolutions:
+                x = torch.cat([x, geom_feature[geo_idx].to(self.device, torch.float32)], dim=1)
+                geo_idx += 1
+        return img, uvs, feats
+
+    def _blend_nchw(self, x, bf):
+        saved = bf.features.to(self.device, torch.float32).expand_as(x).contiguous()
+        alpha = bf.alpha.to(self.device, torch.float32)
+        H, W = x.shape[-2:]
+        alpha = alpha.reshape(-1, H, W).contiguous()
+        x = x.clone()
+        _lib.call('nbe_blend_features', _lib.ptr(x), _lib.ptr(saved), _lib.ptr(alpha), (H * W if alpha.shape[0] > 1 else 0),
+                  x.shape[0], x.shape[1], H, W, 0, 0, _lib.stream())
+        return x
+
+    def _torgb(self, x, is_bf16, x_cs, rgb_styles, colors, B):
+        R = self.img_resolution
+        img = torch.empty((B, 3, R, R), dtype=torch.float32, device=self.device)
+        uvs = torch.empty((B, 3, R, R), dtype=torch.float32, device=self.device)
+        clamp = self.cfg.conv_clamp if self.cfg.conv_clamp is not None else -1
+        _lib.call('nbe_torgb_triad', _lib.ptr(x), int(is_bf16), int(x_cs), _lib.ptr(self._rgb_w), _lib.ptr(rgb_styles),
+                  _lib.ptr(self._rgb_b), _lib.ptr(colors.contiguous()), float(clamp), _lib.ptr(img), _lib.ptr(uvs),
+                  B, self._rgb_w.shape[1], R, R, _lib.stream())
+        return img, uvs
+
+    # ---- BF16 tensor-core mode -----------------------------------------------------------------
+    def _conv_tc(self, x, L, B, R, x_cs, y, y_cs, valid, dcoef, noise, nsn, ngain, next_scale):
+        clamp = self.cfg.conv_clamp if self.cfg.conv_clamp is not None else -1
+        _lib.call('nbe_conv_tc_bf16', _lib.ptr(x), _lib.ptr(L.wq), _lib.ptr(y), B, R, R, L.cin, x_cs, L.cout, y_cs, 3,
+                  int(valid), _lib.ptr(dcoef), _lib.ptr(noise), nsn, float(ngain), _lib.ptr(L.bias), 0.2, SQRT2,
+                  float(clamp), _lib.ptr(next_scale), _lib.stream())
+
+    def _run_bf16(self, B, styles, dcoefs, colors, rgb_styles, geom_feature, positions, nnp, noise_mode, noise_buffers,
+                  return_features, blended_features):
+        cfg = self.cfg
+        dev = self.device
+        bf = torch.bfloat16
+        feats = {}
+        geo_idx = 0
+        x = None          # un-modulated block output, NHWC bf16, channel stride x_cs
+        x_cs = 0
+        for res in cfg.block_resolutions:
+            conv1 = self._layer_by_name[f'b{res}.conv1']
+            if res == 4:
+                # const input, modulated for b4.conv1 (tiny: B x 4 x 4 x C)
+                xin = (self._const_nhwc.unsqueeze(0) * styles[conv1.name][:, None, None, :]).to(bf).contiguous()
+            else:
+                conv0 = self._layer_by_name[f'b{res}.conv0']
+                Rin = res // 2
+                U = torch.empty((B, res + 2, res + 2, conv0.cin), dtype=bf, device=dev)
+                _lib.call('nbe_upsample2x_nhwc_bf16', _lib.ptr(x), _lib.ptr(self._filter), _lib.ptr(styles[conv0.name]),
+                          _lib.ptr(U), B, Rin, Rin, conv0.cin, x_cs, _lib.stream())
+                noise, nsn, ngain = self._noise_for(conv0, B, noise_mode, positions, nnp,
+                                                    noise_buffers.get(f'{conv0.name}.noise_const'))
+                xin = torch.empty((B, res, res, conv0.cout), dtype=bf, device=dev)
+                self._conv_tc(U, conv0, B, res, conv0.cin, xin, conv0.cout, True, dcoefs[conv0.name], noise, nsn, ngain,
+                              styles[conv1.name])
+            # conv1 writes straight into the (possibly concatenated) buffer of the next block's input
+            extra = cfg.geom_feature_channels[list(cfg.geom_feature_resolutions).index(res)] \
+                if res in cfg.geom_feature_resolutions else 0
+            y_cs = conv1.cout + extra
+            y = torch.empty((B, res, res, y_cs), dtype=bf, device=dev)
+            noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp,
+                                                noise_buffers.get(f'{conv1.name}.noise_const'))
+            self._conv_tc(xin, conv1, B, res, conv1.cin, y, y_cs, False, dcoefs[conv1.name], noise, nsn, ngain, None)
+            x, x_cs = y, y_cs
+            if res in return_features:
+                feats[f'features{res}_preblend'] = self._unpack(x, B, conv1.cout, res, x_cs)
+            if res in blended_features:
+                self._blend_nhwc(x, blended_features[res], B, conv1.cout, res, x_cs)
+            if res in return_features:
+                feats[f'features{res}'] = self._unpack(x, B, conv1.cout, res, x_cs)
+            if res == cfg.img_resolution:
+                img, uvs = self._torgb(x, True, x_cs, rgb_styles, colors, B)
+            if extra:
+                g = geom_feature[geo_idx].to(dev, torch.float32).contiguous()
+                assert g.shape == (B, extra, res, res), f'geometry feature {tuple(g.shape)} != {(B, extra, res, res)}'
+                _lib.call('nbe_pack_nhwc_bf16', _lib.ptr(g), _lib.ptr(x), B, extra, res, res, x_cs, conv1.cout, None,
+                          _lib.stream())
+                geo_idx += 1
+        return img, uvs, feats
+
+    def _unpack(self, x, B, C, R, cs):
+        out = torch.empty((B, C, R, R), dtype=torch.float32, device=self.device)
+        _lib.call('nbe_unpack_nchw_f32', _lib.ptr(x), _lib.ptr(out), B, C, R, R, cs, _lib.stream())
+        return out
+
+    def _blend_nhwc(self, x, bfeat, B, C, R, cs):
+        saved = bfeat.features.to(self.device, torch.float32).expand(B, C, R, R).contiguous()
+        saved_nhwc = torch.empty((B, R, R, cs), dtype=torch.bfloat16, device=self.device)
+        _lib.call('nbe_pack_nhwc_bf16', _lib.ptr(saved), _lib.ptr(saved_nhwc), B, C, R, R, cs, 0, None, _lib.stream())
+        alpha = bfeat.alpha.to(self.device, torch.float32).reshape(-1, R, R).contiguous()
+        _lib.call('nbe_blend_features', _lib.ptr(x), _lib.ptr(saved_nhwc), _lib.ptr(alpha), (R * R if alpha.shape[0] > 1 else 0),
+                  B, C, R, R, 1, cs, _lib.stream())

@@ -1,0 +1,189 @@
+/*
+ * nbe_b200.h -- C ABI of libnbe_b200.so, the B200 (sm_100a) implementation of the
+ * NeuBE generator-forward hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers / sizes / a
+ * cudaStream_t (as void*), launches asynchronously on that stream, never
+ * synchronises, never allocates device memory that outlives the call (the caller
+ * -- the Python shim, via torch's allocator -- owns every buffer, matching the
+ * reference where the plugin returns a torch-allocated tensor), and returns
+ * 0 on success or a negative NBE_E* code; nbe_last_error() gives the message.
+ * Nothing throws across the boundary.  There is no CPU fallback: without a
+ * CUDA device the calls return NBE_ECUDA.
+ *
+ * "Replaces" lines cite the reference interface (paths relative to
+ * /root/reference; SG2 = thirdparty/stylegan2_ada_pytorch).
+ */
+#ifndef NBE_B200_H_
+#define NBE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBE_ABI_VERSION 1
+
+typedef void* nbe_stream_t;                 /* cudaStream_t */
+
+enum nbe_status { NBE_OK = 0, NBE_EINVAL = -1, NBE_ECUDA = -2, NBE_EUNSUPPORTED = -3 };
+enum nbe_dtype  { NBE_F32 = 0, NBE_F16 = 1, NBE_BF16 = 2, NBE_F64 = 3 };
+
+/* activation indices = the reference's `cuda_idx` (SG2/torch_utils/ops/bias_act.py:23-33) */
+enum nbe_act { NBE_ACT_LINEAR = 1, NBE_ACT_RELU = 2, NBE_ACT_LRELU = 3, NBE_ACT_TANH = 4, NBE_ACT_SIGMOID = 5,
+               NBE_ACT_ELU = 6, NBE_ACT_SELU = 7, NBE_ACT_SOFTPLUS = 8, NBE_ACT_SWISH = 9 };
+
+int         nbe_abi_version(void);
+const char* nbe_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+int64_t     nbe_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * bias_act  --  y = clamp(act(x + b[(i / step_b) % size_b]) * gain, +-clamp), clamp < 0 = off.
+ * Replaces: bias_act_plugin.bias_act(x, b, xref, yref, dy, grad=0, dim, act, alpha, gain, clamp)
+ *           SG2/torch_utils/ops/bias_act.cpp:32-90, kernel bias_act.cu:23-147 (forward, grad == 0).
+ * x, y: dense, size_x elements of `dtype`; b: size_b elements of `dtype` or NULL (size_b = 0).
+ * step_b = stride (in elements) of the bias dimension, as bias_act.cpp:75. */
+int nbe_bias_act(const void* x, const void* b, void* y, int64_t size_x, int64_t size_b, int64_t step_b,
+                 int act, float alpha, float gain, float clamp, int dtype, nbe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * upfirdn2d  --  pad, zero-insert upsample, 2-D FIR, decimate (closed form in SURVEY.md appendix C.2).
+ * Replaces: upfirdn2d_plugin.upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)
+ *           SG2/torch_utils/ops/upfirdn2d.cpp:16-94, kernels upfirdn2d.cu:29-200.
+ * x: [N,C,H,W] with element strides xs_*; y: [N,C,OH,OW] with element strides ys_*, where
+ * OH = (H*upy + pady0 + pady1 - fh + downy) / downy (same for W); f: fh x fw float32, dense, on device. */
+int nbe_upfirdn2d(const void* x, const float* f, void* y,
+                  int N, int C, int H, int W, int64_t xs_n, int64_t xs_c, int64_t xs_h, int64_t xs_w,
+                  int OH, int OW, int64_t ys_n, int64_t ys_c, int64_t ys_h, int64_t ys_w,
+                  int fh, int fw, int upx, int upy, int downx, int downy,
+                  int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                  int dtype, nbe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Direct convolution, true FP32 (no TF32), NCHW -- the FP32-mode core of modulated_conv2d.
+ *   y[n,o,oy,ox] = post( dcoef[n,o] * sum_{i,kh,kw} w[o,i,kh',kw'] * (x[n,g*cin_g+i, oy*stride+kh-pad, ox*stride+kw-pad] * xscale[n,i]) )
+ * with (kh',kw') = (kh,kw) when flip == 0 (correlation, = F.conv2d) or (K-1-kh, K-1-kw) when flip == 1 (convolution);
+ * out-of-range taps read 0.  post(v) = v + noise[n? ,oy,ox] * noise_gain, then optionally the bias_act epilogue.
+ * Replaces: F.conv2d call sites SG2/torch_utils/ops/conv2d_gradfix.py:38 as used by conv2d_resample.py:29-54,144-147
+ *           and the demodulation / noise glue of SG2/training/networks.py:66-76 (un-fused order).
+ * xscale [N,Cin] / dcoef [N,Cout] / noise / bias may be NULL.  noise element (n,oy,ox) is at noise[n*noise_sn + oy*OW + ox]
+ * (noise_sn = 0 broadcasts one map).  act == 0 skips the bias_act epilogue. */
+int nbe_conv2d_f32(const float* x, const float* w, float* y,
+                   int N, int Cin, int H, int W, int Cout, int K, int pad, int stride, int groups, int flip,
+                   const float* xscale, const float* dcoef,
+                   const float* noise, int64_t noise_sn, float noise_gain,
+                   const float* bias, int act, float alpha, float gain, float clamp,
+                   nbe_stream_t stream);
+
+/* wsq[o,i] = sum_k w[o,i,k]^2   (plan-time constant for demodulation). */
+int nbe_weight_sqsum_f32(const float* w, float* wsq, int Cout, int Cin, int KK, nbe_stream_t stream);
+
+/* d[n,o] = rsqrt(sum_i styles[n,i]^2 * wsq[o,i] + 1e-8)      -- SG2/training/networks.py:59-64 */
+int nbe_demod_coefs_f32(const float* styles, const float* wsq, float* d, int N, int Cin, int Cout, nbe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fully connected layer: y[n,o] = act( sum_i x[n,i] * w[o,i] * wgain + b[o] * bgain ) * act_gain
+ * Replaces: FullyConnectedLayer.forward SG2/training/networks.py:109-122 (addmm / matmul + bias_act).
+ * x may be float64 (x_is_f64 != 0: z arrives as float64, forger/ui/brush.py:669); output float32.
+ * normalize != 0 first applies normalize_2nd_moment (networks.py:24-26) to each row of x. */
+int nbe_fc_f32(const void* x, int x_is_f64, const float* w, const float* b, float* y, int N, int In, int Out,
+               int64_t xs_n, int64_t ys_n, float wgain, float bgain, int act, float alpha, float act_gain,
+               int normalize, nbe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-patch shifted constant noise.
+ *   out[n,i,j] = bilinear(noise_const, row = frac(lin[j] + p1[n]) * (R-1), col = frac(lin[i] + p0[n]) * (R-1))
+ *   with p = float32(positions[n] % mod) / float32(mod - 1), positions int64 [N,2] = (y, x).
+ * Replaces: the grid_sample branch of SynthesisLayer.forward SG2/training/networks.py:371-382 together with
+ *           Generator.forward_pre_mapped's normalisation networks_modified.py:351-353.  lin = torch.linspace(0,1,R). */
+int nbe_shifted_noise_f32(const float* noise_const, const float* lin, const int64_t* positions, float* out,
+                          int N, int R, int mod, nbe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core (BF16, tcgen05 + TMA + TMEM) path.  Activations are NHWC bf16 with a channel stride
+ * (so geometry features can live in the same buffer: SG2/training/networks_modified.py:219 torch.cat).
+ */
+
+/* NCHW float32 -> NHWC bf16 (dst[n,h,w,c_off + c], pixel stride dst_cs elements), optional per-(n,c) scale. */
+int nbe_pack_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int dst_cs, int c_off,
+                       const float* scale, nbe_stream_t stream);
+/* NHWC bf16 (channel stride src_cs, first C channels) -> NCHW float32 */
+int nbe_unpack_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int src_cs, nbe_stream_t stream);
+
+/* U[n, 0..2H+1, 0..2W+1, c] = 4 * FIR4x4( zero-stuff( x[n,:,:,c] * scale[n,c] ) ) with padding (3,2,3,2):
+ * the up=2 branch of conv2d_resample written FIR-first (= the reference's own generic fallback,
+ * SG2/torch_utils/ops/conv2d_resample.py:149-154), so that the transposed conv becomes a *valid* 3x3
+ * convolution over U.  x: NHWC bf16 [N,H,W,C] (pixel stride xs_c), U: NHWC bf16 [N,2H+2,2W+2,C] dense.
+ * f: 4 separable taps are NOT assumed; f is the 4x4 float32 filter (setup_filter([1,3,3,1])).  scale may be NULL. */
+int nbe_upsample2x_nhwc_bf16(const void* x, const float* f, const float* scale, void* u,
+                             int N, int H, int W, int C, int xs_c, nbe_stream_t stream);
+
+
+/* wq: bf16 weights re-laid out as [K*K][Cout][Cin_pad] (tap-major, Cin_pad = Cin rounded up to 64, zero padded,
+ * already flipped if the layer is a true convolution) -- produced by nbe_prepare_weights_bf16. */
+int nbe_prepare_weights_bf16(const float* w, void* wq, int Cout, int Cin, int K, int flip, nbe_stream_t stream);
+
+/* 3x3 (or 1x1) stride-1 convolution as an implicit GEMM on tcgen05 tensor cores:
+ *   M = N*OH*OW pixels (tiles of 128), N = Cout (128), K = KK * Cin_pad; A tiles come straight from the NHWC
+ *   activation tensor through a 4-D TMA box per filter tap (out-of-bounds = zero padding), B tiles from wq,
+ *   accumulators live in TMEM, and the epilogue fuses demodulation, noise, bias, leaky-ReLU, gain, clamp and the
+ *   NEXT layer's modulation:   y = clamp(lrelu(acc * dcoef[n,o] + noise*noise_gain + bias[o]) * gain, clamp) * next_scale[n,o]
+ * x: NHWC bf16 [N, IH, IW, x_cs>=Cin]; "valid" selects IH = OH+2 (no padding, used after nbe_upsample2x) versus
+ * IH = OH with zero padding 1.  y: NHWC bf16 [N,OH,OW,y_cs] written at channel offset 0.
+ * Replaces: modulated_conv2d SG2/training/networks.py:31-88 + bias_act of SynthesisLayer.forward :386-390
+ *           (cuDNN grouped conv, K5/K6 in SURVEY.md section 2.3). */
+int nbe_conv_tc_bf16(const void* x, const void* wq, void* y,
+                     int N, int OH, int OW, int Cin, int x_cs, int Cout, int y_cs, int K, int valid,
+                     const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                     const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                     nbe_stream_t stream);
+
+/* Fused ToRGB (1x1 modulated conv, no demodulation) + bias + clamp + softmax(3) + triad colour mix.
+ *   t[k] = clamp(sum_c x[c] * w[k,c] * styles[n,c] + bias[k], +-clamp);  uvs = softmax(t);  img[c] = sum_k uvs[k]*colors[n,c,k]
+ * Replaces: ToRGBColorTriadLayer.forward SG2/training/networks.py:451-485.
+ * x: NHWC bf16 (x_is_bf16 = 1, pixel stride x_cs) or NCHW float32 (x_is_bf16 = 0); img/uvs: NCHW float32 [N,3,H,W]
+ * (either may be NULL). */
+int nbe_torgb_triad(const void* x, int x_is_bf16, int x_cs, const float* w, const float* styles, const float* bias,
+                    const float* colors, float clamp, float* img, float* uvs, int N, int C, int H, int W,
+                    nbe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Engine composite and canvas placement.
+ */
+
+/* rgba[n,:,y,x] in [0,1] from uvs [N,3,H,W] and colors01 [N,3,3] (C x ncolors):
+ *   optional UVS "clear background" remap with per-patch sfactor[n] (NULL = off), rgb = sum_k uvs_k colors_k,
+ *   alpha = U+V (mode 0, 'clear') or 1 (mode 1, 'full').
+ * Replaces: TriadGanPaintEngine._render_stroke_torch tail forger/ui/brush.py:763-792 and
+ *           StyleUVSMapper._map_style_s forger/ui/mapper.py:53-72.
+ * out_f32: [N,4,H,W] float32 or NULL.  out_u8: [N,H-2m,W-2m,4] uint8 HWC tiles, trunc(clip(255*v)) as
+ * PaintingHelper.render_stroke forger/ui/brush.py:369-377, or NULL. */
+int nbe_triad_composite(const float* uvs, const float* colors01, const float* sfactor, int mode,
+                        float* out_f32, uint8_t* out_u8, int N, int H, int W, int crop_margin, nbe_stream_t stream);
+
+/* geom[n,0,y,x] = 1 - (255 - canvas[(cy[n]+y)*canvas_w + cx[n]+x]) / 255  for 0 <= y,x < P  (float32, 0 = stroke):
+ * the crop + `255 - geom` + prepare_geom_input chain of forger/viz/paint_image_main.py:164-167 and
+ * forger/ui/brush.py:672-681.  canvas: padded guidance, uint8 [canvas_h, canvas_w], 0 = stroke. crops: int32 [N,2] = (y,x). */
+int nbe_gather_geom_patches(const uint8_t* canvas, int canvas_h, int canvas_w, const int32_t* crops, float* geom,
+                            int N, int P, nbe_stream_t stream);
+
+/* Place uint8 RGBA tiles [N,T,T,4] at (ty[n], tx[n]) into canvas [canvas_h, canvas_w, 4] with the reference's
+ * last-writer-wins raster semantics (forger/viz/paint_image_main.py:163-177): a tile pixel is written only if
+ * owner[y*canvas_w+x] == order[n] where owner is the int32 map of the highest raster index covering each pixel
+ * (computed once per canvas by nbe_tile_owner_map). */
+int nbe_tile_owner_map(const int32_t* tile_yx, int n_tiles, int T, int32_t* owner, int canvas_h, int canvas_w,
+                       nbe_stream_t stream);
+int nbe_place_tiles(const uint8_t* tiles, const int32_t* tile_yx, const int32_t* order, int N, int T,
+                    const int32_t* owner, uint8_t* canvas, int canvas_h, int canvas_w, nbe_stream_t stream);
+
+/* x = alpha * saved + (1 - alpha) * x on NCHW float32 or NHWC bf16 features (BlendedFeatures.blend,
+ * forger/train/stitching.py:24-25), alpha [H,W] shared over channels, per patch n (alpha_sn = 0 broadcasts). */
+int nbe_blend_features(void* x, const void* saved, const float* alpha, int64_t alpha_sn, int N, int C, int H, int W,
+                       int is_nhwc_bf16, int cs, nbe_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBE_B200_H_ */

@@ -1,0 +1,134 @@
+"""GPU parity of the generator forward (FP32 mode <= 1e-4; BF16 tensor-core mode <= 2e-2 and PSNR >= 40 dB on the
+[-1,1] image) against the golden outputs of the unmodified reference and against the CPU oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, t
+from oracle import neube_oracle as O
+from brushstroke_engine_b200 import params as P
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def md(a, b):
+    return float((torch.as_tensor(a).detach().cpu().double() - torch.as_tensor(b).detach().cpu().double()).abs().max())
+
+
+def psnr(a, b):
+    a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
+    mse = float(((a - b) ** 2).mean())
+    return 10 * math.log10(4.0 / max(mse, 1e-30))          # peak-to-peak 2 on the [-1, 1] image
+
+
+@pytest.fixture(scope='module')
+def G32(bundles):
+    from brushstroke_engine_b200.generator import Generator
+    cfg, ecfg, gp, ep = bundles
+    return Generator(gp, cfg, DEV, mode='fp32')
+
+
+@pytest.fixture(scope='module')
+def G16(bundles):
+    from brushstroke_engine_b200.generator import Generator
+    cfg, ecfg, gp, ep = bundles
+    return Generator(gp, cfg, DEV, mode='bf16')
+
+
+@pytest.fixture(scope='module')
+def golden_inputs(bundles):
+    cfg, ecfg, gp, ep = bundles
+    g = load_golden('generator')
+    gf = [x for x in O.geometry_encode(ep, ecfg, t(g['geom']))]
+    return g, gf
+
+
+def test_encoder_matches_golden(bundles, golden_inputs):
+    from brushstroke_engine_b200.geo_encoder import GeometryEncoder
+    cfg, ecfg, gp, ep = bundles
+    g, _ = golden_inputs
+    enc = GeometryEncoder(ep, ecfg, DEV)
+    g0, g1 = enc.encode(t(g['geom']).to(DEV))
+    assert md(g0, g['g0']) < 5e-5
+    assert md(g1[:, ::8], g['g1_sub']) < 5e-5
+    assert enc.feature_channels(0) == 16 and enc.feature_channels(1) == 256
+    assert enc.featuremap_resolution(128, 0) == 16 and enc.featuremap_resolution(128, 1) == 32
+
+
+def test_mapping_matches_golden(G32, golden_inputs):
+    g, _ = golden_inputs
+    ws = G32.mapping(t(g['z']).to(DEV), None)           # z is float64, as GanPaintEngine.random_style makes it
+    assert ws.shape == (2, 12, 64)
+    assert md(ws, g['ws']) < 1e-5
+
+
+@pytest.mark.parametrize('tag', ['nopos', 'pos'])
+def test_fp32_mode_within_1e4_of_reference(G32, golden_inputs, tag):
+    g, gf = golden_inputs
+    pos = t(g['positions']).to(DEV) if tag == 'pos' else None
+    img, dbg = G32(t(g['z']).to(DEV), None, [x.to(DEV) for x in gf], positions=pos, return_debug_data=True,
+                   return_features=[64], noise_mode='const', force_fp32=True)
+    assert img.dtype == torch.float32 and img.shape == (2, 3, 128, 128)
+    assert md(dbg['colors'], g[f'colors32_{tag}']) < 1e-5
+    assert md(dbg['features64'][:, ::16, ::2, ::2], g[f'feat64_sub_{tag}']) < 1e-4
+    assert md(dbg['uvs'], g[f'uvs32_{tag}']) < 1e-4
+    assert md(img, g[f'img32_{tag}']) < 1e-4            # north-star FP32 tolerance
+
+
+@pytest.mark.parametrize('tag', ['nopos', 'pos'])
+def test_bf16_mode_within_tolerance(G16, golden_inputs, tag):
+    g, gf = golden_inputs
+    pos = t(g['positions']).to(DEV) if tag == 'pos' else None
+    img, dbg = G16(t(g['z']).to(DEV), None, [x.to(DEV) for x in gf], positions=pos, return_debug_data=True,
+                   noise_mode='const')
+    ref = g[f'img32_{tag}']
+    assert md(img, ref) < 2e-2, md(img, ref)              # north-star BF16/TF32 tolerance
+    assert psnr(img, ref) >= 40.0, psnr(img, ref)
+    assert md(dbg['uvs'], g[f'uvs32_{tag}']) < 2e-2
+
+
+def test_shifted_noise_matches_grid_sample(G32, bundles):
+    cfg, ecfg, gp, ep = bundles
+    pos = torch.tensor([[88, 176], [1144, 264], [0, 0], [127, 127], [128, 1], [5000, 12345]])
+    npos = (pos % 128) / 127
+    for name in ('b4.conv1', 'b16.conv1', 'b128.conv0'):
+        L = G32._layer_by_name[name]
+        out, sn, gain = G32._noise_for(L, pos.shape[0], 'const', pos.to(DEV), None, None)
+        ref = O.shifted_noise(gp[f'synthesis.{name}.noise_const'], npos)[:, 0]
+        assert md(out, ref) < 1e-5, name
+
+
+def test_blending_and_feature_taps(G32, G16, golden_inputs):
+    g, gf = golden_inputs
+    z = t(g['z']).to(DEV)
+    gfd = [x.to(DEV) for x in gf]
+    _, d0 = G32(z, None, gfd, return_debug_data=True, return_features=[64], noise_mode='const')
+    saved = torch.randn(1, 128, 64, 64, generator=torch.Generator().manual_seed(3))
+    alpha = torch.rand(1, 1, 64, 64, generator=torch.Generator().manual_seed(4))
+    bf = O.BlendedFeatures(saved.to(DEV), alpha.to(DEV))
+    _, d1 = G32(z, None, gfd, return_debug_data=True, return_features=[64], blended_features={64: bf}, noise_mode='const')
+    assert md(d1['features64_preblend'], d0['features64']) < 1e-6
+    expect = alpha * saved + (1 - alpha) * d0['features64'].cpu()
+    assert md(d1['features64'], expect) < 1e-5
+    _, d2 = G16(z, None, gfd, return_debug_data=True, return_features=[64], blended_features={64: bf}, noise_mode='const')
+    assert md(d2['features64'], expect) < 0.15          # bf16 feature maps (|x| up to ~10)
+
+
+def test_noise_modes_and_errors(G16, golden_inputs):
+    g, gf = golden_inputs
+    z = t(g['z']).to(DEV)
+    gfd = [x.to(DEV) for x in gf]
+    torch.manual_seed(0)
+    a = G16(z, None, gfd, noise_mode='random')
+    torch.manual_seed(0)
+    b = G16(z, None, gfd, noise_mode='random')
+    assert md(a, b) == 0                                # RNG drawn in torch -> reproducible
+    c = G16(z, None, gfd, noise_mode='none')
+    assert c.shape == (2, 3, 128, 128)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        G16.mapping(t(g['z']), None)
+    with pytest.raises(RuntimeError):
+        G16(z, None, gfd, style_mixing_prob=0.9)

@@ -1,0 +1,110 @@
+"""CPU: the oracle restatement against fixtures produced by the unmodified reference
+(oracle/make_golden.py).  No GPU, no /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, t
+from oracle import neube_oracle as O
+from brushstroke_engine_b200 import params as P
+
+
+def md(a, b):
+    return float((torch.as_tensor(a).double() - torch.as_tensor(b).double()).abs().max())
+
+
+def test_bias_act_all_activations():
+    g = load_golden('bias_act')
+    x, b = t(g['x']), t(g['b'])
+    for act in O.ACTIVATIONS:
+        for tag, clamp in (('n', None), ('c', 0.7)):
+            assert md(O.bias_act(x, b, dim=1, act=act, clamp=clamp), g[f'y_{act}_{tag}']) < 1e-6, (act, tag)
+    assert md(O.bias_act(x, b, dim=1, act='lrelu', alpha=0.1, gain=2.5, clamp=4.0), g['y_lrelu_custom']) < 1e-6
+    assert md(O.bias_act(t(g['x2']), t(g['b2']), dim=1, act='tanh'), g['y2_tanh']) < 1e-6
+
+
+UPFIRDN_CASES = {
+    'gen':   dict(f='f4', up=1, down=1, padding=[1, 1, 1, 1], flip_filter=False, gain=4.0),
+    'up2':   dict(f='f4', up=2, down=1, padding=[2, 1, 2, 1], flip_filter=False, gain=4.0),
+    'down2': dict(f='f4', up=1, down=2, padding=[1, 1, 1, 1], flip_filter=False, gain=1.0),
+    'asym':  dict(f='fa', up=[3, 2], down=[2, 1], padding=[2, -1, 0, 3], flip_filter=True, gain=1.5),
+    'neg':   dict(f='fa', up=1, down=1, padding=[-1, 2, -2, 3], flip_filter=False, gain=1.0),
+    'sep':   dict(f='f1', up=2, down=1, padding=[4, 3, 4, 3], flip_filter=False, gain=4.0),
+    'none':  dict(f=None, up=2, down=1, padding=0, flip_filter=False, gain=1.0),
+}
+
+
+def test_upfirdn2d_cases():
+    g = load_golden('upfirdn2d')
+    x = t(g['x'])
+    assert md(O.setup_filter([1, 3, 3, 1]), g['f4']) == 0
+    for name, kw in UPFIRDN_CASES.items():
+        kw = dict(kw)
+        f = kw.pop('f')
+        y = O.upfirdn2d(x, None if f is None else t(g[f]), **kw)
+        assert y.shape == g[f'y_{name}'].shape, name
+        assert md(y, g[f'y_{name}']) < 2e-6, name
+    f4 = t(g['f4'])
+    assert md(O.upfirdn2d(t(g['xg']), f4, padding=[1, 1, 1, 1], gain=4.0), g['yg']) < 2e-6
+    assert md(O.upsample2d(x, f4), g['y_upsample2d']) < 2e-6
+    assert md(O.downsample2d(x, f4), g['y_downsample2d']) < 2e-6
+    assert md(O.filter2d(x, f4), g['y_filter2d']) < 2e-6
+
+
+def test_modulated_conv2d():
+    g = load_golden('modconv')
+    f4 = O.setup_filter([1, 3, 3, 1])
+    for name, up in (('up1', 1), ('up2', 2), ('up2_odd', 2)):
+        x, w, s, n = (t(g[f'{name}_{k}']) for k in 'xwsn')
+        y = O.conv2d_resample(x, w, f=(f4 if up > 1 else None), up=up, padding=1, flip_weight=(up == 1))
+        assert md(y, g[f'{name}_conv']) < 2e-5, name
+        for demod in (True, False):
+            y = O.modulated_conv2d(x, w, s, noise=n, up=up, padding=1, resample_filter=f4, demodulate=demod,
+                                   flip_weight=(up == 1))
+            assert md(y, g[f'{name}_mod_d{int(demod)}']) < 5e-5, (name, demod)
+
+
+def test_generator_and_encoder(bundles):
+    cfg, ecfg, gp, ep = bundles
+    g = load_golden('generator')
+    z, geom, pos = t(g['z']), t(g['geom']), t(g['positions'])
+    gf = O.geometry_encode(ep, ecfg, geom)
+    assert md(gf[0], g['g0']) < 2e-5
+    assert md(gf[1][:, ::8], g['g1_sub']) < 2e-5
+    for tag, positions in (('nopos', None), ('pos', pos)):
+        img, dbg = O.generator_forward(gp, cfg, z, gf, positions=positions, return_features=[64])
+        assert md(dbg['ws'], g['ws']) < 1e-5
+        assert md(img, g[f'img32_{tag}']) < 1e-4
+        assert md(dbg['uvs'], g[f'uvs32_{tag}']) < 1e-4
+        assert md(dbg['colors'], g[f'colors32_{tag}']) < 1e-5
+        assert md(dbg['features64'][:, ::16, ::2, ::2], g[f'feat64_sub_{tag}']) < 1e-4
+        # the reference's own mixed-fp16 output stays within the BF16-mode tolerance of the fp32 oracle
+        assert md(img, g[f'img16_{tag}'].astype(np.float32)) < 2e-2
+    npos = (pos % 128) / 127
+    nc = gp['synthesis.b16.conv1.noise_const']
+    assert md(O.shifted_noise(nc, npos), g['noise16_pos']) < 1e-6
+    assert md(O.shifted_noise_closed_form(nc, npos), g['noise16_pos']) < 1e-5
+
+
+def test_stylizer_engine(bundles):
+    cfg, ecfg, gp, ep = bundles
+    g = load_golden('engine')
+    guidance = g['guidance']
+    z = P.style_z_from_seed(594)
+    for level, mode in ((0, 'clear'), (0, 'full'), (2, 'clear')):
+        canvas, crops, metas = O.stylize(gp, ep, cfg, ecfg, guidance, z, 10, 'all', mode, level)
+        assert np.array_equal(np.array(crops, dtype=np.int32), g['crops'])          # bit-exact patch indexing
+        assert np.array_equal(np.array(metas, dtype=np.int32), g['metas'])          # bit-exact tile placement
+        diff = np.abs(canvas.astype(np.int32) - g[f'canvas_l{level}_{mode}'].astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (level, mode, diff.max())
+    sf = O.uvs_sfactor  # noqa: F841  (exercised through map_style_s below)
+    mapped = O.map_style_s(torch.tensor(float(g['sfactor'])), t(g['uvs5_sub']))
+    assert md(mapped, g['mapped5_sub']) < 1e-6
+
+
+def test_crop_grid_sizes():
+    """2000^2 -> 529 crops / 2152^2 canvas; 4096^2 -> 2209 crops / 4264^2."""
+    for size, ncrops, canvas in ((2000, 529, 2152), (4096, 2209, 4264)):
+        geo = O.pad_geo(np.full((size, size, 1), 255, np.uint8), 10)
+        crops, padded = O.generate_stitching_crops(geo, 128, 'all', 20)
+        assert len(crops) == ncrops and padded.shape[:2] == (canvas, canvas)
