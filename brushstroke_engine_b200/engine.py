@@ -1,0 +1,269 @@
+"""Triad paint engine on B200: geometry -> encoder -> generator -> triband alpha/colour composite.
+
+Host-side mirror of ``TriadGanPaintEngine`` / ``GanBrushOptions`` / ``StyleUVSMapper``
+(forger/ui/brush.py:410-527, 607-805; forger/ui/mapper.py:16-135):
+
+* ``engine._render_stroke_torch(geom, canvas, opts, **generator_kwargs) -> (result[B,4,W,W], raw, debug_img)``
+  with the same argument meaning (geom: float [B,1,W,W], 0 = stroke) and the same ``raw`` dict keys;
+* ``engine.render_tiles(...)`` is the batched form of the tail of ``PaintingHelper.render_stroke``
+  (brush.py:369-377): crop the margin, x255, clip, truncate to uint8, HWC -- done inside the composite kernel;
+* ``GanBrushOptions`` keeps the reference attribute names (style_z, style_ws, color0, color1, canvas_color,
+  position, enable_uvs_mapping, custom_args) so caller code reads the same.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import synthetic
+from .generator import Generator
+from .geo_encoder import GeometryEncoder
+from .params import Bundle, EncoderConfig, GeneratorConfig, style_z_from_seed
+
+RENDER_MODES = {'clear': 0, 'full': 1}
+
+
+class GanBrushOptions:
+    """forger/ui/brush.py:410-527."""
+    def __init__(self, primary_color=None, secondary_color=None, debug=False):
+        self.color0 = primary_color
+        self.color1 = secondary_color
+        self.canvas_color = None
+        self.style_z = None
+        self.style_id = None
+        self.library_id = ''
+        self.style_ws = None
+        self.opacity = 1.0
+        self.debug = debug
+        self.position = None          # [B, 2] int64 (y, x)
+        self.custom_args = {}
+        self.enable_uvs_mapping = False
+
+    def to(self, device):
+        if self.style_z is not None:
+            self.style_z = self.style_z.to(device)
+        if self.style_ws is not None:
+            self.style_ws = self.style_ws.to(device)
+        if 'noise_buffers' in self.custom_args:
+            for k, v in self.custom_args['noise_buffers'].items():
+                if not torch.is_tensor(v):
+                    v = torch.from_numpy(v)
+                self.custom_args['noise_buffers'][k] = v.to(device)
+        return self
+
+    def set_position(self, x, y):
+        if type(x) is int:
+            self.position = torch.tensor([y, x], dtype=torch.int64).unsqueeze(0)
+        else:
+            self.position = torch.stack([y, x], dim=1)
+
+    def get_position(self, device):
+        return None if self.position is None else self.position.to(device)
+
+    def set_color(self, color_idx, in_color):
+        def prep(x):
+            if x is None:
+                return None
+            color = x if torch.is_tensor(x) else torch.from_numpy(np.asarray(x))
+            color = color.to(torch.float32) / 255 if color.dtype == torch.uint8 else color.to(torch.float32)
+            return color.unsqueeze(0) if color.ndim == 1 else color
+        if color_idx == 0:
+            self.color0 = prep(in_color)
+        elif color_idx == 1:
+            self.color1 = prep(in_color)
+        elif color_idx == 2:
+            self.canvas_color = prep(in_color)
+        else:
+            raise ValueError(f'Wrong color idx {color_idx}')
+
+    def set_style(self, style_z, style_id=None):
+        self.style_z, self.style_id, self.style_ws = style_z, style_id, None
+
+    def set_style_w(self, style_w, style_id=None, custom_args=None):
+        self.style_ws, self.style_id, self.style_z = style_w, style_id, None
+        self.custom_args = custom_args if custom_args is not None else {}
+
+    def prepare_style(self, batch_size, device):
+        def prep(x):
+            if x is None:
+                return None
+            if x.shape[0] != batch_size:
+                assert x.shape[0] == 1, 'Brush options must either have correct style batch, or batch of 1'
+                return x.expand(batch_size, *([-1] * (x.ndim - 1))).to(device)
+            return x.to(device)
+        self.style_z = prep(self.style_z)
+        self.style_ws = prep(self.style_ws)
+
+    def prepare_colors(self, default_colors):
+        """[B,3,ncolors] in [0,1]; user colours override columns (brush.py:514-527)."""
+        out = default_colors.clone()
+        for idx, col in enumerate((self.color0, self.color1, self.canvas_color)):
+            if col is not None:
+                out[:, :, idx] = col.to(out.device)
+        return out
+
+
+class StyleUVSMapper:
+    """"Clear background" UVS mapping (forger/ui/mapper.py:16-135).  The reference measures the background S level on
+    five bundled 128^2 spline patches; without the reference's image folder the same measurement runs on five
+    synthetic cross/stroke patches, or on whatever ``set_geometry`` is given."""
+    def __init__(self, engine: 'TriadPaintEngine'):
+        self.engine = engine
+        self.sfactors: Dict[object, torch.Tensor] = {}
+        self.geom_feature = None
+        self.bmask = None
+        self.fmask = None
+
+    def set_geometry(self, geo_med: torch.Tensor, geo_thick: torch.Tensor):
+        """geo_*: [5,1,W,W] float in [0,1], 0 = stroke (medium / thick renderings of the same strokes)."""
+        dev = self.engine.device
+        geo_med, geo_thick = geo_med.to(dev, torch.float32), geo_thick.to(dev, torch.float32)
+        self.geom_feature = self.engine.encoder.encode(geo_med)
+        self.fmask = geo_med < 0.01
+        self.bmask = geo_thick > 0.99
+        self.sfactors = {}
+
+    def _init_geometry(self):
+        W = self.engine.patch_width
+        med = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(W, seed=10 + i, radius=8) for i in range(5)]))
+        thick = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(W, seed=10 + i, radius=12) for i in range(5)]))
+        self.set_geometry(med, thick)
+
+    def _render(self, brush_opts, geo_feature):
+        G = self.engine.G
+        n = geo_feature[0].shape[0]
+        if brush_opts.style_ws is not None:
+            ws = brush_opts.style_ws.expand(n, -1, -1).to(self.engine.device)
+            return G.synthesis(ws, geom_feature=geo_feature, noise_mode='const', return_debug_data=True)
+        z = brush_opts.style_z.expand(n, -1).to(self.engine.device)
+        return G(z=z, c=None, geom_feature=geo_feature, noise_mode='const', return_debug_data=True)
+
+    def get_colors_raw(self, brush_opts):
+        if self.geom_feature is None:
+            self._init_geometry()
+        _, raw = self._render(brush_opts, [x[:1] for x in self.geom_feature])
+        return raw['colors']
+
+    def get_sfactor(self, brush_opts):
+        """1 / min_i min(topk15(S_i[background_i])) (mapper.py:117-135); cached per style_id."""
+        style_id = brush_opts.style_id
+        if style_id is not None and style_id in self.sfactors:
+            return self.sfactors[style_id]
+        if self.geom_feature is None:
+            self._init_geometry()
+        _, raw = self._render(brush_opts, self.geom_feature)
+        S = raw['uvs'][:, 2:3]
+        val = torch.stack([torch.topk(S[i][self.bmask[i]], k=15)[0].min() for i in range(S.shape[0])]).min()
+        sfactor = 1 / val
+        if style_id is not None:
+            self.sfactors[style_id] = sfactor
+        return sfactor
+
+
+class TriadPaintEngine:
+    """forger/ui/brush.py:607-805 (``GanPaintEngine`` + ``TriadGanPaintEngine``) built from parameter bundles."""
+
+    def __init__(self, gen_params: Bundle, enc_params: Bundle, device='cuda', mode: str = 'bf16',
+                 gen_cfg: GeneratorConfig = GeneratorConfig(), enc_cfg: EncoderConfig = EncoderConfig()):
+        self.device = torch.device(device)
+        self.G = Generator(gen_params, gen_cfg, self.device, mode=mode)
+        self.encoder = GeometryEncoder(enc_params, enc_cfg, self.device)
+        self.patch_width = self.G.img_resolution
+        self.render_modes = set(RENDER_MODES)
+        self.render_mode = 'clear'
+        self.style_c = None
+        self.uvs_mapper = StyleUVSMapper(self)
+
+    def set_render_mode(self, mode):
+        if mode not in self.render_modes:
+            raise RuntimeError(f'Render mode should be one of {self.render_modes}')
+        self.render_mode = mode
+
+    def random_style(self, seed):
+        return style_z_from_seed(seed, self.G.z_dim).to(self.device)
+
+    def prepare_geom_input(self, stroke_patch: np.ndarray) -> torch.Tensor:
+        """[W,W,C] uint8 (last channel: 255 = stroke) -> [1,1,W,W] float32, 0 = stroke (brush.py:672-681)."""
+        g = torch.from_numpy(np.ascontiguousarray(stroke_patch[:, :, -1])).to(self.device)
+        return (1 - g.to(torch.float32) / 255.0)[None, None]
+
+    # ------------------------------------------------------------------------------------------------
+    def _generate(self, geom, opts, **generator_kwargs):
+        geom_feature = self.encoder.encode(geom)
+        opts.to(self.device)
+        B = geom.shape[0]
+        opts.prepare_style(B, self.device)
+        if opts.style_ws is not None:
+            return self.G.forward_pre_mapped(ws=opts.style_ws, positions=opts.get_position(self.device),
+                                             geom_feature=geom_feature, return_debug_data=True, noise_mode='const',
+                                             **opts.custom_args, **generator_kwargs)
+        return self.G(z=opts.style_z, c=self.style_c, positions=opts.get_position(self.device),
+                      geom_feature=geom_feature, return_debug_data=True, noise_mode='const', **generator_kwargs)
+
+    def _composite(self, triad_data, opts, B, want_f32=True, crop_margin=None):
+        uvs = triad_data['uvs'].contiguous()
+        default_colors = (triad_data['colors'] + 1) / 2.0
+        sfactor = None
+        if opts.enable_uvs_mapping:
+            sf = self.uvs_mapper.get_sfactor(opts)
+            sfactor = sf.reshape(-1).to(self.device, torch.float32).expand(B).contiguous()
+        colors = opts.prepare_colors(default_colors).contiguous()
+        W = self.patch_width
+        out_f32 = torch.empty((B, 4, W, W), dtype=torch.float32, device=self.device) if want_f32 else None
+        out_u8 = None
+        m = 0
+        if crop_margin is not None:
+            m = int(crop_margin)
+            out_u8 = torch.empty((B, W - 2 * m, W - 2 * m, 4), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call('nbe_triad_composite', _lib.ptr(uvs), _lib.ptr(colors), _lib.ptr(sfactor), RENDER_MODES[self.render_mode],
+                      _lib.ptr(out_f32), _lib.ptr(out_u8), B, W, W, m, _lib.stream())
+        return out_f32, out_u8
+
+    def _render_stroke_torch(self, geom, canvas, opts, **generator_kwargs):
+        """-> (result [B,4,W,W] float in [0,1] (straight RGBA), raw net output dict, None)."""
+        _lib.require_cuda(geom, '_render_stroke_torch')
+        result_img, triad_data = self._generate(geom, opts, **generator_kwargs)
+        out_f32, _ = self._composite(triad_data, opts, geom.shape[0], want_f32=True)
+        return out_f32, triad_data, None
+
+    def render_tiles(self, geom, opts, crop_margin=0, **generator_kwargs):
+        """Batched tail of ``PaintingHelper.render_stroke``: -> (uint8 tiles [B,W-2m,W-2m,4] on device, raw)."""
+        _lib.require_cuda(geom, 'render_tiles')
+        result_img, triad_data = self._generate(geom, opts, **generator_kwargs)
+        _, out_u8 = self._composite(triad_data, opts, geom.shape[0], want_f32=False, crop_margin=crop_margin)
+        return out_u8, triad_data
+
+    def render_stroke(self, stroke_patch, canvas_patch, opts, **generator_kwargs):
+        """[W,W,C] uint8 stroke patch -> ([W,W,4] uint8, None) (brush.py:683-701)."""
+        geom = self.prepare_geom_input(stroke_patch)
+        tiles, _ = self.render_tiles(geom, opts, crop_margin=0, **generator_kwargs)
+        return np.ascontiguousarray(tiles[0].cpu().numpy()), None
+
+    def render_patches_host(self, guidance_patches: torch.Tensor, z: torch.Tensor, positions: torch.Tensor,
+                            crop_margin: int = 10, out: Optional[torch.Tensor] = None, **generator_kwargs) -> torch.Tensor:
+        """End-to-end batched entry point with HOST buffers (the stylizer's per-batch work):
+        guidance_patches [B,W,W] uint8 (0 = stroke, as sliced from the padded guidance image), z [B,z_dim] float64,
+        positions [B,2] int64 (y, x) -- all on the host (pinned for async copies) -> uint8 tiles [B,W-2m,W-2m,4] on the host."""
+        B, W = guidance_patches.shape[0], self.patch_width
+        assert guidance_patches.dtype == torch.uint8 and guidance_patches.shape == (B, W, W)
+        dev = self.device
+        d_patches = guidance_patches.to(dev, non_blocking=True)
+        d_z = z.to(dev, non_blocking=True)
+        d_pos = positions.to(dev, non_blocking=True)
+        crops = torch.stack([torch.arange(B, dtype=torch.int32, device=dev) * W, torch.zeros(B, dtype=torch.int32, device=dev)], dim=1).contiguous()
+        geom = torch.empty((B, 1, W, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call('nbe_gather_geom_patches', _lib.ptr(d_patches), B * W, W, _lib.ptr(crops), _lib.ptr(geom), B, W, _lib.stream())
+        opts = GanBrushOptions()
+        opts.set_style(d_z)
+        opts.position = d_pos
+        tiles, _ = self.render_tiles(geom, opts, crop_margin=crop_margin, **generator_kwargs)
+        if out is None:
+            out = torch.empty(tiles.shape, dtype=torch.uint8, pin_memory=True)
+        out.copy_(tiles, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out

@@ -125,7 +125,7 @@ class Generator:
         self._build(params)
         self.mapping = MappingNetwork(self)
         self.synthesis = SynthesisNetwork(self)
-        self._ws_cache = {}
+        self.probe = None       # optional {layer_name: [(start_event, end_event), ...]} filled by _conv_tc (bench.py roofline)
 
     # ------------------------------------------------------------------------------------------ plan
     def _build(self, p: Bundle) -> None:
@@ -324,9 +324,16 @@ class Generator:
     # ---- BF16 tensor-core mode -----------------------------------------------------------------
     def _conv_tc(self, x, L, B, R, x_cs, y, y_cs, valid, dcoef, noise, nsn, ngain, next_scale):
         clamp = self.cfg.conv_clamp if self.cfg.conv_clamp is not None else -1
+        ev = None
+        if self.probe is not None and L.name in self.probe:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         _lib.call('nbe_conv_tc_bf16', _lib.ptr(x), _lib.ptr(L.wq), _lib.ptr(y), B, R, R, L.cin, x_cs, L.cout, y_cs, 3,
                   int(valid), _lib.ptr(dcoef), _lib.ptr(noise), nsn, float(ngain), _lib.ptr(L.bias), 0.2, SQRT2,
                   float(clamp), _lib.ptr(next_scale), _lib.stream())
+        if ev is not None:
+            ev[1].record()
+            self.probe[L.name].append(ev)
 
     def _run_bf16(self, B, styles, dcoefs, colors, rgb_styles, geom_feature, positions, nnp, noise_mode, noise_buffers,
                   return_features, blended_features):

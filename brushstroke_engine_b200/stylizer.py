@@ -1,0 +1,261 @@
+"""Patch scheduler: the batched, multi-GPU replacement for the per-patch loop of
+forger/viz/paint_image_main.py:145-186 (+ forger/viz/style_transfer.py:15-48).
+
+Semantics kept bit-exact (integer work): crop list, padded canvas size, ``meta`` offsets ``(y+m, x+m)``,
+last-writer-wins tile placement in raster order, final crop back to the input size, ``on_white`` composite.
+
+Execution on B200:
+* the padded guidance image lives on the device once (uint8); each batch of crops is gathered straight into
+  the encoder's float input (``nbe_gather_geom_patches`` = crop + ``255 - g`` + ``prepare_geom_input``);
+* patches of a batch go through encoder -> generator -> composite as ONE batched launch sequence
+  (``TriadPaintEngine.render_tiles``), per-patch ``positions`` = crop (y, x) exactly as the loop sets them;
+* tiles are written into a device canvas under an ownership map (``nbe_tile_owner_map`` / ``nbe_place_tiles``),
+  so overlapping tiles of one batch resolve to "highest raster index wins" without ordering the launches;
+* across GPUs, contiguous bands of crop rows go to ranks (patches are independent when
+  ``feature_blending_level == 0``); the only inter-GPU traffic is one gather of finished uint8 tiles to rank 0.
+
+``feature_blending_level > 0`` makes patch n read features written by raster-earlier neighbours
+(forger/ui/brush.py:190-242); it is executed in raster order with the reference's exact mask arithmetic
+(single GPU), see ``_stylize_blended``.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import GanBrushOptions, TriadPaintEngine
+
+
+# ------------------------------------------------------------------------------------------------ integer host logic
+def pad_geo(geo: np.ndarray, crop_margin: int) -> np.ndarray:
+    """paint_image_main.py:59-62."""
+    out = np.full((geo.shape[0] + crop_margin, geo.shape[1] + crop_margin, geo.shape[2]), 255, dtype=np.uint8)
+    out[crop_margin:, crop_margin:, :] = geo
+    return out
+
+
+def generate_stitching_crops(stroke_image: np.ndarray, patch_width: int, mode: str = 'all', overlap_margin: int = 15):
+    """style_transfer.py:15-48 -> (list of (y, x, w, w), padded image)."""
+    rwidth = patch_width - overlap_margin * 2
+    img_height, img_width, nchannels = stroke_image.shape
+    assert nchannels in [1, 2, 3, 4], f'Wrong shape {stroke_image.shape}'
+    nrows = img_height // rwidth + 1
+    ncols = img_width // rwidth + 1
+    padded = np.full((nrows * rwidth + patch_width, ncols * rwidth + patch_width, nchannels), 255, dtype=np.uint8)
+    padded[0:img_height, 0:img_width, ...] = stroke_image
+    if mode == 'all':
+        ys, xs = np.meshgrid(np.arange(nrows) * rwidth, np.arange(ncols) * rwidth, indexing='ij')
+        crops = [(int(y), int(x), patch_width, patch_width) for y, x in zip(ys.ravel(), xs.ravel())]
+    else:
+        crops = []
+        for r in range(nrows):
+            for c in range(ncols):
+                y, x = r * rwidth, c * rwidth
+                if np.sum(padded[y:y + patch_width, x:x + patch_width, ...] < 0.001) > 10:
+                    crops.append((y, x, patch_width, patch_width))
+    return crops, padded
+
+
+def shard_crops(crops: Sequence[Tuple[int, int, int, int]], world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous bands of crop *rows* per rank: -> [start, end) indices into ``crops``.
+    Rows are split as evenly as possible, earlier ranks take the extra rows (47 rows / 8 -> 6,6,6,6,6,6,6,5)."""
+    row_ys = sorted({c[0] for c in crops})
+    nrows = len(row_ys)
+    base, extra = divmod(nrows, world_size)
+    r0 = rank * base + min(rank, extra)
+    r1 = r0 + base + (1 if rank < extra else 0)
+    if r0 >= nrows:
+        return len(crops), len(crops)
+    ys = [c[0] for c in crops]
+    start = ys.index(row_ys[r0])
+    end = len(crops) if r1 >= nrows else ys.index(row_ys[r1])
+    return start, end
+
+
+def composite_on_white(result: np.ndarray) -> np.ndarray:
+    """paint_image_main.py:179-183."""
+    alpha = result[..., 3:].astype(np.float32) / 255
+    out = result[..., :3].astype(np.float32) * alpha + 255 * (1 - alpha)
+    return out.clip(0, 255).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------ device-side scheduler
+class CanvasJob:
+    """One stylization of one guidance image on one rank."""
+
+    def __init__(self, engine: TriadPaintEngine, guidance: np.ndarray, crop_margin: int = 10, stitching_mode: str = 'all'):
+        assert guidance.ndim == 3 and guidance.dtype == np.uint8
+        self.engine = engine
+        self.crop_margin = int(crop_margin)
+        self.patch = engine.patch_width
+        self.orig_shape = guidance.shape
+        geom = pad_geo(guidance[:, :, -1:], self.crop_margin)
+        self.crops, self.geom = generate_stitching_crops(geom, self.patch, mode=stitching_mode,
+                                                         overlap_margin=self.crop_margin * 2)
+        self.canvas_h, self.canvas_w = self.geom.shape[:2]
+        self.tile = self.patch - 2 * self.crop_margin
+        dev = engine.device
+        self.d_geom = torch.from_numpy(np.ascontiguousarray(self.geom[:, :, 0])).to(dev)
+        self.crops_yx = np.array([(c[0], c[1]) for c in self.crops], dtype=np.int32).reshape(-1, 2)
+        self.d_crops = torch.from_numpy(self.crops_yx).to(dev)
+        self.tiles_yx = self.crops_yx + self.crop_margin                 # meta: (y + m, x + m)  (brush.py:365-373)
+        self.d_tiles_yx = torch.from_numpy(self.tiles_yx).to(dev)
+
+    def gather(self, start: int, end: int) -> torch.Tensor:
+        n = end - start
+        out = torch.empty((n, 1, self.patch, self.patch), dtype=torch.float32, device=self.engine.device)
+        _lib.call('nbe_gather_geom_patches', _lib.ptr(self.d_geom), self.canvas_h, self.canvas_w,
+                  _lib.ptr(self.d_crops[start:end]), _lib.ptr(out), n, self.patch, _lib.stream())
+        return out
+
+    def owner_map(self) -> torch.Tensor:
+        owner = torch.empty((self.canvas_h, self.canvas_w), dtype=torch.int32, device=self.engine.device)
+        _lib.call('nbe_tile_owner_map', _lib.ptr(self.d_tiles_yx), len(self.crops), self.tile, _lib.ptr(owner),
+                  self.canvas_h, self.canvas_w, _lib.stream())
+        return owner
+
+    def place(self, canvas: torch.Tensor, owner: torch.Tensor, tiles: torch.Tensor, start: int, end: int):
+        order = torch.arange(start, end, dtype=torch.int32, device=self.engine.device)
+        _lib.call('nbe_place_tiles', _lib.ptr(tiles), _lib.ptr(self.d_tiles_yx[start:end]), _lib.ptr(order), end - start,
+                  self.tile, _lib.ptr(owner), _lib.ptr(canvas), self.canvas_h, self.canvas_w, _lib.stream())
+
+    def finish(self, canvas: torch.Tensor, on_white: bool) -> np.ndarray:
+        result = canvas.cpu().numpy()
+        if on_white:
+            result = composite_on_white(result)
+        m = self.crop_margin
+        return result[m:m + self.orig_shape[0], m:m + self.orig_shape[1], :]
+
+
+def _batch_opts(base: GanBrushOptions, z_per_patch: Optional[torch.Tensor], start: int, end: int, positions: torch.Tensor):
+    o = GanBrushOptions()
+    o.__dict__.update(base.__dict__)
+    if z_per_patch is not None:
+        o.style_z, o.style_ws = z_per_patch[start:end], None
+    o.position = positions
+    return o
+
+
+def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOptions, crop_margin: int = 10,
+            stitching_mode: str = 'all', feature_blending_level: int = 0, batch_size: int = 256, on_white: bool = False,
+            z_per_patch: Optional[torch.Tensor] = None, group=None, return_job: bool = False):
+    """Stylize a whole guidance drawing.  guidance: [H,W,C] uint8 (last channel, 0 = stroke).
+
+    With an initialised ``torch.distributed`` process group (one process per GPU) the crop rows are sharded across
+    ranks and rank 0 returns the finished canvas (other ranks return None).  ``z_per_patch`` ([n_crops, z_dim])
+    gives every patch its own style (style interpolation across the canvas, BASELINE config 5)."""
+    import torch.distributed as dist
+    world, rank = 1, 0
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    job = CanvasJob(engine, guidance, crop_margin, stitching_mode)
+    if feature_blending_level > 0:
+        if world > 1:
+            raise RuntimeError('stylize: feature blending makes patches raster-dependent; run it on one GPU')
+        canvas = _stylize_blended(engine, job, opts, feature_blending_level, z_per_patch)
+        out = job.finish(canvas, on_white)
+        return (out, job) if return_job else out
+    start, end = shard_crops(job.crops, world, rank)
+    dev = engine.device
+    tiles_local = torch.empty((end - start, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
+    for b0 in range(start, end, batch_size):
+        b1 = min(b0 + batch_size, end)
+        geom = job.gather(b0, b1)
+        pos = job.d_crops[b0:b1].to(torch.int64)
+        tiles, _ = engine.render_tiles(geom, _batch_opts(opts, z_per_patch, b0, b1, pos), crop_margin=crop_margin)
+        tiles_local[b0 - start:b1 - start] = tiles
+    if world == 1:
+        canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
+        job.place(canvas, job.owner_map(), tiles_local, start, end)
+        out = job.finish(canvas, on_white)
+        return (out, job) if return_job else out
+    # ---- multi-GPU: one gather of finished tiles to rank 0 (NCCL over NVLink; gloo in CPU tests is not used here) ----
+    bounds = [shard_crops(job.crops, world, r) for r in range(world)]
+    max_n = max(e - s for s, e in bounds)
+    padded = torch.zeros((max_n, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
+    padded[: end - start] = tiles_local
+    gathered = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded, gathered, dst=0, group=group)
+    if rank != 0:
+        return (None, job) if return_job else None
+    canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
+    owner = job.owner_map()
+    for r, (s, e) in enumerate(bounds):
+        if e > s:
+            job.place(canvas, owner, gathered[r][: e - s].contiguous(), s, e)
+    out = job.finish(canvas, on_white)
+    return (out, job) if return_job else out
+
+
+# ------------------------------------------------------------------------------------------------ feature blending
+def dirty_area_alpha(width: int, margin: int, crop_margin: int, device) -> torch.Tensor:
+    """``PaintingHelper.generate_dirty_area_alpha`` for a full-patch dirty area (brush.py:159-187)."""
+    lo = margin + crop_margin
+    hi = lo + width - 2 * margin - 2 * crop_margin
+    x = torch.linspace(0, width - 1, steps=width, device=device)
+    gy, gx = torch.meshgrid(x, x, indexing='ij')
+    dx = torch.min((gx - lo) ** 2, (gx - hi + 1) ** 2)
+    dy = torch.min((gy - lo) ** 2, (gy - hi + 1) ** 2)
+    d = dx + dy
+    d[0:lo, lo:hi] = dy[0:lo, lo:hi]
+    d[hi:, lo:hi] = dy[hi:, lo:hi]
+    d[lo:hi, 0:lo] = dx[lo:hi, 0:lo]
+    d[lo:hi, hi:] = dx[lo:hi, hi:]
+    res = 1 - torch.sqrt(d) / margin
+    res[res < 0] = 0
+    res[lo:hi, lo:hi] = 1
+    return res
+
+
+class _Blended:
+    def __init__(self, features, alpha):
+        self.features, self.alpha = features, alpha
+
+
+def _stylize_blended(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOptions, level: int, z_per_patch):
+    """Raster-order execution with a feature canvas (brush.py:33-92, 190-242): patch n blends the features saved
+    by earlier overlapping patches into its own post-b(128/2^(level-1)) activations, then saves its core."""
+    dev = engine.device
+    down = 2 ** (level - 1)
+    res = engine.patch_width // down
+    fh, fw = int(math.ceil(job.canvas_h / down)), int(math.ceil(job.canvas_w / down))
+    margin = 16 // down                                   # PaintingHelper.feature_blending_margin = 16
+    cm = job.crop_margin // down
+    base_alpha = dirty_area_alpha(res, margin, cm, dev)
+    base_update = base_alpha > 0.99
+    features, mask = None, None
+    canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
+    for i, (y, x, _, _) in enumerate(job.crops):
+        ys, xs = (y // down * down) // down, (x // down * down) // down       # snap to the feature grid (brush.py:253-258)
+        alpha, update = base_alpha, base_update
+        blended = {}
+        if mask is not None:
+            m = mask[ys:ys + res, xs:xs + res]
+            update = update | (m & (alpha > 0))
+            alpha = alpha.clone()
+            alpha[~m] = 1
+            blended = {res: _Blended(features[..., ys:ys + res, xs:xs + res], (1 - alpha)[None, None])}
+        if cm > 0:
+            update = update.clone()
+            update[:cm, :] = False
+            update[-cm:, :] = False
+            update[:, :cm] = False
+            update[:, -cm:] = False
+        geom = job.gather(i, i + 1)
+        pos = job.d_crops[i:i + 1].to(torch.int64)
+        tiles, raw = engine.render_tiles(geom, _batch_opts(opts, z_per_patch, i, i + 1, pos), crop_margin=job.crop_margin,
+                                         return_features=[res], blended_features=blended)
+        feat = raw[f'features{res}']
+        if features is None:
+            features = torch.zeros((1, feat.shape[1], fh, fw), dtype=feat.dtype, device=dev)
+            mask = torch.zeros((fh, fw), dtype=torch.bool, device=dev)
+        mask[ys:ys + res, xs:xs + res][update] = True
+        um = update[None, None].expand(-1, feat.shape[1], -1, -1)
+        features[..., ys:ys + res, xs:xs + res][um] = feat[um]
+        ty, tx = (y // down * down) + job.crop_margin, (x // down * down) + job.crop_margin
+        canvas[ty:ty + job.tile, tx:tx + job.tile] = tiles[0]                 # raster order = last writer wins
+    return canvas

@@ -127,7 +127,34 @@ def _pad4(padding):
 
 
 def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1.0):
-    """Closed form of SURVEY.md appendix C.2 evaluated tap by tap:
+    """The reference's formulation (upfirdn2d.py:168-208): zero-stuff, pad / crop, depthwise correlation with the
+    flipped filter (ATen conv2d, the same primitive the reference calls), decimate.  Cross-checked against the
+    tap-by-tap closed form :func:`upfirdn2d_closed_form` in tests/test_oracle_golden.py."""
+    assert x.ndim == 4
+    upx, upy = _pair(up)
+    downx, downy = _pair(down)
+    px0, px1, py0, py1 = _pad4(padding)
+    if f is None:
+        f = torch.ones([1, 1], dtype=torch.float32)
+    N, C, H, W = x.shape
+    u = x.new_zeros(N, C, H * upy, W * upx)
+    u[:, :, ::upy, ::upx] = x
+    u = F.pad(u, [max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
+    u = u[:, :, max(-py0, 0): u.shape[2] - max(-py1, 0), max(-px0, 0): u.shape[3] - max(-px1, 0)]
+    f = (f * (gain ** (f.ndim / 2))).to(x.dtype)
+    if not flip_filter:
+        f = f.flip(list(range(f.ndim)))
+    k = f[None, None].repeat([C, 1] + [1] * f.ndim)
+    if f.ndim == 2:
+        u = F.conv2d(u, k, groups=C)
+    else:
+        u = F.conv2d(u, k.unsqueeze(2), groups=C)
+        u = F.conv2d(u, k.unsqueeze(3), groups=C)
+    return u[:, :, ::downy, ::downx]
+
+
+def upfirdn2d_closed_form(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1.0):
+    """Closed form of SURVEY.md appendix C.2 evaluated tap by tap (what the CUDA kernels implement):
 
     ``y[oy,ox] = gain * sum_{a,b} ft[a,b] * xhat[oy*downy + a - pady0, ox*downx + b - padx0]``
     with ``xhat`` the zero-stuffed input and ``ft`` = f flipped unless flip_filter.
@@ -141,8 +168,8 @@ def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1.0):
         f = torch.ones([1, 1], dtype=torch.float32)
     if f.ndim == 1:
         g = math.sqrt(gain)
-        x = upfirdn2d(x, f[None, :], up=(upx, 1), down=(downx, 1), padding=(px0, px1, 0, 0), flip_filter=flip_filter, gain=g)
-        return upfirdn2d(x, f[:, None], up=(1, upy), down=(1, downy), padding=(0, 0, py0, py1), flip_filter=flip_filter, gain=g)
+        x = upfirdn2d_closed_form(x, f[None, :], up=(upx, 1), down=(downx, 1), padding=(px0, px1, 0, 0), flip_filter=flip_filter, gain=g)
+        return upfirdn2d_closed_form(x, f[:, None], up=(1, upy), down=(1, downy), padding=(0, 0, py0, py1), flip_filter=flip_filter, gain=g)
     N, C, H, W = x.shape
     fh, fw = f.shape
     ft = (f if flip_filter else f.flip([0, 1])).to(x.dtype) * gain
@@ -196,11 +223,8 @@ def downsample2d(x, f, down=2, padding=0, flip_filter=False, gain=1.0):
 # conv2d_resample -- torch_utils/ops/conv2d_resample.py:59-154
 # --------------------------------------------------------------------------------------
 
-def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
-    """Mathematical definition (the reference's own generic fallback,
-    conv2d_resample.py:149-154): FIR-upsample, convolve, FIR-downsample, with
-    the padding bookkeeping of :94-104.  The reference's transposed-conv fast
-    path (:124-142) is algebraically identical (full convolutions commute)."""
+def _resample_padding(f, up, down, padding):
+    """conv2d_resample.py:94-104."""
     fw = fh = 1
     if f is not None:
         fh, fw = f.shape[0], f.shape[-1]
@@ -215,6 +239,13 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         px1 += (fw - down) // 2
         py0 += (fh - down + 1) // 2
         py1 += (fh - down) // 2
+    return px0, px1, py0, py1
+
+
+def conv2d_resample_definition(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
+    """Mathematical definition = the reference's generic fallback (conv2d_resample.py:149-154): FIR-upsample, convolve,
+    FIR-downsample.  This FIR-first order is what the CUDA product executes for up-sampling layers."""
+    px0, px1, py0, py1 = _resample_padding(f, up, down, padding)
     x = upfirdn2d(x, f if up > 1 else None, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
     if not flip_weight:
         w = w.flip([2, 3])
@@ -222,6 +253,30 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     if down > 1:
         x = upfirdn2d(x, f, down=down, flip_filter=flip_filter)
     return x
+
+
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
+    """conv2d_resample.py:59-154 with the reference's own choice of path for the cases the generator hits:
+    up > 1 -> transposed strided convolution followed by the FIR (:124-142); up == down == 1 with symmetric
+    padding -> plain convolution (:144-147); anything else -> the definition above.  (The two up-sampling orders are
+    algebraically identical -- full convolutions commute -- and tests assert they agree.)"""
+    kh, kw = w.shape[2], w.shape[3]
+    px0, px1, py0, py1 = _resample_padding(f, up, down, padding)
+    if up > 1 and groups == 1 and down == 1:
+        wt = w.transpose(0, 1)
+        px0 -= kw - 1
+        px1 -= kw - up
+        py0 -= kh - 1
+        py1 -= kh - up
+        pxt = max(min(-px0, -px1), 0)
+        pyt = max(min(-py0, -py1), 0)
+        # _conv2d_wrapper(transpose=True, flip_weight=(not flip_weight)): flips when flip_weight is True
+        wt = wt.flip([2, 3]) if flip_weight else wt
+        x = F.conv_transpose2d(x, wt.to(x.dtype), stride=up, padding=[pyt, pxt])
+        return upfirdn2d(x, f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2, flip_filter=flip_filter)
+    if up == 1 and down == 1 and px0 == px1 and py0 == py1 and px0 >= 0 and py0 >= 0:
+        return F.conv2d(x, (w if flip_weight else w.flip([2, 3])).to(x.dtype), padding=[py0, px0], groups=groups)
+    return conv2d_resample_definition(x, w, f, up, down, padding, groups, flip_weight, flip_filter)
 
 
 # --------------------------------------------------------------------------------------

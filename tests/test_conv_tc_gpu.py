@@ -17,6 +17,7 @@ def md(a, b):
 
 
 def pack(x_nchw, cs=None, c_off=0, scale=None):
+    x_nchw = x_nchw.contiguous()
     N, C, H, W = x_nchw.shape
     cs = cs or C
     dst = torch.zeros((N, H, W, cs), dtype=torch.bfloat16, device=DEV)
@@ -57,7 +58,8 @@ def test_conv_tc_matches_fp64_conv(R, cin, B, valid):
     x_cs = cin + 16                                                  # exercise a channel stride > Cin (concat buffers)
     xq = pack(x.to(DEV), cs=x_cs)
     wq = torch.empty((9, cout, (cin + 63) // 64 * 64), dtype=torch.bfloat16, device=DEV)
-    _lib.call('nbe_prepare_weights_bf16', _lib.ptr(w.to(DEV)), _lib.ptr(wq), cout, cin, 3, 0, _lib.stream())
+    wd = w.to(DEV)
+    _lib.call('nbe_prepare_weights_bf16', _lib.ptr(wd), _lib.ptr(wq), cout, cin, 3, 0, _lib.stream())
     y_cs = cout + 8
     y = torch.full((B, R, R, y_cs), 7.0, dtype=torch.bfloat16, device=DEV)
     dd, nn, bb, nsd = d.to(DEV), noise.to(DEV), bias.to(DEV), ns.to(DEV)
@@ -81,7 +83,8 @@ def test_prepare_weights_flip_and_pad():
     w = torch.randn(16, 20, 3, 3, generator=g)
     for flip in (0, 1):
         wq = torch.empty((9, 16, 64), dtype=torch.bfloat16, device=DEV)
-        _lib.call('nbe_prepare_weights_bf16', _lib.ptr(w.to(DEV)), _lib.ptr(wq), 16, 20, 3, flip, _lib.stream())
+        wd = w.to(DEV)
+        _lib.call('nbe_prepare_weights_bf16', _lib.ptr(wd), _lib.ptr(wq), 16, 20, 3, flip, _lib.stream())
         ref = (w.flip([2, 3]) if flip else w).reshape(16, 20, 9).permute(2, 0, 1).to(torch.bfloat16).float()
         assert md(wq[:, :, :20].float(), ref) == 0
         assert float(wq[:, :, 20:].float().abs().max()) == 0
@@ -95,7 +98,8 @@ def test_upsample2x_nhwc_matches_oracle(H, C, cs):
     f4 = O.setup_filter([1, 3, 3, 1])
     xq = pack(x.to(DEV), cs=cs)
     u = torch.empty((2, 2 * H + 2, 2 * H + 2, C), dtype=torch.bfloat16, device=DEV)
-    _lib.call('nbe_upsample2x_nhwc_bf16', _lib.ptr(xq), _lib.ptr(f4.to(DEV)), _lib.ptr(s.to(DEV)), _lib.ptr(u), 2, H, H, C, cs, _lib.stream())
+    fd, sd = f4.to(DEV), s.to(DEV)          # keep device copies alive across the async launch
+    _lib.call('nbe_upsample2x_nhwc_bf16', _lib.ptr(xq), _lib.ptr(fd), _lib.ptr(sd), _lib.ptr(u), 2, H, H, C, cs, _lib.stream())
     ref = O.upfirdn2d(x.to(torch.bfloat16).float() * s[:, :, None, None], f4, up=2, padding=[3, 2, 3, 2], gain=4.0)
     got = u.permute(0, 3, 1, 2).float()
     assert md(got, ref) < 1e-2 * float(ref.abs().max())
@@ -112,11 +116,12 @@ def test_torgb_triad_both_layouts():
     tt = torch.einsum('bchw,kc,bc->bkhw', x.double(), w.double(), st.double()) + bias.double()[None, :, None, None]
     uvs_ref = torch.softmax(tt.clamp(-256, 256), dim=1)
     img_ref = torch.einsum('bkhw,bck->bchw', uvs_ref, colors.double())
+    wd, std, bd, cd = w.to(DEV), st.to(DEV), bias.to(DEV), colors.to(DEV)
     for is_bf16 in (0, 1):
         xin = pack(x.to(DEV)) if is_bf16 else x.to(DEV)
         img = torch.empty((B, 3, R, R), device=DEV)
         uvs = torch.empty((B, 3, R, R), device=DEV)
-        _lib.call('nbe_torgb_triad', _lib.ptr(xin), is_bf16, C, _lib.ptr(w.to(DEV)), _lib.ptr(st.to(DEV)), _lib.ptr(bias.to(DEV)),
-                  _lib.ptr(colors.to(DEV)), 256.0, _lib.ptr(img), _lib.ptr(uvs), B, C, R, R, _lib.stream())
+        _lib.call('nbe_torgb_triad', _lib.ptr(xin), is_bf16, C, _lib.ptr(wd), _lib.ptr(std), _lib.ptr(bd),
+                  _lib.ptr(cd), 256.0, _lib.ptr(img), _lib.ptr(uvs), B, C, R, R, _lib.stream())
         tol = 2e-2 if is_bf16 else 1e-5
         assert md(uvs, uvs_ref) < tol and md(img, img_ref) < tol

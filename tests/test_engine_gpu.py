@@ -1,0 +1,140 @@
+"""GPU parity of the engine composite and the batched patch scheduler against the reference-generated canvases
+(tests/golden/engine.npz) and the CPU oracle: bit-exact crop list / tile placement, uint8 pixels within
+1 LSB (FP32 mode; truncation can flip at a boundary) or 3 LSB (BF16 mode, 255 * 1e-2)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, t
+from oracle import neube_oracle as O
+from brushstroke_engine_b200 import params as P, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def engines(bundles):
+    from brushstroke_engine_b200.engine import TriadPaintEngine
+    cfg, ecfg, gp, ep = bundles
+    return {m: TriadPaintEngine(gp, ep, DEV, mode=m) for m in ('fp32', 'bf16')}
+
+
+def _opts(z, style_id=None):
+    from brushstroke_engine_b200.engine import GanBrushOptions
+    o = GanBrushOptions()
+    o.set_style(z, style_id)
+    return o
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
+@pytest.mark.parametrize('render_mode', ['clear', 'full'])
+def test_render_stroke_torch_matches_oracle(engines, bundles, mode, tol, render_mode):
+    cfg, ecfg, gp, ep = bundles
+    eng = engines[mode]
+    eng.set_render_mode(render_mode)
+    geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=s) for s in (3, 4, 5)]))
+    z = torch.cat([P.style_z_from_seed(s) for s in (594, 7, 11)])
+    pos = torch.tensor([[0, 88], [264, 1144], [88, 88]])
+    o = _opts(z.to(DEV))
+    o.position = pos.to(DEV)
+    o.set_color(1, np.array([255, 0, 128], dtype=np.uint8))          # user colour override (brush.py:514-527)
+    rgba, raw, dbg = eng._render_stroke_torch(geom.to(DEV), None, o)
+    gf = O.geometry_encode(ep, ecfg, geom)
+    _, d = O.generator_forward(gp, cfg, z, gf, positions=pos)
+    ref = O.triad_composite(d['uvs'], d['colors'], render_mode, color1=torch.tensor([1.0, 0.0, 128 / 255]))
+    assert rgba.shape == (3, 4, 128, 128) and dbg is None
+    assert float((rgba.cpu() - ref).abs().max()) < tol
+    assert set(raw.keys()) >= {'uvs', 'colors', 'ws'}
+    eng.set_render_mode('clear')
+    with pytest.raises(RuntimeError):
+        eng.set_render_mode('bogus')
+
+
+@pytest.mark.parametrize('mode,lsb', [('fp32', 1), ('bf16', 3)])
+@pytest.mark.parametrize('level,render_mode', [(0, 'clear'), (0, 'full'), (2, 'clear')])
+def test_stylize_matches_reference_canvas(engines, mode, lsb, level, render_mode):
+    from brushstroke_engine_b200 import stylizer
+    g = load_golden('engine')
+    eng = engines[mode]
+    eng.set_render_mode(render_mode)
+    out, job = stylizer.stylize(eng, g['guidance'], _opts(P.style_z_from_seed(594), '594'), crop_margin=10,
+                                feature_blending_level=level, batch_size=5, return_job=True)
+    eng.set_render_mode('clear')
+    assert np.array_equal(np.array(job.crops, dtype=np.int32), g['crops'])            # bit-exact patch indexing
+    assert np.array_equal(job.tiles_yx, g['metas'])                                   # bit-exact tile placement offsets
+    ref = g[f'canvas_l{level}_{render_mode}']
+    assert out.shape == ref.shape and out.dtype == np.uint8
+    diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= lsb, diff.max()
+    if mode == 'fp32':
+        assert (diff > 0).mean() < 2e-3
+
+
+def test_batching_is_invisible(engines):
+    """Any batch size gives the same canvas bit for bit (ownership map, not launch order, resolves overlaps)."""
+    from brushstroke_engine_b200 import stylizer
+    g = load_golden('engine')
+    eng = engines['bf16']
+    o = _opts(P.style_z_from_seed(594), '594')
+    a = stylizer.stylize(eng, g['guidance'], o, batch_size=16)
+    b = stylizer.stylize(eng, g['guidance'], o, batch_size=3)
+    c = stylizer.stylize(eng, g['guidance'], o, batch_size=1, on_white=True)
+    assert np.array_equal(a, b)
+    assert np.array_equal(stylizer.composite_on_white(a), c)
+
+
+def test_owner_map_equals_raster_loop(engines):
+    from brushstroke_engine_b200 import stylizer
+    guidance = synthetic.synthetic_guidance(500, 333, num_lines=6, seed=2, radii=(3, 9))
+    for mode in ('all', 'full'):
+        job = stylizer.CanvasJob(engines['bf16'], guidance, 10, mode)
+        owner = job.owner_map().cpu().numpy()
+        ref = np.full((job.canvas_h, job.canvas_w), -1, dtype=np.int32)
+        for i, (y, x) in enumerate(job.tiles_yx):
+            ref[y:y + job.tile, x:x + job.tile] = i
+        assert np.array_equal(owner, ref), mode
+        crops_o, _ = O.generate_stitching_crops(O.pad_geo(guidance, 10), 128, mode, 20)
+        assert crops_o == job.crops
+
+
+def test_gather_geom_matches_prepare_geom_input(engines):
+    from brushstroke_engine_b200 import stylizer
+    guidance = synthetic.synthetic_guidance(300, 260, num_lines=10, seed=5, radii=(1, 3, 9))
+    job = stylizer.CanvasJob(engines['bf16'], guidance, 10, 'all')
+    got = job.gather(0, len(job.crops)).cpu()
+    for i, (y, x, _, _) in enumerate(job.crops):
+        ref = O.prepare_geom_input(255 - job.geom[y:y + 128, x:x + 128, :])
+        assert torch.equal(got[i:i + 1], ref)
+    e = engines['bf16']
+    assert torch.equal(e.prepare_geom_input(255 - job.geom[0:128, 0:128, :]).cpu(), O.prepare_geom_input(255 - job.geom[0:128, 0:128, :]))
+
+
+def test_uvs_mapping(engines, bundles):
+    cfg, ecfg, gp, ep = bundles
+    g = load_golden('engine')
+    eng = engines['fp32']
+    o = _opts(P.style_z_from_seed(594), '594')
+    sf = eng.uvs_mapper.get_sfactor(o)                     # same synthetic mapper geometry as make_golden.py
+    assert abs(float(sf) - float(g['sfactor'])) < 1e-4 * float(g['sfactor'])
+    o.enable_uvs_mapping = True
+    geom = torch.from_numpy(synthetic.synthetic_patch(128, seed=3))
+    rgba, raw, _ = eng._render_stroke_torch(geom.to(DEV), None, o)
+    ref = O.triad_composite(raw['uvs'].cpu(), raw['colors'].cpu(), 'clear', sfactor=torch.tensor(float(sf)))
+    assert float((rgba.cpu() - ref).abs().max()) < 1e-5
+
+
+def test_render_patches_host_equals_device_path(engines):
+    eng = engines['bf16']
+    guidance = synthetic.synthetic_guidance(300, 260, num_lines=10, seed=5, radii=(1, 3, 9))
+    from brushstroke_engine_b200 import stylizer
+    job = stylizer.CanvasJob(eng, guidance, 10, 'all')
+    n = 6
+    patches = torch.from_numpy(np.stack([job.geom[y:y + 128, x:x + 128, 0] for (y, x, _, _) in job.crops[:n]]))
+    z = torch.cat([P.style_z_from_seed(i) for i in range(n)])
+    pos = torch.from_numpy(job.crops_yx[:n].astype(np.int64))
+    host = eng.render_patches_host(patches.pin_memory(), z.pin_memory(), pos.pin_memory(), crop_margin=10)
+    o = _opts(z.to(DEV))
+    o.position = pos.to(DEV)
+    tiles, _ = eng.render_tiles(job.gather(0, n), o, crop_margin=10)
+    assert host.shape == (n, 108, 108, 4) and torch.equal(host, tiles.cpu())

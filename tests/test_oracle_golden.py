@@ -108,3 +108,20 @@ def test_crop_grid_sizes():
         geo = O.pad_geo(np.full((size, size, 1), 255, np.uint8), 10)
         crops, padded = O.generate_stitching_crops(geo, 128, 'all', 20)
         assert len(crops) == ncrops and padded.shape[:2] == (canvas, canvas)
+
+
+def test_two_restatements_agree():
+    """conv-based vs tap-by-tap upfirdn2d; transposed-conv vs FIR-first conv2d_resample (what the CUDA path runs)."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, 9, 11, generator=g)
+    fa = torch.rand(3, 5, generator=g)
+    f4 = O.setup_filter([1, 3, 3, 1])
+    for kw in (dict(up=[3, 2], down=[2, 1], padding=[2, -1, 0, 3], flip_filter=True, gain=1.5),
+               dict(up=2, padding=[3, 2, 3, 2], gain=4.0), dict(down=2, padding=[1, 1, 1, 1])):
+        f = fa if 'flip_filter' in kw else f4
+        assert md(O.upfirdn2d(x, f, **kw), O.upfirdn2d_closed_form(x, f, **kw)) < 2e-6
+    w = torch.randn(5, 3, 3, 3, generator=g)
+    for up, fl in ((2, False), (2, True), (1, True), (1, False)):
+        a = O.conv2d_resample(x, w, f=f4 if up > 1 else None, up=up, padding=1, flip_weight=fl)
+        b = O.conv2d_resample_definition(x, w, f=f4 if up > 1 else None, up=up, padding=1, flip_weight=fl)
+        assert a.shape == b.shape and md(a, b) < 2e-5
