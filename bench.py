@@ -141,6 +141,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (profiling runs under ncu)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -211,14 +212,16 @@ def main():
         engine.G.probe = None
         dom_ms = float(np.mean([a.elapsed_time(b) for a, b in probe]))
         # ---- end-to-end (host buffers) ----
-        for i in range(3):
-            e2e_step(i)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            e2e_step(i)
-        barrier()
-        e2e_s = time.perf_counter() - t0
+        e2e_s = float('nan')
+        if not args.no_e2e:
+            for i in range(3):
+                e2e_step(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                e2e_step(i)
+            barrier()
+            e2e_s = time.perf_counter() - t0
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 

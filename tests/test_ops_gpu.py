@@ -28,9 +28,10 @@ def test_bias_act_golden_all_activations():
     assert md(bias_act(t(g['x2']).to(DEV), t(g['b2']).to(DEV), dim=1, act='tanh'), g['y2_tanh']) < 2e-6
 
 
-@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-6), (torch.float16, 4e-3), (torch.bfloat16, 3e-2), (torch.float64, 1e-12)])
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-6), (torch.float16, 4e-3), (torch.bfloat16, 3e-2), (torch.float64, 2e-7)])
 @pytest.mark.parametrize('shape,dim', [((3, 128, 16, 16), 1), ((2, 7, 5, 3), 1), ((5, 9), 1), ((4, 6, 10), 2), ((1, 1, 1, 1), 1), ((0, 4, 2, 2), 1)])
 def test_bias_act_dtypes_shapes(dtype, tol, shape, dim):
+    # float64: alpha / gain / clamp cross the ABI as float32, exactly like the reference plugin (bias_act.cpp:32)
     from brushstroke_engine_b200.bias_act import bias_act
     gen = torch.Generator().manual_seed(sum(shape) + dim)
     x = (torch.randn(shape, generator=gen) * 2).to(dtype)
