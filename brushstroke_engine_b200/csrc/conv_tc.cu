@@ -93,6 +93,8 @@ struct ConvTcParams {
     int bw, bh, bn;                 // pixel box of one M tile (bw * bh * bn == 128)
     int tiles_x, tiles_y;           // tiles per image in x / y
     int KK, K, pad_off;             // taps, kernel size, coordinate offset (= -pad for 'same', 0 for 'valid')
+    int in_stride;                  // 1 or 2 (input pixel = out pixel * in_stride + tap)
+    long long y_row_pitch, y_img_pitch;   // output addressing in pixels (lets the epilogue write into the interior of a padded buffer)
     int k_chunks;                   // Cin_pad / 64
     const float* dcoef; const float* noise; long long noise_sn; float noise_gain;
     const float* bias; float alpha, gain, clamp; const float* next_scale;
@@ -149,7 +151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 mbar_wait(smem_u32(&bars[TC_STAGES + stage]), phase ^ 1);
                 const uint32_t full = smem_u32(&bars[stage]);
                 mbar_expect_tx(full, TC_A_BYTES + b_bytes);
-                tma_load_4d(smem_u32(smem_a + stage * TC_A_BYTES), &tmap_a, full, cc * 64, x0 + kw + p.pad_off, y0 + kh + p.pad_off, n0);
+                tma_load_4d(smem_u32(smem_a + stage * TC_A_BYTES), &tmap_a, full, cc * 64, x0 * p.in_stride + kw + p.pad_off, y0 * p.in_stride + kh + p.pad_off, n0);
                 tma_load_3d(smem_u32(smem_b + stage * b_bytes), &tmap_b, full, cc * 64, 0, tap);
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -189,7 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (valid) {
-                __nv_bfloat16* yp = p.y + (((long long)n * p.OH + oy) * p.OW + ox) * p.y_cs + c0;
+                __nv_bfloat16* yp = p.y + ((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs + c0;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     int4 out;
@@ -256,10 +258,10 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                     const cuuint32_t* box, const char* what) {
+                     const cuuint32_t* box, const char* what, int spatial_stride = 1) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail(NBE_ECUDA, "conv_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -286,6 +288,19 @@ extern "C" int nbe_conv_tc_bf16(const void* x, const void* wq, void* y,
                                 const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
                                 const float* bias, float alpha, float gain, float clamp, const float* next_scale,
                                 nbe_stream_t stream) {
+    return nbe_conv_tc_bf16_ex(x, wq, y, N, OH, OW, Cin, x_cs, Cout, y_cs, K, valid, 1, 0, 0, OW, (int64_t)OH * OW,
+                               dcoef, noise, noise_sn, noise_gain, bias, alpha, gain, clamp, next_scale, stream);
+}
+
+extern "C" int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
+                                   int N, int OH, int OW, int Cin, int x_cs, int Cout, int y_cs, int K, int valid,
+                                   int in_stride, int in_h, int in_w, int64_t y_row_pitch, int64_t y_img_pitch,
+                                   const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                                   const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                                   nbe_stream_t stream) {
+    NBE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride must be 1 or 2");
+    NBE_REQUIRE(in_stride == 1 || valid, "conv_tc: strided convolution needs a pre-padded input (valid = 1)");
+    NBE_REQUIRE(y_row_pitch >= OW && y_img_pitch >= y_row_pitch * OH, "conv_tc: bad output pitches");
     NBE_REQUIRE(x && wq && y, "conv_tc: null tensor");
     NBE_REQUIRE(N >= 0 && OH >= 1 && OW >= 1 && Cin >= 1, "conv_tc: bad shape");
     NBE_REQUIRE(K == 1 || K == 3, "conv_tc: kernel size %d not supported (1 or 3)", K);
@@ -304,7 +319,10 @@ extern "C" int nbe_conv_tc_bf16(const void* x, const void* wq, void* y,
     p.K = K; p.KK = K * K;
     const int pad = K / 2;
     p.pad_off = valid ? 0 : -pad;
-    const int IH = valid ? OH + 2 * pad : OH, IW = valid ? OW + 2 * pad : OW;
+    const int need_h = valid ? (OH - 1) * in_stride + K : OH, need_w = valid ? (OW - 1) * in_stride + K : OW;
+    const int IH = in_h > 0 ? in_h : need_h, IW = in_w > 0 ? in_w : need_w;
+    NBE_REQUIRE(IH >= need_h && IW >= need_w, "conv_tc: input %dx%d too small for output %dx%d", IH, IW, OH, OW);
+    p.in_stride = in_stride; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch;
     const int Cin_pad = (Cin + 63) / 64 * 64;
     p.k_chunks = Cin_pad / 64;
     p.dcoef = dcoef; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain;
@@ -317,8 +335,8 @@ extern "C" int nbe_conv_tc_bf16(const void* x, const void* wq, void* y,
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)x_cs * 2, (cuuint64_t)IW * x_cs * 2, (cuuint64_t)IH * IW * x_cs * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
-        int st = make_tmap(&tmap_a, x, 4, dims, strides, box, "activations");
+        cuuint32_t box[4] = {64, (cuuint32_t)(p.bw * in_stride), (cuuint32_t)(p.bh * in_stride), (cuuint32_t)p.bn};
+        int st = make_tmap(&tmap_a, x, 4, dims, strides, box, "activations", in_stride);
         if (st) return st;
     }
     {

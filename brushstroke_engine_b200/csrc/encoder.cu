@@ -1,0 +1,179 @@
+// Geometry-encoder helpers for the tensor-core path (NHWC bf16, reflect padding kept explicit in the buffers so the
+// 3x3 convolutions become *valid* implicit GEMMs for nbe_conv_tc_bf16_ex):
+//   * enc_conv7x7_kernel      : first layer, 1 -> 64 channels, 7x7, reflect pad 3, folded BN bias + LeakyReLU (CUDA cores:
+//                               K = 49 is too thin for the tensor pipe), writes the interior of a 1-px padded NHWC buffer
+//   * reflect_border_kernel   : fills the 1-px border of a padded NHWC buffer by reflection (torch 'reflect' semantics)
+//   * bilinear2x_pad_kernel   : bilinear x2 (align_corners = True) + reflect pad 1 in one pass
+// Reference: forger/experimental/autoenc/simple_autoencoder.py:95-126 (SingleConvolution / ScaleUp), 155-199, 251-261.
+#include "common.cuh"
+
+namespace nbe {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {        // torch 'reflect': -1 -> 1, n -> n-2
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+constexpr int E7_T = 16;                                             // 16 x 16 output pixels per CTA
+
+__global__ void __launch_bounds__(256)
+enc_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   __nv_bfloat16* __restrict__ y, int H, int W, int Cout, int y_cs, float neg_slope, int preproc) {
+    __shared__ float s_in[E7_T + 6][E7_T + 6 + 1];
+    extern __shared__ float s_w[];                                   // [49][Cout] then bias[Cout]
+    float* s_b = s_w + 49 * Cout;
+    const int n = blockIdx.z, ty0 = blockIdx.y * E7_T, tx0 = blockIdx.x * E7_T;
+    for (int i = threadIdx.x; i < 49 * Cout; i += 256) {
+        const int t = i / Cout, o = i - t * Cout;
+        s_w[i] = w[o * 49 + t];
+    }
+    for (int i = threadIdx.x; i < Cout; i += 256) s_b[i] = bias[i];
+    for (int i = threadIdx.x; i < (E7_T + 6) * (E7_T + 6); i += 256) {
+        const int r = i / (E7_T + 6), c = i - r * (E7_T + 6);
+        const int iy = reflect_idx(ty0 + r - 3, H), ix = reflect_idx(tx0 + c - 3, W);
+        float v = x[((long long)n * H + iy) * W + ix];
+        if (preproc == 1) v = 1.f - v;                               // 'inverse'      (base.py:46-49)
+        else if (preproc == 2) v = (1.f - v) * 2.f - 1.f;            // '-11inverse'   (base.py:42-45)
+        s_in[r][c] = v;
+    }
+    __syncthreads();
+    const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
+    const int oy = ty0 + ly, ox = tx0 + lx;
+    float in[49];
+#pragma unroll
+    for (int kh = 0; kh < 7; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw) in[kh * 7 + kw] = s_in[ly + kh][lx + kw];
+    if (oy >= H || ox >= W) return;
+    // output goes to the interior of a [N, H+2, W+2, y_cs] buffer
+    __nv_bfloat16* yp = y + (((long long)n * (H + 2) + oy + 1) * (W + 2) + ox + 1) * y_cs;
+    for (int o0 = 0; o0 < Cout; o0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = s_b[o0 + j];
+#pragma unroll
+        for (int t = 0; t < 49; ++t) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[t * Cout + o0]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[t * Cout + o0 + 4]);
+            acc[0] = fmaf(in[t], w0.x, acc[0]); acc[1] = fmaf(in[t], w0.y, acc[1]);
+            acc[2] = fmaf(in[t], w0.z, acc[2]); acc[3] = fmaf(in[t], w0.w, acc[3]);
+            acc[4] = fmaf(in[t], w1.x, acc[4]); acc[5] = fmaf(in[t], w1.y, acc[5]);
+            acc[6] = fmaf(in[t], w1.z, acc[6]); acc[7] = fmaf(in[t], w1.w, acc[7]);
+        }
+        int4 out;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = acc[2 * j], b = acc[2 * j + 1];
+            a = a > 0.f ? a : a * neg_slope;
+            b = b > 0.f ? b : b * neg_slope;
+            o2[j] = __floats2bfloat162_rn(a, b);
+        }
+        *reinterpret_cast<int4*>(yp + o0) = out;
+    }
+}
+
+// One thread per (border pixel, 8-channel vector).  Border pixels of an Hp x Wp image: 2*Wp + 2*(Hp-2).
+__global__ void __launch_bounds__(256)
+reflect_border_kernel(__nv_bfloat16* __restrict__ buf, int N, int Hp, int Wp, int C, int cs) {
+    const int CV = C / 8;
+    const int nb = 2 * Wp + 2 * (Hp - 2);
+    const long long total = (long long)N * nb * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int b = (int)(t % nb);
+        const int n = (int)(t / nb);
+        int py, px;
+        if (b < Wp) { py = 0; px = b; }
+        else if (b < 2 * Wp) { py = Hp - 1; px = b - Wp; }
+        else { const int r = b - 2 * Wp; py = 1 + (r >> 1); px = (r & 1) ? Wp - 1 : 0; }
+        // interior coordinates are padded coordinates - 1; reflect in interior space
+        const int sy = reflect_idx(py - 1, Hp - 2) + 1, sx = reflect_idx(px - 1, Wp - 2) + 1;
+        const int4 v = *reinterpret_cast<const int4*>(buf + (((long long)n * Hp + sy) * Wp + sx) * cs + cv * 8);
+        *reinterpret_cast<int4*>(buf + (((long long)n * Hp + py) * Wp + px) * cs + cv * 8) = v;
+    }
+}
+
+// out[n, py, px, :] (padded (2h+2) x (2w+2)) = bilinear_x2_align_corners(x)[reflect(py-1), reflect(px-1)]
+__global__ void __launch_bounds__(256)
+bilinear2x_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int h, int w, int C,
+                      int xs_c, int out_cs) {
+    const int CV = C / 8;
+    const int Hp = 2 * h + 2, Wp = 2 * w + 2;
+    const long long total = (long long)N * Hp * Wp * CV;
+    const float sy_scale = (float)(h - 1) / (float)(2 * h - 1), sx_scale = (float)(w - 1) / (float)(2 * w - 1);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int px = (int)(t % Wp); t /= Wp;
+        const int py = (int)(t % Hp);
+        const int n = (int)(t / Hp);
+        const int Y = reflect_idx(py - 1, 2 * h), X = reflect_idx(px - 1, 2 * w);
+        const float fy = sy_scale * (float)Y, fx = sx_scale * (float)X;      // ATen: scale * dst_index (align_corners)
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        const __nv_bfloat16* base = x + (long long)n * h * w * xs_c + cv * 8;
+        const int4 r00 = *reinterpret_cast<const int4*>(base + ((long long)y0 * w + x0) * xs_c);
+        const int4 r01 = *reinterpret_cast<const int4*>(base + ((long long)y0 * w + x1) * xs_c);
+        const int4 r10 = *reinterpret_cast<const int4*>(base + ((long long)y1 * w + x0) * xs_c);
+        const int4 r11 = *reinterpret_cast<const int4*>(base + ((long long)y1 * w + x1) * xs_c);
+        const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&r00);
+        const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&r01);
+        const __nv_bfloat162* c = reinterpret_cast<const __nv_bfloat162*>(&r10);
+        const __nv_bfloat162* d = reinterpret_cast<const __nv_bfloat162*>(&r11);
+        int4 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 va = __bfloat1622float2(a[k]), vb = __bfloat1622float2(b[k]);
+            const float2 vc = __bfloat1622float2(c[k]), vd = __bfloat1622float2(d[k]);
+            o2[k] = __floats2bfloat162_rn(w00 * va.x + w01 * vb.x + w10 * vc.x + w11 * vd.x,
+                                          w00 * va.y + w01 * vb.y + w10 * vc.y + w11 * vd.y);
+        }
+        *reinterpret_cast<int4*>(out + (((long long)n * Hp + py) * Wp + px) * out_cs + cv * 8) = o;
+    }
+}
+
+}  // namespace nbe
+
+using namespace nbe;
+
+extern "C" int nbe_enc_conv7x7_bf16(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
+                                    int y_cs, float neg_slope, int preproc, nbe_stream_t stream) {
+    NBE_REQUIRE(x && w && bias && y && N >= 0 && H >= 4 && W >= 4, "enc_conv7x7: bad arguments");
+    NBE_REQUIRE(Cout % 8 == 0 && Cout <= 128 && y_cs % 8 == 0 && y_cs >= Cout, "enc_conv7x7: Cout must be a multiple of 8 (<= 128)");
+    NBE_REQUIRE(preproc >= 0 && preproc <= 2, "enc_conv7x7: unknown preprocessing %d", preproc);
+    if (N == 0) return NBE_OK;
+    NBE_REQUIRE(N <= 65535, "enc_conv7x7: batch too large for one launch");
+    dim3 grid((W + E7_T - 1) / E7_T, (H + E7_T - 1) / E7_T, N);
+    const size_t smem = (size_t)(49 + 1) * Cout * sizeof(float);
+    enc_conv7x7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (__nv_bfloat16*)y, H, W, Cout, y_cs, neg_slope, preproc);
+    return launched("enc_conv7x7_kernel");
+}
+
+extern "C" int nbe_reflect_border_nhwc_bf16(void* buf, int N, int Hp, int Wp, int C, int cs, nbe_stream_t stream) {
+    NBE_REQUIRE(buf && N >= 0 && Hp >= 4 && Wp >= 4 && C >= 8 && C % 8 == 0 && cs % 8 == 0 && cs >= C, "reflect_border: bad arguments");
+    if (N == 0) return NBE_OK;
+    const long long total = (long long)N * (2 * Wp + 2 * (Hp - 2)) * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    reflect_border_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, N, Hp, Wp, C, cs);
+    return launched("reflect_border_kernel");
+}
+
+extern "C" int nbe_bilinear2x_pad_nhwc_bf16(const void* x, void* out, int N, int h, int w, int C, int xs_c, int out_cs,
+                                            nbe_stream_t stream) {
+    NBE_REQUIRE(x && out && N >= 0 && h >= 2 && w >= 2 && C >= 8 && C % 8 == 0, "bilinear2x_pad: bad arguments");
+    NBE_REQUIRE(xs_c % 8 == 0 && xs_c >= C && out_cs % 8 == 0 && out_cs >= C, "bilinear2x_pad: bad channel strides");
+    NBE_REQUIRE((((uintptr_t)x | (uintptr_t)out) & 15) == 0, "bilinear2x_pad: tensors must be 16-byte aligned");
+    if (N == 0) return NBE_OK;
+    const long long total = (long long)N * (2 * h + 2) * (2 * w + 2) * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    bilinear2x_pad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, h, w, C, xs_c, out_cs);
+    return launched("bilinear2x_pad_kernel");
+}

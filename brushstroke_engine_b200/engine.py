@@ -170,7 +170,7 @@ class TriadPaintEngine:
                  gen_cfg: GeneratorConfig = GeneratorConfig(), enc_cfg: EncoderConfig = EncoderConfig()):
         self.device = torch.device(device)
         self.G = Generator(gen_params, gen_cfg, self.device, mode=mode)
-        self.encoder = GeometryEncoder(enc_params, enc_cfg, self.device)
+        self.encoder = GeometryEncoder(enc_params, enc_cfg, self.device, mode=mode)
         self.patch_width = self.G.img_resolution
         self.render_modes = set(RENDER_MODES)
         self.render_mode = 'clear'
@@ -192,7 +192,13 @@ class TriadPaintEngine:
 
     # ------------------------------------------------------------------------------------------------
     def _generate(self, geom, opts, **generator_kwargs):
-        geom_feature = self.encoder.encode(geom)
+        if self.G.mode == 'bf16' and self.encoder.mode == 'bf16' and not generator_kwargs.get('force_fp32', False) \
+                and list(self.encoder.res) == list(range(len(self.G.cfg.geom_feature_resolutions))):
+            # fused injection: the encoder writes g0 / g1 straight into the generator's concatenated NHWC inputs
+            geom_feature, dests = self.G.alloc_injection(geom.shape[0])
+            self.encoder.encode_into(geom, dests)
+        else:
+            geom_feature = self.encoder.encode(geom)
         opts.to(self.device)
         B = geom.shape[0]
         opts.prepare_style(B, self.device)

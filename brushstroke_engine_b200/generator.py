@@ -52,6 +52,15 @@ def fully_connected(x, weight, bias, activation=ACT_LINEAR, lr_multiplier=1.0, a
     return out
 
 
+class InjectedGeometry:
+    """Geometry features already resident in the generator's concatenated NHWC bf16 inputs: ``buffers[res]`` is the
+    [B, res, res, C_block + C_geo] tensor whose trailing C_geo channels the encoder has written
+    (``GeometryEncoder.encode_into``); the block's conv1 epilogue fills the leading channels.  Replaces the
+    ``torch.cat([x, geom_feature[i]], dim=1)`` of networks_modified.py:219."""
+    def __init__(self, buffers: Dict[int, torch.Tensor]):
+        self.buffers = buffers
+
+
 class _Layer:
     """Device-side constants of one SynthesisLayer."""
     __slots__ = ('name', 'res', 'up', 'cin', 'cout', 'w32', 'wq', 'wsq', 'bias', 'noise_const', 'noise_strength',
@@ -169,6 +178,17 @@ class Generator:
             self._rgb_affine_b = f32(p[f'{k}.affine.bias'])
         self._layer_by_name = {L.name: L for L in self._layers}
 
+    def alloc_injection(self, B: int):
+        """-> (InjectedGeometry, [(tensor, c_off), ...] in geom_feature order) for ``GeometryEncoder.encode_into``."""
+        cfg = self.cfg
+        bufs, dests = {}, []
+        for res, cg in zip(cfg.geom_feature_resolutions, cfg.geom_feature_channels):
+            cb = cfg.channels(res)
+            t = torch.empty((B, res, res, cb + cg), dtype=torch.bfloat16, device=self.device)
+            bufs[res] = t
+            dests.append((t, cb))
+        return InjectedGeometry(bufs), dests
+
     # ------------------------------------------------------------------------------------------ API
     def __call__(self, *args, **kwargs):
         return self.forward(*args, **kwargs)
@@ -255,6 +275,8 @@ class Generator:
         assert ws.shape[1:] == (self.num_ws, self.w_dim)
         ws = ws.to(torch.float32)
         mode = 'fp32' if (force_fp32 or self.mode == 'fp32') else 'bf16'
+        if isinstance(geom_feature, InjectedGeometry) and mode != 'bf16':
+            raise RuntimeError('synthesis: InjectedGeometry buffers are NHWC bf16 and need the bf16 mode')
         with torch.cuda.device(self.device):
             styles, dcoefs, colors, rgb_styles = self._styles(ws)
             run = self._run_fp32 if mode == 'fp32' else self._run_bf16
@@ -364,7 +386,12 @@ class Generator:
             extra = cfg.geom_feature_channels[list(cfg.geom_feature_resolutions).index(res)] \
                 if res in cfg.geom_feature_resolutions else 0
             y_cs = conv1.cout + extra
-            y = torch.empty((B, res, res, y_cs), dtype=bf, device=dev)
+            injected = isinstance(geom_feature, InjectedGeometry)
+            if extra and injected:
+                y = geom_feature.buffers[res]
+                assert y.shape == (B, res, res, y_cs) and y.dtype == bf
+            else:
+                y = torch.empty((B, res, res, y_cs), dtype=bf, device=dev)
             noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp,
                                                 noise_buffers.get(f'{conv1.name}.noise_const'))
             self._conv_tc(xin, conv1, B, res, conv1.cin, y, y_cs, False, dcoefs[conv1.name], noise, nsn, ngain, None)
@@ -377,7 +404,7 @@ class Generator:
                 feats[f'features{res}'] = self._unpack(x, B, conv1.cout, res, x_cs)
             if res == cfg.img_resolution:
                 img, uvs = self._torgb(x, True, x_cs, rgb_styles, colors, B)
-            if extra:
+            if extra and not injected:
                 g = geom_feature[geo_idx].to(dev, torch.float32).contiguous()
                 assert g.shape == (B, extra, res, res), f'geometry feature {tuple(g.shape)} != {(B, extra, res, res)}'
                 _lib.call('nbe_pack_nhwc_bf16', _lib.ptr(g), _lib.ptr(x), B, extra, res, res, x_cs, conv1.cout, None,

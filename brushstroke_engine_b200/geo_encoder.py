@@ -5,8 +5,17 @@ Mirrors ``BaseGeoEncoder.encode`` -> ``AutoEncoder._encode``
 conv7x7(reflect)+BN+LeakyReLU -> 3x conv3x3 stride 2 -> conv3x3 x2 = g0; bilinear x2 -> conv3x3 = g1.
 Eval-mode BatchNorm is folded into each conv's weight/bias at plan time (exact: the default layer
 order is conv -> BN -> LeakyReLU, simple_autoencoder.py:102-105) and LeakyReLU(0.01) rides in the
-conv epilogue, so each SingleConvolution is one ``nbe_conv2d_f32`` launch.  Reflection padding and
-the bilinear x2 resize are pure data movement and stay on torch in this round.
+conv epilogue, so each SingleConvolution is one launch.
+
+Two execution modes (same switch as the generator):
+* ``'fp32'``: ``nbe_conv2d_f32`` per layer (true FP32, CUDA cores); reflection padding / bilinear resize are torch
+  data-movement ops here.
+* ``'bf16'``: NHWC bf16 buffers that carry their reflect padding explicitly; the 7x7 first layer runs on CUDA cores
+  (``nbe_enc_conv7x7_bf16``, K = 49 is too thin for the tensor pipe), every 3x3 layer (stride 1 or 2) is a *valid*
+  tcgen05 implicit GEMM (``nbe_conv_tc_bf16_ex``: TMA traversal stride 2, epilogue writing into the interior of the
+  next padded buffer), borders are refreshed by ``nbe_reflect_border_nhwc_bf16`` and ``ScaleUp`` is
+  ``nbe_bilinear2x_pad_nhwc_bf16``.  ``encode_into`` writes g0 / g1 straight into the generator's concatenated
+  NHWC inputs (torch.cat of networks_modified.py:219 disappears).
 """
 from __future__ import annotations
 
@@ -22,8 +31,18 @@ from .params import Bundle, EncoderConfig
 ACT_LRELU = 3
 
 
+PREPROC_CODE = {None: 0, 'none': 0, 'inverse': 1, '-11inverse': 2}
+
+
+def _cs(c: int) -> int:
+    """Channel stride of an intermediate NHWC buffer: whole 64-channel TMA boxes (padding channels stay zero)."""
+    return (c + 63) // 64 * 64
+
+
 class GeometryEncoder:
-    def __init__(self, params: Bundle, cfg: EncoderConfig = EncoderConfig(), device='cuda'):
+    def __init__(self, params: Bundle, cfg: EncoderConfig = EncoderConfig(), device='cuda', mode: str = 'fp32'):
+        assert mode in ('fp32', 'bf16')
+        self.mode = mode
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -39,6 +58,21 @@ class GeometryEncoder:
         for i in range(max(self.res)):
             self._layers.append(self._fold(params, f'decoder.model.{i}.conv.conv') + (1, 1, True))
         self._n_enc = n_enc
+        self._ws = {}
+        if mode == 'bf16':
+            if cfg.in_channels != 1 or cfg.pre_filters <= 0 or cfg.pre_filters % 8 or cfg.preproc_type not in PREPROC_CODE:
+                raise RuntimeError('GeometryEncoder: the tensor-core path covers the sauto layout (1-channel input, 7x7 pre-layer)')
+            with torch.cuda.device(self.device):
+                w0 = self._layers[0][0]
+                self._w7 = w0.reshape(w0.shape[0], 49).contiguous()
+                self._wq = [None]
+                for (w, b, stride, pad, up) in self._layers[1:]:
+                    cout, cin = w.shape[0], w.shape[1]
+                    if cout % 16:
+                        raise RuntimeError('GeometryEncoder: tensor-core path needs out-channels in multiples of 16')
+                    wq = torch.empty((9, cout, _cs(cin)), dtype=torch.bfloat16, device=self.device)
+                    _lib.call('nbe_prepare_weights_bf16', _lib.ptr(w), _lib.ptr(wq), cout, cin, 3, 0, _lib.stream())
+                    self._wq.append(wq)
 
     def _fold(self, p, prefix):
         """conv -> eval BatchNorm  ==  conv with w' = w * g/sqrt(v+eps), b' = (b - m) * g/sqrt(v+eps) + beta."""
@@ -71,11 +105,105 @@ class GeometryEncoder:
             return 1 - x
         raise RuntimeError(f'Unknown preprocessing type "{t}"')
 
+    # ---- tensor-core path ----------------------------------------------------------------------------
+    def _workspace(self, B: int, H: int):
+        key = (B, H)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = []
+            h = H
+            for i, (w, b, stride, pad, up) in enumerate(self._layers):
+                if up:
+                    ws.append(torch.zeros((B, 2 * h + 2, 2 * h + 2, _cs(w.shape[1])), dtype=torch.bfloat16, device=self.device))
+                    h *= 2
+                else:
+                    h //= stride
+                # output of layer i, padded for the next conv
+                ws.append(torch.zeros((B, h + 2, h + 2, _cs(w.shape[0])), dtype=torch.bfloat16, device=self.device))
+            self._ws = {key: ws}                           # keep one batch size resident
+        return ws
+
+    def encode_into(self, geom, dests):
+        """Run the bf16 encoder and write feature map ``r`` (index into ``self.res``) into ``dests[r] = (tensor, c_off)``:
+        an NHWC bf16 tensor [B, R, R, cs] whose channels [c_off, c_off + C_r) receive the features (e.g. the generator's
+        concat buffers).  geom: [B,1,H,W] float32, 0 = stroke."""
+        assert self.mode == 'bf16'
+        _lib.require_cuda(geom, 'GeometryEncoder.encode_into')
+        geom = geom.to(torch.float32).contiguous()
+        B, _, H, W = geom.shape
+        assert H == W and (H & (H - 1)) == 0, 'square power-of-two patches'
+        res = self.res if isinstance(self.res, (list, tuple)) else [self.res]
+        max_res = max(res)
+        ws = self._workspace(B, H)
+        slope = float(self.cfg.neg_slope)
+        with torch.cuda.device(self.device):
+            st = _lib.stream()
+            wi = 0
+            w, b, _, _, _ = self._layers[0]
+            cur = ws[wi]; wi += 1
+            _lib.call('nbe_enc_conv7x7_bf16', _lib.ptr(geom), _lib.ptr(self._w7), _lib.ptr(b), _lib.ptr(cur), B, H, W, w.shape[0],
+                      cur.shape[3], slope, PREPROC_CODE[self.cfg.preproc_type], st)
+            _lib.call('nbe_reflect_border_nhwc_bf16', _lib.ptr(cur), B, H + 2, W + 2, w.shape[0], cur.shape[3], st)
+            h = H
+            cur_view = None            # (ptr, cs, C) of the latest un-padded feature map when it lives in a destination buffer
+            for i in range(1, self._n_enc + max_res):
+                w, b, stride, pad, up = self._layers[i]
+                cout = w.shape[0]
+                if up:
+                    src_ptr, src_cs, src_c = cur_view
+                    upbuf = ws[wi]; wi += 1
+                    _lib.call('nbe_bilinear2x_pad_nhwc_bf16', src_ptr, _lib.ptr(upbuf), B, h, h, src_c, src_cs, upbuf.shape[3], st)
+                    cur = upbuf
+                    h *= 2
+                ho = h // stride
+                feat_idx = i - (self._n_enc - 1)            # >= 0: this layer's output is feature map `feat_idx`
+                nxt = ws[wi]; wi += 1
+                if feat_idx >= 0 and feat_idx in res:
+                    dst, c_off = dests[res.index(feat_idx)]
+                    assert dst.dtype == torch.bfloat16 and dst.shape[:3] == (B, ho, ho) and dst.shape[3] >= c_off + cout
+                    y_ptr, y_cs, rp, ip = dst.data_ptr() + 2 * c_off, dst.shape[3], ho, ho * ho
+                    cur_view = (y_ptr, y_cs, cout)
+                    padded_out = None
+                else:
+                    y_cs, rp, ip = nxt.shape[3], ho + 2, (ho + 2) * (ho + 2)
+                    y_ptr = nxt.data_ptr() + 2 * ((ho + 2) + 1) * y_cs
+                    padded_out = nxt
+                    cur_view = None
+                _lib.call('nbe_conv_tc_bf16_ex', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cur.shape[3], cur.shape[3],
+                          cout, y_cs, 3, 1, stride, cur.shape[1], cur.shape[2], rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0,
+                          -1.0, None, st)
+                h = ho
+                if padded_out is not None:
+                    _lib.call('nbe_reflect_border_nhwc_bf16', _lib.ptr(padded_out), B, h + 2, h + 2, cout, padded_out.shape[3], st)
+                    cur = padded_out
+                elif i + 1 < self._n_enc + max_res and not self._layers[i + 1][4]:
+                    raise RuntimeError('GeometryEncoder: a feature map that feeds a non-upsampling layer must stay padded')
+        return dests
+
+    def _encode_bf16(self, geom, res) -> List[torch.Tensor]:
+        B, H = geom.shape[0], geom.shape[2]
+        rl = self.res if isinstance(self.res, (list, tuple)) else [self.res]
+        n_down = len(self.cfg.down_filters)
+        dests = []
+        for r in rl:
+            R = (H // (2 ** n_down)) * (2 ** r)
+            dests.append((torch.zeros((B, R, R, self.cfg.feature_channels(r)), dtype=torch.bfloat16, device=self.device), 0))
+        self.encode_into(geom, dests)
+        outs = []
+        for (tns, _), r in zip(dests, rl):
+            C, R = tns.shape[3], tns.shape[1]
+            o = torch.empty((B, C, R, R), dtype=torch.float32, device=self.device)
+            _lib.call('nbe_unpack_nchw_f32', _lib.ptr(tns), _lib.ptr(o), B, C, R, R, C, _lib.stream())
+            outs.append(o)
+        return outs
+
     def encode(self, geom, res=None) -> List[torch.Tensor]:
         """geom: [B,1,H,W] float, 0 = stroke, 1 = background -> list of float32 NCHW feature maps."""
         _lib.require_cuda(geom, 'GeometryEncoder.encode')
         if res is None:
             res = self.res
+        if self.mode == 'bf16' and res == self.res:
+            return self._encode_bf16(geom, res)
         x = self.preprocess(geom.to(torch.float32))
         results = []
         max_res = res if not isinstance(res, (list, tuple)) else max(res)

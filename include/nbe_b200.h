@@ -140,6 +140,18 @@ int nbe_conv_tc_bf16(const void* x, const void* wq, void* y,
                      const float* bias, float alpha, float gain, float clamp, const float* next_scale,
                      nbe_stream_t stream);
 
+/* Same kernel with (a) an input pixel stride of 1 or 2 (TMA traversal stride; needs valid = 1, the input then has
+ * at least (O-1)*in_stride + K rows/cols; in_h/in_w give its real size, 0 = exactly that) and (b) explicit output pitches in pixels, so that the epilogue can write into the
+ * interior of a larger (e.g. reflect-padded) NHWC buffer: element (n,oy,ox,c) goes to
+ * y[(n*y_img_pitch + oy*y_row_pitch + ox)*y_cs + c].  Used by the geometry encoder
+ * (forger/experimental/autoenc/simple_autoencoder.py:95-109,155-199: conv3x3 stride 1/2 + folded BN + LeakyReLU). */
+int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
+                        int N, int OH, int OW, int Cin, int x_cs, int Cout, int y_cs, int K, int valid,
+                        int in_stride, int in_h, int in_w, int64_t y_row_pitch, int64_t y_img_pitch,
+                        const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                        const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                        nbe_stream_t stream);
+
 /* Fused ToRGB (1x1 modulated conv, no demodulation) + bias + clamp + softmax(3) + triad colour mix.
  *   t[k] = clamp(sum_c x[c] * w[k,c] * styles[n,c] + bias[k], +-clamp);  uvs = softmax(t);  img[c] = sum_k uvs[k]*colors[n,c,k]
  * Replaces: ToRGBColorTriadLayer.forward SG2/training/networks.py:451-485.
@@ -148,6 +160,24 @@ int nbe_conv_tc_bf16(const void* x, const void* wq, void* y,
 int nbe_torgb_triad(const void* x, int x_is_bf16, int x_cs, const float* w, const float* styles, const float* bias,
                     const float* colors, float clamp, float* img, float* uvs, int N, int C, int H, int W,
                     nbe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Geometry encoder, tensor-core path (forger/experimental/autoenc/simple_autoencoder.py:95-126,155-199,251-261).
+ * Activations are NHWC bf16 buffers that carry their 1-pixel reflect padding explicitly, [N, H+2, W+2, cs].
+ */
+
+/* First layer: conv7x7(1 -> Cout, reflect pad 3) + folded eval-BatchNorm bias + LeakyReLU(neg_slope) on x [N,1,H,W] float32
+ * (preproc: 0 none, 1 'inverse', 2 '-11inverse', base.py:32-58); writes the interior of y [N,H+2,W+2,y_cs] bf16.
+ * w: [Cout,49] float32 with BN folded. */
+int nbe_enc_conv7x7_bf16(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
+                         int y_cs, float neg_slope, int preproc, nbe_stream_t stream);
+
+/* Fill the 1-pixel border of buf [N,Hp,Wp,cs] (first C channels) by reflection of its interior (torch padding_mode='reflect'). */
+int nbe_reflect_border_nhwc_bf16(void* buf, int N, int Hp, int Wp, int C, int cs, nbe_stream_t stream);
+
+/* out [N,2h+2,2w+2,out_cs] = reflect_pad1( bilinear_x2(x [N,h,w,xs_c], align_corners=True) )   (ScaleUp.up + conv padding) */
+int nbe_bilinear2x_pad_nhwc_bf16(const void* x, void* out, int N, int h, int w, int C, int xs_c, int out_cs,
+                                 nbe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Engine composite and canvas placement.

@@ -58,6 +58,24 @@ def test_encoder_matches_golden(bundles, golden_inputs):
     assert enc.featuremap_resolution(128, 0) == 16 and enc.featuremap_resolution(128, 1) == 32
 
 
+def test_encoder_bf16_tensor_core_path(bundles, golden_inputs):
+    """bf16 encoder (7x7 on CUDA cores, 3x3 layers on tcgen05 incl. TMA stride 2, reflect borders, bilinear x2):
+    features within bf16 rounding of the fp32 reference."""
+    from brushstroke_engine_b200.geo_encoder import GeometryEncoder
+    cfg, ecfg, gp, ep = bundles
+    g, gf = golden_inputs
+    enc = GeometryEncoder(ep, ecfg, DEV, mode='bf16')
+    g0, g1 = enc.encode(t(g['geom']).to(DEV))
+    assert g0.shape == (2, 16, 16, 16) and g1.shape == (2, 256, 32, 32)
+    for got, ref in ((g0, gf[0]), (g1, gf[1])):
+        err = md(got, ref)
+        assert err < 0.03 * float(ref.abs().max()), (err, float(ref.abs().max()))
+    # a second batch size re-plans the workspace; padding channels must stay zero
+    geom5 = t(g['geom']).repeat(3, 1, 1, 1)[:5].to(DEV)
+    h0, h1 = enc.encode(geom5)
+    assert md(h0[:2], g0) == 0 and md(h1[:2], g1) == 0
+
+
 def test_mapping_matches_golden(G32, golden_inputs):
     g, _ = golden_inputs
     ws = G32.mapping(t(g['z']).to(DEV), None)           # z is float64, as GanPaintEngine.random_style makes it

@@ -11,7 +11,7 @@ mode = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
 cfg, ecfg = P.GeneratorConfig(), P.EncoderConfig()
 gp = P.init_generator_params(cfg, 0, 0.1); ep = P.init_encoder_params(ecfg, 1, 0.1)
 G = Generator(gp, cfg, 'cuda', mode=mode)
-enc = GeometryEncoder(ep, ecfg, 'cuda')
+enc = GeometryEncoder(ep, ecfg, 'cuda', mode=mode)
 z = torch.randn(B, 64, device='cuda', dtype=torch.float64)
 geom = (torch.rand(B, 1, 128, 128, device='cuda') > 0.2).float()
 pos = torch.randint(0, 4000, (B, 2), device='cuda')
@@ -25,11 +25,16 @@ def timed_call(name, *args):
 def run(timed):
     _lib.call = timed_call if timed else orig_call
     import brushstroke_engine_b200.generator as gm, brushstroke_engine_b200.conv2d_resample as cr, brushstroke_engine_b200.modconv as mc, brushstroke_engine_b200.upfirdn2d as up, brushstroke_engine_b200.bias_act as ba
-    for m in (gm, cr, mc, up, ba):
+    import brushstroke_engine_b200.geo_encoder as ge
+    for m in (gm, cr, mc, up, ba, ge):
         m._lib.call = _lib.call
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True); t2 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    gf = enc.encode(geom)
+    if mode == 'bf16':
+        gf, dests = G.alloc_injection(B)
+        enc.encode_into(geom, dests)
+    else:
+        gf = enc.encode(geom)
     t1.record()
     img, dbg = G(z, None, gf, positions=pos, return_debug_data=True, noise_mode='const')
     t2.record(); torch.cuda.synchronize()
@@ -43,7 +48,8 @@ tot = 0
 for name, args, s, e in records:
     ms = s.elapsed_time(e); tot += ms
     shape = ''
-    if name == 'nbe_conv_tc_bf16': shape = f'N={args[3]} R={args[4]} Cin={args[6]} valid={args[11]}'
+    if name == 'nbe_conv_tc_bf16_ex': shape = f'N={args[3]} R={args[4]} Cin={args[6]} Cout={args[8]} stride={args[12]}'
+    elif name == 'nbe_conv_tc_bf16': shape = f'N={args[3]} R={args[4]} Cin={args[6]} valid={args[11]}'
     elif name == 'nbe_conv2d_f32': shape = f'N={args[3]} Cin={args[4]} H={args[5]} Cout={args[7]} K={args[8]} s={args[10]}'
     elif name == 'nbe_upsample2x_nhwc_bf16': shape = f'N={args[4]} H={args[5]} C={args[7]}'
     if ms > 0.02: print(f'  {name:28s} {ms:8.3f} ms  {shape}')
