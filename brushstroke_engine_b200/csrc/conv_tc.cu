@@ -194,6 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 __nv_bfloat16* yp = p.y + ((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs + c0;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
+                    if (c0 + g * 8 >= p.Cout) break;                 // Cout is a multiple of 16, chunks are 32 wide
                     int4 out;
                     __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
 #pragma unroll
