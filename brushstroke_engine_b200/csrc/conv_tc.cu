@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace nbe {
 
@@ -227,6 +228,203 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-resident persistent variant for the 128-wide layers (OW % 128 == 0, Cin_pad == 128, Cout == 128, 3x3, stride 1):
+// the per-tap kernel above is bound by L2->SM bandwidth (every 128x128x64 MMA block streams 16 KiB of A and 16 KiB of
+// B: ~128 B/clk/SM wanted, ~40 B/clk/SM available chip-wide), so this kernel cuts the traffic per FLOP ~3x:
+//  * one CTA per SM, persistent; a work item is TWO output rows (2 x 128 pixels = two TMEM accumulators) of one image;
+//  * for each 64-channel chunk the FOUR input rows those outputs touch are loaded ONCE (130 pixels each, halo included)
+//    and kept in shared memory; the three horizontal taps are the same smem rows read through UMMA descriptors whose
+//    start address is shifted by kw pixels (kw * 128 B -- the 128-byte swizzle is a function of the absolute smem
+//    address, so a row-shifted start reads exactly what TMA wrote);
+//  * every weight tile (tap, chunk) is streamed once per work item through a 4-deep ring and feeds 8 MMAs
+//    (2 output rows x 4 K-steps) instead of 4;
+//  * accumulators are double-buffered in TMEM (2 x 2 x 128 columns = all 512), so the epilogue of item i overlaps
+//    the MMAs of item i+1; per-image epilogue vectors (demod, bias, next-layer styles) are staged in smem.
+constexpr int R_ABUF = 17 * 1024;                                  // 130 px x 128 B = 16640 B, padded to a 1 KiB multiple
+constexpr int R_AROW_BYTES = 130 * 128;
+constexpr int R_BSTAGES = 4;
+constexpr int R_BBYTES = 128 * 128;
+
+struct ConvRowParams {
+    __nv_bfloat16* y;
+    int N, OH, OW, y_cs;
+    int pad_off;                                                    // -1: zero padding 1 ('same'); 0: input already has the halo ('valid')
+    long long y_row_pitch, y_img_pitch;
+    int items_per_row, items_per_img, total_items;                  // item = (n, row pair, 128-px x segment)
+    const float* dcoef; const float* noise; long long noise_sn; float noise_gain;
+    const float* bias; float alpha, gain, clamp; const float* next_scale;
+    uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvRowParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                         // [2 chunks][4 rows][R_ABUF]
+    uint8_t* smem_b = smem + 8 * R_ABUF;                            // [R_BSTAGES][R_BBYTES]
+    float* s_vec = reinterpret_cast<float*>(smem_b + R_BSTAGES * R_BBYTES);   // [3][128]: dcoef, bias, next_scale of the current image
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + 3 * 128);
+    uint64_t* a_full = bars;            // [2]
+    uint64_t* a_empty = bars + 2;       // [2]
+    uint64_t* b_full = bars + 4;        // [R_BSTAGES]
+    uint64_t* b_empty = bars + 4 + R_BSTAGES;
+    uint64_t* acc_full = bars + 4 + 2 * R_BSTAGES;      // [2]
+    uint64_t* acc_empty = acc_full + 2;                 // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1);
+                                      mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+        for (int i = 0; i < R_BSTAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            uint32_t a_phase[2] = {0, 0};
+            int bs = 0; uint32_t b_phase = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int n = item / p.items_per_img;
+                const int rem = item - n * p.items_per_img;
+                const int yp = rem / p.items_per_row, xs = rem - yp * p.items_per_row;
+                const int y0 = yp * 2, x0 = xs * 128;
+                for (int c = 0; c < 2; ++c) {
+                    mbar_wait(smem_u32(&a_empty[c]), a_phase[c] ^ 1);
+                    const uint32_t full = smem_u32(&a_full[c]);
+                    mbar_expect_tx(full, 4 * R_AROW_BYTES);
+                    for (int j = 0; j < 4; ++j)
+                        tma_load_4d(smem_u32(smem_a + (c * 4 + j) * R_ABUF), &tmap_a, full, c * 64, x0 + p.pad_off, y0 + j + p.pad_off, n);
+                    a_phase[c] ^= 1;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(smem_u32(&b_empty[bs]), b_phase ^ 1);
+                        const uint32_t bf = smem_u32(&b_full[bs]);
+                        mbar_expect_tx(bf, R_BBYTES);
+                        tma_load_3d(smem_u32(smem_b + bs * R_BBYTES), &tmap_b, bf, c * 64, 0, tap);
+                        if (++bs == R_BSTAGES) { bs = 0; b_phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            uint32_t a_phase[2] = {0, 0}, acc_phase[2] = {0, 0};
+            int bs = 0; uint32_t b_phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+                const int ab = it & 1;
+                mbar_wait(smem_u32(&acc_empty[ab]), acc_phase[ab] ^ 1);       // epilogue has drained this accumulator pair
+                tcgen05_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(ab * 256);
+                for (int c = 0; c < 2; ++c) {
+                    mbar_wait(smem_u32(&a_full[c]), a_phase[c]);
+                    tcgen05_fence_after();
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        mbar_wait(smem_u32(&b_full[bs]), b_phase);
+                        tcgen05_fence_after();
+                        const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b + bs * R_BBYTES));
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            // output row r takes input row r + kh; the horizontal tap is a kw-pixel (kw * 128 B) shift of the start address
+                            const uint64_t a_desc = umma_smem_desc(smem_u32(smem_a + (c * 4 + r + kh) * R_ABUF) + (uint32_t)(kw * 128));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d0 + (uint32_t)(r * 128), a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc,
+                                          (c | tap | k) != 0);
+                        }
+                        umma_commit(smem_u32(&b_empty[bs]));
+                        if (++bs == R_BSTAGES) { bs = 0; b_phase ^= 1; }
+                    }
+                    umma_commit(smem_u32(&a_empty[c]));             // the four input rows of this chunk may be overwritten
+                    a_phase[c] ^= 1;
+                }
+                umma_commit(smem_u32(&acc_full[ab]));
+                acc_phase[ab] ^= 1;
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5) ==============================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;                                // pixel x within the 128-px segment
+        const int et = threadIdx.x - 64;                            // 0..127
+        uint32_t acc_phase[2] = {0, 0};
+        int it = 0, cur_n = -1;
+        const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const int n = item / p.items_per_img;
+            const int rem = item - n * p.items_per_img;
+            const int yp = rem / p.items_per_row, xs = rem - yp * p.items_per_row;
+            const int y0 = yp * 2, ox = xs * 128 + m;
+            if (n != cur_n) {                                       // per-image epilogue vectors -> smem (epilogue warps only)
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone is done reading the previous image's vectors
+                s_vec[et] = p.dcoef ? p.dcoef[(long long)n * 128 + et] : 1.f;
+                s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
+                s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * 128 + et] : 1.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cur_n = n;
+            }
+            mbar_wait(smem_u32(&acc_full[ab]), acc_phase[ab]);
+            acc_phase[ab] ^= 1;
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int r = 0; r < 2; ++r) {
+                const int oy = y0 + r;
+                float nz = 0.f;
+                if (p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
+                __nv_bfloat16* yrow = p.y + ((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256 + r * 128 + c0), v);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        int4 out;
+                        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float rr[2];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int o = c0 + g * 8 + e * 2 + h;
+                                float a = __uint_as_float(v[g * 8 + e * 2 + h]) * s_vec[o] + nz + s_vec[128 + o];
+                                a *= (a > 0.f) ? pos_gain : neg_gain;
+                                if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
+                                rr[h] = a * s_vec[256 + o];
+                            }
+                            o2[e] = __floats2bfloat162_rn(rr[0], rr[1]);
+                        }
+                        *reinterpret_cast<int4*>(yrow + c0 + g * 8) = out;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&acc_empty[ab])) : "memory");
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // [Cout][Cin][K][K] f32 -> [KK][Cout][Cin_pad] bf16 (flip = true convolution)
 __global__ void prepare_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wq, int Cout, int Cin, int Cin_pad, int KK, int flip) {
     const int64_t total = (int64_t)KK * Cout * Cin_pad;
@@ -331,6 +529,45 @@ extern "C" int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
     // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), K-major A and B, N >> 3 at 17, M >> 4 at 24
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.tmem_cols = Cout <= 32 ? 32 : Cout <= 64 ? 64 : Cout <= 128 ? 128 : 256;
+
+    // ---- 128-wide layers: row-resident persistent kernel (see conv_tc_row128_kernel) ----
+    static const bool force_v1 = getenv("NBE_CONV_TC_V1") != nullptr;
+    if (!force_v1 && K == 3 && in_stride == 1 && Cout == 128 && Cin_pad == 128 && OW % 128 == 0 && OH % 2 == 0) {
+        ConvRowParams r;
+        r.y = (__nv_bfloat16*)y; r.N = N; r.OH = OH; r.OW = OW; r.y_cs = y_cs; r.pad_off = p.pad_off;
+        r.y_row_pitch = y_row_pitch; r.y_img_pitch = y_img_pitch;
+        r.items_per_row = OW / 128; r.items_per_img = (OH / 2) * r.items_per_row;
+        const int64_t total = (int64_t)N * r.items_per_img;
+        NBE_REQUIRE(total <= INT32_MAX, "conv_tc: too many work items");
+        r.total_items = (int)total;
+        r.dcoef = dcoef; r.noise = noise; r.noise_sn = noise_sn; r.noise_gain = noise_gain;
+        r.bias = bias; r.alpha = alpha; r.gain = gain; r.clamp = clamp; r.next_scale = next_scale; r.idesc = p.idesc;
+        CUtensorMap ta, tb;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)N};
+            cuuint64_t strides[3] = {(cuuint64_t)x_cs * 2, (cuuint64_t)IW * x_cs * 2, (cuuint64_t)IH * IW * x_cs * 2};
+            cuuint32_t box[4] = {64, 130, 1, 1};
+            int st = make_tmap(&ta, x, 4, dims, strides, box, "activation rows");
+            if (st) return st;
+        }
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, (cuuint64_t)Cout, 9};
+            cuuint64_t strides[2] = {(cuuint64_t)Cin_pad * 2, (cuuint64_t)Cout * Cin_pad * 2};
+            cuuint32_t box[3] = {64, 128, 1};
+            int st = make_tmap(&tb, wq, 3, dims, strides, box, "weights");
+            if (st) return st;
+        }
+        const size_t rsmem = 1024 + 8 * R_ABUF + R_BSTAGES * R_BBYTES + 3 * 128 * sizeof(float) + 256;
+        static std::once_flag row_once;
+        static cudaError_t row_err = cudaSuccess;
+        std::call_once(row_once, [] {
+            row_err = cudaFuncSetAttribute(conv_tc_row128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        });
+        if (row_err != cudaSuccess) return fail(NBE_ECUDA, "conv_tc: cudaFuncSetAttribute(row128): %s", cudaGetErrorString(row_err));
+        const int grid = total < kNumSMs ? (int)total : kNumSMs;
+        conv_tc_row128_kernel<<<grid, TC_THREADS, rsmem, (cudaStream_t)stream>>>(ta, tb, r);
+        return launched("conv_tc_row128_kernel");
+    }
 
     CUtensorMap tmap_a, tmap_b;
     {

@@ -43,7 +43,7 @@ def test_pack_unpack_roundtrip():
     assert md(unpack(d[..., 8:].contiguous(), 37), ref) == 0
 
 
-@pytest.mark.parametrize('R,cin,B', [(4, 128, 3), (8, 128, 5), (16, 128, 2), (32, 144, 2), (64, 384, 1), (128, 128, 1), (4, 128, 1), (8, 64, 17)])
+@pytest.mark.parametrize('R,cin,B', [(4, 128, 3), (8, 128, 5), (16, 128, 2), (32, 144, 2), (64, 384, 1), (128, 128, 1), (4, 128, 1), (8, 64, 17), (128, 128, 3), (128, 100, 2), (256, 128, 1)])
 @pytest.mark.parametrize('valid', [False, True])
 def test_conv_tc_matches_fp64_conv(R, cin, B, valid):
     g = torch.Generator().manual_seed(R * 7 + cin + B)
