@@ -255,6 +255,9 @@ struct ConvRowParams {
     const float* dcoef; const float* noise; long long noise_sn; float noise_gain;
     const float* bias; float alpha, gain, clamp; const float* next_scale;
     uint32_t idesc;
+    // optional fused ToRGB + triad colour mix (ToRGBColorTriadLayer, networks.py:451-485) on the activated output
+    const float* rgb_w; const float* rgb_styles; const float* rgb_bias; const float* rgb_colors; float rgb_clamp;
+    float* img; float* uvs; int write_y;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -263,8 +266,8 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                         // [2 chunks][4 rows][R_ABUF]
     uint8_t* smem_b = smem + 8 * R_ABUF;                            // [R_BSTAGES][R_BBYTES]
-    float* s_vec = reinterpret_cast<float*>(smem_b + R_BSTAGES * R_BBYTES);   // [3][128]: dcoef, bias, next_scale of the current image
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + 3 * 128);
+    float* s_vec = reinterpret_cast<float*>(smem_b + R_BSTAGES * R_BBYTES);   // [6][128]: dcoef, bias, next_scale, 3 x modulated ToRGB weights of the current image
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + 6 * 128);
     uint64_t* a_full = bars;            // [2]
     uint64_t* a_empty = bars + 2;       // [2]
     uint64_t* b_full = bars + 4;        // [R_BSTAGES]
@@ -375,6 +378,10 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 s_vec[et] = p.dcoef ? p.dcoef[(long long)n * 128 + et] : 1.f;
                 s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
                 s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * 128 + et] : 1.f;
+                if (p.rgb_w) {
+                    const float st = p.rgb_styles[(long long)n * 128 + et];
+                    s_vec[384 + et] = p.rgb_w[et] * st; s_vec[512 + et] = p.rgb_w[128 + et] * st; s_vec[640 + et] = p.rgb_w[256 + et] * st;
+                }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 cur_n = n;
             }
@@ -387,6 +394,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 float nz = 0.f;
                 if (p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
                 __nv_bfloat16* yrow = p.y + ((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs;
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t v[32];
@@ -404,11 +412,37 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                 float a = __uint_as_float(v[g * 8 + e * 2 + h]) * s_vec[o] + nz + s_vec[128 + o];
                                 a *= (a > 0.f) ? pos_gain : neg_gain;
                                 if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
+                                if (p.rgb_w) {
+                                    t0 = fmaf(a, s_vec[384 + o], t0); t1 = fmaf(a, s_vec[512 + o], t1); t2 = fmaf(a, s_vec[640 + o], t2);
+                                }
                                 rr[h] = a * s_vec[256 + o];
                             }
                             o2[e] = __floats2bfloat162_rn(rr[0], rr[1]);
                         }
-                        *reinterpret_cast<int4*>(yrow + c0 + g * 8) = out;
+                        if (p.write_y) *reinterpret_cast<int4*>(yrow + c0 + g * 8) = out;
+                    }
+                }
+                if (p.rgb_w) {
+                    t0 += p.rgb_bias[0]; t1 += p.rgb_bias[1]; t2 += p.rgb_bias[2];
+                    if (p.rgb_clamp >= 0.f) {
+                        t0 = fminf(fmaxf(t0, -p.rgb_clamp), p.rgb_clamp); t1 = fminf(fmaxf(t1, -p.rgb_clamp), p.rgb_clamp);
+                        t2 = fminf(fmaxf(t2, -p.rgb_clamp), p.rgb_clamp);
+                    }
+                    const float mx = fmaxf(t0, fmaxf(t1, t2));
+                    const float e0 = expf(t0 - mx), e1 = expf(t1 - mx), e2 = expf(t2 - mx);
+                    const float inv = 1.f / (e0 + e1 + e2);
+                    const float u0 = e0 * inv, u1 = e1 * inv, u2 = e2 * inv;
+                    const long long plane = (long long)p.OH * p.OW, pix = (long long)oy * p.OW + ox;
+                    const float* col = p.rgb_colors + (long long)n * 9;
+                    if (p.uvs) {
+                        float* up = p.uvs + (long long)n * 3 * plane + pix;
+                        up[0] = u0; up[plane] = u1; up[2 * plane] = u2;
+                    }
+                    if (p.img) {
+                        float* ip = p.img + (long long)n * 3 * plane + pix;
+                        ip[0] = u0 * col[0] + u1 * col[1] + u2 * col[2];
+                        ip[plane] = u0 * col[3] + u1 * col[4] + u2 * col[5];
+                        ip[2 * plane] = u0 * col[6] + u1 * col[7] + u2 * col[8];
                     }
                 }
             }
@@ -491,12 +525,14 @@ extern "C" int nbe_conv_tc_bf16(const void* x, const void* wq, void* y,
                                dcoef, noise, noise_sn, noise_gain, bias, alpha, gain, clamp, next_scale, stream);
 }
 
-extern "C" int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
-                                   int N, int OH, int OW, int Cin, int x_cs, int Cout, int y_cs, int K, int valid,
-                                   int in_stride, int in_h, int in_w, int64_t y_row_pitch, int64_t y_img_pitch,
-                                   const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
-                                   const float* bias, float alpha, float gain, float clamp, const float* next_scale,
-                                   nbe_stream_t stream) {
+struct TorgbArgs { const float* w; const float* styles; const float* bias; const float* colors; float clamp; float* img; float* uvs; int write_y; };
+
+static int conv_tc_impl(const void* x, const void* wq, void* y,
+                        int N, int OH, int OW, int Cin, int x_cs, int Cout, int y_cs, int K, int valid,
+                        int in_stride, int in_h, int in_w, int64_t y_row_pitch, int64_t y_img_pitch,
+                        const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                        const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                        const TorgbArgs* rgb, nbe_stream_t stream) {
     NBE_REQUIRE(in_stride == 1 || in_stride == 2, "conv_tc: input stride must be 1 or 2");
     NBE_REQUIRE(in_stride == 1 || valid, "conv_tc: strided convolution needs a pre-padded input (valid = 1)");
     NBE_REQUIRE(y_row_pitch >= OW && y_img_pitch >= y_row_pitch * OH, "conv_tc: bad output pitches");
@@ -542,6 +578,12 @@ extern "C" int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
         r.total_items = (int)total;
         r.dcoef = dcoef; r.noise = noise; r.noise_sn = noise_sn; r.noise_gain = noise_gain;
         r.bias = bias; r.alpha = alpha; r.gain = gain; r.clamp = clamp; r.next_scale = next_scale; r.idesc = p.idesc;
+        r.rgb_w = nullptr; r.rgb_styles = nullptr; r.rgb_bias = nullptr; r.rgb_colors = nullptr; r.rgb_clamp = -1.f;
+        r.img = nullptr; r.uvs = nullptr; r.write_y = 1;
+        if (rgb) {
+            r.rgb_w = rgb->w; r.rgb_styles = rgb->styles; r.rgb_bias = rgb->bias; r.rgb_colors = rgb->colors; r.rgb_clamp = rgb->clamp;
+            r.img = rgb->img; r.uvs = rgb->uvs; r.write_y = rgb->write_y;
+        }
         CUtensorMap ta, tb;
         {
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)N};
@@ -569,6 +611,8 @@ extern "C" int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
         return launched("conv_tc_row128_kernel");
     }
 
+    if (rgb) return fail(NBE_EUNSUPPORTED, "conv_tc: the fused ToRGB epilogue needs a 128-wide layer (OW %% 128 == 0, Cin <= 128, Cout == 128)");
+
     CUtensorMap tmap_a, tmap_b;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)N};
@@ -595,4 +639,27 @@ extern "C" int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
     if (attr_err != cudaSuccess) return fail(NBE_ECUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     conv_tc_kernel<<<(int)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, p);
     return launched("conv_tc_kernel");
+}
+
+extern "C" int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
+                                   int N, int OH, int OW, int Cin, int x_cs, int Cout, int y_cs, int K, int valid,
+                                   int in_stride, int in_h, int in_w, int64_t y_row_pitch, int64_t y_img_pitch,
+                                   const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                                   const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                                   nbe_stream_t stream) {
+    return conv_tc_impl(x, wq, y, N, OH, OW, Cin, x_cs, Cout, y_cs, K, valid, in_stride, in_h, in_w, y_row_pitch, y_img_pitch,
+                        dcoef, noise, noise_sn, noise_gain, bias, alpha, gain, clamp, next_scale, nullptr, stream);
+}
+
+extern "C" int nbe_conv_tc_bf16_torgb(const void* x, const void* wq, void* y,
+                                      int N, int OH, int OW, int Cin, int x_cs, int Cout, int y_cs, int valid,
+                                      const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                                      const float* bias, float alpha, float gain, float clamp,
+                                      const float* rgb_w, const float* rgb_styles, const float* rgb_bias, const float* rgb_colors,
+                                      float rgb_clamp, float* img, float* uvs, int write_y, nbe_stream_t stream) {
+    NBE_REQUIRE(rgb_w && rgb_styles && rgb_bias && rgb_colors && (img || uvs), "conv_tc_torgb: null ToRGB tensor");
+    NBE_REQUIRE(y || !write_y, "conv_tc_torgb: feature output requested without a buffer");
+    TorgbArgs a{rgb_w, rgb_styles, rgb_bias, rgb_colors, rgb_clamp, img, uvs, write_y};
+    return conv_tc_impl(x, wq, y ? y : (void*)x, N, OH, OW, Cin, x_cs, Cout, y_cs, 3, valid, 1, 0, 0, OW, (int64_t)OH * OW,
+                        dcoef, noise, noise_sn, noise_gain, bias, alpha, gain, clamp, nullptr, &a, stream);
 }

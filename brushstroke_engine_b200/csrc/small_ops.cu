@@ -109,8 +109,10 @@ unpack_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ ds
 // ---------------------------------------------------------------------------------------------
 // FIR-first x2 upsample on NHWC bf16:  U[n, uy, ux, c] = sum over the (<=2)x(<=2) taps with even parity of
 //   g[a,b] * x[n, (uy+a-3)/2, (ux+b-3)/2, c] * scale[n,c],   g = f flipped * 4,  U is (2H+2) x (2W+2).
-// One thread = one output pixel x 8 channels (16-byte vector); consecutive threads walk the channel
-// dimension so both the loads (4 neighbouring input pixels) and the store are fully coalesced.
+// The four outputs of a 2x2 output quad (uy = 2q, 2q+1; ux = 2p, 2p+1) read the SAME 2x2 input pixels
+// (rows q-1, q; cols p-1, p), so one thread = one quad x 8 channels: 4 x 16-byte loads, 16 tap products per channel,
+// 4 x 16-byte stores.  Consecutive threads walk the channel vectors of a quad, then the quads of a row: loads and
+// stores are whole 32-byte sectors.  HBM-bound: (H*W + (2H+2)(2W+2)) * C * 2 bytes per image.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 upsample2x_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ f, const float* __restrict__ scale,
@@ -121,52 +123,67 @@ upsample2x_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
         s_g[threadIdx.x] = f[(3 - a) * 4 + (3 - b)] * 4.f;          // flip_filter = False, gain = up^2
     }
     __syncthreads();
-    const int CV = C / 8;
-    const int UH = 2 * H + 2, UW = 2 * W + 2;
-    const int64_t total = (int64_t)N * UH * UW * CV;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(idx % CV);
-        int64_t t = idx / CV;
-        const int ux = (int)(t % UW); t /= UW;
-        const int uy = (int)(t % UH);
-        const int n = (int)(t / UH);
-        float acc[8];
+    const int CV = C >> 3;
+    const int QW = W + 1;                                           // quads per output row
+    const int UW = 2 * W + 2, UH = 2 * H + 2;
+    const int q = blockIdx.x % (H + 1);                             // quad row
+    const int n = blockIdx.x / (H + 1);
+    const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (idx >= QW * CV) return;
+    const int cv = idx % CV, pq = idx / CV;
+    // input pixels (q-1, q) x (pq-1, pq); out-of-range -> 0
+    float in[2][2][8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        // taps a with (uy + a - 3) even: a0 = (uy + 1) & 1, a0 + 2
+    for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-        for (int da = 0; da < 2; ++da) {
-            const int a = ((uy + 1) & 1) + 2 * da;
-            const int iy = (uy + a - 3) >> 1;
-            if (iy < 0 || iy >= H) continue;
-#pragma unroll
-            for (int db = 0; db < 2; ++db) {
-                const int b = ((ux + 1) & 1) + 2 * db;
-                const int ix = (ux + b - 3) >> 1;
-                if (ix < 0 || ix >= W) continue;
-                const float g = s_g[a * 4 + b];
-                const int4 raw = *reinterpret_cast<const int4*>(x + (((int64_t)n * H + iy) * W + ix) * xs_c + cv * 8);
+        for (int dx = 0; dx < 2; ++dx) {
+            const int iy = q - 1 + dy, ix = pq - 1 + dx;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                const int4 raw = ld_stream16(x + (((long long)n * H + iy) * W + ix) * xs_c + cv * 8);
                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float2 v = __bfloat1622float2(h2[k]);
-                    acc[2 * k] = fmaf(g, v.x, acc[2 * k]);
-                    acc[2 * k + 1] = fmaf(g, v.y, acc[2 * k + 1]);
+                    const float2 v = __bfloat1622float2(h2[k]);
+                    in[dy][dx][2 * k] = v.x; in[dy][dx][2 * k + 1] = v.y;
                 }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) in[dy][dx][k] = 0.f;
             }
         }
-        if (scale) {
-            const float4 s0 = *reinterpret_cast<const float4*>(scale + (int64_t)n * C + cv * 8);
-            const float4 s1 = *reinterpret_cast<const float4*>(scale + (int64_t)n * C + cv * 8 + 4);
-            acc[0] *= s0.x; acc[1] *= s0.y; acc[2] *= s0.z; acc[3] *= s0.w;
-            acc[4] *= s1.x; acc[5] *= s1.y; acc[6] *= s1.z; acc[7] *= s1.w;
-        }
-        int4 outv;
-        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
+    float sc[8];
+    if (scale) {
+        const float4 s0 = *reinterpret_cast<const float4*>(scale + (long long)n * C + cv * 8);
+        const float4 s1 = *reinterpret_cast<const float4*>(scale + (long long)n * C + cv * 8 + 4);
+        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+    } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o2[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
-        *reinterpret_cast<int4*>(u + (((int64_t)n * UH + uy) * UW + ux) * C + cv * 8) = outv;
+        for (int k = 0; k < 8; ++k) sc[k] = 1.f;
     }
+    // output (uy = 2q + py, ux = 2pq + px): taps a = ((uy+1)&1) + 2*da -> input row (uy + a - 3) >> 1 = q - 1 + da
+    // (py = 0: a = 1 + 2da ; py = 1: a = 2da), likewise for columns.
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+            for (int da = 0; da < 2; ++da)
+#pragma unroll
+                for (int db = 0; db < 2; ++db) {
+                    const float g = s_g[((1 - py) + 2 * da) * 4 + (1 - px) + 2 * db];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(g, in[da][db][k], acc[k]);
+                }
+            int4 outv;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o2[k] = __floats2bfloat162_rn(acc[2 * k] * sc[2 * k], acc[2 * k + 1] * sc[2 * k + 1]);
+            const int uy = 2 * q + py, ux = 2 * pq + px;
+            st_stream16(u + (((long long)n * UH + uy) * UW + ux) * C + cv * 8, outv);
+        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,10 +351,11 @@ extern "C" int nbe_upsample2x_nhwc_bf16(const void* x, const float* f, const flo
     NBE_REQUIRE(C % 8 == 0 && xs_c % 8 == 0 && xs_c >= C, "upsample2x: channels must be a multiple of 8");
     NBE_REQUIRE((((uintptr_t)x | (uintptr_t)u) & 15) == 0, "upsample2x: tensors must be 16-byte aligned");
     if (N == 0) return NBE_OK;
-    const int64_t total = (int64_t)N * (2 * H + 2) * (2 * W + 2) * (C / 8);
-    int64_t blocks = (total + 255) / 256;
-    if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-    upsample2x_nhwc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+    NBE_REQUIRE((int64_t)N * (H + 1) <= INT32_MAX, "upsample2x: too many rows");
+    const int per_row = (W + 1) * (C / 8);
+    dim3 grid(N * (H + 1), (per_row + 255) / 256);
+    NBE_REQUIRE(grid.y <= 65535u, "upsample2x: rows too wide");
+    upsample2x_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, f, scale, (__nv_bfloat16*)u, N, H, W, C, xs_c);
     return launched("upsample2x_nhwc_kernel");
 }

@@ -394,7 +394,21 @@ class Generator:
                 y = torch.empty((B, res, res, y_cs), dtype=bf, device=dev)
             noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp,
                                                 noise_buffers.get(f'{conv1.name}.noise_const'))
-            self._conv_tc(xin, conv1, B, res, conv1.cin, y, y_cs, False, dcoefs[conv1.name], noise, nsn, ngain, None)
+            is_last = res == cfg.img_resolution
+            fused_rgb = is_last and res not in blended_features and res % 128 == 0 and conv1.cout == 128 and conv1.cin <= 128
+            if fused_rgb:
+                # last layer: ToRGB + softmax + colour mix ride in the conv epilogue; the 128-channel map is only stored on request
+                need_y = res in return_features
+                img = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
+                uvs = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
+                clamp = cfg.conv_clamp if cfg.conv_clamp is not None else -1
+                _lib.call('nbe_conv_tc_bf16_torgb', _lib.ptr(xin), _lib.ptr(conv1.wq), _lib.ptr(y) if need_y else None, B, res, res,
+                          conv1.cin, conv1.cin, conv1.cout, y_cs, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
+                          _lib.ptr(conv1.bias), 0.2, SQRT2, float(clamp), _lib.ptr(self._rgb_w), _lib.ptr(rgb_styles),
+                          _lib.ptr(self._rgb_b), _lib.ptr(colors.contiguous()), float(clamp), _lib.ptr(img), _lib.ptr(uvs),
+                          int(need_y), _lib.stream())
+            else:
+                self._conv_tc(xin, conv1, B, res, conv1.cin, y, y_cs, False, dcoefs[conv1.name], noise, nsn, ngain, None)
             x, x_cs = y, y_cs
             if res in return_features:
                 feats[f'features{res}_preblend'] = self._unpack(x, B, conv1.cout, res, x_cs)
@@ -402,7 +416,7 @@ class Generator:
                 self._blend_nhwc(x, blended_features[res], B, conv1.cout, res, x_cs)
             if res in return_features:
                 feats[f'features{res}'] = self._unpack(x, B, conv1.cout, res, x_cs)
-            if res == cfg.img_resolution:
+            if is_last and not fused_rgb:
                 img, uvs = self._torgb(x, True, x_cs, rgb_styles, colors, B)
             if extra and not injected:
                 g = geom_feature[geo_idx].to(dev, torch.float32).contiguous()

@@ -152,6 +152,19 @@ int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
                         const float* bias, float alpha, float gain, float clamp, const float* next_scale,
                         nbe_stream_t stream);
 
+/* The last synthesis layer with ToRGB fused into its epilogue (SynthesisBlock.forward networks.py:663-672 for the last
+ * block): the 3x3 modulated conv of nbe_conv_tc_bf16 followed, per pixel and still in registers, by the 1x1 modulated
+ * ToRGB (rgb_w [3,Cout] * rgb_styles [N,Cout], no demodulation), bias, clamp, softmax over the three UVS logits and the
+ * triad colour mix (rgb_colors [N,3,3]) -> img / uvs [N,3,OH,OW] float32.  write_y = 0 skips storing the Cout-channel
+ * feature map altogether (y may then be NULL).  Needs a 128-wide layer (OW % 128 == 0, OH even, Cin <= 128, Cout == 128);
+ * returns NBE_EUNSUPPORTED otherwise (callers then run nbe_conv_tc_bf16 + nbe_torgb_triad). */
+int nbe_conv_tc_bf16_torgb(const void* x, const void* wq, void* y,
+                           int N, int OH, int OW, int Cin, int x_cs, int Cout, int y_cs, int valid,
+                           const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                           const float* bias, float alpha, float gain, float clamp,
+                           const float* rgb_w, const float* rgb_styles, const float* rgb_bias, const float* rgb_colors,
+                           float rgb_clamp, float* img, float* uvs, int write_y, nbe_stream_t stream);
+
 /* Fused ToRGB (1x1 modulated conv, no demodulation) + bias + clamp + softmax(3) + triad colour mix.
  *   t[k] = clamp(sum_c x[c] * w[k,c] * styles[n,c] + bias[k], +-clamp);  uvs = softmax(t);  img[c] = sum_k uvs[k]*colors[n,c,k]
  * Replaces: ToRGBColorTriadLayer.forward SG2/training/networks.py:451-485.

@@ -43,7 +43,7 @@ def test_pack_unpack_roundtrip():
     assert md(unpack(d[..., 8:].contiguous(), 37), ref) == 0
 
 
-@pytest.mark.parametrize('R,cin,B', [(4, 128, 3), (8, 128, 5), (16, 128, 2), (32, 144, 2), (64, 384, 1), (128, 128, 1), (4, 128, 1), (8, 64, 17), (128, 128, 3), (128, 100, 2), (256, 128, 1)])
+@pytest.mark.parametrize('R,cin,B', [(4, 128, 3), (8, 128, 5), (16, 128, 2), (32, 144, 2), (64, 384, 1), (128, 128, 1), (4, 128, 1), (8, 64, 17), (128, 128, 3), (128, 104, 2), (256, 128, 1)])
 @pytest.mark.parametrize('valid', [False, True])
 def test_conv_tc_matches_fp64_conv(R, cin, B, valid):
     g = torch.Generator().manual_seed(R * 7 + cin + B)
@@ -125,3 +125,48 @@ def test_torgb_triad_both_layouts():
                   _lib.ptr(cd), 256.0, _lib.ptr(img), _lib.ptr(uvs), B, C, R, R, _lib.stream())
         tol = 2e-2 if is_bf16 else 1e-5
         assert md(uvs, uvs_ref) < tol and md(img, img_ref) < tol
+
+
+@pytest.mark.parametrize('write_y', [0, 1])
+def test_fused_torgb_epilogue_matches_separate_kernels(write_y):
+    """nbe_conv_tc_bf16_torgb == nbe_conv_tc_bf16 followed by nbe_torgb_triad (ToRGB fed with the un-rounded activations)."""
+    g = torch.Generator().manual_seed(21)
+    B, R, C = 3, 128, 128
+    x = torch.randn(B, C, R, R, generator=g)
+    w = torch.randn(C, C, 3, 3, generator=g) / np.sqrt(C * 9)
+    d = (torch.rand(B, C, generator=g) + 0.5).to(DEV)
+    noise = torch.randn(B, R, R, generator=g).to(DEV)
+    bias = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    rw = torch.randn(3, C, generator=g).to(DEV)
+    rst = ((torch.randn(B, C, generator=g) + 1) / np.sqrt(C)).to(DEV)
+    rb = (torch.randn(3, generator=g) * 0.1).to(DEV)
+    col = torch.tanh(torch.randn(B, 3, 3, generator=g)).to(DEV)
+    xq = pack(x.to(DEV))
+    wd = w.to(DEV)
+    wq = torch.empty((9, C, C), dtype=torch.bfloat16, device=DEV)
+    _lib.call('nbe_prepare_weights_bf16', _lib.ptr(wd), _lib.ptr(wq), C, C, 3, 0, _lib.stream())
+    sq2 = float(np.sqrt(2))
+    y_ref = torch.empty((B, R, R, C), dtype=torch.bfloat16, device=DEV)
+    _lib.call('nbe_conv_tc_bf16', _lib.ptr(xq), _lib.ptr(wq), _lib.ptr(y_ref), B, R, R, C, C, C, C, 3, 0, _lib.ptr(d), _lib.ptr(noise),
+              R * R, 0.7, _lib.ptr(bias), 0.2, sq2, 256.0, None, _lib.stream())
+    img_ref = torch.empty((B, 3, R, R), device=DEV)
+    uvs_ref = torch.empty((B, 3, R, R), device=DEV)
+    _lib.call('nbe_torgb_triad', _lib.ptr(y_ref), 1, C, _lib.ptr(rw), _lib.ptr(rst), _lib.ptr(rb), _lib.ptr(col), 256.0,
+              _lib.ptr(img_ref), _lib.ptr(uvs_ref), B, C, R, R, _lib.stream())
+    y = torch.full((B, R, R, C), 3.0, dtype=torch.bfloat16, device=DEV)
+    img = torch.empty((B, 3, R, R), device=DEV)
+    uvs = torch.empty((B, 3, R, R), device=DEV)
+    _lib.call('nbe_conv_tc_bf16_torgb', _lib.ptr(xq), _lib.ptr(wq), _lib.ptr(y) if write_y else None, B, R, R, C, C, C, C, 0,
+              _lib.ptr(d), _lib.ptr(noise), R * R, 0.7, _lib.ptr(bias), 0.2, sq2, 256.0, _lib.ptr(rw), _lib.ptr(rst), _lib.ptr(rb),
+              _lib.ptr(col), 256.0, _lib.ptr(img), _lib.ptr(uvs), write_y, _lib.stream())
+    torch.cuda.synchronize()
+    assert md(uvs, uvs_ref) < 2e-2 and md(img, img_ref) < 2e-2        # separate path rounds the activations to bf16 first
+    if write_y:
+        assert md(y.float(), y_ref.float()) == 0
+    else:
+        assert float((y.float() - 3.0).abs().max()) == 0
+    # unsupported shapes are reported, not silently mis-executed
+    with pytest.raises(RuntimeError, match='fused ToRGB'):
+        _lib.call('nbe_conv_tc_bf16_torgb', _lib.ptr(xq), _lib.ptr(wq), _lib.ptr(y), B * 4, 64, 64, C, C, C, C, 0,
+                  _lib.ptr(d), None, 0, 0.0, _lib.ptr(bias), 0.2, sq2, 256.0, _lib.ptr(rw), _lib.ptr(rst), _lib.ptr(rb),
+                  _lib.ptr(col), 256.0, _lib.ptr(img), _lib.ptr(uvs), 1, _lib.stream())
