@@ -599,7 +599,7 @@ static int conv_tc_impl(const void* x, const void* wq, void* y,
             int st = make_tmap(&tb, wq, 3, dims, strides, box, "weights");
             if (st) return st;
         }
-        const size_t rsmem = 1024 + 8 * R_ABUF + R_BSTAGES * R_BBYTES + 3 * 128 * sizeof(float) + 256;
+        const size_t rsmem = 1024 + 8 * R_ABUF + R_BSTAGES * R_BBYTES + 6 * 128 * sizeof(float) + 256;
         static std::once_flag row_once;
         static cudaError_t row_err = cudaSuccess;
         std::call_once(row_once, [] {
