@@ -136,7 +136,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
@@ -261,7 +261,7 @@ def main():
                        'batch_per_gpu': B, 'parallelism': f'patch-sharded x{world} (no data-path collective)',
                        'l2': 'per-step working set ~6 GB >> 126 MB L2; inputs rotate over 8 distinct batches (8 x 16.8 MB)',
                        'mode': 'bf16 tensor-core (tcgen05), fp32 accumulate'},
-            'roofline': {'bound': 'tensor', 'kernel': f'conv_tc_kernel @ {DOM} (3x3 modconv 128->128 @128^2, batch {B})',
+            'roofline': {'bound': 'tensor', 'kernel': f'conv_tc_row128_kernel @ {DOM} (3x3 modconv 128->128 @128^2 with ToRGB/triad fused in the epilogue, batch {B})',
                          'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                          'traffic': traffic, 'peak_source': peak_src, 'avg_launch_ms': dom_ms,
                          'algorithmic_flops_per_launch': dom_flops},

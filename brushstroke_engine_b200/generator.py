@@ -402,11 +402,18 @@ class Generator:
                 img = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
                 uvs = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
                 clamp = cfg.conv_clamp if cfg.conv_clamp is not None else -1
+                ev = None
+                if self.probe is not None and conv1.name in self.probe:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
                 _lib.call('nbe_conv_tc_bf16_torgb', _lib.ptr(xin), _lib.ptr(conv1.wq), _lib.ptr(y) if need_y else None, B, res, res,
                           conv1.cin, conv1.cin, conv1.cout, y_cs, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
                           _lib.ptr(conv1.bias), 0.2, SQRT2, float(clamp), _lib.ptr(self._rgb_w), _lib.ptr(rgb_styles),
                           _lib.ptr(self._rgb_b), _lib.ptr(colors.contiguous()), float(clamp), _lib.ptr(img), _lib.ptr(uvs),
                           int(need_y), _lib.stream())
+                if ev is not None:
+                    ev[1].record()
+                    self.probe[conv1.name].append(ev)
             else:
                 self._conv_tc(xin, conv1, B, res, conv1.cin, y, y_cs, False, dcoefs[conv1.name], noise, nsn, ngain, None)
             x, x_cs = y, y_cs
