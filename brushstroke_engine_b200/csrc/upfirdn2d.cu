@@ -5,10 +5,9 @@
 //   ft = f flipped in both axes unless `flip`                       
 //
 // Two kernels:
-//  * upfirdn2d_tiled_kernel<T, UP>: the cases the generator / public helpers hit -- 4x4 filter, down = 1,
-//    up in {1, 2}, dense NCHW.  One CTA = one 32x64 output tile of one (n,c) plane; the input footprint is
-//    staged in shared memory as fp32 with coalesced row loads, every thread produces a 1x8 (UP=1) or
-//    2x4 (UP=2) register strip so each staged value is re-used from registers, stores are row-contiguous.
+//  * upfirdn2d_rows_up{1,2}_kernel<T>: the cases the generator / public helpers hit -- 4x4 filter, down = 1,
+//    up in {1, 2}, dense NCHW.  A lane owns 16 bytes of consecutive output columns and walks 16 output rows with a
+//    register window of input rows (no shared memory, no barriers); stores are 16-byte streaming vectors.
 //    HBM-bound: algorithmic bytes = numel(x) + numel(y) elements.
 //  * upfirdn2d_generic_kernel<T>: any filter size / up / down / padding / strides (incl. channels_last),
 //    one thread per output element.
@@ -53,119 +52,159 @@ upfirdn2d_generic_kernel(UpfirdnParams p) {
     }
 }
 
-// ---- tiled 4x4 kernel -------------------------------------------------------------------------
-constexpr int TILE_OH = 32;
-constexpr int TILE_OW = 64;
+// ---- register-window 4x4 kernels (dense NCHW, down = 1) ------------------------------------------
+// One lane owns VPT consecutive output columns (16 bytes of output) and walks ROWS output rows of one (n,c) plane
+// keeping the input rows it needs in registers: no shared memory, no barriers, ~1.5 global loads (L1 hits for the
+// overlap between neighbouring lanes / rows) + 16 (UP=1) or 4 (UP=2) FMAs + 1/VPT vector store per output.
+constexpr int RW_ROWS = 16;
 
-template <class T, int UP>
-__global__ void __launch_bounds__(256)
-upfirdn2d_tiled_kernel(UpfirdnParams p, int tiles_x, int tiles_y) {
-    // input footprint of a TILE_OH x TILE_OW output tile
-    constexpr int IN_H = (UP == 1) ? TILE_OH + 3 : TILE_OH / 2 + 2;
-    constexpr int IN_W = (UP == 1) ? TILE_OW + 3 : TILE_OW / 2 + 2;
-    constexpr int IN_WP = IN_W + 1;                              // +1: odd pitch, conflict-free column walks
-    __shared__ float s_in[IN_H][IN_WP];
+template <class T> struct VecOut;                                       // VPT outputs packed into one 16-byte store
+template <> struct VecOut<float> { static constexpr int VPT = 4; };
+template <> struct VecOut<__half> { static constexpr int VPT = 8; };
+template <> struct VecOut<__nv_bfloat16> { static constexpr int VPT = 8; };
+
+template <class T, int VPT>
+__device__ __forceinline__ void store_row(T* dst, const float (&acc)[VPT], int n_valid) {
+    if (n_valid == VPT && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        int4 v;
+        T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) e[k] = Cvt<T>::st(acc[k]);
+        st_stream16(dst, v);
+    } else {
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) if (k < n_valid) dst[k] = Cvt<T>::st(acc[k]);
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(128)
+upfirdn2d_rows_up1_kernel(UpfirdnParams p, int col_blocks, int row_blocks) {
+    constexpr int VPT = VecOut<T>::VPT;
+    constexpr int WIN = VPT + 3;
     __shared__ float s_f[16];
-
-    int tile = blockIdx.x;
-    const int tx = tile % tiles_x; tile /= tiles_x;
-    const int ty = tile % tiles_y; tile /= tiles_y;
-    const int plane = tile;                                      // n * C + c
-    const int oy0 = ty * TILE_OH, ox0 = tx * TILE_OW;
-    const T* xp = (const T*)p.x + (int64_t)plane * p.H * p.W;
-    T* yp = (T*)p.y + (int64_t)plane * p.OH * p.OW;
-
     if (threadIdx.x < 16) {
         int a = threadIdx.x >> 2, b = threadIdx.x & 3;
         s_f[threadIdx.x] = (p.flip ? p.f[a * 4 + b] : p.f[(3 - a) * 4 + (3 - b)]) * p.gain;
     }
-    // First input row/col touched by this tile.  UP == 1: u = oy + a - pad.  UP == 2: iy = (oy + a - pad) / 2
-    // for the taps with even (oy + a - pad); floor-div of the smallest candidate.
-    int iy0, ix0;
-    if (UP == 1) { iy0 = oy0 - p.pady0; ix0 = ox0 - p.padx0; }
-    else {
-        // floor((oy0 - pad) / 2) and one extra row of slack handled by IN_H = TILE/2 + 2
-        int u0 = oy0 - p.pady0, v0 = ox0 - p.padx0;
-        iy0 = (u0 >= 0) ? (u0 + 1) / 2 : -((-u0) / 2);           // ceil(u0 / 2): first even-aligned input row >= u0/2
-        ix0 = (v0 >= 0) ? (v0 + 1) / 2 : -((-v0) / 2);
-    }
-    for (int i = threadIdx.x; i < IN_H * IN_W; i += 256) {
-        int r = i / IN_W, c = i - r * IN_W;
-        int iy = iy0 + r, ix = ix0 + c;
-        float v = 0.f;
-        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = Cvt<T>::ld(xp[(int64_t)iy * p.W + ix]);
-        s_in[r][c] = v;
-    }
     __syncthreads();
-
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = s_f[i];
+    int blk = blockIdx.x;
+    const int cb = blk % col_blocks; blk /= col_blocks;
+    const int rb = blk % row_blocks; blk /= row_blocks;
+    const int plane = blk;
+    const int ox0 = (cb * 128 + threadIdx.x) * VPT;
+    if (ox0 >= p.OW) return;
+    const int oy0 = rb * RW_ROWS;
+    const T* xp = (const T*)p.x + (int64_t)plane * p.H * p.W;
+    T* yp = (T*)p.y + (int64_t)plane * p.OH * p.OW;
+    const int ix0 = ox0 - p.padx0;
+    const int n_valid = min(VPT, p.OW - ox0);
+    float win[4][WIN];
+    auto load_row = [&](float (&dst)[WIN], int iy) {
+        const bool row_ok = iy >= 0 && iy < p.H;
+        const T* rp = xp + (int64_t)iy * p.W;
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) {
+            const int ix = ix0 + j;
+            dst[j] = (row_ok && ix >= 0 && ix < p.W) ? Cvt<T>::ld(rp[ix]) : 0.f;
+        }
+    };
+    const int iy0 = oy0 - p.pady0;
+    load_row(win[0], iy0); load_row(win[1], iy0 + 1); load_row(win[2], iy0 + 2);
+#pragma unroll
+    for (int r = 0; r < RW_ROWS; ++r) {
+        const int oy = oy0 + r;
+        if (oy >= p.OH) break;
+        load_row(win[(r + 3) & 3], iy0 + r + 3);
+        float acc[VPT];
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) acc[k] = fmaf(f[a * 4 + b], win[(r + a) & 3][k + b], acc[k]);
+        store_row<T, VPT>(yp + (int64_t)oy * p.OW + ox0, acc, n_valid);
+    }
+}
 
-    if (UP == 1) {
-        // thread -> column lx (0..63), rows ly0..ly0+7 ; 256 threads = 64 cols x 4 row groups
-        const int lx = threadIdx.x & 63;
-        const int ly0 = (threadIdx.x >> 6) * 8;
-        float acc[8];
+template <class T>
+__global__ void __launch_bounds__(128)
+upfirdn2d_rows_up2_kernel(UpfirdnParams p, int col_blocks, int row_blocks) {
+    constexpr int VPT = VecOut<T>::VPT;
+    constexpr int WIN = VPT / 2 + 2;
+    __shared__ float s_f[16];
+    if (threadIdx.x < 16) {
+        int a = threadIdx.x >> 2, b = threadIdx.x & 3;
+        s_f[threadIdx.x] = (p.flip ? p.f[a * 4 + b] : p.f[(3 - a) * 4 + (3 - b)]) * p.gain;
+    }
+    __syncthreads();
+    float f[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 16; ++i) f[i] = s_f[i];
+    int blk = blockIdx.x;
+    const int cb = blk % col_blocks; blk /= col_blocks;
+    const int rb = blk % row_blocks; blk /= row_blocks;
+    const int plane = blk;
+    const int ox0 = (cb * 128 + threadIdx.x) * VPT;
+    if (ox0 >= p.OW) return;
+    const int oy0 = rb * RW_ROWS;
+    const T* xp = (const T*)p.x + (int64_t)plane * p.H * p.W;
+    T* yp = (T*)p.y + (int64_t)plane * p.OH * p.OW;
+    const int n_valid = min(VPT, p.OW - ox0);
+    // first input column any of this lane's outputs can touch: floor((ox0 - padx0) / 2) (arithmetic shift = floor)
+    const int ixb = (ox0 - p.padx0) >> 1;
+    // per output column k and tap parity: b0 = first tap with even (ox + b - padx0)
+#pragma unroll 1
+    for (int r = 0; r < RW_ROWS; ++r) {
+        const int oy = oy0 + r;
+        if (oy >= p.OH) break;
+        const int u0 = oy - p.pady0;
+        const int a0 = u0 & 1;                                      // taps a0, a0 + 2 hit even rows of the zero-stuffed grid
+        const int iyA = (u0 + a0) >> 1;
+        float rowA[WIN], rowB[WIN];
 #pragma unroll
-        for (int r = 0; r < 11; ++r) {
-            float v0 = s_in[ly0 + r][lx], v1 = s_in[ly0 + r][lx + 1], v2 = s_in[ly0 + r][lx + 2], v3 = s_in[ly0 + r][lx + 3];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                int o = r - a;                                   // output row (within strip) fed by input row r via tap a
-                if (o >= 0 && o < 8)
-                    acc[o] += f[a * 4 + 0] * v0 + f[a * 4 + 1] * v1 + f[a * 4 + 2] * v2 + f[a * 4 + 3] * v3;
-            }
+        for (int j = 0; j < WIN; ++j) {
+            const int ix = ixb + j;
+            const bool cok = ix >= 0 && ix < p.W;
+            rowA[j] = (cok && iyA >= 0 && iyA < p.H) ? Cvt<T>::ld(xp[(int64_t)iyA * p.W + ix]) : 0.f;
+            rowB[j] = (cok && iyA + 1 >= 0 && iyA + 1 < p.H) ? Cvt<T>::ld(xp[(int64_t)(iyA + 1) * p.W + ix]) : 0.f;
         }
-        const int ox = ox0 + lx;
-        if (ox < p.OW) {
+        float acc[VPT];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int oy = oy0 + ly0 + i;
-                if (oy < p.OH) yp[(int64_t)oy * p.OW + ox] = Cvt<T>::st(acc[i]);
-            }
+        for (int k = 0; k < VPT; ++k) {
+            const int v0 = ox0 + k - p.padx0;
+            const int b0 = v0 & 1;
+            const int j0 = ((v0 + b0) >> 1) - ixb;                  // 0 .. WIN-2
+            // select the four active taps without dynamic indexing (keeps f[] in registers)
+            const float fa0 = a0 ? (b0 ? f[5] : f[4]) : (b0 ? f[1] : f[0]);
+            const float fa1 = a0 ? (b0 ? f[7] : f[6]) : (b0 ? f[3] : f[2]);
+            const float fb0 = a0 ? (b0 ? f[13] : f[12]) : (b0 ? f[9] : f[8]);
+            const float fb1 = a0 ? (b0 ? f[15] : f[14]) : (b0 ? f[11] : f[10]);
+            float x00 = 0.f, x01 = 0.f, x10 = 0.f, x11 = 0.f;
+#pragma unroll
+            for (int j = 0; j < WIN - 1; ++j)                       // static indexing of the register window
+                if (j == j0) { x00 = rowA[j]; x01 = rowA[j + 1]; x10 = rowB[j]; x11 = rowB[j + 1]; }
+            acc[k] = fa0 * x00 + fa1 * x01 + fb0 * x10 + fb1 * x11;
         }
-    } else {
-        // Each thread: 2 output columns (ox even/odd pair) x 4 output rows.  256 threads = 32 col pairs x 8 row groups.
-        const int lxp = threadIdx.x & 31;
-        const int ly0 = (threadIdx.x >> 5) * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int oy = oy0 + ly0 + i;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int ox = ox0 + lxp * 2 + j;
-                float acc = 0.f;
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    int u = oy + a - p.pady0;
-                    if (u & 1) continue;
-                    int r = (u >> 1) - iy0;                      // arithmetic shift = floor for negatives
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        int v = ox + b - p.padx0;
-                        if (v & 1) continue;
-                        int c = (v >> 1) - ix0;
-                        acc += f[a * 4 + b] * s_in[r][c];
-                    }
-                }
-                if (oy < p.OH && ox < p.OW) yp[(int64_t)oy * p.OW + ox] = Cvt<T>::st(acc);
-            }
-        }
+        store_row<T, VPT>(yp + (int64_t)oy * p.OW + ox0, acc, n_valid);
     }
 }
 
 template <class T>
 static int run_typed(const UpfirdnParams& p, bool tiled_ok, cudaStream_t s) {
     if (tiled_ok) {
-        const int tiles_x = (p.OW + TILE_OW - 1) / TILE_OW, tiles_y = (p.OH + TILE_OH - 1) / TILE_OH;
-        const int64_t blocks = (int64_t)tiles_x * tiles_y * p.N * p.C;
+        constexpr int VPT = VecOut<T>::VPT;
+        const int col_blocks = (p.OW + 128 * VPT - 1) / (128 * VPT), row_blocks = (p.OH + RW_ROWS - 1) / RW_ROWS;
+        const int64_t blocks = (int64_t)col_blocks * row_blocks * p.N * p.C;
         if (blocks <= INT32_MAX) {
-            if (p.upx == 1) upfirdn2d_tiled_kernel<T, 1><<<(int)blocks, 256, 0, s>>>(p, tiles_x, tiles_y);
-            else            upfirdn2d_tiled_kernel<T, 2><<<(int)blocks, 256, 0, s>>>(p, tiles_x, tiles_y);
-            return launched("upfirdn2d_tiled_kernel");
+            if (p.upx == 1) upfirdn2d_rows_up1_kernel<T><<<(int)blocks, 128, 0, s>>>(p, col_blocks, row_blocks);
+            else            upfirdn2d_rows_up2_kernel<T><<<(int)blocks, 128, 0, s>>>(p, col_blocks, row_blocks);
+            return launched("upfirdn2d_rows_kernel");
         }
     }
     const int64_t total = (int64_t)p.N * p.C * p.OH * p.OW;
