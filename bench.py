@@ -141,6 +141,8 @@ def main():
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-canvas', action='store_true')
+    ap.add_argument('--canvas', type=int, default=4096, help='side of the synthetic canvas for the stylization leg')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (profiling runs under ncu)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -225,10 +227,40 @@ def main():
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 
-    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- BASELINE configs[4]: 4096^2 canvas, style interpolated across 8 z anchors, crop rows sharded over the ranks,
+    #      one NCCL gather of finished tiles to rank 0 (time = host guidance in -> finished uint8 canvas on rank 0) ----
+    canvas_ms = None
+    if not args.no_canvas:
+        from brushstroke_engine_b200 import stylizer
+        size = args.canvas
+        guidance = synthetic.synthetic_guidance(size, size, num_lines=256 if size >= 4096 else 64, seed=0)
+        job_crops, _ = stylizer.generate_stitching_crops(stylizer.pad_geo(guidance, 10), 128, 'all', 20)
+        anchors = np.concatenate([np.random.RandomState(seed=k).randn(1, 64) for k in range(8)])
+        xs = np.array([c[1] for c in job_crops], dtype=np.float64) / max(1, max(c[1] for c in job_crops))
+        t_ = xs * 7.0
+        k0 = np.clip(np.floor(t_).astype(int), 0, 6)
+        a_ = (t_ - k0)[:, None]
+        z_pp = torch.from_numpy((1 - a_) * anchors[k0] + a_ * anchors[k0 + 1]).to(dev)     # z = alpha z1 + (1 - alpha) z2 per patch
+        copts = GanBrushOptions()
+        copts.set_style(z_pp[:1])
+        ctimes = []
+        with torch.no_grad():
+            for rep in range(4):
+                barrier()
+                t0 = time.perf_counter()
+                out = stylizer.stylize(engine, guidance, copts, crop_margin=10, batch_size=B, z_per_patch=z_pp)
+                barrier()
+                if rep > 0:
+                    ctimes.append((time.perf_counter() - t0) * 1e3)
+        canvas_ms = float(np.median(ctimes))
+        n_canvas_patches = len(job_crops)
+
+    times = torch.tensor([ms_total, e2e_s * 1e3, canvas_ms if canvas_ms is not None else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(times[0]), float(times[1])
+    if canvas_ms is not None:
+        canvas_ms = float(times[2])
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
@@ -270,6 +302,10 @@ def main():
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
         }
+        if canvas_ms is not None:
+            line['canvas'] = {'size': args.canvas, 'patches': n_canvas_patches, 'ms': canvas_ms, 'n_gpus': world,
+                              'what': 'host uint8 guidance -> crops -> encoder+generator+composite (8-anchor z interpolation) -> '
+                                      'tile gather to rank 0 (NCCL when n_gpus > 1) -> placed uint8 canvas on the host'}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n = 8
