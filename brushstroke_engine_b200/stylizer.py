@@ -84,26 +84,55 @@ def composite_on_white(result: np.ndarray) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------------------ device-side scheduler
-class CanvasJob:
-    """One stylization of one guidance image on one rank."""
+def crop_grid(img_height: int, img_width: int, patch_width: int, overlap_margin: int):
+    """Arithmetic of style_transfer.py:23-30: -> (nrows, ncols, rwidth, padded_h, padded_w)."""
+    rwidth = patch_width - overlap_margin * 2
+    nrows = img_height // rwidth + 1
+    ncols = img_width // rwidth + 1
+    return nrows, ncols, rwidth, nrows * rwidth + patch_width, ncols * rwidth + patch_width
 
-    def __init__(self, engine: TriadPaintEngine, guidance: np.ndarray, crop_margin: int = 10, stitching_mode: str = 'all'):
-        assert guidance.ndim == 3 and guidance.dtype == np.uint8
+
+class CanvasJob:
+    """One stylization of one guidance image on one rank.  ``guidance`` may be a host ``np.ndarray`` or a CUDA uint8
+    tensor [H,W,C]; the padded canvas (pad_geo + generate_stitching_crops padding, value 255) is built on the device
+    and the crop list comes from the grid arithmetic, so nothing but the (optional) initial upload touches the host."""
+
+    def __init__(self, engine: TriadPaintEngine, guidance, crop_margin: int = 10, stitching_mode: str = 'all'):
         self.engine = engine
-        self.crop_margin = int(crop_margin)
-        self.patch = engine.patch_width
-        self.orig_shape = guidance.shape
-        geom = pad_geo(guidance[:, :, -1:], self.crop_margin)
-        self.crops, self.geom = generate_stitching_crops(geom, self.patch, mode=stitching_mode,
-                                                         overlap_margin=self.crop_margin * 2)
-        self.canvas_h, self.canvas_w = self.geom.shape[:2]
-        self.tile = self.patch - 2 * self.crop_margin
         dev = engine.device
-        self.d_geom = torch.from_numpy(np.ascontiguousarray(self.geom[:, :, 0])).to(dev)
-        self.crops_yx = np.array([(c[0], c[1]) for c in self.crops], dtype=np.int32).reshape(-1, 2)
+        self.crop_margin = m = int(crop_margin)
+        self.patch = engine.patch_width
+        if isinstance(guidance, np.ndarray):
+            assert guidance.ndim == 3 and guidance.dtype == np.uint8
+            guidance = torch.from_numpy(np.ascontiguousarray(guidance[:, :, -1])).to(dev)
+        else:
+            assert guidance.ndim == 3 and guidance.dtype == torch.uint8
+            guidance = guidance[:, :, -1].to(dev)
+        H0, W0 = int(guidance.shape[0]), int(guidance.shape[1])
+        self.orig_shape = (H0, W0)
+        nrows, ncols, rwidth, ph, pw = crop_grid(H0 + m, W0 + m, self.patch, m * 2)
+        self.canvas_h, self.canvas_w = ph, pw
+        self.d_geom = torch.full((ph, pw), 255, dtype=torch.uint8, device=dev)
+        self.d_geom[m:m + H0, m:m + W0] = guidance                       # pad_geo offset + bottom/right padding in one go
+        ys, xs = np.meshgrid(np.arange(nrows) * rwidth, np.arange(ncols) * rwidth, indexing='ij')
+        yx = np.stack([ys.ravel(), xs.ravel()], axis=1).astype(np.int32)
+        if stitching_mode != 'all':
+            # keep crops with more than 10 stroke (zero) pixels (style_transfer.py:45): window sums on the device
+            zeros = (self.d_geom == 0).to(torch.float32)[None, None]
+            counts = torch.nn.functional.avg_pool2d(zeros, self.patch, stride=rwidth, divisor_override=1)[0, 0]
+            keep = (counts[:nrows, :ncols] > 10).cpu().numpy().ravel()
+            yx = yx[keep]
+        self.crops_yx = np.ascontiguousarray(yx).reshape(-1, 2)
+        self.crops = [(int(y), int(x), self.patch, self.patch) for y, x in self.crops_yx]
+        self.tile = self.patch - 2 * m
         self.d_crops = torch.from_numpy(self.crops_yx).to(dev)
-        self.tiles_yx = self.crops_yx + self.crop_margin                 # meta: (y + m, x + m)  (brush.py:365-373)
+        self.tiles_yx = self.crops_yx + m                                # meta: (y + m, x + m)  (brush.py:365-373)
         self.d_tiles_yx = torch.from_numpy(self.tiles_yx).to(dev)
+
+    @property
+    def geom(self) -> np.ndarray:
+        """Host copy of the padded guidance [ph, pw, 1] (tests / debugging)."""
+        return self.d_geom.cpu().numpy()[:, :, None]
 
     def gather(self, start: int, end: int) -> torch.Tensor:
         n = end - start
@@ -123,12 +152,19 @@ class CanvasJob:
         _lib.call('nbe_place_tiles', _lib.ptr(tiles), _lib.ptr(self.d_tiles_yx[start:end]), _lib.ptr(order), end - start,
                   self.tile, _lib.ptr(owner), _lib.ptr(canvas), self.canvas_h, self.canvas_w, _lib.stream())
 
-    def finish(self, canvas: torch.Tensor, on_white: bool) -> np.ndarray:
-        result = canvas.cpu().numpy()
+    def finish(self, canvas: torch.Tensor, on_white: bool, to_host: bool = True):
+        """Crop back to the input size (paint_image_main.py:185-186); optional on-white composite (:179-183)."""
+        m = self.crop_margin
+        result = canvas[m:m + self.orig_shape[0], m:m + self.orig_shape[1], :]
+        if not to_host:
+            if on_white:
+                alpha = result[..., 3:].to(torch.float32) / 255
+                result = (result[..., :3].to(torch.float32) * alpha + 255 * (1 - alpha)).clip(0, 255).to(torch.uint8)
+            return result
+        result = result.cpu().numpy()
         if on_white:
             result = composite_on_white(result)
-        m = self.crop_margin
-        return result[m:m + self.orig_shape[0], m:m + self.orig_shape[1], :]
+        return result
 
 
 def _batch_opts(base: GanBrushOptions, z_per_patch: Optional[torch.Tensor], start: int, end: int, positions: torch.Tensor):
@@ -142,8 +178,9 @@ def _batch_opts(base: GanBrushOptions, z_per_patch: Optional[torch.Tensor], star
 
 def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOptions, crop_margin: int = 10,
             stitching_mode: str = 'all', feature_blending_level: int = 0, batch_size: int = 256, on_white: bool = False,
-            z_per_patch: Optional[torch.Tensor] = None, group=None, return_job: bool = False):
-    """Stylize a whole guidance drawing.  guidance: [H,W,C] uint8 (last channel, 0 = stroke).
+            z_per_patch: Optional[torch.Tensor] = None, group=None, return_job: bool = False, to_host: bool = True):
+    """Stylize a whole guidance drawing.  guidance: [H,W,C] uint8 (last channel, 0 = stroke), host array or CUDA tensor;
+    ``to_host=False`` returns the finished canvas as a CUDA tensor (device-resident in and out).
 
     With an initialised ``torch.distributed`` process group (one process per GPU) the crop rows are sharded across
     ranks and rank 0 returns the finished canvas (other ranks return None).  ``z_per_patch`` ([n_crops, z_dim])
@@ -157,7 +194,7 @@ def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOption
         if world > 1:
             raise RuntimeError('stylize: feature blending makes patches raster-dependent; run it on one GPU')
         canvas = _stylize_blended(engine, job, opts, feature_blending_level, z_per_patch)
-        out = job.finish(canvas, on_white)
+        out = job.finish(canvas, on_white, to_host)
         return (out, job) if return_job else out
     start, end = shard_crops(job.crops, world, rank)
     dev = engine.device
@@ -171,7 +208,7 @@ def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOption
     if world == 1:
         canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
         job.place(canvas, job.owner_map(), tiles_local, start, end)
-        out = job.finish(canvas, on_white)
+        out = job.finish(canvas, on_white, to_host)
         return (out, job) if return_job else out
     # ---- multi-GPU: one gather of finished tiles to rank 0 (NCCL over NVLink; gloo in CPU tests is not used here) ----
     bounds = [shard_crops(job.crops, world, r) for r in range(world)]
@@ -187,7 +224,7 @@ def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOption
     for r, (s, e) in enumerate(bounds):
         if e > s:
             job.place(canvas, owner, gathered[r][: e - s].contiguous(), s, e)
-    out = job.finish(canvas, on_white)
+    out = job.finish(canvas, on_white, to_host)
     return (out, job) if return_job else out
 
 
