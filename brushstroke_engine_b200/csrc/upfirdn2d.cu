@@ -5,10 +5,8 @@
 //   ft = f flipped in both axes unless `flip`                       
 //
 // Two kernels:
-//  * upfirdn2d_rows_up{1,2}_kernel<T>: the cases the generator / public helpers hit -- 4x4 filter, down = 1,
-//    up in {1, 2}, dense NCHW.  A lane owns 16 bytes of consecutive output columns and walks 16 output rows with a
-//    register window of input rows (no shared memory, no barriers); stores are 16-byte streaming vectors.
-//    HBM-bound: algorithmic bytes = numel(x) + numel(y) elements.
+//  * upfirdn2d_staged_kernel<T, UP>: the cases the generator / public helpers hit -- 4x4 filter, down = 1,
+//    up in {1, 2}, dense NCHW (see the comment above the kernel).  HBM-bound: algorithmic bytes = numel(x) + numel(y) elements.
 //  * upfirdn2d_generic_kernel<T>: any filter size / up / down / padding / strides (incl. channels_last),
 //    one thread per output element.
 #include "common.cuh"
@@ -52,11 +50,15 @@ upfirdn2d_generic_kernel(UpfirdnParams p) {
     }
 }
 
-// ---- register-window 4x4 kernels (dense NCHW, down = 1) ------------------------------------------
-// One lane owns VPT consecutive output columns (16 bytes of output) and walks ROWS output rows of one (n,c) plane
-// keeping the input rows it needs in registers: no shared memory, no barriers, ~1.5 global loads (L1 hits for the
-// overlap between neighbouring lanes / rows) + 16 (UP=1) or 4 (UP=2) FMAs + 1/VPT vector store per output.
-constexpr int RW_ROWS = 16;
+// ---- staged 4x4 kernels (dense NCHW, down = 1, up in {1, 2}) ---------------------------------------
+// A CTA owns either a strip of output rows of one (n,c) plane or a group of whole small planes.  Either way the input
+// it needs is ONE contiguous range of the flat tensor, so it is staged into shared memory with aligned 16-byte
+// streaming loads (no per-element index arithmetic, misaligned odd-length rows like 2R+1 do not matter).  Each thread
+// then produces VPT consecutive columns x RPT rows from a sliding register window; rank-1 filters (everything
+// setup_filter builds from a 1-D tap list) take the separable path (4 + 4 FMAs per output instead of 16).  Stores are
+// 16-byte streaming vectors.  HBM-bound: algorithmic bytes = (numel(x) + numel(y)) * sizeof(T).
+constexpr int ST_THREADS = 256;
+constexpr int ST_RPT = 8;                                               // output rows per thread
 
 template <class T> struct VecOut;                                       // VPT outputs packed into one 16-byte store
 template <> struct VecOut<float> { static constexpr int VPT = 4; };
@@ -77,134 +79,220 @@ __device__ __forceinline__ void store_row(T* dst, const float (&acc)[VPT], int n
     }
 }
 
-template <class T>
-__global__ void __launch_bounds__(128)
-upfirdn2d_rows_up1_kernel(UpfirdnParams p, int col_blocks, int row_blocks) {
+struct StagedGeom {
+    int cg;             // column groups per row  = ceil(OW / VPT)
+    int rg;             // row groups per CTA-plane = ceil(rows_per_cta / RPT)
+    int ppc;            // whole planes per CTA (>= 1); > 1 only when a plane fits one CTA
+    int strip;          // output rows per CTA when ppc == 1
+    int strips;         // strips per plane
+    int smem_bytes;
+};
+
+template <int VPT, int WIN, int PI>
+__device__ __forceinline__ void up2_row(float (&acc)[VPT], const float (&rowA)[WIN], const float (&rowB)[WIN], const float (&f)[16], int a0) {
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        constexpr int dummy = 0; (void)dummy;
+        const int b0 = (PI + k) & 1;                                    // compile-time after unrolling
+        const int j0 = (k + PI + b0) >> 1;
+        const float fa0 = a0 ? f[4 + b0] : f[b0];
+        const float fa1 = a0 ? f[6 + b0] : f[2 + b0];
+        const float fb0 = a0 ? f[12 + b0] : f[8 + b0];
+        const float fb1 = a0 ? f[14 + b0] : f[10 + b0];
+        acc[k] = fa0 * rowA[j0] + fa1 * rowA[j0 + 1] + fb0 * rowB[j0] + fb1 * rowB[j0 + 1];
+    }
+}
+
+template <class T, int UP>
+__global__ void __launch_bounds__(ST_THREADS)
+upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
     constexpr int VPT = VecOut<T>::VPT;
-    constexpr int WIN = VPT + 3;
+    extern __shared__ __align__(16) uint8_t st_smem[];
     __shared__ float s_f[16];
+    const T* xbase = (const T*)p.x;
+    // ---- which planes / rows does this CTA own
+    int plane0, oy0, rows;
+    if (g.ppc > 1) { plane0 = blockIdx.x * g.ppc; oy0 = 0; rows = p.OH; }
+    else { plane0 = blockIdx.x / g.strips; oy0 = (blockIdx.x % g.strips) * g.strip; rows = min(g.strip, p.OH - oy0); }
+    const int planes = min(g.ppc, n_planes - plane0);
+    // ---- input rows needed (per plane): UP=1: [oy0 - pad, oy0 - pad + rows + 3) ; UP=2: [(oy0 - pad) >> 1, ((oy0 + rows + 2 - pad) >> 1) + 1)
+    int r_lo, r_hi;
+    if (UP == 1) { r_lo = oy0 - p.pady0; r_hi = r_lo + rows + 3; }
+    else { r_lo = (oy0 - p.pady0) >> 1; r_hi = ((oy0 + rows + 2 - p.pady0) >> 1) + 1; }
+    r_lo = max(r_lo, 0); r_hi = min(r_hi, p.H);
+    if (g.ppc > 1) { r_lo = 0; r_hi = p.H; }
+    const long long plane_elems = (long long)p.H * p.W;
+    const long long e_lo = (long long)plane0 * plane_elems + (long long)r_lo * p.W;                    // first element needed
+    const long long e_hi = (g.ppc > 1) ? (long long)(plane0 + planes) * plane_elems
+                                       : (long long)plane0 * plane_elems + (long long)max(r_hi, r_lo) * p.W;
+    // ---- stage [e_lo, e_hi) with aligned 16-byte chunks; smem byte 0 <-> global byte a_lo
+    const uintptr_t gb_lo = reinterpret_cast<uintptr_t>(xbase + e_lo), gb_hi = reinterpret_cast<uintptr_t>(xbase + e_hi);
+    const uintptr_t a_lo = gb_lo & ~uintptr_t(15);
+    const uintptr_t t_lo = reinterpret_cast<uintptr_t>(xbase), t_hi = reinterpret_cast<uintptr_t>(xbase + (long long)n_planes * plane_elems);
+    const int n_chunks = (int)((gb_hi - a_lo + 15) >> 4);
+    for (int i = threadIdx.x; i < n_chunks; i += ST_THREADS) {
+        const uintptr_t ga = a_lo + ((uintptr_t)i << 4);
+        if (ga >= t_lo && ga + 16 <= t_hi) {
+            reinterpret_cast<int4*>(st_smem)[i] = ld_stream16(reinterpret_cast<const void*>(ga));
+        } else {                                                      // chunk straddles the tensor's first / last bytes
+            for (int k = 0; k < 16 / (int)sizeof(T); ++k) {
+                const uintptr_t ea = ga + k * sizeof(T);
+                reinterpret_cast<T*>(st_smem)[i * (16 / (int)sizeof(T)) + k] =
+                    (ea >= t_lo && ea + sizeof(T) <= t_hi) ? *reinterpret_cast<const T*>(ea) : Cvt<T>::st(0.f);
+            }
+        }
+    }
     if (threadIdx.x < 16) {
         int a = threadIdx.x >> 2, b = threadIdx.x & 3;
         s_f[threadIdx.x] = (p.flip ? p.f[a * 4 + b] : p.f[(3 - a) * 4 + (3 - b)]) * p.gain;
     }
     __syncthreads();
+    const T* sx = reinterpret_cast<const T*>(st_smem + (gb_lo - a_lo));                                // smem view of element e_lo
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = s_f[i];
-    int blk = blockIdx.x;
-    const int cb = blk % col_blocks; blk /= col_blocks;
-    const int rb = blk % row_blocks; blk /= row_blocks;
-    const int plane = blk;
-    const int ox0 = (cb * 128 + threadIdx.x) * VPT;
-    if (ox0 >= p.OW) return;
-    const int oy0 = rb * RW_ROWS;
-    const T* xp = (const T*)p.x + (int64_t)plane * p.H * p.W;
-    T* yp = (T*)p.y + (int64_t)plane * p.OH * p.OW;
-    const int ix0 = ox0 - p.padx0;
+    // rank-1 test: f[a][b] * f[0][0] == f[a][0] * f[0][b]  ->  f = fy (x) fx with fy[a] = f[a][0] / f[0][0], fx[b] = f[0][b]
+    bool sep = f[0] != 0.f;
+#pragma unroll
+    for (int a = 1; a < 4; ++a)
+#pragma unroll
+        for (int b = 1; b < 4; ++b) sep = sep && fabsf(f[a * 4 + b] * f[0] - f[a * 4] * f[b]) <= 1e-6f * fabsf(f[a * 4 + b] * f[0]) + 1e-30f;
+    float fx[4], fy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { fx[i] = f[i]; fy[i] = sep ? f[i * 4] / f[0] : 0.f; }
+
+    // ---- thread -> (plane_local, row group, column group)
+    int t = threadIdx.x;
+    const int cgi = t % g.cg; t /= g.cg;
+    const int rgi = t % g.rg; t /= g.rg;
+    const int pl = t;
+    if (pl >= planes) return;
+    const int ox0 = cgi * VPT;
+    const int ry0 = oy0 + rgi * ST_RPT;
+    if (ox0 >= p.OW || ry0 >= oy0 + rows) return;
     const int n_valid = min(VPT, p.OW - ox0);
-    float win[4][WIN];
-    auto load_row = [&](float (&dst)[WIN], int iy) {
-        const bool row_ok = iy >= 0 && iy < p.H;
-        const T* rp = xp + (int64_t)iy * p.W;
+    const T* sp = sx + (long long)pl * plane_elems - (long long)r_lo * p.W;                             // sp[iy * W + ix] for iy in [r_lo, r_hi)
+    T* yp = (T*)p.y + ((long long)(plane0 + pl) * p.OH) * p.OW;
+    const int row_end = min(ry0 + ST_RPT, oy0 + rows);
+
+    if (UP == 1) {
+        constexpr int WIN = VPT + 3;
+        const int ix0 = ox0 - p.padx0;
+        auto load_in = [&](float (&dst)[WIN], int iy) {
+            const bool rok = iy >= r_lo && iy < r_hi;
+            const T* rp = sp + (long long)iy * p.W;
 #pragma unroll
-        for (int j = 0; j < WIN; ++j) {
-            const int ix = ix0 + j;
-            dst[j] = (row_ok && ix >= 0 && ix < p.W) ? Cvt<T>::ld(rp[ix]) : 0.f;
+            for (int j = 0; j < WIN; ++j) {
+                const int ix = ix0 + j;
+                dst[j] = (rok && ix >= 0 && ix < p.W) ? Cvt<T>::ld(rp[ix]) : 0.f;
+            }
+        };
+        const int iy0 = ry0 - p.pady0;
+        if (sep) {
+            float h[4][VPT];                                                // horizontally filtered input rows (sliding window)
+            auto hrow = [&](float (&dst)[VPT], int iy) {
+                float in[WIN];
+                load_in(in, iy);
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) dst[k] = fx[0] * in[k] + fx[1] * in[k + 1] + fx[2] * in[k + 2] + fx[3] * in[k + 3];
+            };
+            hrow(h[0], iy0); hrow(h[1], iy0 + 1); hrow(h[2], iy0 + 2);
+#pragma unroll
+            for (int r = 0; r < ST_RPT; ++r) {
+                const int oy = ry0 + r;
+                if (oy >= row_end) break;
+                hrow(h[(r + 3) & 3], iy0 + r + 3);
+                float acc[VPT];
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    acc[k] = fy[0] * h[r & 3][k] + fy[1] * h[(r + 1) & 3][k] + fy[2] * h[(r + 2) & 3][k] + fy[3] * h[(r + 3) & 3][k];
+                store_row<T, VPT>(yp + (long long)oy * p.OW + ox0, acc, n_valid);
+            }
+        } else {
+            float win[4][WIN];
+            load_in(win[0], iy0); load_in(win[1], iy0 + 1); load_in(win[2], iy0 + 2);
+#pragma unroll
+            for (int r = 0; r < ST_RPT; ++r) {
+                const int oy = ry0 + r;
+                if (oy >= row_end) break;
+                load_in(win[(r + 3) & 3], iy0 + r + 3);
+                float acc[VPT];
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) acc[k] = 0.f;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                        for (int k = 0; k < VPT; ++k) acc[k] = fmaf(f[a * 4 + b], win[(r + a) & 3][k + b], acc[k]);
+                store_row<T, VPT>(yp + (long long)oy * p.OW + ox0, acc, n_valid);
+            }
         }
-    };
-    const int iy0 = oy0 - p.pady0;
-    load_row(win[0], iy0); load_row(win[1], iy0 + 1); load_row(win[2], iy0 + 2);
+    } else {
+        constexpr int WIN = VPT / 2 + 2;
+        const int ixb = (ox0 - p.padx0) >> 1;
+#pragma unroll 1
+        for (int oy = ry0; oy < row_end; ++oy) {
+            const int u0 = oy - p.pady0;
+            const int a0 = u0 & 1;
+            const int iyA = (u0 + a0) >> 1;
+            float rowA[WIN], rowB[WIN];
+            const bool okA = iyA >= r_lo && iyA < r_hi, okB = iyA + 1 >= r_lo && iyA + 1 < r_hi;
 #pragma unroll
-    for (int r = 0; r < RW_ROWS; ++r) {
-        const int oy = oy0 + r;
-        if (oy >= p.OH) break;
-        load_row(win[(r + 3) & 3], iy0 + r + 3);
-        float acc[VPT];
-#pragma unroll
-        for (int k = 0; k < VPT; ++k) acc[k] = 0.f;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-                for (int k = 0; k < VPT; ++k) acc[k] = fmaf(f[a * 4 + b], win[(r + a) & 3][k + b], acc[k]);
-        store_row<T, VPT>(yp + (int64_t)oy * p.OW + ox0, acc, n_valid);
+            for (int j = 0; j < WIN; ++j) {
+                const int ix = ixb + j;
+                const bool cok = ix >= 0 && ix < p.W;
+                rowA[j] = (cok && okA) ? Cvt<T>::ld(sp[(long long)iyA * p.W + ix]) : 0.f;
+                rowB[j] = (cok && okB) ? Cvt<T>::ld(sp[(long long)(iyA + 1) * p.W + ix]) : 0.f;
+            }
+            float acc[VPT];
+            // column parity pi = (ox0 - padx0) & 1 is uniform across the CTA (ox0 is a multiple of VPT): with it fixed,
+            // the tap parity b0 = (pi + k) & 1 and the window slot j0 = (k + pi + b0) >> 1 are compile-time per k.
+            if (((ox0 - p.padx0) & 1) == 0) up2_row<VPT, WIN, 0>(acc, rowA, rowB, f, a0);
+            else                            up2_row<VPT, WIN, 1>(acc, rowA, rowB, f, a0);
+            store_row<T, VPT>(yp + (long long)oy * p.OW + ox0, acc, n_valid);
+        }
     }
 }
 
 template <class T>
-__global__ void __launch_bounds__(128)
-upfirdn2d_rows_up2_kernel(UpfirdnParams p, int col_blocks, int row_blocks) {
+static bool staged_geometry(const UpfirdnParams& p, StagedGeom& g) {
     constexpr int VPT = VecOut<T>::VPT;
-    constexpr int WIN = VPT / 2 + 2;
-    __shared__ float s_f[16];
-    if (threadIdx.x < 16) {
-        int a = threadIdx.x >> 2, b = threadIdx.x & 3;
-        s_f[threadIdx.x] = (p.flip ? p.f[a * 4 + b] : p.f[(3 - a) * 4 + (3 - b)]) * p.gain;
+    g.cg = (p.OW + VPT - 1) / VPT;
+    if (g.cg > ST_THREADS) return false;
+    const int rg_plane = (p.OH + ST_RPT - 1) / ST_RPT;
+    const int es = (int)sizeof(T);
+    if (g.cg * rg_plane * 2 <= ST_THREADS) {                          // several whole planes per CTA
+        g.ppc = ST_THREADS / (g.cg * rg_plane);
+        g.rg = rg_plane; g.strip = p.OH; g.strips = 1;
+        while (g.ppc > 1 && (long long)g.ppc * p.H * p.W * es + 32 > 96 * 1024) --g.ppc;
+        g.smem_bytes = (int)((long long)g.ppc * p.H * p.W * es + 32);
+    } else {
+        g.ppc = 1;
+        g.rg = ST_THREADS / g.cg;
+        if (g.rg > rg_plane) g.rg = rg_plane;
+        g.strip = g.rg * ST_RPT;
+        g.strips = (p.OH + g.strip - 1) / g.strip;
+        const int in_rows = (p.upy == 1) ? g.strip + 3 : g.strip / 2 + 3;
+        g.smem_bytes = (int)((long long)in_rows * p.W * es + 32);
     }
-    __syncthreads();
-    float f[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = s_f[i];
-    int blk = blockIdx.x;
-    const int cb = blk % col_blocks; blk /= col_blocks;
-    const int rb = blk % row_blocks; blk /= row_blocks;
-    const int plane = blk;
-    const int ox0 = (cb * 128 + threadIdx.x) * VPT;
-    if (ox0 >= p.OW) return;
-    const int oy0 = rb * RW_ROWS;
-    const T* xp = (const T*)p.x + (int64_t)plane * p.H * p.W;
-    T* yp = (T*)p.y + (int64_t)plane * p.OH * p.OW;
-    const int n_valid = min(VPT, p.OW - ox0);
-    // first input column any of this lane's outputs can touch: floor((ox0 - padx0) / 2) (arithmetic shift = floor)
-    const int ixb = (ox0 - p.padx0) >> 1;
-    // per output column k and tap parity: b0 = first tap with even (ox + b - padx0)
-#pragma unroll 1
-    for (int r = 0; r < RW_ROWS; ++r) {
-        const int oy = oy0 + r;
-        if (oy >= p.OH) break;
-        const int u0 = oy - p.pady0;
-        const int a0 = u0 & 1;                                      // taps a0, a0 + 2 hit even rows of the zero-stuffed grid
-        const int iyA = (u0 + a0) >> 1;
-        float rowA[WIN], rowB[WIN];
-#pragma unroll
-        for (int j = 0; j < WIN; ++j) {
-            const int ix = ixb + j;
-            const bool cok = ix >= 0 && ix < p.W;
-            rowA[j] = (cok && iyA >= 0 && iyA < p.H) ? Cvt<T>::ld(xp[(int64_t)iyA * p.W + ix]) : 0.f;
-            rowB[j] = (cok && iyA + 1 >= 0 && iyA + 1 < p.H) ? Cvt<T>::ld(xp[(int64_t)(iyA + 1) * p.W + ix]) : 0.f;
-        }
-        float acc[VPT];
-#pragma unroll
-        for (int k = 0; k < VPT; ++k) {
-            const int v0 = ox0 + k - p.padx0;
-            const int b0 = v0 & 1;
-            const int j0 = ((v0 + b0) >> 1) - ixb;                  // 0 .. WIN-2
-            // select the four active taps without dynamic indexing (keeps f[] in registers)
-            const float fa0 = a0 ? (b0 ? f[5] : f[4]) : (b0 ? f[1] : f[0]);
-            const float fa1 = a0 ? (b0 ? f[7] : f[6]) : (b0 ? f[3] : f[2]);
-            const float fb0 = a0 ? (b0 ? f[13] : f[12]) : (b0 ? f[9] : f[8]);
-            const float fb1 = a0 ? (b0 ? f[15] : f[14]) : (b0 ? f[11] : f[10]);
-            float x00 = 0.f, x01 = 0.f, x10 = 0.f, x11 = 0.f;
-#pragma unroll
-            for (int j = 0; j < WIN - 1; ++j)                       // static indexing of the register window
-                if (j == j0) { x00 = rowA[j]; x01 = rowA[j + 1]; x10 = rowB[j]; x11 = rowB[j + 1]; }
-            acc[k] = fa0 * x00 + fa1 * x01 + fb0 * x10 + fb1 * x11;
-        }
-        store_row<T, VPT>(yp + (int64_t)oy * p.OW + ox0, acc, n_valid);
-    }
+    return g.smem_bytes <= 96 * 1024;
 }
 
 template <class T>
 static int run_typed(const UpfirdnParams& p, bool tiled_ok, cudaStream_t s) {
-    if (tiled_ok) {
-        constexpr int VPT = VecOut<T>::VPT;
-        const int col_blocks = (p.OW + 128 * VPT - 1) / (128 * VPT), row_blocks = (p.OH + RW_ROWS - 1) / RW_ROWS;
-        const int64_t blocks = (int64_t)col_blocks * row_blocks * p.N * p.C;
+    StagedGeom g;
+    if (tiled_ok && staged_geometry<T>(p, g)) {
+        const int n_planes = p.N * p.C;
+        const int64_t blocks = g.ppc > 1 ? (n_planes + g.ppc - 1) / g.ppc : (int64_t)n_planes * g.strips;
         if (blocks <= INT32_MAX) {
-            if (p.upx == 1) upfirdn2d_rows_up1_kernel<T><<<(int)blocks, 128, 0, s>>>(p, col_blocks, row_blocks);
-            else            upfirdn2d_rows_up2_kernel<T><<<(int)blocks, 128, 0, s>>>(p, col_blocks, row_blocks);
-            return launched("upfirdn2d_rows_kernel");
+            auto kern = (p.upx == 1) ? upfirdn2d_staged_kernel<T, 1> : upfirdn2d_staged_kernel<T, 2>;
+            if (g.smem_bytes > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                if (e != cudaSuccess) return fail(NBE_ECUDA, "upfirdn2d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            }
+            kern<<<(int)blocks, ST_THREADS, g.smem_bytes, s>>>(p, g, n_planes);
+            return launched("upfirdn2d_staged_kernel");
         }
     }
     const int64_t total = (int64_t)p.N * p.C * p.OH * p.OW;
