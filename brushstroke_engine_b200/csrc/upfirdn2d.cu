@@ -56,7 +56,7 @@ upfirdn2d_generic_kernel(UpfirdnParams p) {
 // streaming loads (no per-element index arithmetic, misaligned odd-length rows like 2R+1 do not matter).  Each thread
 // then walks RPT output rows of its column word with a sliding register window; rank-1 filters (everything
 // setup_filter builds from a 1-D tap list) take the separable path (4 + 4 FMAs per output instead of 16).  HBM-bound: algorithmic bytes = (numel(x) + numel(y)) * sizeof(T).
-constexpr int ST_THREADS = 256;
+constexpr int ST_THREADS = 128;
 constexpr int ST_RPT = 16;                                              // output rows per thread
 
 // Consecutive lanes own consecutive 4-byte words of an output row (1 fp32 column or 2 half/bf16 columns): shared-memory
