@@ -54,23 +54,25 @@ upfirdn2d_generic_kernel(UpfirdnParams p) {
 // A CTA owns either a strip of output rows of one (n,c) plane or a group of whole small planes.  Either way the input
 // it needs is ONE contiguous range of the flat tensor, so it is staged into shared memory with aligned 16-byte
 // streaming loads (no per-element index arithmetic, misaligned odd-length rows like 2R+1 do not matter).  Each thread
-// then walks RPT output rows of its column word with a sliding register window; rank-1 filters (everything
-// setup_filter builds from a 1-D tap list) take the separable path (4 + 4 FMAs per output instead of 16).  HBM-bound: algorithmic bytes = (numel(x) + numel(y)) * sizeof(T).
+// then produces VPT consecutive columns x RPT rows from a sliding register window; rank-1 filters (everything
+// setup_filter builds from a 1-D tap list) take the separable path (4 + 4 FMAs per output instead of 16).  Stores are
+// 16-byte streaming vectors.  HBM-bound: algorithmic bytes = (numel(x) + numel(y)) * sizeof(T).
 constexpr int ST_THREADS = 128;
-constexpr int ST_RPT = 16;                                              // output rows per thread
+constexpr int ST_RPT = 8;                                               // output rows per thread
 
-// Consecutive lanes own consecutive 4-byte words of an output row (1 fp32 column or 2 half/bf16 columns): shared-memory
-// window reads are then stride-1 across the warp (no bank conflicts) and every warp store is one full 128-byte line.
-template <class T> struct VecOut;
-template <> struct VecOut<float> { static constexpr int VPT = 1; };
-template <> struct VecOut<__half> { static constexpr int VPT = 2; };
-template <> struct VecOut<__nv_bfloat16> { static constexpr int VPT = 2; };
+template <class T> struct VecOut;                                       // VPT outputs packed into one 16-byte store
+template <> struct VecOut<float> { static constexpr int VPT = 4; };
+template <> struct VecOut<__half> { static constexpr int VPT = 8; };
+template <> struct VecOut<__nv_bfloat16> { static constexpr int VPT = 8; };
 
 template <class T, int VPT>
 __device__ __forceinline__ void store_row(T* dst, const float (&acc)[VPT], int n_valid) {
-    if (VPT == 2 && n_valid == 2 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
-        T pair[2] = {Cvt<T>::st(acc[0]), Cvt<T>::st(acc[VPT - 1])};
-        *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(pair);
+    if (n_valid == VPT && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        int4 v;
+        T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) e[k] = Cvt<T>::st(acc[k]);
+        st_stream16(dst, v);
     } else {
 #pragma unroll
         for (int k = 0; k < VPT; ++k) if (k < n_valid) dst[k] = Cvt<T>::st(acc[k]);
@@ -227,7 +229,7 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
             }
         }
     } else {
-        constexpr int WIN = (VPT + 1) / 2 + 2;
+        constexpr int WIN = VPT / 2 + 2;
         const int ixb = (ox0 - p.padx0) >> 1;
 #pragma unroll 1
         for (int oy = ry0; oy < row_end; ++oy) {
