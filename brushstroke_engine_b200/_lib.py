@@ -37,6 +37,7 @@ _SIGNATURES = {
     'nbe_conv_tc_bf16_ex': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P, _P, _L, _F, _P, _F, _F, _F, _P, _P],
     'nbe_conv_tc_bf16_torgb': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _F, _P, _F, _F, _F, _P, _P, _P, _P, _F, _P, _P, _I, _P],
     'nbe_enc_conv7x7_bf16': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    'nbe_enc_conv7x7_tc_bf16': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     'nbe_reflect_border_nhwc_bf16': [_P, _I, _I, _I, _I, _I, _P],
     'nbe_bilinear2x_pad_nhwc_bf16': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'nbe_torgb_triad': [_P, _I, _I, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P],

@@ -459,6 +459,136 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Encoder first layer on the tensor pipe: conv7x7(1 -> Cout <= 64... here N = Cout, multiple of 16) with reflect
+// padding 3 as ONE K = 64 GEMM per 128-pixel tile (49 taps + 15 zero columns).  The im2col A tile does not exist in
+// memory: each thread writes the 49 taps of ITS pixel (bf16) straight into the 128-byte-swizzled K-major smem layout
+// the UMMA descriptor expects (16-byte chunk c of row r lives at chunk c ^ (r & 7)), a fence.proxy.async makes the
+// generic-proxy writes visible to the tensor core, one thread issues the four K = 16 MMAs, and the usual TMEM
+// epilogue applies the folded-BatchNorm bias + LeakyReLU and writes the interior of the reflect-padded NHWC buffer.
+constexpr int E7T_TW = 16, E7T_TH = 8;                             // 16 x 8 = 128 output pixels per tile
+
+__global__ void __launch_bounds__(128)
+enc_conv7x7_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wq, const float* __restrict__ bias,
+                      __nv_bfloat16* __restrict__ y, int N, int H, int W, int Cout, int y_cs, float neg_slope, int preproc,
+                      int tiles_x, int tiles_y, uint32_t idesc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                         // 128 rows x 128 B
+    uint8_t* smem_b = smem + 128 * 128;                             // Cout rows x 128 B
+    float* s_in = reinterpret_cast<float*>(smem_b + 64 * 128);      // [E7T_TH + 6][E7T_TW + 6]
+    float* s_bias = s_in + (E7T_TH + 6) * (E7T_TW + 6);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_bias + 64);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // weights -> swizzled smem B tile (row o = out channel, 64 K values = 8 chunks of 16 B), once per CTA
+    for (int i = threadIdx.x; i < Cout * 8; i += 128) {
+        const int o = i >> 3, c = i & 7;
+        const int4 v = *reinterpret_cast<const int4*>(wq + o * 64 + c * 8);
+        *reinterpret_cast<int4*>(smem_b + o * 128 + ((c ^ (o & 7)) << 4)) = v;
+    }
+    if (threadIdx.x < Cout) s_bias[threadIdx.x] = bias[threadIdx.x];
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int m = threadIdx.x;                                      // pixel / accumulator row of this thread
+    const int ly = m / E7T_TW, lx = m % E7T_TW;
+    const int total = tiles_x * tiles_y * N;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % tiles_x; t /= tiles_x;
+        const int ty = t % tiles_y; t /= tiles_y;
+        const int n = t;
+        const int ty0 = ty * E7T_TH, tx0 = tx * E7T_TW;
+        for (int i = threadIdx.x; i < (E7T_TH + 6) * (E7T_TW + 6); i += 128) {
+            const int r = i / (E7T_TW + 6), c = i - r * (E7T_TW + 6);
+            int iy = ty0 + r - 3, ix = tx0 + c - 3;
+            iy = iy < 0 ? -iy : iy; iy = iy >= H ? 2 * H - 2 - iy : iy;     // reflect
+            ix = ix < 0 ? -ix : ix; ix = ix >= W ? 2 * W - 2 - ix : ix;
+            iy = min(max(iy, 0), H - 1); ix = min(max(ix, 0), W - 1);       // tiles hanging over the border: any in-range value
+            float v = x[((long long)n * H + iy) * W + ix];
+            if (preproc == 1) v = 1.f - v;
+            else if (preproc == 2) v = (1.f - v) * 2.f - 1.f;
+            s_in[i] = v;
+        }
+        __syncthreads();
+        // this thread's im2col row: taps 0..48 (kh * 7 + kw), zero padded to 64, as 8 chunks of 8 bf16
+        {
+            float taps[56];
+#pragma unroll
+            for (int kh = 0; kh < 7; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 7; ++kw) taps[kh * 7 + kw] = s_in[(ly + kh) * (E7T_TW + 6) + lx + kw];
+#pragma unroll
+            for (int k = 49; k < 56; ++k) taps[k] = 0.f;
+            uint8_t* row = smem_a + m * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                int4 v = make_int4(0, 0, 0, 0);
+                if (c < 7) {
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(taps[c * 8 + 2 * e], taps[c * 8 + 2 * e + 1]);
+                }
+                *reinterpret_cast<int4*>(row + ((c ^ (m & 7)) << 4)) = v;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the async (tensor) proxy
+        tcgen05_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tcgen05_fence_after();
+            const uint64_t a_desc = umma_smem_desc(smem_u32(smem_a));
+            const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, k != 0);
+            umma_commit(smem_u32(bar));
+        }
+        mbar_wait(smem_u32(bar), phase);
+        phase ^= 1;
+        tcgen05_fence_after();
+        const int oy = ty0 + ly, ox = tx0 + lx;
+        const bool ok = oy < H && ox < W;
+        __nv_bfloat16* yp = y + (((long long)n * (H + 2) + oy + 1) * (W + 2) + ox + 1) * y_cs;
+        for (int c0 = 0; c0 < Cout; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            if (ok) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (c0 + g * 8 >= Cout) break;
+                    int4 out;
+                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a = __uint_as_float(v[g * 8 + 2 * e]) + s_bias[c0 + g * 8 + 2 * e];
+                        float b = __uint_as_float(v[g * 8 + 2 * e + 1]) + s_bias[c0 + g * 8 + 2 * e + 1];
+                        a = a > 0.f ? a : a * neg_slope;
+                        b = b > 0.f ? b : b * neg_slope;
+                        o2[e] = __floats2bfloat162_rn(a, b);
+                    }
+                    *reinterpret_cast<int4*>(yp + c0 + g * 8) = out;
+                }
+            }
+        }
+        tcgen05_fence_before();
+        __syncthreads();                                            // A tile / s_in / TMEM accumulator are reused by the next tile
+        tcgen05_fence_after();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(64u) : "memory");
+}
+
 // [Cout][Cin][K][K] f32 -> [KK][Cout][Cin_pad] bf16 (flip = true convolution)
 __global__ void prepare_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wq, int Cout, int Cin, int Cin_pad, int KK, int flip) {
     const int64_t total = (int64_t)KK * Cout * Cin_pad;
@@ -662,4 +792,23 @@ extern "C" int nbe_conv_tc_bf16_torgb(const void* x, const void* wq, void* y,
     TorgbArgs a{rgb_w, rgb_styles, rgb_bias, rgb_colors, rgb_clamp, img, uvs, write_y};
     return conv_tc_impl(x, wq, y ? y : (void*)x, N, OH, OW, Cin, x_cs, Cout, y_cs, 3, valid, 1, 0, 0, OW, (int64_t)OH * OW,
                         dcoef, noise, noise_sn, noise_gain, bias, alpha, gain, clamp, nullptr, &a, stream);
+}
+
+extern "C" int nbe_enc_conv7x7_tc_bf16(const float* x, const void* wq, const float* bias, void* y, int N, int H, int W, int Cout,
+                                       int y_cs, float neg_slope, int preproc, nbe_stream_t stream) {
+    NBE_REQUIRE(x && wq && bias && y && N >= 0 && H >= 4 && W >= 4, "enc_conv7x7_tc: bad arguments");
+    NBE_REQUIRE(Cout % 16 == 0 && Cout >= 16 && Cout <= 64 && y_cs % 8 == 0 && y_cs >= Cout, "enc_conv7x7_tc: Cout must be 16..64 in steps of 16");
+    NBE_REQUIRE(preproc >= 0 && preproc <= 2, "enc_conv7x7_tc: unknown preprocessing %d", preproc);
+    NBE_REQUIRE((((uintptr_t)wq | (uintptr_t)y) & 15) == 0, "enc_conv7x7_tc: tensors must be 16-byte aligned");
+    if (N == 0) return NBE_OK;
+    const int tiles_x = (W + E7T_TW - 1) / E7T_TW, tiles_y = (H + E7T_TH - 1) / E7T_TH;
+    const int64_t total = (int64_t)tiles_x * tiles_y * N;
+    NBE_REQUIRE(total <= INT32_MAX, "enc_conv7x7_tc: too many tiles");
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const size_t smem = 1024 + 128 * 128 + 64 * 128 + (E7T_TH + 6) * (E7T_TW + 6) * 4 + 64 * 4 + 64;
+    int grid = kNumSMs * 4;
+    if (total < grid) grid = (int)total;
+    enc_conv7x7_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)wq, bias, (__nv_bfloat16*)y, N, H, W, Cout,
+                                                                   y_cs, neg_slope, preproc, tiles_x, tiles_y, idesc);
+    return launched("enc_conv7x7_tc_kernel");
 }

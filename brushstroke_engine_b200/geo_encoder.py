@@ -65,6 +65,9 @@ class GeometryEncoder:
             with torch.cuda.device(self.device):
                 w0 = self._layers[0][0]
                 self._w7 = w0.reshape(w0.shape[0], 49).contiguous()
+                self._w7q = torch.zeros((w0.shape[0], 64), dtype=torch.bfloat16, device=self.device)
+                self._w7q[:, :49] = self._w7.to(torch.bfloat16)
+                self._tc7 = w0.shape[0] % 16 == 0 and w0.shape[0] <= 64
                 self._wq = [None]
                 for (w, b, stride, pad, up) in self._layers[1:]:
                     cout, cin = w.shape[0], w.shape[1]
@@ -141,8 +144,12 @@ class GeometryEncoder:
             wi = 0
             w, b, _, _, _ = self._layers[0]
             cur = ws[wi]; wi += 1
-            _lib.call('nbe_enc_conv7x7_bf16', _lib.ptr(geom), _lib.ptr(self._w7), _lib.ptr(b), _lib.ptr(cur), B, H, W, w.shape[0],
-                      cur.shape[3], slope, PREPROC_CODE[self.cfg.preproc_type], st)
+            if self._tc7:
+                _lib.call('nbe_enc_conv7x7_tc_bf16', _lib.ptr(geom), _lib.ptr(self._w7q), _lib.ptr(b), _lib.ptr(cur), B, H, W, w.shape[0],
+                          cur.shape[3], slope, PREPROC_CODE[self.cfg.preproc_type], st)
+            else:
+                _lib.call('nbe_enc_conv7x7_bf16', _lib.ptr(geom), _lib.ptr(self._w7), _lib.ptr(b), _lib.ptr(cur), B, H, W, w.shape[0],
+                          cur.shape[3], slope, PREPROC_CODE[self.cfg.preproc_type], st)
             _lib.call('nbe_reflect_border_nhwc_bf16', _lib.ptr(cur), B, H + 2, W + 2, w.shape[0], cur.shape[3], st)
             h = H
             cur_view = None            # (ptr, cs, C) of the latest un-padded feature map when it lives in a destination buffer

@@ -185,6 +185,11 @@ int nbe_torgb_triad(const void* x, int x_is_bf16, int x_cs, const float* w, cons
 int nbe_enc_conv7x7_bf16(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, int Cout,
                          int y_cs, float neg_slope, int preproc, nbe_stream_t stream);
 
+/* The same layer as one K = 64 tensor-core GEMM per 128-pixel tile (49 taps + 15 zero columns; the im2col tile is written
+ * directly in the swizzled UMMA smem layout).  wq: [Cout,64] bf16 = BN-folded weights, taps kh*7+kw in columns 0..48, zeros after. */
+int nbe_enc_conv7x7_tc_bf16(const float* x, const void* wq, const float* bias, void* y, int N, int H, int W, int Cout,
+                            int y_cs, float neg_slope, int preproc, nbe_stream_t stream);
+
 /* Fill the 1-pixel border of buf [N,Hp,Wp,cs] (first C channels) by reflection of its interior (torch padding_mode='reflect'). */
 int nbe_reflect_border_nhwc_bf16(void* buf, int N, int Hp, int Wp, int C, int cs, nbe_stream_t stream);
 
