@@ -1,0 +1,173 @@
+// 4x4 FIR + modulated-conv epilogue on NHWC bf16: the second half of an up-sampling SynthesisLayer when the
+// transposed convolution runs at its algorithmic cost (nbe_convT3x3s2_flat_bf16):
+//   y[n,oy,ox,c] = post( fgain * sum_{a,b} ft[a,b] * T[n, oy+a-pad, ox+b-pad, c] )     (upfirdn2d after conv_transpose2d,
+//   SG2/torch_utils/ops/conv2d_resample.py:139 ; T is zero outside [0,TH) x [0,TW))
+//   post(v) = clamp(lrelu(v * scale[n,c] + noise[n,oy,ox] * noise_gain + bias[c]) * gain) * next_scale[n,c]
+//   (SG2/training/networks.py:71-75,386-390).
+// One thread = one output column x 8 channels (16 bytes), walking 8 output rows with a sliding window of horizontally
+// filtered rows (rank-1 filters: 4 + 4 FMAs per output; general filters: 16).  Consecutive threads walk the channel
+// vectors of a pixel, then the pixels of a row, so every global access is a whole 32-byte sector and the 4x overlap
+// between neighbouring windows is served by L1.  HBM-bound: (TH*TW + OH*OW) * C * 2 bytes per image.
+#include "common.cuh"
+
+namespace nbe {
+
+constexpr int FIR_RPT = 8;
+
+struct FirParams {
+    const __nv_bfloat16* t; __nv_bfloat16* y; const float* f;
+    int N, OH, OW, C, TH, TW, pad;
+    int t_cs; long long t_row_pitch, t_img_pitch;
+    int y_cs; long long y_row_pitch, y_img_pitch;
+    float fgain;
+    const float* scale; const float* noise; long long noise_sn; float noise_gain; const float* bias;
+    float alpha, gain, clamp; const float* next_scale;
+    int row_groups;
+};
+
+__device__ __forceinline__ void unpack8(const int4& raw, float (&v)[8]) {
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f2 = __bfloat1622float2(h2[k]); v[2 * k] = f2.x; v[2 * k + 1] = f2.y; }
+}
+
+__global__ void __launch_bounds__(256)
+fir_act_nhwc_kernel(const FirParams p) {
+    __shared__ float s_f[16];
+    if (threadIdx.x < 16) {
+        const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
+        s_f[threadIdx.x] = p.f[(3 - a) * 4 + (3 - b)] * p.fgain;      // flip_filter = False
+    }
+    __syncthreads();
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = s_f[i];
+    bool sep = f[0] != 0.f;
+#pragma unroll
+    for (int a = 1; a < 4; ++a)
+#pragma unroll
+        for (int b = 1; b < 4; ++b) sep = sep && fabsf(f[a * 4 + b] * f[0] - f[a * 4] * f[b]) <= 1e-6f * fabsf(f[a * 4 + b] * f[0]) + 1e-30f;
+    float fx[4], fy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { fx[i] = f[i]; fy[i] = sep ? f[i * 4] / f[0] : 0.f; }
+
+    const int CV = p.C >> 3;
+    const int n = blockIdx.x / p.row_groups;
+    const int oy0 = (blockIdx.x - n * p.row_groups) * FIR_RPT;
+    const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (idx >= p.OW * CV) return;
+    const int cv = idx % CV, ox = idx / CV;
+    const __nv_bfloat16* tp = p.t + (long long)n * p.t_img_pitch * p.t_cs + cv * 8;
+    const int ix0 = ox - p.pad;
+
+    // per-channel epilogue vectors
+    float sc[8], bs[8], ns[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cv * 8 + k;
+        sc[k] = p.scale ? p.scale[(long long)n * p.C + c] : 1.f;
+        bs[k] = p.bias ? p.bias[c] : 0.f;
+        ns[k] = p.next_scale ? p.next_scale[(long long)n * p.C + c] : 1.f;
+    }
+    const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
+
+    auto load_px = [&](int iy, int ix, float (&v)[8]) {
+        if (iy >= 0 && iy < p.TH && ix >= 0 && ix < p.TW) {
+            const int4 raw = *reinterpret_cast<const int4*>(tp + ((long long)iy * p.t_row_pitch + ix) * p.t_cs);
+            unpack8(raw, v);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = 0.f;
+        }
+    };
+    auto finish = [&](int oy, float (&acc)[8]) {
+        float nz = 0.f;
+        if (p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
+        int4 outv;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
+        float r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float a = acc[k] * sc[k] + nz + bs[k];
+            a *= (a > 0.f) ? pos_gain : neg_gain;
+            if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
+            r[k] = a * ns[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o2[k] = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
+        st_stream16(p.y + (((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs + cv * 8), outv);
+    };
+
+    const int iy0 = oy0 - p.pad;
+    if (sep) {
+        float h[4][8];
+        auto hrow = [&](float (&dst)[8], int iy) {
+            float v0[8], v1[8], v2[8], v3[8];
+            load_px(iy, ix0, v0); load_px(iy, ix0 + 1, v1); load_px(iy, ix0 + 2, v2); load_px(iy, ix0 + 3, v3);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k] = fx[0] * v0[k] + fx[1] * v1[k] + fx[2] * v2[k] + fx[3] * v3[k];
+        };
+        hrow(h[0], iy0); hrow(h[1], iy0 + 1); hrow(h[2], iy0 + 2);
+#pragma unroll
+        for (int r = 0; r < FIR_RPT; ++r) {
+            const int oy = oy0 + r;
+            if (oy >= p.OH) break;
+            hrow(h[(r + 3) & 3], iy0 + r + 3);
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                acc[k] = fy[0] * h[r & 3][k] + fy[1] * h[(r + 1) & 3][k] + fy[2] * h[(r + 2) & 3][k] + fy[3] * h[(r + 3) & 3][k];
+            finish(oy, acc);
+        }
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < FIR_RPT; ++r) {
+            const int oy = oy0 + r;
+            if (oy >= p.OH) break;
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    float v[8];
+                    load_px(oy - p.pad + a, ix0 + b, v);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[a * 4 + b], v[k], acc[k]);
+                }
+            finish(oy, acc);
+        }
+    }
+}
+
+}  // namespace nbe
+
+using namespace nbe;
+
+extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int N, int OH, int OW, int C, int TH, int TW, int pad,
+                                     int t_cs, int64_t t_row_pitch, int64_t t_img_pitch,
+                                     int y_cs, int64_t y_row_pitch, int64_t y_img_pitch, float fgain,
+                                     const float* scale, const float* noise, int64_t noise_sn, float noise_gain, const float* bias,
+                                     float alpha, float gain, float clamp, const float* next_scale, nbe_stream_t stream) {
+    NBE_REQUIRE(t && f && y && N >= 0 && OH >= 1 && OW >= 1 && C >= 8 && C % 8 == 0, "fir_act_nhwc: bad arguments");
+    NBE_REQUIRE(TH >= 1 && TW >= 1 && pad >= 0, "fir_act_nhwc: bad input extent");
+    NBE_REQUIRE(OH == TH + 2 * pad - 3 && OW == TW + 2 * pad - 3, "fir_act_nhwc: output %dx%d does not match input %dx%d, pad %d, 4x4 filter", OH, OW, TH, TW, pad);
+    NBE_REQUIRE(t_cs % 8 == 0 && t_cs >= C && y_cs % 8 == 0 && y_cs >= C, "fir_act_nhwc: channel strides must be multiples of 8");
+    NBE_REQUIRE(t_row_pitch >= TW && t_img_pitch >= t_row_pitch * TH && y_row_pitch >= OW && y_img_pitch >= y_row_pitch * OH, "fir_act_nhwc: bad pitches");
+    NBE_REQUIRE((((uintptr_t)t | (uintptr_t)y) & 15) == 0, "fir_act_nhwc: tensors must be 16-byte aligned");
+    if (N == 0) return NBE_OK;
+    FirParams p;
+    p.t = (const __nv_bfloat16*)t; p.y = (__nv_bfloat16*)y; p.f = f; p.N = N; p.OH = OH; p.OW = OW; p.C = C; p.TH = TH; p.TW = TW; p.pad = pad;
+    p.t_cs = t_cs; p.t_row_pitch = t_row_pitch; p.t_img_pitch = t_img_pitch; p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch;
+    p.fgain = fgain; p.scale = scale; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain; p.bias = bias;
+    p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.next_scale = next_scale;
+    p.row_groups = (OH + FIR_RPT - 1) / FIR_RPT;
+    const int64_t gx = (int64_t)N * p.row_groups;
+    NBE_REQUIRE(gx <= INT32_MAX, "fir_act_nhwc: too many row groups");
+    const int per_row = OW * (C / 8);
+    dim3 grid((unsigned)gx, (per_row + 255) / 256);
+    NBE_REQUIRE(grid.y <= 65535u, "fir_act_nhwc: rows too wide");
+    fir_act_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    return launched("fir_act_nhwc_kernel");
+}

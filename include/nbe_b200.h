@@ -152,6 +152,42 @@ int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
                         const float* bias, float alpha, float gain, float clamp, const float* next_scale,
                         nbe_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Flat" tensor-core convolutions: activations are NHWC bf16 whose rows are stored with a pitch x_pitch >= W + 1 and ZERO
+ * gap columns, so that every filter tap is a constant row shift of the [positions x channels] matrix (see csrc/conv_flat.cu).
+ * Cout must be 128.  wq as produced by nbe_prepare_weights_bf16.
+ */
+
+/* 3x3 stride-1 modulated convolution + the fused epilogue of nbe_conv_tc_bf16.
+ * valid = 0: x is [N, OH, x_pitch >= OW+1, x_cs] (zero gap columns supply the padding);
+ * valid = 1: x is [N, OH+2, x_pitch >= OW+2, x_cs] and already contains the 1-pixel halo (e.g. the FIR-upsampled U).
+ * y element (n,oy,ox,c) -> y[(n*y_img_pitch + oy*y_row_pitch + ox)*y_cs + c]; gap columns of y are never written. */
+int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
+                          int N, int OH, int OW, int Cin, int x_cs, int x_pitch, int valid, int Cout, int y_cs,
+                          int64_t y_row_pitch, int64_t y_img_pitch,
+                          const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                          const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                          nbe_stream_t stream);
+
+/* Transposed 3x3 convolution, stride 2, at its algorithmic cost (9 taps per INPUT pixel):
+ *   T[n, 2Y+kh, 2X+kw, o] += dcoef[n,o] * sum_i wq[kh*3+kw][o][i] * x[n,Y,X,i]     -> T is (2H+1) x (2W+1)
+ * = F.conv_transpose2d(x, w, stride=2) of the up-sampling path SG2/torch_utils/ops/conv2d_resample.py:124-138
+ * (wq prepared with flip = 0).  x: [N, H, x_pitch >= W+1, x_cs] with zero gap columns (already modulated).
+ * The four output parity classes are four TMEM accumulators of one pass over x. */
+int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_out,
+                             int N, int H, int W, int Cin, int x_cs, int x_pitch, int Cout, int t_cs,
+                             int64_t t_row_pitch, int64_t t_img_pitch, const float* dcoef, nbe_stream_t stream);
+
+/* 4x4 FIR (pad `pad`, filter gain fgain) followed by the SynthesisLayer epilogue, NHWC bf16 -> NHWC bf16:
+ *   y = clamp(lrelu(fgain * FIR(T) * scale[n,c] + noise * noise_gain + bias[c]) * gain) * next_scale[n,c]
+ * T: [N, TH, TW] valid extent (zero outside) with pitches; OH = TH + 2*pad - 3.  Replaces upfirdn2d after the transposed
+ * conv (conv2d_resample.py:139) + fma/bias_act (SG2/training/networks.py:71-75, 386-390). */
+int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int N, int OH, int OW, int C, int TH, int TW, int pad,
+                          int t_cs, int64_t t_row_pitch, int64_t t_img_pitch,
+                          int y_cs, int64_t y_row_pitch, int64_t y_img_pitch, float fgain,
+                          const float* scale, const float* noise, int64_t noise_sn, float noise_gain, const float* bias,
+                          float alpha, float gain, float clamp, const float* next_scale, nbe_stream_t stream);
+
 /* The last synthesis layer with ToRGB fused into its epilogue (SynthesisBlock.forward networks.py:663-672 for the last
  * block): the 3x3 modulated conv of nbe_conv_tc_bf16 followed, per pixel and still in registers, by the 1x1 modulated
  * ToRGB (rgb_w [3,Cout] * rgb_styles [N,Cout], no demodulation), bias, clamp, softmax over the three UVS logits and the

@@ -1,0 +1,148 @@
+"""GPU parity of the flat shifted-window tensor-core kernels (3x3 conv over zero-gapped rows, stride-2 transposed conv as
+four parity classes) and the NHWC FIR + epilogue kernel, against float64 torch references on the same bf16 operands."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from brushstroke_engine_b200 import _lib
+from oracle import neube_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+SQ2 = float(np.sqrt(2))
+
+
+def md(a, b):
+    return float((torch.as_tensor(a).detach().cpu().double() - torch.as_tensor(b).detach().cpu().double()).abs().max())
+
+
+def pitched(x_nchw, pitch, cs, rows=None):
+    """NCHW float -> zero-initialised NHWC bf16 [N, rows or H, pitch, cs] with the data in [:, :H, :W, :C]."""
+    N, C, H, W = x_nchw.shape
+    buf = torch.zeros((N, rows or H, pitch, cs), dtype=torch.bfloat16, device=DEV)
+    buf[:, :H, :W, :C] = x_nchw.to(DEV).permute(0, 2, 3, 1).to(torch.bfloat16)
+    return buf
+
+
+def prep_w(w, flip):
+    cout, cin = w.shape[:2]
+    wd = w.to(DEV).contiguous()
+    wq = torch.empty((9, cout, (cin + 63) // 64 * 64), dtype=torch.bfloat16, device=DEV)
+    _lib.call('nbe_prepare_weights_bf16', _lib.ptr(wd), _lib.ptr(wq), cout, cin, 3, flip, _lib.stream())
+    torch.cuda.synchronize()
+    return wq
+
+
+@pytest.mark.parametrize('R,cin,B,gap', [(4, 128, 3, 1), (8, 128, 5, 1), (16, 64, 2, 3), (32, 144, 2, 1), (64, 384, 1, 1), (64, 128, 3, 1), (128, 128, 1, 1)])
+@pytest.mark.parametrize('valid', [0, 1])
+def test_conv3x3_flat(R, cin, B, gap, valid):
+    g = torch.Generator().manual_seed(R + cin + B + valid)
+    IH = R + 2 if valid else R
+    x = torch.randn(B, cin, IH, IH, generator=g)
+    w = torch.randn(128, cin, 3, 3, generator=g) / np.sqrt(cin * 9)
+    d = torch.rand(B, 128, generator=g) + 0.5
+    ns = torch.rand(B, 128, generator=g) + 0.5
+    noise = torch.randn(B, R, R, generator=g)
+    bias = torch.randn(128, generator=g) * 0.1
+    x_cs = cin + 8
+    pitch = IH + gap
+    xq = pitched(x, pitch, x_cs)
+    wq = prep_w(w, 0)
+    y_pitch = R + 2
+    y = torch.full((B, R, y_pitch, 136), 5.0, dtype=torch.bfloat16, device=DEV)
+    dd, nn, bb, nsd = d.to(DEV), noise.to(DEV), bias.to(DEV), ns.to(DEV)
+    _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(xq), _lib.ptr(wq), _lib.ptr(y), B, R, R, cin, x_cs, pitch, valid, 128, 136,
+              y_pitch, R * y_pitch, _lib.ptr(dd), _lib.ptr(nn), R * R, 0.5, _lib.ptr(bb), 0.2, SQ2, 256.0, _lib.ptr(nsd), _lib.stream())
+    torch.cuda.synchronize()
+    acc = F.conv2d(x.to(torch.bfloat16).double(), w.to(torch.bfloat16).double(), padding=0 if valid else 1)
+    ref = acc * d.double()[:, :, None, None] + 0.5 * noise.double()[:, None] + bias.double()[None, :, None, None]
+    ref = (torch.where(ref > 0, ref, ref * 0.2) * SQ2).clamp(-256, 256) * ns.double()[:, :, None, None]
+    got = y[:, :, :R, :128].permute(0, 3, 1, 2).float()
+    assert md(got, ref) < 1e-2 * max(float(ref.abs().max()), 1.0)
+    assert float((y[:, :, R:, :].float() - 5.0).abs().max()) == 0          # gap columns of the output untouched
+    assert float((y[..., 128:].float() - 5.0).abs().max()) == 0
+
+
+@pytest.mark.parametrize('H,cin,B,gap', [(4, 128, 3, 1), (8, 128, 2, 2), (16, 144, 2, 1), (32, 384, 1, 1), (64, 128, 2, 1)])
+def test_convT_flat_matches_conv_transpose2d(H, cin, B, gap):
+    g = torch.Generator().manual_seed(H * 3 + cin)
+    x = torch.randn(B, cin, H, H, generator=g)
+    w = torch.randn(128, cin, 3, 3, generator=g) / np.sqrt(cin * 9)
+    d = (torch.rand(B, 128, generator=g) + 0.5)
+    pitch = H + gap
+    xq = pitched(x, pitch, cin)
+    wq = prep_w(w, 0)
+    TP = 2 * H + 2
+    t = torch.full((B, TP, TP, 128), 9.0, dtype=torch.bfloat16, device=DEV)
+    dd = d.to(DEV)
+    _lib.call('nbe_convT3x3s2_flat_bf16', _lib.ptr(xq), _lib.ptr(wq), _lib.ptr(t), B, H, H, cin, cin, pitch, 128, 128, TP, TP * TP,
+              _lib.ptr(dd), _lib.stream())
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(x.to(torch.bfloat16).double(), w.to(torch.bfloat16).double().transpose(0, 1), stride=2) * d.double()[:, :, None, None]
+    got = t[:, :2 * H + 1, :2 * H + 1].permute(0, 3, 1, 2).float()
+    assert md(got, ref) < 1e-2 * max(float(ref.abs().max()), 1.0)
+    assert float((t[:, 2 * H + 1:].float() - 9.0).abs().max()) == 0 and float((t[:, :, 2 * H + 1:].float() - 9.0).abs().max()) == 0
+
+
+@pytest.mark.parametrize('H,C,B', [(4, 128, 2), (16, 128, 3), (64, 128, 1)])
+def test_fir_act_nhwc(H, C, B):
+    g = torch.Generator().manual_seed(H + 7)
+    TH = 2 * H + 1
+    tt = torch.randn(B, C, TH, TH, generator=g)
+    f4 = O.setup_filter([1, 3, 3, 1])
+    sc = torch.rand(B, C, generator=g) + 0.5
+    ns = torch.rand(B, C, generator=g) + 0.5
+    noise = torch.randn(B, 2 * H, 2 * H, generator=g)
+    bias = torch.randn(C, generator=g) * 0.1
+    TP = TH + 1
+    tq = pitched(tt, TP, C, rows=TP)
+    yp = 2 * H + 1
+    y = torch.full((B, 2 * H, yp, C), 3.0, dtype=torch.bfloat16, device=DEV)
+    fd, scd, nsd, nd, bd = f4.to(DEV), sc.to(DEV), ns.to(DEV), noise.to(DEV), bias.to(DEV)
+    _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(tq), _lib.ptr(fd), _lib.ptr(y), B, 2 * H, 2 * H, C, TH, TH, 1, C, TP, TP * TP,
+              C, yp, 2 * H * yp, 4.0, _lib.ptr(scd), _lib.ptr(nd), 4 * H * H, 0.3, _lib.ptr(bd), 0.2, SQ2, 256.0, _lib.ptr(nsd), _lib.stream())
+    torch.cuda.synchronize()
+    ref = O.upfirdn2d(tt.to(torch.bfloat16).double(), f4, padding=[1, 1, 1, 1], gain=4.0)
+    ref = ref * sc.double()[:, :, None, None] + 0.3 * noise.double()[:, None] + bias.double()[None, :, None, None]
+    ref = (torch.where(ref > 0, ref, ref * 0.2) * SQ2).clamp(-256, 256) * ns.double()[:, :, None, None]
+    got = y[:, :, :2 * H].permute(0, 3, 1, 2).float()
+    assert md(got, ref) < 1e-2 * max(float(ref.abs().max()), 1.0)
+    assert float((y[:, :, 2 * H:].float() - 3.0).abs().max()) == 0
+    # a non-separable filter takes the general 16-tap path
+    fr = torch.rand(4, 4, generator=g)
+    frd = fr.to(DEV)
+    _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(tq), _lib.ptr(frd), _lib.ptr(y), B, 2 * H, 2 * H, C, TH, TH, 1, C, TP, TP * TP,
+              C, yp, 2 * H * yp, 1.0, None, None, 0, 0.0, None, 1.0, 1.0, -1.0, None, _lib.stream())
+    torch.cuda.synchronize()
+    ref = O.upfirdn2d(tt.to(torch.bfloat16).double(), fr, padding=[1, 1, 1, 1], gain=1.0)
+    assert md(y[:, :, :2 * H].permute(0, 3, 1, 2).float(), ref) < 1e-2 * max(float(ref.abs().max()), 1.0)
+
+
+def test_up_layer_equals_reference_formulation():
+    """convT (algorithmic FLOPs) + FIR/epilogue == the reference's up-sampling modulated conv (oracle, fp64)."""
+    g = torch.Generator().manual_seed(99)
+    B, cin, H = 2, 144, 16
+    x = torch.randn(B, cin, H, H, generator=g)
+    w = torch.randn(128, cin, 3, 3, generator=g)
+    s = torch.randn(B, cin, generator=g) * 0.3 + 1
+    noise = torch.randn(B, 1, 2 * H, 2 * H, generator=g)
+    bias = torch.randn(128, generator=g) * 0.1
+    f4 = O.setup_filter([1, 3, 3, 1])
+    ref = O.modulated_conv2d(x.double(), w.double(), s.double(), noise=noise.double() * 0.4, up=2, padding=1, resample_filter=f4, flip_weight=False)
+    ref = O.bias_act(ref, bias.double(), act='lrelu', gain=SQ2, clamp=256)
+    wsq = w.square().sum(dim=[2, 3])
+    d = (s.square() @ wsq.t() + 1e-8).rsqrt()
+    xq = pitched(x * s[:, :, None, None], H + 1, cin)
+    wq = prep_w(w, 0)
+    TP = 2 * H + 2
+    t = torch.zeros((B, TP, TP, 128), dtype=torch.bfloat16, device=DEV)
+    dd = d.to(DEV)
+    _lib.call('nbe_convT3x3s2_flat_bf16', _lib.ptr(xq), _lib.ptr(wq), _lib.ptr(t), B, H, H, cin, cin, H + 1, 128, 128, TP, TP * TP, _lib.ptr(dd), _lib.stream())
+    y = torch.zeros((B, 2 * H, 2 * H, 128), dtype=torch.bfloat16, device=DEV)
+    fd, nd, bd = f4.to(DEV), noise.to(DEV).contiguous(), bias.to(DEV)
+    _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(t), _lib.ptr(fd), _lib.ptr(y), B, 2 * H, 2 * H, 128, 2 * H + 1, 2 * H + 1, 1, 128, TP, TP * TP,
+              128, 2 * H, 4 * H * H, 4.0, None, _lib.ptr(nd), 4 * H * H, 0.4, _lib.ptr(bd), 0.2, SQ2, 256.0, None, _lib.stream())
+    torch.cuda.synchronize()
+    got = y.permute(0, 3, 1, 2).float()
+    assert md(got, ref) < 2e-2 * float(ref.abs().max())
