@@ -192,22 +192,31 @@ class TriadPaintEngine:
 
     # ------------------------------------------------------------------------------------------------
     def _generate(self, geom, opts, **generator_kwargs):
-        if self.G.mode == 'bf16' and self.encoder.mode == 'bf16' and not generator_kwargs.get('force_fp32', False) \
-                and list(self.encoder.res) == list(range(len(self.G.cfg.geom_feature_resolutions))):
-            # fused injection: the encoder writes g0 / g1 straight into the generator's concatenated NHWC inputs
-            geom_feature, dests = self.G.alloc_injection(geom.shape[0])
-            self.encoder.encode_into(geom, dests)
-        else:
-            geom_feature = self.encoder.encode(geom)
         opts.to(self.device)
         B = geom.shape[0]
         opts.prepare_style(B, self.device)
+        G = self.G
+        fused = G.mode == 'bf16' and self.encoder.mode == 'bf16' and G.use_flat \
+            and not generator_kwargs.get('force_fp32', False) and not generator_kwargs.get('return_features') \
+            and not generator_kwargs.get('blended_features') \
+            and list(self.encoder.res) == list(range(len(G.cfg.geom_feature_resolutions)))
+        if fused:
+            # mapping first, then the encoder writes g0 / g1 -- already multiplied by the consuming layers' styles --
+            # straight into the generator's concatenated, zero-gapped NHWC inputs
+            ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
+            ws = ws.to(self.device, torch.float32).contiguous()
+            inj, dests, scales = G.alloc_injection(ws)
+            self.encoder.encode_into(geom, dests, scales)
+            extra = opts.custom_args if opts.style_ws is not None else {}
+            return G.forward_pre_mapped(ws=ws, positions=opts.get_position(self.device), geom_feature=inj,
+                                        return_debug_data=True, noise_mode='const', **extra, **generator_kwargs)
+        geom_feature = self.encoder.encode(geom)
         if opts.style_ws is not None:
-            return self.G.forward_pre_mapped(ws=opts.style_ws, positions=opts.get_position(self.device),
-                                             geom_feature=geom_feature, return_debug_data=True, noise_mode='const',
-                                             **opts.custom_args, **generator_kwargs)
-        return self.G(z=opts.style_z, c=self.style_c, positions=opts.get_position(self.device),
-                      geom_feature=geom_feature, return_debug_data=True, noise_mode='const', **generator_kwargs)
+            return G.forward_pre_mapped(ws=opts.style_ws, positions=opts.get_position(self.device),
+                                        geom_feature=geom_feature, return_debug_data=True, noise_mode='const',
+                                        **opts.custom_args, **generator_kwargs)
+        return G(z=opts.style_z, c=self.style_c, positions=opts.get_position(self.device),
+                 geom_feature=geom_feature, return_debug_data=True, noise_mode='const', **generator_kwargs)
 
     def _composite(self, triad_data, opts, B, want_f32=True, crop_margin=None):
         uvs = triad_data['uvs'].contiguous()

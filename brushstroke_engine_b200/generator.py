@@ -20,6 +20,7 @@ Forward only.  All compute is in libnbe_b200.so; torch provides memory, streams 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -53,17 +54,18 @@ def fully_connected(x, weight, bias, activation=ACT_LINEAR, lr_multiplier=1.0, a
 
 
 class InjectedGeometry:
-    """Geometry features already resident in the generator's concatenated NHWC bf16 inputs: ``buffers[res]`` is the
-    [B, res, res, C_block + C_geo] tensor whose trailing C_geo channels the encoder has written
-    (``GeometryEncoder.encode_into``); the block's conv1 epilogue fills the leading channels.  Replaces the
-    ``torch.cat([x, geom_feature[i]], dim=1)`` of networks_modified.py:219."""
-    def __init__(self, buffers: Dict[int, torch.Tensor]):
-        self.buffers = buffers
+    """Geometry features already resident in the generator's concatenated inputs (flat tensor-core path):
+    ``buffers[res]`` is the zero-gapped NHWC bf16 tensor [B, res, res + 1, C_block + C_geo] that feeds ``b{2 res}.conv0``;
+    its trailing C_geo channels are written by ``GeometryEncoder.encode_into`` *already multiplied by that layer's styles*
+    (``scales``), the block's conv1 epilogue fills the leading channels.  Replaces the ``torch.cat([x, geom_feature[i]])``
+    of networks_modified.py:219 and the ``x * styles`` of networks.py:68.  Tied to the ``ws`` it was prepared for."""
+    def __init__(self, buffers: Dict[int, torch.Tensor], ws, prep):
+        self.buffers, self.ws, self.prep = buffers, ws, prep
 
 
 class _Layer:
     """Device-side constants of one SynthesisLayer."""
-    __slots__ = ('name', 'res', 'up', 'cin', 'cout', 'w32', 'wq', 'wsq', 'bias', 'noise_const', 'noise_strength',
+    __slots__ = ('name', 'res', 'up', 'cin', 'cout', 'w32', 'wq', 'wqT', 'wsq', 'bias', 'noise_const', 'noise_strength',
                  'affine_w', 'affine_b')
 
 
@@ -134,6 +136,8 @@ class Generator:
         self._build(params)
         self.mapping = MappingNetwork(self)
         self.synthesis = SynthesisNetwork(self)
+        self._flat_ws = {}
+        self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
         self.probe = None       # optional {layer_name: [(start_event, end_event), ...]} filled by _conv_tc (bench.py roofline)
 
     # ------------------------------------------------------------------------------------------ plan
@@ -163,6 +167,10 @@ class Generator:
                     # up layers are true convolutions (flip_weight = (up == 1), networks.py:384): pre-flip
                     _lib.call('nbe_prepare_weights_bf16', _lib.ptr(L.w32), _lib.ptr(L.wq), L.cout, L.cin, 3,
                               int(L.up == 2), _lib.stream())
+                    L.wqT = None
+                    if L.up == 2:                                                  # transposed-conv form: taps as stored (no flip)
+                        L.wqT = torch.empty((9, L.cout, cin_pad), dtype=torch.bfloat16, device=dev)
+                        _lib.call('nbe_prepare_weights_bf16', _lib.ptr(L.w32), _lib.ptr(L.wqT), L.cout, L.cin, 3, 0, _lib.stream())
                     L.bias = f32(p[f'{k}.bias'])
                     L.noise_const = f32(p[f'{k}.noise_const'])
                     L.noise_strength = float(p[f'{k}.noise_strength'])
@@ -178,16 +186,42 @@ class Generator:
             self._rgb_affine_b = f32(p[f'{k}.affine.bias'])
         self._layer_by_name = {L.name: L for L in self._layers}
 
-    def alloc_injection(self, B: int):
-        """-> (InjectedGeometry, [(tensor, c_off), ...] in geom_feature order) for ``GeometryEncoder.encode_into``."""
+    def _workspace(self, B: int):
+        """Zero-gapped NHWC bf16 buffers of the flat path, allocated (and zeroed) once per batch size: kernels only ever
+        write the valid columns, so the gap columns stay zero across calls."""
+        ws = self._flat_ws.get(B)
+        if ws is None:
+            cfg, dev, bf = self.cfg, self.device, torch.bfloat16
+            ws = {}
+            for res in cfg.block_resolutions:
+                if res < cfg.img_resolution:
+                    ctot = cfg.block_in_channels(res * 2)
+                    ws[f'out{res}'] = torch.zeros((B, res, res + 1, ctot), dtype=bf, device=dev)       # conv1 output = next conv0 input
+                if res > 4:
+                    ws[f't{res}'] = torch.zeros((B, res + 2, res + 2, cfg.channels(res)), dtype=bf, device=dev)  # transposed-conv output
+                    pitch = res if res == cfg.img_resolution else res + 1
+                    ws[f'x{res}'] = torch.zeros((B, res, pitch, cfg.channels(res)), dtype=bf, device=dev)        # conv0 output = conv1 input
+            ws['in4'] = torch.zeros((B, 4, 5, cfg.channels(4)), dtype=bf, device=dev)
+            self._flat_ws = {B: ws}
+        return ws
+
+    def alloc_injection(self, ws_latents: torch.Tensor):
+        """Prepare the flat path for ``ws_latents`` [B, num_ws, w_dim]: computes all styles, and returns
+        ``(InjectedGeometry, dests, scales)`` where ``dests[i] = (tensor, c_off)`` / ``scales[i]`` ([B, C_geo] float32) are
+        what ``GeometryEncoder.encode_into`` needs to write feature map i, pre-modulated, into its concat buffer."""
         cfg = self.cfg
-        bufs, dests = {}, []
+        B = ws_latents.shape[0]
+        with torch.cuda.device(self.device):
+            prep = self._styles(ws_latents.to(torch.float32))
+        wsb = self._workspace(B)
+        bufs, dests, scales = {}, [], []
         for res, cg in zip(cfg.geom_feature_resolutions, cfg.geom_feature_channels):
             cb = cfg.channels(res)
-            t = torch.empty((B, res, res, cb + cg), dtype=torch.bfloat16, device=self.device)
+            t = wsb[f'out{res}']
             bufs[res] = t
             dests.append((t, cb))
-        return InjectedGeometry(bufs), dests
+            scales.append(prep[0][f'b{res * 2}.conv0'][:, cb:cb + cg].contiguous())
+        return InjectedGeometry(bufs, ws_latents, prep), dests, scales
 
     # ------------------------------------------------------------------------------------------ API
     def __call__(self, *args, **kwargs):
@@ -273,13 +307,22 @@ class Generator:
         cfg = self.cfg
         B = ws.shape[0]
         assert ws.shape[1:] == (self.num_ws, self.w_dim)
+        ws_in = ws
         ws = ws.to(torch.float32)
         mode = 'fp32' if (force_fp32 or self.mode == 'fp32') else 'bf16'
-        if isinstance(geom_feature, InjectedGeometry) and mode != 'bf16':
-            raise RuntimeError('synthesis: InjectedGeometry buffers are NHWC bf16 and need the bf16 mode')
+        injected = isinstance(geom_feature, InjectedGeometry)
+        flat = mode == 'bf16' and not return_features and not blended_features and self.use_flat and \
+            cfg.img_resolution == 128 and all(cfg.channels(r) == 128 for r in cfg.block_resolutions)
+        if injected and not flat:
+            raise RuntimeError('synthesis: InjectedGeometry needs the flat bf16 path (no force_fp32 / return_features / blended_features)')
         with torch.cuda.device(self.device):
-            styles, dcoefs, colors, rgb_styles = self._styles(ws)
-            run = self._run_fp32 if mode == 'fp32' else self._run_bf16
+            if injected and geom_feature.ws is ws_in:
+                styles, dcoefs, colors, rgb_styles = geom_feature.prep
+            else:
+                if injected:
+                    raise RuntimeError('synthesis: InjectedGeometry was prepared for a different ws tensor')
+                styles, dcoefs, colors, rgb_styles = self._styles(ws)
+            run = self._run_fp32 if mode == 'fp32' else (self._run_bf16_flat if flat else self._run_bf16)
             img, uvs, feats = run(B, styles, dcoefs, colors, rgb_styles, geom_feature, positions, norm_noise_positions,
                                   noise_mode, noise_buffers, return_features, blended_features)
         debug = dict(feats)
@@ -386,12 +429,7 @@ class Generator:
             extra = cfg.geom_feature_channels[list(cfg.geom_feature_resolutions).index(res)] \
                 if res in cfg.geom_feature_resolutions else 0
             y_cs = conv1.cout + extra
-            injected = isinstance(geom_feature, InjectedGeometry)
-            if extra and injected:
-                y = geom_feature.buffers[res]
-                assert y.shape == (B, res, res, y_cs) and y.dtype == bf
-            else:
-                y = torch.empty((B, res, res, y_cs), dtype=bf, device=dev)
+            y = torch.empty((B, res, res, y_cs), dtype=bf, device=dev)
             noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp,
                                                 noise_buffers.get(f'{conv1.name}.noise_const'))
             is_last = res == cfg.img_resolution
@@ -425,13 +463,84 @@ class Generator:
                 feats[f'features{res}'] = self._unpack(x, B, conv1.cout, res, x_cs)
             if is_last and not fused_rgb:
                 img, uvs = self._torgb(x, True, x_cs, rgb_styles, colors, B)
-            if extra and not injected:
+            if extra:
                 g = geom_feature[geo_idx].to(dev, torch.float32).contiguous()
                 assert g.shape == (B, extra, res, res), f'geometry feature {tuple(g.shape)} != {(B, extra, res, res)}'
                 _lib.call('nbe_pack_nhwc_bf16', _lib.ptr(g), _lib.ptr(x), B, extra, res, res, x_cs, conv1.cout, None,
                           _lib.stream())
                 geo_idx += 1
         return img, uvs, feats
+
+    # ---- BF16 tensor-core mode, flat kernels ------------------------------------------------------------
+    def _run_bf16_flat(self, B, styles, dcoefs, colors, rgb_styles, geom_feature, positions, nnp, noise_mode, noise_buffers,
+                       return_features, blended_features):
+        """Every 3x3 layer on the flat shifted-window kernels; up-sampling layers as transposed conv (algorithmic FLOPs) +
+        FIR/epilogue; each producer writes its consumer's input already multiplied by the consumer's styles."""
+        cfg, dev = self.cfg, self.device
+        wsb = self._workspace(B)
+        clamp = float(cfg.conv_clamp if cfg.conv_clamp is not None else -1)
+        st = _lib.stream()
+        injected = isinstance(geom_feature, InjectedGeometry)
+        geo_idx = 0
+        img = uvs = None
+        last = cfg.img_resolution
+        # b4 input: const * styles(b4.conv1), zero-gapped [B,4,5,C]
+        c4 = self._layer_by_name['b4.conv1']
+        xin = wsb['in4']
+        xin[:, :, :4, :] = (self._const_nhwc.unsqueeze(0) * styles[c4.name][:, None, None, :]).to(torch.bfloat16)
+        xin_pitch = 5
+        for res in cfg.block_resolutions:
+            conv1 = self._layer_by_name[f'b{res}.conv1']
+            if res > 4:
+                conv0 = self._layer_by_name[f'b{res}.conv0']
+                Rin = res // 2
+                t = wsb[f't{res}']
+                TP = res + 2
+                _lib.call('nbe_convT3x3s2_flat_bf16', _lib.ptr(xin), _lib.ptr(conv0.wqT), _lib.ptr(t), B, Rin, Rin, conv0.cin,
+                          xin.shape[3], xin_pitch, conv0.cout, conv0.cout, TP, TP * TP, _lib.ptr(dcoefs[conv0.name]), st)
+                noise, nsn, ngain = self._noise_for(conv0, B, noise_mode, positions, nnp, noise_buffers.get(f'{conv0.name}.noise_const'))
+                x1 = wsb[f'x{res}']
+                x1_pitch = x1.shape[2]
+                _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(t), _lib.ptr(self._filter), _lib.ptr(x1), B, res, res, conv0.cout,
+                          res + 1, res + 1, 1, conv0.cout, TP, TP * TP, conv0.cout, x1_pitch, res * x1_pitch, 4.0, None,
+                          _lib.ptr(noise), nsn, float(ngain), _lib.ptr(conv0.bias), 0.2, SQRT2, clamp, _lib.ptr(styles[conv1.name]), st)
+            else:
+                x1, x1_pitch = xin, xin_pitch
+            noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp, noise_buffers.get(f'{conv1.name}.noise_const'))
+            if res == last:
+                ev = None
+                if self.probe is not None and conv1.name in self.probe:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
+                img = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
+                uvs = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
+                _lib.call('nbe_conv_tc_bf16_torgb', _lib.ptr(x1), _lib.ptr(conv1.wq), None, B, res, res, conv1.cin, conv1.cin,
+                          conv1.cout, conv1.cout, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
+                          _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(self._rgb_w), _lib.ptr(rgb_styles), _lib.ptr(self._rgb_b),
+                          _lib.ptr(colors.contiguous()), clamp, _lib.ptr(img), _lib.ptr(uvs), 0, st)
+                if ev is not None:
+                    ev[1].record()
+                    self.probe[conv1.name].append(ev)
+                break
+            # conv1 -> next block's (pre-modulated, concatenated, zero-gapped) input
+            nxt = self._layer_by_name[f'b{res * 2}.conv0']
+            out = geom_feature.buffers[res] if (injected and res in cfg.geom_feature_resolutions) else wsb[f'out{res}']
+            ns = styles[nxt.name][:, :conv1.cout].contiguous() if nxt.cin != conv1.cout else styles[nxt.name]
+            _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(out), B, res, res, conv1.cin, x1.shape[3],
+                      x1_pitch, 0, conv1.cout, out.shape[3], res + 1, res * (res + 1), _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn,
+                      float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(ns), st)
+            if res in cfg.geom_feature_resolutions:
+                extra = cfg.geom_feature_channels[list(cfg.geom_feature_resolutions).index(res)]
+                if not injected:
+                    g = geom_feature[geo_idx].to(dev, torch.float32).contiguous()
+                    assert g.shape == (B, extra, res, res), f'geometry feature {tuple(g.shape)} != {(B, extra, res, res)}'
+                    tmp = torch.empty((B, res, res, extra), dtype=torch.bfloat16, device=dev)
+                    gs = styles[nxt.name][:, conv1.cout:conv1.cout + extra].contiguous()
+                    _lib.call('nbe_pack_nhwc_bf16', _lib.ptr(g), _lib.ptr(tmp), B, extra, res, res, extra, 0, _lib.ptr(gs), st)
+                    out[:, :, :res, conv1.cout:conv1.cout + extra] = tmp
+                geo_idx += 1
+            xin, xin_pitch = out, res + 1
+        return img, uvs, {}
 
     def _unpack(self, x, B, C, R, cs):
         out = torch.empty((B, C, R, R), dtype=torch.float32, device=self.device)

@@ -126,10 +126,11 @@ class GeometryEncoder:
             self._ws = {key: ws}                           # keep one batch size resident
         return ws
 
-    def encode_into(self, geom, dests):
+    def encode_into(self, geom, dests, scales=None):
         """Run the bf16 encoder and write feature map ``r`` (index into ``self.res``) into ``dests[r] = (tensor, c_off)``:
-        an NHWC bf16 tensor [B, R, R, cs] whose channels [c_off, c_off + C_r) receive the features (e.g. the generator's
-        concat buffers).  geom: [B,1,H,W] float32, 0 = stroke."""
+        an NHWC bf16 tensor [B, R, pitch >= R, cs] whose channels [c_off, c_off + C_r) of the first R columns receive the
+        features (e.g. the generator's zero-gapped concat buffers), optionally multiplied by ``scales[r]`` ([B, C_r] float32,
+        the consuming layer's styles).  geom: [B,1,H,W] float32, 0 = stroke."""
         assert self.mode == 'bf16'
         _lib.require_cuda(geom, 'GeometryEncoder.encode_into')
         geom = geom.to(torch.float32).contiguous()
@@ -139,6 +140,7 @@ class GeometryEncoder:
         max_res = max(res)
         ws = self._workspace(B, H)
         slope = float(self.cfg.neg_slope)
+        n_layers = self._n_enc + max_res
         with torch.cuda.device(self.device):
             st = _lib.stream()
             wi = 0
@@ -152,39 +154,56 @@ class GeometryEncoder:
                           cur.shape[3], slope, PREPROC_CODE[self.cfg.preproc_type], st)
             _lib.call('nbe_reflect_border_nhwc_bf16', _lib.ptr(cur), B, H + 2, W + 2, w.shape[0], cur.shape[3], st)
             h = H
-            cur_view = None            # (ptr, cs, C) of the latest un-padded feature map when it lives in a destination buffer
-            for i in range(1, self._n_enc + max_res):
+            feat_dense = None          # latest feature map as a dense NHWC tensor [B,h,h,C] (input of the next ScaleUp)
+            for i in range(1, n_layers):
                 w, b, stride, pad, up = self._layers[i]
                 cout = w.shape[0]
                 if up:
-                    src_ptr, src_cs, src_c = cur_view
+                    if feat_dense is None:
+                        raise RuntimeError('GeometryEncoder: ScaleUp needs the previous feature map (encode resolutions must be 0..k)')
                     upbuf = ws[wi]; wi += 1
-                    _lib.call('nbe_bilinear2x_pad_nhwc_bf16', src_ptr, _lib.ptr(upbuf), B, h, h, src_c, src_cs, upbuf.shape[3], st)
+                    _lib.call('nbe_bilinear2x_pad_nhwc_bf16', _lib.ptr(feat_dense), _lib.ptr(upbuf), B, h, h, feat_dense.shape[3],
+                              feat_dense.shape[3], upbuf.shape[3], st)
                     cur = upbuf
                     h *= 2
                 ho = h // stride
                 feat_idx = i - (self._n_enc - 1)            # >= 0: this layer's output is feature map `feat_idx`
                 nxt = ws[wi]; wi += 1
-                if feat_idx >= 0 and feat_idx in res:
+                is_feat = feat_idx >= 0 and feat_idx in res
+                last_layer = i == n_layers - 1
+                next_scale = None
+                direct = is_feat and last_layer             # nothing else consumes it: write (pre-scaled) straight into the destination
+                if direct:
                     dst, c_off = dests[res.index(feat_idx)]
-                    assert dst.dtype == torch.bfloat16 and dst.shape[:3] == (B, ho, ho) and dst.shape[3] >= c_off + cout
-                    y_ptr, y_cs, rp, ip = dst.data_ptr() + 2 * c_off, dst.shape[3], ho, ho * ho
-                    cur_view = (y_ptr, y_cs, cout)
+                    assert dst.dtype == torch.bfloat16 and dst.shape[0] == B and dst.shape[1] == ho and dst.shape[2] >= ho \
+                        and dst.shape[3] >= c_off + cout
+                    y_ptr, y_cs, rp, ip = dst.data_ptr() + 2 * c_off, dst.shape[3], dst.shape[2], ho * dst.shape[2]
+                    if scales is not None and scales[res.index(feat_idx)] is not None:
+                        next_scale = scales[res.index(feat_idx)].to(self.device, torch.float32).contiguous()
+                        assert next_scale.shape == (B, cout)
+                    padded_out = None
+                elif feat_idx >= 0 and (i + 1 < n_layers and self._layers[i + 1][4]):
+                    feat_dense = torch.empty((B, ho, ho, cout), dtype=torch.bfloat16, device=self.device)
+                    y_ptr, y_cs, rp, ip = feat_dense.data_ptr(), cout, ho, ho * ho
                     padded_out = None
                 else:
                     y_cs, rp, ip = nxt.shape[3], ho + 2, (ho + 2) * (ho + 2)
                     y_ptr = nxt.data_ptr() + 2 * ((ho + 2) + 1) * y_cs
                     padded_out = nxt
-                    cur_view = None
                 _lib.call('nbe_conv_tc_bf16_ex', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cur.shape[3], cur.shape[3],
                           cout, y_cs, 3, 1, stride, cur.shape[1], cur.shape[2], rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0,
-                          -1.0, None, st)
+                          -1.0, _lib.ptr(next_scale), st)
                 h = ho
                 if padded_out is not None:
                     _lib.call('nbe_reflect_border_nhwc_bf16', _lib.ptr(padded_out), B, h + 2, h + 2, cout, padded_out.shape[3], st)
                     cur = padded_out
-                elif i + 1 < self._n_enc + max_res and not self._layers[i + 1][4]:
-                    raise RuntimeError('GeometryEncoder: a feature map that feeds a non-upsampling layer must stay padded')
+                elif is_feat and not direct:
+                    # a feature that also feeds the decoder: keep the un-scaled dense copy, hand a (scaled) copy to the destination
+                    dst, c_off = dests[res.index(feat_idx)]
+                    assert dst.shape[0] == B and dst.shape[1] == ho and dst.shape[2] >= ho and dst.shape[3] >= c_off + cout
+                    sc = scales[res.index(feat_idx)] if scales is not None else None
+                    src = feat_dense if sc is None else (feat_dense.float() * sc.to(self.device)[:, None, None, :]).to(torch.bfloat16)
+                    dst[:, :, :ho, c_off:c_off + cout] = src
         return dests
 
     def _encode_bf16(self, geom, res) -> List[torch.Tensor]:

@@ -31,12 +31,15 @@ def run(timed):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True); t2 = torch.cuda.Event(enable_timing=True)
     t0.record()
     if mode == 'bf16':
-        gf, dests = G.alloc_injection(B)
-        enc.encode_into(geom, dests)
+        ws = G.mapping(z, None).contiguous()
+        gf, dests, scales = G.alloc_injection(ws)
+        enc.encode_into(geom, dests, scales)
+        t1.record()
+        img, dbg = G.forward_pre_mapped(ws, gf, positions=pos, return_debug_data=True, noise_mode='const')
     else:
         gf = enc.encode(geom)
-    t1.record()
-    img, dbg = G(z, None, gf, positions=pos, return_debug_data=True, noise_mode='const')
+        t1.record()
+        img, dbg = G(z, None, gf, positions=pos, return_debug_data=True, noise_mode='const')
     t2.record(); torch.cuda.synchronize()
     return t0.elapsed_time(t1), t1.elapsed_time(t2)
 
@@ -50,6 +53,9 @@ for name, args, s, e in records:
     shape = ''
     if name == 'nbe_conv_tc_bf16_ex': shape = f'N={args[3]} R={args[4]} Cin={args[6]} Cout={args[8]} stride={args[12]}'
     elif name == 'nbe_conv_tc_bf16': shape = f'N={args[3]} R={args[4]} Cin={args[6]} valid={args[11]}'
+    elif name in ('nbe_conv3x3_flat_bf16',): shape = f'N={args[3]} R={args[4]} Cin={args[6]}'
+    elif name == 'nbe_convT3x3s2_flat_bf16': shape = f'N={args[3]} H={args[4]} Cin={args[6]}'
+    elif name == 'nbe_fir_act_nhwc_bf16': shape = f'N={args[3]} OH={args[4]} C={args[6]}'
     elif name == 'nbe_conv2d_f32': shape = f'N={args[3]} Cin={args[4]} H={args[5]} Cout={args[7]} K={args[8]} s={args[10]}'
     elif name == 'nbe_upsample2x_nhwc_bf16': shape = f'N={args[4]} H={args[5]} C={args[7]}'
     if ms > 0.02: print(f'  {name:28s} {ms:8.3f} ms  {shape}')
