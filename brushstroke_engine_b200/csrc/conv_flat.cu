@@ -42,6 +42,7 @@ struct FlatParams {
     uint32_t idesc;
 };
 
+template <int EPI>   // 0: accumulators are stored as they are (bf16); 1: full SynthesisLayer epilogue
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const FlatParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -154,7 +155,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int ab = (p.nbuf == 2) ? (it & 1) : 0;
             const int n = item / p.items_per_img;
             const int q0 = (item - n * p.items_per_img) * p.T * 128;
-            if (n != cur_n) {
+            if (EPI == 1 && n != cur_n) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 s_vec[et] = p.dcoef ? p.dcoef[(long long)n * 128 + et] : 1.f;
                 s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
@@ -187,18 +188,22 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                float rr[2];
+                                if (EPI == 0) {
+                                    o2[e] = __floats2bfloat162_rn(__uint_as_float(v[gg * 8 + e * 2]), __uint_as_float(v[gg * 8 + e * 2 + 1]));
+                                } else {
+                                    float rr[2];
 #pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    const int o = c0 + gg * 8 + e * 2 + h;
-                                    float a = __uint_as_float(v[gg * 8 + e * 2 + h]) * s_vec[o] + nz + s_vec[128 + o];
-                                    if (p.act) {
-                                        a *= (a > 0.f) ? pos_gain : neg_gain;
-                                        if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
+                                    for (int h = 0; h < 2; ++h) {
+                                        const int o = c0 + gg * 8 + e * 2 + h;
+                                        float a = __uint_as_float(v[gg * 8 + e * 2 + h]) * s_vec[o] + nz + s_vec[128 + o];
+                                        if (p.act) {
+                                            a *= (a > 0.f) ? pos_gain : neg_gain;
+                                            if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
+                                        }
+                                        rr[h] = a * s_vec[256 + o];
                                     }
-                                    rr[h] = a * s_vec[256 + o];
+                                    o2[e] = __floats2bfloat162_rn(rr[0], rr[1]);
                                 }
-                                o2[e] = __floats2bfloat162_rn(rr[0], rr[1]);
                             }
                             *reinterpret_cast<int4*>(yrow + c0 + gg * 8) = out;
                         }
@@ -253,10 +258,15 @@ static int launch_flat(const void* x, const void* wq, FlatParams& p, int N, int 
     }
     static std::once_flag once;
     static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] { err = cudaFuncSetAttribute(conv_tc_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    std::call_once(once, [] {
+        err = cudaFuncSetAttribute(conv_tc_flat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "conv_flat: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     const int grid = total < kNumSMs ? (int)total : kNumSMs;
-    conv_tc_flat_kernel<<<grid, F_THREADS, smem, stream>>>(ta, tb, p);
+    const bool raw = !p.dcoef && !p.noise && !p.bias && !p.act && !p.next_scale;
+    if (raw) conv_tc_flat_kernel<0><<<grid, F_THREADS, smem, stream>>>(ta, tb, p);
+    else     conv_tc_flat_kernel<1><<<grid, F_THREADS, smem, stream>>>(ta, tb, p);
     return launched("conv_tc_flat_kernel");
 }
 

@@ -4,7 +4,8 @@
 //   SG2/torch_utils/ops/conv2d_resample.py:139 ; T is zero outside [0,TH) x [0,TW))
 //   post(v) = clamp(lrelu(v * scale[n,c] + noise[n,oy,ox] * noise_gain + bias[c]) * gain) * next_scale[n,c]
 //   (SG2/training/networks.py:71-75,386-390).
-// One thread = one output column x 8 channels (16 bytes), walking 8 output rows with a sliding window of horizontally
+// One thread = one output column x 4 channels (8 bytes; keeps the register footprint small enough for 4 CTAs/SM, which is
+// what hides the load latency), walking 8 output rows with a sliding window of horizontally
 // filtered rows (rank-1 filters: 4 + 4 FMAs per output; general filters: 16).  Consecutive threads walk the channel
 // vectors of a pixel, then the pixels of a row, so every global access is a whole 32-byte sector and the 4x overlap
 // between neighbouring windows is served by L1.  HBM-bound: (TH*TW + OH*OW) * C * 2 bytes per image.
@@ -25,18 +26,29 @@ struct FirParams {
     int row_groups;
 };
 
-__device__ __forceinline__ void unpack8(const int4& raw, float (&v)[8]) {
+constexpr int FIR_CPT = 4;                                          // channels per thread
+
+__device__ __forceinline__ void unpack4(const uint2& raw, float (&v)[FIR_CPT]) {
     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { const float2 f2 = __bfloat1622float2(h2[k]); v[2 * k] = f2.x; v[2 * k + 1] = f2.y; }
+    for (int k = 0; k < 2; ++k) { const float2 f2 = __bfloat1622float2(h2[k]); v[2 * k] = f2.x; v[2 * k + 1] = f2.y; }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 fir_act_nhwc_kernel(const FirParams p) {
     __shared__ float s_f[16];
+    extern __shared__ float s_epi[];                               // [3][C]: scale, bias, next_scale of this CTA's image
     if (threadIdx.x < 16) {
         const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
         s_f[threadIdx.x] = p.f[(3 - a) * 4 + (3 - b)] * p.fgain;      // flip_filter = False
+    }
+    {
+        const int n_ = blockIdx.x / p.row_groups;
+        for (int c = threadIdx.x; c < p.C; c += 256) {
+            s_epi[c] = p.scale ? p.scale[(long long)n_ * p.C + c] : 1.f;
+            s_epi[p.C + c] = p.bias ? p.bias[c] : 0.f;
+            s_epi[2 * p.C + c] = p.next_scale ? p.next_scale[(long long)n_ * p.C + c] : 1.f;
+        }
     }
     __syncthreads();
     float f[16];
@@ -51,61 +63,55 @@ fir_act_nhwc_kernel(const FirParams p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { fx[i] = f[i]; fy[i] = sep ? f[i * 4] / f[0] : 0.f; }
 
-    const int CV = p.C >> 3;
+    const int CV = p.C / FIR_CPT;
     const int n = blockIdx.x / p.row_groups;
     const int oy0 = (blockIdx.x - n * p.row_groups) * FIR_RPT;
     const int idx = blockIdx.y * blockDim.x + threadIdx.x;
     if (idx >= p.OW * CV) return;
     const int cv = idx % CV, ox = idx / CV;
-    const __nv_bfloat16* tp = p.t + (long long)n * p.t_img_pitch * p.t_cs + cv * 8;
+    const __nv_bfloat16* tp = p.t + (long long)n * p.t_img_pitch * p.t_cs + cv * FIR_CPT;
     const int ix0 = ox - p.pad;
 
-    // per-channel epilogue vectors
-    float sc[8], bs[8], ns[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = cv * 8 + k;
-        sc[k] = p.scale ? p.scale[(long long)n * p.C + c] : 1.f;
-        bs[k] = p.bias ? p.bias[c] : 0.f;
-        ns[k] = p.next_scale ? p.next_scale[(long long)n * p.C + c] : 1.f;
-    }
+    const float* sc = s_epi + cv * FIR_CPT;                        // per-channel epilogue vectors (shared memory)
+    const float* bs = s_epi + p.C + cv * FIR_CPT;
+    const float* ns = s_epi + 2 * p.C + cv * FIR_CPT;
     const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
 
-    auto load_px = [&](int iy, int ix, float (&v)[8]) {
+    auto load_px = [&](int iy, int ix, float (&v)[FIR_CPT]) {
         if (iy >= 0 && iy < p.TH && ix >= 0 && ix < p.TW) {
-            const int4 raw = *reinterpret_cast<const int4*>(tp + ((long long)iy * p.t_row_pitch + ix) * p.t_cs);
-            unpack8(raw, v);
+            const uint2 raw = *reinterpret_cast<const uint2*>(tp + ((long long)iy * p.t_row_pitch + ix) * p.t_cs);
+            unpack4(raw, v);
         } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            for (int k = 0; k < FIR_CPT; ++k) v[k] = 0.f;
         }
     };
-    auto finish = [&](int oy, float (&acc)[8]) {
+    auto finish = [&](int oy, float (&acc)[FIR_CPT]) {
         float nz = 0.f;
         if (p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
-        int4 outv;
+        uint2 outv;
         __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
-        float r[8];
+        float r[FIR_CPT];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < FIR_CPT; ++k) {
             float a = acc[k] * sc[k] + nz + bs[k];
             a *= (a > 0.f) ? pos_gain : neg_gain;
             if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
             r[k] = a * ns[k];
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o2[k] = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
-        st_stream16(p.y + (((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs + cv * 8), outv);
+        for (int k = 0; k < FIR_CPT / 2; ++k) o2[k] = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
+        *reinterpret_cast<uint2*>(p.y + (((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs + cv * FIR_CPT)) = outv;
     };
 
     const int iy0 = oy0 - p.pad;
     if (sep) {
-        float h[4][8];
-        auto hrow = [&](float (&dst)[8], int iy) {
-            float v0[8], v1[8], v2[8], v3[8];
+        float h[4][FIR_CPT];
+        auto hrow = [&](float (&dst)[FIR_CPT], int iy) {
+            float v0[FIR_CPT], v1[FIR_CPT], v2[FIR_CPT], v3[FIR_CPT];
             load_px(iy, ix0, v0); load_px(iy, ix0 + 1, v1); load_px(iy, ix0 + 2, v2); load_px(iy, ix0 + 3, v3);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) dst[k] = fx[0] * v0[k] + fx[1] * v1[k] + fx[2] * v2[k] + fx[3] * v3[k];
+            for (int k = 0; k < FIR_CPT; ++k) dst[k] = fx[0] * v0[k] + fx[1] * v1[k] + fx[2] * v2[k] + fx[3] * v3[k];
         };
         hrow(h[0], iy0); hrow(h[1], iy0 + 1); hrow(h[2], iy0 + 2);
 #pragma unroll
@@ -113,9 +119,9 @@ fir_act_nhwc_kernel(const FirParams p) {
             const int oy = oy0 + r;
             if (oy >= p.OH) break;
             hrow(h[(r + 3) & 3], iy0 + r + 3);
-            float acc[8];
+            float acc[FIR_CPT];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < FIR_CPT; ++k)
                 acc[k] = fy[0] * h[r & 3][k] + fy[1] * h[(r + 1) & 3][k] + fy[2] * h[(r + 2) & 3][k] + fy[3] * h[(r + 3) & 3][k];
             finish(oy, acc);
         }
@@ -124,17 +130,17 @@ fir_act_nhwc_kernel(const FirParams p) {
         for (int r = 0; r < FIR_RPT; ++r) {
             const int oy = oy0 + r;
             if (oy >= p.OH) break;
-            float acc[8];
+            float acc[FIR_CPT];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+            for (int k = 0; k < FIR_CPT; ++k) acc[k] = 0.f;
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    float v[8];
+                    float v[FIR_CPT];
                     load_px(oy - p.pad + a, ix0 + b, v);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[a * 4 + b], v[k], acc[k]);
+                    for (int k = 0; k < FIR_CPT; ++k) acc[k] = fmaf(f[a * 4 + b], v[k], acc[k]);
                 }
             finish(oy, acc);
         }
@@ -165,9 +171,9 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
     p.row_groups = (OH + FIR_RPT - 1) / FIR_RPT;
     const int64_t gx = (int64_t)N * p.row_groups;
     NBE_REQUIRE(gx <= INT32_MAX, "fir_act_nhwc: too many row groups");
-    const int per_row = OW * (C / 8);
+    const int per_row = OW * (C / FIR_CPT);
     dim3 grid((unsigned)gx, (per_row + 255) / 256);
     NBE_REQUIRE(grid.y <= 65535u, "fir_act_nhwc: rows too wide");
-    fir_act_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    fir_act_nhwc_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>(p);
     return launched("fir_act_nhwc_kernel");
 }

@@ -497,12 +497,12 @@ class Generator:
                 t = wsb[f't{res}']
                 TP = res + 2
                 _lib.call('nbe_convT3x3s2_flat_bf16', _lib.ptr(xin), _lib.ptr(conv0.wqT), _lib.ptr(t), B, Rin, Rin, conv0.cin,
-                          xin.shape[3], xin_pitch, conv0.cout, conv0.cout, TP, TP * TP, _lib.ptr(dcoefs[conv0.name]), st)
+                          xin.shape[3], xin_pitch, conv0.cout, conv0.cout, TP, TP * TP, None, st)
                 noise, nsn, ngain = self._noise_for(conv0, B, noise_mode, positions, nnp, noise_buffers.get(f'{conv0.name}.noise_const'))
                 x1 = wsb[f'x{res}']
                 x1_pitch = x1.shape[2]
                 _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(t), _lib.ptr(self._filter), _lib.ptr(x1), B, res, res, conv0.cout,
-                          res + 1, res + 1, 1, conv0.cout, TP, TP * TP, conv0.cout, x1_pitch, res * x1_pitch, 4.0, None,
+                          res + 1, res + 1, 1, conv0.cout, TP, TP * TP, conv0.cout, x1_pitch, res * x1_pitch, 4.0, _lib.ptr(dcoefs[conv0.name]),
                           _lib.ptr(noise), nsn, float(ngain), _lib.ptr(conv0.bias), 0.2, SQRT2, clamp, _lib.ptr(styles[conv1.name]), st)
             else:
                 x1, x1_pitch = xin, xin_pitch
