@@ -9,7 +9,9 @@
 // filtered rows (rank-1 filters: 4 + 4 FMAs per output; general filters: 16).  Consecutive threads walk the channel
 // vectors of a pixel, then the pixels of a row, so every global access is a whole 32-byte sector and the 4x overlap
 // between neighbouring windows is served by L1.  HBM-bound: (TH*TW + OH*OW) * C * 2 bytes per image.
-#include "common.cuh"
+#include "tc_common.cuh"
+#include <mutex>
+#include <cstdlib>
 
 namespace nbe {
 
@@ -147,6 +149,146 @@ fir_act_nhwc_kernel(const FirParams p) {
     }
 }
 
+// ---- TMA-tiled variant for C == 128 ------------------------------------------------------------------
+// The register-window kernel above is latency-bound (every thread waits on its own global loads).  Here a persistent CTA
+// streams (8+3) x (16+3) pixel x 128-channel tiles of T through a double-buffered shared-memory ring with 4-D TMA boxes
+// (out-of-range rows / columns are zero-filled by TMA = the FIR's padding), the next tile is in flight while the
+// current one is filtered, and every shared-memory read is a conflict-free 16-byte vector.
+constexpr int FT_OW = 16, FT_OH = 8;
+constexpr int FT_IW = FT_OW + 3, FT_IH = FT_OH + 3;
+constexpr int FT_TILE_BYTES = FT_IH * FT_IW * 256;                  // 128 bf16 channels per pixel
+
+__global__ void __launch_bounds__(256, 2)
+fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams p, int tiles_x, int tiles_y, int total_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    uint8_t* bufs = smem;                                           // [2][FT_TILE_BYTES]
+    float* s_epi = reinterpret_cast<float*>(bufs + 2 * ((FT_TILE_BYTES + 127) & ~127));   // [3][128]
+    float* s_f = s_epi + 3 * 128;                                   // [16]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_f + 16);         // [2]
+    constexpr int BUF_STRIDE = (FT_TILE_BYTES + 127) & ~127;
+
+    if (threadIdx.x < 16) {
+        const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
+        s_f[threadIdx.x] = p.f[(3 - a) * 4 + (3 - b)] * p.fgain;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&full[0]), 1); mbar_init(smem_u32(&full[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_t) : "memory");
+    }
+    __syncthreads();
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = s_f[i];
+    bool sep = f[0] != 0.f;
+#pragma unroll
+    for (int a = 1; a < 4; ++a)
+#pragma unroll
+        for (int b = 1; b < 4; ++b) sep = sep && fabsf(f[a * 4 + b] * f[0] - f[a * 4] * f[b]) <= 1e-6f * fabsf(f[a * 4 + b] * f[0]) + 1e-30f;
+    float fx[4], fy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { fx[i] = f[i]; fy[i] = sep ? f[i * 4] / f[0] : 0.f; }
+
+    const int cv = threadIdx.x & 15, px = threadIdx.x >> 4;       // 16 channel vectors x 16 pixels
+    const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
+    auto issue = [&](int tile, int b) {
+        int t = tile;
+        const int tx = t % tiles_x; t /= tiles_x;
+        const int ty = t % tiles_y; t /= tiles_y;
+        const uint32_t bar = smem_u32(&full[b]);
+        mbar_expect_tx(bar, FT_TILE_BYTES);
+        tma_load_4d(smem_u32(bufs + b * BUF_STRIDE), &tmap_t, bar, 0, tx * FT_OW - p.pad, ty * FT_OH - p.pad, t);
+    };
+    if (threadIdx.x == 0 && (int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+    int it = 0, cur_n = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < total_tiles) issue(next, b ^ 1);     // buffer b^1 was released by the __syncthreads of the previous iteration
+        int t = tile;
+        const int tx = t % tiles_x; t /= tiles_x;
+        const int ty = t % tiles_y; t /= tiles_y;
+        const int n = t;
+        if (n != cur_n) {
+            for (int c = threadIdx.x; c < 128; c += 256) {
+                s_epi[c] = p.scale ? p.scale[(long long)n * 128 + c] : 1.f;
+                s_epi[128 + c] = p.bias ? p.bias[c] : 0.f;
+                s_epi[256 + c] = p.next_scale ? p.next_scale[(long long)n * 128 + c] : 1.f;
+            }
+            cur_n = n;
+            __syncthreads();
+        }
+        mbar_wait(smem_u32(&full[b]), (uint32_t)((it >> 1) & 1));
+        const uint8_t* tb = bufs + b * BUF_STRIDE + cv * 16;
+        const int ox = tx * FT_OW + px, oy0 = ty * FT_OH;
+        float sc[8], bs[8], ns[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = s_epi[cv * 8 + k]; bs[k] = s_epi[128 + cv * 8 + k]; ns[k] = s_epi[256 + cv * 8 + k]; }
+        auto ld = [&](int r, int c, float (&v)[8]) {
+            const int4 raw = *reinterpret_cast<const int4*>(tb + (r * FT_IW + c) * 256);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 f2 = __bfloat1622float2(h2[k]); v[2 * k] = f2.x; v[2 * k + 1] = f2.y; }
+        };
+        auto finish = [&](int oy, float (&acc)[8]) {
+            if (oy >= p.OH || ox >= p.OW) return;
+            float nz = 0.f;
+            if (p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
+            int4 outv;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
+            float r[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float a = acc[k] * sc[k] + nz + bs[k];
+                a *= (a > 0.f) ? pos_gain : neg_gain;
+                if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
+                r[k] = a * ns[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o2[k] = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
+            st_stream16(p.y + (((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs + cv * 8), outv);
+        };
+        if (sep) {
+            float h[4][8];
+            auto hrow = [&](float (&dst)[8], int r) {
+                float v0[8], v1[8], v2[8], v3[8];
+                ld(r, px, v0); ld(r, px + 1, v1); ld(r, px + 2, v2); ld(r, px + 3, v3);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dst[k] = fx[0] * v0[k] + fx[1] * v1[k] + fx[2] * v2[k] + fx[3] * v3[k];
+            };
+            hrow(h[0], 0); hrow(h[1], 1); hrow(h[2], 2);
+#pragma unroll
+            for (int r = 0; r < FT_OH; ++r) {
+                hrow(h[(r + 3) & 3], r + 3);
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    acc[k] = fy[0] * h[r & 3][k] + fy[1] * h[(r + 1) & 3][k] + fy[2] * h[(r + 2) & 3][k] + fy[3] * h[(r + 3) & 3][k];
+                finish(oy0 + r, acc);
+            }
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < FT_OH; ++r) {
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) {
+                        float v[8];
+                        ld(r + a, px + bb, v);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[a * 4 + bb], v[k], acc[k]);
+                    }
+                finish(oy0 + r, acc);
+            }
+        }
+        __syncthreads();                                            // everyone is done with buffer b (and s_epi) before it is refilled
+    }
+}
+
 }  // namespace nbe
 
 using namespace nbe;
@@ -168,6 +310,28 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
     p.t_cs = t_cs; p.t_row_pitch = t_row_pitch; p.t_img_pitch = t_img_pitch; p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch;
     p.fgain = fgain; p.scale = scale; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain; p.bias = bias;
     p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.next_scale = next_scale;
+    static const bool force_simple = getenv("NBE_FIR_SIMPLE") != nullptr;
+    if (C == 128 && t_cs == 128 && !force_simple) {
+        // T is described to TMA with its VALID extent, so halo reads outside [0,TH) x [0,TW) come back as zeros
+        CUtensorMap tm;
+        cuuint64_t dims[4] = {128, (cuuint64_t)TW, (cuuint64_t)TH, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)t_cs * 2, (cuuint64_t)t_row_pitch * t_cs * 2, (cuuint64_t)t_img_pitch * t_cs * 2};
+        cuuint32_t box[4] = {128, FT_IW, FT_IH, 1};
+        int st = make_tmap(&tm, t, 4, dims, strides, box, "FIR input", 1, /*swizzle=*/0);
+        if (st) return st;
+        const int tiles_x = (OW + FT_OW - 1) / FT_OW, tiles_y = (OH + FT_OH - 1) / FT_OH;
+        const int64_t total = (int64_t)tiles_x * tiles_y * N;
+        NBE_REQUIRE(total <= INT32_MAX, "fir_act_nhwc: too many tiles");
+        const size_t smem = 128 + 2 * ((FT_TILE_BYTES + 127) & ~127) + (3 * 128 + 16) * sizeof(float) + 64;
+        static std::once_flag once;
+        static cudaError_t err = cudaSuccess;
+        std::call_once(once, [] { err = cudaFuncSetAttribute(fir_act_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); });
+        if (err != cudaSuccess) return fail(NBE_ECUDA, "fir_act_nhwc: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+        int grid = kNumSMs * 2;
+        if (total < grid) grid = (int)total;
+        fir_act_tiled_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(tm, p, tiles_x, tiles_y, (int)total);
+        return launched("fir_act_tiled_kernel");
+    }
     p.row_groups = (OH + FIR_RPT - 1) / FIR_RPT;
     const int64_t gx = (int64_t)N * p.row_groups;
     NBE_REQUIRE(gx <= INT32_MAX, "fir_act_nhwc: too many row groups");
