@@ -32,6 +32,7 @@ _SIGNATURES = {
     'nbe_pack_nhwc_bf16': [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     'nbe_unpack_nchw_f32': [_P, _P, _I, _I, _I, _I, _I, _P],
     'nbe_upsample2x_nhwc_bf16': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'nbe_upsample2x_nhwc_bf16_ex': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'nbe_prepare_weights_bf16': [_P, _P, _I, _I, _I, _I, _P],
     'nbe_conv_tc_bf16': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _F, _P, _F, _F, _F, _P, _P],
     'nbe_conv_tc_bf16_ex': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P, _P, _L, _F, _P, _F, _F, _F, _P, _P],

@@ -116,7 +116,7 @@ unpack_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ ds
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 upsample2x_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ f, const float* __restrict__ scale,
-                       __nv_bfloat16* __restrict__ u, int N, int H, int W, int C, int xs_c) {
+                       __nv_bfloat16* __restrict__ u, int N, int H, int W, int C, int xs_c, int x_pitch) {
     __shared__ float s_g[16];
     if (threadIdx.x < 16) {
         int a = threadIdx.x >> 2, b = threadIdx.x & 3;
@@ -139,7 +139,7 @@ upsample2x_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
         for (int dx = 0; dx < 2; ++dx) {
             const int iy = q - 1 + dy, ix = pq - 1 + dx;
             if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-                const int4 raw = ld_stream16(x + (((long long)n * H + iy) * W + ix) * xs_c + cv * 8);
+                const int4 raw = ld_stream16(x + (((long long)n * H + iy) * x_pitch + ix) * xs_c + cv * 8);
                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -347,6 +347,12 @@ extern "C" int nbe_unpack_nchw_f32(const void* src, float* dst, int N, int C, in
 
 extern "C" int nbe_upsample2x_nhwc_bf16(const void* x, const float* f, const float* scale, void* u,
                                         int N, int H, int W, int C, int xs_c, nbe_stream_t stream) {
+    return nbe_upsample2x_nhwc_bf16_ex(x, f, scale, u, N, H, W, C, xs_c, W, stream);
+}
+
+extern "C" int nbe_upsample2x_nhwc_bf16_ex(const void* x, const float* f, const float* scale, void* u,
+                                           int N, int H, int W, int C, int xs_c, int x_pitch, nbe_stream_t stream) {
+    NBE_REQUIRE(x_pitch >= W, "upsample2x: input row pitch smaller than the width");
     NBE_REQUIRE(x && f && u && N >= 0 && H >= 1 && W >= 1 && C >= 8, "upsample2x: bad arguments");
     NBE_REQUIRE(C % 8 == 0 && xs_c % 8 == 0 && xs_c >= C, "upsample2x: channels must be a multiple of 8");
     NBE_REQUIRE((((uintptr_t)x | (uintptr_t)u) & 15) == 0, "upsample2x: tensors must be 16-byte aligned");
@@ -356,7 +362,7 @@ extern "C" int nbe_upsample2x_nhwc_bf16(const void* x, const float* f, const flo
     dim3 grid(N * (H + 1), (per_row + 255) / 256);
     NBE_REQUIRE(grid.y <= 65535u, "upsample2x: rows too wide");
     upsample2x_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, f, scale, (__nv_bfloat16*)u, N, H, W, C, xs_c);
+        (const __nv_bfloat16*)x, f, scale, (__nv_bfloat16*)u, N, H, W, C, xs_c, x_pitch);
     return launched("upsample2x_nhwc_kernel");
 }
 

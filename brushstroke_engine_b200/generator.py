@@ -137,6 +137,7 @@ class Generator:
         self.mapping = MappingNetwork(self)
         self.synthesis = SynthesisNetwork(self)
         self._flat_ws = {}
+        self.last_up_fir_first = os.environ.get('NBE_LAST_UP_CONVT') is None
         self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
         self.probe = None       # optional {layer_name: [(start_event, end_event), ...]} filled by _conv_tc (bench.py roofline)
 
@@ -494,16 +495,30 @@ class Generator:
             if res > 4:
                 conv0 = self._layer_by_name[f'b{res}.conv0']
                 Rin = res // 2
-                t = wsb[f't{res}']
-                TP = res + 2
-                _lib.call('nbe_convT3x3s2_flat_bf16', _lib.ptr(xin), _lib.ptr(conv0.wqT), _lib.ptr(t), B, Rin, Rin, conv0.cin,
-                          xin.shape[3], xin_pitch, conv0.cout, conv0.cout, TP, TP * TP, None, st)
                 noise, nsn, ngain = self._noise_for(conv0, B, noise_mode, positions, nnp, noise_buffers.get(f'{conv0.name}.noise_const'))
                 x1 = wsb[f'x{res}']
                 x1_pitch = x1.shape[2]
-                _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(t), _lib.ptr(self._filter), _lib.ptr(x1), B, res, res, conv0.cout,
-                          res + 1, res + 1, 1, conv0.cout, TP, TP * TP, conv0.cout, x1_pitch, res * x1_pitch, 4.0, _lib.ptr(dcoefs[conv0.name]),
-                          _lib.ptr(noise), nsn, float(ngain), _lib.ptr(conv0.bias), 0.2, SQRT2, clamp, _lib.ptr(styles[conv1.name]), st)
+                if res == last and self.last_up_fir_first:
+                    # 128^2: the CUDA-core FIR pass over the 129^2 x 128-channel map costs more than running the 3x3 conv on
+                    # the FIR-upsampled input at tensor-core speed -> FIR first (xin is already modulated), then the
+                    # row-resident kernel in 'valid' mode
+                    U = wsb.get('u128')
+                    if U is None:
+                        U = wsb['u128'] = torch.empty((B, res + 2, res + 2, conv0.cin), dtype=torch.bfloat16, device=dev)
+                    _lib.call('nbe_upsample2x_nhwc_bf16_ex', _lib.ptr(xin), _lib.ptr(self._filter), None, _lib.ptr(U), B, Rin, Rin,
+                              conv0.cin, xin.shape[3], xin_pitch, st)
+                    _lib.call('nbe_conv_tc_bf16', _lib.ptr(U), _lib.ptr(conv0.wq), _lib.ptr(x1), B, res, res, conv0.cin, conv0.cin,
+                              conv0.cout, conv0.cout, 3, 1, _lib.ptr(dcoefs[conv0.name]), _lib.ptr(noise), nsn, float(ngain),
+                              _lib.ptr(conv0.bias), 0.2, SQRT2, clamp, _lib.ptr(styles[conv1.name]), st)
+                else:
+                    t = wsb[f't{res}']
+                    TP = res + 2
+                    _lib.call('nbe_convT3x3s2_flat_bf16', _lib.ptr(xin), _lib.ptr(conv0.wqT), _lib.ptr(t), B, Rin, Rin, conv0.cin,
+                              xin.shape[3], xin_pitch, conv0.cout, conv0.cout, TP, TP * TP, None, st)
+                    _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(t), _lib.ptr(self._filter), _lib.ptr(x1), B, res, res, conv0.cout,
+                              res + 1, res + 1, 1, conv0.cout, TP, TP * TP, conv0.cout, x1_pitch, res * x1_pitch, 4.0,
+                              _lib.ptr(dcoefs[conv0.name]), _lib.ptr(noise), nsn, float(ngain), _lib.ptr(conv0.bias), 0.2, SQRT2, clamp,
+                              _lib.ptr(styles[conv1.name]), st)
             else:
                 x1, x1_pitch = xin, xin_pitch
             noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp, noise_buffers.get(f'{conv1.name}.noise_const'))

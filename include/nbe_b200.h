@@ -121,6 +121,10 @@ int nbe_upsample2x_nhwc_bf16(const void* x, const float* f, const float* scale, 
                              int N, int H, int W, int C, int xs_c, nbe_stream_t stream);
 
 
+/* Same with an input row pitch in pixels (x is [N, H, x_pitch >= W, xs_c]; e.g. the zero-gapped buffers of the flat path). */
+int nbe_upsample2x_nhwc_bf16_ex(const void* x, const float* f, const float* scale, void* u,
+                                int N, int H, int W, int C, int xs_c, int x_pitch, nbe_stream_t stream);
+
 /* wq: bf16 weights re-laid out as [K*K][Cout][Cin_pad] (tap-major, Cin_pad = Cin rounded up to 64, zero padded,
  * already flipped if the layer is a true convolution) -- produced by nbe_prepare_weights_bf16. */
 int nbe_prepare_weights_bf16(const float* w, void* wq, int Cout, int Cin, int K, int flip, nbe_stream_t stream);
