@@ -406,3 +406,144 @@ extern "C" int nbe_blend_features(void* x, const void* saved, const float* alpha
     }
     return launched("blend_features_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------
+// All per-layer affines + demodulation coefficients of one forward pass in ONE launch, and all shifted-noise maps in
+// another: at batch 256 the ~40 tiny per-layer launches they replace cost ~0.5 ms of pure launch/drain latency.
+// ---------------------------------------------------------------------------------------------
+namespace nbe {
+
+constexpr int SD_MAX_LAYERS = 16;
+
+struct StylesTable {
+    int n_layers;
+    const float* affine_w[SD_MAX_LAYERS];     // [cin, w_dim]
+    const float* affine_b[SD_MAX_LAYERS];     // [cin]
+    const float* wsq[SD_MAX_LAYERS];          // [cout, cin] or NULL (no demodulation)
+    float* styles[SD_MAX_LAYERS];             // [N, cin]
+    float* dcoef[SD_MAX_LAYERS];              // [N, cout] or NULL
+    int cin[SD_MAX_LAYERS], cout[SD_MAX_LAYERS], w_index[SD_MAX_LAYERS];
+    float post_scale[SD_MAX_LAYERS];          // styles *= post_scale for channels >= post_from (ToRGB: 1/sqrt(C) after the 9 colour outputs)
+    int post_from[SD_MAX_LAYERS];
+};
+
+// grid = (N, n_layers); block = 128 threads.  styles = affine(w) (FullyConnectedLayer, lr 1, bias_init 1: networks.py:109-122),
+// d[o] = rsqrt(sum_i styles[i]^2 wsq[o,i] + 1e-8) (networks.py:59-64).
+__global__ void __launch_bounds__(128)
+styles_demod_kernel(const float* __restrict__ ws, int num_ws, int w_dim, const StylesTable tab) {
+    extern __shared__ float s_sd[];                                 // [w_dim] latent, then [cin] styles^2
+    const int n = blockIdx.x, l = blockIdx.y;
+    const int cin = tab.cin[l], cout = tab.cout[l];
+    float* s_w = s_sd;
+    float* s_s2 = s_sd + w_dim;
+    for (int i = threadIdx.x; i < w_dim; i += 128) s_w[i] = ws[((long long)n * num_ws + tab.w_index[l]) * w_dim + i];
+    __syncthreads();
+    const float wgain = rsqrtf((float)w_dim);
+    for (int c = threadIdx.x; c < cin; c += 128) {
+        const float* wr = tab.affine_w[l] + (long long)c * w_dim;
+        float acc = 0.f;
+        for (int i = 0; i < w_dim; ++i) acc = fmaf(s_w[i], wr[i] * wgain, acc);
+        acc += tab.affine_b[l][c];
+        s_s2[c] = acc * acc;
+        if (c >= tab.post_from[l]) acc *= tab.post_scale[l];
+        tab.styles[l][(long long)n * cin + c] = acc;
+    }
+    __syncthreads();
+    if (tab.wsq[l] == nullptr || tab.dcoef[l] == nullptr) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o = warp; o < cout; o += 4) {
+        const float* q = tab.wsq[l] + (long long)o * cin;
+        float s = 0.f;
+        for (int i = lane; i < cin; i += 32) s = fmaf(s_s2[i], q[i], s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) tab.dcoef[l][(long long)n * cout + o] = rsqrtf(s + 1e-8f);
+    }
+}
+
+constexpr int SN_MAX_LAYERS = 16;
+struct NoiseTable {
+    int n_layers;
+    const float* noise_const[SN_MAX_LAYERS];
+    const float* lin[SN_MAX_LAYERS];
+    float* out[SN_MAX_LAYERS];                // [N, R, R]
+    int res[SN_MAX_LAYERS];
+    long long start[SN_MAX_LAYERS + 1];       // prefix sums of N * R * R
+};
+
+__global__ void __launch_bounds__(256)
+shifted_noise_all_kernel(const int64_t* __restrict__ positions, int N, int mod, const NoiseTable tab) {
+    const long long total = tab.start[tab.n_layers];
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        int l = 0;
+        while (g >= tab.start[l + 1]) ++l;
+        const int R = tab.res[l];
+        const int idx = (int)(g - tab.start[l]);
+        const int j = idx % R, i = (idx / R) % R, n = idx / (R * R);
+        const float* nc = tab.noise_const[l];
+        const float* lin = tab.lin[l];
+        int64_t py = positions[2 * n] % mod, px = positions[2 * n + 1] % mod;
+        if (py < 0) py += mod;
+        if (px < 0) px += mod;
+        const float p0 = __fdiv_rn((float)py, (float)(mod - 1));
+        const float p1 = __fdiv_rn((float)px, (float)(mod - 1));
+        float sx = __fadd_rn(lin[i], p0); sx = __fsub_rn(sx, floorf(sx));
+        float sy = __fadd_rn(lin[j], p1); sy = __fsub_rn(sy, floorf(sy));
+        const float gx = __fsub_rn(__fmul_rn(sx, 2.f), 1.f), gy = __fsub_rn(__fmul_rn(sy, 2.f), 1.f);
+        const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(R - 1));
+        const float cy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(R - 1));
+        const float fx0 = floorf(cx), fy0 = floorf(cy);
+        const float tx = cx - fx0, ty = cy - fy0;
+        const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+        auto at = [&](int yy, int xx) -> float { return (yy >= 0 && yy < R && xx >= 0 && xx < R) ? nc[yy * R + xx] : 0.f; };
+        tab.out[l][idx] = at(y0, x0) * (1.f - tx) * (1.f - ty) + at(y0, x1) * tx * (1.f - ty) +
+                          at(y1, x0) * (1.f - tx) * ty + at(y1, x1) * tx * ty;
+    }
+}
+
+}  // namespace nbe
+
+extern "C" int nbe_styles_demod_f32(const float* ws, int N, int num_ws, int w_dim, int n_layers,
+                                    const void* const* affine_w, const void* const* affine_b, const void* const* wsq,
+                                    void* const* styles, void* const* dcoef, const int* cin, const int* cout, const int* w_index,
+                                    const float* post_scale, const int* post_from, nbe_stream_t stream) {
+    NBE_REQUIRE(ws && N >= 0 && n_layers >= 1 && n_layers <= SD_MAX_LAYERS && w_dim >= 1 && num_ws >= 1, "styles_demod: bad arguments");
+    NBE_REQUIRE(affine_w && affine_b && wsq && styles && dcoef && cin && cout && w_index && post_scale && post_from, "styles_demod: null table");
+    if (N == 0) return NBE_OK;
+    NBE_REQUIRE(N <= INT32_MAX / 2, "styles_demod: batch too large");
+    StylesTable tab;
+    tab.n_layers = n_layers;
+    int max_cin = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        NBE_REQUIRE(affine_w[l] && affine_b[l] && styles[l] && cin[l] >= 1 && w_index[l] >= 0 && w_index[l] < num_ws, "styles_demod: bad layer %d", l);
+        tab.affine_w[l] = (const float*)affine_w[l]; tab.affine_b[l] = (const float*)affine_b[l]; tab.wsq[l] = (const float*)wsq[l];
+        tab.styles[l] = (float*)styles[l]; tab.dcoef[l] = (float*)dcoef[l]; tab.cin[l] = cin[l]; tab.cout[l] = cout[l];
+        tab.w_index[l] = w_index[l]; tab.post_scale[l] = post_scale[l]; tab.post_from[l] = post_from[l];
+        if (cin[l] > max_cin) max_cin = cin[l];
+    }
+    dim3 grid(N, n_layers);
+    const size_t smem = (size_t)(w_dim + max_cin) * sizeof(float);
+    NBE_REQUIRE(smem <= 48 * 1024, "styles_demod: layer too wide");
+    styles_demod_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(ws, num_ws, w_dim, tab);
+    return launched("styles_demod_kernel");
+}
+
+extern "C" int nbe_shifted_noise_all_f32(const int64_t* positions, int N, int mod, int n_layers,
+                                         const void* const* noise_const, const void* const* lin, void* const* out, const int* res,
+                                         nbe_stream_t stream) {
+    NBE_REQUIRE(positions && N >= 0 && mod >= 2 && n_layers >= 1 && n_layers <= SN_MAX_LAYERS && noise_const && lin && out && res, "shifted_noise_all: bad arguments");
+    if (N == 0) return NBE_OK;
+    NoiseTable tab;
+    tab.n_layers = n_layers;
+    tab.start[0] = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        NBE_REQUIRE(noise_const[l] && lin[l] && out[l] && res[l] >= 2, "shifted_noise_all: bad layer %d", l);
+        tab.noise_const[l] = (const float*)noise_const[l]; tab.lin[l] = (const float*)lin[l]; tab.out[l] = (float*)out[l]; tab.res[l] = res[l];
+        NBE_REQUIRE((long long)N * res[l] * res[l] <= INT32_MAX, "shifted_noise_all: layer %d too large", l);
+        tab.start[l + 1] = tab.start[l] + (long long)N * res[l] * res[l];
+    }
+    long long blocks = (tab.start[n_layers] + 255) / 256;
+    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    shifted_noise_all_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(positions, N, mod, tab);
+    return launched("shifted_noise_all_kernel");
+}

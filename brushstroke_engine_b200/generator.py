@@ -19,6 +19,7 @@ Forward only.  All compute is in libnbe_b200.so; torch provides memory, streams 
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 from typing import Dict, List, Optional, Sequence
@@ -137,6 +138,7 @@ class Generator:
         self.mapping = MappingNetwork(self)
         self.synthesis = SynthesisNetwork(self)
         self._flat_ws = {}
+        self._noise_cache = None
         self.last_up_fir_first = os.environ.get('NBE_LAST_UP_CONVT') is None
         self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
         self.probe = None       # optional {layer_name: [(start_event, end_event), ...]} filled by _conv_tc (bench.py roofline)
@@ -186,6 +188,23 @@ class Generator:
             self._rgb_affine_w = f32(p[f'{k}.affine.weight'])
             self._rgb_affine_b = f32(p[f'{k}.affine.bias'])
         self._layer_by_name = {L.name: L for L in self._layers}
+        # static halves of the fused styles/demod and shifted-noise launch tables (host arrays of device pointers)
+        nl = len(self._layers) + 1
+        VP, IA, FA = ctypes.c_void_p * nl, ctypes.c_int * nl, ctypes.c_float * nl
+        self._tab_n = nl
+        self._tab_aw = VP(*([L.affine_w.data_ptr() for L in self._layers] + [self._rgb_affine_w.data_ptr()]))
+        self._tab_ab = VP(*([L.affine_b.data_ptr() for L in self._layers] + [self._rgb_affine_b.data_ptr()]))
+        self._tab_wsq = VP(*([L.wsq.data_ptr() for L in self._layers] + [None]))
+        self._tab_cin = IA(*([L.cin for L in self._layers] + [self._rgb_affine_w.shape[0]]))
+        self._tab_cout = IA(*([L.cout for L in self._layers] + [0]))
+        self._tab_widx = IA(*list(range(nl)))                       # layer l reads ws[:, l] (networks_modified.py:144-151)
+        self._tab_pscale = FA(*([1.0] * (nl - 1) + [1.0 / math.sqrt(self._rgb_w.shape[1])]))
+        self._tab_pfrom = IA(*([0] * (nl - 1) + [9]))
+        self._VP = VP
+        nn = len(self._layers)
+        self._ntab_nc = (ctypes.c_void_p * nn)(*[L.noise_const.data_ptr() for L in self._layers])
+        self._ntab_lin = (ctypes.c_void_p * nn)(*[self._lin[L.res].data_ptr() for L in self._layers])
+        self._ntab_res = (ctypes.c_int * nn)(*[L.res for L in self._layers])
 
     def _workspace(self, B: int):
         """Zero-gapped NHWC bf16 buffers of the flat path, allocated (and zeroed) once per batch size: kernels only ever
@@ -262,6 +281,8 @@ class Generator:
             n = torch.randn([B, 1, R, R], device=self.device)                    # RNG stays in torch (same stream as the reference)
             return n, R * R, L.noise_strength
         assert noise_mode == 'const'
+        if positions is not None and input_noise is None and self._noise_cache is not None:
+            return self._noise_cache[L.name], R * R, L.noise_strength
         nc = L.noise_const if input_noise is None else input_noise.to(self.device, torch.float32).contiguous()
         if positions is not None:
             out = torch.empty((B, R, R), dtype=torch.float32, device=self.device)
@@ -276,24 +297,43 @@ class Generator:
         return nc, 0, L.noise_strength
 
     def _styles(self, ws: torch.Tensor):
-        """All affine layers + demodulation coefficients up front (they depend on ws only)."""
-        styles, dcoefs = {}, {}
-        w_idx = 0
-        for res in self.cfg.block_resolutions:
-            names = ([f'b{res}.conv0'] if res > 4 else []) + [f'b{res}.conv1']
-            for j, name in enumerate(names):
-                L = self._layer_by_name[name]
-                s = fully_connected(ws[:, w_idx + j].contiguous(), L.affine_w, L.affine_b)
-                styles[name] = s
-                dcoefs[name] = demod_coefs(s, L.wsq)
-            w_idx += len(names)
-        # ToRGB: affine -> [colors(9) | styles(C)] (networks.py:455-462); w index = last conv + 1
-        scaled = fully_connected(ws[:, w_idx].contiguous(), self._rgb_affine_w, self._rgb_affine_b)
-        cin = self._rgb_w.shape[1]
+        """All affine layers + demodulation coefficients in one launch (they depend on ws only)."""
+        B = ws.shape[0]
+        ws = ws.contiguous()
+        dev = self.device
+        st_t = [torch.empty((B, L.cin), dtype=torch.float32, device=dev) for L in self._layers]
+        dc_t = [torch.empty((B, L.cout), dtype=torch.float32, device=dev) for L in self._layers]
+        scaled = torch.empty((B, self._rgb_affine_w.shape[0]), dtype=torch.float32, device=dev)
+        tab_st = self._VP(*([t.data_ptr() for t in st_t] + [scaled.data_ptr()]))
+        tab_dc = self._VP(*([t.data_ptr() for t in dc_t] + [None]))
+        _lib.call('nbe_styles_demod_f32', _lib.ptr(ws), B, self.num_ws, self.w_dim, self._tab_n, self._tab_aw, self._tab_ab,
+                  self._tab_wsq, tab_st, tab_dc, self._tab_cin, self._tab_cout, self._tab_widx, self._tab_pscale, self._tab_pfrom,
+                  _lib.stream())
+        styles = {L.name: t for L, t in zip(self._layers, st_t)}
+        dcoefs = {L.name: t for L, t in zip(self._layers, dc_t)}
+        # ToRGB: affine -> [colors(9) | styles(C) / sqrt(C)] (networks.py:455-462)
         from .bias_act import bias_act
         colors = bias_act(scaled[:, :9].contiguous(), self._rgb_color_bias, dim=1, act='tanh').reshape(-1, 3, 3)
-        rgb_styles = (scaled[:, 9:] * (1.0 / math.sqrt(cin))).contiguous()
+        rgb_styles = scaled[:, 9:].contiguous()
         return styles, dcoefs, colors, rgb_styles
+
+    def _noise_all(self, B: int, positions):
+        """Shifted constant noise of every layer in one launch -> {layer name: [B, R, R]}."""
+        pos = positions.to(self.device, torch.int64).contiguous()
+        assert pos.shape == (B, 2)
+        total = sum(L.res * L.res for L in self._layers)
+        buf = torch.empty((B * total,), dtype=torch.float32, device=self.device)
+        outs, off = {}, 0
+        ptrs = []
+        for L in self._layers:
+            n = B * L.res * L.res
+            outs[L.name] = buf[off:off + n].view(B, L.res, L.res)
+            ptrs.append(buf.data_ptr() + 4 * off)
+            off += n
+        tab_out = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        _lib.call('nbe_shifted_noise_all_f32', _lib.ptr(pos), B, self.img_resolution, len(ptrs), self._ntab_nc, self._ntab_lin,
+                  tab_out, self._ntab_res, _lib.stream())
+        return outs
 
     def _synthesis(self, ws, geom_feature, pos_encoding=None, return_debug_data=False, return_features=None,
                    blended_features=None, noise_buffers=None, positions=None, noise_mode='random', force_fp32=False,
@@ -324,6 +364,7 @@ class Generator:
                     raise RuntimeError('synthesis: InjectedGeometry was prepared for a different ws tensor')
                 styles, dcoefs, colors, rgb_styles = self._styles(ws)
             run = self._run_fp32 if mode == 'fp32' else (self._run_bf16_flat if flat else self._run_bf16)
+            self._noise_cache = self._noise_all(B, positions) if (positions is not None and noise_mode == 'const') else None
             img, uvs, feats = run(B, styles, dcoefs, colors, rgb_styles, geom_feature, positions, norm_noise_positions,
                                   noise_mode, noise_buffers, return_features, blended_features)
         debug = dict(feats)

@@ -101,6 +101,21 @@ int nbe_fc_f32(const void* x, int x_is_f64, const float* w, const float* b, floa
 int nbe_shifted_noise_f32(const float* noise_const, const float* lin, const int64_t* positions, float* out,
                           int N, int R, int mod, nbe_stream_t stream);
 
+/* All style affines and demodulation coefficients of one forward pass in one launch (the arrays are HOST arrays of
+ * n_layers device pointers / ints):  styles_l[n,:] = affine_l(ws[n, w_index_l, :]) (FullyConnectedLayer, lr 1),
+ * channels >= post_from_l multiplied by post_scale_l (ToRGB: 1/sqrt(C) after its 9 colour outputs, networks.py:455-462);
+ * dcoef_l[n,o] = rsqrt(sum_i styles_l[n,i]^2 wsq_l[o,i] + 1e-8) from the UN-scaled styles when wsq_l / dcoef_l are non-NULL.
+ * Replaces 12 x nbe_fc_f32 + 11 x nbe_demod_coefs_f32. */
+int nbe_styles_demod_f32(const float* ws, int N, int num_ws, int w_dim, int n_layers,
+                         const void* const* affine_w, const void* const* affine_b, const void* const* wsq,
+                         void* const* styles, void* const* dcoef, const int* cin, const int* cout, const int* w_index,
+                         const float* post_scale, const int* post_from, nbe_stream_t stream);
+
+/* nbe_shifted_noise_f32 for n_layers noise buffers at once (HOST arrays of device pointers; out_l is [N, res_l, res_l]). */
+int nbe_shifted_noise_all_f32(const int64_t* positions, int N, int mod, int n_layers,
+                              const void* const* noise_const, const void* const* lin, void* const* out, const int* res,
+                              nbe_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core (BF16, tcgen05 + TMA + TMEM) path.  Activations are NHWC bf16 with a channel stride
  * (so geometry features can live in the same buffer: SG2/training/networks_modified.py:219 torch.cat).
