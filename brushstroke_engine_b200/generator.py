@@ -281,8 +281,8 @@ class Generator:
             n = torch.randn([B, 1, R, R], device=self.device)                    # RNG stays in torch (same stream as the reference)
             return n, R * R, L.noise_strength
         assert noise_mode == 'const'
-        if positions is not None and input_noise is None and self._noise_cache is not None:
-            return self._noise_cache[L.name], R * R, L.noise_strength
+        if positions is not None and input_noise is None and self._noise_cache is not None and self._noise_cache[0] is positions:
+            return self._noise_cache[1][L.name], R * R, L.noise_strength
         nc = L.noise_const if input_noise is None else input_noise.to(self.device, torch.float32).contiguous()
         if positions is not None:
             out = torch.empty((B, R, R), dtype=torch.float32, device=self.device)
@@ -364,7 +364,7 @@ class Generator:
                     raise RuntimeError('synthesis: InjectedGeometry was prepared for a different ws tensor')
                 styles, dcoefs, colors, rgb_styles = self._styles(ws)
             run = self._run_fp32 if mode == 'fp32' else (self._run_bf16_flat if flat else self._run_bf16)
-            self._noise_cache = self._noise_all(B, positions) if (positions is not None and noise_mode == 'const') else None
+            self._noise_cache = (positions, self._noise_all(B, positions)) if (positions is not None and noise_mode == 'const') else None
             img, uvs, feats = run(B, styles, dcoefs, colors, rgb_styles, geom_feature, positions, norm_noise_positions,
                                   noise_mode, noise_buffers, return_features, blended_features)
         debug = dict(feats)
