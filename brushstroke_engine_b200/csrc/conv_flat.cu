@@ -18,24 +18,33 @@
 //     T[2Y+py, 2X+px]; the 4x4 FIR + bias/activation follow in nbe_fir_act_nhwc_bf16.
 #include "tc_common.cuh"
 #include <mutex>
+#include <algorithm>
+#include <cstdlib>
 
 namespace nbe {
 
-constexpr int F_BOX_ROWS = 64;
-constexpr int F_BOX_BYTES = F_BOX_ROWS * 128;
-constexpr int F_BSTAGES = 4;
+constexpr int F_BSTAGES = 4;                                       // weight ring depth (streamed mode)
 constexpr int F_BBYTES = 128 * 128;
 constexpr int F_MAX_TAPS = 9;
 constexpr int F_MAX_CLASSES = 4;
-constexpr int F_THREADS = 192;
+constexpr int F_THREADS = 320;                                     // TMA warp, MMA warp, 8 epilogue warps
+constexpr int F_EPI_WARPS = 8;
+constexpr int F_STAGE_BYTES = 32 * 64;                             // per epilogue warp: 32 positions x 32 channels
 
 struct FlatParams {
     __nv_bfloat16* y;
-    int N, P, positions, tiles_per_img, T, G, nbuf, items_per_img, total_items;
+    int N, P, positions, tiles_per_img, T, nbuf, items_per_img, total_items;
     int ntaps;
     int tap_shift[F_MAX_TAPS], tap_acc[F_MAX_TAPS], tap_btile[F_MAX_TAPS], tap_first[F_MAX_TAPS];
     int cls_sy[F_MAX_CLASSES], cls_sx[F_MAX_CLASSES], cls_oy[F_MAX_CLASSES], cls_ox[F_MAX_CLASSES], cls_vy[F_MAX_CLASSES], cls_vx[F_MAX_CLASSES];
-    int min_shift, n_boxes, k_chunks;
+    int min_shift, n_boxes, box_rows, k_chunks;
+    // phases: a work item is processed as n_phases sub-items that share the position window but own disjoint taps /
+    // classes, so that the accumulators of one phase fit in half of TMEM and can be double-buffered against the epilogue
+    int n_phases, ph_t0[2], ph_t1[2], ph_G[2], ph_cls[2][F_MAX_CLASSES], Gmax;
+    // resident: the weights of ONE phase stay in shared memory while the CTA sweeps all of its items (phase-major order),
+    // so that only the position windows stream from L2; otherwise weights stream through a F_BSTAGES ring (item-major)
+    int resident, b_tiles;
+    uint32_t smem_need;
     int y_cs; long long y_row_pitch, y_img_pitch; int noise_w;
     const float* dcoef; const float* noise; long long noise_sn; float noise_gain;
     const float* bias; int act; float alpha, gain, clamp; const float* next_scale;
@@ -45,26 +54,35 @@ struct FlatParams {
 template <int EPI>   // 0: accumulators are stored as they are (bf16); 1: full SynthesisLayer epilogue
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const FlatParams p) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int a_bytes = p.n_boxes * F_BOX_BYTES;
-    uint8_t* smem_a = smem;                                         // [2][n_boxes * 8 KiB]
-    uint8_t* smem_b = smem + 2 * a_bytes;                           // [F_BSTAGES][16 KiB]
-    float* s_vec = reinterpret_cast<float*>(smem_b + F_BSTAGES * F_BBYTES);   // [3][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + 3 * 128);
+    {
+        uint32_t dyn;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if ((uint32_t)(smem - smem_raw) + p.smem_need > dyn) __trap();   // the host sized the buffer for an aligned base
+    }
+    const int a_bytes = p.n_boxes * p.box_rows * 128;
+    uint8_t* smem_a = smem;                                         // [2][window of one 64-channel chunk]
+    uint8_t* smem_b = smem + 2 * a_bytes;                           // [b_tiles][16 KiB]: ring, or the resident phase weights
+    uint8_t* smem_stage = smem_b + p.b_tiles * F_BBYTES;            // [F_EPI_WARPS][F_STAGE_BYTES] epilogue transposition buffers
+    float* s_vec = reinterpret_cast<float*>(smem_stage + F_EPI_WARPS * F_STAGE_BYTES);   // [3][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + (EPI == 1 ? 3 * 128 : 0));
     uint64_t* a_full = bars;            // [2]
     uint64_t* a_empty = bars + 2;       // [2]
     uint64_t* b_full = bars + 4;        // [F_BSTAGES]
     uint64_t* b_empty = bars + 4 + F_BSTAGES;
     uint64_t* acc_full = bars + 4 + 2 * F_BSTAGES;      // [2]
     uint64_t* acc_empty = acc_full + 2;                 // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* res_full = acc_empty + 2;                 // resident weights landed
+    uint64_t* res_free = res_full + 1;                  // all MMAs of the phase have drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_free + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1);
-                                      mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+                                      mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), F_EPI_WARPS); }
         for (int i = 0; i < F_BSTAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+        mbar_init(smem_u32(res_full), 1); mbar_init(smem_u32(res_free), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
@@ -77,31 +95,50 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int set_cols = p.T * p.G * 128;                           // TMEM columns of one accumulator set
+    const int set_cols = p.T * p.Gmax * 128;                        // TMEM columns of one accumulator set
+    // this CTA's schedule: n_local items x n_phases, item-major (streamed weights) or phase-major (resident weights)
+    const int n_local = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_steps = n_local * p.n_phases;
+    auto decode = [&](int s, int& k, int& ph) {
+        if (p.resident) { ph = s / n_local; k = s - ph * n_local; }
+        else            { k = s / p.n_phases; ph = s - k * p.n_phases; }
+    };
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
         if (lane == 0) {
             int ai = 0; uint32_t a_phase[2] = {0, 0};
             int bs = 0; uint32_t b_phase = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            for (int s = 0; s < n_steps; ++s) {
+                int k, ph; decode(s, k, ph);
+                const int item = blockIdx.x + k * gridDim.x;
                 const int n = item / p.items_per_img;
                 const int q0 = (item - n * p.items_per_img) * p.T * 128;
+                const int t0 = p.ph_t0[ph], ntp = p.ph_t1[ph] - t0;
+                if (p.resident && k == 0) {
+                    if (ph > 0) mbar_wait(smem_u32(res_free), (uint32_t)((ph - 1) & 1));   // previous phase's MMAs are done with smem_b
+                    const uint32_t rf = smem_u32(res_full);
+                    mbar_expect_tx(rf, (uint32_t)(ntp * p.k_chunks) * F_BBYTES);
+                    for (int c = 0; c < p.k_chunks; ++c)
+                        for (int t = 0; t < ntp; ++t)
+                            tma_load_3d(smem_u32(smem_b + (c * ntp + t) * F_BBYTES), &tmap_b, rf, c * 64, 0, p.tap_btile[t0 + t]);
+                }
                 for (int c = 0; c < p.k_chunks; ++c) {
                     mbar_wait(smem_u32(&a_empty[ai]), a_phase[ai] ^ 1);
                     const uint32_t full = smem_u32(&a_full[ai]);
                     mbar_expect_tx(full, (uint32_t)a_bytes);
                     for (int b = 0; b < p.n_boxes; ++b)
-                        tma_load_3d(smem_u32(smem_a + ai * a_bytes + b * F_BOX_BYTES), &tmap_a, full, c * 64,
-                                    q0 + p.min_shift + b * F_BOX_ROWS, n);
+                        tma_load_3d(smem_u32(smem_a + ai * a_bytes + b * p.box_rows * 128), &tmap_a, full, c * 64,
+                                    q0 + p.min_shift + b * p.box_rows, n);
                     a_phase[ai] ^= 1; ai ^= 1;
-                    for (int t = 0; t < p.ntaps; ++t) {
-                        mbar_wait(smem_u32(&b_empty[bs]), b_phase ^ 1);
-                        const uint32_t bf = smem_u32(&b_full[bs]);
-                        mbar_expect_tx(bf, F_BBYTES);
-                        tma_load_3d(smem_u32(smem_b + bs * F_BBYTES), &tmap_b, bf, c * 64, 0, p.tap_btile[t]);
-                        if (++bs == F_BSTAGES) { bs = 0; b_phase ^= 1; }
-                    }
+                    if (!p.resident)
+                        for (int t = t0; t < t0 + ntp; ++t) {
+                            mbar_wait(smem_u32(&b_empty[bs]), b_phase ^ 1);
+                            const uint32_t bf = smem_u32(&b_full[bs]);
+                            mbar_expect_tx(bf, F_BBYTES);
+                            tma_load_3d(smem_u32(smem_b + bs * F_BBYTES), &tmap_b, bf, c * 64, 0, p.tap_btile[t]);
+                            if (++bs == F_BSTAGES) { bs = 0; b_phase ^= 1; }
+                        }
                 }
             }
         }
@@ -110,9 +147,12 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int ai = 0; uint32_t a_phase[2] = {0, 0}, acc_phase[2] = {0, 0};
             int bs = 0; uint32_t b_phase = 0;
-            int it = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-                const int ab = (p.nbuf == 2) ? (it & 1) : 0;
+            for (int s = 0; s < n_steps; ++s) {
+                int k, ph; decode(s, k, ph);
+                const int G = p.ph_G[ph];
+                const int t0 = p.ph_t0[ph], ntp = p.ph_t1[ph] - t0;
+                const int ab = (p.nbuf == 2) ? (s & 1) : 0;
+                if (p.resident && k == 0) { mbar_wait(smem_u32(res_full), (uint32_t)(ph & 1)); tcgen05_fence_after(); }
                 mbar_wait(smem_u32(&acc_empty[ab]), acc_phase[ab] ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(ab * set_cols);
@@ -120,47 +160,70 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_wait(smem_u32(&a_full[ai]), a_phase[ai]);
                     tcgen05_fence_after();
                     const uint32_t a_base = smem_u32(smem_a + ai * a_bytes);
-                    for (int t = 0; t < p.ntaps; ++t) {
-                        mbar_wait(smem_u32(&b_full[bs]), b_phase);
-                        tcgen05_fence_after();
-                        const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b + bs * F_BBYTES));
+                    for (int t = t0; t < t0 + ntp; ++t) {
+                        uint32_t b_addr;
+                        if (p.resident) b_addr = smem_u32(smem_b + (c * ntp + (t - t0)) * F_BBYTES);
+                        else {
+                            mbar_wait(smem_u32(&b_full[bs]), b_phase);
+                            tcgen05_fence_after();
+                            b_addr = smem_u32(smem_b + bs * F_BBYTES);
+                        }
+                        const uint64_t b_desc = umma_smem_desc(b_addr);
                         const uint32_t accum0 = (c != 0 || !p.tap_first[t]) ? 1u : 0u;
                         for (int i = 0; i < p.T; ++i) {
                             // position tile i, tap t: rows [i*128 + shift - min_shift, +128) of the window
                             const uint64_t a_desc = umma_smem_desc(a_base + (uint32_t)((i * 128 + p.tap_shift[t] - p.min_shift) * 128));
-                            const uint32_t d = d0 + (uint32_t)((i * p.G + p.tap_acc[t]) * 128);
+                            const uint32_t d = d0 + (uint32_t)((i * G + p.tap_acc[t]) * 128);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16(d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, accum0 | (uint32_t)(k != 0));
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16(d, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), p.idesc, accum0 | (uint32_t)(kk != 0));
                         }
-                        umma_commit(smem_u32(&b_empty[bs]));
-                        if (++bs == F_BSTAGES) { bs = 0; b_phase ^= 1; }
+                        if (!p.resident) {
+                            umma_commit(smem_u32(&b_empty[bs]));
+                            if (++bs == F_BSTAGES) { bs = 0; b_phase ^= 1; }
+                        }
                     }
                     umma_commit(smem_u32(&a_empty[ai]));
                     a_phase[ai] ^= 1; ai ^= 1;
                 }
                 umma_commit(smem_u32(&acc_full[ab]));
                 acc_phase[ab] ^= 1;
+                if (p.resident && k == n_local - 1) umma_commit(smem_u32(res_free));
             }
         }
     } else {
-        // ============================== epilogue (warps 2..5) ==============================
-        const int qd = warp & 3;
+        // ============================== epilogue (warps 2..9) ==============================
+        // The epilogue has 4x less MMA time to hide behind than in an ordinary 3x3 conv (2.25 taps per class tile), so it
+        // runs on 8 warps: TMEM lane quarter qd = warp % 4 (hardware rule), channel half hsel = (warp - 2) / 4.
+        // A TMEM lane (= position) is owned by one thread, but a position's channels are contiguous bytes of the output:
+        // storing them straight from the owning lanes costs one wavefront per lane and instruction.  Each warp therefore
+        // transposes 32 positions x 32 channels through a swizzled shared-memory buffer and writes 64-byte runs
+        // (4 lanes per position, 8 positions per instruction).
+        const int qd = warp & 3, hsel = (warp - 2) >> 2;
         const int m = qd * 32 + lane;
         const int et = threadIdx.x - 64;
+        uint8_t* stg = smem_stage + (warp - 2) * F_STAGE_BYTES;
+        const uint32_t stg_wr = smem_u32(stg) + lane * 64;
+        const int wr_sw = (lane >> 1) & 3;
+        const int rd_row0 = lane >> 2, rd_ch = lane & 3;
         uint32_t acc_phase[2] = {0, 0};
-        int it = 0, cur_n = -1;
+        int cur_n = -1;
         const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-            const int ab = (p.nbuf == 2) ? (it & 1) : 0;
+        for (int s = 0; s < n_steps; ++s) {
+            int k, ph; decode(s, k, ph);
+            const int item = blockIdx.x + k * gridDim.x;
+            const int G = p.ph_G[ph];
+            const int ab = (p.nbuf == 2) ? (s & 1) : 0;
             const int n = item / p.items_per_img;
             const int q0 = (item - n * p.items_per_img) * p.T * 128;
             if (EPI == 1 && n != cur_n) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                s_vec[et] = p.dcoef ? p.dcoef[(long long)n * 128 + et] : 1.f;
-                s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
-                s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * 128 + et] : 1.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et < 128) {
+                    s_vec[et] = p.dcoef ? p.dcoef[(long long)n * 128 + et] : 1.f;
+                    s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
+                    s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * 128 + et] : 1.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_n = n;
             }
             mbar_wait(smem_u32(&acc_full[ab]), acc_phase[ab]);
@@ -171,42 +234,57 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int q = q0 + i * 128 + m;
                 const int gy = q / p.P, gx = q - gy * p.P;
 #pragma unroll 1
-                for (int g = 0; g < p.G; ++g) {
+                for (int gl = 0; gl < G; ++gl) {
+                    const int g = p.ph_cls[ph][gl];                  // global class (output mapping) of local accumulator gl
                     const bool valid = q < p.positions && gy < p.cls_vy[g] && gx < p.cls_vx[g];
                     const int oy = gy * p.cls_sy[g] + p.cls_oy[g], ox = gx * p.cls_sx[g] + p.cls_ox[g];
                     float nz = 0.f;
-                    if (valid && p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.noise_w + ox] * p.noise_gain;
-                    __nv_bfloat16* yrow = p.y + ((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs;
+                    if (EPI == 1 && valid && p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.noise_w + ox] * p.noise_gain;
+                    // output pixel index of this lane's position (-1: not stored), handed to the lanes that write it
+                    const long long pix = valid ? (long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox : -1;
+                    long long rp[4];
+#pragma unroll
+                    for (int r8 = 0; r8 < 4; ++r8) rp[r8] = __shfl_sync(0xffffffffu, pix, r8 * 8 + rd_row0);
 #pragma unroll 1
-                    for (int c0 = 0; c0 < 128; c0 += 32) {
+                    for (int c32 = 0; c32 < 2; ++c32) {
+                        const int c0 = hsel * 64 + c32 * 32;
                         uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * set_cols + (i * p.G + g) * 128 + c0), v);
-                        if (!valid) continue;
+                        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * set_cols + (i * G + gl) * 128 + c0), v);
 #pragma unroll
                         for (int gg = 0; gg < 4; ++gg) {
-                            int4 out;
-                            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
+                            uint32_t o[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                if (EPI == 0) {
-                                    o2[e] = __floats2bfloat162_rn(__uint_as_float(v[gg * 8 + e * 2]), __uint_as_float(v[gg * 8 + e * 2 + 1]));
-                                } else {
-                                    float rr[2];
+                                float r0 = __uint_as_float(v[gg * 8 + e * 2]), r1 = __uint_as_float(v[gg * 8 + e * 2 + 1]);
+                                if (EPI == 1) {
+                                    float rr[2] = {r0, r1};
 #pragma unroll
                                     for (int h = 0; h < 2; ++h) {
-                                        const int o = c0 + gg * 8 + e * 2 + h;
-                                        float a = __uint_as_float(v[gg * 8 + e * 2 + h]) * s_vec[o] + nz + s_vec[128 + o];
+                                        const int oc = c0 + gg * 8 + e * 2 + h;
+                                        float a = rr[h] * s_vec[oc] + nz + s_vec[128 + oc];
                                         if (p.act) {
                                             a *= (a > 0.f) ? pos_gain : neg_gain;
                                             if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
                                         }
-                                        rr[h] = a * s_vec[256 + o];
+                                        rr[h] = a * s_vec[256 + oc];
                                     }
-                                    o2[e] = __floats2bfloat162_rn(rr[0], rr[1]);
+                                    r0 = rr[0]; r1 = rr[1];
                                 }
+                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
+                                o[e] = *reinterpret_cast<const uint32_t*>(&b2);
                             }
-                            *reinterpret_cast<int4*>(yrow + c0 + gg * 8) = out;
+                            // 16-byte chunk gg of this lane's 64-byte row, XOR-swizzled so that 8 lanes cover 8 bank groups
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                         :: "r"(stg_wr + (uint32_t)((gg ^ wr_sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
                         }
+                        __syncwarp();
+#pragma unroll
+                        for (int r8 = 0; r8 < 4; ++r8) {
+                            const int row = r8 * 8 + rd_row0;
+                            const int4 val = *reinterpret_cast<const int4*>(stg + row * 64 + ((rd_ch ^ ((row >> 1) & 3)) << 4));
+                            if (rp[r8] >= 0) *reinterpret_cast<int4*>(p.y + rp[r8] * p.y_cs + c0 + rd_ch * 8) = val;
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -232,20 +310,33 @@ static int launch_flat(const void* x, const void* wq, FlatParams& p, int N, int 
     p.min_shift = p.tap_shift[0];
     for (int t = 1; t < p.ntaps; ++t) { if (p.tap_shift[t] < p.min_shift) p.min_shift = p.tap_shift[t]; if (p.tap_shift[t] > max_shift) max_shift = p.tap_shift[t]; }
     const int win_rows = 128 * p.T + (max_shift - p.min_shift);
-    p.n_boxes = (win_rows + F_BOX_ROWS - 1) / F_BOX_ROWS;
+    p.n_boxes = (win_rows + 255) / 256;                             // TMA boxes of <= 256 rows, whole 8-row swizzle atoms
+    p.box_rows = ((win_rows + p.n_boxes - 1) / p.n_boxes + 7) / 8 * 8;
     p.tiles_per_img = (p.positions + 127) / 128;
     p.items_per_img = (p.tiles_per_img + p.T - 1) / p.T;
     const int64_t total = (int64_t)N * p.items_per_img;
-    if (total > INT32_MAX) return fail(NBE_EINVAL, "conv_flat: too many work items");
+    if (total * p.n_phases > INT32_MAX) return fail(NBE_EINVAL, "conv_flat: too many work items");
     p.total_items = (int)total;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const size_t smem = 1024 + 2 * (size_t)p.n_boxes * F_BOX_BYTES + F_BSTAGES * F_BBYTES + 3 * 128 * sizeof(float) + 256;
-    if (smem > 227 * 1024) return fail(NBE_EUNSUPPORTED, "conv_flat: window of %d rows does not fit in shared memory", win_rows);
+    const int grid = total < kNumSMs ? (int)total : kNumSMs;
+    const bool raw = !p.dcoef && !p.noise && !p.bias && !p.act && !p.next_scale;
+    const size_t fixed = 2 * (size_t)p.n_boxes * p.box_rows * 128 + F_EPI_WARPS * F_STAGE_BYTES + (raw ? 0 : 3 * 128 * sizeof(float)) + 256;
+    const size_t limit = 227 * 1024;
+    // resident weights pay off when the CTA sweeps several items per phase and the largest phase fits next to the windows
+    int max_phase_tiles = 0;
+    for (int ph = 0; ph < p.n_phases; ++ph) max_phase_tiles = std::max(max_phase_tiles, (p.ph_t1[ph] - p.ph_t0[ph]) * p.k_chunks);
+    static const bool no_resident = getenv("NBE_FLAT_NO_RESIDENT") != nullptr;
+    p.resident = !no_resident && p.n_phases > 1 && total >= 4 * (int64_t)grid && fixed + (size_t)max_phase_tiles * F_BBYTES <= limit;
+    p.b_tiles = p.resident ? max_phase_tiles : F_BSTAGES;
+    p.smem_need = (uint32_t)(fixed + (size_t)p.b_tiles * F_BBYTES);
+    if (p.smem_need > limit) return fail(NBE_EUNSUPPORTED, "conv_flat: window of %d rows does not fit in shared memory", win_rows);
+    // the kernel aligns its base to 1 KiB; dynamic shared memory normally starts aligned, so the slack is only added when it fits
+    const size_t smem = std::min(limit, (size_t)p.smem_need + 1024);
     CUtensorMap ta, tb;
     {
         cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)in_positions, (cuuint64_t)N};
         cuuint64_t strides[2] = {(cuuint64_t)x_cs * 2, (cuuint64_t)in_positions * x_cs * 2};
-        cuuint32_t box[3] = {64, F_BOX_ROWS, 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)p.box_rows, 1};
         int st = make_tmap(&ta, x, 3, dims, strides, box, "flat activations");
         if (st) return st;
     }
@@ -263,8 +354,6 @@ static int launch_flat(const void* x, const void* wq, FlatParams& p, int N, int 
         if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "conv_flat: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-    const int grid = total < kNumSMs ? (int)total : kNumSMs;
-    const bool raw = !p.dcoef && !p.noise && !p.bias && !p.act && !p.next_scale;
     if (raw) conv_tc_flat_kernel<0><<<grid, F_THREADS, smem, stream>>>(ta, tb, p);
     else     conv_tc_flat_kernel<1><<<grid, F_THREADS, smem, stream>>>(ta, tb, p);
     return launched("conv_tc_flat_kernel");
@@ -288,7 +377,7 @@ extern "C" int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
     NBE_REQUIRE(y_row_pitch >= OW && y_img_pitch >= y_row_pitch * OH, "conv3x3_flat: bad output pitches");
     if (N == 0) return NBE_OK;
     FlatParams p;
-    p.y = (__nv_bfloat16*)y; p.N = N; p.P = x_pitch; p.positions = OH * x_pitch; p.T = 2; p.G = 1; p.nbuf = 2;
+    p.y = (__nv_bfloat16*)y; p.N = N; p.P = x_pitch; p.positions = OH * x_pitch; p.T = 2; p.nbuf = 2;
     p.ntaps = 9;
     const int off = valid ? 0 : -1;
     for (int kh = 0; kh < 3; ++kh)
@@ -297,6 +386,7 @@ extern "C" int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
             p.tap_shift[t] = (kh + off) * x_pitch + (kw + off); p.tap_acc[t] = 0; p.tap_btile[t] = t; p.tap_first[t] = (t == 0);
         }
     p.cls_sy[0] = 1; p.cls_sx[0] = 1; p.cls_oy[0] = 0; p.cls_ox[0] = 0; p.cls_vy[0] = OH; p.cls_vx[0] = OW;
+    p.n_phases = 1; p.ph_t0[0] = 0; p.ph_t1[0] = 9; p.ph_G[0] = 1; p.ph_cls[0][0] = 0; p.Gmax = 1;
     p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch; p.noise_w = OW;
     p.dcoef = dcoef; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain;
     p.bias = bias; p.act = 1; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.next_scale = next_scale;
@@ -315,24 +405,32 @@ extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_o
     NBE_REQUIRE(t_row_pitch >= 2 * W + 1 && t_img_pitch >= t_row_pitch * (2 * H + 1), "convT3x3s2_flat: bad output pitches");
     if (N == 0) return NBE_OK;
     FlatParams p;
-    p.y = (__nv_bfloat16*)t_out; p.N = N; p.P = x_pitch; p.positions = (H + 1) * x_pitch; p.T = 1; p.G = 4; p.nbuf = 1;
+    p.y = (__nv_bfloat16*)t_out; p.N = N; p.P = x_pitch; p.positions = (H + 1) * x_pitch; p.T = 1; p.nbuf = 2;
     // T[2Y+kh, 2X+kw] += W[kh,kw] x[Y,X]  (F.conv_transpose2d, SG2/torch_utils/ops/conv2d_resample.py:124-138):
-    // class (py,px) at grid (Y',X') sums the taps with kh = py, kw = px (mod 2) over x[Y' - (kh-py)/2, X' - (kw-px)/2]
+    // class (py,px) at grid (Y',X') sums the taps with kh = py, kw = px (mod 2) over x[Y' - (kh-py)/2, X' - (kw-px)/2].
+    // Two phases of two classes each -- {(0,0): 4 taps, (1,1): 1 tap} and {(0,1): 2 taps, (1,0): 2 taps} -- so that a
+    // phase's two accumulators take 256 TMEM columns and the other 256 hold the previous phase while its epilogue runs.
+    const int phase_classes[2][2][2] = {{{0, 0}, {1, 1}}, {{0, 1}, {1, 0}}};
     int t = 0;
-    for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px) {
+    for (int ph = 0; ph < 2; ++ph) {
+        p.ph_t0[ph] = t;
+        for (int gl = 0; gl < 2; ++gl) {
+            const int py = phase_classes[ph][gl][0], px = phase_classes[ph][gl][1];
             const int g = py * 2 + px;
+            p.ph_cls[ph][gl] = g;
             bool first = true;
             for (int kh = py; kh < 3; kh += 2)
                 for (int kw = px; kw < 3; kw += 2) {
                     p.tap_shift[t] = -((kh - py) / 2) * x_pitch - (kw - px) / 2;
-                    p.tap_acc[t] = g; p.tap_btile[t] = kh * 3 + kw; p.tap_first[t] = first ? 1 : 0;
+                    p.tap_acc[t] = gl; p.tap_btile[t] = kh * 3 + kw; p.tap_first[t] = first ? 1 : 0;
                     first = false; ++t;
                 }
             p.cls_sy[g] = 2; p.cls_sx[g] = 2; p.cls_oy[g] = py; p.cls_ox[g] = px;
             p.cls_vy[g] = py ? H : H + 1; p.cls_vx[g] = px ? W : W + 1;
         }
-    p.ntaps = t;
+        p.ph_t1[ph] = t; p.ph_G[ph] = 2;
+    }
+    p.ntaps = t; p.n_phases = 2; p.Gmax = 2;
     p.y_cs = t_cs; p.y_row_pitch = t_row_pitch; p.y_img_pitch = t_img_pitch; p.noise_w = 0;
     p.dcoef = dcoef; p.noise = nullptr; p.noise_sn = 0; p.noise_gain = 0.f;
     p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.gain = 1.f; p.clamp = -1.f; p.next_scale = nullptr;

@@ -190,8 +190,14 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
 #pragma unroll
     for (int i = 0; i < 4; ++i) { fx[i] = f[i]; fy[i] = sep ? f[i * 4] / f[0] : 0.f; }
 
-    const int cv = threadIdx.x & 15, px = threadIdx.x >> 4;       // 16 channel vectors x 16 pixels
-    const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
+    // thread = 4 channels (8 bytes) x 2 adjacent output pixels x FT_OH rows: the pair shares 5 input columns per row (2.5
+    // unpacked vectors per output instead of 4), a warp reads 256 contiguous bytes of one pixel (conflict-free)
+    const int cq = threadIdx.x & 31, px = (threadIdx.x >> 5) * 2;
+    // lrelu(a) * gain == max(a*gain, a*gain*alpha) for gain > 0, 0 <= alpha <= 1: gain is folded into scale/bias/noise
+    const bool fold = p.gain > 0.f && p.alpha >= 0.f && p.alpha <= 1.f;
+    const float g_pre = fold ? p.gain : 1.f, g_post = fold ? 1.f : p.gain;
+    const float clamp_hi = p.clamp >= 0.f ? p.clamp : INFINITY;
+    const bool pair_noise = p.noise && ((p.OW | p.noise_sn) & 1) == 0 && ((uintptr_t)p.noise & 7) == 0;
     auto issue = [&](int tile, int b) {
         int t = tile;
         const int tx = t % tiles_x; t /= tiles_x;
@@ -212,77 +218,96 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
         const int n = t;
         if (n != cur_n) {
             for (int c = threadIdx.x; c < 128; c += 256) {
-                s_epi[c] = p.scale ? p.scale[(long long)n * 128 + c] : 1.f;
-                s_epi[128 + c] = p.bias ? p.bias[c] : 0.f;
+                s_epi[c] = (p.scale ? p.scale[(long long)n * 128 + c] : 1.f) * g_pre;
+                s_epi[128 + c] = (p.bias ? p.bias[c] : 0.f) * g_pre;
                 s_epi[256 + c] = p.next_scale ? p.next_scale[(long long)n * 128 + c] : 1.f;
             }
             cur_n = n;
             __syncthreads();
         }
-        mbar_wait(smem_u32(&full[b]), (uint32_t)((it >> 1) & 1));
-        const uint8_t* tb = bufs + b * BUF_STRIDE + cv * 16;
         const int ox = tx * FT_OW + px, oy0 = ty * FT_OH;
-        float sc[8], bs[8], ns[8];
+        // the per-pixel noise of the 2 x FT_OH outputs is fetched before waiting for the tile, off the critical path
+        float nz[FT_OH][2];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { sc[k] = s_epi[cv * 8 + k]; bs[k] = s_epi[128 + cv * 8 + k]; ns[k] = s_epi[256 + cv * 8 + k]; }
-        auto ld = [&](int r, int c, float (&v)[8]) {
-            const int4 raw = *reinterpret_cast<const int4*>(tb + (r * FT_IW + c) * 256);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { const float2 f2 = __bfloat1622float2(h2[k]); v[2 * k] = f2.x; v[2 * k + 1] = f2.y; }
-        };
-        auto finish = [&](int oy, float (&acc)[8]) {
-            if (oy >= p.OH || ox >= p.OW) return;
-            float nz = 0.f;
-            if (p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
-            int4 outv;
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
-            float r[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float a = acc[k] * sc[k] + nz + bs[k];
-                a *= (a > 0.f) ? pos_gain : neg_gain;
-                if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
-                r[k] = a * ns[k];
+        for (int r = 0; r < FT_OH; ++r) {
+            nz[r][0] = nz[r][1] = 0.f;
+            const int oy = oy0 + r;
+            if (p.noise && oy < p.OH && ox < p.OW) {
+                const float* np = p.noise + (long long)n * p.noise_sn + (long long)oy * p.OW + ox;
+                if (pair_noise) { const float2 v = __ldg(reinterpret_cast<const float2*>(np)); nz[r][0] = v.x; nz[r][1] = v.y; }
+                else { nz[r][0] = __ldg(np); if (ox + 1 < p.OW) nz[r][1] = __ldg(np + 1); }
             }
+        }
+        float sc[4], bs[4], ns[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o2[k] = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
-            st_stream16(p.y + (((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs + cv * 8), outv);
+        for (int k = 0; k < 4; ++k) { sc[k] = s_epi[cq * 4 + k]; bs[k] = s_epi[128 + cq * 4 + k]; ns[k] = s_epi[256 + cq * 4 + k]; }
+        const float ngain = p.noise_gain * g_pre;
+        mbar_wait(smem_u32(&full[b]), (uint32_t)((it >> 1) & 1));
+        const uint8_t* tb = bufs + b * BUF_STRIDE + cq * 8;
+        auto ld = [&](int r, int c, float (&v)[4]) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(tb + (r * FT_IW + c) * 256);
+            v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+            v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+        };
+        auto finish = [&](int r, int j, float (&acc)[4]) {
+            const int oy = oy0 + r;
+            if (oy >= p.OH || ox + j >= p.OW) return;
+            const float nzg = nz[r][j] * ngain;
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float a = fmaf(acc[k], sc[k], nzg + bs[k]);
+                if (fold) a = fmaxf(a, a * p.alpha);
+                else a *= ((a > 0.f) ? 1.f : p.alpha) * g_post;
+                a = fminf(fmaxf(a, -clamp_hi), clamp_hi);
+                o[k] = a * ns[k];
+            }
+            uint2 outv;
+            *reinterpret_cast<__nv_bfloat162*>(&outv.x) = __floats2bfloat162_rn(o[0], o[1]);
+            *reinterpret_cast<__nv_bfloat162*>(&outv.y) = __floats2bfloat162_rn(o[2], o[3]);
+            __stcs(reinterpret_cast<uint2*>(p.y + (((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox + j) * p.y_cs + cq * 4)), outv);
         };
         if (sep) {
-            float h[4][8];
-            auto hrow = [&](float (&dst)[8], int r) {
-                float v0[8], v1[8], v2[8], v3[8];
-                ld(r, px, v0); ld(r, px + 1, v1); ld(r, px + 2, v2); ld(r, px + 3, v3);
+            float h[4][2][4];
+            auto hrow = [&](float (&dst)[2][4], int r) {
+                float v[5][4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) dst[k] = fx[0] * v0[k] + fx[1] * v1[k] + fx[2] * v2[k] + fx[3] * v3[k];
+                for (int c = 0; c < 5; ++c) ld(r, px + c, v[c]);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dst[j][k] = fx[0] * v[j][k] + fx[1] * v[j + 1][k] + fx[2] * v[j + 2][k] + fx[3] * v[j + 3][k];
             };
             hrow(h[0], 0); hrow(h[1], 1); hrow(h[2], 2);
 #pragma unroll
             for (int r = 0; r < FT_OH; ++r) {
                 hrow(h[(r + 3) & 3], r + 3);
-                float acc[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    acc[k] = fy[0] * h[r & 3][k] + fy[1] * h[(r + 1) & 3][k] + fy[2] * h[(r + 2) & 3][k] + fy[3] * h[(r + 3) & 3][k];
-                finish(oy0 + r, acc);
+                for (int j = 0; j < 2; ++j) {
+                    float acc[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        acc[k] = fy[0] * h[r & 3][j][k] + fy[1] * h[(r + 1) & 3][j][k] + fy[2] * h[(r + 2) & 3][j][k] + fy[3] * h[(r + 3) & 3][j][k];
+                    finish(r, j, acc);
+                }
             }
         } else {
-#pragma unroll 1
+#pragma unroll
             for (int r = 0; r < FT_OH; ++r) {
-                float acc[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+                for (int j = 0; j < 2; ++j) {
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) {
-                        float v[8];
-                        ld(r + a, px + bb, v);
+                        for (int bb = 0; bb < 4; ++bb) {
+                            float v[4];
+                            ld(r + a, px + j + bb, v);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[a * 4 + bb], v[k], acc[k]);
-                    }
-                finish(oy0 + r, acc);
+                            for (int k = 0; k < 4; ++k) acc[k] = fmaf(f[a * 4 + bb], v[k], acc[k]);
+                        }
+                    finish(r, j, acc);
+                }
             }
         }
         __syncthreads();                                            // everyone is done with buffer b (and s_epi) before it is refilled

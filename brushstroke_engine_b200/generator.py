@@ -139,7 +139,7 @@ class Generator:
         self.synthesis = SynthesisNetwork(self)
         self._flat_ws = {}
         self._noise_cache = None
-        self.last_up_fir_first = os.environ.get('NBE_LAST_UP_CONVT') is None
+        self.last_up_fir_first = os.environ.get('NBE_LAST_UP_FIR_FIRST') is not None   # A/B switch: 4x-FLOP FIR-first path at 128^2
         self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
         self.probe = None       # optional {layer_name: [(start_event, end_event), ...]} filled by _conv_tc (bench.py roofline)
 
@@ -540,9 +540,8 @@ class Generator:
                 x1 = wsb[f'x{res}']
                 x1_pitch = x1.shape[2]
                 if res == last and self.last_up_fir_first:
-                    # 128^2: the CUDA-core FIR pass over the 129^2 x 128-channel map costs more than running the 3x3 conv on
-                    # the FIR-upsampled input at tensor-core speed -> FIR first (xin is already modulated), then the
-                    # row-resident kernel in 'valid' mode
+                    # A/B path (NBE_LAST_UP_FIR_FIRST): FIR-upsample the modulated input first, then the row-resident kernel
+                    # in 'valid' mode -- 4x the algorithmic FLOPs; was the faster choice at 128^2 until the FIR pass was tiled
                     U = wsb.get('u128')
                     if U is None:
                         U = wsb['u128'] = torch.empty((B, res + 2, res + 2, conv0.cin), dtype=torch.bfloat16, device=dev)
