@@ -1,21 +1,31 @@
-// "Flat" shifted-window implicit GEMM on tcgen05: 3x3 stride-1 convolutions AND stride-2 transposed convolutions of
-// NHWC bf16 activations whose rows are stored with a pitch P >= W + 1 and zero gap columns.
+// "Flat" shifted-window implicit GEMM on tcgen05 CTA pairs: 3x3 stride-1 convolutions AND stride-2 transposed
+// convolutions of NHWC bf16 activations whose rows are stored with a pitch P >= W + 1 and zero gap columns.
 //
 // With such a layout a pixel is one row of a [positions x channels] matrix (position q = y * P + x), the zero gap
 // columns / TMA out-of-bounds rows supply the convolution's padding, and EVERY filter tap is the same matrix shifted by a
-// constant number of rows (kh * P + kw).  One CTA therefore loads a window of positions ONCE per 64-channel chunk
+// constant number of rows (kh * P + kw).  A CTA therefore loads a window of positions ONCE per 64-channel chunk
 // (128 * T + halo rows, 128-byte swizzled) and feeds all taps from it through UMMA descriptors whose start address is
 // shifted by whole rows -- the 128-byte swizzle is a function of the absolute smem address, so a row-shifted start reads
-// exactly what TMA wrote.  Weight tiles stream through a 4-deep ring and are shared by the T position tiles of the item.
+// exactly what TMA wrote.
 //
 // A launch runs a small "tap program": taps = (row shift, accumulator, weight tile); accumulators = "classes" with
-// their own output mapping.  Two programs are built on the host:
-//   * conv3x3 ('same' over a zero-gapped input, or 'valid' over a haloed one): 9 taps -> 1 class, T = 2 tiles per item,
-//     accumulators double-buffered in TMEM (2 x 2 x 128 columns) so the epilogue overlaps the next item's MMAs;
+// their own output mapping; phases = groups of classes whose accumulators fit in half of TMEM, so that the epilogue of one
+// phase overlaps the MMAs of the next.  Two programs are built on the host:
+//   * conv3x3 ('same' over a zero-gapped input, or 'valid' over a haloed one): 9 taps -> 1 class, T = 2 tiles per item;
 //   * transposed conv 3x3 stride 2 (the up-sampling layers at their ALGORITHMIC cost: 9 taps per *input* pixel instead
 //     of 9 per output pixel): output parity class (py, px) takes the taps with kh = py (mod 2), kw = px (mod 2):
-//     4 + 2 + 2 + 1 taps -> 4 classes = 4 accumulators (all 512 TMEM columns), written interleaved into
-//     T[2Y+py, 2X+px]; the 4x4 FIR + bias/activation follow in nbe_fir_act_nhwc_bf16.
+//     4 + 2 + 2 + 1 taps -> 4 classes in 2 phases, written interleaved into T[2Y+py, 2X+px]; the 4x4 FIR +
+//     bias/activation follow in nbe_fir_act_nhwc_bf16.
+//
+// The kernel runs on CTA PAIRS (cta_group::2): the two SMs of a TPC execute ONE M = 256 MMA; CTA r of the pair owns item
+// 2j + r (its own position window and its own 128 accumulator lanes) and holds only HALF of every weight tile (64 of the
+// 128 output channels) -- the tensor core reads both halves.  Per SM this halves the L2 -> SM weight traffic and the
+// weight footprint in shared memory; when all weights of a phase fit (Cin <= 128) they stay RESIDENT while the pair
+// sweeps its items phase by phase, and only position windows stream from L2 through a deep ring.
+//
+// With 2.25 taps per class tile the transposed conv leaves the single MMA-issuing thread ~64 cycles per instruction, so
+// its loop is kept to a handful of instructions per tap: tap programs live in registers, descriptors are formed by 32-bit
+// adds on a precomputed low word, waits have a fast path.
 #include "tc_common.cuh"
 #include <mutex>
 #include <algorithm>
@@ -23,27 +33,26 @@
 
 namespace nbe {
 
-constexpr int F_BSTAGES = 4;                                       // weight ring depth (streamed mode)
-constexpr int F_BBYTES = 128 * 128;
 constexpr int F_MAX_TAPS = 9;
 constexpr int F_MAX_CLASSES = 4;
 constexpr int F_THREADS = 320;                                     // TMA warp, MMA warp, 8 epilogue warps
 constexpr int F_EPI_WARPS = 8;
 constexpr int F_STAGE_BYTES = 32 * 64;                             // per epilogue warp: 32 positions x 32 channels
+constexpr int F_MAX_ABUF = 6;
+constexpr int F_BSTAGES = 6;
+constexpr int F_BHALF = 64 * 128;                                  // this CTA's half of a [128 Cout x 64 Cin] weight tile
 
 struct FlatParams {
     __nv_bfloat16* y;
-    int N, P, positions, tiles_per_img, T, nbuf, items_per_img, total_items;
+    int N, P, positions, tiles_per_img, T, items_per_img, total_items;
     int ntaps;
     int tap_shift[F_MAX_TAPS], tap_acc[F_MAX_TAPS], tap_btile[F_MAX_TAPS], tap_first[F_MAX_TAPS];
     int cls_sy[F_MAX_CLASSES], cls_sx[F_MAX_CLASSES], cls_oy[F_MAX_CLASSES], cls_ox[F_MAX_CLASSES], cls_vy[F_MAX_CLASSES], cls_vx[F_MAX_CLASSES];
     int min_shift, n_boxes, box_rows, k_chunks;
-    // phases: a work item is processed as n_phases sub-items that share the position window but own disjoint taps /
-    // classes, so that the accumulators of one phase fit in half of TMEM and can be double-buffered against the epilogue
     int n_phases, ph_t0[2], ph_t1[2], ph_G[2], ph_cls[2][F_MAX_CLASSES], Gmax;
-    // resident: the weights of ONE phase stay in shared memory while the CTA sweeps all of its items (phase-major order),
+    // resident: the weights of ONE phase stay in shared memory while the pair sweeps all of its items (phase-major order),
     // so that only the position windows stream from L2; otherwise weights stream through a F_BSTAGES ring (item-major)
-    int resident, b_tiles;
+    int resident, b_tiles, n_abuf;
     uint32_t smem_need;
     int y_cs; long long y_row_pitch, y_img_pitch; int noise_w;
     const float* dcoef; const float* noise; long long noise_sn; float noise_gain;
@@ -51,8 +60,31 @@ struct FlatParams {
     uint32_t idesc;
 };
 
+// mbarrier wait whose common case (already complete) is one instruction; the bounded slow path is in mbar_wait
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) mbar_wait(bar, parity);
+}
+// MMA of the pair with descriptors given as (low word, shared high word): K-major SW128 operands differ only in bits 0..13
+// The whole MMA warp runs the issue loop with warp-uniform operands and only the instructions themselves sit behind
+// elect.sync: issued from inside a divergent `if (lane == 0)` region, ptxas cannot keep the descriptors in uniform
+// registers and wraps every tcgen05.mma in an elect / R2UR "waterfall" loop of ~15 instructions.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 template <int EPI>   // 0: accumulators are stored as they are (bf16); 1: full SynthesisLayer epilogue
-__global__ void __launch_bounds__(F_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const FlatParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,137 +94,177 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if ((uint32_t)(smem - smem_raw) + p.smem_need > dyn) __trap();   // the host sized the buffer for an aligned base
     }
     const int a_bytes = p.n_boxes * p.box_rows * 128;
-    uint8_t* smem_a = smem;                                         // [2][window of one 64-channel chunk]
-    uint8_t* smem_b = smem + 2 * a_bytes;                           // [b_tiles][16 KiB]: ring, or the resident phase weights
-    uint8_t* smem_stage = smem_b + p.b_tiles * F_BBYTES;            // [F_EPI_WARPS][F_STAGE_BYTES] epilogue transposition buffers
-    float* s_vec = reinterpret_cast<float*>(smem_stage + F_EPI_WARPS * F_STAGE_BYTES);   // [3][128]
+    uint8_t* smem_a = smem;                                         // [n_abuf][window of one 64-channel chunk]
+    uint8_t* smem_b = smem + p.n_abuf * a_bytes;                    // [b_tiles][8 KiB]: ring, or the resident phase weights
+    uint8_t* smem_stage = smem_b + p.b_tiles * F_BHALF;             // [F_EPI_WARPS][F_STAGE_BYTES] epilogue transposition buffers
+    float* s_vec = reinterpret_cast<float*>(smem_stage + F_EPI_WARPS * F_STAGE_BYTES);   // [3][128] (EPI == 1)
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + (EPI == 1 ? 3 * 128 : 0));
-    uint64_t* a_full = bars;            // [2]
-    uint64_t* a_empty = bars + 2;       // [2]
-    uint64_t* b_full = bars + 4;        // [F_BSTAGES]
-    uint64_t* b_empty = bars + 4 + F_BSTAGES;
-    uint64_t* acc_full = bars + 4 + 2 * F_BSTAGES;      // [2]
-    uint64_t* acc_empty = acc_full + 2;                 // [2]
-    uint64_t* res_full = acc_empty + 2;                 // resident weights landed
+    uint64_t* a_full = bars;                            // [F_MAX_ABUF]  (the leader's is the live one)
+    uint64_t* a_empty = a_full + F_MAX_ABUF;            // [F_MAX_ABUF]
+    uint64_t* b_full = a_empty + F_MAX_ABUF;            // [F_BSTAGES]
+    uint64_t* b_empty = b_full + F_BSTAGES;             // [F_BSTAGES]
+    uint64_t* acc_full = b_empty + F_BSTAGES;           // [2]
+    uint64_t* acc_empty = acc_full + 2;                 // [2]  (the leader's: both CTAs' epilogue warps arrive on it)
+    uint64_t* res_full = acc_empty + 2;                 // resident weights of both CTAs landed
     uint64_t* res_free = res_full + 1;                  // all MMAs of the phase have drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_free + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
+    const int rank = __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0);
+    const bool leader = rank == 0;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1);
-                                      mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), F_EPI_WARPS); }
+        for (int i = 0; i < F_MAX_ABUF; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
         for (int i = 0; i < F_BSTAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 2 * F_EPI_WARPS); }
         mbar_init(smem_u32(res_full), 1); mbar_init(smem_u32(res_free), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                             // barriers of BOTH CTAs are initialised before any remote arrive
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (UTCHMMA takes uniform registers)
     const int set_cols = p.T * p.Gmax * 128;                        // TMEM columns of one accumulator set
-    // this CTA's schedule: n_local items x n_phases, item-major (streamed weights) or phase-major (resident weights)
-    const int n_local = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // schedule of this pair: n_local item pairs x n_phases, item-major (streamed weights) or phase-major (resident weights);
+    // CTA r takes item 2j + r (the last pair may hold a dummy)
+    const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int pairs = (p.total_items + 1) >> 1;
+    const int n_local = (pairs - cid + n_clusters - 1) / n_clusters;
     const int n_steps = n_local * p.n_phases;
-    auto decode = [&](int s, int& k, int& ph) {
-        if (p.resident) { ph = s / n_local; k = s - ph * n_local; }
-        else            { k = s / p.n_phases; ph = s - k * p.n_phases; }
-    };
 
     if (warp == 0) {
-        // ============================== TMA producer ==============================
+        // ============================== TMA producer (both CTAs) ==============================
         if (lane == 0) {
-            int ai = 0; uint32_t a_phase[2] = {0, 0};
-            int bs = 0; uint32_t b_phase = 0;
+            uint32_t acnt = 0, bcnt = 0;
+            int k = 0, ph = 0;
             for (int s = 0; s < n_steps; ++s) {
-                int k, ph; decode(s, k, ph);
-                const int item = blockIdx.x + k * gridDim.x;
+                int item = 2 * (cid + k * n_clusters) + rank;
+                if (item >= p.total_items) item = p.total_items - 1;           // dummy: loads stay in range, nothing is stored
                 const int n = item / p.items_per_img;
                 const int q0 = (item - n * p.items_per_img) * p.T * 128;
                 const int t0 = p.ph_t0[ph], ntp = p.ph_t1[ph] - t0;
                 if (p.resident && k == 0) {
                     if (ph > 0) mbar_wait(smem_u32(res_free), (uint32_t)((ph - 1) & 1));   // previous phase's MMAs are done with smem_b
                     const uint32_t rf = smem_u32(res_full);
-                    mbar_expect_tx(rf, (uint32_t)(ntp * p.k_chunks) * F_BBYTES);
+                    if (leader) mbar_expect_tx(rf, 2u * (uint32_t)(ntp * p.k_chunks) * F_BHALF);
                     for (int c = 0; c < p.k_chunks; ++c)
                         for (int t = 0; t < ntp; ++t)
-                            tma_load_3d(smem_u32(smem_b + (c * ntp + t) * F_BBYTES), &tmap_b, rf, c * 64, 0, p.tap_btile[t0 + t]);
+                            tma_load_3d_2sm(smem_u32(smem_b + (c * ntp + t) * F_BHALF), &tmap_b, rf, c * 64, rank * 64, p.tap_btile[t0 + t]);
                 }
                 for (int c = 0; c < p.k_chunks; ++c) {
-                    mbar_wait(smem_u32(&a_empty[ai]), a_phase[ai] ^ 1);
-                    const uint32_t full = smem_u32(&a_full[ai]);
-                    mbar_expect_tx(full, (uint32_t)a_bytes);
+                    const int slot = (int)(acnt % (uint32_t)p.n_abuf);
+                    const uint32_t par = (acnt / (uint32_t)p.n_abuf) & 1u;
+                    ++acnt;
+                    mbar_wait_fast(smem_u32(&a_empty[slot]), par ^ 1);
+                    const uint32_t full = smem_u32(&a_full[slot]);
+                    if (leader) mbar_expect_tx(full, 2u * (uint32_t)a_bytes);
                     for (int b = 0; b < p.n_boxes; ++b)
-                        tma_load_3d(smem_u32(smem_a + ai * a_bytes + b * p.box_rows * 128), &tmap_a, full, c * 64,
-                                    q0 + p.min_shift + b * p.box_rows, n);
-                    a_phase[ai] ^= 1; ai ^= 1;
+                        tma_load_3d_2sm(smem_u32(smem_a + slot * a_bytes + b * p.box_rows * 128), &tmap_a, full, c * 64,
+                                        q0 + p.min_shift + b * p.box_rows, n);
                     if (!p.resident)
                         for (int t = t0; t < t0 + ntp; ++t) {
-                            mbar_wait(smem_u32(&b_empty[bs]), b_phase ^ 1);
+                            const int bs = (int)(bcnt % F_BSTAGES);
+                            const uint32_t bpar = (bcnt / F_BSTAGES) & 1u;
+                            ++bcnt;
+                            mbar_wait_fast(smem_u32(&b_empty[bs]), bpar ^ 1);
                             const uint32_t bf = smem_u32(&b_full[bs]);
-                            mbar_expect_tx(bf, F_BBYTES);
-                            tma_load_3d(smem_u32(smem_b + bs * F_BBYTES), &tmap_b, bf, c * 64, 0, p.tap_btile[t]);
-                            if (++bs == F_BSTAGES) { bs = 0; b_phase ^= 1; }
+                            if (leader) mbar_expect_tx(bf, 2u * F_BHALF);
+                            tma_load_3d_2sm(smem_u32(smem_b + bs * F_BHALF), &tmap_b, bf, c * 64, rank * 64, p.tap_btile[t]);
                         }
                 }
+                if (p.resident) { if (++k == n_local) { k = 0; ++ph; } }
+                else            { if (++ph == p.n_phases) { ph = 0; ++k; } }
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer ==============================
-        if (lane == 0) {
-            int ai = 0; uint32_t a_phase[2] = {0, 0}, acc_phase[2] = {0, 0};
-            int bs = 0; uint32_t b_phase = 0;
+        // ============================== MMA issuer (leader CTA only; whole warp, elected lane issues) ==============================
+        if (leader) {
+            // descriptor words: low = start address >> 4 | LBO, high = SBO (1024 B) | version 1 | SWIZZLE_128B
+            const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t a_step = (uint32_t)a_bytes >> 4;
+            const uint32_t idesc = p.idesc;
+            const int T = p.T, k_chunks = p.k_chunks, n_abuf = p.n_abuf;
+            const bool resident = p.resident != 0;
+            // the tap program of the current phase, in registers: row offset of the A start (16-byte units), accumulator column
+            // offset, "first tap of its accumulator" flag
+            uint32_t op_a[F_MAX_TAPS], op_d[F_MAX_TAPS], op_first[F_MAX_TAPS];
+            int ntp = 0, G = 1, cur_ph = -1;
+            uint32_t acc_par0 = 0, acc_par1 = 0;
+            int slot = 0; uint32_t a_par = 0;
+            int bs = 0; uint32_t b_par = 0;
+            int k = 0, ph = 0;
             for (int s = 0; s < n_steps; ++s) {
-                int k, ph; decode(s, k, ph);
-                const int G = p.ph_G[ph];
-                const int t0 = p.ph_t0[ph], ntp = p.ph_t1[ph] - t0;
-                const int ab = (p.nbuf == 2) ? (s & 1) : 0;
-                if (p.resident && k == 0) { mbar_wait(smem_u32(res_full), (uint32_t)(ph & 1)); tcgen05_fence_after(); }
-                mbar_wait(smem_u32(&acc_empty[ab]), acc_phase[ab] ^ 1);
+                if (ph != cur_ph) {
+                    cur_ph = ph;
+                    const int t0 = p.ph_t0[ph];
+                    ntp = p.ph_t1[ph] - t0; G = p.ph_G[ph];
+#pragma unroll
+                    for (int t = 0; t < F_MAX_TAPS; ++t)
+                        if (t < ntp) {
+                            op_a[t] = __shfl_sync(0xffffffffu, (uint32_t)((p.tap_shift[t0 + t] - p.min_shift) * 8), 0);
+                            op_d[t] = __shfl_sync(0xffffffffu, (uint32_t)(p.tap_acc[t0 + t] * 128), 0);
+                            op_first[t] = __shfl_sync(0xffffffffu, (uint32_t)p.tap_first[t0 + t], 0);
+                        }
+                }
+                const int ab = s & 1;
+                if (resident && k == 0) { mbar_wait(smem_u32(res_full), (uint32_t)(ph & 1)); tcgen05_fence_after(); }
+                if (ab) { mbar_wait_fast(smem_u32(&acc_empty[1]), acc_par1 ^ 1); acc_par1 ^= 1; }
+                else    { mbar_wait_fast(smem_u32(&acc_empty[0]), acc_par0 ^ 1); acc_par0 ^= 1; }
                 tcgen05_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(ab * set_cols);
-                for (int c = 0; c < p.k_chunks; ++c) {
-                    mbar_wait(smem_u32(&a_full[ai]), a_phase[ai]);
+                const uint32_t d_tile = (uint32_t)(G * 128);
+                for (int c = 0; c < k_chunks; ++c) {
+                    mbar_wait_fast(smem_u32(&a_full[slot]), a_par);
                     tcgen05_fence_after();
-                    const uint32_t a_base = smem_u32(smem_a + ai * a_bytes);
-                    for (int t = t0; t < t0 + ntp; ++t) {
-                        uint32_t b_addr;
-                        if (p.resident) b_addr = smem_u32(smem_b + (c * ntp + (t - t0)) * F_BBYTES);
-                        else {
-                            mbar_wait(smem_u32(&b_full[bs]), b_phase);
-                            tcgen05_fence_after();
-                            b_addr = smem_u32(smem_b + bs * F_BBYTES);
-                        }
-                        const uint64_t b_desc = umma_smem_desc(b_addr);
-                        const uint32_t accum0 = (c != 0 || !p.tap_first[t]) ? 1u : 0u;
-                        for (int i = 0; i < p.T; ++i) {
-                            // position tile i, tap t: rows [i*128 + shift - min_shift, +128) of the window
-                            const uint64_t a_desc = umma_smem_desc(a_base + (uint32_t)((i * 128 + p.tap_shift[t] - p.min_shift) * 128));
-                            const uint32_t d = d0 + (uint32_t)((i * G + p.tap_acc[t]) * 128);
+                    const uint32_t a_lo = a_lo0 + (uint32_t)slot * a_step;
+                    const uint32_t b_res = b_lo0 + (uint32_t)(c * ntp) * (F_BHALF >> 4);
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_bf16(d, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), p.idesc, accum0 | (uint32_t)(kk != 0));
-                        }
-                        if (!p.resident) {
-                            umma_commit(smem_u32(&b_empty[bs]));
-                            if (++bs == F_BSTAGES) { bs = 0; b_phase ^= 1; }
+                    for (int t = 0; t < F_MAX_TAPS; ++t) {
+                        if (t < ntp) {
+                            uint32_t b_lo;
+                            if (resident) b_lo = b_res + (uint32_t)t * (F_BHALF >> 4);
+                            else {
+                                mbar_wait_fast(smem_u32(&b_full[bs]), b_par);
+                                tcgen05_fence_after();
+                                b_lo = b_lo0 + (uint32_t)bs * (F_BHALF >> 4);
+                            }
+                            const uint32_t acc0 = (c != 0 || !op_first[t]) ? 1u : 0u;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int i = 0; i < 2; ++i) {
+                                    if (i < T) {
+                                        // position tile i, tap t: rows [i*128 + shift - min_shift, +128) of the window
+                                        const uint32_t al = a_lo + op_a[t] + (uint32_t)(i * 1024);
+                                        const uint32_t d = d0 + op_d[t] + (uint32_t)i * d_tile;
+                                        umma_pair(d, al, b_lo, desc_hi, idesc, acc0);
+                                        umma_pair(d, al + 2, b_lo + 2, desc_hi, idesc, 1u);
+                                        umma_pair(d, al + 4, b_lo + 4, desc_hi, idesc, 1u);
+                                        umma_pair(d, al + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                    }
+                                }
+                                if (!resident) umma_commit_2sm(smem_u32(&b_empty[bs]));
+                            }
+                            if (!resident) { if (++bs == F_BSTAGES) { bs = 0; b_par ^= 1; } }
                         }
                     }
-                    umma_commit(smem_u32(&a_empty[ai]));
-                    a_phase[ai] ^= 1; ai ^= 1;
+                    if (elect_one()) umma_commit_2sm(smem_u32(&a_empty[slot]));
+                    if (++slot == n_abuf) { slot = 0; a_par ^= 1; }
                 }
-                umma_commit(smem_u32(&acc_full[ab]));
-                acc_phase[ab] ^= 1;
-                if (p.resident && k == n_local - 1) umma_commit(smem_u32(res_free));
+                if (elect_one()) umma_commit_2sm(smem_u32(&acc_full[ab]));
+                if (resident) { if (++k == n_local) { if (elect_one()) umma_commit_2sm(smem_u32(res_free)); k = 0; ++ph; } }
+                else          { if (++ph == p.n_phases) { ph = 0; ++k; } }
             }
         }
     } else {
-        // ============================== epilogue (warps 2..9) ==============================
+        // ============================== epilogue (warps 2..9, both CTAs) ==============================
         // The epilogue has 4x less MMA time to hide behind than in an ordinary 3x3 conv (2.25 taps per class tile), so it
         // runs on 8 warps: TMEM lane quarter qd = warp % 4 (hardware rule), channel half hsel = (warp - 2) / 4.
         // A TMEM lane (= position) is owned by one thread, but a position's channels are contiguous bytes of the output:
@@ -209,11 +281,13 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t acc_phase[2] = {0, 0};
         int cur_n = -1;
         const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
+        int k = 0, ph = 0;
         for (int s = 0; s < n_steps; ++s) {
-            int k, ph; decode(s, k, ph);
-            const int item = blockIdx.x + k * gridDim.x;
+            int item = 2 * (cid + k * n_clusters) + rank;
+            const bool dummy = item >= p.total_items;
+            if (dummy) item = p.total_items - 1;
             const int G = p.ph_G[ph];
-            const int ab = (p.nbuf == 2) ? (s & 1) : 0;
+            const int ab = s & 1;
             const int n = item / p.items_per_img;
             const int q0 = (item - n * p.items_per_img) * p.T * 128;
             if (EPI == 1 && n != cur_n) {
@@ -229,75 +303,79 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_wait(smem_u32(&acc_full[ab]), acc_phase[ab]);
             acc_phase[ab] ^= 1;
             tcgen05_fence_after();
+            if (!dummy) {
 #pragma unroll 1
-            for (int i = 0; i < p.T; ++i) {
-                const int q = q0 + i * 128 + m;
-                const int gy = q / p.P, gx = q - gy * p.P;
+                for (int i = 0; i < p.T; ++i) {
+                    const int q = q0 + i * 128 + m;
+                    const int gy = q / p.P, gx = q - gy * p.P;
 #pragma unroll 1
-                for (int gl = 0; gl < G; ++gl) {
-                    const int g = p.ph_cls[ph][gl];                  // global class (output mapping) of local accumulator gl
-                    const bool valid = q < p.positions && gy < p.cls_vy[g] && gx < p.cls_vx[g];
-                    const int oy = gy * p.cls_sy[g] + p.cls_oy[g], ox = gx * p.cls_sx[g] + p.cls_ox[g];
-                    float nz = 0.f;
-                    if (EPI == 1 && valid && p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.noise_w + ox] * p.noise_gain;
-                    // output pixel index of this lane's position (-1: not stored), handed to the lanes that write it
-                    const long long pix = valid ? (long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox : -1;
-                    long long rp[4];
+                    for (int gl = 0; gl < G; ++gl) {
+                        const int g = p.ph_cls[ph][gl];              // global class (output mapping) of local accumulator gl
+                        const bool valid = q < p.positions && gy < p.cls_vy[g] && gx < p.cls_vx[g];
+                        const int oy = gy * p.cls_sy[g] + p.cls_oy[g], ox = gx * p.cls_sx[g] + p.cls_ox[g];
+                        float nz = 0.f;
+                        if (EPI == 1 && valid && p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.noise_w + ox] * p.noise_gain;
+                        // output pixel index of this lane's position (-1: not stored), handed to the lanes that write it
+                        const long long pix = valid ? (long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox : -1;
+                        long long rp[4];
 #pragma unroll
-                    for (int r8 = 0; r8 < 4; ++r8) rp[r8] = __shfl_sync(0xffffffffu, pix, r8 * 8 + rd_row0);
+                        for (int r8 = 0; r8 < 4; ++r8) rp[r8] = __shfl_sync(0xffffffffu, pix, r8 * 8 + rd_row0);
 #pragma unroll 1
-                    for (int c32 = 0; c32 < 2; ++c32) {
-                        const int c0 = hsel * 64 + c32 * 32;
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * set_cols + (i * G + gl) * 128 + c0), v);
+                        for (int c32 = 0; c32 < 2; ++c32) {
+                            const int c0 = hsel * 64 + c32 * 32;
+                            uint32_t v[32];
+                            tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * set_cols + (i * G + gl) * 128 + c0), v);
 #pragma unroll
-                        for (int gg = 0; gg < 4; ++gg) {
-                            uint32_t o[4];
+                            for (int gg = 0; gg < 4; ++gg) {
+                                uint32_t o[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float r0 = __uint_as_float(v[gg * 8 + e * 2]), r1 = __uint_as_float(v[gg * 8 + e * 2 + 1]);
-                                if (EPI == 1) {
-                                    float rr[2] = {r0, r1};
+                                for (int e = 0; e < 4; ++e) {
+                                    float r0 = __uint_as_float(v[gg * 8 + e * 2]), r1 = __uint_as_float(v[gg * 8 + e * 2 + 1]);
+                                    if (EPI == 1) {
+                                        float rr[2] = {r0, r1};
 #pragma unroll
-                                    for (int h = 0; h < 2; ++h) {
-                                        const int oc = c0 + gg * 8 + e * 2 + h;
-                                        float a = rr[h] * s_vec[oc] + nz + s_vec[128 + oc];
-                                        if (p.act) {
-                                            a *= (a > 0.f) ? pos_gain : neg_gain;
-                                            if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
+                                        for (int h = 0; h < 2; ++h) {
+                                            const int oc = c0 + gg * 8 + e * 2 + h;
+                                            float a = rr[h] * s_vec[oc] + nz + s_vec[128 + oc];
+                                            if (p.act) {
+                                                a *= (a > 0.f) ? pos_gain : neg_gain;
+                                                if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
+                                            }
+                                            rr[h] = a * s_vec[256 + oc];
                                         }
-                                        rr[h] = a * s_vec[256 + oc];
+                                        r0 = rr[0]; r1 = rr[1];
                                     }
-                                    r0 = rr[0]; r1 = rr[1];
+                                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
+                                    o[e] = *reinterpret_cast<const uint32_t*>(&b2);
                                 }
-                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(r0, r1);
-                                o[e] = *reinterpret_cast<const uint32_t*>(&b2);
+                                // 16-byte chunk gg of this lane's 64-byte row, XOR-swizzled so that 8 lanes cover 8 bank groups
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                             :: "r"(stg_wr + (uint32_t)((gg ^ wr_sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
                             }
-                            // 16-byte chunk gg of this lane's 64-byte row, XOR-swizzled so that 8 lanes cover 8 bank groups
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                         :: "r"(stg_wr + (uint32_t)((gg ^ wr_sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-                        }
-                        __syncwarp();
+                            __syncwarp();
 #pragma unroll
-                        for (int r8 = 0; r8 < 4; ++r8) {
-                            const int row = r8 * 8 + rd_row0;
-                            const int4 val = *reinterpret_cast<const int4*>(stg + row * 64 + ((rd_ch ^ ((row >> 1) & 3)) << 4));
-                            if (rp[r8] >= 0) *reinterpret_cast<int4*>(p.y + rp[r8] * p.y_cs + c0 + rd_ch * 8) = val;
+                            for (int r8 = 0; r8 < 4; ++r8) {
+                                const int row = r8 * 8 + rd_row0;
+                                const int4 val = *reinterpret_cast<const int4*>(stg + row * 64 + ((rd_ch ^ ((row >> 1) & 3)) << 4));
+                                if (rp[r8] >= 0) *reinterpret_cast<int4*>(p.y + rp[r8] * p.y_cs + c0 + rd_ch * 8) = val;
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                 }
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&acc_empty[ab])) : "memory");
+            if (lane == 0) mbar_arrive_leader(smem_u32(&acc_empty[ab]));
+            if (p.resident) { if (++k == n_local) { k = 0; ++ph; } }
+            else            { if (++ph == p.n_phases) { ph = 0; ++k; } }
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                             // the peer's smem / TMEM stay alive until the leader's last MMA is done
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -317,21 +395,15 @@ static int launch_flat(const void* x, const void* wq, FlatParams& p, int N, int 
     const int64_t total = (int64_t)N * p.items_per_img;
     if (total * p.n_phases > INT32_MAX) return fail(NBE_EINVAL, "conv_flat: too many work items");
     p.total_items = (int)total;
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int grid = total < kNumSMs ? (int)total : kNumSMs;
+    // kind::f16: D = f32, A = B = bf16, K-major; N = 128, M = 256 (the pair)
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     const bool raw = !p.dcoef && !p.noise && !p.bias && !p.act && !p.next_scale;
-    const size_t fixed = 2 * (size_t)p.n_boxes * p.box_rows * 128 + F_EPI_WARPS * F_STAGE_BYTES + (raw ? 0 : 3 * 128 * sizeof(float)) + 256;
     const size_t limit = 227 * 1024;
-    // resident weights pay off when the CTA sweeps several items per phase and the largest phase fits next to the windows
     int max_phase_tiles = 0;
     for (int ph = 0; ph < p.n_phases; ++ph) max_phase_tiles = std::max(max_phase_tiles, (p.ph_t1[ph] - p.ph_t0[ph]) * p.k_chunks);
     static const bool no_resident = getenv("NBE_FLAT_NO_RESIDENT") != nullptr;
-    p.resident = !no_resident && p.n_phases > 1 && total >= 4 * (int64_t)grid && fixed + (size_t)max_phase_tiles * F_BBYTES <= limit;
-    p.b_tiles = p.resident ? max_phase_tiles : F_BSTAGES;
-    p.smem_need = (uint32_t)(fixed + (size_t)p.b_tiles * F_BBYTES);
-    if (p.smem_need > limit) return fail(NBE_EUNSUPPORTED, "conv_flat: window of %d rows does not fit in shared memory", win_rows);
-    // the kernel aligns its base to 1 KiB; dynamic shared memory normally starts aligned, so the slack is only added when it fits
-    const size_t smem = std::min(limit, (size_t)p.smem_need + 1024);
+    const size_t a_bytes = (size_t)p.n_boxes * p.box_rows * 128;
+    const size_t epi_bytes = F_EPI_WARPS * F_STAGE_BYTES + (raw ? 0 : 3 * 128 * sizeof(float)) + 256;
     CUtensorMap ta, tb;
     {
         cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)in_positions, (cuuint64_t)N};
@@ -343,7 +415,7 @@ static int launch_flat(const void* x, const void* wq, FlatParams& p, int N, int 
     {
         cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, 128, (cuuint64_t)n_wtiles};
         cuuint64_t strides[2] = {(cuuint64_t)Cin_pad * 2, (cuuint64_t)128 * Cin_pad * 2};
-        cuuint32_t box[3] = {64, 128, 1};
+        cuuint32_t box[3] = {64, 64, 1};                            // half of the output channels per CTA of the pair
         int st = make_tmap(&tb, wq, 3, dims, strides, box, "weights");
         if (st) return st;
     }
@@ -354,6 +426,18 @@ static int launch_flat(const void* x, const void* wq, FlatParams& p, int N, int 
         if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "conv_flat: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    const int64_t pairs = (total + 1) / 2;
+    const int grid = (int)std::min<int64_t>(kNumSMs / 2, pairs) * 2;
+    // resident weights pay off when a pair sweeps several items per phase and the largest phase fits next to >= 3 windows
+    p.resident = !no_resident && p.n_phases > 1 && pairs >= 2 * (int64_t)(grid / 2) &&
+                 epi_bytes + (size_t)max_phase_tiles * F_BHALF + 3 * a_bytes <= limit;
+    p.b_tiles = p.resident ? max_phase_tiles : F_BSTAGES;
+    const size_t rest = epi_bytes + (size_t)p.b_tiles * F_BHALF;
+    if (rest + 2 * a_bytes > limit) return fail(NBE_EUNSUPPORTED, "conv_flat: window of %d rows does not fit in shared memory", win_rows);
+    p.n_abuf = (int)std::min<size_t>(F_MAX_ABUF, (limit - rest) / a_bytes);
+    p.smem_need = (uint32_t)(rest + (size_t)p.n_abuf * a_bytes);
+    // the kernel aligns its base to 1 KiB; dynamic shared memory normally starts aligned, so the slack is only added when it fits
+    const size_t smem = std::min(limit, (size_t)p.smem_need + 1024);
     if (raw) conv_tc_flat_kernel<0><<<grid, F_THREADS, smem, stream>>>(ta, tb, p);
     else     conv_tc_flat_kernel<1><<<grid, F_THREADS, smem, stream>>>(ta, tb, p);
     return launched("conv_tc_flat_kernel");
@@ -377,7 +461,7 @@ extern "C" int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
     NBE_REQUIRE(y_row_pitch >= OW && y_img_pitch >= y_row_pitch * OH, "conv3x3_flat: bad output pitches");
     if (N == 0) return NBE_OK;
     FlatParams p;
-    p.y = (__nv_bfloat16*)y; p.N = N; p.P = x_pitch; p.positions = OH * x_pitch; p.T = 2; p.nbuf = 2;
+    p.y = (__nv_bfloat16*)y; p.N = N; p.P = x_pitch; p.positions = OH * x_pitch; p.T = 2;
     p.ntaps = 9;
     const int off = valid ? 0 : -1;
     for (int kh = 0; kh < 3; ++kh)
@@ -405,7 +489,7 @@ extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_o
     NBE_REQUIRE(t_row_pitch >= 2 * W + 1 && t_img_pitch >= t_row_pitch * (2 * H + 1), "convT3x3s2_flat: bad output pitches");
     if (N == 0) return NBE_OK;
     FlatParams p;
-    p.y = (__nv_bfloat16*)t_out; p.N = N; p.P = x_pitch; p.positions = (H + 1) * x_pitch; p.T = 1; p.nbuf = 2;
+    p.y = (__nv_bfloat16*)t_out; p.N = N; p.P = x_pitch; p.positions = (H + 1) * x_pitch; p.T = 1;
     // T[2Y+kh, 2X+kw] += W[kh,kw] x[Y,X]  (F.conv_transpose2d, SG2/torch_utils/ops/conv2d_resample.py:124-138):
     // class (py,px) at grid (Y',X') sums the taps with kh = py, kw = px (mod 2) over x[Y' - (kh-py)/2, X' - (kw-px)/2].
     // Two phases of two classes each -- {(0,0): 4 taps, (1,1): 1 tap} and {(0,1): 2 taps, (1,0): 2 taps} -- so that a

@@ -75,4 +75,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
               const cuuint32_t* box, const char* what, int spatial_stride = 1, int swizzle128 = 1);
 
+
+// ---- CTA-pair (cta_group::2) variants -------------------------------------------------------------------
+// Two CTAs of a cluster (same TPC) run ONE M=256 MMA: each holds its own 128 rows of A and HALF of B (N/2 rows) in its
+// shared memory and receives its 128 accumulator rows in its own TMEM.  Only the even-ranked ("leader") CTA issues MMAs
+// and waits for operands, so TMA loads of both CTAs complete on the LEADER's barrier, while tcgen05.commit multicasts the
+// "operands consumed" / "accumulator ready" arrivals to the barrier at the same offset in both CTAs.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                       // shared::cluster address -> same offset in the even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {      // arrives on [bar] in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the leader CTA's barrier at this offset
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar & kPeerBitMask) : "memory");
+}
+
 }  // namespace nbe
