@@ -60,29 +60,6 @@ struct FlatParams {
     uint32_t idesc;
 };
 
-// mbarrier wait whose common case (already complete) is one instruction; the bounded slow path is in mbar_wait
-__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done) mbar_wait(bar, parity);
-}
-// MMA of the pair with descriptors given as (low word, shared high word): K-major SW128 operands differ only in bits 0..13
-// The whole MMA warp runs the issue loop with warp-uniform operands and only the instructions themselves sit behind
-// elect.sync: issued from inside a divergent `if (lane == 0)` region, ptxas cannot keep the descriptors in uniform
-// registers and wraps every tcgen05.mma in an elect / R2UR "waterfall" loop of ~15 instructions.
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
-                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
-
 template <int EPI>   // 0: accumulators are stored as they are (bf16); 1: full SynthesisLayer epilogue
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const FlatParams p) {
@@ -109,9 +86,9 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* res_free = res_full + 1;                  // all MMAs of the phase have drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_free + 1);
 
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform for the compiler
+    const int warp = (int)uniform_u32(threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const int rank = __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0);
+    const int rank = (int)uniform_u32(cluster_ctarank());
     const bool leader = rank == 0;
     if (threadIdx.x == 0) {
         for (int i = 0; i < F_MAX_ABUF; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
@@ -129,7 +106,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tcgen05_fence_before();
     cluster_sync_all();                                             // barriers of BOTH CTAs are initialised before any remote arrive
     tcgen05_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler (UTCHMMA takes uniform registers)
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
     const int set_cols = p.T * p.Gmax * 128;                        // TMEM columns of one accumulator set
     // schedule of this pair: n_local item pairs x n_phases, item-major (streamed weights) or phase-major (resident weights);
     // CTA r takes item 2j + r (the last pair may hold a dummy)
@@ -185,10 +162,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ============================== MMA issuer (leader CTA only; whole warp, elected lane issues) ==============================
         if (leader) {
-            // descriptor words: low = start address >> 4 | LBO, high = SBO (1024 B) | version 1 | SWIZZLE_128B
-            const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-            const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFF) >> 4) | (1u << 16);
-            const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a)), b_lo0 = umma_desc_lo(smem_u32(smem_b));
             const uint32_t a_step = (uint32_t)a_bytes >> 4;
             const uint32_t idesc = p.idesc;
             const int T = p.T, k_chunks = p.k_chunks, n_abuf = p.n_abuf;
@@ -209,9 +183,9 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int t = 0; t < F_MAX_TAPS; ++t)
                         if (t < ntp) {
-                            op_a[t] = __shfl_sync(0xffffffffu, (uint32_t)((p.tap_shift[t0 + t] - p.min_shift) * 8), 0);
-                            op_d[t] = __shfl_sync(0xffffffffu, (uint32_t)(p.tap_acc[t0 + t] * 128), 0);
-                            op_first[t] = __shfl_sync(0xffffffffu, (uint32_t)p.tap_first[t0 + t], 0);
+                            op_a[t] = uniform_u32((uint32_t)((p.tap_shift[t0 + t] - p.min_shift) * 8));
+                            op_d[t] = uniform_u32((uint32_t)(p.tap_acc[t0 + t] * 128));
+                            op_first[t] = uniform_u32((uint32_t)p.tap_first[t0 + t]);
                         }
                 }
                 const int ab = s & 1;
@@ -244,10 +218,10 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                         // position tile i, tap t: rows [i*128 + shift - min_shift, +128) of the window
                                         const uint32_t al = a_lo + op_a[t] + (uint32_t)(i * 1024);
                                         const uint32_t d = d0 + op_d[t] + (uint32_t)i * d_tile;
-                                        umma_pair(d, al, b_lo, desc_hi, idesc, acc0);
-                                        umma_pair(d, al + 2, b_lo + 2, desc_hi, idesc, 1u);
-                                        umma_pair(d, al + 4, b_lo + 4, desc_hi, idesc, 1u);
-                                        umma_pair(d, al + 6, b_lo + 6, desc_hi, idesc, 1u);
+                                        umma_bf16_lo_2sm(d, al, b_lo, idesc, acc0);
+                                        umma_bf16_lo_2sm(d, al + 2, b_lo + 2, idesc, 1u);
+                                        umma_bf16_lo_2sm(d, al + 4, b_lo + 4, idesc, 1u);
+                                        umma_bf16_lo_2sm(d, al + 6, b_lo + 6, idesc, 1u);
                                     }
                                 }
                                 if (!resident) umma_commit_2sm(smem_u32(&b_empty[bs]));

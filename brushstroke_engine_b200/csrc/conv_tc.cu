@@ -51,7 +51,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full ; then the TMEM base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
 
     // tile -> (n0, y0, x0)
     int tile = blockIdx.x;
@@ -74,7 +74,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -92,21 +92,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer ==============================
-        if (lane == 0) {
+        // ============================== MMA issuer (whole warp, elected lane issues: see tc_common.cuh) ==============================
+        {
+            const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a)), b_lo0 = umma_desc_lo(smem_u32(smem_b));
+            const uint32_t b_step = (uint32_t)b_bytes >> 4, idesc = p.idesc;
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(smem_u32(&bars[stage]), phase);
+                mbar_wait_fast(smem_u32(&bars[stage]), phase);
                 tcgen05_fence_after();
-                const uint64_t a_desc = umma_smem_desc(smem_u32(smem_a + stage * TC_A_BYTES));
-                const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b + stage * b_bytes));
+                if (elect_one()) {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)stage * (TC_A_BYTES >> 4), b_lo = b_lo0 + (uint32_t)stage * b_step;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)                         // 4 x (K = 16) per 64-channel block: +32 B inside the swizzle atom
-                    umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
-                umma_commit(smem_u32(&bars[TC_STAGES + stage]));    // frees the smem stage when these MMAs retire
+                    for (int k = 0; k < 4; ++k)                     // 4 x (K = 16) per 64-channel block: +32 B inside the swizzle atom
+                        umma_bf16_lo(tmem_base, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(smem_u32(&bars[TC_STAGES + stage]));    // frees the smem stage when these MMAs retire
+                }
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(smem_u32(&bars[2 * TC_STAGES]));            // accumulator complete
+            if (elect_one()) umma_commit(smem_u32(&bars[2 * TC_STAGES]));            // accumulator complete
         }
     } else {
         // ============================== epilogue (warps 2..5) ==============================
@@ -210,7 +213,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint64_t* acc_empty = acc_full + 2;                 // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1);
                                       mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
@@ -226,7 +229,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -256,41 +259,47 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer ==============================
-        if (lane == 0) {
-            uint32_t a_phase[2] = {0, 0}, acc_phase[2] = {0, 0};
+        // ============================== MMA issuer (whole warp, elected lane issues: see tc_common.cuh) ==============================
+        {
+            const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a)), b_lo0 = umma_desc_lo(smem_u32(smem_b));
+            const uint32_t idesc = p.idesc;
+            uint32_t a_par = 0, acc_par0 = 0, acc_par1 = 0;
             int bs = 0; uint32_t b_phase = 0;
             int it = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
                 const int ab = it & 1;
-                mbar_wait(smem_u32(&acc_empty[ab]), acc_phase[ab] ^ 1);       // epilogue has drained this accumulator pair
+                // the epilogue has drained this accumulator pair
+                if (ab) { mbar_wait_fast(smem_u32(&acc_empty[1]), acc_par1 ^ 1); acc_par1 ^= 1; }
+                else    { mbar_wait_fast(smem_u32(&acc_empty[0]), acc_par0 ^ 1); acc_par0 ^= 1; }
                 tcgen05_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(ab * 256);
+#pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    mbar_wait(smem_u32(&a_full[c]), a_phase[c]);
+                    mbar_wait_fast(smem_u32(&a_full[c]), a_par);
                     tcgen05_fence_after();
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int kh = tap / 3, kw = tap - kh * 3;
-                        mbar_wait(smem_u32(&b_full[bs]), b_phase);
+                        mbar_wait_fast(smem_u32(&b_full[bs]), b_phase);
                         tcgen05_fence_after();
-                        const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b + bs * R_BBYTES));
+                        if (elect_one()) {
+                            const uint32_t b_lo = b_lo0 + (uint32_t)bs * (R_BBYTES >> 4);
 #pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            // output row r takes input row r + kh; the horizontal tap is a kw-pixel (kw * 128 B) shift of the start address
-                            const uint64_t a_desc = umma_smem_desc(smem_u32(smem_a + (c * 4 + r + kh) * R_ABUF) + (uint32_t)(kw * 128));
+                            for (int r = 0; r < 2; ++r) {
+                                // output row r takes input row r + kh; the horizontal tap is a kw-pixel (kw * 128 B) shift of the start address
+                                const uint32_t a_lo = a_lo0 + (uint32_t)(((c * 4 + r + kh) * R_ABUF + kw * 128) >> 4);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16(d0 + (uint32_t)(r * 128), a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc,
-                                          (c | tap | k) != 0);
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16_lo(d0 + (uint32_t)(r * 128), a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (c | tap | k) != 0);
+                            }
+                            umma_commit(smem_u32(&b_empty[bs]));
                         }
-                        umma_commit(smem_u32(&b_empty[bs]));
                         if (++bs == R_BSTAGES) { bs = 0; b_phase ^= 1; }
                     }
-                    umma_commit(smem_u32(&a_empty[c]));             // the four input rows of this chunk may be overwritten
-                    a_phase[c] ^= 1;
+                    if (elect_one()) umma_commit(smem_u32(&a_empty[c]));             // the four input rows of this chunk may be overwritten
                 }
-                umma_commit(smem_u32(&acc_full[ab]));
-                acc_phase[ab] ^= 1;
+                a_par ^= 1;
+                if (elect_one()) umma_commit(smem_u32(&acc_full[ab]));
             }
         }
     } else {

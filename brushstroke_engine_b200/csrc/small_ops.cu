@@ -427,37 +427,64 @@ struct StylesTable {
     int post_from[SD_MAX_LAYERS];
 };
 
-// grid = (N, n_layers); block = 128 threads.  styles = affine(w) (FullyConnectedLayer, lr 1, bias_init 1: networks.py:109-122),
-// d[o] = rsqrt(sum_i styles[i]^2 wsq[o,i] + 1e-8) (networks.py:59-64).
+// grid = (ceil(N / SD_NB), n_layers); block = 128 threads.  styles = affine(w) (FullyConnectedLayer, lr 1, bias_init 1:
+// networks.py:109-122), d[o] = rsqrt(sum_i styles[i]^2 wsq[o,i] + 1e-8) (networks.py:59-64).  A block handles SD_NB samples
+// so that every affine / wsq weight it loads feeds SD_NB FMAs (the weights are re-read by every block: L2-bound otherwise).
+constexpr int SD_NB = 8;
+
 __global__ void __launch_bounds__(128)
-styles_demod_kernel(const float* __restrict__ ws, int num_ws, int w_dim, const StylesTable tab) {
-    extern __shared__ float s_sd[];                                 // [w_dim] latent, then [cin] styles^2
-    const int n = blockIdx.x, l = blockIdx.y;
+styles_demod_kernel(const float* __restrict__ ws, int N, int num_ws, int w_dim, const StylesTable tab) {
+    extern __shared__ float s_sd[];                                 // [SD_NB][w_dim] latents, then [SD_NB][cin] styles^2
+    const int n0 = blockIdx.x * SD_NB, l = blockIdx.y;
     const int cin = tab.cin[l], cout = tab.cout[l];
     float* s_w = s_sd;
-    float* s_s2 = s_sd + w_dim;
-    for (int i = threadIdx.x; i < w_dim; i += 128) s_w[i] = ws[((long long)n * num_ws + tab.w_index[l]) * w_dim + i];
+    float* s_s2 = s_sd + SD_NB * w_dim;
+    for (int i = threadIdx.x; i < SD_NB * w_dim; i += 128) {
+        const int nb = i / w_dim, k = i - nb * w_dim;
+        const int n = min(n0 + nb, N - 1);                          // tail block: duplicates, never stored
+        s_w[i] = ws[((long long)n * num_ws + tab.w_index[l]) * w_dim + k];
+    }
     __syncthreads();
     const float wgain = rsqrtf((float)w_dim);
     for (int c = threadIdx.x; c < cin; c += 128) {
         const float* wr = tab.affine_w[l] + (long long)c * w_dim;
-        float acc = 0.f;
-        for (int i = 0; i < w_dim; ++i) acc = fmaf(s_w[i], wr[i] * wgain, acc);
-        acc += tab.affine_b[l][c];
-        s_s2[c] = acc * acc;
-        if (c >= tab.post_from[l]) acc *= tab.post_scale[l];
-        tab.styles[l][(long long)n * cin + c] = acc;
+        float acc[SD_NB];
+#pragma unroll
+        for (int nb = 0; nb < SD_NB; ++nb) acc[nb] = 0.f;
+        for (int i = 0; i < w_dim; ++i) {
+            const float w = wr[i] * wgain;
+#pragma unroll
+            for (int nb = 0; nb < SD_NB; ++nb) acc[nb] = fmaf(s_w[nb * w_dim + i], w, acc[nb]);
+        }
+        const float bias = tab.affine_b[l][c];
+        const float post = (c >= tab.post_from[l]) ? tab.post_scale[l] : 1.f;
+#pragma unroll
+        for (int nb = 0; nb < SD_NB; ++nb) {
+            const float a = acc[nb] + bias;
+            s_s2[nb * cin + c] = a * a;
+            if (n0 + nb < N) tab.styles[l][(long long)(n0 + nb) * cin + c] = (c >= tab.post_from[l]) ? a * post : a;
+        }
     }
     __syncthreads();
     if (tab.wsq[l] == nullptr || tab.dcoef[l] == nullptr) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int o = warp; o < cout; o += 4) {
         const float* q = tab.wsq[l] + (long long)o * cin;
-        float s = 0.f;
-        for (int i = lane; i < cin; i += 32) s = fmaf(s_s2[i], q[i], s);
+        float sm[SD_NB];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) tab.dcoef[l][(long long)n * cout + o] = rsqrtf(s + 1e-8f);
+        for (int nb = 0; nb < SD_NB; ++nb) sm[nb] = 0.f;
+        for (int i = lane; i < cin; i += 32) {
+            const float qv = q[i];
+#pragma unroll
+            for (int nb = 0; nb < SD_NB; ++nb) sm[nb] = fmaf(s_s2[nb * cin + i], qv, sm[nb]);
+        }
+#pragma unroll
+        for (int nb = 0; nb < SD_NB; ++nb) {
+            float v = sm[nb];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0 && n0 + nb < N) tab.dcoef[l][(long long)(n0 + nb) * cout + o] = rsqrtf(v + 1e-8f);
+        }
     }
 }
 
@@ -468,36 +495,46 @@ struct NoiseTable {
     const float* lin[SN_MAX_LAYERS];
     float* out[SN_MAX_LAYERS];                // [N, R, R]
     int res[SN_MAX_LAYERS];
-    long long start[SN_MAX_LAYERS + 1];       // prefix sums of N * R * R
+    long long start[SN_MAX_LAYERS + 1];       // prefix sums of N * chunks(layer): first block of each layer
 };
+
+// One block = up to SN_CHUNK elements of ONE (layer, sample): the sample's wrapped position (two 64-bit modulos, two IEEE
+// divisions) is computed once per thread instead of once per element.  The float expression order is the one of
+// nbe_shifted_noise_f32 / the oracle (grid_sample restated), so results are bit-identical to the per-layer kernel.
+constexpr int SN_CHUNK = 2048;
 
 __global__ void __launch_bounds__(256)
 shifted_noise_all_kernel(const int64_t* __restrict__ positions, int N, int mod, const NoiseTable tab) {
-    const long long total = tab.start[tab.n_layers];
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-        int l = 0;
-        while (g >= tab.start[l + 1]) ++l;
-        const int R = tab.res[l];
-        const int idx = (int)(g - tab.start[l]);
-        const int j = idx % R, i = (idx / R) % R, n = idx / (R * R);
-        const float* nc = tab.noise_const[l];
-        const float* lin = tab.lin[l];
-        int64_t py = positions[2 * n] % mod, px = positions[2 * n + 1] % mod;
-        if (py < 0) py += mod;
-        if (px < 0) px += mod;
-        const float p0 = __fdiv_rn((float)py, (float)(mod - 1));
-        const float p1 = __fdiv_rn((float)px, (float)(mod - 1));
+    // block -> (layer, sample, chunk): tab.start[] holds prefix sums of N * chunks(layer)
+    int l = 0;
+    while ((long long)blockIdx.x >= tab.start[l + 1]) ++l;
+    const int R = tab.res[l];
+    const int chunks = (R * R + SN_CHUNK - 1) / SN_CHUNK;
+    const int b = (int)(blockIdx.x - tab.start[l]);
+    const int n = b / chunks, e0 = (b - n * chunks) * SN_CHUNK;
+    const float* __restrict__ nc = tab.noise_const[l];
+    const float* __restrict__ lin = tab.lin[l];
+    int64_t py = positions[2 * n] % mod, px = positions[2 * n + 1] % mod;
+    if (py < 0) py += mod;
+    if (px < 0) px += mod;
+    const float p0 = __fdiv_rn((float)py, (float)(mod - 1));
+    const float p1 = __fdiv_rn((float)px, (float)(mod - 1));
+    const float rm1 = (float)(R - 1);
+    float* out = tab.out[l] + (long long)n * R * R;
+    const int e1 = min(e0 + SN_CHUNK, R * R);
+    for (int idx = e0 + threadIdx.x; idx < e1; idx += 256) {
+        const int i = idx / R, j = idx - i * R;
         float sx = __fadd_rn(lin[i], p0); sx = __fsub_rn(sx, floorf(sx));
         float sy = __fadd_rn(lin[j], p1); sy = __fsub_rn(sy, floorf(sy));
         const float gx = __fsub_rn(__fmul_rn(sx, 2.f), 1.f), gy = __fsub_rn(__fmul_rn(sy, 2.f), 1.f);
-        const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(R - 1));
-        const float cy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(R - 1));
+        const float cx = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), rm1);     // x / 2 == x * 0.5 exactly
+        const float cy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), rm1);
         const float fx0 = floorf(cx), fy0 = floorf(cy);
         const float tx = cx - fx0, ty = cy - fy0;
         const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
-        auto at = [&](int yy, int xx) -> float { return (yy >= 0 && yy < R && xx >= 0 && xx < R) ? nc[yy * R + xx] : 0.f; };
-        tab.out[l][idx] = at(y0, x0) * (1.f - tx) * (1.f - ty) + at(y0, x1) * tx * (1.f - ty) +
-                          at(y1, x0) * (1.f - tx) * ty + at(y1, x1) * tx * ty;
+        auto at = [&](int yy, int xx) -> float { return (yy >= 0 && yy < R && xx >= 0 && xx < R) ? __ldg(nc + yy * R + xx) : 0.f; };
+        out[idx] = at(y0, x0) * (1.f - tx) * (1.f - ty) + at(y0, x1) * tx * (1.f - ty) +
+                   at(y1, x0) * (1.f - tx) * ty + at(y1, x1) * tx * ty;
     }
 }
 
@@ -521,10 +558,10 @@ extern "C" int nbe_styles_demod_f32(const float* ws, int N, int num_ws, int w_di
         tab.w_index[l] = w_index[l]; tab.post_scale[l] = post_scale[l]; tab.post_from[l] = post_from[l];
         if (cin[l] > max_cin) max_cin = cin[l];
     }
-    dim3 grid(N, n_layers);
-    const size_t smem = (size_t)(w_dim + max_cin) * sizeof(float);
+    dim3 grid((N + SD_NB - 1) / SD_NB, n_layers);
+    const size_t smem = (size_t)SD_NB * (w_dim + max_cin) * sizeof(float);
     NBE_REQUIRE(smem <= 48 * 1024, "styles_demod: layer too wide");
-    styles_demod_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(ws, num_ws, w_dim, tab);
+    styles_demod_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(ws, N, num_ws, w_dim, tab);
     return launched("styles_demod_kernel");
 }
 
@@ -540,10 +577,9 @@ extern "C" int nbe_shifted_noise_all_f32(const int64_t* positions, int N, int mo
         NBE_REQUIRE(noise_const[l] && lin[l] && out[l] && res[l] >= 2, "shifted_noise_all: bad layer %d", l);
         tab.noise_const[l] = (const float*)noise_const[l]; tab.lin[l] = (const float*)lin[l]; tab.out[l] = (float*)out[l]; tab.res[l] = res[l];
         NBE_REQUIRE((long long)N * res[l] * res[l] <= INT32_MAX, "shifted_noise_all: layer %d too large", l);
-        tab.start[l + 1] = tab.start[l] + (long long)N * res[l] * res[l];
+        tab.start[l + 1] = tab.start[l] + (long long)N * ((res[l] * res[l] + SN_CHUNK - 1) / SN_CHUNK);
     }
-    long long blocks = (tab.start[n_layers] + 255) / 256;
-    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-    shifted_noise_all_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(positions, N, mod, tab);
+    NBE_REQUIRE(tab.start[n_layers] <= INT32_MAX, "shifted_noise_all: too many blocks");
+    shifted_noise_all_kernel<<<(int)tab.start[n_layers], 256, 0, (cudaStream_t)stream>>>(positions, N, mod, tab);
     return launched("shifted_noise_all_kernel");
 }

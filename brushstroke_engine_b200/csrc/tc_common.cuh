@@ -76,6 +76,42 @@ int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* di
               const cuuint32_t* box, const char* what, int spatial_stride = 1, int swizzle128 = 1);
 
 
+// ---- lean single-warp MMA issue ----------------------------------------------------------------------------
+// tcgen05.mma / commit take their operands from UNIFORM registers.  Issued from inside a divergent `if (lane == 0)`
+// region, ptxas computes the descriptors in vector registers and wraps every instruction in an elect / R2UR "waterfall"
+// loop of ~15 instructions -- enough to make the single issuing thread the bottleneck of a kernel.  The MMA warp therefore
+// runs its loop warp-uniformly (warp index, TMEM base, ... passed through uniform_u32) and only the issue sits behind
+// elect.sync.
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// mbarrier wait whose common case (already complete) is one instruction; the bounded slow path is in mbar_wait
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) mbar_wait(bar, parity);
+}
+// K-major SWIZZLE_128B descriptors differ only in their low word: start address >> 4 | LBO(1) << 16; the high word is
+// SBO (1024 B >> 4) | version 1 << 14 | layout SWIZZLE_128B (2) << 29
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHiSw128), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lo_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHiSw128), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // ---- CTA-pair (cta_group::2) variants -------------------------------------------------------------------
 // Two CTAs of a cluster (same TPC) run ONE M=256 MMA: each holds its own 128 rows of A and HALF of B (N/2 rows) in its
 // shared memory and receives its 128 accumulator rows in its own TMEM.  Only the even-ranked ("leader") CTA issues MMAs
