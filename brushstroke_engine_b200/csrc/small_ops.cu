@@ -427,34 +427,47 @@ struct StylesTable {
     int post_from[SD_MAX_LAYERS];
 };
 
-// grid = (ceil(N / SD_NB), n_layers); block = 128 threads.  styles = affine(w) (FullyConnectedLayer, lr 1, bias_init 1:
+// grid = (ceil(N / SD_NB), n_layers); block = SD_THREADS threads.  styles = affine(w) (FullyConnectedLayer, lr 1, bias_init 1:
 // networks.py:109-122), d[o] = rsqrt(sum_i styles[i]^2 wsq[o,i] + 1e-8) (networks.py:59-64).  A block handles SD_NB samples
 // so that every affine / wsq weight it loads feeds SD_NB FMAs (the weights are re-read by every block: L2-bound otherwise).
 constexpr int SD_NB = 8;
+constexpr int SD_THREADS = 256;
+static_assert(SD_NB == 8, "the affine inner loop is written for 8 samples");
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SD_THREADS)
 styles_demod_kernel(const float* __restrict__ ws, int N, int num_ws, int w_dim, const StylesTable tab) {
-    extern __shared__ float s_sd[];                                 // [SD_NB][w_dim] latents, then [SD_NB][cin] styles^2
+    extern __shared__ __align__(16) float s_sd[];                              // [SD_NB][w_dim] latents, then [SD_NB][cin] styles^2
     const int n0 = blockIdx.x * SD_NB, l = blockIdx.y;
     const int cin = tab.cin[l], cout = tab.cout[l];
     float* s_w = s_sd;
     float* s_s2 = s_sd + SD_NB * w_dim;
-    for (int i = threadIdx.x; i < SD_NB * w_dim; i += 128) {
+    // latents transposed to [w_dim][SD_NB]: the SD_NB values that meet one weight are two 16-byte broadcast loads
+    for (int i = threadIdx.x; i < SD_NB * w_dim; i += SD_THREADS) {
         const int nb = i / w_dim, k = i - nb * w_dim;
         const int n = min(n0 + nb, N - 1);                          // tail block: duplicates, never stored
-        s_w[i] = ws[((long long)n * num_ws + tab.w_index[l]) * w_dim + k];
+        s_w[k * SD_NB + nb] = ws[((long long)n * num_ws + tab.w_index[l]) * w_dim + k];
     }
     __syncthreads();
     const float wgain = rsqrtf((float)w_dim);
-    for (int c = threadIdx.x; c < cin; c += 128) {
+    for (int c = threadIdx.x; c < cin; c += SD_THREADS) {
         const float* wr = tab.affine_w[l] + (long long)c * w_dim;
         float acc[SD_NB];
 #pragma unroll
         for (int nb = 0; nb < SD_NB; ++nb) acc[nb] = 0.f;
-        for (int i = 0; i < w_dim; ++i) {
-            const float w = wr[i] * wgain;
-#pragma unroll
-            for (int nb = 0; nb < SD_NB; ++nb) acc[nb] = fmaf(s_w[nb * w_dim + i], w, acc[nb]);
+        auto step = [&](int i, float wv) {
+            const float w = wv * wgain;
+            const float4 a = *reinterpret_cast<const float4*>(s_w + i * SD_NB);
+            const float4 b = *reinterpret_cast<const float4*>(s_w + i * SD_NB + 4);
+            acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+            acc[4] = fmaf(b.x, w, acc[4]); acc[5] = fmaf(b.y, w, acc[5]); acc[6] = fmaf(b.z, w, acc[6]); acc[7] = fmaf(b.w, w, acc[7]);
+        };
+        if ((w_dim & 3) == 0 && (((uintptr_t)wr) & 15) == 0) {
+            for (int i = 0; i < w_dim; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wr + i);
+                step(i, w4.x); step(i + 1, w4.y); step(i + 2, w4.z); step(i + 3, w4.w);
+            }
+        } else {
+            for (int i = 0; i < w_dim; ++i) step(i, wr[i]);
         }
         const float bias = tab.affine_b[l][c];
         const float post = (c >= tab.post_from[l]) ? tab.post_scale[l] : 1.f;
@@ -468,7 +481,7 @@ styles_demod_kernel(const float* __restrict__ ws, int N, int num_ws, int w_dim, 
     __syncthreads();
     if (tab.wsq[l] == nullptr || tab.dcoef[l] == nullptr) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int o = warp; o < cout; o += 4) {
+    for (int o = warp; o < cout; o += SD_THREADS / 32) {
         const float* q = tab.wsq[l] + (long long)o * cin;
         float sm[SD_NB];
 #pragma unroll
@@ -495,46 +508,72 @@ struct NoiseTable {
     const float* lin[SN_MAX_LAYERS];
     float* out[SN_MAX_LAYERS];                // [N, R, R]
     int res[SN_MAX_LAYERS];
-    long long start[SN_MAX_LAYERS + 1];       // prefix sums of N * chunks(layer): first block of each layer
+    long long start[SN_MAX_LAYERS + 1];       // prefix sums of N * tiles(layer): first block of each layer
 };
 
-// One block = up to SN_CHUNK elements of ONE (layer, sample): the sample's wrapped position (two 64-bit modulos, two IEEE
-// divisions) is computed once per thread instead of once per element.  The float expression order is the one of
-// nbe_shifted_noise_f32 / the oracle (grid_sample restated), so results are bit-identical to the per-layer kernel.
-constexpr int SN_CHUNK = 2048;
+// One block = one 32 x 32 output tile of ONE (layer, sample).  The reference's sampling grid is TRANSPOSED (output row i
+// selects the source COLUMN, output column j the source ROW), so a thread-per-output-column mapping reads the noise constant
+// down its columns (32 cache lines per load).  Here lanes run along the output ROW index i -- the four taps are then
+// (nearly) contiguous reads -- and the tile is transposed through shared memory so that the stores are contiguous too.
+// The separable part of the grid (source index + weight per output row / column; two 64-bit modulos and two IEEE divisions
+// per sample) is computed once per block by 64 threads.  The float expression order is the one of nbe_shifted_noise_f32 /
+// the oracle (grid_sample restated), so results are bit-identical to the per-layer kernel.
+constexpr int SN_TILE = 32;
 
 __global__ void __launch_bounds__(256)
 shifted_noise_all_kernel(const int64_t* __restrict__ positions, int N, int mod, const NoiseTable tab) {
-    // block -> (layer, sample, chunk): tab.start[] holds prefix sums of N * chunks(layer)
+    __shared__ int s_i0[2][SN_TILE];                                // [0]: x0 of output row i0 + k, [1]: y0 of output column j0 + k
+    __shared__ float s_t[2][SN_TILE];                               // the matching fractional weights
+    __shared__ float s_tile[SN_TILE][SN_TILE + 1];                  // [i][j]
+    // block -> (layer, sample, tile): tab.start[] holds prefix sums of N * tiles(layer)
     int l = 0;
     while ((long long)blockIdx.x >= tab.start[l + 1]) ++l;
     const int R = tab.res[l];
-    const int chunks = (R * R + SN_CHUNK - 1) / SN_CHUNK;
+    const int tpr = (R + SN_TILE - 1) / SN_TILE;
     const int b = (int)(blockIdx.x - tab.start[l]);
-    const int n = b / chunks, e0 = (b - n * chunks) * SN_CHUNK;
+    const int n = b / (tpr * tpr), t2 = b - n * tpr * tpr;
+    const int i0 = (t2 / tpr) * SN_TILE, j0 = (t2 % tpr) * SN_TILE;
     const float* __restrict__ nc = tab.noise_const[l];
-    const float* __restrict__ lin = tab.lin[l];
-    int64_t py = positions[2 * n] % mod, px = positions[2 * n + 1] % mod;
-    if (py < 0) py += mod;
-    if (px < 0) px += mod;
-    const float p0 = __fdiv_rn((float)py, (float)(mod - 1));
-    const float p1 = __fdiv_rn((float)px, (float)(mod - 1));
-    const float rm1 = (float)(R - 1);
+    if (threadIdx.x < 2 * SN_TILE) {
+        const int which = threadIdx.x >= SN_TILE, kk = threadIdx.x & (SN_TILE - 1);
+        const int k = (which ? j0 : i0) + kk;
+        if (k < R) {
+            int64_t pp = positions[2 * n + which] % mod;
+            if (pp < 0) pp += mod;
+            const float pf = __fdiv_rn((float)pp, (float)(mod - 1));
+            float sv = __fadd_rn(tab.lin[l][k], pf); sv = __fsub_rn(sv, floorf(sv));
+            const float g = __fsub_rn(__fmul_rn(sv, 2.f), 1.f);
+            const float c = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), (float)(R - 1));   // x / 2 == x * 0.5 exactly
+            const float f0 = floorf(c);
+            s_i0[which][kk] = (int)f0;
+            s_t[which][kk] = c - f0;
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (i0 + lane < R) {
+        const int x0 = s_i0[0][lane], x1 = x0 + 1;
+        const float tx = s_t[0][lane];
+#pragma unroll
+        for (int q = 0; q < SN_TILE / 8; ++q) {
+            const int jj = warp + q * 8;
+            if (j0 + jj < R) {
+                const int y0 = s_i0[1][jj], y1 = y0 + 1;
+                const float ty = s_t[1][jj];
+                auto at = [&](int yy, int xx) -> float { return (yy >= 0 && yy < R && xx >= 0 && xx < R) ? __ldg(nc + yy * R + xx) : 0.f; };
+                s_tile[lane][jj] = at(y0, x0) * (1.f - tx) * (1.f - ty) + at(y0, x1) * tx * (1.f - ty) +
+                                   at(y1, x0) * (1.f - tx) * ty + at(y1, x1) * tx * ty;
+            }
+        }
+    }
+    __syncthreads();
     float* out = tab.out[l] + (long long)n * R * R;
-    const int e1 = min(e0 + SN_CHUNK, R * R);
-    for (int idx = e0 + threadIdx.x; idx < e1; idx += 256) {
-        const int i = idx / R, j = idx - i * R;
-        float sx = __fadd_rn(lin[i], p0); sx = __fsub_rn(sx, floorf(sx));
-        float sy = __fadd_rn(lin[j], p1); sy = __fsub_rn(sy, floorf(sy));
-        const float gx = __fsub_rn(__fmul_rn(sx, 2.f), 1.f), gy = __fsub_rn(__fmul_rn(sy, 2.f), 1.f);
-        const float cx = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), rm1);     // x / 2 == x * 0.5 exactly
-        const float cy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), rm1);
-        const float fx0 = floorf(cx), fy0 = floorf(cy);
-        const float tx = cx - fx0, ty = cy - fy0;
-        const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
-        auto at = [&](int yy, int xx) -> float { return (yy >= 0 && yy < R && xx >= 0 && xx < R) ? __ldg(nc + yy * R + xx) : 0.f; };
-        out[idx] = at(y0, x0) * (1.f - tx) * (1.f - ty) + at(y0, x1) * tx * (1.f - ty) +
-                   at(y1, x0) * (1.f - tx) * ty + at(y1, x1) * tx * ty;
+    if (j0 + lane < R) {
+#pragma unroll
+        for (int q = 0; q < SN_TILE / 8; ++q) {
+            const int ii = warp + q * 8;
+            if (i0 + ii < R) out[(i0 + ii) * R + j0 + lane] = s_tile[ii][lane];
+        }
     }
 }
 
@@ -561,7 +600,7 @@ extern "C" int nbe_styles_demod_f32(const float* ws, int N, int num_ws, int w_di
     dim3 grid((N + SD_NB - 1) / SD_NB, n_layers);
     const size_t smem = (size_t)SD_NB * (w_dim + max_cin) * sizeof(float);
     NBE_REQUIRE(smem <= 48 * 1024, "styles_demod: layer too wide");
-    styles_demod_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(ws, N, num_ws, w_dim, tab);
+    styles_demod_kernel<<<grid, SD_THREADS, smem, (cudaStream_t)stream>>>(ws, N, num_ws, w_dim, tab);
     return launched("styles_demod_kernel");
 }
 
@@ -574,10 +613,10 @@ extern "C" int nbe_shifted_noise_all_f32(const int64_t* positions, int N, int mo
     tab.n_layers = n_layers;
     tab.start[0] = 0;
     for (int l = 0; l < n_layers; ++l) {
-        NBE_REQUIRE(noise_const[l] && lin[l] && out[l] && res[l] >= 2, "shifted_noise_all: bad layer %d", l);
+        NBE_REQUIRE(noise_const[l] && lin[l] && out[l] && res[l] >= 2 , "shifted_noise_all: bad layer %d", l);
         tab.noise_const[l] = (const float*)noise_const[l]; tab.lin[l] = (const float*)lin[l]; tab.out[l] = (float*)out[l]; tab.res[l] = res[l];
         NBE_REQUIRE((long long)N * res[l] * res[l] <= INT32_MAX, "shifted_noise_all: layer %d too large", l);
-        tab.start[l + 1] = tab.start[l] + (long long)N * ((res[l] * res[l] + SN_CHUNK - 1) / SN_CHUNK);
+        { const long long tpr = (res[l] + SN_TILE - 1) / SN_TILE; tab.start[l + 1] = tab.start[l] + (long long)N * tpr * tpr; }
     }
     NBE_REQUIRE(tab.start[n_layers] <= INT32_MAX, "shifted_noise_all: too many blocks");
     shifted_noise_all_kernel<<<(int)tab.start[n_layers], 256, 0, (cudaStream_t)stream>>>(positions, N, mod, tab);
