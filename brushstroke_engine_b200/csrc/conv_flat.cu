@@ -23,6 +23,13 @@
 // weight footprint in shared memory; when all weights of a phase fit (Cin <= 128) they stay RESIDENT while the pair
 // sweeps its items phase by phase, and only position windows stream from L2 through a deep ring.
 //
+// Stride-2 3x3 convolutions (the geometry encoder's down-sampling layers) run on the same kernel at their algorithmic
+// cost: the reflect-padded NHWC input is read as its four parity planes xp[2Y'+a, 2X'+b] (a 5-D tensor map: the pixel
+// pair (b, c) is the contiguous dimension), each plane is a flat [positions x channels] matrix with pitch Wp/2, and tap
+// (kh, kw) is plane (kh & 1, kw & 1) shifted by (kh >> 1) * P + (kw >> 1) rows.  A launch is therefore described by a list
+// of ENTRIES (K chunk, row shift, accumulator, weight tile): for ordinary convolutions every tap meets every chunk, for
+// the strided ones a chunk (= 64 channels of one plane) meets only the taps of its plane.
+//
 // With 2.25 taps per class tile the transposed conv leaves the single MMA-issuing thread ~64 cycles per instruction, so
 // its loop is kept to a handful of instructions per tap: tap programs live in registers, descriptors are formed by 32-bit
 // adds on a precomputed low word, waits have a fast path.
@@ -33,7 +40,7 @@
 
 namespace nbe {
 
-constexpr int F_MAX_TAPS = 9;
+constexpr int F_MAX_ENT = 64;
 constexpr int F_MAX_CLASSES = 4;
 constexpr int F_THREADS = 320;                                     // TMA warp, MMA warp, 8 epilogue warps
 constexpr int F_EPI_WARPS = 8;
@@ -45,16 +52,25 @@ constexpr int F_BHALF = 64 * 128;                                  // this CTA's
 struct FlatParams {
     __nv_bfloat16* y;
     int N, P, positions, tiles_per_img, T, items_per_img, total_items;
-    int ntaps;
-    int tap_shift[F_MAX_TAPS], tap_acc[F_MAX_TAPS], tap_btile[F_MAX_TAPS], tap_first[F_MAX_TAPS];
+    // entries, sorted by A chunk within each phase: MMA group (A chunk c shifted by `shift` rows) x (weight tile btile, K block bk)
+    int n_ent;
+    short ent_c[F_MAX_ENT], ent_shift[F_MAX_ENT];
+    unsigned char ent_acc[F_MAX_ENT], ent_first[F_MAX_ENT], ent_btile[F_MAX_ENT], ent_bk[F_MAX_ENT];
+    // the same, packed for the MMA issuer: A start offset in 16-byte units [0,16) | accumulator column offset [16,26) | first [26] | chunk [27,32)
+    uint32_t ent_w[F_MAX_ENT + 1];
     int cls_sy[F_MAX_CLASSES], cls_sx[F_MAX_CLASSES], cls_oy[F_MAX_CLASSES], cls_ox[F_MAX_CLASSES], cls_vy[F_MAX_CLASSES], cls_vx[F_MAX_CLASSES];
     int min_shift, n_boxes, box_rows, k_chunks;
-    int n_phases, ph_t0[2], ph_t1[2], ph_G[2], ph_cls[2][F_MAX_CLASSES], Gmax;
+    // phases: groups of classes whose accumulators fit in half of TMEM; each phase owns the entries [ph_e0, ph_e1)
+    int n_phases, ph_e0[2], ph_e1[2], ph_G[2], ph_cls[2][F_MAX_CLASSES], Gmax;
     // resident: the weights of ONE phase stay in shared memory while the pair sweeps all of its items (phase-major order),
     // so that only the position windows stream from L2; otherwise weights stream through a F_BSTAGES ring (item-major)
     int resident, b_tiles, n_abuf;
+    // planes: A chunks are 64 channels of one parity plane of a padded NHWC image (stride-2 convs); cpp = chunks per plane
+    int planes, cpp, plane_C, plane_rows;
+    int cout_off;                                                   // first output channel of this launch within the weight tiles
     uint32_t smem_need;
     int y_cs; long long y_row_pitch, y_img_pitch; int noise_w;
+    int vec_stride;                                                 // per-sample stride of dcoef / next_scale
     const float* dcoef; const float* noise; long long noise_sn; float noise_gain;
     const float* bias; int act; float alpha, gain, clamp; const float* next_scale;
     uint32_t idesc;
@@ -70,7 +86,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
         if ((uint32_t)(smem - smem_raw) + p.smem_need > dyn) __trap();   // the host sized the buffer for an aligned base
     }
-    const int a_bytes = p.n_boxes * p.box_rows * 128;
+    const int a_bytes = (p.n_boxes * p.box_rows * 128 + 1023) & ~1023;
     uint8_t* smem_a = smem;                                         // [n_abuf][window of one 64-channel chunk]
     uint8_t* smem_b = smem + p.n_abuf * a_bytes;                    // [b_tiles][8 KiB]: ring, or the resident phase weights
     uint8_t* smem_stage = smem_b + p.b_tiles * F_BHALF;             // [F_EPI_WARPS][F_STAGE_BYTES] epilogue transposition buffers
@@ -108,10 +124,11 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tcgen05_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
     const int set_cols = p.T * p.Gmax * 128;                        // TMEM columns of one accumulator set
-    // schedule of this pair: n_local item pairs x n_phases, item-major (streamed weights) or phase-major (resident weights);
-    // CTA r takes item 2j + r (the last pair may hold a dummy)
+    // schedule of this pair: n_local item pairs x n_phases, item-major (streamed weights) or phase-major (resident weights).
+    // Pair j = (image pair j / items_per_img, tile j % items_per_img): CTA r takes that tile of image 2 * (j / items_per_img) + r,
+    // so both CTAs share q0 and with it every descriptor offset (the last image pair may hold a dummy).
     const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int pairs = (p.total_items + 1) >> 1;
+    const int pairs = ((p.N + 1) >> 1) * p.items_per_img;
     const int n_local = (pairs - cid + n_clusters - 1) / n_clusters;
     const int n_steps = n_local * p.n_phases;
 
@@ -121,38 +138,44 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t acnt = 0, bcnt = 0;
             int k = 0, ph = 0;
             for (int s = 0; s < n_steps; ++s) {
-                int item = 2 * (cid + k * n_clusters) + rank;
-                if (item >= p.total_items) item = p.total_items - 1;           // dummy: loads stay in range, nothing is stored
-                const int n = item / p.items_per_img;
-                const int q0 = (item - n * p.items_per_img) * p.T * 128;
-                const int t0 = p.ph_t0[ph], ntp = p.ph_t1[ph] - t0;
+                const int j = cid + k * n_clusters;
+                const int np = j / p.items_per_img;
+                const int n = min(2 * np + rank, p.N - 1);                       // dummy: loads stay in range, nothing is stored
+                const int q0 = (j - np * p.items_per_img) * p.T * 128;
+                const int e0 = p.ph_e0[ph], e1 = p.ph_e1[ph];
                 if (p.resident && k == 0) {
                     if (ph > 0) mbar_wait(smem_u32(res_free), (uint32_t)((ph - 1) & 1));   // previous phase's MMAs are done with smem_b
                     const uint32_t rf = smem_u32(res_full);
-                    if (leader) mbar_expect_tx(rf, 2u * (uint32_t)(ntp * p.k_chunks) * F_BHALF);
-                    for (int c = 0; c < p.k_chunks; ++c)
-                        for (int t = 0; t < ntp; ++t)
-                            tma_load_3d_2sm(smem_u32(smem_b + (c * ntp + t) * F_BHALF), &tmap_b, rf, c * 64, rank * 64, p.tap_btile[t0 + t]);
+                    if (leader) mbar_expect_tx(rf, 2u * (uint32_t)(e1 - e0) * F_BHALF);
+                    for (int e = e0; e < e1; ++e)
+                        tma_load_3d_2sm(smem_u32(smem_b + (e - e0) * F_BHALF), &tmap_b, rf, p.ent_bk[e] * 64, p.cout_off + rank * 64, p.ent_btile[e]);
                 }
+                int e = e0;
+                const int wrow0 = p.planes ? q0 / p.P : 0;                        // first plane row of the window
                 for (int c = 0; c < p.k_chunks; ++c) {
                     const int slot = (int)(acnt % (uint32_t)p.n_abuf);
                     const uint32_t par = (acnt / (uint32_t)p.n_abuf) & 1u;
                     ++acnt;
                     mbar_wait_fast(smem_u32(&a_empty[slot]), par ^ 1);
                     const uint32_t full = smem_u32(&a_full[slot]);
-                    if (leader) mbar_expect_tx(full, 2u * (uint32_t)a_bytes);
-                    for (int b = 0; b < p.n_boxes; ++b)
-                        tma_load_3d_2sm(smem_u32(smem_a + slot * a_bytes + b * p.box_rows * 128), &tmap_a, full, c * 64,
-                                        q0 + p.min_shift + b * p.box_rows, n);
+                    if (leader) mbar_expect_tx(full, 2u * (uint32_t)(p.n_boxes * p.box_rows * 128));
+                    if (p.planes) {
+                        const int pl = c / p.cpp, cl = c - pl * p.cpp;
+                        tma_load_5d_2sm(smem_u32(smem_a + slot * a_bytes), &tmap_a, full, (pl & 1) * p.plane_C + cl * 64, 0, pl >> 1, wrow0, n);
+                    } else {
+                        for (int b = 0; b < p.n_boxes; ++b)
+                            tma_load_3d_2sm(smem_u32(smem_a + slot * a_bytes + b * p.box_rows * 128), &tmap_a, full, c * 64,
+                                            q0 + p.min_shift + b * p.box_rows, n);
+                    }
                     if (!p.resident)
-                        for (int t = t0; t < t0 + ntp; ++t) {
+                        for (; e < e1 && p.ent_c[e] == c; ++e) {
                             const int bs = (int)(bcnt % F_BSTAGES);
                             const uint32_t bpar = (bcnt / F_BSTAGES) & 1u;
                             ++bcnt;
                             mbar_wait_fast(smem_u32(&b_empty[bs]), bpar ^ 1);
                             const uint32_t bf = smem_u32(&b_full[bs]);
                             if (leader) mbar_expect_tx(bf, 2u * F_BHALF);
-                            tma_load_3d_2sm(smem_u32(smem_b + bs * F_BHALF), &tmap_b, bf, c * 64, rank * 64, p.tap_btile[t]);
+                            tma_load_3d_2sm(smem_u32(smem_b + bs * F_BHALF), &tmap_b, bf, p.ent_bk[e] * 64, p.cout_off + rank * 64, p.ent_btile[e]);
                         }
                 }
                 if (p.resident) { if (++k == n_local) { k = 0; ++ph; } }
@@ -167,26 +190,18 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t idesc = p.idesc;
             const int T = p.T, k_chunks = p.k_chunks, n_abuf = p.n_abuf;
             const bool resident = p.resident != 0;
-            // the tap program of the current phase, in registers: row offset of the A start (16-byte units), accumulator column
-            // offset, "first tap of its accumulator" flag
-            uint32_t op_a[F_MAX_TAPS], op_d[F_MAX_TAPS], op_first[F_MAX_TAPS];
-            int ntp = 0, G = 1, cur_ph = -1;
             uint32_t acc_par0 = 0, acc_par1 = 0;
             int slot = 0; uint32_t a_par = 0;
             int bs = 0; uint32_t b_par = 0;
             int k = 0, ph = 0;
             for (int s = 0; s < n_steps; ++s) {
-                if (ph != cur_ph) {
-                    cur_ph = ph;
-                    const int t0 = p.ph_t0[ph];
-                    ntp = p.ph_t1[ph] - t0; G = p.ph_G[ph];
-#pragma unroll
-                    for (int t = 0; t < F_MAX_TAPS; ++t)
-                        if (t < ntp) {
-                            op_a[t] = uniform_u32((uint32_t)((p.tap_shift[t0 + t] - p.min_shift) * 8));
-                            op_d[t] = uniform_u32((uint32_t)(p.tap_acc[t0 + t] * 128));
-                            op_first[t] = uniform_u32((uint32_t)p.tap_first[t0 + t]);
-                        }
+                const int e0 = p.ph_e0[ph], e1 = p.ph_e1[ph], G = p.ph_G[ph];
+                // planes: the window starts at a plane-row boundary, q0 sits (q0 mod P) rows into it
+                uint32_t row0 = 0;
+                if (p.planes) {
+                    const int j = cid + k * n_clusters;
+                    const int q0 = (j % p.items_per_img) * T * 128;
+                    row0 = (uint32_t)(q0 % p.P);
                 }
                 const int ab = s & 1;
                 if (resident && k == 0) { mbar_wait(smem_u32(res_full), (uint32_t)(ph & 1)); tcgen05_fence_after(); }
@@ -195,39 +210,41 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tcgen05_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(ab * set_cols);
                 const uint32_t d_tile = (uint32_t)(G * 128);
+                int e = e0;
+                uint32_t w = p.ent_w[e0];
                 for (int c = 0; c < k_chunks; ++c) {
                     mbar_wait_fast(smem_u32(&a_full[slot]), a_par);
                     tcgen05_fence_after();
-                    const uint32_t a_lo = a_lo0 + (uint32_t)slot * a_step;
-                    const uint32_t b_res = b_lo0 + (uint32_t)(c * ntp) * (F_BHALF >> 4);
-#pragma unroll
-                    for (int t = 0; t < F_MAX_TAPS; ++t) {
-                        if (t < ntp) {
-                            uint32_t b_lo;
-                            if (resident) b_lo = b_res + (uint32_t)t * (F_BHALF >> 4);
-                            else {
-                                mbar_wait_fast(smem_u32(&b_full[bs]), b_par);
-                                tcgen05_fence_after();
-                                b_lo = b_lo0 + (uint32_t)bs * (F_BHALF >> 4);
-                            }
-                            const uint32_t acc0 = (c != 0 || !op_first[t]) ? 1u : 0u;
-                            if (elect_one()) {
-#pragma unroll
-                                for (int i = 0; i < 2; ++i) {
-                                    if (i < T) {
-                                        // position tile i, tap t: rows [i*128 + shift - min_shift, +128) of the window
-                                        const uint32_t al = a_lo + op_a[t] + (uint32_t)(i * 1024);
-                                        const uint32_t d = d0 + op_d[t] + (uint32_t)i * d_tile;
-                                        umma_bf16_lo_2sm(d, al, b_lo, idesc, acc0);
-                                        umma_bf16_lo_2sm(d, al + 2, b_lo + 2, idesc, 1u);
-                                        umma_bf16_lo_2sm(d, al + 4, b_lo + 4, idesc, 1u);
-                                        umma_bf16_lo_2sm(d, al + 6, b_lo + 6, idesc, 1u);
-                                    }
-                                }
-                                if (!resident) umma_commit_2sm(smem_u32(&b_empty[bs]));
-                            }
-                            if (!resident) { if (++bs == F_BSTAGES) { bs = 0; b_par ^= 1; } }
+                    const uint32_t a_lo = a_lo0 + (uint32_t)slot * a_step + row0 * 8u;
+                    while (e < e1 && (int)(w >> 27) == c) {
+                        const uint32_t wn = p.ent_w[e + 1];          // next entry (the table has a sentinel), fetched ahead of the issue
+                        uint32_t b_lo;
+                        if (resident) b_lo = b_lo0 + (uint32_t)(e - e0) * (F_BHALF >> 4);
+                        else {
+                            mbar_wait_fast(smem_u32(&b_full[bs]), b_par);
+                            tcgen05_fence_after();
+                            b_lo = b_lo0 + (uint32_t)bs * (F_BHALF >> 4);
                         }
+                        // position tile i: rows [i*128 + shift - min_shift, +128) of the window
+                        const uint32_t al0 = a_lo + (w & 0xFFFFu);
+                        const uint32_t dd = d0 + ((w >> 16) & 0x3FFu);
+                        const uint32_t acc0 = ((w >> 26) & 1u) ^ 1u;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                if (i < T) {
+                                    const uint32_t al = al0 + (uint32_t)(i * 1024);
+                                    const uint32_t d = dd + (uint32_t)i * d_tile;
+                                    umma_bf16_lo_2sm(d, al, b_lo, idesc, acc0);
+                                    umma_bf16_lo_2sm(d, al + 2, b_lo + 2, idesc, 1u);
+                                    umma_bf16_lo_2sm(d, al + 4, b_lo + 4, idesc, 1u);
+                                    umma_bf16_lo_2sm(d, al + 6, b_lo + 6, idesc, 1u);
+                                }
+                            }
+                            if (!resident) umma_commit_2sm(smem_u32(&b_empty[bs]));
+                        }
+                        if (!resident) { if (++bs == F_BSTAGES) { bs = 0; b_par ^= 1; } }
+                        ++e; w = wn;
                     }
                     if (elect_one()) umma_commit_2sm(smem_u32(&a_empty[slot]));
                     if (++slot == n_abuf) { slot = 0; a_par ^= 1; }
@@ -257,19 +274,19 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
         int k = 0, ph = 0;
         for (int s = 0; s < n_steps; ++s) {
-            int item = 2 * (cid + k * n_clusters) + rank;
-            const bool dummy = item >= p.total_items;
-            if (dummy) item = p.total_items - 1;
+            const int j = cid + k * n_clusters;
+            const int np = j / p.items_per_img;
+            const bool dummy = 2 * np + rank >= p.N;
+            const int n = min(2 * np + rank, p.N - 1);
+            const int q0 = (j - np * p.items_per_img) * p.T * 128;
             const int G = p.ph_G[ph];
             const int ab = s & 1;
-            const int n = item / p.items_per_img;
-            const int q0 = (item - n * p.items_per_img) * p.T * 128;
             if (EPI == 1 && n != cur_n) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (et < 128) {
-                    s_vec[et] = p.dcoef ? p.dcoef[(long long)n * 128 + et] : 1.f;
+                    s_vec[et] = p.dcoef ? p.dcoef[(long long)n * p.vec_stride + et] : 1.f;
                     s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
-                    s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * 128 + et] : 1.f;
+                    s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * p.vec_stride + et] : 1.f;
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_n = n;
@@ -354,42 +371,98 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ---- host ----------------------------------------------------------------------------------------
-static int launch_flat(const void* x, const void* wq, FlatParams& p, int N, int in_positions, int Cin, int x_cs, int n_wtiles,
+// One tap of a launch's program, before expansion into entries
+struct FlatTap { int shift, acc, btile, plane; };                   // plane: parity plane the tap reads (-1: all chunks)
+
+struct FlatInput {
+    const void* x; int N, Cin, x_cs;
+    int in_positions;                                               // flat mode: positions per image
+    int planes, Hp, Wp;                                             // plane mode: padded image extent (even)
+};
+
+static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_cout, FlatParams& p, const FlatTap* taps, const int* phase_ntaps,
                        cudaStream_t stream) {
-    const int Cin_pad = (Cin + 63) / 64 * 64;
-    p.k_chunks = Cin_pad / 64;
-    int max_shift = p.tap_shift[0];
-    p.min_shift = p.tap_shift[0];
-    for (int t = 1; t < p.ntaps; ++t) { if (p.tap_shift[t] < p.min_shift) p.min_shift = p.tap_shift[t]; if (p.tap_shift[t] > max_shift) max_shift = p.tap_shift[t]; }
-    const int win_rows = 128 * p.T + (max_shift - p.min_shift);
-    p.n_boxes = (win_rows + 255) / 256;                             // TMA boxes of <= 256 rows, whole 8-row swizzle atoms
-    p.box_rows = ((win_rows + p.n_boxes - 1) / p.n_boxes + 7) / 8 * 8;
+    const int Cin_pad = (in.Cin + 63) / 64 * 64;
+    const int cpp = Cin_pad / 64;
+    p.planes = in.planes; p.cpp = cpp; p.plane_C = in.Cin;
+    p.k_chunks = in.planes ? 4 * cpp : cpp;
+    // expand the tap program into entries sorted by chunk within each phase
+    int ntaps = 0;
+    for (int ph = 0; ph < p.n_phases; ++ph) ntaps += phase_ntaps[ph];
+    int max_shift = taps[0].shift;
+    p.min_shift = taps[0].shift;
+    for (int t = 1; t < ntaps; ++t) { p.min_shift = std::min(p.min_shift, taps[t].shift); max_shift = std::max(max_shift, taps[t].shift); }
+    int e = 0, t0 = 0, max_phase_tiles = 0;
+    for (int ph = 0; ph < p.n_phases; ++ph) {
+        p.ph_e0[ph] = e;
+        bool seen[F_MAX_CLASSES] = {false, false, false, false};
+        for (int c = 0; c < p.k_chunks; ++c)
+            for (int t = t0; t < t0 + phase_ntaps[ph]; ++t) {
+                if (in.planes && taps[t].plane != c / cpp) continue;
+                if (e >= F_MAX_ENT) return fail(NBE_EUNSUPPORTED, "conv_flat: tap program too long (%d chunks x %d taps)", p.k_chunks, ntaps);
+                p.ent_c[e] = (short)c; p.ent_shift[e] = (short)taps[t].shift; p.ent_acc[e] = (unsigned char)taps[t].acc;
+                p.ent_btile[e] = (unsigned char)taps[t].btile; p.ent_bk[e] = (unsigned char)(in.planes ? c % cpp : c);
+                p.ent_first[e] = seen[taps[t].acc] ? 0 : 1; seen[taps[t].acc] = true;
+                ++e;
+            }
+        p.ph_e1[ph] = e;
+        max_phase_tiles = std::max(max_phase_tiles, e - p.ph_e0[ph]);
+        t0 += phase_ntaps[ph];
+    }
+    p.n_ent = e;
+    for (int i = 0; i < e; ++i) {
+        const int a_off = (p.ent_shift[i] - p.min_shift) * 8;
+        if (a_off < 0 || a_off > 0xFFFF || p.ent_c[i] > 31) return fail(NBE_EUNSUPPORTED, "conv_flat: tap program out of range");
+        p.ent_w[i] = (uint32_t)a_off | ((uint32_t)p.ent_acc[i] * 128u) << 16 | (uint32_t)p.ent_first[i] << 26 | (uint32_t)p.ent_c[i] << 27;
+    }
+    p.ent_w[e] = 0xFFFFFFFFu;                                       // sentinel: chunk 31 never matches
+    if (max_shift > 32767 || p.min_shift < -32768) return fail(NBE_EUNSUPPORTED, "conv_flat: row pitch too large");
+    int win_rows;
+    if (in.planes) {
+        // whole plane rows: the window starts at the row that holds q0 and covers 128 T + max_shift more positions
+        const int rows = (p.P - 1 + 128 * p.T + max_shift + p.P - 1) / p.P;       // ceil((worst start offset + tiles + halo) / P)
+        p.n_boxes = 1; p.box_rows = rows * p.P; p.plane_rows = rows;
+        win_rows = p.box_rows;
+        if (rows > 256 || p.P > 256) return fail(NBE_EUNSUPPORTED, "conv_flat: plane window too large");
+    } else {
+        win_rows = 128 * p.T + (max_shift - p.min_shift);
+        p.n_boxes = (win_rows + 255) / 256;                         // TMA boxes of <= 256 rows, whole 8-row swizzle atoms
+        p.box_rows = ((win_rows + p.n_boxes - 1) / p.n_boxes + 7) / 8 * 8;
+        p.plane_rows = 0;
+    }
     p.tiles_per_img = (p.positions + 127) / 128;
     p.items_per_img = (p.tiles_per_img + p.T - 1) / p.T;
-    const int64_t total = (int64_t)N * p.items_per_img;
+    const int64_t total = (int64_t)in.N * p.items_per_img;
     if (total * p.n_phases > INT32_MAX) return fail(NBE_EINVAL, "conv_flat: too many work items");
     p.total_items = (int)total;
+    p.N = in.N;
     // kind::f16: D = f32, A = B = bf16, K-major; N = 128, M = 256 (the pair)
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     const bool raw = !p.dcoef && !p.noise && !p.bias && !p.act && !p.next_scale;
     const size_t limit = 227 * 1024;
-    int max_phase_tiles = 0;
-    for (int ph = 0; ph < p.n_phases; ++ph) max_phase_tiles = std::max(max_phase_tiles, (p.ph_t1[ph] - p.ph_t0[ph]) * p.k_chunks);
     static const bool no_resident = getenv("NBE_FLAT_NO_RESIDENT") != nullptr;
-    const size_t a_bytes = (size_t)p.n_boxes * p.box_rows * 128;
+    const size_t a_bytes = ((size_t)p.n_boxes * p.box_rows * 128 + 1023) & ~(size_t)1023;
     const size_t epi_bytes = F_EPI_WARPS * F_STAGE_BYTES + (raw ? 0 : 3 * 128 * sizeof(float)) + 256;
     CUtensorMap ta, tb;
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)in_positions, (cuuint64_t)N};
-        cuuint64_t strides[2] = {(cuuint64_t)x_cs * 2, (cuuint64_t)in_positions * x_cs * 2};
+    if (in.planes) {
+        // (pixel pair x channels, X', row parity, Y', image) over the padded NHWC image
+        cuuint64_t dims[5] = {(cuuint64_t)2 * in.Cin, (cuuint64_t)in.Wp / 2, 2, (cuuint64_t)in.Hp / 2, (cuuint64_t)in.N};
+        cuuint64_t strides[4] = {(cuuint64_t)2 * in.x_cs * 2, (cuuint64_t)in.Wp * in.x_cs * 2, (cuuint64_t)2 * in.Wp * in.x_cs * 2,
+                                 (cuuint64_t)in.Hp * in.Wp * in.x_cs * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)p.P, 1, (cuuint32_t)p.plane_rows, 1};
+        int st = make_tmap(&ta, in.x, 5, dims, strides, box, "parity planes");
+        if (st) return st;
+    } else {
+        cuuint64_t dims[3] = {(cuuint64_t)in.Cin, (cuuint64_t)in.in_positions, (cuuint64_t)in.N};
+        cuuint64_t strides[2] = {(cuuint64_t)in.x_cs * 2, (cuuint64_t)in.in_positions * in.x_cs * 2};
         cuuint32_t box[3] = {64, (cuuint32_t)p.box_rows, 1};
-        int st = make_tmap(&ta, x, 3, dims, strides, box, "flat activations");
+        int st = make_tmap(&ta, in.x, 3, dims, strides, box, "flat activations");
         if (st) return st;
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, 128, (cuuint64_t)n_wtiles};
-        cuuint64_t strides[2] = {(cuuint64_t)Cin_pad * 2, (cuuint64_t)128 * Cin_pad * 2};
-        cuuint32_t box[3] = {64, 64, 1};                            // half of the output channels per CTA of the pair
+        cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, (cuuint64_t)w_cout, (cuuint64_t)n_wtiles};
+        cuuint64_t strides[2] = {(cuuint64_t)Cin_pad * 2, (cuuint64_t)w_cout * Cin_pad * 2};
+        cuuint32_t box[3] = {64, 64, 1};                            // half of the 128 output channels per CTA of the pair
         int st = make_tmap(&tb, wq, 3, dims, strides, box, "weights");
         if (st) return st;
     }
@@ -400,11 +473,10 @@ static int launch_flat(const void* x, const void* wq, FlatParams& p, int N, int 
         if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "conv_flat: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-    const int64_t pairs = (total + 1) / 2;
+    const int64_t pairs = (int64_t)((in.N + 1) / 2) * p.items_per_img;
     const int grid = (int)std::min<int64_t>(kNumSMs / 2, pairs) * 2;
     // resident weights pay off when a pair sweeps several items per phase and the largest phase fits next to >= 3 windows
-    p.resident = !no_resident && p.n_phases > 1 && pairs >= 2 * (int64_t)(grid / 2) &&
-                 epi_bytes + (size_t)max_phase_tiles * F_BHALF + 3 * a_bytes <= limit;
+    p.resident = !no_resident && pairs >= 2 * (int64_t)(grid / 2) && epi_bytes + (size_t)max_phase_tiles * F_BHALF + 3 * a_bytes <= limit;
     p.b_tiles = p.resident ? max_phase_tiles : F_BSTAGES;
     const size_t rest = epi_bytes + (size_t)p.b_tiles * F_BHALF;
     if (rest + 2 * a_bytes > limit) return fail(NBE_EUNSUPPORTED, "conv_flat: window of %d rows does not fit in shared memory", win_rows);
@@ -434,22 +506,61 @@ extern "C" int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
     NBE_REQUIRE((((uintptr_t)x | (uintptr_t)wq | (uintptr_t)y) & 15) == 0, "conv3x3_flat: tensors must be 16-byte aligned");
     NBE_REQUIRE(y_row_pitch >= OW && y_img_pitch >= y_row_pitch * OH, "conv3x3_flat: bad output pitches");
     if (N == 0) return NBE_OK;
-    FlatParams p;
-    p.y = (__nv_bfloat16*)y; p.N = N; p.P = x_pitch; p.positions = OH * x_pitch; p.T = 2;
-    p.ntaps = 9;
+    FlatParams p{};
+    p.y = (__nv_bfloat16*)y; p.P = x_pitch; p.positions = OH * x_pitch; p.T = 2;
+    FlatTap taps[9];
     const int off = valid ? 0 : -1;
     for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw) {
-            const int t = kh * 3 + kw;
-            p.tap_shift[t] = (kh + off) * x_pitch + (kw + off); p.tap_acc[t] = 0; p.tap_btile[t] = t; p.tap_first[t] = (t == 0);
-        }
+        for (int kw = 0; kw < 3; ++kw) taps[kh * 3 + kw] = {(kh + off) * x_pitch + (kw + off), 0, kh * 3 + kw, -1};
     p.cls_sy[0] = 1; p.cls_sx[0] = 1; p.cls_oy[0] = 0; p.cls_ox[0] = 0; p.cls_vy[0] = OH; p.cls_vx[0] = OW;
-    p.n_phases = 1; p.ph_t0[0] = 0; p.ph_t1[0] = 9; p.ph_G[0] = 1; p.ph_cls[0][0] = 0; p.Gmax = 1;
-    p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch; p.noise_w = OW;
+    p.n_phases = 1; p.ph_G[0] = 1; p.ph_cls[0][0] = 0; p.Gmax = 1;
+    const int phase_ntaps[2] = {9, 0};
+    p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch; p.noise_w = OW; p.vec_stride = 128; p.cout_off = 0;
     p.dcoef = dcoef; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain;
     p.bias = bias; p.act = 1; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.next_scale = next_scale;
     const int in_rows = valid ? OH + 2 : OH;
-    return launch_flat(x, wq, p, N, in_rows * x_pitch, Cin, x_cs, 9, (cudaStream_t)stream);
+    FlatInput in{x, N, Cin, x_cs, in_rows * x_pitch, 0, 0, 0};
+    return launch_flat(in, wq, 9, 128, p, taps, phase_ntaps, (cudaStream_t)stream);
+}
+
+extern "C" int nbe_conv3x3s2_flat_bf16(const void* xp, const void* wq, void* y,
+                                       int N, int H, int W, int Cin, int Cout, int y_cs, int64_t y_row_pitch, int64_t y_img_pitch,
+                                       const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                                       nbe_stream_t stream) {
+    NBE_REQUIRE(xp && wq && y && N >= 0 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0, "conv3x3s2_flat: bad arguments (H, W must be even)");
+    NBE_REQUIRE(Cin >= 64 && Cin % 64 == 0, "conv3x3s2_flat: Cin must be a multiple of 64 (dense channels: x_cs == Cin)");
+    NBE_REQUIRE(Cout >= 128 && Cout % 128 == 0, "conv3x3s2_flat: Cout must be a multiple of 128");
+    NBE_REQUIRE(y_cs % 8 == 0 && y_cs >= Cout, "conv3x3s2_flat: channel stride must be a multiple of 8");
+    NBE_REQUIRE((((uintptr_t)xp | (uintptr_t)wq | (uintptr_t)y) & 15) == 0, "conv3x3s2_flat: tensors must be 16-byte aligned");
+    const int OH = H / 2, OW = W / 2;
+    NBE_REQUIRE(y_row_pitch >= OW && y_img_pitch >= y_row_pitch * OH, "conv3x3s2_flat: bad output pitches");
+    if (N == 0) return NBE_OK;
+    // out[Y, X] = sum_{kh,kw} W[kh,kw] xp[2Y + kh, 2X + kw]  (xp = the input with its 1-pixel border, (H+2) x (W+2)):
+    // tap (kh, kw) reads parity plane (kh & 1, kw & 1) at plane position (Y + (kh >> 1), X + (kw >> 1))
+    const int P = (W + 2) / 2;
+    for (int co = 0; co < Cout; co += 128) {
+        FlatParams p{};
+        p.y = (__nv_bfloat16*)y + co; p.P = P; p.positions = OH * P;
+        // two position tiles per item share every weight tile, unless the padding of the last item costs more than that saves
+        const int tiles = (OH * P + 127) / 128;
+        p.T = ((tiles + 1) / 2 * 2 * 100 > tiles * 115) ? 1 : 2;
+        FlatTap taps[9];
+        int t = 0;
+        for (int pl = 0; pl < 4; ++pl)
+            for (int kh = (pl >> 1); kh < 3; kh += 2)
+                for (int kw = (pl & 1); kw < 3; kw += 2) taps[t++] = {(kh >> 1) * P + (kw >> 1), 0, kh * 3 + kw, pl};
+        p.cls_sy[0] = 1; p.cls_sx[0] = 1; p.cls_oy[0] = 0; p.cls_ox[0] = 0; p.cls_vy[0] = OH; p.cls_vx[0] = OW;
+        p.n_phases = 1; p.ph_G[0] = 1; p.ph_cls[0][0] = 0; p.Gmax = 1;
+        const int phase_ntaps[2] = {9, 0};
+        p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch; p.noise_w = OW; p.vec_stride = Cout; p.cout_off = co;
+        p.dcoef = nullptr; p.noise = nullptr; p.noise_sn = 0; p.noise_gain = 0.f;
+        p.bias = bias ? bias + co : nullptr; p.act = 1; p.alpha = alpha; p.gain = gain; p.clamp = clamp;
+        p.next_scale = next_scale ? next_scale + co : nullptr;
+        FlatInput in{xp, N, Cin, Cin, 0, 1, H + 2, W + 2};
+        int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream);
+        if (st) return st;
+    }
+    return NBE_OK;
 }
 
 extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_out,
@@ -462,35 +573,32 @@ extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_o
     NBE_REQUIRE((((uintptr_t)x | (uintptr_t)wq | (uintptr_t)t_out) & 15) == 0, "convT3x3s2_flat: tensors must be 16-byte aligned");
     NBE_REQUIRE(t_row_pitch >= 2 * W + 1 && t_img_pitch >= t_row_pitch * (2 * H + 1), "convT3x3s2_flat: bad output pitches");
     if (N == 0) return NBE_OK;
-    FlatParams p;
-    p.y = (__nv_bfloat16*)t_out; p.N = N; p.P = x_pitch; p.positions = (H + 1) * x_pitch; p.T = 1;
+    FlatParams p{};
+    p.y = (__nv_bfloat16*)t_out; p.P = x_pitch; p.positions = (H + 1) * x_pitch; p.T = 1;
     // T[2Y+kh, 2X+kw] += W[kh,kw] x[Y,X]  (F.conv_transpose2d, SG2/torch_utils/ops/conv2d_resample.py:124-138):
     // class (py,px) at grid (Y',X') sums the taps with kh = py, kw = px (mod 2) over x[Y' - (kh-py)/2, X' - (kw-px)/2].
     // Two phases of two classes each -- {(0,0): 4 taps, (1,1): 1 tap} and {(0,1): 2 taps, (1,0): 2 taps} -- so that a
     // phase's two accumulators take 256 TMEM columns and the other 256 hold the previous phase while its epilogue runs.
     const int phase_classes[2][2][2] = {{{0, 0}, {1, 1}}, {{0, 1}, {1, 0}}};
+    FlatTap taps[9];
+    int phase_ntaps[2] = {0, 0};
     int t = 0;
     for (int ph = 0; ph < 2; ++ph) {
-        p.ph_t0[ph] = t;
         for (int gl = 0; gl < 2; ++gl) {
             const int py = phase_classes[ph][gl][0], px = phase_classes[ph][gl][1];
             const int g = py * 2 + px;
             p.ph_cls[ph][gl] = g;
-            bool first = true;
             for (int kh = py; kh < 3; kh += 2)
-                for (int kw = px; kw < 3; kw += 2) {
-                    p.tap_shift[t] = -((kh - py) / 2) * x_pitch - (kw - px) / 2;
-                    p.tap_acc[t] = gl; p.tap_btile[t] = kh * 3 + kw; p.tap_first[t] = first ? 1 : 0;
-                    first = false; ++t;
-                }
+                for (int kw = px; kw < 3; kw += 2) { taps[t++] = {-((kh - py) / 2) * x_pitch - (kw - px) / 2, gl, kh * 3 + kw, -1}; ++phase_ntaps[ph]; }
             p.cls_sy[g] = 2; p.cls_sx[g] = 2; p.cls_oy[g] = py; p.cls_ox[g] = px;
             p.cls_vy[g] = py ? H : H + 1; p.cls_vx[g] = px ? W : W + 1;
         }
-        p.ph_t1[ph] = t; p.ph_G[ph] = 2;
+        p.ph_G[ph] = 2;
     }
-    p.ntaps = t; p.n_phases = 2; p.Gmax = 2;
-    p.y_cs = t_cs; p.y_row_pitch = t_row_pitch; p.y_img_pitch = t_img_pitch; p.noise_w = 0;
+    p.n_phases = 2; p.Gmax = 2;
+    p.y_cs = t_cs; p.y_row_pitch = t_row_pitch; p.y_img_pitch = t_img_pitch; p.noise_w = 0; p.vec_stride = 128; p.cout_off = 0;
     p.dcoef = dcoef; p.noise = nullptr; p.noise_sn = 0; p.noise_gain = 0.f;
     p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.gain = 1.f; p.clamp = -1.f; p.next_scale = nullptr;
-    return launch_flat(x, wq, p, N, H * x_pitch, Cin, x_cs, 9, (cudaStream_t)stream);
+    FlatInput in{x, N, Cin, x_cs, H * x_pitch, 0, 0, 0};
+    return launch_flat(in, wq, 9, 128, p, taps, phase_ntaps, (cudaStream_t)stream);
 }

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 from typing import List
 
+import os
 import torch
 import torch.nn.functional as F
 
@@ -59,6 +60,7 @@ class GeometryEncoder:
             self._layers.append(self._fold(params, f'decoder.model.{i}.conv.conv') + (1, 1, True))
         self._n_enc = n_enc
         self._ws = {}
+        self._flat_s2 = os.environ.get('NBE_ENC_PER_TAP') is None      # A/B switch: strided layers on the per-tap kernel
         if mode == 'bf16':
             if cfg.in_channels != 1 or cfg.pre_filters <= 0 or cfg.pre_filters % 8 or cfg.preproc_type not in PREPROC_CODE:
                 raise RuntimeError('GeometryEncoder: the tensor-core path covers the sauto layout (1-channel input, 7x7 pre-layer)')
@@ -190,9 +192,16 @@ class GeometryEncoder:
                     y_cs, rp, ip = nxt.shape[3], ho + 2, (ho + 2) * (ho + 2)
                     y_ptr = nxt.data_ptr() + 2 * ((ho + 2) + 1) * y_cs
                     padded_out = nxt
-                _lib.call('nbe_conv_tc_bf16_ex', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cur.shape[3], cur.shape[3],
-                          cout, y_cs, 3, 1, stride, cur.shape[1], cur.shape[2], rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0,
-                          -1.0, _lib.ptr(next_scale), st)
+                cin = w.shape[1]
+                if stride == 2 and not up and self._flat_s2 and cin % 64 == 0 and cur.shape[3] == cin and cout % 128 == 0 and h % 2 == 0 and ho >= 32:
+                    # down-sampling layer at its algorithmic cost: parity planes of the bordered input on the flat CTA-pair kernel
+                    # (below 32^2 the per-image tiling pads too much; the per-tap kernel batches images into one tile)
+                    _lib.call('nbe_conv3x3s2_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, h, h, cin, cout, y_cs, rp, ip,
+                              _lib.ptr(b), slope, 1.0, -1.0, _lib.ptr(next_scale), st)
+                else:
+                    _lib.call('nbe_conv_tc_bf16_ex', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cur.shape[3], cur.shape[3],
+                              cout, y_cs, 3, 1, stride, cur.shape[1], cur.shape[2], rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0,
+                              -1.0, _lib.ptr(next_scale), st)
                 h = ho
                 if padded_out is not None:
                     _lib.call('nbe_reflect_border_nhwc_bf16', _lib.ptr(padded_out), B, h + 2, h + 2, cout, padded_out.shape[3], st)

@@ -188,6 +188,18 @@ int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
                           const float* bias, float alpha, float gain, float clamp, const float* next_scale,
                           nbe_stream_t stream);
 
+/* 3x3 stride-2 convolution (+ bias, leaky ReLU, gain, clamp, next_scale) at its algorithmic cost: the geometry encoder's
+ * down-sampling layers (simple_autoencoder.py:46-70, Conv2d(k=3, stride=2, padding=1, padding_mode='reflect') + BN folded
+ * into wq / bias + LeakyReLU).  xp: [N, H+2, W+2, Cin] NHWC bf16, dense channels, ALREADY carrying its 1-pixel border
+ * (nbe_reflect_border_nhwc_bf16); H, W even; Cin % 64 == 0; Cout % 128 == 0 (one pass per 128 output channels).
+ *   y[n, Y, X, o] = post( sum_{kh,kw,i} wq[kh*3+kw][o][i] * xp[n, 2Y+kh, 2X+kw, i] + bias[o] ),   Y < H/2, X < W/2
+ * The input is read as its four parity planes xp[2Y'+a, 2X'+b] through one 5-D tensor map; tap (kh, kw) is plane
+ * (kh & 1, kw & 1) shifted by (kh >> 1, kw >> 1) -- see csrc/conv_flat.cu. */
+int nbe_conv3x3s2_flat_bf16(const void* xp, const void* wq, void* y,
+                            int N, int H, int W, int Cin, int Cout, int y_cs, int64_t y_row_pitch, int64_t y_img_pitch,
+                            const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                            nbe_stream_t stream);
+
 /* Transposed 3x3 convolution, stride 2, at its algorithmic cost (9 taps per INPUT pixel):
  *   T[n, 2Y+kh, 2X+kw, o] += dcoef[n,o] * sum_i wq[kh*3+kw][o][i] * x[n,Y,X,i]     -> T is (2H+1) x (2W+1)
  * = F.conv_transpose2d(x, w, stride=2) of the up-sampling path SG2/torch_utils/ops/conv2d_resample.py:124-138

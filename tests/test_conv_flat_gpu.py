@@ -146,3 +146,28 @@ def test_up_layer_equals_reference_formulation():
     torch.cuda.synchronize()
     got = y.permute(0, 3, 1, 2).float()
     assert md(got, ref) < 2e-2 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('H,cin,cout,B', [(128, 64, 128, 3), (64, 128, 256, 2), (32, 256, 256, 5), (8, 64, 128, 1), (16, 192, 128, 4)])
+def test_conv3x3s2_flat_matches_strided_conv2d(H, cin, cout, B):
+    """Stride-2 3x3 conv over a pre-padded NHWC input read as four parity planes == F.conv2d(stride=2) on the padded input."""
+    g = torch.Generator().manual_seed(H + cin + cout + B)
+    xp = torch.randn(B, cin, H + 2, H + 2, generator=g)            # already carries its 1-pixel border
+    w = torch.randn(cout, cin, 3, 3, generator=g) / np.sqrt(cin * 9)
+    bias = torch.randn(cout, generator=g) * 0.1
+    ns = torch.rand(B, cout, generator=g) + 0.5
+    xq = xp.to(DEV).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    wq = prep_w(w, 0)
+    OH = H // 2
+    y_pitch, y_cs = OH + 3, cout + 8
+    y = torch.full((B, OH, y_pitch, y_cs), 7.0, dtype=torch.bfloat16, device=DEV)
+    bb, nsd = bias.to(DEV), ns.to(DEV)
+    _lib.call('nbe_conv3x3s2_flat_bf16', _lib.ptr(xq), _lib.ptr(wq), _lib.ptr(y), B, H, H, cin, cout, y_cs, y_pitch, OH * y_pitch,
+              _lib.ptr(bb), 0.01, 1.0, -1.0, _lib.ptr(nsd), _lib.stream())
+    torch.cuda.synchronize()
+    ref = F.conv2d(xp.to(torch.bfloat16).double(), w.to(torch.bfloat16).double(), stride=2) + bias.double()[None, :, None, None]
+    ref = torch.where(ref > 0, ref, ref * 0.01) * ns.double()[:, :, None, None]
+    got = y[:, :, :OH, :cout].permute(0, 3, 1, 2).float()
+    assert md(got, ref) < 1e-2 * max(float(ref.abs().max()), 1.0)
+    assert float((y[:, :, OH:, :].float() - 7.0).abs().max()) == 0         # columns past the output untouched
+    assert float((y[..., cout:].float() - 7.0).abs().max()) == 0
