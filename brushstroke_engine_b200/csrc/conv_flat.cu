@@ -500,27 +500,32 @@ extern "C" int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
                                      const float* bias, float alpha, float gain, float clamp, const float* next_scale,
                                      nbe_stream_t stream) {
     NBE_REQUIRE(x && wq && y && N >= 0 && OH >= 1 && OW >= 1 && Cin >= 1, "conv3x3_flat: bad arguments");
-    NBE_REQUIRE(Cout == 128, "conv3x3_flat: Cout must be 128");
+    NBE_REQUIRE(Cout >= 128 && Cout % 128 == 0, "conv3x3_flat: Cout must be a multiple of 128 (one pass per 128 output channels)");
     NBE_REQUIRE(x_pitch >= OW + (valid ? 2 : 1), "conv3x3_flat: input pitch %d too small (needs a zero gap column / the halo)", x_pitch);
     NBE_REQUIRE(x_cs % 8 == 0 && x_cs >= Cin && y_cs % 8 == 0 && y_cs >= Cout, "conv3x3_flat: channel strides must be multiples of 8");
     NBE_REQUIRE((((uintptr_t)x | (uintptr_t)wq | (uintptr_t)y) & 15) == 0, "conv3x3_flat: tensors must be 16-byte aligned");
     NBE_REQUIRE(y_row_pitch >= OW && y_img_pitch >= y_row_pitch * OH, "conv3x3_flat: bad output pitches");
     if (N == 0) return NBE_OK;
-    FlatParams p{};
-    p.y = (__nv_bfloat16*)y; p.P = x_pitch; p.positions = OH * x_pitch; p.T = 2;
-    FlatTap taps[9];
-    const int off = valid ? 0 : -1;
-    for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw) taps[kh * 3 + kw] = {(kh + off) * x_pitch + (kw + off), 0, kh * 3 + kw, -1};
-    p.cls_sy[0] = 1; p.cls_sx[0] = 1; p.cls_oy[0] = 0; p.cls_ox[0] = 0; p.cls_vy[0] = OH; p.cls_vx[0] = OW;
-    p.n_phases = 1; p.ph_G[0] = 1; p.ph_cls[0][0] = 0; p.Gmax = 1;
-    const int phase_ntaps[2] = {9, 0};
-    p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch; p.noise_w = OW; p.vec_stride = 128; p.cout_off = 0;
-    p.dcoef = dcoef; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain;
-    p.bias = bias; p.act = 1; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.next_scale = next_scale;
-    const int in_rows = valid ? OH + 2 : OH;
-    FlatInput in{x, N, Cin, x_cs, in_rows * x_pitch, 0, 0, 0};
-    return launch_flat(in, wq, 9, 128, p, taps, phase_ntaps, (cudaStream_t)stream);
+    for (int co = 0; co < Cout; co += 128) {
+        FlatParams p{};
+        p.y = (__nv_bfloat16*)y + co; p.P = x_pitch; p.positions = OH * x_pitch; p.T = 2;
+        FlatTap taps[9];
+        const int off = valid ? 0 : -1;
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) taps[kh * 3 + kw] = {(kh + off) * x_pitch + (kw + off), 0, kh * 3 + kw, -1};
+        p.cls_sy[0] = 1; p.cls_sx[0] = 1; p.cls_oy[0] = 0; p.cls_ox[0] = 0; p.cls_vy[0] = OH; p.cls_vx[0] = OW;
+        p.n_phases = 1; p.ph_G[0] = 1; p.ph_cls[0][0] = 0; p.Gmax = 1;
+        const int phase_ntaps[2] = {9, 0};
+        p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch; p.noise_w = OW; p.vec_stride = Cout; p.cout_off = co;
+        p.dcoef = dcoef ? dcoef + co : nullptr; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain;
+        p.bias = bias ? bias + co : nullptr; p.act = 1; p.alpha = alpha; p.gain = gain; p.clamp = clamp;
+        p.next_scale = next_scale ? next_scale + co : nullptr;
+        const int in_rows = valid ? OH + 2 : OH;
+        FlatInput in{x, N, Cin, x_cs, in_rows * x_pitch, 0, 0, 0};
+        int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream);
+        if (st) return st;
+    }
+    return NBE_OK;
 }
 
 extern "C" int nbe_conv3x3s2_flat_bf16(const void* xp, const void* wq, void* y,

@@ -198,6 +198,11 @@ class GeometryEncoder:
                     # (below 32^2 the per-image tiling pads too much; the per-tap kernel batches images into one tile)
                     _lib.call('nbe_conv3x3s2_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, h, h, cin, cout, y_cs, rp, ip,
                               _lib.ptr(b), slope, 1.0, -1.0, _lib.ptr(next_scale), st)
+                elif stride == 1 and self._flat_s2 and cout % 128 == 0 and ho >= 32:
+                    # ScaleUp conv over the bordered bilinear map: 'valid' flat conv, one pass per 128 output channels
+                    _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cur.shape[3], cur.shape[3],
+                              cur.shape[2], 1, cout, y_cs, rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0, -1.0,
+                              _lib.ptr(next_scale), st)
                 else:
                     _lib.call('nbe_conv_tc_bf16_ex', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cur.shape[3], cur.shape[3],
                               cout, y_cs, 3, 1, stride, cur.shape[1], cur.shape[2], rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0,

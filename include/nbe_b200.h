@@ -174,13 +174,14 @@ int nbe_conv_tc_bf16_ex(const void* x, const void* wq, void* y,
 /* ------------------------------------------------------------------------------------------------
  * "Flat" tensor-core convolutions: activations are NHWC bf16 whose rows are stored with a pitch x_pitch >= W + 1 and ZERO
  * gap columns, so that every filter tap is a constant row shift of the [positions x channels] matrix (see csrc/conv_flat.cu).
- * Cout must be 128.  wq as produced by nbe_prepare_weights_bf16.
+ * wq as produced by nbe_prepare_weights_bf16; the kernels work on 128 output channels at a time.
  */
 
 /* 3x3 stride-1 modulated convolution + the fused epilogue of nbe_conv_tc_bf16.
  * valid = 0: x is [N, OH, x_pitch >= OW+1, x_cs] (zero gap columns supply the padding);
  * valid = 1: x is [N, OH+2, x_pitch >= OW+2, x_cs] and already contains the 1-pixel halo (e.g. the FIR-upsampled U).
- * y element (n,oy,ox,c) -> y[(n*y_img_pitch + oy*y_row_pitch + ox)*y_cs + c]; gap columns of y are never written. */
+ * y element (n,oy,ox,c) -> y[(n*y_img_pitch + oy*y_row_pitch + ox)*y_cs + c]; gap columns of y are never written.
+ * Cout: a multiple of 128 (one pass per 128 output channels; dcoef / next_scale are [N, Cout]). */
 int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
                           int N, int OH, int OW, int Cin, int x_cs, int x_pitch, int valid, int Cout, int y_cs,
                           int64_t y_row_pitch, int64_t y_img_pitch,

@@ -171,3 +171,26 @@ def test_conv3x3s2_flat_matches_strided_conv2d(H, cin, cout, B):
     assert md(got, ref) < 1e-2 * max(float(ref.abs().max()), 1.0)
     assert float((y[:, :, OH:, :].float() - 7.0).abs().max()) == 0         # columns past the output untouched
     assert float((y[..., cout:].float() - 7.0).abs().max()) == 0
+
+
+def test_conv3x3_flat_two_output_passes():
+    """Cout = 256 runs as two 128-channel passes; per-sample vectors are [N, Cout]."""
+    g = torch.Generator().manual_seed(77)
+    B, R, cin, cout = 3, 32, 64, 256
+    x = torch.randn(B, cin, R + 2, R + 2, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / np.sqrt(cin * 9)
+    bias = torch.randn(cout, generator=g) * 0.1
+    ns = torch.rand(B, cout, generator=g) + 0.5
+    xq = pitched(x, R + 2, cin)
+    wq = prep_w(w, 0)
+    y = torch.full((B, R, R + 1, cout + 16), 3.0, dtype=torch.bfloat16, device=DEV)
+    bb, nsd = bias.to(DEV), ns.to(DEV)
+    _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(xq), _lib.ptr(wq), _lib.ptr(y), B, R, R, cin, cin, R + 2, 1, cout, cout + 16,
+              R + 1, R * (R + 1), None, None, 0, 0.0, _lib.ptr(bb), 0.01, 1.0, -1.0, _lib.ptr(nsd), _lib.stream())
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.to(torch.bfloat16).double(), w.to(torch.bfloat16).double()) + bias.double()[None, :, None, None]
+    ref = torch.where(ref > 0, ref, ref * 0.01) * ns.double()[:, :, None, None]
+    got = y[:, :, :R, :cout].permute(0, 3, 1, 2).float()
+    assert md(got, ref) < 1e-2 * max(float(ref.abs().max()), 1.0)
+    assert float((y[:, :, R:, :].float() - 3.0).abs().max()) == 0
+    assert float((y[..., cout:].float() - 3.0).abs().max()) == 0
