@@ -11,6 +11,7 @@
 // between neighbouring windows is served by L1.  HBM-bound: (TH*TW + OH*OW) * C * 2 bytes per image.
 #include "tc_common.cuh"
 #include <mutex>
+#include <type_traits>
 #include <cstdlib>
 
 namespace nbe {
@@ -165,7 +166,8 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
     uint8_t* bufs = smem;                                           // [2][FT_TILE_BYTES]
     float* s_epi = reinterpret_cast<float*>(bufs + 2 * ((FT_TILE_BYTES + 127) & ~127));   // [3][128]
     float* s_f = s_epi + 3 * 128;                                   // [16]
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_f + 16);         // [2]
+    float* s_nz = s_f + 16;                                         // [FT_OH][FT_OW] noise of the current tile
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_nz + FT_OH * FT_OW);   // [2]
     constexpr int BUF_STRIDE = (FT_TILE_BYTES + 127) & ~127;
 
     if (threadIdx.x < 16) {
@@ -197,7 +199,6 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
     const bool fold = p.gain > 0.f && p.alpha >= 0.f && p.alpha <= 1.f;
     const float g_pre = fold ? p.gain : 1.f, g_post = fold ? 1.f : p.gain;
     const float clamp_hi = p.clamp >= 0.f ? p.clamp : INFINITY;
-    const bool pair_noise = p.noise && ((p.OW | p.noise_sn) & 1) == 0 && ((uintptr_t)p.noise & 7) == 0;
     auto issue = [&](int tile, int b) {
         int t = tile;
         const int tx = t % tiles_x; t /= tiles_x;
@@ -226,90 +227,100 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
             __syncthreads();
         }
         const int ox = tx * FT_OW + px, oy0 = ty * FT_OH;
-        // the per-pixel noise of the 2 x FT_OH outputs is fetched before waiting for the tile, off the critical path
-        float nz[FT_OH][2];
-#pragma unroll
-        for (int r = 0; r < FT_OH; ++r) {
-            nz[r][0] = nz[r][1] = 0.f;
-            const int oy = oy0 + r;
-            if (p.noise && oy < p.OH && ox < p.OW) {
-                const float* np = p.noise + (long long)n * p.noise_sn + (long long)oy * p.OW + ox;
-                if (pair_noise) { const float2 v = __ldg(reinterpret_cast<const float2*>(np)); nz[r][0] = v.x; nz[r][1] = v.y; }
-                else { nz[r][0] = __ldg(np); if (ox + 1 < p.OW) nz[r][1] = __ldg(np + 1); }
-            }
+        // tiles that lie completely inside the output (all of them at 2^k resolutions) skip the per-store bounds checks
+        const bool full_tile = oy0 + FT_OH <= p.OH && tx * FT_OW + FT_OW <= p.OW;
+        // the tile's noise (already times noise_gain * folded gain) is staged in shared memory before waiting for the tile,
+        // off the critical path and out of the register file
+        if (threadIdx.x < FT_OH * FT_OW) {
+            const int r = threadIdx.x / FT_OW, c = threadIdx.x - r * FT_OW;
+            const int oy = oy0 + r, oxx = tx * FT_OW + c;
+            float v = 0.f;
+            if (p.noise && oy < p.OH && oxx < p.OW) v = __ldg(p.noise + (long long)n * p.noise_sn + (long long)oy * p.OW + oxx) * (p.noise_gain * g_pre);
+            s_nz[threadIdx.x] = v;
         }
+        __syncthreads();
         float sc[4], bs[4], ns[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { sc[k] = s_epi[cq * 4 + k]; bs[k] = s_epi[128 + cq * 4 + k]; ns[k] = s_epi[256 + cq * 4 + k]; }
-        const float ngain = p.noise_gain * g_pre;
+        const float alpha = p.alpha;
+        // output pointer of (oy0, ox), advanced by one row per output row: no 64-bit index math inside the loops
+        __nv_bfloat16* yrow = p.y + (((long long)n * p.y_img_pitch + (long long)oy0 * p.y_row_pitch + ox) * p.y_cs + cq * 4);
+        const long long yrow_step = p.y_row_pitch * p.y_cs;
+        const int ycs = p.y_cs;
         mbar_wait(smem_u32(&full[b]), (uint32_t)((it >> 1) & 1));
-        const uint8_t* tb = bufs + b * BUF_STRIDE + cq * 8;
-        auto ld = [&](int r, int c, float (&v)[4]) {
-            const uint2 raw = *reinterpret_cast<const uint2*>(tb + (r * FT_IW + c) * 256);
-            v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
-            v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+        const uint32_t tb = smem_u32(bufs + b * BUF_STRIDE) + (uint32_t)(cq * 8 + px * 256);   // 32-bit shared address: immediate offsets
+        auto ldi = [&](uint32_t off, float (&v)[4]) {
+            uint32_t x, y2;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y2) : "r"(tb + off));
+            v[0] = __uint_as_float(x << 16); v[1] = __uint_as_float(x & 0xffff0000u);
+            v[2] = __uint_as_float(y2 << 16); v[3] = __uint_as_float(y2 & 0xffff0000u);
         };
-        auto finish = [&](int r, int j, float (&acc)[4]) {
-            const int oy = oy0 + r;
-            if (oy >= p.OH || ox + j >= p.OW) return;
-            const float nzg = nz[r][j] * ngain;
-            float o[4];
+        auto body = [&](auto full_c) {
+            constexpr bool FULL = decltype(full_c)::value;
+            auto finish = [&](int r, int j, float (&acc)[4]) {
+                if (!FULL && (oy0 + r >= p.OH || ox + j >= p.OW)) return;
+                const float nzg = s_nz[r * FT_OW + px + j];
+                float o[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float a = fmaf(acc[k], sc[k], nzg + bs[k]);
-                if (fold) a = fmaxf(a, a * p.alpha);
-                else a *= ((a > 0.f) ? 1.f : p.alpha) * g_post;
-                a = fminf(fmaxf(a, -clamp_hi), clamp_hi);
-                o[k] = a * ns[k];
-            }
-            uint2 outv;
-            *reinterpret_cast<__nv_bfloat162*>(&outv.x) = __floats2bfloat162_rn(o[0], o[1]);
-            *reinterpret_cast<__nv_bfloat162*>(&outv.y) = __floats2bfloat162_rn(o[2], o[3]);
-            __stcs(reinterpret_cast<uint2*>(p.y + (((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox + j) * p.y_cs + cq * 4)), outv);
-        };
-        if (sep) {
-            float h[4][2][4];
-            auto hrow = [&](float (&dst)[2][4], int r) {
-                float v[5][4];
-#pragma unroll
-                for (int c = 0; c < 5; ++c) ld(r, px + c, v[c]);
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) dst[j][k] = fx[0] * v[j][k] + fx[1] * v[j + 1][k] + fx[2] * v[j + 2][k] + fx[3] * v[j + 3][k];
+                for (int k = 0; k < 4; ++k) {
+                    float a = fmaf(acc[k], sc[k], nzg + bs[k]);
+                    if (fold) a = fmaxf(a, a * alpha);
+                    else a *= ((a > 0.f) ? 1.f : alpha) * g_post;
+                    a = fminf(fmaxf(a, -clamp_hi), clamp_hi);
+                    o[k] = a * ns[k];
+                }
+                uint2 outv;
+                *reinterpret_cast<__nv_bfloat162*>(&outv.x) = __floats2bfloat162_rn(o[0], o[1]);
+                *reinterpret_cast<__nv_bfloat162*>(&outv.y) = __floats2bfloat162_rn(o[2], o[3]);
+                __stcs(reinterpret_cast<uint2*>(yrow + j * ycs), outv);
             };
-            hrow(h[0], 0); hrow(h[1], 1); hrow(h[2], 2);
+            if (sep) {
+                float h[4][2][4];
+                auto hrow = [&](float (&dst)[2][4], int r) {
+                    float v[5][4];
 #pragma unroll
-            for (int r = 0; r < FT_OH; ++r) {
-                hrow(h[(r + 3) & 3], r + 3);
+                    for (int c = 0; c < 5; ++c) ldi((uint32_t)((r * FT_IW + c) * 256), v[c]);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    float acc[4];
+                    for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        acc[k] = fy[0] * h[r & 3][j][k] + fy[1] * h[(r + 1) & 3][j][k] + fy[2] * h[(r + 2) & 3][j][k] + fy[3] * h[(r + 3) & 3][j][k];
-                    finish(r, j, acc);
+                        for (int k = 0; k < 4; ++k) dst[j][k] = fx[0] * v[j][k] + fx[1] * v[j + 1][k] + fx[2] * v[j + 2][k] + fx[3] * v[j + 3][k];
+                };
+                hrow(h[0], 0); hrow(h[1], 1); hrow(h[2], 2);
+#pragma unroll
+                for (int r = 0; r < FT_OH; ++r) {
+                    hrow(h[(r + 3) & 3], r + 3);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float acc[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            acc[k] = fy[0] * h[r & 3][j][k] + fy[1] * h[(r + 1) & 3][j][k] + fy[2] * h[(r + 2) & 3][j][k] + fy[3] * h[(r + 3) & 3][j][k];
+                        finish(r, j, acc);
+                    }
+                    yrow += yrow_step;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < FT_OH; ++r) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+#pragma unroll
+                            for (int bb = 0; bb < 4; ++bb) {
+                                float v[4];
+                                ldi((uint32_t)(((r + a) * FT_IW + j + bb) * 256), v);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) acc[k] = fmaf(f[a * 4 + bb], v[k], acc[k]);
+                            }
+                        finish(r, j, acc);
+                    }
+                    yrow += yrow_step;
                 }
             }
-        } else {
-#pragma unroll
-            for (int r = 0; r < FT_OH; ++r) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int bb = 0; bb < 4; ++bb) {
-                            float v[4];
-                            ld(r + a, px + j + bb, v);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[k] = fmaf(f[a * 4 + bb], v[k], acc[k]);
-                        }
-                    finish(r, j, acc);
-                }
-            }
-        }
+        };
+        if (full_tile) body(std::true_type{}); else body(std::false_type{});
         __syncthreads();                                            // everyone is done with buffer b (and s_epi) before it is refilled
     }
 }
@@ -347,7 +358,7 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
         const int tiles_x = (OW + FT_OW - 1) / FT_OW, tiles_y = (OH + FT_OH - 1) / FT_OH;
         const int64_t total = (int64_t)tiles_x * tiles_y * N;
         NBE_REQUIRE(total <= INT32_MAX, "fir_act_nhwc: too many tiles");
-        const size_t smem = 128 + 2 * ((FT_TILE_BYTES + 127) & ~127) + (3 * 128 + 16) * sizeof(float) + 64;
+        const size_t smem = 128 + 2 * ((FT_TILE_BYTES + 127) & ~127) + (3 * 128 + 16 + FT_OH * FT_OW) * sizeof(float) + 64;
         static std::once_flag once;
         static cudaError_t err = cudaSuccess;
         std::call_once(once, [] { err = cudaFuncSetAttribute(fir_act_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); });
