@@ -16,6 +16,7 @@
 //   full/empty mbarriers; tcgen05.commit releases a stage when the MMAs that read it retire.
 // * Two CTAs fit per SM (<= 113 KiB smem, 128 TMEM columns each) so one CTA's epilogue overlaps the other's MMAs.
 #include "tc_common.cuh"
+#include <algorithm>
 #include <mutex>
 #include <cstdlib>
 
@@ -174,14 +175,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 //    and kept in shared memory; the three horizontal taps are the same smem rows read through UMMA descriptors whose
 //    start address is shifted by kw pixels (kw * 128 B -- the 128-byte swizzle is a function of the absolute smem
 //    address, so a row-shifted start reads exactly what TMA wrote);
-//  * every weight tile (tap, chunk) is streamed once per work item through a 4-deep ring and feeds 8 MMAs
+//  * every weight tile (tap, chunk) is streamed once per work item through an 8-deep ring and feeds 8 MMAs
 //    (2 output rows x 4 K-steps) instead of 4;
+//  * the kernel runs on CTA PAIRS (cta_group::2, M = 256): each CTA of the pair owns its own work item and accumulators
+//    but holds only HALF of every weight tile (64 of the 128 output channels), which halves the weight traffic per SM;
 //  * accumulators are double-buffered in TMEM (2 x 2 x 128 columns = all 512), so the epilogue of item i overlaps
 //    the MMAs of item i+1; per-image epilogue vectors (demod, bias, next-layer styles) are staged in smem.
 constexpr int R_ABUF = 17 * 1024;                                  // 130 px x 128 B = 16640 B, padded to a 1 KiB multiple
 constexpr int R_AROW_BYTES = 130 * 128;
-constexpr int R_BSTAGES = 4;
-constexpr int R_BBYTES = 128 * 128;
+constexpr int R_BSTAGES = 8;
+constexpr int R_BBYTES = 64 * 128;                                  // this CTA's half (64 output channels) of a weight tile
 
 struct ConvRowParams {
     __nv_bfloat16* y;
@@ -197,7 +200,7 @@ struct ConvRowParams {
     float* img; float* uvs; int write_y;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvRowParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -205,70 +208,76 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint8_t* smem_b = smem + 8 * R_ABUF;                            // [R_BSTAGES][R_BBYTES]
     float* s_vec = reinterpret_cast<float*>(smem_b + R_BSTAGES * R_BBYTES);   // [6][128]: dcoef, bias, next_scale, 3 x modulated ToRGB weights of the current image
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + 6 * 128);
-    uint64_t* a_full = bars;            // [2]
+    uint64_t* a_full = bars;            // [2]   (the leader's is the live one: TMA of both CTAs completes on it)
     uint64_t* a_empty = bars + 2;       // [2]
     uint64_t* b_full = bars + 4;        // [R_BSTAGES]
     uint64_t* b_empty = bars + 4 + R_BSTAGES;
     uint64_t* acc_full = bars + 4 + 2 * R_BSTAGES;      // [2]
-    uint64_t* acc_empty = acc_full + 2;                 // [2]
+    uint64_t* acc_empty = acc_full + 2;                 // [2]   (the leader's: both CTAs' epilogue warps arrive on it)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int rank = (int)uniform_u32(cluster_ctarank());
+    const bool leader = rank == 0;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1);
-                                      mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+                                      mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 8); }
         for (int i = 0; i < R_BSTAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                             // barriers of BOTH CTAs are initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    // pair jp of the cluster: CTA r takes item 2 jp + r (the last pair may hold a dummy item: loaded, computed, never stored)
+    const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int pairs = (p.total_items + 1) >> 1;
 
     if (warp == 0) {
-        // ============================== TMA producer ==============================
+        // ============================== TMA producer (both CTAs) ==============================
         if (lane == 0) {
-            uint32_t a_phase[2] = {0, 0};
+            uint32_t a_phase = 0;
             int bs = 0; uint32_t b_phase = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            for (int jp = cid; jp < pairs; jp += n_clusters) {
+                const int item = min(2 * jp + rank, p.total_items - 1);
                 const int n = item / p.items_per_img;
                 const int rem = item - n * p.items_per_img;
                 const int yp = rem / p.items_per_row, xs = rem - yp * p.items_per_row;
                 const int y0 = yp * 2, x0 = xs * 128;
                 for (int c = 0; c < 2; ++c) {
-                    mbar_wait(smem_u32(&a_empty[c]), a_phase[c] ^ 1);
+                    mbar_wait_fast(smem_u32(&a_empty[c]), a_phase ^ 1);
                     const uint32_t full = smem_u32(&a_full[c]);
-                    mbar_expect_tx(full, 4 * R_AROW_BYTES);
+                    if (leader) mbar_expect_tx(full, 2 * 4 * R_AROW_BYTES);
                     for (int j = 0; j < 4; ++j)
-                        tma_load_4d(smem_u32(smem_a + (c * 4 + j) * R_ABUF), &tmap_a, full, c * 64, x0 + p.pad_off, y0 + j + p.pad_off, n);
-                    a_phase[c] ^= 1;
+                        tma_load_4d_2sm(smem_u32(smem_a + (c * 4 + j) * R_ABUF), &tmap_a, full, c * 64, x0 + p.pad_off, y0 + j + p.pad_off, n);
                     for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(smem_u32(&b_empty[bs]), b_phase ^ 1);
+                        mbar_wait_fast(smem_u32(&b_empty[bs]), b_phase ^ 1);
                         const uint32_t bf = smem_u32(&b_full[bs]);
-                        mbar_expect_tx(bf, R_BBYTES);
-                        tma_load_3d(smem_u32(smem_b + bs * R_BBYTES), &tmap_b, bf, c * 64, 0, tap);
+                        if (leader) mbar_expect_tx(bf, 2 * R_BBYTES);
+                        tma_load_3d_2sm(smem_u32(smem_b + bs * R_BBYTES), &tmap_b, bf, c * 64, rank * 64, tap);
                         if (++bs == R_BSTAGES) { bs = 0; b_phase ^= 1; }
                     }
                 }
+                a_phase ^= 1;
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer (whole warp, elected lane issues: see tc_common.cuh) ==============================
-        {
+        // ============================== MMA issuer (leader CTA; whole warp, elected lane issues: see tc_common.cuh) ==============================
+        if (leader) {
             const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a)), b_lo0 = umma_desc_lo(smem_u32(smem_b));
             const uint32_t idesc = p.idesc;
             uint32_t a_par = 0, acc_par0 = 0, acc_par1 = 0;
             int bs = 0; uint32_t b_phase = 0;
             int it = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+            for (int jp = cid; jp < pairs; jp += n_clusters, ++it) {
                 const int ab = it & 1;
-                // the epilogue has drained this accumulator pair
+                // the epilogues of both CTAs have drained this accumulator pair
                 if (ab) { mbar_wait_fast(smem_u32(&acc_empty[1]), acc_par1 ^ 1); acc_par1 ^= 1; }
                 else    { mbar_wait_fast(smem_u32(&acc_empty[0]), acc_par0 ^ 1); acc_par0 ^= 1; }
                 tcgen05_fence_after();
@@ -290,16 +299,16 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                 const uint32_t a_lo = a_lo0 + (uint32_t)(((c * 4 + r + kh) * R_ABUF + kw * 128) >> 4);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    umma_bf16_lo(d0 + (uint32_t)(r * 128), a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (c | tap | k) != 0);
+                                    umma_bf16_lo_2sm(d0 + (uint32_t)(r * 128), a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (c | tap | k) != 0);
                             }
-                            umma_commit(smem_u32(&b_empty[bs]));
+                            umma_commit_2sm(smem_u32(&b_empty[bs]));
                         }
                         if (++bs == R_BSTAGES) { bs = 0; b_phase ^= 1; }
                     }
-                    if (elect_one()) umma_commit(smem_u32(&a_empty[c]));             // the four input rows of this chunk may be overwritten
+                    if (elect_one()) umma_commit_2sm(smem_u32(&a_empty[c]));         // the four input rows of this chunk may be overwritten
                 }
                 a_par ^= 1;
-                if (elect_one()) umma_commit(smem_u32(&acc_full[ab]));
+                if (elect_one()) umma_commit_2sm(smem_u32(&acc_full[ab]));
             }
         }
     } else {
@@ -310,8 +319,10 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         uint32_t acc_phase[2] = {0, 0};
         int it = 0, cur_n = -1;
         const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        for (int jp = cid; jp < pairs; jp += n_clusters, ++it) {
             const int ab = it & 1;
+            const bool dummy = 2 * jp + rank >= p.total_items;
+            const int item = min(2 * jp + rank, p.total_items - 1);
             const int n = item / p.items_per_img;
             const int rem = item - n * p.items_per_img;
             const int yp = rem / p.items_per_row, xs = rem - yp * p.items_per_row;
@@ -332,7 +343,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             acc_phase[ab] ^= 1;
             tcgen05_fence_after();
 #pragma unroll 1
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < (dummy ? 0 : 2); ++r) {
                 const int oy = y0 + r;
                 float nz = 0.f;
                 if (p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
@@ -391,14 +402,14 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&acc_empty[ab])) : "memory");
+            if (lane == 0) mbar_arrive_leader(smem_u32(&acc_empty[ab]));
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                             // the peer's smem / TMEM stay alive until the leader's last MMA is done
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -650,7 +661,9 @@ static int conv_tc_impl(const void* x, const void* wq, void* y,
         NBE_REQUIRE(total <= INT32_MAX, "conv_tc: too many work items");
         r.total_items = (int)total;
         r.dcoef = dcoef; r.noise = noise; r.noise_sn = noise_sn; r.noise_gain = noise_gain;
-        r.bias = bias; r.alpha = alpha; r.gain = gain; r.clamp = clamp; r.next_scale = next_scale; r.idesc = p.idesc;
+        r.bias = bias; r.alpha = alpha; r.gain = gain; r.clamp = clamp; r.next_scale = next_scale;
+        // kind::f16, f32 accumulate, bf16 x bf16, K-major, N = 128, M = 256 (CTA pair)
+        r.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
         r.rgb_w = nullptr; r.rgb_styles = nullptr; r.rgb_bias = nullptr; r.rgb_colors = nullptr; r.rgb_clamp = -1.f;
         r.img = nullptr; r.uvs = nullptr; r.write_y = 1;
         if (rgb) {
@@ -668,7 +681,7 @@ static int conv_tc_impl(const void* x, const void* wq, void* y,
         {
             cuuint64_t dims[3] = {(cuuint64_t)Cin_pad, (cuuint64_t)Cout, 9};
             cuuint64_t strides[2] = {(cuuint64_t)Cin_pad * 2, (cuuint64_t)Cout * Cin_pad * 2};
-            cuuint32_t box[3] = {64, 128, 1};
+            cuuint32_t box[3] = {64, 64, 1};                        // half of the output channels per CTA of the pair
             int st = make_tmap(&tb, wq, 3, dims, strides, box, "weights");
             if (st) return st;
         }
@@ -679,7 +692,7 @@ static int conv_tc_impl(const void* x, const void* wq, void* y,
             row_err = cudaFuncSetAttribute(conv_tc_row128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         });
         if (row_err != cudaSuccess) return fail(NBE_ECUDA, "conv_tc: cudaFuncSetAttribute(row128): %s", cudaGetErrorString(row_err));
-        const int grid = total < kNumSMs ? (int)total : kNumSMs;
+        const int grid = (int)std::min<int64_t>(kNumSMs / 2, (total + 1) / 2) * 2;      // whole CTA pairs
         conv_tc_row128_kernel<<<grid, TC_THREADS, rsmem, (cudaStream_t)stream>>>(ta, tb, r);
         return launched("conv_tc_row128_kernel");
     }
