@@ -422,7 +422,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 // epilogue applies the folded-BatchNorm bias + LeakyReLU and writes the interior of the reflect-padded NHWC buffer.
 constexpr int E7T_TW = 16, E7T_TH = 8;                             // 16 x 8 = 128 output pixels per tile
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 enc_conv7x7_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wq, const float* __restrict__ bias,
                       __nv_bfloat16* __restrict__ y, int N, int H, int W, int Cout, int y_cs, float neg_slope, int preproc,
                       int tiles_x, int tiles_y, uint32_t idesc) {
@@ -514,26 +514,41 @@ enc_conv7x7_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restri
         tcgen05_fence_after();
         const int oy = ty0 + ly, ox = tx0 + lx;
         const bool ok = oy < H && ox < W;
-        __nv_bfloat16* yp = y + (((long long)n * (H + 2) + oy + 1) * (W + 2) + ox + 1) * y_cs;
+        // A pixel's channels are contiguous bytes of the output, but a pixel is owned by one lane: stored straight from the
+        // owning lanes every instruction touches 32 lines 16 bytes at a time.  The warp's 32 pixels x 64 channels go through
+        // its own quarter of the (now idle) A tile instead and leave as whole 128-byte lines.
+        const long long pix = ok ? ((long long)n * (H + 2) + oy + 1) * (W + 2) + ox + 1 : -1;
+        uint8_t* stg = smem_a + warp * 32 * 128;
         for (int c0 = 0; c0 < Cout; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-            if (ok) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (c0 + g * 8 >= Cout) break;
-                    int4 out;
-                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
+            for (int g = 0; g < 4; ++g) {
+                if (c0 + g * 8 >= Cout) break;
+                int4 out;
+                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float a = __uint_as_float(v[g * 8 + 2 * e]) + s_bias[c0 + g * 8 + 2 * e];
-                        float b = __uint_as_float(v[g * 8 + 2 * e + 1]) + s_bias[c0 + g * 8 + 2 * e + 1];
-                        a = a > 0.f ? a : a * neg_slope;
-                        b = b > 0.f ? b : b * neg_slope;
-                        o2[e] = __floats2bfloat162_rn(a, b);
-                    }
-                    *reinterpret_cast<int4*>(yp + c0 + g * 8) = out;
+                for (int e = 0; e < 4; ++e) {
+                    float a = __uint_as_float(v[g * 8 + 2 * e]) + s_bias[c0 + g * 8 + 2 * e];
+                    float b = __uint_as_float(v[g * 8 + 2 * e + 1]) + s_bias[c0 + g * 8 + 2 * e + 1];
+                    a = a > 0.f ? a : a * neg_slope;
+                    b = b > 0.f ? b : b * neg_slope;
+                    o2[e] = __floats2bfloat162_rn(a, b);
                 }
+                const int j = (c0 >> 3) + g;                         // 16-byte chunk of the pixel's 128-byte row
+                *reinterpret_cast<int4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = out;
+            }
+        }
+        __syncwarp();
+        {
+            const int chunks = Cout >> 3;                           // 16-byte chunks per pixel (<= 8)
+            const int rd_ch = lane & 7, rd_row0 = lane >> 3;
+#pragma unroll
+            for (int r8 = 0; r8 < 8; ++r8) {
+                const int row = r8 * 4 + rd_row0;
+                const long long rp = __shfl_sync(0xffffffffu, pix, row);
+                const int4 val = *reinterpret_cast<const int4*>(stg + row * 128 + ((rd_ch ^ (row & 7)) << 4));
+                if (rp >= 0 && rd_ch < chunks) *reinterpret_cast<int4*>(y + rp * y_cs + rd_ch * 8) = val;
             }
         }
         tcgen05_fence_before();
@@ -762,7 +777,7 @@ extern "C" int nbe_enc_conv7x7_tc_bf16(const float* x, const void* wq, const flo
     NBE_REQUIRE(total <= INT32_MAX, "enc_conv7x7_tc: too many tiles");
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const size_t smem = 1024 + 128 * 128 + 64 * 128 + (E7T_TH + 6) * (E7T_TW + 6) * 4 + 64 * 4 + 64;
-    int grid = kNumSMs * 4;
+    int grid = kNumSMs * 8;                                         // 8 CTAs per SM: each tile is a chain of barriers, the CTAs hide one another's latency
     if (total < grid) grid = (int)total;
     enc_conv7x7_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)wq, bias, (__nv_bfloat16*)y, N, H, W, Cout,
                                                                    y_cs, neg_slope, preproc, tiles_x, tiles_y, idesc);
