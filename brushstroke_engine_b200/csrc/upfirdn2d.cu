@@ -10,6 +10,8 @@
 //  * upfirdn2d_generic_kernel<T>: any filter size / up / down / padding / strides (incl. channels_last),
 //    one thread per output element.
 #include "common.cuh"
+#include <type_traits>
+#include <cstdlib>
 
 namespace nbe {
 
@@ -61,18 +63,22 @@ constexpr int ST_THREADS = 128;
 constexpr int ST_RPT = 8;                                               // output rows per thread
 
 template <class T> struct VecOut;                                       // VPT outputs packed into one 16-byte store
-template <> struct VecOut<float> { static constexpr int VPT = 4; };
+template <> struct VecOut<float> { static constexpr int VPT = 8; };          // two 16-byte stores
 template <> struct VecOut<__half> { static constexpr int VPT = 8; };
 template <> struct VecOut<__nv_bfloat16> { static constexpr int VPT = 8; };
 
 template <class T, int VPT>
 __device__ __forceinline__ void store_row(T* dst, const float (&acc)[VPT], int n_valid) {
+    constexpr int PER16 = 16 / (int)sizeof(T);                          // elements per 16-byte store
     if (n_valid == VPT && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        int4 v;
-        T* e = reinterpret_cast<T*>(&v);
 #pragma unroll
-        for (int k = 0; k < VPT; ++k) e[k] = Cvt<T>::st(acc[k]);
-        st_stream16(dst, v);
+        for (int v0 = 0; v0 < VPT; v0 += PER16) {
+            int4 v;
+            T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+            for (int k = 0; k < PER16; ++k) e[k] = Cvt<T>::st(acc[v0 + k]);
+            st_stream16(dst + v0, v);
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < VPT; ++k) if (k < n_valid) dst[k] = Cvt<T>::st(acc[k]);
@@ -103,10 +109,9 @@ __device__ __forceinline__ void up2_row(float (&acc)[VPT], const float (&rowA)[W
     }
 }
 
-template <class T, int UP>
+template <class T, int UP, int VPT>
 __global__ void __launch_bounds__(ST_THREADS)
 upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
-    constexpr int VPT = VecOut<T>::VPT;
     extern __shared__ __align__(16) uint8_t st_smem[];
     __shared__ float s_f[16];
     const T* xbase = (const T*)p.x;
@@ -130,14 +135,26 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
     const uintptr_t a_lo = gb_lo & ~uintptr_t(15);
     const uintptr_t t_lo = reinterpret_cast<uintptr_t>(xbase), t_hi = reinterpret_cast<uintptr_t>(xbase + (long long)n_planes * plane_elems);
     const int n_chunks = (int)((gb_hi - a_lo + 15) >> 4);
-    for (int i = threadIdx.x; i < n_chunks; i += ST_THREADS) {
+    // interior chunks: 4 independent 16-byte loads in flight per thread before the first shared-memory store
+    const bool all_inside = a_lo >= t_lo && a_lo + ((uintptr_t)n_chunks << 4) <= t_hi;
+    int i0 = threadIdx.x;
+    if (all_inside) {
+        for (; i0 + 3 * ST_THREADS < n_chunks; i0 += 4 * ST_THREADS) {
+            int4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ld_stream16(reinterpret_cast<const void*>(a_lo + ((uintptr_t)(i0 + u * ST_THREADS) << 4)));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) reinterpret_cast<int4*>(st_smem)[1 + i0 + u * ST_THREADS] = v[u];
+        }
+    }
+    for (int i = i0; i < n_chunks; i += ST_THREADS) {
         const uintptr_t ga = a_lo + ((uintptr_t)i << 4);
         if (ga >= t_lo && ga + 16 <= t_hi) {
-            reinterpret_cast<int4*>(st_smem)[i] = ld_stream16(reinterpret_cast<const void*>(ga));
+            reinterpret_cast<int4*>(st_smem)[1 + i] = ld_stream16(reinterpret_cast<const void*>(ga));
         } else {                                                      // chunk straddles the tensor's first / last bytes
             for (int k = 0; k < 16 / (int)sizeof(T); ++k) {
                 const uintptr_t ea = ga + k * sizeof(T);
-                reinterpret_cast<T*>(st_smem)[i * (16 / (int)sizeof(T)) + k] =
+                reinterpret_cast<T*>(st_smem)[(1 + i) * (16 / (int)sizeof(T)) + k] =
                     (ea >= t_lo && ea + sizeof(T) <= t_hi) ? *reinterpret_cast<const T*>(ea) : Cvt<T>::st(0.f);
             }
         }
@@ -147,7 +164,9 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
         s_f[threadIdx.x] = (p.flip ? p.f[a * 4 + b] : p.f[(3 - a) * 4 + (3 - b)]) * p.gain;
     }
     __syncthreads();
-    const T* sx = reinterpret_cast<const T*>(st_smem + (gb_lo - a_lo));                                // smem view of element e_lo
+    // chunk 0 of the buffer is a guard: edge threads over-read up to 3 elements to the left of the staged range (and to
+    // the right, into the tail guard) and then zero what lies outside the row -- no per-element predicate on the loads
+    const T* sx = reinterpret_cast<const T*>(st_smem + 16 + (gb_lo - a_lo));                                // smem view of element e_lo
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = s_f[i];
@@ -178,16 +197,28 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
     if (UP == 1) {
         constexpr int WIN = VPT + 3;
         const int ix0 = ox0 - p.padx0;
+        const int iy0 = ry0 - p.pady0;
+        const int W = p.W;
+        // loads are unconditional (guards on both sides of the staged range); only threads whose window hangs over a row
+        // end zero the 1..3 elements outside it, rows outside the staged range are zero rows
+        const int jl = ix0 < 0 ? -ix0 : 0;                                  // first valid j
+        const int jh = ix0 + WIN > W ? W - ix0 : WIN;                       // one past the last valid j
         auto load_in = [&](float (&dst)[WIN], int iy) {
-            const bool rok = iy >= r_lo && iy < r_hi;
-            const T* rp = sp + (long long)iy * p.W;
+            if (iy >= r_lo && iy < r_hi) {
+                const T* rp = sp + (long long)iy * W + ix0;
 #pragma unroll
-            for (int j = 0; j < WIN; ++j) {
-                const int ix = ix0 + j;
-                dst[j] = (rok && ix >= 0 && ix < p.W) ? Cvt<T>::ld(rp[ix]) : 0.f;
+                for (int j = 0; j < WIN; ++j) dst[j] = Cvt<T>::ld(rp[j]);
+                if (jl > 0 || jh < WIN) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) if (j < jl) dst[j] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < WIN; ++j) if (j >= jh) dst[j] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < WIN; ++j) dst[j] = 0.f;
             }
         };
-        const int iy0 = ry0 - p.pady0;
         if (sep) {
             float h[4][VPT];                                                // horizontally filtered input rows (sliding window)
             auto hrow = [&](float (&dst)[VPT], int iy) {
@@ -197,16 +228,17 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
                 for (int k = 0; k < VPT; ++k) dst[k] = fx[0] * in[k] + fx[1] * in[k + 1] + fx[2] * in[k + 2] + fx[3] * in[k + 3];
             };
             hrow(h[0], iy0); hrow(h[1], iy0 + 1); hrow(h[2], iy0 + 2);
+            T* yrow = yp + (long long)ry0 * p.OW + ox0;
 #pragma unroll
             for (int r = 0; r < ST_RPT; ++r) {
-                const int oy = ry0 + r;
-                if (oy >= row_end) break;
+                if (ry0 + r >= row_end) break;
                 hrow(h[(r + 3) & 3], iy0 + r + 3);
                 float acc[VPT];
 #pragma unroll
                 for (int k = 0; k < VPT; ++k)
                     acc[k] = fy[0] * h[r & 3][k] + fy[1] * h[(r + 1) & 3][k] + fy[2] * h[(r + 2) & 3][k] + fy[3] * h[(r + 3) & 3][k];
-                store_row<T, VPT>(yp + (long long)oy * p.OW + ox0, acc, n_valid);
+                store_row<T, VPT>(yrow, acc, n_valid);
+                yrow += p.OW;
             }
         } else {
             float win[4][WIN];
@@ -229,35 +261,61 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
             }
         }
     } else {
+        // up = 2: output row oy reads input rows iyA = (oy - pady0 + a0) >> 1 and iyA + 1 with the taps of row parity a0; the
+        // ST_RPT output rows of a thread touch ST_RPT / 2 + 2 input rows, each loaded ONCE into a sliding register window
         constexpr int WIN = VPT / 2 + 2;
+        constexpr int NR = ST_RPT / 2 + 2;
         const int ixb = (ox0 - p.padx0) >> 1;
-#pragma unroll 1
-        for (int oy = ry0; oy < row_end; ++oy) {
-            const int u0 = oy - p.pady0;
-            const int a0 = u0 & 1;
-            const int iyA = (u0 + a0) >> 1;
-            float rowA[WIN], rowB[WIN];
-            const bool okA = iyA >= r_lo && iyA < r_hi, okB = iyA + 1 >= r_lo && iyA + 1 < r_hi;
+        const int W = p.W;
+        const int u00 = ry0 - p.pady0;
+        const int iy_first = (u00 + (u00 & 1)) >> 1;                       // first input row of the thread's first output row
+        const int jl = ixb < 0 ? -ixb : 0;
+        const int jh = ixb + WIN > W ? W - ixb : WIN;
+        float rows[NR][WIN];
 #pragma unroll
-            for (int j = 0; j < WIN; ++j) {
-                const int ix = ixb + j;
-                const bool cok = ix >= 0 && ix < p.W;
-                rowA[j] = (cok && okA) ? Cvt<T>::ld(sp[(long long)iyA * p.W + ix]) : 0.f;
-                rowB[j] = (cok && okB) ? Cvt<T>::ld(sp[(long long)(iyA + 1) * p.W + ix]) : 0.f;
+        for (int q = 0; q < NR; ++q) {
+            const int iy = iy_first + q;
+            if (iy >= r_lo && iy < r_hi) {
+                const T* rp = sp + (long long)iy * W + ixb;
+#pragma unroll
+                for (int j = 0; j < WIN; ++j) rows[q][j] = Cvt<T>::ld(rp[j]);
+                if (jl > 0 || jh < WIN) {
+#pragma unroll
+                    for (int j = 0; j < WIN; ++j) if (j < jl || j >= jh) rows[q][j] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < WIN; ++j) rows[q][j] = 0.f;
             }
+        }
+        // column parity pi = (ox0 - padx0) & 1 is uniform across the CTA (ox0 is a multiple of VPT): with it fixed,
+        // the tap parity b0 = (pi + k) & 1 and the window slot j0 = (k + pi + b0) >> 1 are compile-time per k.
+        const int pi = (ox0 - p.padx0) & 1;
+        const int par0 = u00 & 1;                                          // row parity of the first output row (uniform per launch)
+        T* yrow = yp + (long long)ry0 * p.OW + ox0;
+#pragma unroll
+        for (int r = 0; r < ST_RPT; ++r) {
+            if (ry0 + r >= row_end) break;
             float acc[VPT];
-            // column parity pi = (ox0 - padx0) & 1 is uniform across the CTA (ox0 is a multiple of VPT): with it fixed,
-            // the tap parity b0 = (pi + k) & 1 and the window slot j0 = (k + pi + b0) >> 1 are compile-time per k.
-            if (((ox0 - p.padx0) & 1) == 0) up2_row<VPT, WIN, 0>(acc, rowA, rowB, f, a0);
-            else                            up2_row<VPT, WIN, 1>(acc, rowA, rowB, f, a0);
-            store_row<T, VPT>(yp + (long long)oy * p.OW + ox0, acc, n_valid);
+            // q = (u0 + a0) / 2 - iy_first with u0 = u00 + r, a0 = u0 & 1: compile-time per (r, par0)
+            if (par0 == 0) {
+                constexpr int dummy = 0; (void)dummy;
+                const int a0 = r & 1, q = (r + a0) >> 1;
+                if (pi == 0) up2_row<VPT, WIN, 0>(acc, rows[q], rows[q + 1], f, a0);
+                else         up2_row<VPT, WIN, 1>(acc, rows[q], rows[q + 1], f, a0);
+            } else {
+                const int a0 = (r + 1) & 1, q = (r + 1 + a0) / 2 - 1;
+                if (pi == 0) up2_row<VPT, WIN, 0>(acc, rows[q], rows[q + 1], f, a0);
+                else         up2_row<VPT, WIN, 1>(acc, rows[q], rows[q + 1], f, a0);
+            }
+            store_row<T, VPT>(yrow, acc, n_valid);
+            yrow += p.OW;
         }
     }
 }
 
 template <class T>
-static bool staged_geometry(const UpfirdnParams& p, StagedGeom& g) {
-    constexpr int VPT = VecOut<T>::VPT;
+static bool staged_geometry(const UpfirdnParams& p, StagedGeom& g, int VPT) {
     g.cg = (p.OW + VPT - 1) / VPT;
     if (g.cg > ST_THREADS) return false;
     const int rg_plane = (p.OH + ST_RPT - 1) / ST_RPT;
@@ -265,8 +323,8 @@ static bool staged_geometry(const UpfirdnParams& p, StagedGeom& g) {
     if (g.cg * rg_plane * 2 <= ST_THREADS) {                          // several whole planes per CTA
         g.ppc = ST_THREADS / (g.cg * rg_plane);
         g.rg = rg_plane; g.strip = p.OH; g.strips = 1;
-        while (g.ppc > 1 && (long long)g.ppc * p.H * p.W * es + 32 > 96 * 1024) --g.ppc;
-        g.smem_bytes = (int)((long long)g.ppc * p.H * p.W * es + 32);
+        while (g.ppc > 1 && (long long)g.ppc * p.H * p.W * es + 80 > 96 * 1024) --g.ppc;
+        g.smem_bytes = (int)((long long)g.ppc * p.H * p.W * es + 80);
     } else {
         g.ppc = 1;
         g.rg = ST_THREADS / g.cg;
@@ -274,7 +332,7 @@ static bool staged_geometry(const UpfirdnParams& p, StagedGeom& g) {
         g.strip = g.rg * ST_RPT;
         g.strips = (p.OH + g.strip - 1) / g.strip;
         const int in_rows = (p.upy == 1) ? g.strip + 3 : g.strip / 2 + 3;
-        g.smem_bytes = (int)((long long)in_rows * p.W * es + 32);
+        g.smem_bytes = (int)((long long)in_rows * p.W * es + 80);
     }
     return g.smem_bytes <= 96 * 1024;
 }
@@ -282,11 +340,19 @@ static bool staged_geometry(const UpfirdnParams& p, StagedGeom& g) {
 template <class T>
 static int run_typed(const UpfirdnParams& p, bool tiled_ok, cudaStream_t s) {
     StagedGeom g;
-    if (tiled_ok && staged_geometry<T>(p, g)) {
+    // outputs per thread and row: 8 (one or two 16-byte stores); 4-byte types filtering at the input resolution keep 4 --
+    // half the shared memory per CTA, twice the CTAs per SM to hide the staging latency
+    static const char* vpt_env = getenv("NBE_UPF_VPT");
+    int vpt = VecOut<T>::VPT;
+    if (sizeof(T) == 4 && p.upx == 1) vpt = 4;
+    if (sizeof(T) == 4 && vpt_env) vpt = atoi(vpt_env) == 4 ? 4 : 8;
+    if (tiled_ok && staged_geometry<T>(p, g, vpt)) {
         const int n_planes = p.N * p.C;
         const int64_t blocks = g.ppc > 1 ? (n_planes + g.ppc - 1) / g.ppc : (int64_t)n_planes * g.strips;
         if (blocks <= INT32_MAX) {
-            auto kern = (p.upx == 1) ? upfirdn2d_staged_kernel<T, 1> : upfirdn2d_staged_kernel<T, 2>;
+            void (*kern)(UpfirdnParams, StagedGeom, int);
+            if (sizeof(T) == 4 && vpt == 4) kern = (p.upx == 1) ? upfirdn2d_staged_kernel<T, 1, (sizeof(T) == 4 ? 4 : 8)> : upfirdn2d_staged_kernel<T, 2, (sizeof(T) == 4 ? 4 : 8)>;
+            else kern = (p.upx == 1) ? upfirdn2d_staged_kernel<T, 1, 8> : upfirdn2d_staged_kernel<T, 2, 8>;
             if (g.smem_bytes > 48 * 1024) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
                 if (e != cudaSuccess) return fail(NBE_ECUDA, "upfirdn2d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -199,6 +199,11 @@ def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOption
     start, end = shard_crops(job.crops, world, rank)
     dev = engine.device
     tiles_local = torch.empty((end - start, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
+    # even batches: a short tail batch costs almost a full launch sequence (276 patches -> 1 x 276, not 256 + 20)
+    n_batches = max(1, -(-(end - start) // batch_size))
+    if (end - start) <= batch_size * 5 // 4:
+        n_batches = 1
+    batch_size = max(1, -(-(end - start) // n_batches))
     for b0 in range(start, end, batch_size):
         b1 = min(b0 + batch_size, end)
         geom = job.gather(b0, b1)
