@@ -142,6 +142,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-canvas', action='store_true')
+    ap.add_argument('--no-blend', action='store_true', help='skip the feature-blending (level 2) canvas leg')
     ap.add_argument('--canvas', type=int, default=4096, help='side of the synthetic canvas for the stylization leg')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (profiling runs under ncu)')
     args = ap.parse_args()
@@ -262,6 +263,21 @@ def main():
                     htimes.append((time.perf_counter() - t0) * 1e3)
         canvas_ms = float(np.median(ctimes))
         canvas_host_ms = float(np.median(htimes))
+        # the reference's own stylization script runs with --feature_blending_level=2 (scripts/neube_stylize.sh): patches then
+        # depend on their raster predecessors; wavefront-batched on one GPU (rank 0 only, the other ranks idle)
+        blend_ms = None
+        if rank == 0 and not args.no_blend:
+            btimes = []
+            with torch.no_grad():
+                for rep in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    out = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, feature_blending_level=2, z_per_patch=z_pp, to_host=False)
+                    torch.cuda.synchronize()
+                    if rep > 0:
+                        btimes.append((time.perf_counter() - t0) * 1e3)
+            blend_ms = float(np.median(btimes))
+        barrier()
         n_canvas_patches = len(job_crops)
 
     times = torch.tensor([ms_total, e2e_s * 1e3, canvas_ms if canvas_ms is not None else 0.0], dtype=torch.float64, device=dev)
@@ -313,6 +329,7 @@ def main():
         }
         if canvas_ms is not None:
             line['canvas'] = {'size': args.canvas, 'patches': n_canvas_patches, 'ms': canvas_ms, 'ms_host_to_host': canvas_host_ms, 'n_gpus': world,
+                              'ms_feature_blending_level2_1gpu': blend_ms,
                               'what': 'uint8 guidance on the device -> crops -> encoder+generator+composite (8-anchor z interpolation) -> '
                                       'tile gather to rank 0 (NCCL when n_gpus > 1) -> placed uint8 canvas on rank 0 (SURVEY 8d config 5); '
                                       'ms_host_to_host adds the guidance upload and the canvas download (rank-0 wall clock)'}

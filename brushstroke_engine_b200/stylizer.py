@@ -21,6 +21,7 @@ Execution on B200:
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -141,6 +142,15 @@ class CanvasJob:
                   _lib.ptr(self.d_crops[start:end]), _lib.ptr(out), n, self.patch, _lib.stream())
         return out
 
+    def gather_indices(self, d_idx: torch.Tensor) -> torch.Tensor:
+        """``gather`` for an arbitrary list of crop indices (int64 tensor on the device)."""
+        n = int(d_idx.shape[0])
+        crops = self.d_crops[d_idx].contiguous()
+        out = torch.empty((n, 1, self.patch, self.patch), dtype=torch.float32, device=self.engine.device)
+        _lib.call('nbe_gather_geom_patches', _lib.ptr(self.d_geom), self.canvas_h, self.canvas_w, _lib.ptr(crops), _lib.ptr(out), n,
+                  self.patch, _lib.stream())
+        return out
+
     def owner_map(self) -> torch.Tensor:
         owner = torch.empty((self.canvas_h, self.canvas_w), dtype=torch.int32, device=self.engine.device)
         _lib.call('nbe_tile_owner_map', _lib.ptr(self.d_tiles_yx), len(self.crops), self.tile, _lib.ptr(owner),
@@ -193,7 +203,8 @@ def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOption
     if feature_blending_level > 0:
         if world > 1:
             raise RuntimeError('stylize: feature blending makes patches raster-dependent; run it on one GPU')
-        canvas = _stylize_blended(engine, job, opts, feature_blending_level, z_per_patch)
+        blend = _stylize_blended if os.environ.get('NBE_BLEND_SEQUENTIAL') else _stylize_blended_wavefront
+        canvas = blend(engine, job, opts, feature_blending_level, z_per_patch)
         out = job.finish(canvas, on_white, to_host)
         return (out, job) if return_job else out
     start, end = shard_crops(job.crops, world, rank)
@@ -300,4 +311,97 @@ def _stylize_blended(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOpt
         features[..., ys:ys + res, xs:xs + res][um] = feat[um]
         ty, tx = (y // down * down) + job.crop_margin, (x // down * down) + job.crop_margin
         canvas[ty:ty + job.tile, tx:tx + job.tile] = tiles[0]                 # raster order = last writer wins
+    return canvas
+
+
+def blending_wavefronts(crops_yx: np.ndarray, patch: int):
+    """Group raster-ordered crops into wavefronts of mutually independent patches.
+
+    Patch n depends on the earlier patches whose 128-px windows overlap its own (it reads the features they saved) and
+    must run before the later ones that overlap it.  On the regular crop grid (stride = patch - 2 * margin > patch / 2)
+    a window only overlaps its 8 grid neighbours, so with grid coordinates (r, c) the patches of one anti-diagonal
+    ``2 r + c = const`` neither read nor write each other's windows, and every raster predecessor among the neighbours --
+    (r, c-1), (r-1, c-1), (r-1, c), (r-1, c+1) -- lies on an earlier one.  Executing the diagonals in order, each as one
+    batch, therefore reproduces the sequential raster loop of brush.py:190-242 exactly.
+    Returns a list of int64 index arrays (raster indices, ascending inside a wavefront)."""
+    ys = np.unique(crops_yx[:, 0])
+    xs = np.unique(crops_yx[:, 1])
+    if (len(ys) > 1 and np.diff(ys).min() * 2 <= patch) or (len(xs) > 1 and np.diff(xs).min() * 2 <= patch):
+        raise RuntimeError('blending_wavefronts: crop stride must exceed half a patch (windows overlap more than their neighbours)')
+    r = np.searchsorted(ys, crops_yx[:, 0])
+    c = np.searchsorted(xs, crops_yx[:, 1])
+    w = 2 * r + c
+    order = np.argsort(w, kind='stable')
+    bounds = np.flatnonzero(np.diff(w[order])) + 1
+    return [g.astype(np.int64) for g in np.split(order, bounds)]
+
+
+def _stylize_blended_wavefront(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOptions, level: int, z_per_patch):
+    """Feature blending with the raster semantics of ``_stylize_blended`` (brush.py:33-92, 190-242), executed one
+    anti-diagonal wavefront of independent patches at a time (see ``blending_wavefronts``): ~2 rows + cols batched
+    generator calls instead of rows x cols single-patch ones.  The feature canvas starts as zeros with an all-False
+    mask (alpha = 1 wherever nothing was saved yet)."""
+    dev = engine.device
+    down = 2 ** (level - 1)
+    res = engine.patch_width // down
+    fh, fw = int(math.ceil(job.canvas_h / down)), int(math.ceil(job.canvas_w / down))
+    margin = 16 // down                                   # PaintingHelper.feature_blending_margin = 16
+    cm = job.crop_margin // down
+    base_alpha = dirty_area_alpha(res, margin, cm, dev)
+    base_update = base_alpha > 0.99
+    inner = torch.ones((res, res), dtype=torch.bool, device=dev)
+    if cm > 0:
+        inner[:cm, :] = False
+        inner[-cm:, :] = False
+        inner[:, :cm] = False
+        inner[:, -cm:] = False
+    C = engine.G.cfg.channels(res)
+    features = torch.zeros((C, fh + res, fw + res), dtype=torch.float32, device=dev)      # + res: windows never leave the buffer
+    mask = torch.zeros((fh + res, fw + res), dtype=torch.bool, device=dev)
+    snapped = (job.crops_yx // down) * down                                               # brush.py:253-258
+    tiles_yx = torch.from_numpy(np.ascontiguousarray(snapped + job.crop_margin).astype(np.int32)).to(dev)
+    n_crops = len(job.crops)
+    tiles_all = torch.empty((n_crops, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
+    ar = torch.arange(res, device=dev)
+    waves = []
+    for idx in blending_wavefronts(job.crops_yx, engine.patch_width):
+        # the raster loop does not blend its very first patch (no feature canvas yet, brush.py:196-201): on the bf16 path
+        # "blend with alpha 0" and "no blend" round differently (the un-blended layer fuses the next layer's modulation),
+        # so patch 0 runs on its own, un-blended, exactly as in the sequential loop
+        if idx[0] == 0 and len(idx) > 1:
+            waves += [idx[:1], idx[1:]]
+        else:
+            waves.append(idx)
+    for idx in waves:
+        n = len(idx)
+        d_idx = torch.from_numpy(idx).to(dev)
+        fy = torch.from_numpy(snapped[idx, 0] // down).to(dev)
+        fx = torch.from_numpy(snapped[idx, 1] // down).to(dev)
+        rows = (fy[:, None] + ar[None, :])[:, :, None].expand(n, res, res)                # [n,res,res] feature-canvas rows
+        cols = (fx[:, None] + ar[None, :])[:, None, :].expand(n, res, res)
+        m = mask[rows, cols]                                                              # [n,res,res]
+        update = (base_update[None] | (m & (base_alpha > 0)[None])) & inner[None]
+        alpha = torch.where(m, base_alpha[None].expand(n, -1, -1), torch.ones((), device=dev))
+        saved = features[:, rows, cols].permute(1, 0, 2, 3)                               # [n,C,res,res]
+        geom = job.gather_indices(d_idx)
+        pos = job.d_crops[d_idx].to(torch.int64)
+        o = GanBrushOptions()
+        o.__dict__.update(opts.__dict__)
+        if z_per_patch is not None:
+            o.style_z, o.style_ws = z_per_patch[d_idx], None
+        o.position = pos
+        blended = {} if idx[0] == 0 else {res: _Blended(saved, (1 - alpha)[:, None])}
+        tiles, raw = engine.render_tiles(geom, o, crop_margin=job.crop_margin, return_features=[res], blended_features=blended)
+        feat = raw[f'features{res}']                                                      # [n,C,res,res]
+        # windows of one wavefront are disjoint: plain indexed writes, no ordering issue
+        mask[rows[update], cols[update]] = True
+        un, uy, ux = torch.nonzero(update, as_tuple=True)
+        features[:, fy[un] + uy, fx[un] + ux] = feat[un, :, uy, ux].t()
+        tiles_all[d_idx] = tiles
+    canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
+    owner = torch.empty((job.canvas_h, job.canvas_w), dtype=torch.int32, device=dev)
+    _lib.call('nbe_tile_owner_map', _lib.ptr(tiles_yx), n_crops, job.tile, _lib.ptr(owner), job.canvas_h, job.canvas_w, _lib.stream())
+    order = torch.arange(n_crops, dtype=torch.int32, device=dev)
+    _lib.call('nbe_place_tiles', _lib.ptr(tiles_all), _lib.ptr(tiles_yx), _lib.ptr(order), n_crops, job.tile, _lib.ptr(owner),
+              _lib.ptr(canvas), job.canvas_h, job.canvas_w, _lib.stream())
     return canvas

@@ -138,3 +138,21 @@ def test_render_patches_host_equals_device_path(engines):
     o.position = pos.to(DEV)
     tiles, _ = eng.render_tiles(job.gather(0, n), o, crop_margin=10)
     assert host.shape == (n, 108, 108, 4) and torch.equal(host, tiles.cpu())
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('level', [1, 2, 3])
+def test_blending_wavefronts_equal_raster_loop(engines, mode, level):
+    """The wavefront-batched feature-blending scheduler reproduces the sequential raster loop bit for bit
+    (brush.py:190-242): same kernels on the same data, only the launch grouping differs."""
+    from brushstroke_engine_b200 import stylizer
+    eng = engines[mode]
+    guidance = synthetic.synthetic_guidance(450, 560, num_lines=24, seed=3)          # 5 x 6 crops
+    opts = _opts(P.style_z_from_seed(17), '17')
+    job = stylizer.CanvasJob(eng, guidance, 10, 'all')
+    assert len(job.crops) >= 20
+    with torch.no_grad():
+        seq = stylizer._stylize_blended(eng, job, opts, level, None)
+        wav = stylizer._stylize_blended_wavefront(eng, job, opts, level, None)
+    assert torch.equal(seq, wav)
+    assert int((wav[..., 3] > 0).sum()) > 1000                                       # something was painted

@@ -83,3 +83,28 @@ def test_two_rank_gather_reassembles_canvas(tmp_path):
     port = 29500 + (os.getpid() % 500)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert bool(np.load(os.path.join(str(tmp_path), 'ok.npy'))[0])
+
+
+def test_blending_wavefronts_respect_raster_dependencies():
+    """Every raster-earlier patch whose window overlaps a patch lies in an earlier wavefront, and patches that share a
+    wavefront do not overlap (so a wavefront can run as one batch)."""
+    import numpy as np
+    from brushstroke_engine_b200.stylizer import blending_wavefronts
+    ys, xs = np.meshgrid(np.arange(6) * 108, np.arange(9) * 108, indexing='ij')
+    yx = np.stack([ys.ravel(), xs.ravel()], axis=1)
+    keep = np.ones(len(yx), dtype=bool); keep[[7, 20, 21, 33]] = False               # 'auto' stitching drops empty crops
+    yx = yx[keep]
+    waves = blending_wavefronts(yx, 128)
+    assert sorted(np.concatenate(waves).tolist()) == list(range(len(yx)))
+    wave_of = np.empty(len(yx), dtype=int)
+    for w, idx in enumerate(waves):
+        wave_of[idx] = w
+    overlap = lambda a, b: abs(yx[a, 0] - yx[b, 0]) < 128 and abs(yx[a, 1] - yx[b, 1]) < 128
+    for a in range(len(yx)):
+        for b in range(a):
+            if overlap(a, b):
+                assert wave_of[b] < wave_of[a]
+    assert len(waves) <= 2 * 6 + 9
+    import pytest
+    with pytest.raises(RuntimeError):
+        blending_wavefronts(np.array([[0, 0], [0, 60]]), 128)                        # stride <= half a patch
