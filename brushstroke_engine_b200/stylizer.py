@@ -372,32 +372,43 @@ def _stylize_blended_wavefront(engine: TriadPaintEngine, job: CanvasJob, opts: G
             waves += [idx[:1], idx[1:]]
         else:
             waves.append(idx)
+    # one upload for the whole schedule; the loop below never synchronises with the host
+    d_order = torch.from_numpy(np.concatenate(waves)).to(dev)
+    d_fy = torch.from_numpy(np.ascontiguousarray(snapped[:, 0] // down)).to(dev)[d_order]
+    d_fx = torch.from_numpy(np.ascontiguousarray(snapped[:, 1] // down)).to(dev)[d_order]
+    d_pos = job.d_crops.to(torch.int64)[d_order]
+    d_cropsel = job.d_crops[d_order].contiguous()
+    z_sel = z_per_patch[d_order] if z_per_patch is not None else None
+    alpha_pos = (base_alpha > 0)[None]
+    one = torch.ones((), device=dev)
+    off = 0
     for idx in waves:
         n = len(idx)
-        d_idx = torch.from_numpy(idx).to(dev)
-        fy = torch.from_numpy(snapped[idx, 0] // down).to(dev)
-        fx = torch.from_numpy(snapped[idx, 1] // down).to(dev)
+        sl = slice(off, off + n)
+        off += n
+        fy, fx = d_fy[sl], d_fx[sl]
         rows = (fy[:, None] + ar[None, :])[:, :, None].expand(n, res, res)                # [n,res,res] feature-canvas rows
         cols = (fx[:, None] + ar[None, :])[:, None, :].expand(n, res, res)
         m = mask[rows, cols]                                                              # [n,res,res]
-        update = (base_update[None] | (m & (base_alpha > 0)[None])) & inner[None]
-        alpha = torch.where(m, base_alpha[None].expand(n, -1, -1), torch.ones((), device=dev))
+        update = (base_update[None] | (m & alpha_pos)) & inner[None]
+        alpha = torch.where(m, base_alpha[None], one)
         saved = features[:, rows, cols].permute(1, 0, 2, 3)                               # [n,C,res,res]
-        geom = job.gather_indices(d_idx)
-        pos = job.d_crops[d_idx].to(torch.int64)
+        geom = torch.empty((n, 1, job.patch, job.patch), dtype=torch.float32, device=dev)
+        _lib.call('nbe_gather_geom_patches', _lib.ptr(job.d_geom), job.canvas_h, job.canvas_w, _lib.ptr(d_cropsel[sl]), _lib.ptr(geom), n,
+                  job.patch, _lib.stream())
         o = GanBrushOptions()
         o.__dict__.update(opts.__dict__)
-        if z_per_patch is not None:
-            o.style_z, o.style_ws = z_per_patch[d_idx], None
-        o.position = pos
+        if z_sel is not None:
+            o.style_z, o.style_ws = z_sel[sl], None
+        o.position = d_pos[sl]
         blended = {} if idx[0] == 0 else {res: _Blended(saved, (1 - alpha)[:, None])}
         tiles, raw = engine.render_tiles(geom, o, crop_margin=job.crop_margin, return_features=[res], blended_features=blended)
         feat = raw[f'features{res}']                                                      # [n,C,res,res]
-        # windows of one wavefront are disjoint: plain indexed writes, no ordering issue
-        mask[rows[update], cols[update]] = True
-        un, uy, ux = torch.nonzero(update, as_tuple=True)
-        features[:, fy[un] + uy, fx[un] + ux] = feat[un, :, uy, ux].t()
-        tiles_all[d_idx] = tiles
+        # windows of one wavefront are disjoint: whole windows are written back (new value where `update`, old elsewhere),
+        # which needs no data-dependent index list and therefore no host synchronisation
+        mask[rows, cols] = m | update
+        features[:, rows, cols] = torch.where(update[:, None], feat, saved).permute(1, 0, 2, 3)
+        tiles_all[d_order[sl]] = tiles
     canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
     owner = torch.empty((job.canvas_h, job.canvas_w), dtype=torch.int32, device=dev)
     _lib.call('nbe_tile_owner_map', _lib.ptr(tiles_yx), n_crops, job.tile, _lib.ptr(owner), job.canvas_h, job.canvas_w, _lib.stream())
