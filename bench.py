@@ -280,6 +280,24 @@ def main():
         barrier()
         n_canvas_patches = len(job_crops)
 
+    # ---- interactive use: one 128^2 stroke patch per call through the reference-facing render_stroke
+    #      (host uint8 patch in, host uint8 RGBA out; wall clock, rank 0) ----
+    interactive_ms = None
+    if rank == 0 and not args.no_e2e:
+        from brushstroke_engine_b200.engine import GanBrushOptions as _GBO
+        patch = np.ascontiguousarray(((1.0 - synthetic.synthetic_patch(128, seed=5)[0, 0]) * 255).astype(np.uint8)[:, :, None])   # [W,W,1], 255 = stroke
+        iopts = _GBO()
+        iopts.set_style(torch.from_numpy(np.random.RandomState(594).randn(1, 64)).to(dev), '594')
+        iopts.position = torch.tensor([[88, 176]], device=dev)
+        lat = []
+        with torch.no_grad():
+            for i in range(60):
+                t0 = time.perf_counter()
+                engine.render_stroke(patch, None, iopts)
+                if i >= 10:
+                    lat.append((time.perf_counter() - t0) * 1e3)
+        interactive_ms = float(np.median(lat))
+    barrier()
     times = torch.tensor([ms_total, e2e_s * 1e3, canvas_ms if canvas_ms is not None else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -327,6 +345,8 @@ def main():
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
         }
+        if interactive_ms is not None:
+            line['interactive'] = {'ms_per_stroke_patch': interactive_ms, 'what': 'TriadPaintEngine.render_stroke, batch 1, host uint8 patch -> host uint8 RGBA, wall-clock median of 50 (rank 0)'}
         if canvas_ms is not None:
             line['canvas'] = {'size': args.canvas, 'patches': n_canvas_patches, 'ms': canvas_ms, 'ms_host_to_host': canvas_host_ms, 'n_gpus': world,
                               'ms_feature_blending_level2_1gpu': blend_ms,
