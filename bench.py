@@ -184,9 +184,13 @@ def main():
         tiles, _ = engine.render_tiles(g, opts, crop_margin=10)
         return tiles
 
+    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+
     def e2e_step(i):
+        # two pinned result buffers: the download of batch i overlaps the compute of batch i+1; every result is complete on
+        # the host (event.synchronize) before its buffer is handed out again
         p_, z, pos = hsets[i % len(hsets)]
-        return engine.render_patches_host(p_, z, pos, crop_margin=10, out=out_host)
+        return engine.render_patches_host(p_, z, pos, crop_margin=10, out=out_hosts[i & 1], wait=False)[1]
 
     def barrier():
         if world > 1:
@@ -218,11 +222,16 @@ def main():
         e2e_s = float('nan')
         if not args.no_e2e:
             for i in range(3):
-                e2e_step(i)
+                e2e_step(i).synchronize()
             barrier()
             t0 = time.perf_counter()
+            pending = None
             for i in range(args.steps):
-                e2e_step(i)
+                ev = e2e_step(i)
+                if pending is not None:
+                    pending.synchronize()                               # batch i-1 is on the host
+                pending = ev
+            pending.synchronize()
             barrier()
             e2e_s = time.perf_counter() - t0
         sampler.stop_flag.set()

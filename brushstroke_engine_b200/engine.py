@@ -259,10 +259,14 @@ class TriadPaintEngine:
         return np.ascontiguousarray(tiles[0].cpu().numpy()), None
 
     def render_patches_host(self, guidance_patches: torch.Tensor, z: torch.Tensor, positions: torch.Tensor,
-                            crop_margin: int = 10, out: Optional[torch.Tensor] = None, **generator_kwargs) -> torch.Tensor:
+                            crop_margin: int = 10, out: Optional[torch.Tensor] = None, wait: bool = True, **generator_kwargs):
         """End-to-end batched entry point with HOST buffers (the stylizer's per-batch work):
         guidance_patches [B,W,W] uint8 (0 = stroke, as sliced from the padded guidance image), z [B,z_dim] float64,
-        positions [B,2] int64 (y, x) -- all on the host (pinned for async copies) -> uint8 tiles [B,W-2m,W-2m,4] on the host."""
+        positions [B,2] int64 (y, x) -- all on the host (pinned for async copies) -> uint8 tiles [B,W-2m,W-2m,4] on the host.
+
+        ``wait=False`` returns ``(out, event)`` instead: the device->host copy runs on a side stream and ``event`` fires
+        when ``out`` is complete, so a caller that keeps two pinned output buffers overlaps the download of batch i with
+        the compute of batch i+1 (``event.synchronize()`` before reading ``out``)."""
         B, W = guidance_patches.shape[0], self.patch_width
         assert guidance_patches.dtype == torch.uint8 and guidance_patches.shape == (B, W, W)
         dev = self.device
@@ -279,6 +283,18 @@ class TriadPaintEngine:
         tiles, _ = self.render_tiles(geom, opts, crop_margin=crop_margin, **generator_kwargs)
         if out is None:
             out = torch.empty(tiles.shape, dtype=torch.uint8, pin_memory=True)
-        out.copy_(tiles, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return out
+        if wait:
+            out.copy_(tiles, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out
+        with torch.cuda.device(dev):
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream()
+            self._copy_stream.wait_stream(main)
+            with torch.cuda.stream(self._copy_stream):
+                out.copy_(tiles, non_blocking=True)
+                tiles.record_stream(self._copy_stream)
+                done = torch.cuda.Event()
+                done.record(self._copy_stream)
+        return out, done

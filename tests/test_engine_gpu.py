@@ -138,6 +138,12 @@ def test_render_patches_host_equals_device_path(engines):
     o.position = pos.to(DEV)
     tiles, _ = eng.render_tiles(job.gather(0, n), o, crop_margin=10)
     assert host.shape == (n, 108, 108, 4) and torch.equal(host, tiles.cpu())
+    # pipelined form: two pinned buffers, the copy of one call may still be in flight while the next call computes
+    bufs = [torch.empty((n, 108, 108, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    evs = [eng.render_patches_host(patches.pin_memory(), z.pin_memory(), pos.pin_memory(), crop_margin=10, out=b, wait=False)[1] for b in bufs]
+    for ev, b in zip(evs, bufs):
+        ev.synchronize()
+        assert torch.equal(b, host)
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
