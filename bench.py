@@ -281,7 +281,8 @@ def main():
                 for rep in range(3):
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    out = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, feature_blending_level=2, z_per_patch=z_pp, to_host=False)
+                    out = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, feature_blending_level=2, z_per_patch=z_pp, to_host=False,
+                                           distributed=False)
                     torch.cuda.synchronize()
                     if rep > 0:
                         btimes.append((time.perf_counter() - t0) * 1e3)

@@ -117,18 +117,24 @@ class CanvasJob:
         self.d_geom[m:m + H0, m:m + W0] = guidance                       # pad_geo offset + bottom/right padding in one go
         ys, xs = np.meshgrid(np.arange(nrows) * rwidth, np.arange(ncols) * rwidth, indexing='ij')
         yx = np.stack([ys.ravel(), xs.ravel()], axis=1).astype(np.int32)
+        d_yx = None
         if stitching_mode != 'all':
             # keep crops with more than 10 stroke (zero) pixels (style_transfer.py:45): window sums on the device
             zeros = (self.d_geom == 0).to(torch.float32)[None, None]
             counts = torch.nn.functional.avg_pool2d(zeros, self.patch, stride=rwidth, divisor_override=1)[0, 0]
             keep = (counts[:nrows, :ncols] > 10).cpu().numpy().ravel()
             yx = yx[keep]
+        else:
+            # the full grid is pure arithmetic: build it on the device too instead of uploading it (no synchronous copy)
+            gy = torch.arange(nrows, dtype=torch.int32, device=dev) * rwidth
+            gx = torch.arange(ncols, dtype=torch.int32, device=dev) * rwidth
+            d_yx = torch.stack([gy[:, None].expand(nrows, ncols), gx[None, :].expand(nrows, ncols)], dim=2).reshape(-1, 2).contiguous()
         self.crops_yx = np.ascontiguousarray(yx).reshape(-1, 2)
         self.crops = [(int(y), int(x), self.patch, self.patch) for y, x in self.crops_yx]
         self.tile = self.patch - 2 * m
-        self.d_crops = torch.from_numpy(self.crops_yx).to(dev)
+        self.d_crops = d_yx if d_yx is not None else torch.from_numpy(self.crops_yx).to(dev)
         self.tiles_yx = self.crops_yx + m                                # meta: (y + m, x + m)  (brush.py:365-373)
-        self.d_tiles_yx = torch.from_numpy(self.tiles_yx).to(dev)
+        self.d_tiles_yx = self.d_crops + m
 
     @property
     def geom(self) -> np.ndarray:
@@ -188,28 +194,34 @@ def _batch_opts(base: GanBrushOptions, z_per_patch: Optional[torch.Tensor], star
 
 def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOptions, crop_margin: int = 10,
             stitching_mode: str = 'all', feature_blending_level: int = 0, batch_size: int = 256, on_white: bool = False,
-            z_per_patch: Optional[torch.Tensor] = None, group=None, return_job: bool = False, to_host: bool = True):
+            z_per_patch: Optional[torch.Tensor] = None, group=None, return_job: bool = False, to_host: bool = True,
+            distributed: bool = True):
     """Stylize a whole guidance drawing.  guidance: [H,W,C] uint8 (last channel, 0 = stroke), host array or CUDA tensor;
     ``to_host=False`` returns the finished canvas as a CUDA tensor (device-resident in and out).
 
     With an initialised ``torch.distributed`` process group (one process per GPU) the crop rows are sharded across
     ranks and rank 0 returns the finished canvas (other ranks return None).  ``z_per_patch`` ([n_crops, z_dim])
-    gives every patch its own style (style interpolation across the canvas, BASELINE config 5)."""
+    gives every patch its own style (style interpolation across the canvas, BASELINE config 5).
+    ``distributed=False`` ignores the process group: this rank renders the whole canvas by itself."""
     import torch.distributed as dist
     world, rank = 1, 0
-    if dist.is_available() and dist.is_initialized():
+    if distributed and dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     job = CanvasJob(engine, guidance, crop_margin, stitching_mode)
     if feature_blending_level > 0:
         if world > 1:
-            raise RuntimeError('stylize: feature blending makes patches raster-dependent; run it on one GPU')
+            raise RuntimeError('stylize: feature blending makes patches raster-dependent; one canvas runs on one GPU '
+                               '(pass distributed=False and give every rank its own canvas)')
         blend = _stylize_blended if os.environ.get('NBE_BLEND_SEQUENTIAL') else _stylize_blended_wavefront
         canvas = blend(engine, job, opts, feature_blending_level, z_per_patch)
         out = job.finish(canvas, on_white, to_host)
         return (out, job) if return_job else out
     start, end = shard_crops(job.crops, world, rank)
     dev = engine.device
-    tiles_local = torch.empty((end - start, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
+    bounds = [shard_crops(job.crops, world, r) for r in range(world)]
+    max_n = max(e - s for s, e in bounds)
+    # every rank's tile buffer has the same (maximum) length so that it can be gathered as it is
+    tiles_local = torch.empty((max_n, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
     # even batches: a short tail batch costs almost a full launch sequence (276 patches -> 1 x 276, not 256 + 20)
     n_batches = max(1, -(-(end - start) // batch_size))
     if (end - start) <= batch_size * 5 // 4:
@@ -227,19 +239,18 @@ def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOption
         out = job.finish(canvas, on_white, to_host)
         return (out, job) if return_job else out
     # ---- multi-GPU: one gather of finished tiles to rank 0 (NCCL over NVLink; gloo in CPU tests is not used here) ----
-    bounds = [shard_crops(job.crops, world, r) for r in range(world)]
-    max_n = max(e - s for s, e in bounds)
-    padded = torch.zeros((max_n, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
-    padded[: end - start] = tiles_local
-    gathered = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
-    dist.gather(padded, gathered, dst=0, group=group)
+    gathered = None
+    if rank == 0:
+        big = torch.empty((world, max_n, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
+        gathered = list(big.unbind(0))
+    dist.gather(tiles_local, gathered, dst=0, group=group)
     if rank != 0:
         return (None, job) if return_job else None
     canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
     owner = job.owner_map()
     for r, (s, e) in enumerate(bounds):
         if e > s:
-            job.place(canvas, owner, gathered[r][: e - s].contiguous(), s, e)
+            job.place(canvas, owner, gathered[r], s, e)                 # only the first e - s tiles of the buffer are read
     out = job.finish(canvas, on_white, to_host)
     return (out, job) if return_job else out
 
