@@ -293,6 +293,7 @@ def main():
     # ---- interactive use: one 128^2 stroke patch per call through the reference-facing render_stroke
     #      (host uint8 patch in, host uint8 RGBA out; wall clock, rank 0) ----
     interactive_ms = None
+    interactive_graph_ms = None
     if rank == 0 and not args.no_e2e:
         from brushstroke_engine_b200.engine import GanBrushOptions as _GBO
         patch = np.ascontiguousarray(((1.0 - synthetic.synthetic_patch(128, seed=5)[0, 0]) * 255).astype(np.uint8)[:, :, None])   # [W,W,1], 255 = stroke
@@ -307,6 +308,15 @@ def main():
                 if i >= 10:
                     lat.append((time.perf_counter() - t0) * 1e3)
         interactive_ms = float(np.median(lat))
+        # the same through a CUDA-graph session (one capture per brush, one replay per stroke patch)
+        sess = engine.interactive_session(iopts, crop_margin=0)
+        glat = []
+        for i in range(110):
+            t0 = time.perf_counter()
+            sess.render_stroke(patch, (88 + i, 176))
+            if i >= 10:
+                glat.append((time.perf_counter() - t0) * 1e3)
+        interactive_graph_ms = float(np.median(glat))
     barrier()
     times = torch.tensor([ms_total, e2e_s * 1e3, canvas_ms if canvas_ms is not None else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -356,7 +366,8 @@ def main():
             'clocks': sampler.summary(),
         }
         if interactive_ms is not None:
-            line['interactive'] = {'ms_per_stroke_patch': interactive_ms, 'what': 'TriadPaintEngine.render_stroke, batch 1, host uint8 patch -> host uint8 RGBA, wall-clock median of 50 (rank 0)'}
+            line['interactive'] = {'ms_per_stroke_patch': interactive_ms, 'ms_per_stroke_patch_cuda_graph': interactive_graph_ms,
+                                   'what': 'batch 1, host uint8 patch -> host uint8 RGBA, wall-clock median (rank 0): TriadPaintEngine.render_stroke (eager, ~60 launches) and InteractiveSession.render_stroke (one CUDA-graph replay)'}
         if canvas_ms is not None:
             line['canvas'] = {'size': args.canvas, 'patches': n_canvas_patches, 'ms': canvas_ms, 'ms_host_to_host': canvas_host_ms, 'n_gpus': world,
                               'ms_feature_blending_level2_1gpu': blend_ms,

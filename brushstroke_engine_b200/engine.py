@@ -258,6 +258,10 @@ class TriadPaintEngine:
         tiles, _ = self.render_tiles(geom, opts, crop_margin=0, **generator_kwargs)
         return np.ascontiguousarray(tiles[0].cpu().numpy()), None
 
+    def interactive_session(self, opts: GanBrushOptions, crop_margin: int = 0) -> 'InteractiveSession':
+        """CUDA-graph session for one-patch-at-a-time rendering with a fixed brush (see ``InteractiveSession``)."""
+        return InteractiveSession(self, opts, crop_margin)
+
     def render_patches_host(self, guidance_patches: torch.Tensor, z: torch.Tensor, positions: torch.Tensor,
                             crop_margin: int = 10, out: Optional[torch.Tensor] = None, wait: bool = True, **generator_kwargs):
         """End-to-end batched entry point with HOST buffers (the stylizer's per-batch work):
@@ -298,3 +302,80 @@ class TriadPaintEngine:
                 done = torch.cuda.Event()
                 done.record(self._copy_stream)
         return out, done
+
+
+class InteractiveSession:
+    """One-patch-at-a-time rendering for the interactive UI (forger/ui/util.py:176-195 calls ``helper.render_stroke`` per
+    websocket message): the whole batch-1 forward -- uint8 patch -> geometry -> encoder -> synthesis -> composite -> uint8
+    RGBA -- is captured ONCE into a CUDA graph for the current brush (style, colours, render mode) and replayed per stroke
+    patch, so a call costs two small pinned copies and one graph launch instead of ~60 kernel launches issued from Python.
+
+    The graph is re-captured when the brush changes (``set_brush``); stroke geometry and canvas position are the only
+    per-call inputs and live in static device buffers."""
+
+    def __init__(self, engine: 'TriadPaintEngine', opts: GanBrushOptions, crop_margin: int = 0):
+        self.engine = engine
+        self.crop_margin = int(crop_margin)
+        dev = engine.device
+        W = engine.patch_width
+        self._h_patch = torch.empty((W, W), dtype=torch.uint8, pin_memory=True)
+        self._h_pos = torch.empty((1, 2), dtype=torch.int64, pin_memory=True)
+        self._d_patch = torch.empty((W, W), dtype=torch.uint8, device=dev)
+        self._d_pos = torch.zeros((1, 2), dtype=torch.int64, device=dev)
+        self._crop0 = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        T = W - 2 * self.crop_margin
+        self._h_out = torch.empty((1, T, T, 4), dtype=torch.uint8, pin_memory=True)
+        self._stream = torch.cuda.Stream(device=dev)
+        self._graph = None
+        self.set_brush(opts)
+
+    def _forward(self):
+        eng, W = self.engine, self.engine.patch_width
+        geom = torch.empty((1, 1, W, W), dtype=torch.float32, device=eng.device)
+        # stroke alpha (255 = stroke) -> geometry (0 = stroke): the gather kernel computes 1 - (255 - v) / 255 on v = 255 - alpha
+        inv = 255 - self._d_patch
+        _lib.call('nbe_gather_geom_patches', _lib.ptr(inv), W, W, _lib.ptr(self._crop0), _lib.ptr(geom), 1, W, _lib.stream())
+        self._opts.position = self._d_pos
+        tiles, _ = eng.render_tiles(geom, self._opts, crop_margin=self.crop_margin)
+        return tiles
+
+    def set_brush(self, opts: GanBrushOptions):
+        """(Re)capture the graph for ``opts`` (style z / w+, colours, UVS mapping flag) and the engine's render mode."""
+        eng = self.engine
+        o = GanBrushOptions()
+        o.__dict__.update(opts.__dict__)
+        o.to(eng.device)
+        for name in ('color0', 'color1', 'canvas_color'):
+            c = getattr(o, name, None)
+            if c is not None:
+                setattr(o, name, c.to(eng.device))
+        self._opts = o
+        with torch.no_grad(), torch.cuda.device(eng.device):
+            if o.enable_uvs_mapping:
+                eng.uvs_mapper.get_sfactor(o)                      # fills the per-style cache outside the capture
+            self._d_patch.zero_()
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                for _ in range(2):                                  # warm-up: lazy allocations, cudaFuncSetAttribute, workspaces
+                    eng.G._noise_cache = None
+                    self._forward()
+            self._stream.synchronize()
+            eng.G._noise_cache = None                               # the noise maps depend on the position: they must be IN the graph
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._stream):
+                self._d_out = self._forward()
+            eng.G._noise_cache = None
+            self._graph = g
+
+    def render_stroke(self, stroke_patch: np.ndarray, position_yx=None) -> np.ndarray:
+        """[W,W,C] uint8 stroke patch (last channel: 255 = stroke), optional canvas position (y, x) -> [T,T,4] uint8 RGBA."""
+        a = np.ascontiguousarray(stroke_patch[:, :, -1])
+        self._h_patch.numpy()[...] = a
+        self._h_pos[0, 0], self._h_pos[0, 1] = (0, 0) if position_yx is None else (int(position_yx[0]), int(position_yx[1]))
+        with torch.cuda.stream(self._stream):
+            self._d_patch.copy_(self._h_patch, non_blocking=True)
+            self._d_pos.copy_(self._h_pos, non_blocking=True)
+            self._graph.replay()
+            self._h_out.copy_(self._d_out, non_blocking=True)
+        self._stream.synchronize()
+        return self._h_out[0].numpy().copy()

@@ -162,3 +162,28 @@ def test_blending_wavefronts_equal_raster_loop(engines, mode, level):
         wav = stylizer._stylize_blended_wavefront(eng, job, opts, level, None)
     assert torch.equal(seq, wav)
     assert int((wav[..., 3] > 0).sum()) > 1000                                       # something was painted
+
+
+def test_interactive_graph_session_equals_render_stroke(engines):
+    """The CUDA-graph replay of the batch-1 forward gives the same bytes as the eager call, for changing stroke patches
+    and canvas positions (the shifted noise depends on the position and must be recomputed inside the graph)."""
+    eng = engines['bf16']
+    rng = np.random.RandomState(3)
+    opts = _opts(P.style_z_from_seed(21), '21')
+    sess = eng.interactive_session(opts, crop_margin=0)
+    for k in range(4):
+        geom = synthetic.synthetic_patch(128, seed=10 + k)[0, 0]
+        patch = np.ascontiguousarray(((1.0 - geom) * 255).astype(np.uint8)[:, :, None])
+        pos = (int(rng.randint(0, 3000)), int(rng.randint(0, 3000)))
+        o = _opts(P.style_z_from_seed(21), '21')
+        o.position = torch.tensor([[pos[0], pos[1]]], dtype=torch.int64)
+        ref, _ = eng.render_stroke(patch, None, o)
+        got = sess.render_stroke(patch, pos)
+        assert got.shape == ref.shape == (128, 128, 4) and np.array_equal(got, ref), k
+    # a new brush re-captures the graph
+    opts2 = _opts(P.style_z_from_seed(99), '99')
+    sess.set_brush(opts2)
+    o = _opts(P.style_z_from_seed(99), '99')
+    o.position = torch.tensor([[5, 7]], dtype=torch.int64)
+    ref, _ = eng.render_stroke(patch, None, o)
+    assert np.array_equal(sess.render_stroke(patch, (5, 7)), ref)
