@@ -187,3 +187,43 @@ def test_interactive_graph_session_equals_render_stroke(engines):
     o.position = torch.tensor([[5, 7]], dtype=torch.int64)
     ref, _ = eng.render_stroke(patch, None, o)
     assert np.array_equal(sess.render_stroke(patch, (5, 7)), ref)
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
+def test_wplus_library_style_with_noise_buffers_matches_oracle(engines, bundles, mode, tol, tmp_path):
+    """A projected brush (w+ code and its own per-layer noise maps, forger/ui/library.py:146-202) set through
+    ``WBrushLibrary`` drives the engine exactly as it drives the oracle: the noise buffers replace the shifted
+    ``noise_const`` (networks.py:365-370), the mapping network is bypassed."""
+    import pickle
+    from brushstroke_engine_b200.library import WBrushLibrary
+    from brushstroke_engine_b200.engine import GanBrushOptions
+    cfg, ecfg, gp, ep = bundles
+    eng = engines[mode]
+    g = torch.Generator().manual_seed(11)
+    def style():
+        noise = {}
+        for res in cfg.block_resolutions:
+            for conv in (('conv0', 'conv1') if res > 4 else ('conv1',)):
+                noise[f'b{res}.{conv}.noise_const'] = torch.randn(res, res, generator=g)
+        return {'w': torch.randn(1, cfg.num_ws, cfg.w_dim, generator=g), 'noise': noise}
+    path = str(tmp_path / 'brushes.pkl')
+    with open(path, 'wb') as f:
+        pickle.dump({'p': style(), 'q': style()}, f)
+    lib = WBrushLibrary.from_file(path)
+    o = GanBrushOptions()
+    lib.set_interpolated_style('p', 'q', 0.35, o)
+    ws, nb = o.style_ws.clone(), {k: v.clone() for k, v in o.custom_args['noise_buffers'].items()}
+    geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=s) for s in (8, 9)]))
+    pos = torch.tensor([[0, 88], [264, 1144]])
+    o.position = pos.to(DEV)
+    rgba, raw, _ = eng._render_stroke_torch(geom.to(DEV), None, o)
+    gf = O.geometry_encode(ep, ecfg, geom)
+    _, d = O.generator_forward(gp, cfg, None, gf, positions=pos, ws=ws.expand(2, -1, -1), noise_buffers=nb)
+    ref = O.triad_composite(d['uvs'], d['colors'], 'clear')
+    assert float((rgba.cpu() - ref).abs().max()) < tol
+    # the noise maps matter: the same w+ without them gives a different image
+    o2 = GanBrushOptions()
+    o2.set_style_w(ws, style_id='x')
+    o2.position = pos.to(DEV)
+    rgba2, _, _ = eng._render_stroke_torch(geom.to(DEV), None, o2)
+    assert float((rgba2 - rgba).abs().max()) > 1e-3
