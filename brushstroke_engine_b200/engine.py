@@ -196,7 +196,7 @@ class TriadPaintEngine:
         B = geom.shape[0]
         opts.prepare_style(B, self.device)
         G = self.G
-        fused = G.mode == 'bf16' and self.encoder.mode == 'bf16' and G.use_flat \
+        fused = G.flat_supported and self.encoder.mode == 'bf16' \
             and not generator_kwargs.get('force_fp32', False) and not generator_kwargs.get('return_features') \
             and not generator_kwargs.get('blended_features') \
             and list(self.encoder.res) == list(range(len(G.cfg.geom_feature_resolutions)))

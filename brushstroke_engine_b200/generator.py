@@ -243,6 +243,14 @@ class Generator:
             scales.append(prep[0][f'b{res * 2}.conv0'][:, cb:cb + cg].contiguous())
         return InjectedGeometry(bufs, ws_latents, prep), dests, scales
 
+    @property
+    def flat_supported(self) -> bool:
+        """The flat tensor-core path covers the stock configuration (128^2 output, 128 channels in every block); other
+        configurations run on the per-tap / generic kernels."""
+        cfg = self.cfg
+        return self.mode == 'bf16' and self.use_flat and cfg.img_resolution == 128 and \
+            all(cfg.channels(r) == 128 for r in cfg.block_resolutions)
+
     # ------------------------------------------------------------------------------------------ API
     def __call__(self, *args, **kwargs):
         return self.forward(*args, **kwargs)
@@ -352,8 +360,7 @@ class Generator:
         ws = ws.to(torch.float32)
         mode = 'fp32' if (force_fp32 or self.mode == 'fp32') else 'bf16'
         injected = isinstance(geom_feature, InjectedGeometry)
-        flat = mode == 'bf16' and not return_features and not blended_features and self.use_flat and \
-            cfg.img_resolution == 128 and all(cfg.channels(r) == 128 for r in cfg.block_resolutions)
+        flat = mode == 'bf16' and not return_features and not blended_features and self.flat_supported
         if injected and not flat:
             raise RuntimeError('synthesis: InjectedGeometry needs the flat bf16 path (no force_fp32 / return_features / blended_features)')
         with torch.cuda.device(self.device):

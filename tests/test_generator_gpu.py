@@ -150,3 +150,23 @@ def test_noise_modes_and_errors(G16, golden_inputs):
         G16.mapping(t(g['z']), None)
     with pytest.raises(RuntimeError):
         G16(z, None, gfd, style_mixing_prob=0.9)
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
+def test_non_stock_configuration_runs_on_generic_kernels(mode, tol):
+    """A generator that is NOT the stock 128^2 / 128-channel model (here 64^2, 64 channels, one injection point) cannot
+    use the flat tensor-core path; it must still match the oracle on the per-tap / generic kernels."""
+    from brushstroke_engine_b200.generator import Generator
+    cfg = P.GeneratorConfig(img_resolution=64, channel_max=64, geom_feature_channels=(16,), geom_feature_resolutions=(16,))
+    gp = P.init_generator_params(cfg, 5, 0.1)
+    G = Generator(gp, cfg, DEV, mode=mode)
+    assert not G.flat_supported
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(3, cfg.z_dim, generator=g, dtype=torch.float64)
+    gf = [torch.randn(3, 16, 16, 16, generator=g)]
+    pos = torch.tensor([[0, 8], [100, 33], [64, 64]])
+    img, dbg = G(z.to(DEV), None, [t_.to(DEV) for t_ in gf], positions=pos.to(DEV), return_debug_data=True, noise_mode='const')
+    ref_img, ref = O.generator_forward(gp, cfg, z, gf, positions=pos)
+    assert img.shape == (3, 3, 64, 64)
+    assert float((img.cpu().float() - ref_img).abs().max()) < tol
+    assert float((dbg['uvs'].cpu().float() - ref['uvs']).abs().max()) < tol
