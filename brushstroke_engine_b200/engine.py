@@ -147,6 +147,51 @@ class StyleUVSMapper:
         _, raw = self._render(brush_opts, [x[:1] for x in self.geom_feature])
         return raw['colors']
 
+    def get_colors(self, brush_opts) -> str:
+        """'rgb(r,g,b):rgb(...):rgb(...)' for the brush's three default colours (mapper.py:74-78, 102-103)."""
+        colors = ((self.get_colors_raw(brush_opts)[0].detach().cpu() / 2 + 0.5) * 255).to(torch.uint8).numpy()
+        return ':'.join('rgb(%s)' % ','.join(str(x) for x in colors[..., i]) for i in range(3))
+
+    def get_brush_icon(self, brush_opts, on_white: bool = True) -> np.ndarray:
+        """[W,W,3] uint8 icon: the brush on the first calibration stroke (mapper.py:105-115)."""
+        if self.geom_feature is None:
+            self._init_geometry()
+        renders, raw = self._render(brush_opts, [x[:1] for x in self.geom_feature])
+        renders = renders.float()
+        if on_white:
+            s = raw['uvs'][:, 2:].float()
+            renders = renders * (1 - s) + s
+        return ((renders[0].permute(1, 2, 0).detach() / 2 + 0.5) * 255).to(torch.uint8).cpu().numpy()
+
+    def get_sfactors(self, opts_list) -> List[torch.Tensor]:
+        """``get_sfactor`` for several brushes with ONE generator call (all uncached styles x the 5 calibration patches
+        in one batch) -- filling a brush library's cache costs one launch sequence instead of one per brush."""
+        if self.geom_feature is None:
+            self._init_geometry()
+        todo = [o for o in opts_list if o.style_id is None or o.style_id not in self.sfactors]
+        fresh = {}
+        if todo:
+            dev, G = self.engine.device, self.engine.G
+            n = self.geom_feature[0].shape[0]
+            ws = []
+            for o in todo:
+                if o.style_ws is not None:
+                    w = o.style_ws.to(dev, torch.float32)
+                    w = w.expand(-1, G.num_ws, -1) if w.shape[1] == 1 else w
+                else:
+                    w = G.mapping(o.style_z.to(dev), None).to(torch.float32)
+                ws.append(w[:1].expand(n, -1, -1))
+            ws = torch.cat(ws).contiguous()
+            gf = [x.repeat(len(todo), 1, 1, 1) for x in self.geom_feature]
+            _, raw = G.synthesis(ws, geom_feature=gf, noise_mode='const', return_debug_data=True)
+            S = raw['uvs'][:, 2:3].reshape(len(todo), n, 1, *raw['uvs'].shape[2:])
+            for k, o in enumerate(todo):
+                val = torch.stack([torch.topk(S[k, i][self.bmask[i]], k=15)[0].min() for i in range(n)]).min()
+                fresh[id(o)] = 1 / val
+                if o.style_id is not None:
+                    self.sfactors[o.style_id] = fresh[id(o)]
+        return [fresh[id(o)] if id(o) in fresh else self.sfactors[o.style_id] for o in opts_list]
+
     def get_sfactor(self, brush_opts):
         """1 / min_i min(topk15(S_i[background_i])) (mapper.py:117-135); cached per style_id."""
         style_id = brush_opts.style_id

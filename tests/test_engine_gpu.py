@@ -227,3 +227,20 @@ def test_wplus_library_style_with_noise_buffers_matches_oracle(engines, bundles,
     o2.position = pos.to(DEV)
     rgba2, _, _ = eng._render_stroke_torch(geom.to(DEV), None, o2)
     assert float((rgba2 - rgba).abs().max()) > 1e-3
+
+
+def test_uvs_mapper_batched_sfactors_icons_and_colors(engines):
+    eng = engines['fp32']
+    from brushstroke_engine_b200.engine import StyleUVSMapper
+    single, batched = StyleUVSMapper(eng), StyleUVSMapper(eng)
+    opts = [_opts(P.style_z_from_seed(s), str(s)) for s in (3, 594, 12)]
+    ref = [single.get_sfactor(o) for o in opts]
+    got = batched.get_sfactors(opts)
+    for a, b in zip(ref, got):
+        assert abs(float(a) - float(b)) <= 1e-5 * abs(float(a))
+    assert all(str(s) in batched.sfactors for s in (3, 594, 12))
+    assert batched.get_sfactors(opts[:1])[0] is batched.sfactors['3']                # served from the cache
+    spec = single.get_colors(opts[1])
+    assert spec.count('rgb(') == 3 and spec.count(':') == 2
+    icon = single.get_brush_icon(opts[1])
+    assert icon.shape == (128, 128, 3) and icon.dtype == np.uint8 and icon.std() > 0
