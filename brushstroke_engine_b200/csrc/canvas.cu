@@ -47,6 +47,46 @@ triad_composite_kernel(const float* __restrict__ uvs, const float* __restrict__ 
     }
 }
 
+// CanvasPaintEngine._render_stroke_torch tail (brush.py:905-935): mode 0 'clear' (stroke colour, generated foreground alpha),
+// 1 'stroke' (opaque stroke colour), 2 'canvas' (the generated canvas), 3 'full' (canvas under the stroke).
+__global__ void __launch_bounds__(256)
+canvas_composite_kernel(const float* __restrict__ uvs, const float* __restrict__ colors01, const float* __restrict__ alpha_fg,
+                        int64_t alpha_sn, const float* __restrict__ gen_canvas, int mode, float* __restrict__ out_f32,
+                        uint8_t* __restrict__ out_u8, int N, int H, int W, int m) {
+    const int HW = H * W;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * HW) return;
+    const int n = idx / HW, pix = idx - n * HW;
+    const int y = pix / W, x = pix - y * W;
+    const float U = uvs[((int64_t)n * 3 + 0) * HW + pix], V = uvs[((int64_t)n * 3 + 1) * HW + pix], S = uvs[((int64_t)n * 3 + 2) * HW + pix];
+    const float a = alpha_fg[(int64_t)n * alpha_sn + pix];
+    const float* c = colors01 + n * 9;
+    float rgba[4];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float stroke = __fadd_rn(__fadd_rn(__fmul_rn(U, c[ch * 3 + 0]), __fmul_rn(V, c[ch * 3 + 1])), __fmul_rn(S, c[ch * 3 + 2]));
+        const float cv = __fdiv_rn(__fadd_rn(gen_canvas[((int64_t)n * 3 + ch) * HW + pix], 1.0f), 2.0f);
+        rgba[ch] = (mode <= 1) ? stroke : (mode == 2) ? cv : __fadd_rn(__fmul_rn(__fsub_rn(1.f, a), cv), __fmul_rn(a, stroke));
+    }
+    rgba[3] = (mode == 0) ? a : 1.f;
+    if (out_f32) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) out_f32[((int64_t)n * 4 + ch) * HW + pix] = rgba[ch];
+    }
+    if (out_u8 && y >= m && y < H - m && x >= m && x < W - m) {
+        const int T = W - 2 * m, TH = H - 2 * m;
+        uchar4 px;
+        uint8_t* o = reinterpret_cast<uint8_t*>(&px);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            float v = __fmul_rn(rgba[ch], 255.f);
+            v = fminf(fmaxf(v, 0.f), 255.f);
+            o[ch] = (uint8_t)v;                                    // truncation, as tensor.to(torch.uint8)
+        }
+        reinterpret_cast<uchar4*>(out_u8)[((int64_t)n * TH + (y - m)) * T + (x - m)] = px;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 gather_geom_kernel(const uint8_t* __restrict__ canvas, int canvas_h, int canvas_w, const int32_t* __restrict__ crops,
                    float* __restrict__ geom, int N, int P) {
@@ -105,6 +145,21 @@ extern "C" int nbe_triad_composite(const float* uvs, const float* colors01, cons
     triad_composite_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         uvs, colors01, sfactor, mode, out_f32, out_u8, N, H, W, crop_margin);
     return launched("triad_composite_kernel");
+}
+
+extern "C" int nbe_canvas_composite(const float* uvs, const float* colors01, const float* alpha_fg, int64_t alpha_sn,
+                                    const float* gen_canvas, int mode, float* out_f32, uint8_t* out_u8,
+                                    int N, int H, int W, int crop_margin, nbe_stream_t stream) {
+    NBE_REQUIRE(uvs && colors01 && alpha_fg && gen_canvas && N >= 0 && H >= 1 && W >= 1, "canvas_composite: bad arguments");
+    NBE_REQUIRE(mode >= 0 && mode <= 3, "canvas_composite: unknown render mode %d", mode);
+    NBE_REQUIRE(crop_margin >= 0 && 2 * crop_margin < H && 2 * crop_margin < W, "canvas_composite: bad crop margin");
+    NBE_REQUIRE(out_f32 || out_u8, "canvas_composite: no output");
+    if (N == 0) return NBE_OK;
+    const int64_t total = (int64_t)N * H * W;
+    NBE_REQUIRE(total <= INT32_MAX, "canvas_composite: too large");
+    canvas_composite_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        uvs, colors01, alpha_fg, alpha_sn, gen_canvas, mode, out_f32, out_u8, N, H, W, crop_margin);
+    return launched("canvas_composite_kernel");
 }
 
 extern "C" int nbe_gather_geom_patches(const uint8_t* canvas, int canvas_h, int canvas_w, const int32_t* crops, float* geom,

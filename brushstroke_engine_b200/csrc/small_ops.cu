@@ -275,6 +275,70 @@ torgb_triad_nchw_kernel(const float* __restrict__ x, const float* __restrict__ w
 }
 
 // ---------------------------------------------------------------------------------------------
+// ToRGBColorTriadLayer in the 'canvas' colour format (networks.py:433-481): 3 UVS logits + a 3-channel canvas + 2 alpha
+// logits from one 1x1 modulated conv; uvs = softmax(t[0:3]), alpha = softmax(t[6:8]),
+// img = alpha_fg * sum_k uvs_k colors_k + alpha_bg * canvas.  One thread per pixel, 8 dot products over the channels.
+// ---------------------------------------------------------------------------------------------
+template <bool NHWC>
+__global__ void __launch_bounds__(128)
+torgb_canvas_kernel(const void* __restrict__ xv, int x_cs, const float* __restrict__ w, const float* __restrict__ styles,
+                    const float* __restrict__ bias, const float* __restrict__ colors, float clamp,
+                    float* __restrict__ img, float* __restrict__ uvs, float* __restrict__ canvas, float* __restrict__ alpha,
+                    int N, int C, int HW) {
+    extern __shared__ float s_w[];                                 // [8][C] modulated weights of this image
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < 8 * C; i += blockDim.x) s_w[i] = w[i] * styles[(int64_t)n * C + (i % C)];
+    __syncthreads();
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = 0.f;
+    if (NHWC) {
+        const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(xv) + ((int64_t)n * HW + pix) * x_cs;
+        for (int c = 0; c < C; c += 8) {
+            const int4 raw = *reinterpret_cast<const int4*>(xp + c);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 v = __bfloat1622float2(h2[q]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { t[k] = fmaf(v.x, s_w[k * C + c + 2 * q], t[k]); t[k] = fmaf(v.y, s_w[k * C + c + 2 * q + 1], t[k]); }
+            }
+        }
+    } else {
+        const float* xp = reinterpret_cast<const float*>(xv) + (int64_t)n * C * HW + pix;
+        for (int c = 0; c < C; ++c) {
+            const float v = xp[(int64_t)c * HW];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = fmaf(v, s_w[k * C + c], t[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        t[k] += bias[k];
+        if (clamp >= 0.f) t[k] = fminf(fmaxf(t[k], -clamp), clamp);
+    }
+    const float m = fmaxf(t[0], fmaxf(t[1], t[2]));
+    const float e0 = expf(t[0] - m), e1 = expf(t[1] - m), e2 = expf(t[2] - m);
+    const float inv = 1.f / (e0 + e1 + e2);
+    const float u[3] = {e0 * inv, e1 * inv, e2 * inv};
+    const float ma = fmaxf(t[6], t[7]);
+    const float a0 = expf(t[6] - ma), a1 = expf(t[7] - ma);
+    const float ainv = 1.f / (a0 + a1);
+    const float afg = a0 * ainv, abg = a1 * ainv;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int64_t o = ((int64_t)n * 3 + c) * HW + pix;
+        const float stroke = u[0] * colors[n * 9 + c * 3 + 0] + u[1] * colors[n * 9 + c * 3 + 1] + u[2] * colors[n * 9 + c * 3 + 2];
+        if (uvs) uvs[o] = u[c];
+        if (canvas) canvas[o] = t[3 + c];
+        if (img) img[o] = afg * stroke + abg * t[3 + c];
+    }
+    if (alpha) { alpha[((int64_t)n * 2 + 0) * HW + pix] = afg; alpha[((int64_t)n * 2 + 1) * HW + pix] = abg; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // BlendedFeatures.blend: x = alpha * saved + (1 - alpha) * x
 // ---------------------------------------------------------------------------------------------
 __global__ void blend_nchw_kernel(float* __restrict__ x, const float* __restrict__ saved, const float* __restrict__ alpha,
@@ -388,6 +452,26 @@ extern "C" int nbe_torgb_triad(const void* x, int x_is_bf16, int x_cs, const flo
     dim3 grid((HW + 255) / 256, N);
     torgb_triad_nchw_kernel<<<grid, 256, smem, s>>>((const float*)x, w, styles, bias, colors, clamp, img, uvs, N, C, HW);
     return launched("torgb_triad_nchw_kernel");
+}
+
+extern "C" int nbe_torgb_canvas(const void* x, int x_is_bf16, int x_cs, const float* w, const float* styles, const float* bias,
+                                const float* colors, float clamp, float* img, float* uvs, float* canvas, float* alpha,
+                                int N, int C, int H, int W, nbe_stream_t stream) {
+    NBE_REQUIRE(x && w && styles && bias && colors && N >= 0 && C >= 1 && H >= 1 && W >= 1, "torgb_canvas: bad arguments");
+    if (N == 0) return NBE_OK;
+    NBE_REQUIRE(N <= 65535, "torgb_canvas: batch too large");
+    const int HW = H * W;
+    const size_t smem = (size_t)8 * C * sizeof(float);
+    NBE_REQUIRE(smem <= 48 * 1024, "torgb_canvas: too many channels");
+    dim3 grid((HW + 127) / 128, N);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (x_is_bf16) {
+        NBE_REQUIRE(C % 8 == 0 && x_cs % 8 == 0 && x_cs >= C && (((uintptr_t)x) & 15) == 0, "torgb_canvas: NHWC bf16 input needs C, x_cs multiples of 8");
+        torgb_canvas_kernel<true><<<grid, 128, smem, s>>>(x, x_cs, w, styles, bias, colors, clamp, img, uvs, canvas, alpha, N, C, HW);
+    } else {
+        torgb_canvas_kernel<false><<<grid, 128, smem, s>>>(x, 0, w, styles, bias, colors, clamp, img, uvs, canvas, alpha, N, C, HW);
+    }
+    return launched("torgb_canvas_kernel");
 }
 
 extern "C" int nbe_blend_features(void* x, const void* saved, const float* alpha, int64_t alpha_sn, int N, int C, int H, int W,

@@ -349,6 +349,40 @@ class TriadPaintEngine:
         return out, done
 
 
+CANVAS_RENDER_MODES = {'clear': 0, 'stroke': 1, 'canvas': 2, 'full': 3}
+
+
+class CanvasPaintEngine(TriadPaintEngine):
+    """forger/ui/brush.py:870-935: the 'canvas' colour format (ToRGB emits a generated canvas and a 2-way alpha next to the
+    UVS stroke, networks.py:476-481).  Render modes: 'clear' (stroke colour with the generated foreground alpha), 'stroke'
+    (opaque stroke colour), 'canvas' (the generated canvas only), 'full' (canvas under the stroke).  No UVS remapping."""
+
+    def __init__(self, gen_params: Bundle, enc_params: Bundle, device='cuda', mode: str = 'bf16',
+                 gen_cfg: Optional[GeneratorConfig] = None, enc_cfg: EncoderConfig = EncoderConfig()):
+        gen_cfg = gen_cfg if gen_cfg is not None else GeneratorConfig(color_format='canvas')
+        if gen_cfg.color_format != 'canvas':
+            raise RuntimeError("CanvasPaintEngine needs a generator with color_format == 'canvas'")
+        super().__init__(gen_params, enc_params, device, mode, gen_cfg, enc_cfg)
+        self.render_modes = set(CANVAS_RENDER_MODES)
+
+    def _composite(self, triad_data, opts, B, want_f32=True, crop_margin=None):
+        uvs = triad_data['uvs'].contiguous()
+        default_colors = (triad_data['colors'] + 1) / 2.0
+        colors = opts.prepare_colors(default_colors).contiguous()
+        alpha = triad_data['alpha'].contiguous()                     # [B,2,W,W]; channel 0 is alpha_fg
+        gen_canvas = triad_data['canvas'].contiguous()
+        W = self.patch_width
+        out_f32 = torch.empty((B, 4, W, W), dtype=torch.float32, device=self.device) if want_f32 else None
+        out_u8, m = None, 0
+        if crop_margin is not None:
+            m = int(crop_margin)
+            out_u8 = torch.empty((B, W - 2 * m, W - 2 * m, 4), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call('nbe_canvas_composite', _lib.ptr(uvs), _lib.ptr(colors), _lib.ptr(alpha), 2 * W * W, _lib.ptr(gen_canvas),
+                      CANVAS_RENDER_MODES[self.render_mode], _lib.ptr(out_f32), _lib.ptr(out_u8), B, W, W, m, _lib.stream())
+        return out_f32, out_u8
+
+
 class InteractiveSession:
     """One-patch-at-a-time rendering for the interactive UI (forger/ui/util.py:176-195 calls ``helper.render_stroke`` per
     websocket message): the whole batch-1 forward -- uint8 patch -> geometry -> encoder -> synthesis -> composite -> uint8

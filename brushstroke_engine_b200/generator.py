@@ -182,7 +182,9 @@ class Generator:
                     self._layers.append(L)
                 self._lin[res] = torch.linspace(0, 1, res).to(dev)                # networks.py:295-299 (CPU linspace)
             k = f'synthesis.b{cfg.img_resolution}.torgb'
-            self._rgb_w = f32(p[f'{k}.weight']).reshape(cfg.img_channels, -1)
+            self._rgb_w = f32(p[f'{k}.weight']).reshape(cfg.torgb_out_channels, -1)      # 3 (triad) or 3 + 5 (canvas) rows
+            self._canvas_format = cfg.color_format == 'canvas'
+            self._rgb_extra = {}
             self._rgb_b = f32(p[f'{k}.bias'])
             self._rgb_color_bias = f32(p[f'{k}.color_bias'])
             self._rgb_affine_w = f32(p[f'{k}.affine.weight'])
@@ -376,6 +378,7 @@ class Generator:
                                   noise_mode, noise_buffers, return_features, blended_features)
         debug = dict(feats)
         if return_debug_data:
+            debug.update(self._rgb_extra)                           # 'canvas', 'alpha_fg', 'alpha' in the canvas colour format
             debug['colors'] = colors
             debug['uvs'] = uvs
         if len(debug) > 0:
@@ -430,6 +433,15 @@ class Generator:
         img = torch.empty((B, 3, R, R), dtype=torch.float32, device=self.device)
         uvs = torch.empty((B, 3, R, R), dtype=torch.float32, device=self.device)
         clamp = self.cfg.conv_clamp if self.cfg.conv_clamp is not None else -1
+        if self._canvas_format:
+            # 'canvas' colour format (networks.py:476-481): generated canvas + 2-way alpha next to the UVS stroke
+            canvas = torch.empty((B, 3, R, R), dtype=torch.float32, device=self.device)
+            alpha = torch.empty((B, 2, R, R), dtype=torch.float32, device=self.device)
+            _lib.call('nbe_torgb_canvas', _lib.ptr(x), int(is_bf16), int(x_cs), _lib.ptr(self._rgb_w), _lib.ptr(rgb_styles),
+                      _lib.ptr(self._rgb_b), _lib.ptr(colors.contiguous()), float(clamp), _lib.ptr(img), _lib.ptr(uvs),
+                      _lib.ptr(canvas), _lib.ptr(alpha), B, self._rgb_w.shape[1], R, R, _lib.stream())
+            self._rgb_extra = {'canvas': canvas, 'alpha_fg': alpha[:, :1], 'alpha': alpha}
+            return img, uvs
         _lib.call('nbe_torgb_triad', _lib.ptr(x), int(is_bf16), int(x_cs), _lib.ptr(self._rgb_w), _lib.ptr(rgb_styles),
                   _lib.ptr(self._rgb_b), _lib.ptr(colors.contiguous()), float(clamp), _lib.ptr(img), _lib.ptr(uvs),
                   B, self._rgb_w.shape[1], R, R, _lib.stream())
@@ -482,7 +494,8 @@ class Generator:
             noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp,
                                                 noise_buffers.get(f'{conv1.name}.noise_const'))
             is_last = res == cfg.img_resolution
-            fused_rgb = is_last and res not in blended_features and res % 128 == 0 and conv1.cout == 128 and conv1.cin <= 128
+            fused_rgb = is_last and res not in blended_features and res % 128 == 0 and conv1.cout == 128 and conv1.cin <= 128 \
+                and not self._canvas_format
             if fused_rgb:
                 # last layer: ToRGB + softmax + colour mix ride in the conv epilogue; the 128-channel map is only stored on request
                 need_y = res in return_features
@@ -569,6 +582,14 @@ class Generator:
             else:
                 x1, x1_pitch = xin, xin_pitch
             noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp, noise_buffers.get(f'{conv1.name}.noise_const'))
+            if res == last and self._canvas_format:
+                # 'canvas' colour format: 8 ToRGB outputs do not fit the fused epilogue -- store the last feature map, then ToRGB
+                y = torch.empty((B, res, res, conv1.cout), dtype=torch.bfloat16, device=dev)
+                _lib.call('nbe_conv_tc_bf16', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(y), B, res, res, conv1.cin, x1.shape[3],
+                          conv1.cout, conv1.cout, 3, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
+                          _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, None, st)
+                img, uvs = self._torgb(y, True, conv1.cout, rgb_styles, colors, B)
+                break
             if res == last:
                 ev = None
                 if self.probe is not None and conv1.name in self.probe:

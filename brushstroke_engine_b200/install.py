@@ -68,7 +68,8 @@ def generator_config_from_reference(G) -> GeneratorConfig:
                            mapping_layers=G.mapping.num_layers, channel_base=c128 * G.img_resolution, channel_max=c128,
                            conv_clamp=last.conv1.conv_clamp,
                            geom_feature_channels=tuple(syn.geom_feature_channels),
-                           geom_feature_resolutions=tuple(syn.geom_feature_resolutions))
+                           geom_feature_resolutions=tuple(syn.geom_feature_resolutions),
+                           color_format=getattr(last.torgb, 'color_format', 'triad'))
 
 
 def encoder_config_from_reference(enc) -> EncoderConfig:
@@ -83,12 +84,14 @@ def encoder_config_from_reference(enc) -> EncoderConfig:
 
 
 def engine_from_reference(ref_engine, mode: str = 'bf16'):
-    """reference ``TriadGanPaintEngine`` -> ``TriadPaintEngine`` sharing its weights, device and render mode."""
-    from .engine import TriadPaintEngine
+    """reference ``TriadGanPaintEngine`` / ``CanvasPaintEngine`` -> ``TriadPaintEngine`` / ``CanvasPaintEngine`` sharing its
+    weights, device and render mode (the class follows the generator's colour format, as brush.py:594-599)."""
+    from .engine import TriadPaintEngine, CanvasPaintEngine
     gp = bundle_from_module(ref_engine.G)
     ep = bundle_from_module(ref_engine.encoder)
-    eng = TriadPaintEngine(gp, ep, ref_engine.device, mode=mode, gen_cfg=generator_config_from_reference(ref_engine.G),
-                           enc_cfg=encoder_config_from_reference(ref_engine.encoder))
+    gen_cfg = generator_config_from_reference(ref_engine.G)
+    cls = CanvasPaintEngine if gen_cfg.color_format == 'canvas' else TriadPaintEngine
+    eng = cls(gp, ep, ref_engine.device, mode=mode, gen_cfg=gen_cfg, enc_cfg=encoder_config_from_reference(ref_engine.encoder))
     eng.set_render_mode(ref_engine.render_mode)
     return eng
 

@@ -51,6 +51,7 @@ class GeneratorConfig:
     conv_clamp: float = 256.0
     geom_feature_channels: Sequence[int] = (16, 256)
     geom_feature_resolutions: Sequence[int] = (16, 32)
+    color_format: str = 'triad'                 # 'triad' (stock models) or 'canvas' (ToRGBColorTriadLayer, networks.py:433-440)
 
     @property
     def block_resolutions(self) -> List[int]:
@@ -69,6 +70,13 @@ class GeneratorConfig:
         if (res // 2) in self.geom_feature_resolutions:
             c += self.geom_feature_channels[list(self.geom_feature_resolutions).index(res // 2)]
         return c
+
+    @property
+    def torgb_out_channels(self) -> int:
+        """3 UVS maps, plus a 3-channel canvas and 2 alpha logits for the 'canvas' format (networks.py:434-440)."""
+        if self.color_format not in ('triad', 'canvas'):
+            raise RuntimeError(f'Unknown format {self.color_format}')
+        return self.img_channels + (5 if self.color_format == 'canvas' else 0)
 
     @property
     def num_ws(self) -> int:
@@ -144,8 +152,8 @@ def init_generator_params(cfg: GeneratorConfig = GeneratorConfig(), seed: int = 
     res = cfg.img_resolution
     cin = cfg.channels(res)
     k = f'synthesis.b{res}.torgb'
-    p[f'{k}.weight'] = _randn(g, cfg.img_channels, cin, 1, 1)
-    p[f'{k}.bias'] = torch.zeros(cfg.img_channels)
+    p[f'{k}.weight'] = _randn(g, cfg.torgb_out_channels, cin, 1, 1)
+    p[f'{k}.bias'] = torch.zeros(cfg.torgb_out_channels)
     p[f'{k}.color_bias'] = torch.zeros(9)
     p[f'{k}.affine.weight'] = _randn(g, cin + 9, cfg.w_dim)
     p[f'{k}.affine.bias'] = torch.ones(cin + 9)

@@ -265,6 +265,14 @@ int nbe_reflect_border_nhwc_bf16(void* buf, int N, int Hp, int Wp, int C, int cs
 int nbe_bilinear2x_pad_nhwc_bf16(const void* x, void* out, int N, int h, int w, int C, int xs_c, int out_cs,
                                  nbe_stream_t stream);
 
+/* ToRGB in the 'canvas' colour format (ToRGBColorTriadLayer with color_format == 'canvas', SG2/training/networks.py:433-481):
+ *   t[k] = clamp(sum_c x[c] * w[k,c] * styles[n,c] + bias[k], +-clamp), k < 8 ;  uvs = softmax(t[0:3]) ; canvas = t[3:6] ;
+ *   alpha = softmax(t[6:8]) ;  img[c] = alpha[0] * sum_k uvs[k] * colors[n,c,k] + alpha[1] * canvas[c]
+ * x as in nbe_torgb_triad; w [8,C]; img / uvs / canvas [N,3,H,W], alpha [N,2,H,W] float32 (each may be NULL). */
+int nbe_torgb_canvas(const void* x, int x_is_bf16, int x_cs, const float* w, const float* styles, const float* bias,
+                     const float* colors, float clamp, float* img, float* uvs, float* canvas, float* alpha,
+                     int N, int C, int H, int W, nbe_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Engine composite and canvas placement.
  */
@@ -278,6 +286,13 @@ int nbe_bilinear2x_pad_nhwc_bf16(const void* x, void* out, int N, int h, int w, 
  * PaintingHelper.render_stroke forger/ui/brush.py:369-377, or NULL. */
 int nbe_triad_composite(const float* uvs, const float* colors01, const float* sfactor, int mode,
                         float* out_f32, uint8_t* out_u8, int N, int H, int W, int crop_margin, nbe_stream_t stream);
+
+/* CanvasPaintEngine._render_stroke_torch tail (forger/ui/brush.py:905-935), outputs as nbe_triad_composite:
+ *   stroke = sum_k uvs_k colors01_k ; cv = (gen_canvas + 1) / 2 ; a = alpha_fg[n * alpha_sn + pix]
+ *   mode 0 'clear': (stroke, a) ; 1 'stroke': (stroke, 1) ; 2 'canvas': (cv, 1) ; 3 'full': ((1 - a) cv + a stroke, 1). */
+int nbe_canvas_composite(const float* uvs, const float* colors01, const float* alpha_fg, int64_t alpha_sn,
+                         const float* gen_canvas, int mode, float* out_f32, uint8_t* out_u8,
+                         int N, int H, int W, int crop_margin, nbe_stream_t stream);
 
 /* geom[n,0,y,x] = 1 - (255 - canvas[(cy[n]+y)*canvas_w + cx[n]+x]) / 255  for 0 <= y,x < P  (float32, 0 = stroke):
  * the crop + `255 - geom` + prepare_geom_input chain of forger/viz/paint_image_main.py:164-167 and

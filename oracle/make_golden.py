@@ -60,7 +60,7 @@ def build_reference_modules(gp, ep, cfg, ecfg):
     enc.eval().requires_grad_(False)
     enc.set_default_encode_resolutions([0, 1])
     syn = dnnlib.EasyDict(channel_base=cfg.channel_base, channel_max=cfg.channel_max, num_fp16_res=cfg.num_fp16_res,
-                          conv_clamp=cfg.conv_clamp, architecture='orig', color_format='triad', color_w_channels=0,
+                          conv_clamp=cfg.conv_clamp, architecture='orig', color_format=cfg.color_format, color_w_channels=0,
                           enable_geom_linear=False,
                           geom_feature_channels=[enc.feature_channels(r) for r in (0, 1)],
                           geom_feature_resolutions=[enc.featuremap_resolution(128, r) for r in (0, 1)])
@@ -302,6 +302,50 @@ def golden_engine(out, G, enc, enc_args, gp, ep, cfg, ecfg):
     save(out, 'engine', **arrays)
 
 
+def golden_canvas(out, ep, ecfg):
+    """The 'canvas' colour format (ToRGBColorTriadLayer with 3 + 5 outputs, networks.py:433-481) through the reference
+    Generator and the reference CanvasPaintEngine (brush.py:870-935) in all four render modes."""
+    import forger.ui.brush as brush
+    cfg = P.GeneratorConfig(color_format='canvas')
+    gp = P.init_generator_params(cfg, seed=3, perturb=0.1)
+    G, enc, enc_args = build_reference_modules(gp, ep, cfg, ecfg)
+    z = torch.cat([P.style_z_from_seed(594), P.style_z_from_seed(7)])
+    geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=3, radius=8),
+                                            synthetic.synthetic_patch(128, seed=4, radius=3)]))
+    gf = enc.encode(geom)
+    img32, dbg = G(z, None, gf, return_debug_data=True, noise_mode='const', force_fp32=True)
+    imgo, dbgo = O.generator_forward(gp, cfg, z, gf)
+    d = max(maxdiff(img32, imgo), *[maxdiff(dbg[k], dbgo[k]) for k in ('uvs', 'colors', 'canvas', 'alpha_fg', 'alpha')])
+    print(f'canvas format generator: oracle vs reference fp32 max diff {d:.3e}')
+    assert d < 1e-4
+    arrays = {'z': z, 'geom': geom, 'img32': img32, 'uvs32_sub': dbg['uvs'][:, :, ::2, ::2], 'colors32': dbg['colors'],
+              'canvas32_sub': dbg['canvas'][:, :, ::2, ::2], 'alpha32_sub': dbg['alpha'][:, :, ::2, ::2], 'gen_digest': np.frombuffer(P.bundle_digest(gp).encode(), dtype=np.uint8)}
+    snap = {'G': G, 'D': torch.nn.Identity(), 'G_ema': G, 'training_set_kwargs': None, 'augment_pipe': None,
+            'args': argparse.Namespace(color_format='canvas', geom_inject_resolutions=[0, 1]),
+            'encoder': {'args': enc_args, 'model_state': enc.state_dict()}}
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, 'snapshot.pkl')
+        with open(path, 'wb') as f:
+            pickle.dump(snap, f)
+        engine = brush.PaintEngineFactory.create(gan_checkpoint=path, device=torch.device('cpu'))
+    assert type(engine).__name__ == 'CanvasPaintEngine'
+    for res in cfg.block_resolutions:
+        getattr(engine.G.synthesis, f'b{res}').use_fp16 = False
+    opts = brush.GanBrushOptions()
+    opts.set_style(z)
+    opts.set_color(1, np.array([255, 0, 128], dtype=np.uint8))
+    for mode in ('clear', 'stroke', 'canvas', 'full'):
+        engine.set_render_mode(mode)
+        rgba, raw, _ = engine._render_stroke_torch(geom, None, opts)
+        ref = O.canvas_composite(dbgo['uvs'], dbgo['colors'], dbgo['alpha_fg'], dbgo['canvas'], mode,
+                                 color1=torch.tensor([1.0, 0.0, 128 / 255]))
+        dm = maxdiff(rgba, ref)
+        print(f'canvas engine [{mode}]: oracle vs reference max diff {dm:.3e}')
+        assert dm < 1e-4
+        arrays[f'rgba_{mode}_sub'] = rgba[:, :, ::2, ::2]
+    save(out, 'canvas', **arrays)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(REPO, 'tests', 'golden'))
@@ -316,6 +360,7 @@ def main():
     golden_ops(args.out)
     golden_generator(args.out, G, enc, gp, ep, cfg, ecfg)
     golden_engine(args.out, G, enc, enc_args, gp, ep, cfg, ecfg)
+    golden_canvas(args.out, ep, ecfg)
 
 
 if __name__ == '__main__':

@@ -394,9 +394,10 @@ def synthesis_layer(p: Bundle, prefix: str, x, w, up: int, noise_mode='const', n
     return bias_act(x, p[f'{prefix}.bias'].to(dtype), act='lrelu', gain=SQRT2 * gain, clamp=act_clamp)
 
 
-def torgb_triad(p: Bundle, prefix: str, x, w, conv_clamp: Optional[float] = 256.0):
+def torgb_triad(p: Bundle, prefix: str, x, w, conv_clamp: Optional[float] = 256.0, color_format: str = 'triad', extra: Optional[dict] = None):
     """``ToRGBColorTriadLayer.forward`` with ``color_w_channels == 0``
-    (networks.py:451-485).  Returns (img, uvs, colors)."""
+    (networks.py:451-485).  Returns (img, uvs, colors); for ``color_format == 'canvas'`` the weight has 3 + 5 output
+    channels and ``extra`` (if given) receives 'canvas', 'alpha_fg', 'alpha' (networks.py:476-481)."""
     dtype = x.dtype
     cin = x.shape[1]
     scaled = fully_connected(w, p[f'{prefix}.affine.weight'], p[f'{prefix}.affine.bias'])
@@ -406,6 +407,14 @@ def torgb_triad(p: Bundle, prefix: str, x, w, conv_clamp: Optional[float] = 256.
     t = bias_act(t, p[f'{prefix}.bias'].to(dtype), clamp=conv_clamp)
     uvs = torch.softmax(t[:, :3], dim=1)
     img = torch.sum(uvs.unsqueeze(1) * colors.unsqueeze(-1).unsqueeze(-1), dim=2)
+    if color_format == 'canvas':
+        canvas = t[:, 3:6]
+        alpha = torch.softmax(t[:, 6:8], dim=1)
+        img = alpha[:, :1] * img + alpha[:, 1:] * canvas
+        if extra is not None:
+            extra['canvas'], extra['alpha_fg'], extra['alpha'] = canvas, alpha[:, :1], alpha
+    elif color_format != 'triad':
+        raise RuntimeError(f'Unknown format {color_format}')
     return img, uvs, colors
 
 
@@ -457,14 +466,16 @@ def synthesis_network(p: Bundle, cfg, ws, geom_feature: Sequence[torch.Tensor], 
                                 norm_positions=norm_positions, input_noise=n1, conv_clamp=cfg.conv_clamp)
             nconv = 2
         if res == last:
-            img, uvs, colors = torgb_triad(p, f'{name}.torgb', x, ws[:, w_idx + nconv], conv_clamp=cfg.conv_clamp)
+            img, uvs, colors = torgb_triad(p, f'{name}.torgb', x, ws[:, w_idx + nconv], conv_clamp=cfg.conv_clamp,
+                                           color_format=getattr(cfg, 'color_format', 'triad'), extra=debug)
             debug['uvs'], debug['colors'] = uvs, colors
         if res in return_features:
             debug[f'features{res}_preblend'] = x
         if res in blended_features:
             x = blended_features[res].blend(x).to(x.dtype)
             if res == last:
-                img, uvs, colors = torgb_triad(p, f'{name}.torgb', x, ws[:, w_idx + nconv], conv_clamp=cfg.conv_clamp)
+                img, uvs, colors = torgb_triad(p, f'{name}.torgb', x, ws[:, w_idx + nconv], conv_clamp=cfg.conv_clamp,
+                                               color_format=getattr(cfg, 'color_format', 'triad'), extra=debug)
                 debug['uvs'], debug['colors'] = uvs, colors
         if res in return_features:
             debug[f'features{res}'] = x
@@ -574,6 +585,27 @@ def triad_composite(uvs, colors, render_mode='clear', color0=None, color1=None, 
     else:
         raise ValueError(render_mode)
     return torch.cat([stroke, alpha], dim=1)
+
+
+def canvas_composite(uvs, colors, alpha_fg, gen_canvas, render_mode='clear', color0=None, color1=None, canvas_color=None):
+    """``CanvasPaintEngine._render_stroke_torch`` tail (brush.py:893-935): ``[B,4,H,W]`` straight RGBA in [0,1];
+    render modes 'clear' (UVS stroke colour + generated foreground alpha), 'stroke' (opaque UVS stroke), 'canvas'
+    (the generated canvas only), 'full' (canvas under the stroke)."""
+    C = ((colors + 1) / 2.0).clone()
+    for idx, col in enumerate((color0, color1, canvas_color)):
+        if col is not None:
+            C[:, :, idx] = col
+    stroke = torch.sum(uvs.unsqueeze(1) * C.unsqueeze(-1).unsqueeze(-1), dim=2)
+    ones = torch.ones_like(stroke[:, :1])
+    if render_mode == 'clear':
+        return torch.cat([stroke, alpha_fg], dim=1)
+    if render_mode == 'stroke':
+        return torch.cat([stroke, ones], dim=1)
+    if render_mode == 'canvas':
+        return torch.cat([(gen_canvas + 1.0) / 2.0, ones], dim=1)
+    if render_mode == 'full':
+        return torch.cat([(1 - alpha_fg) * (gen_canvas + 1.0) / 2.0 + alpha_fg * stroke, ones], dim=1)
+    raise ValueError(render_mode)
 
 
 def to_uint8_tile(rgba, crop_margin: int):

@@ -244,3 +244,34 @@ def test_uvs_mapper_batched_sfactors_icons_and_colors(engines):
     assert spec.count('rgb(') == 3 and spec.count(':') == 2
     icon = single.get_brush_icon(opts[1])
     assert icon.shape == (128, 128, 3) and icon.dtype == np.uint8 and icon.std() > 0
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
+def test_canvas_colour_format_engine(bundles, mode, tol):
+    """'canvas' colour format (networks.py:433-481) + CanvasPaintEngine's four render modes (brush.py:870-935) against the
+    reference-generated fixture (FP32) / the oracle (BF16), and the batched uint8 tiles."""
+    from brushstroke_engine_b200.engine import CanvasPaintEngine, GanBrushOptions
+    _, ecfg, _, ep = bundles
+    g = load_golden('canvas')
+    cfg = P.GeneratorConfig(color_format='canvas')
+    gp = P.init_generator_params(cfg, seed=3, perturb=0.1)
+    assert P.bundle_digest(gp) == bytes(g['gen_digest']).decode()
+    eng = CanvasPaintEngine(gp, ep, DEV, mode=mode)
+    z, geom = t(g['z']), t(g['geom'])
+    o = GanBrushOptions()
+    o.set_style(z.to(DEV))
+    o.set_color(1, np.array([255, 0, 128], dtype=np.uint8))
+    for rm in ('clear', 'stroke', 'canvas', 'full'):
+        eng.set_render_mode(rm)
+        rgba, raw, _ = eng._render_stroke_torch(geom.to(DEV), None, o)
+        assert float((rgba.cpu()[:, :, ::2, ::2] - t(g[f'rgba_{rm}_sub'])).abs().max()) < tol, rm
+        tiles, _ = eng.render_tiles(geom.to(DEV), o, crop_margin=10)
+        ref_u8 = O.to_uint8_tile(rgba.cpu(), 10)
+        assert tiles.shape == (2, 108, 108, 4) and np.abs(tiles.cpu().numpy().astype(int) - ref_u8.astype(int)).max() <= 1
+    assert float((raw['canvas'].cpu()[:, :, ::2, ::2] - t(g['canvas32_sub'])).abs().max()) < tol * 4       # un-normalised logits
+    assert float((raw['alpha'].cpu()[:, :, ::2, ::2] - t(g['alpha32_sub'])).abs().max()) < tol
+    assert set(raw.keys()) >= {'uvs', 'colors', 'canvas', 'alpha_fg', 'alpha', 'ws'}
+    with pytest.raises(RuntimeError):
+        eng.set_render_mode('bogus')
+    with pytest.raises(RuntimeError):
+        CanvasPaintEngine(gp, ep, DEV, mode=mode, gen_cfg=P.GeneratorConfig())

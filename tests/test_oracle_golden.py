@@ -125,3 +125,24 @@ def test_two_restatements_agree():
         a = O.conv2d_resample(x, w, f=f4 if up > 1 else None, up=up, padding=1, flip_weight=fl)
         b = O.conv2d_resample_definition(x, w, f=f4 if up > 1 else None, up=up, padding=1, flip_weight=fl)
         assert a.shape == b.shape and md(a, b) < 2e-5
+
+
+def test_canvas_colour_format(bundles):
+    """'canvas' colour format: 3 + 5 ToRGB outputs, canvas/alpha blend (networks.py:433-481) and the four render modes of
+    ``CanvasPaintEngine`` (brush.py:870-935) against the reference-generated fixture."""
+    _, ecfg, _, ep = bundles
+    g = load_golden('canvas')
+    cfg = P.GeneratorConfig(color_format='canvas')
+    gp = P.init_generator_params(cfg, seed=3, perturb=0.1)
+    assert P.bundle_digest(gp) == bytes(g['gen_digest']).decode()
+    z, geom = t(g['z']), t(g['geom'])
+    gf = O.geometry_encode(ep, ecfg, geom)
+    img, d = O.generator_forward(gp, cfg, z, gf)
+    assert md(img, g['img32']) < 1e-4
+    assert md(d['uvs'][:, :, ::2, ::2], g['uvs32_sub']) < 1e-4 and md(d['colors'], g['colors32']) < 1e-5
+    assert md(d['canvas'][:, :, ::2, ::2], g['canvas32_sub']) < 1e-4 and md(d['alpha'][:, :, ::2, ::2], g['alpha32_sub']) < 1e-4
+    for mode in ('clear', 'stroke', 'canvas', 'full'):
+        rgba = O.canvas_composite(d['uvs'], d['colors'], d['alpha_fg'], d['canvas'], mode, color1=torch.tensor([1.0, 0.0, 128 / 255]))
+        assert md(rgba[:, :, ::2, ::2], g[f'rgba_{mode}_sub']) < 1e-4, mode
+    with pytest.raises(RuntimeError):
+        P.GeneratorConfig(color_format='bogus').torgb_out_channels
