@@ -65,6 +65,7 @@ struct FlatParams {
     // resident: the weights of ONE phase stay in shared memory while the pair sweeps all of its items (phase-major order),
     // so that only the position windows stream from L2; otherwise weights stream through a F_BSTAGES ring (item-major)
     int resident, b_tiles, n_abuf;
+    int nbuf;                                                       // accumulator sets in TMEM: 2 (epilogue overlaps the next MMAs) or 1
     // planes: A chunks are 64 channels of one parity plane of a padded NHWC image (stride-2 convs); cpp = chunks per plane
     int planes, cpp, plane_C, plane_rows;
     int cout_off;                                                   // first output channel of this launch within the weight tiles
@@ -203,7 +204,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const int q0 = (j % p.items_per_img) * T * 128;
                     row0 = (uint32_t)(q0 % p.P);
                 }
-                const int ab = s & 1;
+                const int ab = (p.nbuf == 2) ? (s & 1) : 0;
                 if (resident && k == 0) { mbar_wait(smem_u32(res_full), (uint32_t)(ph & 1)); tcgen05_fence_after(); }
                 if (ab) { mbar_wait_fast(smem_u32(&acc_empty[1]), acc_par1 ^ 1); acc_par1 ^= 1; }
                 else    { mbar_wait_fast(smem_u32(&acc_empty[0]), acc_par0 ^ 1); acc_par0 ^= 1; }
@@ -280,7 +281,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int n = min(2 * np + rank, p.N - 1);
             const int q0 = (j - np * p.items_per_img) * p.T * 128;
             const int G = p.ph_G[ph];
-            const int ab = s & 1;
+            const int ab = (p.nbuf == 2) ? (s & 1) : 0;
             if (EPI == 1 && n != cur_n) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (et < 128) {
@@ -436,6 +437,8 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     if (total * p.n_phases > INT32_MAX) return fail(NBE_EINVAL, "conv_flat: too many work items");
     p.total_items = (int)total;
     p.N = in.N;
+    p.nbuf = (2 * p.T * p.Gmax * 128 <= 512) ? 2 : 1;
+    if (p.T * p.Gmax * 128 > 512) return fail(NBE_EUNSUPPORTED, "conv_flat: accumulators do not fit in TMEM");
     // kind::f16: D = f32, A = B = bf16, K-major; N = 128, M = 256 (the pair)
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     const bool raw = !p.dcoef && !p.noise && !p.bias && !p.act && !p.next_scale;
@@ -579,7 +582,12 @@ extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_o
     NBE_REQUIRE(t_row_pitch >= 2 * W + 1 && t_img_pitch >= t_row_pitch * (2 * H + 1), "convT3x3s2_flat: bad output pitches");
     if (N == 0) return NBE_OK;
     FlatParams p{};
-    p.y = (__nv_bfloat16*)t_out; p.P = x_pitch; p.positions = (H + 1) * x_pitch; p.T = 1;
+    p.y = (__nv_bfloat16*)t_out; p.P = x_pitch; p.positions = (H + 1) * x_pitch;
+    // Cin <= 128: the phase weights stay resident, one tile per item and double-buffered accumulators.  Wider inputs stream
+    // their weights and are L2-bound on them: two tiles per item share every weight tile (all 512 TMEM columns, the epilogue
+    // is then not overlapped -- less than the halved weight traffic buys)
+    static const bool convt_t1 = getenv("NBE_CONVT_T1") != nullptr;
+    p.T = (Cin > 128 && !convt_t1 && (H + 1) * x_pitch >= 1024) ? 2 : 1;            // small maps: padding of the last item costs more
     // T[2Y+kh, 2X+kw] += W[kh,kw] x[Y,X]  (F.conv_transpose2d, SG2/torch_utils/ops/conv2d_resample.py:124-138):
     // class (py,px) at grid (Y',X') sums the taps with kh = py, kw = px (mod 2) over x[Y' - (kh-py)/2, X' - (kw-px)/2].
     // Two phases of two classes each -- {(0,0): 4 taps, (1,1): 1 tap} and {(0,1): 2 taps, (1,0): 2 taps} -- so that a
