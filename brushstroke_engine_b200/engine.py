@@ -14,6 +14,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -221,6 +223,8 @@ class TriadPaintEngine:
         self.render_mode = 'clear'
         self.style_c = None
         self.uvs_mapper = StyleUVSMapper(self)
+        self._side_stream = None
+        self._overlap_styles = os.environ.get('NBE_NO_STREAM_OVERLAP') is None
 
     def set_render_mode(self, mode):
         if mode not in self.render_modes:
@@ -248,12 +252,36 @@ class TriadPaintEngine:
         if fused:
             # mapping first, then the encoder writes g0 / g1 -- already multiplied by the consuming layers' styles --
             # straight into the generator's concatenated, zero-gapped NHWC inputs
-            ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
-            ws = ws.to(self.device, torch.float32).contiguous()
-            inj, dests, scales = G.alloc_injection(ws)
-            self.encoder.encode_into(geom, dests, scales)
             extra = opts.custom_args if opts.style_ws is not None else {}
-            return G.forward_pre_mapped(ws=ws, positions=opts.get_position(self.device), geom_feature=inj,
+            positions = opts.get_position(self.device)
+            if self._overlap_styles and B >= 32 and not torch.cuda.is_current_stream_capturing():
+                # mapping network, per-layer styles / demodulation and the shifted noise maps are small latency-bound kernels
+                # that nothing in the encoder needs before its first feature map: they run on a side stream underneath the
+                # encoder's first layers (large batches only: at batch 1 the extra stream bookkeeping costs more host time than
+                # the overlap saves).  (Memory allocated there is only ever re-used by later side-stream work, which
+                # starts with wait_stream(main), so it cannot be recycled under a main-stream kernel that still reads it.)
+                with torch.cuda.device(self.device):
+                    main = torch.cuda.current_stream()
+                    if self._side_stream is None:
+                        self._side_stream = torch.cuda.Stream(device=self.device)
+                    side = self._side_stream
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
+                        ws = ws.to(self.device, torch.float32).contiguous()
+                        inj, dests, scales = G.alloc_injection(ws)
+                        if 'noise_buffers' not in extra:
+                            G.prefetch_noise(B, positions)
+                        ready = torch.cuda.Event()
+                        ready.record(side)
+                    self.encoder.encode_into(geom, dests, scales, scales_ready=ready)
+                    main.wait_event(ready)
+            else:
+                ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
+                ws = ws.to(self.device, torch.float32).contiguous()
+                inj, dests, scales = G.alloc_injection(ws)
+                self.encoder.encode_into(geom, dests, scales)
+            return G.forward_pre_mapped(ws=ws, positions=positions, geom_feature=inj,
                                         return_debug_data=True, noise_mode='const', **extra, **generator_kwargs)
         geom_feature = self.encoder.encode(geom)
         if opts.style_ws is not None:

@@ -139,6 +139,7 @@ class Generator:
         self.synthesis = SynthesisNetwork(self)
         self._flat_ws = {}
         self._noise_cache = None
+        self._noise_prefetched = None      # one-shot (positions, maps) computed ahead of _synthesis by prefetch_noise
         self.last_up_fir_first = os.environ.get('NBE_LAST_UP_FIR_FIRST') is not None   # A/B switch: 4x-FLOP FIR-first path at 128^2
         self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
         self.probe = None       # optional {layer_name: [(start_event, end_event), ...]} filled by _conv_tc (bench.py roofline)
@@ -345,6 +346,11 @@ class Generator:
                   tab_out, self._ntab_res, _lib.stream())
         return outs
 
+    def prefetch_noise(self, B: int, positions):
+        """Compute the shifted noise maps of the NEXT synthesis call for ``positions`` now (on the current stream); that call
+        picks them up if it is given the same ``positions`` tensor object.  One-shot."""
+        self._noise_prefetched = (positions, self._noise_all(B, positions)) if positions is not None else None
+
     def _synthesis(self, ws, geom_feature, pos_encoding=None, return_debug_data=False, return_features=None,
                    blended_features=None, noise_buffers=None, positions=None, noise_mode='random', force_fp32=False,
                    fused_modconv=None, norm_noise_positions=None, **unused):
@@ -373,7 +379,12 @@ class Generator:
                     raise RuntimeError('synthesis: InjectedGeometry was prepared for a different ws tensor')
                 styles, dcoefs, colors, rgb_styles = self._styles(ws)
             run = self._run_fp32 if mode == 'fp32' else (self._run_bf16_flat if flat else self._run_bf16)
-            self._noise_cache = (positions, self._noise_all(B, positions)) if (positions is not None and noise_mode == 'const') else None
+            pre, self._noise_prefetched = self._noise_prefetched, None
+            if positions is not None and noise_mode == 'const':
+                maps = pre[1] if (pre is not None and pre[0] is positions) else self._noise_all(B, positions)
+                self._noise_cache = (positions, maps)
+            else:
+                self._noise_cache = None
             img, uvs, feats = run(B, styles, dcoefs, colors, rgb_styles, geom_feature, positions, norm_noise_positions,
                                   noise_mode, noise_buffers, return_features, blended_features)
         debug = dict(feats)

@@ -128,11 +128,13 @@ class GeometryEncoder:
             self._ws = {key: ws}                           # keep one batch size resident
         return ws
 
-    def encode_into(self, geom, dests, scales=None):
+    def encode_into(self, geom, dests, scales=None, scales_ready=None):
         """Run the bf16 encoder and write feature map ``r`` (index into ``self.res``) into ``dests[r] = (tensor, c_off)``:
         an NHWC bf16 tensor [B, R, pitch >= R, cs] whose channels [c_off, c_off + C_r) of the first R columns receive the
         features (e.g. the generator's zero-gapped concat buffers), optionally multiplied by ``scales[r]`` ([B, C_r] float32,
-        the consuming layer's styles).  geom: [B,1,H,W] float32, 0 = stroke."""
+        the consuming layer's styles).  geom: [B,1,H,W] float32, 0 = stroke.
+        ``scales_ready``: CUDA event after which ``scales`` (and the destination buffers) may be touched; the layers before
+        the first feature map are issued without waiting for it (the caller computes the styles on another stream)."""
         assert self.mode == 'bf16'
         _lib.require_cuda(geom, 'GeometryEncoder.encode_into')
         geom = geom.to(torch.float32).contiguous()
@@ -175,6 +177,9 @@ class GeometryEncoder:
                 last_layer = i == n_layers - 1
                 next_scale = None
                 direct = is_feat and last_layer             # nothing else consumes it: write (pre-scaled) straight into the destination
+                if is_feat and scales_ready is not None:
+                    torch.cuda.current_stream().wait_event(scales_ready)      # first consumer of the styles / destination buffers
+                    scales_ready = None
                 if direct:
                     dst, c_off = dests[res.index(feat_idx)]
                     assert dst.dtype == torch.bfloat16 and dst.shape[0] == B and dst.shape[1] == ho and dst.shape[2] >= ho \
