@@ -72,3 +72,34 @@ def test_ops_refuse_cpu_tensors():
         modconv.modulated_conv2d(x, torch.zeros(3, 2, 3, 3), torch.ones(1, 2))
     with pytest.raises(RuntimeError, match="impl='cuda'"):
         bias_act.bias_act(x, impl='ref')
+
+
+def test_tensor_core_entry_points_validate_before_launching():
+    """The tcgen05 / canvas entry points reject what they cannot run with a message naming the constraint; all of these
+    checks sit in front of the first CUDA call (dummy non-null pointers, no GPU needed)."""
+    P = 4096                                                             # any non-null, 16-byte aligned "pointer"
+    cases = [
+        ('Cout must be a multiple of 128', 'nbe_conv3x3_flat_bf16',
+         (P, P, P, 1, 8, 8, 64, 64, 9, 0, 96, 96, 8, 64, None, None, 0, 0.0, None, 0.2, 1.0, -1.0, None, None)),
+        ('input pitch', 'nbe_conv3x3_flat_bf16',
+         (P, P, P, 1, 8, 8, 64, 64, 8, 0, 128, 128, 8, 64, None, None, 0, 0.0, None, 0.2, 1.0, -1.0, None, None)),
+        ('16-byte aligned', 'nbe_conv3x3_flat_bf16',
+         (P + 2, P, P, 1, 8, 8, 64, 64, 9, 0, 128, 128, 8, 64, None, None, 0, 0.0, None, 0.2, 1.0, -1.0, None, None)),
+        ('H, W must be even', 'nbe_conv3x3s2_flat_bf16',
+         (P, P, P, 1, 7, 8, 64, 128, 128, 4, 16, None, 0.01, 1.0, -1.0, None, None)),
+        ('Cin must be a multiple of 64', 'nbe_conv3x3s2_flat_bf16',
+         (P, P, P, 1, 8, 8, 48, 128, 128, 4, 16, None, 0.01, 1.0, -1.0, None, None)),
+        ('zero gap column', 'nbe_convT3x3s2_flat_bf16',
+         (P, P, P, 1, 8, 8, 128, 128, 8, 128, 128, 18, 18 * 18, None, None)),
+        ('bad output pitches', 'nbe_convT3x3s2_flat_bf16',
+         (P, P, P, 1, 8, 8, 128, 128, 9, 128, 128, 16, 16 * 16, None, None)),
+        ('does not match input', 'nbe_fir_act_nhwc_bf16',
+         (P, P, P, 1, 16, 16, 128, 16, 16, 1, 128, 18, 18 * 18, 128, 16, 256, 4.0, None, None, 0, 0.0, None, 0.2, 1.0, -1.0, None, None)),
+        ('unknown render mode', 'nbe_canvas_composite', (P, P, P, 0, P, 7, P, None, 1, 8, 8, 0, None)),
+        ('no output', 'nbe_canvas_composite', (P, P, P, 0, P, 0, None, None, 1, 8, 8, 0, None)),
+        ('too many channels', 'nbe_torgb_canvas', (P, 0, 0, P, P, P, P, 256.0, P, P, P, P, 1, 4096, 8, 8, None)),
+    ]
+    for needle, name, args in cases:
+        with pytest.raises(RuntimeError, match=name) as ei:
+            _lib.call(name, *args)
+        assert needle in str(ei.value), (name, needle, str(ei.value))
