@@ -108,3 +108,15 @@ def test_blending_wavefronts_respect_raster_dependencies():
     import pytest
     with pytest.raises(RuntimeError):
         blending_wavefronts(np.array([[0, 0], [0, 60]]), 128)                        # stride <= half a patch
+
+
+def test_shard_bounds_equals_shard_crops():
+    import numpy as np
+    from brushstroke_engine_b200.stylizer import shard_bounds, shard_crops
+    ys, xs = np.meshgrid(np.arange(11) * 108, np.arange(7) * 108, indexing='ij')
+    yx = np.stack([ys.ravel(), xs.ravel()], axis=1)
+    yx = yx[np.r_[0:20, 23:len(yx)]]                                      # a ragged row
+    crops = [(int(y), int(x), 128, 128) for y, x in yx]
+    for world in (1, 2, 3, 8, 16):
+        assert shard_bounds(yx, world) == [shard_crops(crops, world, r) for r in range(world)]
+    assert shard_bounds(np.zeros((0, 2), dtype=np.int32), 4) == [(0, 0)] * 4
