@@ -204,7 +204,12 @@ class CanvasJob:
                 alpha = result[..., 3:].to(torch.float32) / 255
                 result = (result[..., :3].to(torch.float32) * alpha + 255 * (1 - alpha)).clip(0, 255).to(torch.uint8)
             return result
-        result = result.cpu().numpy()
+        # download through pinned memory (torch's caching host allocator makes the buffer free after the first call): ~3x
+        # the bandwidth of a pageable copy, and the strided crop is compacted on the device first
+        host = torch.empty(tuple(result.shape), dtype=result.dtype, pin_memory=True)
+        host.copy_(result.contiguous(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        result = host.numpy()
         if on_white:
             result = composite_on_white(result)
         return result
