@@ -194,3 +194,14 @@ def test_conv3x3_flat_two_output_passes():
     assert md(got, ref) < 1e-2 * max(float(ref.abs().max()), 1.0)
     assert float((y[:, :, R:, :].float() - 3.0).abs().max()) == 0
     assert float((y[..., cout:].float() - 3.0).abs().max()) == 0
+
+
+def test_random_shape_sweep():
+    """Odd sizes, ragged channel counts, odd batches (dummy CTA of the last pair), all four kernels: tools/fuzz_flat.py."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fuzz_flat.py'), '40', '7'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'worst relative error' in r.stdout
