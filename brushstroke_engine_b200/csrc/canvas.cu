@@ -87,6 +87,24 @@ canvas_composite_kernel(const float* __restrict__ uvs, const float* __restrict__
     }
 }
 
+// counts[r * ncols + c] = number of stroke (== 0) pixels of the P x P crop at (r * stride, c * stride): the "> 10 stroke
+// pixels" filter of generate_stitching_crops (style_transfer.py:45).  One warp per crop.
+__global__ void __launch_bounds__(256)
+count_stroke_kernel(const uint8_t* __restrict__ canvas, int canvas_h, int canvas_w, int P, int stride, int nrows, int ncols,
+                    int32_t* __restrict__ counts) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nrows * ncols) return;
+    const int y0 = (warp / ncols) * stride, x0 = (warp % ncols) * stride;
+    int n = 0;
+    for (int i = lane; i < P * P; i += 32) {
+        const int y = y0 + i / P, x = x0 + i % P;
+        if (y < canvas_h && x < canvas_w && canvas[(long long)y * canvas_w + x] == 0) ++n;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) n += __shfl_xor_sync(0xffffffffu, n, off);
+    if (lane == 0) counts[warp] = n;
+}
+
 __global__ void __launch_bounds__(256)
 gather_geom_kernel(const uint8_t* __restrict__ canvas, int canvas_h, int canvas_w, const int32_t* __restrict__ crops,
                    float* __restrict__ geom, int N, int P) {
@@ -160,6 +178,17 @@ extern "C" int nbe_canvas_composite(const float* uvs, const float* colors01, con
     canvas_composite_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         uvs, colors01, alpha_fg, alpha_sn, gen_canvas, mode, out_f32, out_u8, N, H, W, crop_margin);
     return launched("canvas_composite_kernel");
+}
+
+extern "C" int nbe_count_stroke_pixels(const uint8_t* canvas, int canvas_h, int canvas_w, int P, int stride, int nrows, int ncols,
+                                       int32_t* counts, nbe_stream_t stream) {
+    NBE_REQUIRE(canvas && counts && canvas_h >= 1 && canvas_w >= 1 && P >= 1 && stride >= 1 && nrows >= 0 && ncols >= 0,
+                "count_stroke_pixels: bad arguments");
+    const int64_t crops = (int64_t)nrows * ncols;
+    if (crops == 0) return NBE_OK;
+    NBE_REQUIRE(crops <= INT32_MAX / 32, "count_stroke_pixels: too many crops");
+    count_stroke_kernel<<<(int)((crops * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(canvas, canvas_h, canvas_w, P, stride, nrows, ncols, counts);
+    return launched("count_stroke_kernel");
 }
 
 extern "C" int nbe_gather_geom_patches(const uint8_t* canvas, int canvas_h, int canvas_w, const int32_t* crops, float* geom,

@@ -138,6 +138,41 @@ bilinear2x_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
     }
 }
 
+// ---- FP32 parity mode (NCHW float32) ---------------------------------------------------------------------
+// y[nc, i, j] = x[nc, r(i - pad, H), r(j - pad, W)],  r = reflection without repeating the edge (padding_mode='reflect',
+// simple_autoencoder.py:98), optionally of the bilinear x2 up-sampling of x (align_corners=True, ScaleUp :117): the
+// up-sampled map is never materialised.
+__global__ void __launch_bounds__(256)
+reflect_pad_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, long long NC, int H, int W, int pad, int up) {
+    const int SH = up ? 2 * H : H, SW = up ? 2 * W : W;            // size of the (virtual) source map
+    const int OH = SH + 2 * pad, OW = SW + 2 * pad;
+    const long long total = NC * OH * OW;
+    const float sy = (SH > 1) ? (float)(H - 1) / (float)(SH - 1) : 0.f, sx = (SW > 1) ? (float)(W - 1) / (float)(SW - 1) : 0.f;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % OW);
+        const long long t = idx / OW;
+        const int i = (int)(t % OH);
+        const long long nc = t / OH;
+        int u = i - pad, v = j - pad;
+        u = u < 0 ? -u : u; u = u >= SH ? 2 * SH - 2 - u : u;
+        v = v < 0 ? -v : v; v = v >= SW ? 2 * SW - 2 - v : v;
+        const float* xp = x + nc * H * W;
+        float r;
+        if (!up) r = xp[(long long)u * W + v];
+        else {
+            // torch's upsample_bilinear2d, align_corners=True: src = dst * (in - 1) / (out - 1)
+            const float fy = sy * (float)u, fx = sx * (float)v;
+            const int y0 = (int)fy, x0 = (int)fx;
+            const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+            const float ly = fy - (float)y0, lx = fx - (float)x0;
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            r = hy * (hx * xp[(long long)y0 * W + x0] + lx * xp[(long long)y0 * W + x1]) +
+                ly * (hx * xp[(long long)y1 * W + x0] + lx * xp[(long long)y1 * W + x1]);
+        }
+        y[idx] = r;
+    }
+}
+
 }  // namespace nbe
 
 using namespace nbe;
@@ -176,4 +211,17 @@ extern "C" int nbe_bilinear2x_pad_nhwc_bf16(const void* x, void* out, int N, int
     if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
     bilinear2x_pad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, h, w, C, xs_c, out_cs);
     return launched("bilinear2x_pad_kernel");
+}
+
+extern "C" int nbe_reflect_pad_nchw_f32(const float* x, float* y, int64_t NC, int H, int W, int pad, int upsample2x,
+                                        nbe_stream_t stream) {
+    NBE_REQUIRE(x && y && NC >= 0 && H >= 1 && W >= 1 && pad >= 0, "reflect_pad_nchw: bad arguments");
+    const int SH = upsample2x ? 2 * H : H, SW = upsample2x ? 2 * W : W;
+    NBE_REQUIRE(pad < SH && pad < SW, "reflect_pad_nchw: padding %d must be smaller than the map (%d x %d)", pad, SH, SW);
+    if (NC == 0) return NBE_OK;
+    const int64_t total = NC * (SH + 2 * pad) * (SW + 2 * pad);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+    reflect_pad_nchw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, NC, H, W, pad, upsample2x ? 1 : 0);
+    return launched("reflect_pad_nchw_kernel");
 }

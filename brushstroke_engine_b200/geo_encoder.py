@@ -23,7 +23,6 @@ from typing import List
 
 import os
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from .conv2d_resample import conv2d_f32
@@ -253,9 +252,14 @@ class GeometryEncoder:
         results = []
         max_res = res if not isinstance(res, (list, tuple)) else max(res)
         for i, (w, b, stride, pad, up) in enumerate(self._layers[: self._n_enc + max_res]):
-            if up:
-                x = F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)
-            x = F.pad(x, (pad, pad, pad, pad), mode='reflect')
+            # reflect padding (of the bilinear x2 map for ScaleUp layers) in one kernel: no torch compute on this path
+            x = x.contiguous()
+            S = 2 if up else 1
+            xp = torch.empty((x.shape[0], x.shape[1], S * x.shape[2] + 2 * pad, S * x.shape[3] + 2 * pad), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                _lib.call('nbe_reflect_pad_nchw_f32', _lib.ptr(x), _lib.ptr(xp), x.shape[0] * x.shape[1], x.shape[2], x.shape[3], pad,
+                          int(bool(up)), _lib.stream())
+            x = xp
             x = conv2d_f32(x, w, padding=0, stride=stride, bias=b, act=ACT_LRELU, alpha=self.cfg.neg_slope, gain=1.0)
             if i >= self._n_enc - 1:
                 results.append(x)

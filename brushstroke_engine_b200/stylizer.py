@@ -140,9 +140,11 @@ class CanvasJob:
         d_yx = None
         if stitching_mode != 'all':
             # keep crops with more than 10 stroke (zero) pixels (style_transfer.py:45): window sums on the device
-            zeros = (self.d_geom == 0).to(torch.float32)[None, None]
-            counts = torch.nn.functional.avg_pool2d(zeros, self.patch, stride=rwidth, divisor_override=1)[0, 0]
-            keep = (counts[:nrows, :ncols] > 10).cpu().numpy().ravel()
+            counts = torch.empty((nrows * ncols,), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.call('nbe_count_stroke_pixels', _lib.ptr(self.d_geom), ph, pw, self.patch, rwidth, nrows, ncols, _lib.ptr(counts),
+                          _lib.stream())
+            keep = (counts > 10).cpu().numpy()
             yx = yx[keep]
         else:
             # the full grid is pure arithmetic: build it on the device too instead of uploading it (no synchronous copy)

@@ -265,6 +265,13 @@ int nbe_reflect_border_nhwc_bf16(void* buf, int N, int Hp, int Wp, int C, int cs
 int nbe_bilinear2x_pad_nhwc_bf16(const void* x, void* out, int N, int h, int w, int C, int xs_c, int out_cs,
                                  nbe_stream_t stream);
 
+/* FP32 parity mode of the same two steps on NCHW float32: y = reflect_pad(x, pad) (padding_mode='reflect',
+ * simple_autoencoder.py:98), or, with upsample2x != 0, y = reflect_pad(bilinear_x2(x), pad) with align_corners=True
+ * (ScaleUp, simple_autoencoder.py:117) without materialising the up-sampled map.
+ * x: [NC, H, W]; y: [NC, S*H + 2 pad, S*W + 2 pad], S = 2 if upsample2x else 1. */
+int nbe_reflect_pad_nchw_f32(const float* x, float* y, int64_t NC, int H, int W, int pad, int upsample2x,
+                             nbe_stream_t stream);
+
 /* ToRGB in the 'canvas' colour format (ToRGBColorTriadLayer with color_format == 'canvas', SG2/training/networks.py:433-481):
  *   t[k] = clamp(sum_c x[c] * w[k,c] * styles[n,c] + bias[k], +-clamp), k < 8 ;  uvs = softmax(t[0:3]) ; canvas = t[3:6] ;
  *   alpha = softmax(t[6:8]) ;  img[c] = alpha[0] * sum_k uvs[k] * colors[n,c,k] + alpha[1] * canvas[c]
@@ -293,6 +300,12 @@ int nbe_triad_composite(const float* uvs, const float* colors01, const float* sf
 int nbe_canvas_composite(const float* uvs, const float* colors01, const float* alpha_fg, int64_t alpha_sn,
                          const float* gen_canvas, int mode, float* out_f32, uint8_t* out_u8,
                          int N, int H, int W, int crop_margin, nbe_stream_t stream);
+
+/* counts[r*ncols + c] = number of stroke pixels (== 0) of the P x P crop at (r*stride, c*stride) of the padded guidance
+ * (pixels outside the canvas do not count): the "more than 10 stroke pixels" crop filter of
+ * forger/viz/style_transfer.py:43-47 for stitching modes other than 'all'. */
+int nbe_count_stroke_pixels(const uint8_t* canvas, int canvas_h, int canvas_w, int P, int stride, int nrows, int ncols,
+                            int32_t* counts, nbe_stream_t stream);
 
 /* geom[n,0,y,x] = 1 - (255 - canvas[(cy[n]+y)*canvas_w + cx[n]+x]) / 255  for 0 <= y,x < P  (float32, 0 = stroke):
  * the crop + `255 - geom` + prepare_geom_input chain of forger/viz/paint_image_main.py:164-167 and

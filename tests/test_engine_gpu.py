@@ -275,3 +275,32 @@ def test_canvas_colour_format_engine(bundles, mode, tol):
         eng.set_render_mode('bogus')
     with pytest.raises(RuntimeError):
         CanvasPaintEngine(gp, ep, DEV, mode=mode, gen_cfg=P.GeneratorConfig())
+
+
+def test_sparse_stitching_mode_keeps_the_oracles_crops(engines):
+    """Stitching modes other than 'all' keep the crops with more than 10 stroke pixels (style_transfer.py:43-47); the
+    window counts come from nbe_count_stroke_pixels."""
+    from brushstroke_engine_b200 import stylizer
+    eng = engines['bf16']
+    guidance = synthetic.synthetic_guidance(700, 900, num_lines=3, seed=2, radii=(2, 3))      # sparse: many empty crops
+    job = stylizer.CanvasJob(eng, guidance, 10, 'stroke')
+    ref_crops, _ = O.generate_stitching_crops(O.pad_geo(guidance, 10), 128, 'stroke', 20)
+    assert job.crops == ref_crops
+    full = stylizer.CanvasJob(eng, guidance, 10, 'all')
+    assert 0 < len(job.crops) < len(full.crops)
+    out = stylizer.stylize(eng, guidance, _opts(P.style_z_from_seed(5), '5'), crop_margin=10, stitching_mode='stroke')
+    assert out.shape == (700, 900, 4) and int((out[..., 3] > 0).sum()) > 500
+
+
+def test_fp32_reflect_pad_and_bilinear_kernel_matches_torch():
+    import torch.nn.functional as F
+    from brushstroke_engine_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    for (n, c, h, w, pad, up) in [(2, 3, 9, 7, 1, 0), (1, 5, 16, 16, 3, 0), (3, 4, 8, 8, 1, 1), (2, 2, 5, 11, 1, 1)]:
+        x = torch.randn(n, c, h, w, generator=g).to(DEV)
+        S = 2 if up else 1
+        y = torch.empty((n, c, S * h + 2 * pad, S * w + 2 * pad), device=DEV)
+        _lib.call('nbe_reflect_pad_nchw_f32', _lib.ptr(x), _lib.ptr(y), n * c, h, w, pad, up, _lib.stream())
+        ref = F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True) if up else x
+        ref = F.pad(ref, (pad, pad, pad, pad), mode='reflect')
+        assert float((y - ref).abs().max()) < (2e-6 if up else 0.0) + 1e-12, (n, c, h, w, pad, up)
