@@ -376,10 +376,12 @@ def main():
                                       'ms_host_to_host adds the guidance upload and the canvas download (rank-0 wall clock)'}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n = 8
-            v, times_cpu = cpu_port_patches_per_sec(sets, n, 3, threads)
+            # bounded sample, ~10 s of CPU work: 8-patch batches (the port's fastest batch size; larger ones are slower per patch)
+            n, reps = 8, 48
+            v, times_cpu = cpu_port_patches_per_sec(sets, n, reps, threads)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                    'sample': f'{n} patches x 3 reps of the same workload (fp32 oracle port, {threads} threads, median)'}
+                                    'sample': f'{n} patches x {reps} reps of the same workload (fp32 oracle port, {threads} threads, median; '
+                                              f'{sum(times_cpu):.1f} s of CPU work)'}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
