@@ -312,11 +312,18 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         long long rp[4];
 #pragma unroll
                         for (int r8 = 0; r8 < 4; ++r8) rp[r8] = __shfl_sync(0xffffffffu, pix, r8 * 8 + rd_row0);
-#pragma unroll 1
+                        // both 32-column halves of this warp's 64 channels are requested before the one wait
+                        uint32_t vv[2][32];
+                        {
+                            const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * set_cols + (i * G + gl) * 128 + hsel * 64);
+                            tmem_ld32_nowait(ta, vv[0]);
+                            tmem_ld32_nowait(ta + 32, vv[1]);
+                            tmem_ld_wait();
+                        }
+#pragma unroll
                         for (int c32 = 0; c32 < 2; ++c32) {
                             const int c0 = hsel * 64 + c32 * 32;
-                            uint32_t v[32];
-                            tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * set_cols + (i * G + gl) * 128 + c0), v);
+                            uint32_t (&v)[32] = vv[c32];
 #pragma unroll
                             for (int gg = 0; gg < 4; ++gg) {
                                 uint32_t o[4];
