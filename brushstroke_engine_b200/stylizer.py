@@ -426,17 +426,19 @@ def _stylize_blended_wavefront(engine: TriadPaintEngine, job: CanvasJob, opts: G
     z_sel = z_per_patch[d_order] if z_per_patch is not None else None
     alpha_pos = (base_alpha > 0)[None]
     one = torch.ones((), device=dev)
+    # feature-canvas row / column of every window element of every patch, once for the whole schedule (views below)
+    all_rows = (d_fy[:, None] + ar[None, :])[:, :, None].expand(-1, res, res)
+    all_cols = (d_fx[:, None] + ar[None, :])[:, None, :].expand(-1, res, res)
+    base_alpha_b = base_alpha[None]
     off = 0
     for idx in waves:
         n = len(idx)
         sl = slice(off, off + n)
         off += n
-        fy, fx = d_fy[sl], d_fx[sl]
-        rows = (fy[:, None] + ar[None, :])[:, :, None].expand(n, res, res)                # [n,res,res] feature-canvas rows
-        cols = (fx[:, None] + ar[None, :])[:, None, :].expand(n, res, res)
+        rows, cols = all_rows[sl], all_cols[sl]                                           # [n,res,res]
         m = mask[rows, cols]                                                              # [n,res,res]
         update = (base_update[None] | (m & alpha_pos)) & inner[None]
-        alpha = torch.where(m, base_alpha[None], one)
+        alpha = torch.where(m, base_alpha_b, one)
         saved = features[:, rows, cols].permute(1, 0, 2, 3)                               # [n,C,res,res]
         geom = torch.empty((n, 1, job.patch, job.patch), dtype=torch.float32, device=dev)
         _lib.call('nbe_gather_geom_patches', _lib.ptr(job.d_geom), job.canvas_h, job.canvas_w, _lib.ptr(d_cropsel[sl]), _lib.ptr(geom), n,
