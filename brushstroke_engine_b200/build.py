@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed building libnbe_b200.so')
-    cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-lcudart']
+    cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs + ['-lcudart']
     subprocess.check_call(cmd)
     return LIB
 
