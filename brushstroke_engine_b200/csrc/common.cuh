@@ -60,6 +60,32 @@ __device__ __forceinline__ void st_stream16(void* p, const int4& v) {
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Packed FP32 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — two IEEE-rn lanes per issued instruction).  The scalar FP32 pipe
+// issues one 3-register FFMA per two cycles per SM sub-partition; the chip's FP32 peak is only reachable through these.
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+// two bf16 in one 32-bit word -> two exact floats (low half first)
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
 __device__ __forceinline__ float lrelu_gain_clamp(float v, float alpha, float gain, float clamp) {
     v = (v > 0.f) ? v : v * alpha;
     v *= gain;

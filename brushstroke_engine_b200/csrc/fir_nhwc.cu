@@ -159,16 +159,18 @@ constexpr int FT_OW = 16, FT_OH = 8;
 constexpr int FT_IW = FT_OW + 3, FT_IH = FT_OH + 3;
 constexpr int FT_TILE_BYTES = FT_IH * FT_IW * 256;                  // 128 bf16 channels per pixel
 
+template <bool PACKED>
 __global__ void __launch_bounds__(256, 2)
-fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams p, int tiles_x, int tiles_y, int total_tiles) {
+fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_constant__ CUtensorMap tmap_nz, const FirParams p,
+                     int tiles_x, int tiles_y, int total_tiles, int noise_mode) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     uint8_t* bufs = smem;                                           // [2][FT_TILE_BYTES]
-    float* s_epi = reinterpret_cast<float*>(bufs + 2 * ((FT_TILE_BYTES + 127) & ~127));   // [3][128]
-    float* s_f = s_epi + 3 * 128;                                   // [16]
-    float* s_nz = s_f + 16;                                         // [FT_OH][FT_OW] noise of the current tile
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_nz + FT_OH * FT_OW);   // [2]
     constexpr int BUF_STRIDE = (FT_TILE_BYTES + 127) & ~127;
+    float* s_nz = reinterpret_cast<float*>(bufs + 2 * BUF_STRIDE);  // [2][FT_OH][FT_OW] noise tiles (TMA destinations, 512 B each)
+    float* s_epi = s_nz + 2 * FT_OH * FT_OW;                        // [3][128]
+    float* s_f = s_epi + 3 * 128;                                   // [16]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_f + 16);         // [2]
 
     if (threadIdx.x < 16) {
         const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
@@ -178,7 +180,9 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
         mbar_init(smem_u32(&full[0]), 1); mbar_init(smem_u32(&full[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_t) : "memory");
+        if (noise_mode == 1) asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_nz) : "memory");
     }
+    if (noise_mode == 2) s_nz[threadIdx.x] = 0.f;                   // no noise input: both tiles stay zero (2 x 128 floats)
     __syncthreads();
     float f[16];
 #pragma unroll
@@ -199,20 +203,27 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
     const bool fold = p.gain > 0.f && p.alpha >= 0.f && p.alpha <= 1.f;
     const float g_pre = fold ? p.gain : 1.f, g_post = fold ? 1.f : p.gain;
     const float clamp_hi = p.clamp >= 0.f ? p.clamp : INFINITY;
+    const float ngain = p.noise_gain * g_pre;
+    // noise_mode 1: the tile's 8 x 16 noise values arrive by TMA with the tile itself (same mbarrier; out-of-range elements are
+    // zero-filled); 0: staged by the threads (noise tensors TMA cannot describe); 2: no noise
     auto issue = [&](int tile, int b) {
         int t = tile;
         const int tx = t % tiles_x; t /= tiles_x;
         const int ty = t % tiles_y; t /= tiles_y;
         const uint32_t bar = smem_u32(&full[b]);
-        mbar_expect_tx(bar, FT_TILE_BYTES);
+        mbar_expect_tx(bar, FT_TILE_BYTES + (noise_mode == 1 ? FT_OH * FT_OW * 4 : 0));
         tma_load_4d(smem_u32(bufs + b * BUF_STRIDE), &tmap_t, bar, 0, tx * FT_OW - p.pad, ty * FT_OH - p.pad, t);
+        if (noise_mode == 1) tma_load_3d(smem_u32(s_nz + b * FT_OH * FT_OW), &tmap_nz, bar, tx * FT_OW, ty * FT_OH, p.noise_sn ? t : 0);
     };
-    if (threadIdx.x == 0 && (int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+    // every CTA takes one contiguous run of tiles: the image (and with it the per-channel epilogue vectors in s_epi) changes
+    // once per 128 tiles instead of at every tile, so the loop has no exposed global-memory round trip and one barrier per tile
+    const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_begin = blockIdx.x * per_cta, t_end = min(total_tiles, t_begin + per_cta);
+    if (threadIdx.x == 0 && t_begin < t_end) issue(t_begin, 0);
     int it = 0, cur_n = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const int b = it & 1;
-        const int next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < total_tiles) issue(next, b ^ 1);     // buffer b^1 was released by the __syncthreads of the previous iteration
+        if (threadIdx.x == 0 && tile + 1 < t_end) issue(tile + 1, b ^ 1);   // buffer b^1 was released by the __syncthreads of the previous iteration
         int t = tile;
         const int tx = t % tiles_x; t /= tiles_x;
         const int ty = t % tiles_y; t /= tiles_y;
@@ -229,16 +240,17 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
         const int ox = tx * FT_OW + px, oy0 = ty * FT_OH;
         // tiles that lie completely inside the output (all of them at 2^k resolutions) skip the per-store bounds checks
         const bool full_tile = oy0 + FT_OH <= p.OH && tx * FT_OW + FT_OW <= p.OW;
-        // the tile's noise (already times noise_gain * folded gain) is staged in shared memory before waiting for the tile,
-        // off the critical path and out of the register file
-        if (threadIdx.x < FT_OH * FT_OW) {
-            const int r = threadIdx.x / FT_OW, c = threadIdx.x - r * FT_OW;
-            const int oy = oy0 + r, oxx = tx * FT_OW + c;
-            float v = 0.f;
-            if (p.noise && oy < p.OH && oxx < p.OW) v = __ldg(p.noise + (long long)n * p.noise_sn + (long long)oy * p.OW + oxx) * (p.noise_gain * g_pre);
-            s_nz[threadIdx.x] = v;
+        const float* s_nzb = s_nz + b * FT_OH * FT_OW;
+        if (noise_mode == 0) {
+            if (threadIdx.x < FT_OH * FT_OW) {
+                const int r = threadIdx.x / FT_OW, c = threadIdx.x - r * FT_OW;
+                const int oy = oy0 + r, oxx = tx * FT_OW + c;
+                float v = 0.f;
+                if (oy < p.OH && oxx < p.OW) v = __ldg(p.noise + (long long)n * p.noise_sn + (long long)oy * p.OW + oxx);
+                s_nz[b * FT_OH * FT_OW + threadIdx.x] = v;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         float sc[4], bs[4], ns[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { sc[k] = s_epi[cq * 4 + k]; bs[k] = s_epi[128 + cq * 4 + k]; ns[k] = s_epi[256 + cq * 4 + k]; }
@@ -259,7 +271,7 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
             constexpr bool FULL = decltype(full_c)::value;
             auto finish = [&](int r, int j, float (&acc)[4]) {
                 if (!FULL && (oy0 + r >= p.OH || ox + j >= p.OW)) return;
-                const float nzg = s_nz[r * FT_OW + px + j];
+                const float nzg = s_nzb[r * FT_OW + px + j] * ngain;
                 float o[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -274,7 +286,66 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const FirParams
                 *reinterpret_cast<__nv_bfloat162*>(&outv.y) = __floats2bfloat162_rn(o[2], o[3]);
                 __stcs(reinterpret_cast<uint2*>(yrow + j * ycs), outv);
             };
-            if (sep) {
+            if (PACKED && sep) {
+                // the same arithmetic on register pairs: FFMA2 / FMUL2 / FADD2 halve the FP32-pipe instruction count
+                // (6.75 instead of 13.5 per output), which is what bounds this pass
+                const float2 fx2[4] = {{fx[0], fx[0]}, {fx[1], fx[1]}, {fx[2], fx[2]}, {fx[3], fx[3]}};
+                const float2 fy2[4] = {{fy[0], fy[0]}, {fy[1], fy[1]}, {fy[2], fy[2]}, {fy[3], fy[3]}};
+                const float2 sc2[2] = {{sc[0], sc[1]}, {sc[2], sc[3]}}, bs2[2] = {{bs[0], bs[1]}, {bs[2], bs[3]}};
+                const float2 ns2[2] = {{ns[0], ns[1]}, {ns[2], ns[3]}}, alpha2 = {alpha, alpha};
+                auto finish2 = [&](int r, int j, float2 (&acc)[2]) {
+                    if (!FULL && (oy0 + r >= p.OH || ox + j >= p.OW)) return;
+                    const float nzg = s_nzb[r * FT_OW + px + j] * ngain;
+                    const float2 nz2 = {nzg, nzg};
+                    float2 o[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float2 a = fma2(acc[q], sc2[q], add2(nz2, bs2[q]));
+                        if (fold) {
+                            const float2 m = mul2(a, alpha2);
+                            a.x = fmaxf(a.x, m.x); a.y = fmaxf(a.y, m.y);
+                        } else {
+                            a.x *= ((a.x > 0.f) ? 1.f : alpha) * g_post; a.y *= ((a.y > 0.f) ? 1.f : alpha) * g_post;
+                        }
+                        a.x = fminf(fmaxf(a.x, -clamp_hi), clamp_hi); a.y = fminf(fmaxf(a.y, -clamp_hi), clamp_hi);
+                        o[q] = mul2(a, ns2[q]);
+                    }
+                    uint2 outv;
+                    *reinterpret_cast<__nv_bfloat162*>(&outv.x) = __floats2bfloat162_rn(o[0].x, o[0].y);
+                    *reinterpret_cast<__nv_bfloat162*>(&outv.y) = __floats2bfloat162_rn(o[1].x, o[1].y);
+                    __stcs(reinterpret_cast<uint2*>(yrow + j * ycs), outv);
+                };
+                float2 h[4][2][2];
+                auto hrow2 = [&](float2 (&dst)[2][2], int r) {
+                    float2 v[5][2];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        uint32_t x, y2;
+                        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y2) : "r"(tb + (uint32_t)((r * FT_IW + c) * 256)));
+                        v[c][0] = bf16x2_to_f2(x); v[c][1] = bf16x2_to_f2(y2);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+                            dst[j][q] = fma2(fx2[3], v[j + 3][q], fma2(fx2[2], v[j + 2][q], fma2(fx2[1], v[j + 1][q], mul2(fx2[0], v[j][q]))));
+                };
+                hrow2(h[0], 0); hrow2(h[1], 1); hrow2(h[2], 2);
+#pragma unroll
+                for (int r = 0; r < FT_OH; ++r) {
+                    hrow2(h[(r + 3) & 3], r + 3);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float2 acc[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+                            acc[q] = fma2(fy2[3], h[(r + 3) & 3][j][q], fma2(fy2[2], h[(r + 2) & 3][j][q],
+                                     fma2(fy2[1], h[(r + 1) & 3][j][q], mul2(fy2[0], h[r & 3][j][q]))));
+                        finish2(r, j, acc);
+                    }
+                    yrow += yrow_step;
+                }
+            } else if (sep) {
                 float h[4][2][4];
                 auto hrow = [&](float (&dst)[2][4], int r) {
                     float v[5][4];
@@ -358,14 +429,32 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
         const int tiles_x = (OW + FT_OW - 1) / FT_OW, tiles_y = (OH + FT_OH - 1) / FT_OH;
         const int64_t total = (int64_t)tiles_x * tiles_y * N;
         NBE_REQUIRE(total <= INT32_MAX, "fir_act_nhwc: too many tiles");
-        const size_t smem = 128 + 2 * ((FT_TILE_BYTES + 127) & ~127) + (3 * 128 + 16 + FT_OH * FT_OW) * sizeof(float) + 64;
+        const size_t smem = 128 + 2 * ((FT_TILE_BYTES + 127) & ~127) + (2 * FT_OH * FT_OW + 3 * 128 + 16) * sizeof(float) + 64;
         static std::once_flag once;
         static cudaError_t err = cudaSuccess;
-        std::call_once(once, [] { err = cudaFuncSetAttribute(fir_act_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); });
+        std::call_once(once, [] {
+            err = cudaFuncSetAttribute(fir_act_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+            if (err == cudaSuccess) err = cudaFuncSetAttribute(fir_act_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        });
         if (err != cudaSuccess) return fail(NBE_ECUDA, "fir_act_nhwc: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+        // noise [N or 1][OH][OW] fp32 as a 3-D tensor map (8 x 16 boxes), when TMA can describe it
+        static const bool noise_by_threads = getenv("NBE_FIR_NOISE_THREADS") != nullptr;     // A/B switch
+        int noise_mode = noise ? 0 : 2;
+        CUtensorMap tn = tm;
+        if (noise && !noise_by_threads && ((uintptr_t)noise & 15) == 0 && OW % 4 == 0 &&
+            (noise_sn == 0 || (noise_sn % 4 == 0 && noise_sn >= (int64_t)OH * OW))) {
+            cuuint64_t ndims[3] = {(cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)(noise_sn ? N : 1)};
+            cuuint64_t nstr[2] = {(cuuint64_t)OW * 4, (cuuint64_t)(noise_sn ? noise_sn : (int64_t)OH * OW) * 4};
+            cuuint32_t nbox[3] = {FT_OW, FT_OH, 1};
+            st = make_tmap(&tn, noise, 3, ndims, nstr, nbox, "FIR noise", 1, /*swizzle=*/0, /*f32=*/1);
+            if (st) return st;
+            noise_mode = 1;
+        }
         int grid = kNumSMs * 2;
         if (total < grid) grid = (int)total;
-        fir_act_tiled_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(tm, p, tiles_x, tiles_y, (int)total);
+        static const bool scalar_fp32 = getenv("NBE_FIR_SCALAR") != nullptr;      // A/B switch: the unpacked FP32 arithmetic
+        if (scalar_fp32) fir_act_tiled_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tn, p, tiles_x, tiles_y, (int)total, noise_mode);
+        else fir_act_tiled_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tn, p, tiles_x, tiles_y, (int)total, noise_mode);
         return launched("fir_act_tiled_kernel");
     }
     p.row_groups = (OH + FIR_RPT - 1) / FIR_RPT;

@@ -85,7 +85,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box, const char* what, int spatial_stride = 1, int swizzle128 = 1);
+              const cuuint32_t* box, const char* what, int spatial_stride = 1, int swizzle128 = 1, int f32 = 0);
 
 
 // ---- lean single-warp MMA issue ----------------------------------------------------------------------------

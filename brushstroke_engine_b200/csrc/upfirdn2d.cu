@@ -85,6 +85,21 @@ __device__ __forceinline__ void store_row(T* dst, const float (&acc)[VPT], int n
     }
 }
 
+// raw register image of one element (for the AND-mask fix-ups) and its exact conversion to float
+template <class T> struct Raw;
+template <> struct Raw<float> {
+    static __device__ __forceinline__ uint32_t ld(const float* p) { return __float_as_uint(*p); }
+    static __device__ __forceinline__ float to_float(uint32_t r) { return __uint_as_float(r); }
+};
+template <> struct Raw<__nv_bfloat16> {
+    static __device__ __forceinline__ uint32_t ld(const __nv_bfloat16* p) { return *reinterpret_cast<const unsigned short*>(p); }
+    static __device__ __forceinline__ float to_float(uint32_t r) { return __uint_as_float(r << 16); }
+};
+template <> struct Raw<__half> {
+    static __device__ __forceinline__ uint32_t ld(const __half* p) { return *reinterpret_cast<const unsigned short*>(p); }
+    static __device__ __forceinline__ float to_float(uint32_t r) { return __half2float(__ushort_as_half((unsigned short)r)); }
+};
+
 struct StagedGeom {
     int cg;             // column groups per row  = ceil(OW / VPT)
     int rg;             // row groups per CTA-plane = ceil(rows_per_cta / RPT)
@@ -92,6 +107,7 @@ struct StagedGeom {
     int strip;          // output rows per CTA when ppc == 1
     int strips;         // strips per plane
     int smem_bytes;
+    int packed;         // up = 1, windows hang at most 3 elements over a row end, OW % VPT == 0: FFMA2 path with mask fix-ups
 };
 
 template <int VPT, int WIN, int PI>
@@ -219,7 +235,62 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
                 for (int j = 0; j < WIN; ++j) dst[j] = 0.f;
             }
         };
-        if (sep) {
+        if (sep && g.packed) {
+            // column pairs (k, k+1) share one FFMA2 / FMUL2: half the FP32-pipe instructions of the scalar path below, same
+            // operation order per output (bit-identical results)
+            constexpr int VP = VPT / 2;
+            const float2 fx2[4] = {{fx[0], fx[0]}, {fx[1], fx[1]}, {fx[2], fx[2]}, {fx[3], fx[3]}};
+            const float2 fy2[4] = {{fy[0], fy[0]}, {fy[1], fy[1]}, {fy[2], fy[2]}, {fy[3], fy[3]}};
+            // edge fix-up (host guarantees g.packed only when every window hangs at most 3 elements over a row end and
+            // OW % VPT == 0): only the first / last 3 window slots can lie outside the row, at compile-time slots, so they are
+            // cleared with six row-invariant AND masks on the raw bits -- no compares inside the row loop
+            uint32_t mk[6] = {jl > 0 ? 0u : ~0u, jl > 1 ? 0u : ~0u, jl > 2 ? 0u : ~0u,
+                              jh <= WIN - 3 ? 0u : ~0u, jh <= WIN - 2 ? 0u : ~0u, jh <= WIN - 1 ? 0u : ~0u};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) asm volatile("" : "+r"(mk[i]));         // keep them as values (not re-derived predicates)
+            const bool edge = jl > 0 || jh < WIN;
+            float2 h2[4][VP];
+            auto hrow2 = [&](float2 (&dst)[VP], int iy) {
+                if (iy < r_lo || iy >= r_hi) {                                  // a zero row (padding above / below the image)
+#pragma unroll
+                    for (int m = 0; m < VP; ++m) dst[m] = make_float2(0.f, 0.f);
+                    return;
+                }
+                const T* rp = sp + (long long)iy * W + ix0;
+                uint32_t raw[WIN];
+#pragma unroll
+                for (int j = 0; j < WIN; ++j) raw[j] = Raw<T>::ld(rp + j);
+                if (edge) {
+                    raw[0] &= mk[0]; raw[1] &= mk[1]; raw[2] &= mk[2];
+                    raw[WIN - 3] &= mk[3]; raw[WIN - 2] &= mk[4]; raw[WIN - 1] &= mk[5];
+                }
+                float in[WIN];
+#pragma unroll
+                for (int j = 0; j < WIN; ++j) in[j] = Raw<T>::to_float(raw[j]);
+#pragma unroll
+                for (int m = 0; m < VP; ++m) {
+                    const float2 e0 = make_float2(in[2 * m], in[2 * m + 1]), o0 = make_float2(in[2 * m + 1], in[2 * m + 2]);
+                    const float2 e1 = make_float2(in[2 * m + 2], in[2 * m + 3]), o1 = make_float2(in[2 * m + 3], in[2 * m + 4]);
+                    dst[m] = fma2(fx2[3], o1, fma2(fx2[2], e1, fma2(fx2[1], o0, mul2(fx2[0], e0))));
+                }
+            };
+            hrow2(h2[0], iy0); hrow2(h2[1], iy0 + 1); hrow2(h2[2], iy0 + 2);
+            T* yrow = yp + (long long)ry0 * p.OW + ox0;
+#pragma unroll
+            for (int r = 0; r < ST_RPT; ++r) {
+                if (ry0 + r >= row_end) break;
+                hrow2(h2[(r + 3) & 3], iy0 + r + 3);
+                float acc[VPT];
+#pragma unroll
+                for (int m = 0; m < VP; ++m) {
+                    const float2 a2 = fma2(fy2[3], h2[(r + 3) & 3][m], fma2(fy2[2], h2[(r + 2) & 3][m],
+                                      fma2(fy2[1], h2[(r + 1) & 3][m], mul2(fy2[0], h2[r & 3][m]))));
+                    acc[2 * m] = a2.x; acc[2 * m + 1] = a2.y;
+                }
+                store_row<T, VPT>(yrow, acc, n_valid);
+                yrow += p.OW;
+            }
+        } else if (sep) {
             float h[4][VPT];                                                // horizontally filtered input rows (sliding window)
             auto hrow = [&](float (&dst)[VPT], int iy) {
                 float in[WIN];
@@ -346,7 +417,10 @@ static int run_typed(const UpfirdnParams& p, bool tiled_ok, cudaStream_t s) {
     int vpt = VecOut<T>::VPT;
     if (sizeof(T) == 4 && p.upx == 1) vpt = 4;
     if (sizeof(T) == 4 && vpt_env) vpt = atoi(vpt_env) == 4 ? 4 : 8;
+    static const bool scalar_fp32 = getenv("NBE_UPF_SCALAR") != nullptr;          // A/B switch: the unpacked arithmetic / generic fix-ups
     if (tiled_ok && staged_geometry<T>(p, g, vpt)) {
+        const int padx1 = p.OW - p.W - p.padx0 + 3;                               // up = 1: OW = W + padx0 + padx1 - 3
+        g.packed = !scalar_fp32 && p.upx == 1 && p.padx0 <= 3 && padx1 <= 3 && p.OW % vpt == 0;
         const int n_planes = p.N * p.C;
         const int64_t blocks = g.ppc > 1 ? (n_planes + g.ppc - 1) / g.ppc : (int64_t)n_planes * g.strips;
         if (blocks <= INT32_MAX) {

@@ -94,6 +94,38 @@ def test_upfirdn2d_generator_and_upsample_shapes(dtype, tol, H):
     assert md(y, O.upfirdn2d(x.float(), f4, up=2, padding=[3, 2, 3, 2], gain=4.0)) < tol * 4
 
 
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 3e-6), (torch.float16, 2e-3), (torch.bfloat16, 2e-2)])
+def test_upfirdn2d_packed_path_padding_sweep(dtype, tol):
+    """The FFMA2 path of the staged kernel (up = 1, output width a multiple of 8, paddings <= 3 incl. crops): every
+    combination of left / right padding, heights that are not a multiple of the 8-row groups, several planes per CTA
+    (small planes) and one strip per CTA (large planes), against the oracle."""
+    from brushstroke_engine_b200 import upfirdn2d as U
+    f4 = O.setup_filter([1, 3, 3, 1])
+    gen = torch.Generator().manual_seed(17)
+    n = 0
+    for OW in (8, 16, 64, 256):
+        for px0 in (-2, 0, 1, 2, 3):
+            for px1 in (-1, 0, 1, 3):
+                W = OW + 3 - px0 - px1
+                if W < 4:
+                    continue
+                H = {8: 5, 16: 19, 64: 33, 256: 70}[OW]
+                py0, py1 = (px1 % 3), (px0 % 4)
+                x = (torch.randn(3 if OW < 256 else 1, 4 if OW < 256 else 2, H, W, generator=gen) * 3).to(dtype)
+                y = U.upfirdn2d(x.to(DEV), f4.to(DEV), padding=[px0, px1, py0, py1], gain=4)
+                ref = O.upfirdn2d(x.float(), f4, padding=[px0, px1, py0, py1], gain=4.0)
+                assert y.shape == ref.shape and y.shape[-1] == OW
+                assert md(y, ref) < tol * 12, (OW, px0, px1, H, W)
+                n += 1
+    assert n > 60
+    # a non-finite value only reaches the outputs whose 4x4 window contains it (zero padding is a select, not a multiply)
+    x = torch.randn(1, 1, 9, 9, generator=gen).to(dtype)
+    x[0, 0, 3, 8] = float('inf')
+    y = U.upfirdn2d(x.to(DEV), f4.to(DEV), padding=[1, 1, 1, 1], gain=4).float().cpu()
+    ref = O.upfirdn2d(x.float(), f4, padding=[1, 1, 1, 1], gain=4.0)
+    assert torch.equal(torch.isfinite(y), torch.isfinite(ref))
+
+
 def test_modconv_golden():
     from brushstroke_engine_b200.conv2d_resample import conv2d_resample
     from brushstroke_engine_b200.modconv import modulated_conv2d
