@@ -106,7 +106,8 @@ struct StagedGeom {
     int ppc;            // whole planes per CTA (>= 1); > 1 only when a plane fits one CTA
     int strip;          // output rows per CTA when ppc == 1
     int strips;         // strips per plane
-    int smem_bytes;
+    int smem_bytes;     // one input buffer: guard chunk + staged range + tail guard
+    int buf_bytes;      // smem_bytes rounded up to 128
     int packed;         // up = 1, windows hang at most 3 elements over a row end, OW % VPT == 0: FFMA2 path with mask fix-ups
 };
 
@@ -127,62 +128,78 @@ __device__ __forceinline__ void up2_row(float (&acc)[VPT], const float (&rowA)[W
 
 template <class T, int UP, int VPT>
 __global__ void __launch_bounds__(ST_THREADS)
-upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
-    extern __shared__ __align__(16) uint8_t st_smem[];
+upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items) {
+    // Persistent CTA, two input buffers: the contiguous input range of the NEXT work item is in flight (one 1-D bulk copy,
+    // cp.async.bulk -> mbarrier) while the current one is filtered, so no thread ever waits on a global load of its own.
+    extern __shared__ __align__(128) uint8_t st_smem[];                 // [2][g.buf_bytes] input buffers, then 2 mbarriers
     __shared__ float s_f[16];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(st_smem + 2 * (size_t)g.buf_bytes);
     const T* xbase = (const T*)p.x;
-    // ---- which planes / rows does this CTA own
-    int plane0, oy0, rows;
-    if (g.ppc > 1) { plane0 = blockIdx.x * g.ppc; oy0 = 0; rows = p.OH; }
-    else { plane0 = blockIdx.x / g.strips; oy0 = (blockIdx.x % g.strips) * g.strip; rows = min(g.strip, p.OH - oy0); }
-    const int planes = min(g.ppc, n_planes - plane0);
-    // ---- input rows needed (per plane): UP=1: [oy0 - pad, oy0 - pad + rows + 3) ; UP=2: [(oy0 - pad) >> 1, ((oy0 + rows + 2 - pad) >> 1) + 1)
-    int r_lo, r_hi;
-    if (UP == 1) { r_lo = oy0 - p.pady0; r_hi = r_lo + rows + 3; }
-    else { r_lo = (oy0 - p.pady0) >> 1; r_hi = ((oy0 + rows + 2 - p.pady0) >> 1) + 1; }
-    r_lo = max(r_lo, 0); r_hi = min(r_hi, p.H);
-    if (g.ppc > 1) { r_lo = 0; r_hi = p.H; }
     const long long plane_elems = (long long)p.H * p.W;
-    const long long e_lo = (long long)plane0 * plane_elems + (long long)r_lo * p.W;                    // first element needed
-    const long long e_hi = (g.ppc > 1) ? (long long)(plane0 + planes) * plane_elems
-                                       : (long long)plane0 * plane_elems + (long long)max(r_hi, r_lo) * p.W;
-    // ---- stage [e_lo, e_hi) with aligned 16-byte chunks; smem byte 0 <-> global byte a_lo
-    const uintptr_t gb_lo = reinterpret_cast<uintptr_t>(xbase + e_lo), gb_hi = reinterpret_cast<uintptr_t>(xbase + e_hi);
-    const uintptr_t a_lo = gb_lo & ~uintptr_t(15);
     const uintptr_t t_lo = reinterpret_cast<uintptr_t>(xbase), t_hi = reinterpret_cast<uintptr_t>(xbase + (long long)n_planes * plane_elems);
-    const int n_chunks = (int)((gb_hi - a_lo + 15) >> 4);
-    // interior chunks: 4 independent 16-byte loads in flight per thread before the first shared-memory store
-    const bool all_inside = a_lo >= t_lo && a_lo + ((uintptr_t)n_chunks << 4) <= t_hi;
-    int i0 = threadIdx.x;
-    if (all_inside) {
-        for (; i0 + 3 * ST_THREADS < n_chunks; i0 += 4 * ST_THREADS) {
-            int4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ld_stream16(reinterpret_cast<const void*>(a_lo + ((uintptr_t)(i0 + u * ST_THREADS) << 4)));
-#pragma unroll
-            for (int u = 0; u < 4; ++u) reinterpret_cast<int4*>(st_smem)[1 + i0 + u * ST_THREADS] = v[u];
+
+    struct Item { int plane0, oy0, rows, planes, r_lo, r_hi; uintptr_t gb_lo, a_lo; int n_chunks; };
+    auto item_geom = [&](int item, Item& I) {
+        // ---- which planes / rows does this item cover
+        if (g.ppc > 1) { I.plane0 = item * g.ppc; I.oy0 = 0; I.rows = p.OH; }
+        else { I.plane0 = item / g.strips; I.oy0 = (item % g.strips) * g.strip; I.rows = min(g.strip, p.OH - I.oy0); }
+        I.planes = min(g.ppc, n_planes - I.plane0);
+        // ---- input rows needed (per plane): UP=1: [oy0 - pad, oy0 - pad + rows + 3) ; UP=2: [(oy0 - pad) >> 1, ((oy0 + rows + 2 - pad) >> 1) + 1)
+        int r_lo, r_hi;
+        if (UP == 1) { r_lo = I.oy0 - p.pady0; r_hi = r_lo + I.rows + 3; }
+        else { r_lo = (I.oy0 - p.pady0) >> 1; r_hi = ((I.oy0 + I.rows + 2 - p.pady0) >> 1) + 1; }
+        r_lo = max(r_lo, 0); r_hi = min(r_hi, p.H);
+        if (g.ppc > 1) { r_lo = 0; r_hi = p.H; }
+        I.r_lo = r_lo; I.r_hi = r_hi;
+        const long long e_lo = (long long)I.plane0 * plane_elems + (long long)r_lo * p.W;             // first element needed
+        const long long e_hi = (g.ppc > 1) ? (long long)(I.plane0 + I.planes) * plane_elems
+                                           : (long long)I.plane0 * plane_elems + (long long)max(r_hi, r_lo) * p.W;
+        // ---- the range [e_lo, e_hi) in aligned 16-byte chunks; buffer byte 16 <-> global byte a_lo (chunk 0 is a guard)
+        I.gb_lo = reinterpret_cast<uintptr_t>(xbase + e_lo);
+        const uintptr_t gb_hi = reinterpret_cast<uintptr_t>(xbase + e_hi);
+        I.a_lo = I.gb_lo & ~uintptr_t(15);
+        I.n_chunks = (int)((gb_hi - I.a_lo + 15) >> 4);
+    };
+    // all threads call this: thread 0 issues the bulk copy of the chunks that lie completely inside the tensor, the (at most
+    // two) chunks straddling its first / last bytes are assembled element by element with zeros outside
+    auto stage = [&](int item, int b) {
+        Item I;
+        item_geom(item, I);
+        uint8_t* buf = st_smem + (size_t)b * g.buf_bytes;
+        int c0 = 0, c1 = I.n_chunks;
+        if (I.a_lo < t_lo) c0 = min(c1, 1);                              // a_lo > t_lo - 16
+        if (c1 > c0 && I.a_lo + ((uintptr_t)c1 << 4) > t_hi) --c1;       // the last chunk reaches past the tensor
+        if (threadIdx.x == 0) {
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[b]);
+            const uint32_t bytes = (uint32_t)(c1 - c0) << 4;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            if (bytes)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"((uint32_t)__cvta_generic_to_shared(buf + 16 + ((size_t)c0 << 4))), "l"(I.a_lo + ((uintptr_t)c0 << 4)), "r"(bytes), "r"(bar)
+                             : "memory");
         }
-    }
-    for (int i = i0; i < n_chunks; i += ST_THREADS) {
-        const uintptr_t ga = a_lo + ((uintptr_t)i << 4);
-        if (ga >= t_lo && ga + 16 <= t_hi) {
-            reinterpret_cast<int4*>(st_smem)[1 + i] = ld_stream16(reinterpret_cast<const void*>(ga));
-        } else {                                                      // chunk straddles the tensor's first / last bytes
+        const int n_edge = c0 + (I.n_chunks - c1);                       // 0, 1 or 2
+        if ((int)threadIdx.x < n_edge) {
+            const int i = ((int)threadIdx.x == 0 && c0 == 1) ? 0 : c1;
+            const uintptr_t ga = I.a_lo + ((uintptr_t)i << 4);
             for (int k = 0; k < 16 / (int)sizeof(T); ++k) {
                 const uintptr_t ea = ga + k * sizeof(T);
-                reinterpret_cast<T*>(st_smem)[(1 + i) * (16 / (int)sizeof(T)) + k] =
+                reinterpret_cast<T*>(buf)[(1 + i) * (16 / (int)sizeof(T)) + k] =
                     (ea >= t_lo && ea + sizeof(T) <= t_hi) ? *reinterpret_cast<const T*>(ea) : Cvt<T>::st(0.f);
             }
         }
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&bars[i])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 16) {
         int a = threadIdx.x >> 2, b = threadIdx.x & 3;
         s_f[threadIdx.x] = (p.flip ? p.f[a * 4 + b] : p.f[(3 - a) * 4 + (3 - b)]) * p.gain;
     }
     __syncthreads();
-    // chunk 0 of the buffer is a guard: edge threads over-read up to 3 elements to the left of the staged range (and to
-    // the right, into the tail guard) and then zero what lies outside the row -- no per-element predicate on the loads
-    const T* sx = reinterpret_cast<const T*>(st_smem + 16 + (gb_lo - a_lo));                                // smem view of element e_lo
+    if ((int)blockIdx.x < n_items) stage(blockIdx.x, 0);
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = s_f[i];
@@ -195,6 +212,12 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
     float fx[4], fy[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { fx[i] = f[i]; fy[i] = sep ? f[i * 4] / f[0] : 0.f; }
+
+    // chunk 0 of a buffer is a guard: edge threads over-read up to 3 elements to the left of the staged range (and to the
+    // right, into the tail guard) and then clear what lies outside the row -- no per-element predicate on the loads
+    auto compute = [&](const Item& I, const uint8_t* buf) {
+    const int plane0 = I.plane0, oy0 = I.oy0, rows = I.rows, planes = I.planes, r_lo = I.r_lo, r_hi = I.r_hi;
+    const T* sx = reinterpret_cast<const T*>(buf + 16 + (I.gb_lo - I.a_lo));                             // smem view of element e_lo
 
     // ---- thread -> (plane_local, row group, column group)
     int t = threadIdx.x;
@@ -383,6 +406,28 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes) {
             yrow += p.OW;
         }
     }
+    };   // compute
+
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int b = it & 1;
+        if (item + (int)gridDim.x < n_items) stage(item + gridDim.x, b ^ 1);   // buffer b^1 was released by the barrier that ended the previous iteration
+        Item I;
+        item_geom(item, I);
+        {   // bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[b]), parity = (uint32_t)((it >> 1) & 1);
+            uint32_t done = 0;
+            const long long t0 = clock64();
+            while (true) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                if (done) break;
+                if (clock64() - t0 > 4000000000LL) { printf("nbe upfirdn2d: mbarrier wait timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+            }
+        }
+        compute(I, st_smem + (size_t)b * g.buf_bytes);
+        __syncthreads();                                               // everyone is done with buffer b before it is refilled
+    }
 }
 
 template <class T>
@@ -394,7 +439,7 @@ static bool staged_geometry(const UpfirdnParams& p, StagedGeom& g, int VPT) {
     if (g.cg * rg_plane * 2 <= ST_THREADS) {                          // several whole planes per CTA
         g.ppc = ST_THREADS / (g.cg * rg_plane);
         g.rg = rg_plane; g.strip = p.OH; g.strips = 1;
-        while (g.ppc > 1 && (long long)g.ppc * p.H * p.W * es + 80 > 96 * 1024) --g.ppc;
+        while (g.ppc > 1 && (long long)g.ppc * p.H * p.W * es + 80 > 48 * 1024) --g.ppc;
         g.smem_bytes = (int)((long long)g.ppc * p.H * p.W * es + 80);
     } else {
         g.ppc = 1;
@@ -405,7 +450,8 @@ static bool staged_geometry(const UpfirdnParams& p, StagedGeom& g, int VPT) {
         const int in_rows = (p.upy == 1) ? g.strip + 3 : g.strip / 2 + 3;
         g.smem_bytes = (int)((long long)in_rows * p.W * es + 80);
     }
-    return g.smem_bytes <= 96 * 1024;
+    g.buf_bytes = (g.smem_bytes + 127) & ~127;
+    return g.smem_bytes <= 48 * 1024;                                  // two buffers per CTA
 }
 
 template <class T>
@@ -424,14 +470,19 @@ static int run_typed(const UpfirdnParams& p, bool tiled_ok, cudaStream_t s) {
         const int n_planes = p.N * p.C;
         const int64_t blocks = g.ppc > 1 ? (n_planes + g.ppc - 1) / g.ppc : (int64_t)n_planes * g.strips;
         if (blocks <= INT32_MAX) {
-            void (*kern)(UpfirdnParams, StagedGeom, int);
+            void (*kern)(UpfirdnParams, StagedGeom, int, int);
             if (sizeof(T) == 4 && vpt == 4) kern = (p.upx == 1) ? upfirdn2d_staged_kernel<T, 1, (sizeof(T) == 4 ? 4 : 8)> : upfirdn2d_staged_kernel<T, 2, (sizeof(T) == 4 ? 4 : 8)>;
             else kern = (p.upx == 1) ? upfirdn2d_staged_kernel<T, 1, 8> : upfirdn2d_staged_kernel<T, 2, 8>;
-            if (g.smem_bytes > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            const int dyn = 2 * g.buf_bytes + 64;                          // two input buffers + mbarriers
+            if (dyn > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
                 if (e != cudaSuccess) return fail(NBE_ECUDA, "upfirdn2d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             }
-            kern<<<(int)blocks, ST_THREADS, g.smem_bytes, s>>>(p, g, n_planes);
+            // persistent grid: as many CTAs as fit an SM (shared memory; at most 6), each keeps its next item in flight
+            int per_sm = (227 * 1024) / (dyn + 1024);
+            per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+            const int grid = (int)(blocks < (int64_t)kNumSMs * per_sm ? blocks : (int64_t)kNumSMs * per_sm);
+            kern<<<grid, ST_THREADS, dyn, s>>>(p, g, n_planes, (int)blocks);
             return launched("upfirdn2d_staged_kernel");
         }
     }
