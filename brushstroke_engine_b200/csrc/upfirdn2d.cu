@@ -90,14 +90,20 @@ template <class T> struct Raw;
 template <> struct Raw<float> {
     static __device__ __forceinline__ uint32_t ld(const float* p) { return __float_as_uint(*p); }
     static __device__ __forceinline__ float to_float(uint32_t r) { return __uint_as_float(r); }
+    static __device__ __forceinline__ void unpack2(uint32_t, float& lo, float& hi) { lo = hi = 0.f; }   // (16-bit types only)
 };
 template <> struct Raw<__nv_bfloat16> {
     static __device__ __forceinline__ uint32_t ld(const __nv_bfloat16* p) { return *reinterpret_cast<const unsigned short*>(p); }
     static __device__ __forceinline__ float to_float(uint32_t r) { return __uint_as_float(r << 16); }
+    static __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) { lo = __uint_as_float(v << 16); hi = __uint_as_float(v & 0xffff0000u); }
 };
 template <> struct Raw<__half> {
     static __device__ __forceinline__ uint32_t ld(const __half* p) { return *reinterpret_cast<const unsigned short*>(p); }
     static __device__ __forceinline__ float to_float(uint32_t r) { return __half2float(__ushort_as_half((unsigned short)r)); }
+    static __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v));
+        lo = f2.x; hi = f2.y;
+    }
 };
 
 struct StagedGeom {
@@ -108,6 +114,7 @@ struct StagedGeom {
     int strips;         // strips per plane
     int smem_bytes;     // one input buffer: guard chunk + staged range + tail guard
     int buf_bytes;      // smem_bytes rounded up to 128
+    int lds32;          // 16-bit types on the packed path: aligned 32-bit shared-memory loads + funnel shift
     int packed;         // up = 1, windows hang at most 3 elements over a row end, OW % VPT == 0: FFMA2 path with mask fix-ups
 };
 
@@ -280,16 +287,37 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
                     return;
                 }
                 const T* rp = sp + (long long)iy * W + ix0;
-                uint32_t raw[WIN];
+                uint32_t raw[WIN];                                              // float bits (or raw 16-bit values) of the window
+                if (sizeof(T) == 2 && g.lds32) {
+                    // 16-bit types: the lanes of a warp sit 16 bytes apart, so every shared-memory load of a warp costs 4
+                    // wavefronts whatever its width -- read the window as 6 aligned 32-bit words instead of 11 halfwords and
+                    // realign with a funnel shift (rows of odd pitch start on either halfword of a word)
+                    constexpr int NW = (WIN + 1) / 2;
+                    const uint32_t a = (uint32_t)__cvta_generic_to_shared(rp);    // 32-bit shared address: immediate offsets
+                    const uint32_t sh = (a & 2u) ? 16u : 0u;
+                    const uint32_t wa = a & ~3u;
+                    uint32_t w[NW];
 #pragma unroll
-                for (int j = 0; j < WIN; ++j) raw[j] = Raw<T>::ld(rp + j);
-                if (edge) {
+                    for (int k = 0; k < NW; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[k]) : "r"(wa + 4u * k));
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) {
+                        const uint32_t v = __funnelshift_r(w[k], w[k + 1 < NW ? k + 1 : k], sh);   // elements 2k (low half), 2k+1 (high half)
+                        float lo, hi;
+                        Raw<T>::unpack2(v, lo, hi);
+                        raw[2 * k] = __float_as_uint(lo);
+                        if (2 * k + 1 < WIN) raw[2 * k + 1] = __float_as_uint(hi);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < WIN; ++j) raw[j] = __float_as_uint(Raw<T>::to_float(Raw<T>::ld(rp + j)));
+                }
+                if (edge) {                                                     // +0.0f is all-zero bits: masks work on float bits
                     raw[0] &= mk[0]; raw[1] &= mk[1]; raw[2] &= mk[2];
                     raw[WIN - 3] &= mk[3]; raw[WIN - 2] &= mk[4]; raw[WIN - 1] &= mk[5];
                 }
                 float in[WIN];
 #pragma unroll
-                for (int j = 0; j < WIN; ++j) in[j] = Raw<T>::to_float(raw[j]);
+                for (int j = 0; j < WIN; ++j) in[j] = __uint_as_float(raw[j]);
 #pragma unroll
                 for (int m = 0; m < VP; ++m) {
                     const float2 e0 = make_float2(in[2 * m], in[2 * m + 1]), o0 = make_float2(in[2 * m + 1], in[2 * m + 2]);
@@ -467,6 +495,8 @@ static int run_typed(const UpfirdnParams& p, bool tiled_ok, cudaStream_t s) {
     if (tiled_ok && staged_geometry<T>(p, g, vpt)) {
         const int padx1 = p.OW - p.W - p.padx0 + 3;                               // up = 1: OW = W + padx0 + padx1 - 3
         g.packed = !scalar_fp32 && p.upx == 1 && p.padx0 <= 3 && padx1 <= 3 && p.OW % vpt == 0;
+        static const bool lds16 = getenv("NBE_UPF_LDS16") != nullptr;            // A/B switch: halfword shared-memory loads
+        g.lds32 = !lds16;
         const int n_planes = p.N * p.C;
         const int64_t blocks = g.ppc > 1 ? (n_planes + g.ppc - 1) / g.ppc : (int64_t)n_planes * g.strips;
         if (blocks <= INT32_MAX) {

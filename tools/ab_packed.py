@@ -1,5 +1,5 @@
 """A/B of the packed-FP32 (FFMA2) arithmetic against the scalar code it replaces: same inputs through both builds of the
-FIR pass (NBE_FIR_SCALAR) and of the staged upfirdn2d kernel (NBE_UPF_SCALAR) in two child processes (the switches are
+FIR pass (NBE_FIR_SCALAR) and of the staged upfirdn2d kernel (NBE_UPF_SCALAR; NBE_UPF_LDS16 = halfword shared-memory loads) in child processes (the switches are
 read once per process), outputs compared bit for bit, times side by side.
 
     python tools/ab_packed.py            # parent: runs both children, prints the comparison
@@ -84,23 +84,29 @@ def child(out_path):
 def main():
     if len(sys.argv) > 2 and sys.argv[1] == 'child':
         return child(sys.argv[2])
-    outs = []
-    for tag, env in (('packed', {}), ('scalar', {'NBE_FIR_SCALAR': '1', 'NBE_UPF_SCALAR': '1'})):
+    outs = {}
+    for tag, env in (('packed', {}), ('scalar', {'NBE_FIR_SCALAR': '1', 'NBE_UPF_SCALAR': '1'}), ('lds16', {'NBE_UPF_LDS16': '1'})):
         path = os.path.join(tempfile.gettempdir(), f'ab_{tag}.pt')
         e = dict(os.environ); e.update(env)
         subprocess.check_call([sys.executable, os.path.abspath(__file__), 'child', path], env=e)
-        outs.append(torch.load(path))
-    a, b = outs
-    bad = [k for k in a['res'] if not torch.equal(a['res'][k], b['res'][k])]
-    for k in bad:
-        d = (a['res'][k].double() - b['res'][k].double()).abs().max()
-        print(f'DIFF {k}: max abs {float(d):.3e}')
-    print(f"bit-identical outputs: {len(a['res']) - len(bad)} of {len(a['res'])}")
-    print('| case | packed ms | GB/s | scalar ms | GB/s | speed-up |')
-    print('|---|---:|---:|---:|---:|---:|')
+        outs[tag] = torch.load(path)
+    a = outs['packed']
+    bad = []
+    for tag in ('scalar', 'lds16'):
+        b = outs[tag]
+        for k in a['res']:
+            if not torch.equal(a['res'][k], b['res'][k]):
+                d = (a['res'][k].double() - b['res'][k].double()).abs().max()
+                rel = float(d) / max(1e-30, float(b['res'][k].double().abs().max()))
+                print(f'DIFF default vs {tag} {k}: max abs {float(d):.3e} (rel {rel:.1e})')
+                if rel > 1e-6:
+                    bad.append(k)
+    print(f"outputs compared: {len(a['res'])} x 2; beyond 1e-6 relative: {len(bad)}")
+    print('| case | default ms | GB/s | scalar FP32 ms | GB/s | halfword LDS ms | GB/s |')
+    print('|---|---:|---:|---:|---:|---:|---:|')
     for k in a['times']:
-        (m1, g1), (m0, g0) = a['times'][k], b['times'][k]
-        print(f'| {k} | {m1:.4f} | {g1:.0f} | {m0:.4f} | {g0:.0f} | {m0 / m1:.2f}x |')
+        (m1, g1), (m0, g0), (m2, g2) = a['times'][k], outs['scalar']['times'][k], outs['lds16']['times'][k]
+        print(f'| {k} | {m1:.4f} | {g1:.0f} | {m0:.4f} | {g0:.0f} | {m2:.4f} | {g2:.0f} |')
     return 1 if bad else 0
 
 
