@@ -510,8 +510,15 @@ static int run_typed(const UpfirdnParams& p, bool tiled_ok, cudaStream_t s) {
             }
             // persistent grid: as many CTAs as fit an SM (shared memory; at most 6), each keeps its next item in flight
             int per_sm = (227 * 1024) / (dyn + 1024);
-            per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
-            const int grid = (int)(blocks < (int64_t)kNumSMs * per_sm ? blocks : (int64_t)kNumSMs * per_sm);
+            const char* cap_env = getenv("NBE_UPF_PER_SM");                 // A/B: persistent CTAs per SM (default cap 6)
+            const int cap = cap_env ? atoi(cap_env) : 6;
+            per_sm = per_sm < 1 ? 1 : (per_sm > cap ? cap : per_sm);
+            // one item per CTA (the loop runs once; residency is then set by registers / shared memory only): up = 2 writes 4x what
+            // it reads, so it gains nothing from prefetching its small input and loses residency to the persistent grid
+            // (tools/ab_up2.py: fp32 0.63 -> 0.57 ms, bf16 0.41 -> 0.38 ms at 64^2 -> 128^2).  NBE_UPF_ONESHOT=0/1 overrides.
+            const char* one_env = getenv("NBE_UPF_ONESHOT");
+            const bool oneshot = one_env ? atoi(one_env) != 0 : (p.upx == 2);
+            const int grid = (int)(oneshot || blocks < (int64_t)kNumSMs * per_sm ? blocks : (int64_t)kNumSMs * per_sm);
             kern<<<grid, ST_THREADS, dyn, s>>>(p, g, n_planes, (int)blocks);
             return launched("upfirdn2d_staged_kernel");
         }
