@@ -53,12 +53,14 @@ upfirdn2d_generic_kernel(UpfirdnParams p) {
 }
 
 // ---- staged 4x4 kernels (dense NCHW, down = 1, up in {1, 2}) ---------------------------------------
-// A CTA owns either a strip of output rows of one (n,c) plane or a group of whole small planes.  Either way the input
-// it needs is ONE contiguous range of the flat tensor, so it is staged into shared memory with aligned 16-byte
-// streaming loads (no per-element index arithmetic, misaligned odd-length rows like 2R+1 do not matter).  Each thread
-// then produces VPT consecutive columns x RPT rows from a sliding register window; rank-1 filters (everything
-// setup_filter builds from a 1-D tap list) take the separable path (4 + 4 FMAs per output instead of 16).  Stores are
-// 16-byte streaming vectors.  HBM-bound: algorithmic bytes = (numel(x) + numel(y)) * sizeof(T).
+// A work item is either a strip of output rows of one (n,c) plane or a group of whole small planes.  Either way the
+// input it needs is ONE contiguous range of the flat tensor, so it reaches shared memory as one 1-D bulk copy of aligned
+// 16-byte chunks (no per-element index arithmetic, misaligned odd-length rows like 2R+1 do not matter).  up = 1: CTAs are
+// persistent and double-buffered (the next item's copy is in flight while the current one is filtered); up = 2: one item
+// per CTA.  Each thread produces VPT consecutive columns x RPT rows from a sliding register window; rank-1 filters
+// (everything setup_filter builds from a 1-D tap list) take the separable path (4 + 4 taps per output instead of 16; as
+// FFMA2 on column pairs for up = 1 with paddings <= 3).  Stores are 16-byte streaming vectors.
+// HBM-bound: algorithmic bytes = (numel(x) + numel(y)) * sizeof(T).
 constexpr int ST_THREADS = 128;
 constexpr int ST_RPT = 8;                                               // output rows per thread
 
