@@ -154,7 +154,9 @@ fir_act_nhwc_kernel(const FirParams p) {
 // The register-window kernel above is latency-bound (every thread waits on its own global loads).  Here a persistent CTA
 // streams (8+3) x (16+3) pixel x 128-channel tiles of T through a double-buffered shared-memory ring with 4-D TMA boxes
 // (out-of-range rows / columns are zero-filled by TMA = the FIR's padding), the next tile is in flight while the
-// current one is filtered, and every shared-memory read is a conflict-free 16-byte vector.
+// current one is filtered, and every shared-memory read is a conflict-free 8-byte vector (a warp reads the 256 contiguous
+// bytes of one pixel).  The tile's 8 x 16 noise values ride on the same mbarrier through a second (fp32) tensor map, and every
+// CTA walks one contiguous run of tiles so that the per-image epilogue vectors are reloaded once per image, not per tile.
 constexpr int FT_OW = 16, FT_OH = 8;
 constexpr int FT_IW = FT_OW + 3, FT_IH = FT_OH + 3;
 constexpr int FT_TILE_BYTES = FT_IH * FT_IW * 256;                  // 128 bf16 channels per pixel
