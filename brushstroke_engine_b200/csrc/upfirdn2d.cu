@@ -269,7 +269,7 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
         };
         if (sep && g.packed) {
             // column pairs (k, k+1) share one FFMA2 / FMUL2: half the FP32-pipe instructions of the scalar path below, same
-            // operation order per output (bit-identical results)
+            // operation order per output (16-bit outputs bit-identical; fp32 within 1 ulp of the scalar build, whose contraction is the compiler's)
             constexpr int VP = VPT / 2;
             const float2 fx2[4] = {{fx[0], fx[0]}, {fx[1], fx[1]}, {fx[2], fx[2]}, {fx[3], fx[3]}};
             const float2 fy2[4] = {{fy[0], fy[0]}, {fy[1], fy[1]}, {fy[2], fy[2]}, {fy[3], fy[3]}};
