@@ -258,7 +258,7 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
                 for (int j = 0; j < WIN; ++j) dst[j] = Cvt<T>::ld(rp[j]);
                 if (jl > 0 || jh < WIN) {
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) if (j < jl) dst[j] = 0.f;
+                    for (int j = 0; j < WIN; ++j) if (j < jl) dst[j] = 0.f;
 #pragma unroll
                     for (int j = 0; j < WIN; ++j) if (j >= jh) dst[j] = 0.f;
                 }
@@ -559,8 +559,12 @@ extern "C" int nbe_upfirdn2d(const void* x, const float* f, void* y,
     p.gain = gain;
     const bool dense_x = xs_w == 1 && xs_h == W && xs_c == (int64_t)H * W && xs_n == (int64_t)C * H * W;
     const bool dense_y = ys_w == 1 && ys_h == OW && ys_c == (int64_t)OH * OW && ys_n == (int64_t)C * OH * OW;
+    // the staged kernels size their shared-memory guards (and their edge fix-ups) for small paddings -- the generator's
+    // (1,1,1,1), filter2d's / upsample2d's (2,1,2,1), and the swept range of tests/test_ops_gpu.py; larger paddings
+    // (a window that starts >= 4 columns left of the row) and vertical crops take the generic kernel
+    const bool pads_ok = padx0 >= -2 && padx0 <= 3 && padx1 >= -1 && padx1 <= 3 && pady0 >= 0 && pady0 <= 3 && pady1 >= 0 && pady1 <= 3;
     const bool tiled_ok = dense_x && dense_y && fh == 4 && fw == 4 && downx == 1 && downy == 1 && upx == upy &&
-                          (upx == 1 || upx == 2);
+                          (upx == 1 || upx == 2) && pads_ok;
     cudaStream_t s = (cudaStream_t)stream;
     switch (dtype) {
         case NBE_F32:  return run_typed<float>(p, tiled_ok, s);

@@ -49,7 +49,7 @@ class GanBrushOptions:
             self.style_z = self.style_z.to(device)
         if self.style_ws is not None:
             self.style_ws = self.style_ws.to(device)
-        if 'noise_buffers' in self.custom_args:
+        if self.custom_args.get('noise_buffers') is not None:      # WBrushLibrary sets None for plain-tensor styles
             for k, v in self.custom_args['noise_buffers'].items():
                 if not torch.is_tensor(v):
                     v = torch.from_numpy(v)
@@ -268,9 +268,9 @@ class TriadPaintEngine:
                     side.wait_stream(main)
                     with torch.cuda.stream(side):
                         ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
-                        ws = ws.to(self.device, torch.float32).contiguous()
+                        ws = G.expand_ws(ws).to(self.device, torch.float32).contiguous()
                         inj, dests, scales = G.alloc_injection(ws)
-                        if 'noise_buffers' not in extra:
+                        if extra.get('noise_buffers') is None:
                             G.prefetch_noise(B, positions)
                         ready = torch.cuda.Event()
                         ready.record(side)
@@ -278,14 +278,14 @@ class TriadPaintEngine:
                     main.wait_event(ready)
             else:
                 ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
-                ws = ws.to(self.device, torch.float32).contiguous()
+                ws = G.expand_ws(ws).to(self.device, torch.float32).contiguous()
                 inj, dests, scales = G.alloc_injection(ws)
                 self.encoder.encode_into(geom, dests, scales)
             return G.forward_pre_mapped(ws=ws, positions=positions, geom_feature=inj,
                                         return_debug_data=True, noise_mode='const', **extra, **generator_kwargs)
         geom_feature = self.encoder.encode(geom)
         if opts.style_ws is not None:
-            return G.forward_pre_mapped(ws=opts.style_ws, positions=opts.get_position(self.device),
+            return G.forward_pre_mapped(ws=G.expand_ws(opts.style_ws), positions=opts.get_position(self.device),
                                         geom_feature=geom_feature, return_debug_data=True, noise_mode='const',
                                         **opts.custom_args, **generator_kwargs)
         return G(z=opts.style_z, c=self.style_c, positions=opts.get_position(self.device),
@@ -473,6 +473,10 @@ class InteractiveSession:
                 self._d_out = self._forward()
             eng.G._noise_cache = None
             self._graph = g
+            # the captured kernels hold raw pointers into the batch-1 workspaces of the generator and the encoder: keep them
+            # alive (and out of reach of a re-allocation) for as long as the graph exists, whatever other batch sizes the
+            # engine serves in between
+            self._workspaces = (eng.G._flat_ws.get(1), eng.encoder._ws.get((1, eng.patch_width)))
 
     def render_stroke(self, stroke_patch: np.ndarray, position_yx=None) -> np.ndarray:
         """[W,W,C] uint8 stroke patch (last channel: 255 = stroke), optional canvas position (y, x) -> [T,T,4] uint8 RGBA."""

@@ -137,7 +137,8 @@ class Generator:
         self._build(params)
         self.mapping = MappingNetwork(self)
         self.synthesis = SynthesisNetwork(self)
-        self._flat_ws = {}
+        self._flat_ws = {}                 # batch size -> workspace, least recently used first
+        self.max_cached_batch_sizes = 4
         self._noise_cache = None
         self._noise_prefetched = None      # one-shot (positions, maps) computed ahead of _synthesis by prefetch_noise
         self.last_up_fir_first = os.environ.get('NBE_LAST_UP_FIR_FIRST') is not None   # A/B switch: 4x-FLOP FIR-first path at 128^2
@@ -225,8 +226,22 @@ class Generator:
                     pitch = res if res == cfg.img_resolution else res + 1
                     ws[f'x{res}'] = torch.zeros((B, res, pitch, cfg.channels(res)), dtype=bf, device=dev)        # conv0 output = conv1 input
             ws['in4'] = torch.zeros((B, 4, 5, cfg.channels(4)), dtype=bf, device=dev)
-            self._flat_ws = {B: ws}
+            self._flat_ws[B] = ws
+            while len(self._flat_ws) > self.max_cached_batch_sizes:    # least recently used first; holders of an evicted
+                self._flat_ws.pop(next(iter(self._flat_ws)))           # workspace (CUDA-graph sessions) keep it alive themselves
+        else:
+            self._flat_ws[B] = self._flat_ws.pop(B)                    # most recently used last
         return ws
+
+    def expand_ws(self, ws: torch.Tensor) -> torch.Tensor:
+        """w+ latents as [B, num_ws, w_dim]: brush libraries store projections as [1, num_ws, w] or [1, 1, w]
+        (forger/ui/library.py:146-186, "num_ws or 1"); a single w is repeated for every layer, anything else is refused
+        before a kernel could read past the tensor."""
+        if ws.ndim == 2:
+            ws = ws.unsqueeze(1)
+        if ws.ndim != 3 or ws.shape[2] != self.w_dim or ws.shape[1] not in (1, self.num_ws):
+            raise RuntimeError(f'w+ latents must be [B, {self.num_ws} or 1, {self.w_dim}], got {tuple(ws.shape)}')
+        return ws.expand(-1, self.num_ws, -1) if ws.shape[1] == 1 else ws
 
     def alloc_injection(self, ws_latents: torch.Tensor):
         """Prepare the flat path for ``ws_latents`` [B, num_ws, w_dim]: computes all styles, and returns
@@ -234,6 +249,8 @@ class Generator:
         what ``GeometryEncoder.encode_into`` needs to write feature map i, pre-modulated, into its concat buffer."""
         cfg = self.cfg
         B = ws_latents.shape[0]
+        if tuple(ws_latents.shape[1:]) != (self.num_ws, self.w_dim):
+            raise RuntimeError(f'alloc_injection: ws must be [B, {self.num_ws}, {self.w_dim}] (see expand_ws), got {tuple(ws_latents.shape)}')
         with torch.cuda.device(self.device):
             prep = self._styles(ws_latents.to(torch.float32))
         wsb = self._workspace(B)

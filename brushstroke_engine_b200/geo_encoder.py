@@ -58,7 +58,8 @@ class GeometryEncoder:
         for i in range(max(self.res)):
             self._layers.append(self._fold(params, f'decoder.model.{i}.conv.conv') + (1, 1, True))
         self._n_enc = n_enc
-        self._ws = {}
+        self._ws = {}                      # (batch, H) -> workspace, least recently used first
+        self.max_cached_batch_sizes = 4
         self._flat_s2 = os.environ.get('NBE_ENC_PER_TAP') is None      # A/B switch: strided layers on the per-tap kernel
         if mode == 'bf16':
             if cfg.in_channels != 1 or cfg.pre_filters <= 0 or cfg.pre_filters % 8 or cfg.preproc_type not in PREPROC_CODE:
@@ -124,7 +125,11 @@ class GeometryEncoder:
                     h //= stride
                 # output of layer i, padded for the next conv
                 ws.append(torch.zeros((B, h + 2, h + 2, _cs(w.shape[0])), dtype=torch.bfloat16, device=self.device))
-            self._ws = {key: ws}                           # keep one batch size resident
+            self._ws[key] = ws
+            while len(self._ws) > self.max_cached_batch_sizes:     # least recently used first; a CUDA-graph session that
+                self._ws.pop(next(iter(self._ws)))                 # captured an evicted workspace keeps its own reference
+        else:
+            self._ws[key] = self._ws.pop(key)
         return ws
 
     def encode_into(self, geom, dests, scales=None, scales_ready=None):

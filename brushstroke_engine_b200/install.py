@@ -72,15 +72,46 @@ def generator_config_from_reference(G) -> GeneratorConfig:
                            color_format=getattr(last.torgb, 'color_format', 'triad'))
 
 
+def _check_encoder_layer_order(enc) -> float:
+    """The B200 encoder folds eval-mode BatchNorm into the preceding convolution, which is exact only for the default layer
+    order conv -> BatchNorm -> LeakyReLU (simple_autoencoder.py:102-105) with bilinear ``ScaleUp`` decoder stages.  The
+    ``--neg_slope`` variant (``batchnorm_after_activation=True`` + ``ScaleUpV2``, simple_autoencoder.py:48-53,130-145) has
+    conv -> LeakyReLU -> BatchNorm and transposed-conv up-sampling: refuse it by name instead of producing wrong features.
+    Returns the (single) LeakyReLU slope of the checked layers."""
+    import torch.nn as nn
+    slopes = set()
+    stages = list(enc.encoder.model) + [m for m in enc.decoder.model if hasattr(m, 'conv')]
+    for m in stages:
+        if type(m).__name__ == 'ScaleUpV2' or (hasattr(m, 'conv') and isinstance(m.conv, nn.Sequential)
+                                                and isinstance(m.conv[0], nn.ConvTranspose2d)):
+            raise RuntimeError('encoder_config_from_reference: unsupported geometry encoder: ScaleUpV2 (transposed-conv up-sampling of '
+                               'the --neg_slope variant, simple_autoencoder.py:130-145); only the default sauto layout is built')
+        single = m.conv if isinstance(m.conv, nn.Sequential) else m.conv.conv       # SingleConvolution / ScaleUp(SingleConvolution)
+        kinds = [type(x) for x in single]
+        if len(kinds) != 3 or not issubclass(kinds[0], nn.Conv2d):
+            raise RuntimeError(f'encoder_config_from_reference: unsupported encoder stage {[k.__name__ for k in kinds]}')
+        if issubclass(kinds[1], nn.LeakyReLU) and issubclass(kinds[2], nn.BatchNorm2d):
+            raise RuntimeError('encoder_config_from_reference: unsupported geometry encoder: layer order conv -> LeakyReLU -> BatchNorm '
+                               '(batchnorm_after_activation=True, the --neg_slope variant, simple_autoencoder.py:48-53,102-105); '
+                               'BatchNorm cannot be folded into the preceding convolution in that order')
+        if not (issubclass(kinds[1], nn.BatchNorm2d) and issubclass(kinds[2], nn.LeakyReLU)):
+            raise RuntimeError(f'encoder_config_from_reference: unsupported encoder stage {[k.__name__ for k in kinds]}')
+        slopes.add(float(single[2].negative_slope))
+    if len(slopes) != 1:
+        raise RuntimeError(f'encoder_config_from_reference: layers use different LeakyReLU slopes {sorted(slopes)}')
+    return slopes.pop()
+
+
 def encoder_config_from_reference(enc) -> EncoderConfig:
     e, d = enc.encoder, enc.decoder
+    slope = _check_encoder_layer_order(enc)
     convs = [m.conv[0] for m in e.model]
     n_down = e.num_down_layers
     return EncoderConfig(in_channels=e.in_channels, pre_filters=convs[0].out_channels,
                          down_filters=tuple(c.out_channels for c in convs[1:1 + n_down]),
                          post_filters=tuple(c.out_channels for c in convs[1 + n_down:]),
                          up_filters=tuple(d.up_layer_filters), encode_resolutions=tuple(enc.res),
-                         preproc_type=enc.preproc_name)
+                         preproc_type=enc.preproc_name, neg_slope=slope)
 
 
 def engine_from_reference(ref_engine, mode: str = 'bf16'):

@@ -123,11 +123,16 @@ class CanvasJob:
         dev = engine.device
         self.crop_margin = m = int(crop_margin)
         self.patch = engine.patch_width
+        extra_channels = []                                              # channels besides the last one (sparse modes count them too)
         if isinstance(guidance, np.ndarray):
             assert guidance.ndim == 3 and guidance.dtype == np.uint8
+            if stitching_mode != 'all':
+                extra_channels = [torch.from_numpy(np.ascontiguousarray(guidance[:, :, c])).to(dev) for c in range(guidance.shape[2] - 1)]
             guidance = torch.from_numpy(np.ascontiguousarray(guidance[:, :, -1])).to(dev)
         else:
             assert guidance.ndim == 3 and guidance.dtype == torch.uint8
+            if stitching_mode != 'all':
+                extra_channels = [guidance[:, :, c].to(dev) for c in range(guidance.shape[2] - 1)]
             guidance = guidance[:, :, -1].to(dev)
         H0, W0 = int(guidance.shape[0]), int(guidance.shape[1])
         self.orig_shape = (H0, W0)
@@ -140,10 +145,18 @@ class CanvasJob:
         d_yx = None
         if stitching_mode != 'all':
             # keep crops with more than 10 stroke (zero) pixels (style_transfer.py:45): window sums on the device
+            # (the reference sums over every channel of the stroke image; its own caller always passes one channel)
             counts = torch.empty((nrows * ncols,), dtype=torch.int32, device=dev)
             with torch.cuda.device(dev):
                 _lib.call('nbe_count_stroke_pixels', _lib.ptr(self.d_geom), ph, pw, self.patch, rwidth, nrows, ncols, _lib.ptr(counts),
                           _lib.stream())
+                for ch in extra_channels:
+                    padded = torch.full((ph, pw), 255, dtype=torch.uint8, device=dev)
+                    padded[m:m + H0, m:m + W0] = ch
+                    more = torch.empty_like(counts)
+                    _lib.call('nbe_count_stroke_pixels', _lib.ptr(padded), ph, pw, self.patch, rwidth, nrows, ncols, _lib.ptr(more),
+                              _lib.stream())
+                    counts += more
             keep = (counts > 10).cpu().numpy()
             yx = yx[keep]
         else:
@@ -173,8 +186,9 @@ class CanvasJob:
     def gather(self, start: int, end: int) -> torch.Tensor:
         n = end - start
         out = torch.empty((n, 1, self.patch, self.patch), dtype=torch.float32, device=self.engine.device)
-        _lib.call('nbe_gather_geom_patches', _lib.ptr(self.d_geom), self.canvas_h, self.canvas_w,
-                  _lib.ptr(self.d_crops[start:end]), _lib.ptr(out), n, self.patch, _lib.stream())
+        with torch.cuda.device(self.engine.device):
+            _lib.call('nbe_gather_geom_patches', _lib.ptr(self.d_geom), self.canvas_h, self.canvas_w,
+                      _lib.ptr(self.d_crops[start:end]), _lib.ptr(out), n, self.patch, _lib.stream())
         return out
 
     def gather_indices(self, d_idx: torch.Tensor) -> torch.Tensor:
@@ -182,20 +196,23 @@ class CanvasJob:
         n = int(d_idx.shape[0])
         crops = self.d_crops[d_idx].contiguous()
         out = torch.empty((n, 1, self.patch, self.patch), dtype=torch.float32, device=self.engine.device)
-        _lib.call('nbe_gather_geom_patches', _lib.ptr(self.d_geom), self.canvas_h, self.canvas_w, _lib.ptr(crops), _lib.ptr(out), n,
-                  self.patch, _lib.stream())
+        with torch.cuda.device(self.engine.device):
+            _lib.call('nbe_gather_geom_patches', _lib.ptr(self.d_geom), self.canvas_h, self.canvas_w, _lib.ptr(crops), _lib.ptr(out), n,
+                      self.patch, _lib.stream())
         return out
 
     def owner_map(self) -> torch.Tensor:
         owner = torch.empty((self.canvas_h, self.canvas_w), dtype=torch.int32, device=self.engine.device)
-        _lib.call('nbe_tile_owner_map', _lib.ptr(self.d_tiles_yx), len(self.crops_yx), self.tile, _lib.ptr(owner),
-                  self.canvas_h, self.canvas_w, _lib.stream())
+        with torch.cuda.device(self.engine.device):
+            _lib.call('nbe_tile_owner_map', _lib.ptr(self.d_tiles_yx), len(self.crops_yx), self.tile, _lib.ptr(owner),
+                      self.canvas_h, self.canvas_w, _lib.stream())
         return owner
 
     def place(self, canvas: torch.Tensor, owner: torch.Tensor, tiles: torch.Tensor, start: int, end: int):
         order = torch.arange(start, end, dtype=torch.int32, device=self.engine.device)
-        _lib.call('nbe_place_tiles', _lib.ptr(tiles), _lib.ptr(self.d_tiles_yx[start:end]), _lib.ptr(order), end - start,
-                  self.tile, _lib.ptr(owner), _lib.ptr(canvas), self.canvas_h, self.canvas_w, _lib.stream())
+        with torch.cuda.device(self.engine.device):
+            _lib.call('nbe_place_tiles', _lib.ptr(tiles), _lib.ptr(self.d_tiles_yx[start:end]), _lib.ptr(order), end - start,
+                      self.tile, _lib.ptr(owner), _lib.ptr(canvas), self.canvas_h, self.canvas_w, _lib.stream())
 
     def finish(self, canvas: torch.Tensor, on_white: bool, to_host: bool = True):
         """Crop back to the input size (paint_image_main.py:185-186); optional on-white composite (:179-183)."""

@@ -189,6 +189,33 @@ def test_interactive_graph_session_equals_render_stroke(engines):
     assert np.array_equal(sess.render_stroke(patch, (5, 7)), ref)
 
 
+def test_interactive_graph_session_survives_other_batch_sizes(engines):
+    """A graph session keeps replaying correctly while the same engine serves other batch sizes in between (the generator /
+    encoder workspace caches are LRU: more distinct sizes than they hold evict the batch-1 buffers the graph points into,
+    which the session must keep alive itself)."""
+    eng = engines['bf16']
+    opts = _opts(P.style_z_from_seed(33), '33')
+    sess = eng.interactive_session(opts, crop_margin=0)
+    geom = synthetic.synthetic_patch(128, seed=4)[0, 0]
+    patch = np.ascontiguousarray(((1.0 - geom) * 255).astype(np.uint8)[:, :, None])
+    o = _opts(P.style_z_from_seed(33), '33')
+    o.position = torch.tensor([[40, 50]], dtype=torch.int64)
+    ref, _ = eng.render_stroke(patch, None, o)
+    assert np.array_equal(sess.render_stroke(patch, (40, 50)), ref)
+    n_sizes = eng.G.max_cached_batch_sizes + 2
+    for B in range(2, 2 + n_sizes):                               # evicts batch 1 from both caches
+        g = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=50 + i) for i in range(B)])).to(eng.device)
+        ob = _opts(torch.cat([P.style_z_from_seed(100 + i) for i in range(B)]))
+        eng.render_tiles(g, ob, crop_margin=10)
+    assert 1 not in eng.G._flat_ws
+    torch.cuda.synchronize()
+    junk = [torch.full((1 << 22,), 7.0, device=eng.device) for _ in range(8)]      # would land in freed batch-1 buffers
+    assert np.array_equal(sess.render_stroke(patch, (40, 50)), ref)
+    del junk
+    ref2, _ = eng.render_stroke(patch, None, o)                   # a fresh batch-1 workspace next to the session's
+    assert np.array_equal(ref2, ref) and np.array_equal(sess.render_stroke(patch, (40, 50)), ref)
+
+
 @pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
 def test_wplus_library_style_with_noise_buffers_matches_oracle(engines, bundles, mode, tol, tmp_path):
     """A projected brush (w+ code and its own per-layer noise maps, forger/ui/library.py:146-202) set through

@@ -126,6 +126,28 @@ def test_upfirdn2d_packed_path_padding_sweep(dtype, tol):
     assert torch.equal(torch.isfinite(y), torch.isfinite(ref))
 
 
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 3e-6), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize('up', [1, 2])
+def test_upfirdn2d_large_and_negative_paddings(dtype, tol, up):
+    """4x4 filter, dense NCHW, down = 1 with paddings outside the staged kernels' range (>= 4: e.g. filter2d(x, f4,
+    padding=2) gives padx0 = 4; negative = cropping): routed to the generic kernel, checked against the oracle."""
+    from brushstroke_engine_b200 import upfirdn2d as U
+    f4 = O.setup_filter([1, 3, 3, 1])
+    gen = torch.Generator().manual_seed(23 + up)
+    x = (torch.randn(2, 3, 13, 21, generator=gen) * 2).to(dtype)
+    n = 0
+    for px0, px1, py0, py1 in [(4, 1, 1, 1), (4, 3, 4, 3), (5, 5, 5, 5), (8, 0, 2, 7), (0, 6, 6, 0), (3, 4, 3, 3), (2, 1, 4, 1),
+                               (-3, 2, 1, 1), (1, -2, 2, 2), (2, 2, -1, 3), (1, 1, 2, -2), (-2, -1, -1, -1), (7, -1, -2, 8)]:
+        y = U.upfirdn2d(x.to(DEV), f4.to(DEV), up=up, padding=[px0, px1, py0, py1], gain=up * up)
+        ref = O.upfirdn2d(x.float(), f4, up=up, padding=[px0, px1, py0, py1], gain=float(up * up))
+        assert y.shape == ref.shape, (px0, px1, py0, py1)
+        assert md(y, ref) < tol * 12, (px0, px1, py0, py1)
+        n += 1
+    y = U.filter2d(x.to(DEV), f4.to(DEV), padding=2)                  # the advisor's example: padx0 = 4
+    assert md(y, O.upfirdn2d(x.float(), f4, padding=[4, 3, 4, 3])) < tol * 12
+    assert n == 13
+
+
 def test_modconv_golden():
     from brushstroke_engine_b200.conv2d_resample import conv2d_resample
     from brushstroke_engine_b200.modconv import modulated_conv2d
