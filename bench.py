@@ -112,6 +112,52 @@ def cpu_port_patches_per_sec(sets, n_patches: int, reps: int, threads: int):
     return n_patches / float(np.median(times)), times
 
 
+def cpu_port_b1_ms(sets, threads: int) -> float:
+    """BASELINE configs[0]: the CPU path on ONE 128x128 patch, batch 1: median of 20 runs after 3 warm-ups (ms)."""
+    times = []
+    for _ in range(3):
+        cpu_port_patches_per_sec(sets, 1, 1, threads)
+    _, times = cpu_port_patches_per_sec(sets, 1, 20, threads)
+    return float(np.median(times)) * 1e3
+
+
+def gpu_incumbent(sets_dev, dev, B, steps=4):
+    """The incumbent GPU path on the same batch (tools/incumbent_torch.py: the reference as shipped on this torch = its
+    impl='ref' ops + cuDNN): patches/s for stock mixed fp16 (channels_last), the same with bf16
+    operands, and forced fp32.  CUDA events, 2 warm-ups + `steps` timed steps per mode."""
+    sys.path.insert(0, os.path.join(REPO, 'tools'))
+    from incumbent_torch import Incumbent
+    cfg, ecfg = P.GeneratorConfig(), P.EncoderConfig()
+    gp = P.init_generator_params(cfg, 0, 0.1)
+    ep = P.init_encoder_params(ecfg, 1, 0.1)
+    out = {}
+    for tag, lowp, f32 in (('fp16_channels_last', torch.float16, False), ('bf16_channels_last', torch.bfloat16, False), ('fp32', torch.float16, True)):
+        try:
+            inc = Incumbent(gp, ep, cfg, ecfg, dev, lowp=lowp, force_fp32=f32)
+            with torch.no_grad():
+                for i in range(2):
+                    g, z, pos = sets_dev[i % len(sets_dev)]
+                    inc.render_tiles(g, z, pos)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    g, z, pos = sets_dev[i % len(sets_dev)]
+                    inc.render_tiles(g, z, pos)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = {'patches_per_s': B / ms * 1e3, 'ms_per_step': ms}
+            del inc
+            torch.cuda.empty_cache()
+        except Exception as ex:                                      # an out-of-memory cuDNN plan must not take the bench line down
+            out[tag] = {'error': f'{type(ex).__name__}: {str(ex)[:160]}'}
+            torch.cuda.empty_cache()
+    out['what'] = ('reference as shipped on torch 2.x (plugins do not load -> impl=ref ATen ops + cuDNN convs), restated in '
+                   'tools/incumbent_torch.py; same batch, encoder + generator + composite, device-resident inputs')
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -122,13 +168,18 @@ def run_reference(args):
     for _ in range(args.warmup):
         cpu_port_patches_per_sec(sets, n, 1, threads)
     v, times = cpu_port_patches_per_sec(sets, n, max(args.steps, 1), threads)
+    b1_ms = cpu_port_b1_ms(sets, threads)
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': float(np.median(times)) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'NeuBE style2 generator forward (encoder+mapping+synthesis+triad composite), batch {args.batch} '
-                                   f'x 128x128 patches, distinct z per patch', 'batch': args.batch},
+            'config': {'workload': f'NeuBE style2 generator forward (encoder+mapping+synthesis+triad composite), {n}-patch sample per step '
+                                   f'(the first {n} patches of the batch-{args.batch} workload of BASELINE configs[1]; the CPU path is '
+                                   f'fastest per patch at this batch size), 128x128 patches, distinct z per patch',
+                       'batch': n, 'sample_of_batch': args.batch},
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                             'sample': f'{n} patches per step (first {n} of the {args.batch}-patch batch), fp32, {threads} threads'},
+                             'sample': f'{n} patches per step (first {n} of the {args.batch}-patch batch), fp32, {threads} threads',
+                             'config0_b1_ms': b1_ms,
+                             'config0': 'BASELINE configs[0]: one 128x128 patch, batch 1, median of 20 after 3 warm-ups'},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -145,6 +196,7 @@ def main():
     ap.add_argument('--no-blend', action='store_true', help='skip the feature-blending (level 2) canvas leg')
     ap.add_argument('--canvas', type=int, default=4096, help='side of the synthetic canvas for the stylization leg')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (profiling runs under ncu)')
+    ap.add_argument('--no-incumbent', action='store_true', help='skip the cuDNN / ATen incumbent leg')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -243,41 +295,81 @@ def main():
                 reps.append(time.perf_counter() - t0)
             e2e_s = sorted(reps)[1]
 
-    # ---- BASELINE configs[4]: 4096^2 canvas, style interpolated across 8 z anchors, crop rows sharded over the ranks,
-    #      one NCCL gather of finished tiles to rank 0 (time = host guidance in -> finished uint8 canvas on rank 0) ----
+    incumbent = None
+    if world == 1 and not args.no_incumbent:
+        incumbent = gpu_incumbent(dsets, dev, B)
+
+    # ---- BASELINE configs[4] / configs[3]: 4096^2 canvas with the style interpolated across 8 z anchors, and the 2000^2
+    #      line-drawing stylization with one style; crop rows sharded over the ranks, ONE batched send/recv of the owned canvas
+    #      bands to rank 0 (time = guidance in -> finished uint8 canvas on rank 0) ----
     canvas_ms = None
+    canvas_legs = {}
     if not args.no_canvas:
         from brushstroke_engine_b200 import stylizer
+
+        def canvas_leg(size, interpolate):
+            guidance = synthetic.synthetic_guidance(size, size, num_lines=256 if size >= 4096 else 64, seed=0)
+            job_crops, _ = stylizer.generate_stitching_crops(stylizer.pad_geo(guidance, 10), 128, 'all', 20)
+            copts = GanBrushOptions()
+            z_pp = None
+            if interpolate:
+                anchors = np.concatenate([np.random.RandomState(seed=k).randn(1, 64) for k in range(8)])
+                xs = np.array([c[1] for c in job_crops], dtype=np.float64) / max(1, max(c[1] for c in job_crops))
+                t_ = xs * 7.0
+                k0 = np.clip(np.floor(t_).astype(int), 0, 6)
+                a_ = (t_ - k0)[:, None]
+                z_pp = torch.from_numpy((1 - a_) * anchors[k0] + a_ * anchors[k0 + 1]).to(dev)   # z = alpha z1 + (1 - alpha) z2 per patch
+                copts.set_style(z_pp[:1])
+            else:
+                copts.set_style(torch.from_numpy(np.random.RandomState(594).randn(1, 64)).to(dev), '594')
+            ctimes, htimes = [], []
+            d_guidance = torch.from_numpy(guidance).to(dev)
+            out = None
+            with torch.no_grad():
+                for rep in range(4):
+                    barrier()
+                    t0 = time.perf_counter()
+                    out = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, batch_size=B, z_per_patch=z_pp, to_host=False)
+                    barrier()
+                    if rep > 0:
+                        ctimes.append((time.perf_counter() - t0) * 1e3)
+                for rep in range(3):
+                    barrier()
+                    t0 = time.perf_counter()
+                    stylizer.stylize(engine, guidance, copts, crop_margin=10, batch_size=B, z_per_patch=z_pp)
+                    barrier()
+                    if rep > 0:
+                        htimes.append((time.perf_counter() - t0) * 1e3)
+                # per-phase breakdown (its own run: filling `timings` synchronises between phases), max over ranks below
+                phases = {}
+                barrier()
+                stylizer.stylize(engine, d_guidance, copts, crop_margin=10, batch_size=B, z_per_patch=z_pp, to_host=False, timings=phases)
+                barrier()
+                # the sharded canvas must equal the canvas one GPU renders by itself, bit for bit
+                equal = None
+                if world > 1 and rank == 0:
+                    solo = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, batch_size=B, z_per_patch=z_pp, to_host=False,
+                                            distributed=False)
+                    equal = bool(torch.equal(solo, out))
+                barrier()
+            names = ('setup', 'render', 'place', 'exchange', 'finish')
+            pt = torch.tensor([phases.get(k, 0.0) for k in names] + [float(np.median(ctimes)), float(np.median(htimes))],
+                              dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+            leg = {'size': size, 'patches': len(job_crops), 'ms': float(pt[5]), 'ms_host_to_host': float(pt[6]), 'n_gpus': world,
+                   'phases_ms_max_over_ranks': {k: round(float(pt[i]), 3) for i, k in enumerate(names)},
+                   'style': '8-anchor z interpolation along x' if interpolate else 'one style (seed 594)'}
+            if equal is not None:
+                leg['canvas_equals_1gpu'] = equal
+            return leg, d_guidance, copts, z_pp
+
         size = args.canvas
-        guidance = synthetic.synthetic_guidance(size, size, num_lines=256 if size >= 4096 else 64, seed=0)
-        job_crops, _ = stylizer.generate_stitching_crops(stylizer.pad_geo(guidance, 10), 128, 'all', 20)
-        anchors = np.concatenate([np.random.RandomState(seed=k).randn(1, 64) for k in range(8)])
-        xs = np.array([c[1] for c in job_crops], dtype=np.float64) / max(1, max(c[1] for c in job_crops))
-        t_ = xs * 7.0
-        k0 = np.clip(np.floor(t_).astype(int), 0, 6)
-        a_ = (t_ - k0)[:, None]
-        z_pp = torch.from_numpy((1 - a_) * anchors[k0] + a_ * anchors[k0 + 1]).to(dev)     # z = alpha z1 + (1 - alpha) z2 per patch
-        copts = GanBrushOptions()
-        copts.set_style(z_pp[:1])
-        ctimes, htimes = [], []
-        d_guidance = torch.from_numpy(guidance).to(dev)
-        with torch.no_grad():
-            for rep in range(4):
-                barrier()
-                t0 = time.perf_counter()
-                out = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, batch_size=B, z_per_patch=z_pp, to_host=False)
-                barrier()
-                if rep > 0:
-                    ctimes.append((time.perf_counter() - t0) * 1e3)
-            for rep in range(3):
-                barrier()
-                t0 = time.perf_counter()
-                out = stylizer.stylize(engine, guidance, copts, crop_margin=10, batch_size=B, z_per_patch=z_pp)
-                barrier()
-                if rep > 0:
-                    htimes.append((time.perf_counter() - t0) * 1e3)
-        canvas_ms = float(np.median(ctimes))
-        canvas_host_ms = float(np.median(htimes))
+        leg, d_guidance, copts, z_pp = canvas_leg(size, True)
+        canvas_legs['main'] = leg
+        canvas_ms = leg['ms']
+        canvas_host_ms = leg['ms_host_to_host']
+        n_canvas_patches = leg['patches']
         # the reference's own stylization script runs with --feature_blending_level=2 (scripts/neube_stylize.sh): patches then
         # depend on their raster predecessors; wavefront-batched on one GPU (rank 0 only, the other ranks idle)
         blend_ms = None
@@ -287,14 +379,16 @@ def main():
                 for rep in range(3):
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    out = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, feature_blending_level=2, z_per_patch=z_pp, to_host=False,
-                                           distributed=False)
+                    stylizer.stylize(engine, d_guidance, copts, crop_margin=10, feature_blending_level=2, z_per_patch=z_pp, to_host=False,
+                                     distributed=False)
                     torch.cuda.synchronize()
                     if rep > 0:
                         btimes.append((time.perf_counter() - t0) * 1e3)
             blend_ms = float(np.median(btimes))
         barrier()
-        n_canvas_patches = len(job_crops)
+        del d_guidance
+        if size != 2000:
+            canvas_legs['config3_2000'] = canvas_leg(2000, False)[0]          # BASELINE configs[3]
 
     # ---- interactive use: one 128^2 stroke patch per call through the reference-facing render_stroke
     #      (host uint8 patch in, host uint8 RGBA out; wall clock, rank 0) ----
@@ -324,12 +418,10 @@ def main():
                 glat.append((time.perf_counter() - t0) * 1e3)
         interactive_graph_ms = float(np.median(glat))
     barrier()
-    times = torch.tensor([ms_total, e2e_s * 1e3, canvas_ms if canvas_ms is not None else 0.0], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(times[0]), float(times[1])
-    if canvas_ms is not None:
-        canvas_ms = float(times[2])
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
@@ -339,11 +431,16 @@ def main():
         peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
-    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
-    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.4 PFLOP/s sustained (of fallback)'
+    # the dominant kernel is timed inside a step that lasts a few ms at full clock, not inside a seconds-long power-capped
+    # run: the BURST peak is the denominator of `frac`; the sustained one is printed beside it
+    peak_tf = peaks.get('bf16_tflops', 1633.0)
+    peak_sus = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops (burst, measured)' if peaks else 'fallback 1.63 PFLOP/s burst (B200_PROFILING.md)'
     R, C = 128, 128
     dom_flops = 2.0 * C * C * 9 * R * R * B                          # algorithmic: 2*Cout*Cin*k^2*H*W per patch
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
+    step_flops = (8.676e9 + 1.73e9) * B                              # generator 8.676 + encoder 1.73 GFLOP per patch
+    step_tf = step_flops / (ms_per_step * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(REPO, 'profiles', 'dominant_kernel_traffic.json')
     if os.path.exists(tpath):
@@ -365,7 +462,10 @@ def main():
             'roofline': {'bound': 'tensor', 'kernel': f'conv_tc_row128_kernel @ {DOM} (3x3 modconv 128->128 @128^2 with ToRGB/triad fused in the epilogue, batch {B})',
                          'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                          'traffic': traffic, 'peak_source': peak_src, 'avg_launch_ms': dom_ms,
-                         'algorithmic_flops_per_launch': dom_flops},
+                         'algorithmic_flops_per_launch': dom_flops,
+                         'peak_sustained': peak_sus, 'frac_of_sustained': achieved / peak_sus,
+                         'step': {'what': 'whole step: algorithmic FLOPs of encoder + generator (10.406 GFLOP/patch) / ms_per_step',
+                                  'achieved': step_tf, 'frac': step_tf / peak_tf, 'frac_of_sustained': step_tf / peak_sus}},
             'e2e': {'value': e2e_value, 'unit': UNIT,
                     'h2d_bytes_per_step': int(B * 128 * 128 + B * 64 * 8 + B * 2 * 8), 'd2h_bytes_per_step': int(B * 108 * 108 * 4),
                     'timing': f'median of 3 repetitions of {args.steps} steps, wall clock around render_patches_host with pinned host buffers'},
@@ -376,17 +476,24 @@ def main():
             line['interactive'] = {'ms_per_stroke_patch': interactive_ms, 'ms_per_stroke_patch_cuda_graph': interactive_graph_ms,
                                    'what': 'batch 1, host uint8 patch -> host uint8 RGBA, wall-clock median (rank 0): TriadPaintEngine.render_stroke (eager, ~60 launches) and InteractiveSession.render_stroke (one CUDA-graph replay)'}
         if canvas_ms is not None:
-            line['canvas'] = {'size': args.canvas, 'patches': n_canvas_patches, 'ms': canvas_ms, 'ms_host_to_host': canvas_host_ms, 'n_gpus': world,
-                              'ms_feature_blending_level2_1gpu': blend_ms,
-                              'what': 'uint8 guidance on the device -> crops -> encoder+generator+composite (8-anchor z interpolation) -> '
-                                      'tile gather to rank 0 (NCCL when n_gpus > 1) -> placed uint8 canvas on rank 0 (SURVEY 8d config 5); '
-                                      'ms_host_to_host adds the guidance upload and the canvas download (rank-0 wall clock)'}
+            line['canvas'] = dict(canvas_legs['main'])
+            line['canvas'].update({'ms_feature_blending_level2_1gpu': blend_ms,
+                                   'what': 'uint8 guidance on the device -> crops -> encoder+generator+composite (8-anchor z interpolation) -> '
+                                           'every rank places its tiles into the canvas rows it owns -> one batched NCCL send/recv of those bands '
+                                           'into the canvas on rank 0 (SURVEY 8d config 5); ms_host_to_host: host guidance in (each rank uploads '
+                                           'only the rows its crops read), pinned host canvas out (wall clock, max over ranks)'})
+            if 'config3_2000' in canvas_legs:
+                line['canvas_2000'] = canvas_legs['config3_2000']
+        if world == 1 and not args.no_incumbent:
+            line['gpu_incumbent'] = incumbent
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             # bounded sample, ~10 s of CPU work: 8-patch batches (the port's fastest batch size; larger ones are slower per patch)
             n, reps = 8, 48
             v, times_cpu = cpu_port_patches_per_sec(sets, n, reps, threads)
-            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            b1_ms = cpu_port_b1_ms(sets, threads)
+            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'config0_b1_ms': b1_ms,
+                                    'config0': 'BASELINE configs[0]: one 128x128 patch, batch 1, median of 20 after 3 warm-ups',
                                     'sample': f'{n} patches x {reps} reps of the same workload (fp32 oracle port, {threads} threads, median; '
                                               f'{sum(times_cpu):.1f} s of CPU work)'}
         print(json.dumps(line))

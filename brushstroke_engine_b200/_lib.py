@@ -57,6 +57,12 @@ _SIGNATURES = {
     'nbe_tile_owner_map': [_P, _I, _I, _P, _I, _I, _P],
     'nbe_place_tiles': [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P],
     'nbe_blend_features': [_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
+    'nbe_modulated_conv2d': [_P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _L, _P],
+}
+
+# entry points that do not return a status: name -> (restype, argtypes)
+_OTHER = {
+    'nbe_modulated_conv2d_workspace': (c_int64, [_I, _I, _I, _I, _I, _I, _I, _I, _I]),
 }
 
 _lib = None
@@ -79,6 +85,10 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int
+    for name, (restype, argtypes) in _OTHER.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
     if lib.nbe_abi_version() != 1:
         raise RuntimeError(f'libnbe_b200.so ABI version {lib.nbe_abi_version()} != 1; rebuild it')
     _lib = lib
@@ -86,7 +96,7 @@ def load() -> ctypes.CDLL:
 
 
 def exported_symbols():
-    return ['nbe_abi_version', 'nbe_last_error', 'nbe_launch_count'] + list(_SIGNATURES.keys())
+    return ['nbe_abi_version', 'nbe_last_error', 'nbe_launch_count'] + list(_SIGNATURES.keys()) + list(_OTHER.keys())
 
 
 def launch_count() -> int:
@@ -100,6 +110,48 @@ def call(name: str, *args) -> None:
     if status != 0:
         msg = lib.nbe_last_error().decode('utf-8', 'replace')
         raise RuntimeError(f'{name} failed ({status}): {msg}')
+
+
+# ---- profiler ranges --------------------------------------------------------------------------------------------------
+# The reference marks its hot functions with `misc.profiled_function` / `record_function` (SG2/torch_utils/misc.py:98-103;
+# names: 'modulated_conv2d', 'normalize_2nd_moment', '_bias_act_ref' -> 'bias_act', '_upfirdn2d_ref' -> 'upfirdn2d', 'input',
+# 'broadcast', 'truncate', 'split_ws').  With NBE_NVTX=1 the same names appear as NVTX ranges around the corresponding launches
+# (visible in nsys / ncu --nvtx); off by default: a range costs ~1 us of host time per call.
+NVTX = os.environ.get('NBE_NVTX', '0') not in ('', '0')
+
+
+class nvtx_range:
+    __slots__ = ('name',)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+def profiled(name: str):
+    """Decorator form of ``nvtx_range`` (the reference's ``misc.profiled_function``)."""
+    def deco(fn):
+        if not NVTX:
+            return fn
+        import functools
+
+        @functools.wraps(fn)
+        def wrapped(*a, **k):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco
 
 
 def ptr(t):

@@ -26,6 +26,7 @@ activation_funcs = {
 }
 
 
+@_lib.profiled('bias_act')
 def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):
     """Fused bias + activation + gain + clamp.  Same arguments, shape, dtype and
     memory format of the result as the reference op."""

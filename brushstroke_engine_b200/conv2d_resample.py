@@ -57,6 +57,7 @@ def _conv(x, w, padding=0, stride=1, groups=1, flip_weight=True):
     return y.to(dtype)
 
 
+@_lib.profiled('conv2d_resample')
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
     """2D convolution with optional up/downsampling; padding is applied once, up front."""
     assert isinstance(x, torch.Tensor) and (x.ndim == 4)
@@ -71,6 +72,14 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     kh, kw = int(w.shape[2]), int(w.shape[3])
     fw, fh = _get_filter_size(f)
     px0, px1, py0, py1 = _parse_padding(padding)
+    # 16-bit activations, 3x3 kernel, no down-sampling: the tensor-core kernels behind nbe_modulated_conv2d (styles = NULL)
+    if x.dtype in (torch.bfloat16, torch.float16) and groups == 1 and down == 1 and up in (1, 2) and kh == kw == 3 \
+            and px0 == px1 == py0 == py1 and px0 >= 0 and (up == 1 or (f is not None and fw == fh == 4)):
+        from .modconv import modconv_entry
+        if _lib.load().nbe_modulated_conv2d_workspace(_lib.DTYPE_CODE[x.dtype], int(x.shape[0]), int(x.shape[1]), int(x.shape[2]),
+                                                      int(x.shape[3]), int(w.shape[0]), 3, up, px0) >= 0:
+            ff = f if (f is None or not flip_filter) else f.flip(list(range(f.ndim)))
+            return modconv_entry(x, w, None, None, up, px0, ff, False, flip_weight)
 
     # Adjust padding to account for up/downsampling (conv2d_resample.py:94-104).
     if up > 1:

@@ -582,14 +582,15 @@ extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_o
                                         int N, int H, int W, int Cin, int x_cs, int x_pitch, int Cout, int t_cs,
                                         int64_t t_row_pitch, int64_t t_img_pitch, const float* dcoef, nbe_stream_t stream) {
     NBE_REQUIRE(x && wq && t_out && N >= 0 && H >= 1 && W >= 1 && Cin >= 1, "convT3x3s2_flat: bad arguments");
-    NBE_REQUIRE(Cout == 128, "convT3x3s2_flat: Cout must be 128");
+    NBE_REQUIRE(Cout >= 128 && Cout % 128 == 0, "convT3x3s2_flat: Cout must be a multiple of 128 (one pass per 128 output channels)");
     NBE_REQUIRE(x_pitch >= W + 1, "convT3x3s2_flat: input pitch %d too small (needs a zero gap column)", x_pitch);
     NBE_REQUIRE(x_cs % 8 == 0 && x_cs >= Cin && t_cs % 8 == 0 && t_cs >= Cout, "convT3x3s2_flat: channel strides must be multiples of 8");
     NBE_REQUIRE((((uintptr_t)x | (uintptr_t)wq | (uintptr_t)t_out) & 15) == 0, "convT3x3s2_flat: tensors must be 16-byte aligned");
     NBE_REQUIRE(t_row_pitch >= 2 * W + 1 && t_img_pitch >= t_row_pitch * (2 * H + 1), "convT3x3s2_flat: bad output pitches");
     if (N == 0) return NBE_OK;
+  for (int co = 0; co < Cout; co += 128) {
     FlatParams p{};
-    p.y = (__nv_bfloat16*)t_out; p.P = x_pitch; p.positions = (H + 1) * x_pitch;
+    p.y = (__nv_bfloat16*)t_out + co; p.P = x_pitch; p.positions = (H + 1) * x_pitch;
     // Cin <= 128: the phase weights stay resident, one tile per item and double-buffered accumulators.  Wider inputs stream
     // their weights and are L2-bound on them: two tiles per item share every weight tile (all 512 TMEM columns, the epilogue
     // is then not overlapped -- less than the halved weight traffic buys)
@@ -616,9 +617,12 @@ extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_o
         p.ph_G[ph] = 2;
     }
     p.n_phases = 2; p.Gmax = 2;
-    p.y_cs = t_cs; p.y_row_pitch = t_row_pitch; p.y_img_pitch = t_img_pitch; p.noise_w = 0; p.vec_stride = 128; p.cout_off = 0;
-    p.dcoef = dcoef; p.noise = nullptr; p.noise_sn = 0; p.noise_gain = 0.f;
+    p.y_cs = t_cs; p.y_row_pitch = t_row_pitch; p.y_img_pitch = t_img_pitch; p.noise_w = 0; p.vec_stride = Cout; p.cout_off = co;
+    p.dcoef = dcoef ? dcoef + co : nullptr; p.noise = nullptr; p.noise_sn = 0; p.noise_gain = 0.f;
     p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.gain = 1.f; p.clamp = -1.f; p.next_scale = nullptr;
     FlatInput in{x, N, Cin, x_cs, H * x_pitch, 0, 0, 0};
-    return launch_flat(in, wq, 9, 128, p, taps, phase_ntaps, (cudaStream_t)stream);
+    int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream);
+    if (st) return st;
+  }
+    return NBE_OK;
 }

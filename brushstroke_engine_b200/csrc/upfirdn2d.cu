@@ -209,6 +209,11 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
     }
     __syncthreads();
     if ((int)blockIdx.x < n_items) stage(blockIdx.x, 0);
+    // the (at most two) edge chunks of the first item are written by threads 0 / 1 with ordinary stores: the mbarrier only
+    // covers the bulk copy, so the other threads need this barrier before they read them (later items are staged one
+    // iteration ahead and ordered by the barrier that ends every iteration).  Found by compute-sanitizer (round 2):
+    // under its timing the last chunk of a plane was read before it was written.
+    __syncthreads();
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = s_f[i];

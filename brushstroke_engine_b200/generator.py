@@ -83,15 +83,18 @@ class MappingNetwork:
         assert z.ndim == 2 and z.shape[1] == self.z_dim
         x = z if z.dtype in (torch.float32, torch.float64) else z.to(torch.float32)
         x = x.contiguous()
-        for i in range(self.num_layers):
-            x = fully_connected(x, G._map_w[i], G._map_b[i], ACT_LRELU, G.cfg.mapping_lr_multiplier, SQRT2, 0.2,
-                                normalize=(i == 0))
-        ws = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        with _lib.nvtx_range('input'):                              # normalize_2nd_moment is fused into the first FC
+            for i in range(self.num_layers):
+                x = fully_connected(x, G._map_w[i], G._map_b[i], ACT_LRELU, G.cfg.mapping_lr_multiplier, SQRT2, 0.2,
+                                    normalize=(i == 0))
+        with _lib.nvtx_range('broadcast'):
+            ws = x.unsqueeze(1).repeat([1, self.num_ws, 1])
         if truncation_psi != 1:
-            if truncation_cutoff is None:
-                ws = G._w_avg.lerp(ws, truncation_psi)
-            else:
-                ws[:, :truncation_cutoff] = G._w_avg.lerp(ws[:, :truncation_cutoff], truncation_psi)
+            with _lib.nvtx_range('truncate'):
+                if truncation_cutoff is None:
+                    ws = G._w_avg.lerp(ws, truncation_psi)
+                else:
+                    ws[:, :truncation_cutoff] = G._w_avg.lerp(ws[:, :truncation_cutoff], truncation_psi)
         return ws
 
 
@@ -579,8 +582,11 @@ class Generator:
         xin = wsb['in4']
         xin[:, :, :4, :] = (self._const_nhwc.unsqueeze(0) * styles[c4.name][:, None, None, :]).to(torch.bfloat16)
         xin_pitch = 5
+        nvtx = _lib.NVTX
         for res in cfg.block_resolutions:
             conv1 = self._layer_by_name[f'b{res}.conv1']
+            if nvtx:
+                torch.cuda.nvtx.range_push(f'b{res}: modulated_conv2d + bias_act')
             if res > 4:
                 conv0 = self._layer_by_name[f'b{res}.conv0']
                 Rin = res // 2
@@ -617,6 +623,8 @@ class Generator:
                           conv1.cout, conv1.cout, 3, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
                           _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, None, st)
                 img, uvs = self._torgb(y, True, conv1.cout, rgb_styles, colors, B)
+                if nvtx:
+                    torch.cuda.nvtx.range_pop()
                 break
             if res == last:
                 ev = None
@@ -632,6 +640,8 @@ class Generator:
                 if ev is not None:
                     ev[1].record()
                     self.probe[conv1.name].append(ev)
+                if nvtx:
+                    torch.cuda.nvtx.range_pop()
                 break
             # conv1 -> next block's (pre-modulated, concatenated, zero-gapped) input
             nxt = self._layer_by_name[f'b{res * 2}.conv0']
@@ -651,6 +661,8 @@ class Generator:
                     out[:, :, :res, conv1.cout:conv1.cout + extra] = tmp
                 geo_idx += 1
             xin, xin_pitch = out, res + 1
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
         return img, uvs, {}
 
     def _unpack(self, x, B, C, R, cs):

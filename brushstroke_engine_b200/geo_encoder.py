@@ -132,6 +132,7 @@ class GeometryEncoder:
             self._ws[key] = self._ws.pop(key)
         return ws
 
+    @_lib.profiled('encode')
     def encode_into(self, geom, dests, scales=None, scales_ready=None):
         """Run the bf16 encoder and write feature map ``r`` (index into ``self.res``) into ``dests[r] = (tensor, c_off)``:
         an NHWC bf16 tensor [B, R, pitch >= R, cs] whose channels [c_off, c_off + C_r) of the first R columns receive the

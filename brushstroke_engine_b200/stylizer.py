@@ -118,11 +118,20 @@ class CanvasJob:
     tensor [H,W,C]; the padded canvas (pad_geo + generate_stitching_crops padding, value 255) is built on the device
     and the crop list comes from the grid arithmetic, so nothing but the (optional) initial upload touches the host."""
 
-    def __init__(self, engine: TriadPaintEngine, guidance, crop_margin: int = 10, stitching_mode: str = 'all'):
+    def __init__(self, engine: TriadPaintEngine, guidance, crop_margin: int = 10, stitching_mode: str = 'all',
+                 crop_rows: Optional[Tuple[int, int]] = None):
+        """``crop_rows = (r0, r1)`` (dense 'all' grid only) restricts the job to the crop rows [r0, r1) of the grid: only the
+        guidance rows those crops read are uploaded / kept on the device, the crop list holds those rows only (global (y, x)
+        coordinates, as the generator's noise shift needs them) and ``band`` gives the canvas rows the job's tiles own."""
         self.engine = engine
         dev = engine.device
         self.crop_margin = m = int(crop_margin)
         self.patch = engine.patch_width
+        if crop_rows is not None:
+            self._init_row_window(guidance, stitching_mode, crop_rows)
+            return
+        self.geom_row0 = 0
+        self.band = None
         extra_channels = []                                              # channels besides the last one (sparse modes count them too)
         if isinstance(guidance, np.ndarray):
             assert guidance.ndim == 3 and guidance.dtype == np.uint8
@@ -171,6 +180,51 @@ class CanvasJob:
         self.tiles_yx = self.crops_yx + m                                # meta: (y + m, x + m)  (brush.py:365-373)
         self.d_tiles_yx = self.d_crops + m
 
+    def _init_row_window(self, guidance, stitching_mode, crop_rows):
+        if stitching_mode != 'all':
+            raise RuntimeError("CanvasJob: a crop-row window needs the dense grid (stitching_mode='all')")
+        dev, m = self.engine.device, self.crop_margin
+        assert guidance.ndim == 3
+        H0, W0 = int(guidance.shape[0]), int(guidance.shape[1])
+        self.orig_shape = (H0, W0)
+        nrows, ncols, rwidth, ph, pw = crop_grid(H0 + m, W0 + m, self.patch, m * 2)
+        r0, r1 = int(crop_rows[0]), int(crop_rows[1])
+        assert 0 <= r0 <= r1 <= nrows
+        self.canvas_h, self.canvas_w = ph, pw
+        self.tile = self.patch - 2 * m
+        # padded-canvas rows [g0, g1) are what the crops of rows [r0, r1) read; padded row Y is guidance row Y - m
+        g0 = r0 * rwidth
+        g1 = max(g0, (r1 - 1) * rwidth + self.patch) if r1 > r0 else g0
+        self.geom_row0 = g0
+        self.d_geom = torch.full((max(g1 - g0, 1), pw), 255, dtype=torch.uint8, device=dev)
+        s0, s1 = max(0, g0 - m), min(H0, g1 - m)
+        if s1 > s0:
+            if isinstance(guidance, np.ndarray):
+                assert guidance.dtype == np.uint8
+                # pinned staging: the slice is a few MB, the copy is asynchronous and at full PCIe rate
+                host = torch.empty((s1 - s0, W0), dtype=torch.uint8, pin_memory=True)
+                host.numpy()[...] = guidance[s0:s1, :, -1]
+                src = host.to(dev, non_blocking=True)
+            else:
+                assert guidance.dtype == torch.uint8
+                src = guidance[s0:s1, :, -1].to(dev)
+            self.d_geom[s0 + m - g0:s1 + m - g0, m:m + W0] = src
+        gy = torch.arange(r0, r1, dtype=torch.int32, device=dev) * rwidth
+        gx = torch.arange(ncols, dtype=torch.int32, device=dev) * rwidth
+        n_r = r1 - r0
+        d_yx = torch.stack([gy[:, None].expand(n_r, ncols), gx[None, :].expand(n_r, ncols)], dim=2).reshape(-1, 2).contiguous()
+        ys, xs = np.meshgrid(np.arange(r0, r1) * rwidth, np.arange(ncols) * rwidth, indexing='ij')
+        self.crops_yx = np.stack([ys.ravel(), xs.ravel()], axis=1).astype(np.int32).reshape(-1, 2)
+        self._crops = None
+        self.d_crops = d_yx
+        self.tiles_yx = self.crops_yx + m
+        self.d_tiles_yx = self.d_crops + m
+        # canvas rows owned by these crop rows under last-writer-wins (closed form): [r0*rw + m, r1*rw + m), the
+        # first band starts at row 0 (rows < m are never written), the last one runs to the end of the canvas
+        lo = r0 * rwidth + m if r0 > 0 else 0
+        hi = r1 * rwidth + m if r1 < nrows else ph
+        self.band = (lo, max(lo, hi))
+
     @property
     def crops(self) -> List[Tuple[int, int, int, int]]:
         """The reference's crop list [(y, x, h, w), ...] (style_transfer.py:33-48); built on first use."""
@@ -186,10 +240,31 @@ class CanvasJob:
     def gather(self, start: int, end: int) -> torch.Tensor:
         n = end - start
         out = torch.empty((n, 1, self.patch, self.patch), dtype=torch.float32, device=self.engine.device)
+        crops = self.d_crops[start:end]
+        if self.geom_row0:
+            crops = crops - torch.tensor([self.geom_row0, 0], dtype=torch.int32, device=crops.device)
         with torch.cuda.device(self.engine.device):
-            _lib.call('nbe_gather_geom_patches', _lib.ptr(self.d_geom), self.canvas_h, self.canvas_w,
-                      _lib.ptr(self.d_crops[start:end]), _lib.ptr(out), n, self.patch, _lib.stream())
+            _lib.call('nbe_gather_geom_patches', _lib.ptr(self.d_geom), int(self.d_geom.shape[0]), self.canvas_w,
+                      _lib.ptr(crops.contiguous()), _lib.ptr(out), n, self.patch, _lib.stream())
         return out
+
+    def place_band(self, band: torch.Tensor, tiles: torch.Tensor):
+        """Place this job's tiles into ``band`` = canvas rows [band[0], band[1]) (a [rows, canvas_w, 4] uint8 tensor, e.g. a
+        slice of the final canvas): ownership among the job's own tiles, clipped to the band -- exact in 'all' mode, where no
+        other job's tile owns a pixel of these rows."""
+        lo, hi = self.band
+        rows = hi - lo
+        n = len(self.crops_yx)
+        if rows <= 0 or n == 0:
+            return
+        dev = self.engine.device
+        yx = (self.d_tiles_yx - torch.tensor([lo, 0], dtype=torch.int32, device=dev)).contiguous()
+        owner = torch.empty((rows, self.canvas_w), dtype=torch.int32, device=dev)
+        order = torch.arange(n, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call('nbe_tile_owner_map', _lib.ptr(yx), n, self.tile, _lib.ptr(owner), rows, self.canvas_w, _lib.stream())
+            _lib.call('nbe_place_tiles', _lib.ptr(tiles), _lib.ptr(yx), _lib.ptr(order), n, self.tile, _lib.ptr(owner), _lib.ptr(band),
+                      rows, self.canvas_w, _lib.stream())
 
     def gather_indices(self, d_idx: torch.Tensor) -> torch.Tensor:
         """``gather`` for an arbitrary list of crop indices (int64 tensor on the device)."""
@@ -243,23 +318,100 @@ def _batch_opts(base: GanBrushOptions, z_per_patch: Optional[torch.Tensor], star
     return o
 
 
+def row_shards(nrows: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous crop-ROW ranges [r0, r1) per rank, as even as possible, earlier ranks take the extra rows
+    (47 rows / 8 -> 6,6,6,6,6,6,6,5) -- the row view of ``shard_bounds`` for the dense grid."""
+    base, extra = divmod(nrows, world_size)
+    out = []
+    for rank in range(world_size):
+        r0 = rank * base + min(rank, extra)
+        out.append((min(r0, nrows), min(r0 + base + (1 if rank < extra else 0), nrows)))
+    return out
+
+
+def exchange_bands(canvas: Optional[torch.Tensor], band: Optional[torch.Tensor], bands: Sequence[Tuple[int, int]], rank: int,
+                   group=None) -> None:
+    """The one inter-GPU step of a sharded canvas: every rank > 0 sends the canvas rows it owns (``band``, rows
+    ``bands[rank]``) to rank 0, which receives each one straight into ``canvas[lo:hi]`` -- disjoint, contiguous row ranges,
+    so there is no staging buffer and no placement pass on rank 0.  Device-agnostic (NCCL over NVLink on GPUs, gloo in the
+    CPU tests); all transfers are posted as one batch."""
+    import torch.distributed as dist
+    ops = []
+    if rank == 0:
+        for r, (lo, hi) in enumerate(bands):
+            if r != 0 and hi > lo:
+                ops.append(dist.P2POp(dist.irecv, canvas[lo:hi], r, group))
+    else:
+        lo, hi = bands[rank]
+        if hi > lo:
+            ops.append(dist.P2POp(dist.isend, band, 0, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def gather_tiles(tiles_local: torch.Tensor, world: int, rank: int, group=None):
+    """Sparse stitching modes: one gather of every rank's (equal-length, padded) tile buffer to rank 0 -> list of ``world``
+    tensors on rank 0, None elsewhere.  Device-agnostic."""
+    import torch.distributed as dist
+    gathered = None
+    if rank == 0:
+        big = torch.empty((world,) + tuple(tiles_local.shape), dtype=tiles_local.dtype, device=tiles_local.device)
+        gathered = list(big.unbind(0))
+    dist.gather(tiles_local, gathered, dst=0, group=group)
+    return gathered
+
+
+def _render_job_tiles(engine, job, opts, z_per_patch, z_offset, batch_size, crop_margin, out=None):
+    """All crops of ``job`` through encoder -> generator -> composite in even batches -> uint8 tiles [n, T, T, 4]."""
+    n = len(job.crops_yx)
+    tiles_all = out if out is not None else torch.empty((n, job.tile, job.tile, 4), dtype=torch.uint8, device=engine.device)
+    if n == 0:
+        return tiles_all
+    # even batches: a short tail batch costs almost a full launch sequence (276 patches -> 1 x 276, not 256 + 20)
+    n_batches = max(1, -(-n // batch_size))
+    if n <= batch_size * 5 // 4:
+        n_batches = 1
+    bs = max(1, -(-n // n_batches))
+    for b0 in range(0, n, bs):
+        b1 = min(b0 + bs, n)
+        geom = job.gather(b0, b1)
+        pos = job.d_crops[b0:b1].to(torch.int64)
+        tiles, _ = engine.render_tiles(geom, _batch_opts(opts, z_per_patch, z_offset + b0, z_offset + b1, pos), crop_margin=crop_margin)
+        tiles_all[b0:b1] = tiles
+    return tiles_all
+
+
 def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOptions, crop_margin: int = 10,
             stitching_mode: str = 'all', feature_blending_level: int = 0, batch_size: int = 256, on_white: bool = False,
             z_per_patch: Optional[torch.Tensor] = None, group=None, return_job: bool = False, to_host: bool = True,
-            distributed: bool = True):
+            distributed: bool = True, timings: Optional[dict] = None):
     """Stylize a whole guidance drawing.  guidance: [H,W,C] uint8 (last channel, 0 = stroke), host array or CUDA tensor;
     ``to_host=False`` returns the finished canvas as a CUDA tensor (device-resident in and out).
 
     With an initialised ``torch.distributed`` process group (one process per GPU) the crop rows are sharded across
     ranks and rank 0 returns the finished canvas (other ranks return None).  ``z_per_patch`` ([n_crops, z_dim])
     gives every patch its own style (style interpolation across the canvas, BASELINE config 5).
-    ``distributed=False`` ignores the process group: this rank renders the whole canvas by itself."""
+    ``distributed=False`` ignores the process group: this rank renders the whole canvas by itself.
+    ``timings``: a dict that receives per-phase milliseconds (setup / render / place / exchange / finish); filling it
+    synchronises the device between phases, so pass it on profiling runs only."""
+    import time
     import torch.distributed as dist
     world, rank = 1, 0
     if distributed and dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-    job = CanvasJob(engine, guidance, crop_margin, stitching_mode)
+    dev = engine.device
+    t_last = [time.perf_counter()]
+
+    def mark(name):
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + (now - t_last[0]) * 1e3
+            t_last[0] = now
+
     if feature_blending_level > 0:
+        job = CanvasJob(engine, guidance, crop_margin, stitching_mode)
         if world > 1:
             raise RuntimeError('stylize: feature blending makes patches raster-dependent; one canvas runs on one GPU '
                                '(pass distributed=False and give every rank its own canvas)')
@@ -267,42 +419,81 @@ def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOption
         canvas = blend(engine, job, opts, feature_blending_level, z_per_patch)
         out = job.finish(canvas, on_white, to_host)
         return (out, job) if return_job else out
+
+    if world > 1 and stitching_mode == 'all':
+        # ---- dense grid on several GPUs: every rank owns a band of canvas rows (closed-form ownership), renders and places
+        #      its own tiles there, and the bands travel to rank 0 in ONE batched send/recv straight into the final canvas
+        m = int(crop_margin)
+        H0, W0 = int(guidance.shape[0]), int(guidance.shape[1])
+        nrows, ncols, rwidth, ph, pw = crop_grid(H0 + m, W0 + m, engine.patch_width, m * 2)
+        shards = row_shards(nrows, world)
+        r0, r1 = shards[rank]
+        job = CanvasJob(engine, guidance, crop_margin, 'all', crop_rows=(r0, r1))
+        bands = []
+        for (a, b) in shards:
+            lo = a * rwidth + m if a > 0 else 0
+            hi = b * rwidth + m if b < nrows else ph
+            bands.append((lo, max(lo, hi)))
+        mark('setup')
+        tiles_local = _render_job_tiles(engine, job, opts, z_per_patch, r0 * ncols, batch_size, crop_margin)
+        mark('render')
+        lo, hi = bands[rank]
+        if rank == 0:
+            canvas = torch.empty((ph, pw, 4), dtype=torch.uint8, device=dev)   # other ranks' rows are overwritten by the receive
+            band = canvas[lo:hi]
+        else:
+            canvas = None
+            band = torch.empty((hi - lo, pw, 4), dtype=torch.uint8, device=dev)
+        band.zero_()
+        job.place_band(band, tiles_local)
+        mark('place')
+        exchange_bands(canvas, band, bands, rank, group)
+        mark('exchange')
+        if rank != 0:
+            return (None, job) if return_job else None
+        out = job.finish(canvas, on_white, to_host)
+        mark('finish')
+        return (out, job) if return_job else out
+
+    job = CanvasJob(engine, guidance, crop_margin, stitching_mode)
     bounds = shard_bounds(job.crops_yx, world)
     start, end = bounds[rank]
-    dev = engine.device
     max_n = max(e - s for s, e in bounds)
+    mark('setup')
     # every rank's tile buffer has the same (maximum) length so that it can be gathered as it is
     tiles_local = torch.empty((max_n, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
-    # even batches: a short tail batch costs almost a full launch sequence (276 patches -> 1 x 276, not 256 + 20)
     n_batches = max(1, -(-(end - start) // batch_size))
     if (end - start) <= batch_size * 5 // 4:
         n_batches = 1
-    batch_size = max(1, -(-(end - start) // n_batches))
-    for b0 in range(start, end, batch_size):
-        b1 = min(b0 + batch_size, end)
+    bs = max(1, -(-(end - start) // n_batches))
+    for b0 in range(start, end, bs):
+        b1 = min(b0 + bs, end)
         geom = job.gather(b0, b1)
         pos = job.d_crops[b0:b1].to(torch.int64)
         tiles, _ = engine.render_tiles(geom, _batch_opts(opts, z_per_patch, b0, b1, pos), crop_margin=crop_margin)
         tiles_local[b0 - start:b1 - start] = tiles
+    mark('render')
     if world == 1:
         canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
         job.place(canvas, job.owner_map(), tiles_local, start, end)
+        mark('place')
         out = job.finish(canvas, on_white, to_host)
+        mark('finish')
         return (out, job) if return_job else out
-    # ---- multi-GPU: one gather of finished tiles to rank 0 (NCCL over NVLink; gloo in CPU tests is not used here) ----
-    gathered = None
-    if rank == 0:
-        big = torch.empty((world, max_n, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
-        gathered = list(big.unbind(0))
-    dist.gather(tiles_local, gathered, dst=0, group=group)
+    # ---- sparse crop lists on several GPUs: ownership is not a closed form, so finished tiles are gathered to rank 0
+    #      (NCCL over NVLink) and placed there under the global ownership map
+    gathered = gather_tiles(tiles_local, world, rank, group)
+    mark('exchange')
     if rank != 0:
         return (None, job) if return_job else None
     canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
     owner = job.owner_map()
-    for r, (s, e) in enumerate(bounds):
-        if e > s:
-            job.place(canvas, owner, gathered[r], s, e)                 # only the first e - s tiles of the buffer are read
+    for r, (s_, e_) in enumerate(bounds):
+        if e_ > s_:
+            job.place(canvas, owner, gathered[r], s_, e_)               # only the first e - s tiles of the buffer are read
+    mark('place')
     out = job.finish(canvas, on_white, to_host)
+    mark('finish')
     return (out, job) if return_job else out
 
 

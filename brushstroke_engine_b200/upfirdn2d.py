@@ -81,6 +81,7 @@ def _launch(x, f2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, ga
     return y
 
 
+@_lib.profiled('upfirdn2d')
 def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda'):
     """Pad, upsample, FIR filter and downsample a batch of 2D images (upfirdn2d.py:120-164)."""
     assert isinstance(x, torch.Tensor)

@@ -206,6 +206,7 @@ int nbe_conv3x3s2_flat_bf16(const void* xp, const void* wq, void* y,
  * = F.conv_transpose2d(x, w, stride=2) of the up-sampling path SG2/torch_utils/ops/conv2d_resample.py:124-138
  * (wq prepared with flip = 0).  x: [N, H, x_pitch >= W+1, x_cs] with zero gap columns (already modulated).
  * The four output parity classes are four TMEM accumulators of one pass over x. */
+/* Cout: a multiple of 128 (one pass per 128 output channels). */
 int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_out,
                              int N, int H, int W, int Cin, int x_cs, int x_pitch, int Cout, int t_cs,
                              int64_t t_row_pitch, int64_t t_img_pitch, const float* dcoef, nbe_stream_t stream);
@@ -241,6 +242,32 @@ int nbe_conv_tc_bf16_torgb(const void* x, const void* wq, void* y,
 int nbe_torgb_triad(const void* x, int x_is_bf16, int x_cs, const float* w, const float* styles, const float* bias,
                     const float* colors, float clamp, float* img, float* uvs, int N, int C, int H, int W,
                     nbe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * modulated_conv2d behind the reference's operator signature -- ONE call, NCHW in, NCHW out, dtype of x.
+ * Replaces: modulated_conv2d(x, weight, styles, noise, up, down=1, padding, resample_filter, demodulate, flip_weight,
+ *           fused_modconv) SG2/training/networks.py:31-88 (both of its formulations; they agree to ~1e-6) and, with
+ *           styles = NULL / demodulate = 0, conv2d_resample(x, w, f, up, padding, flip_weight)
+ *           SG2/torch_utils/ops/conv2d_resample.py:59-154 (cuDNN call sites conv2d_gradfix.py:38,43).
+ *   y[n,o] = d[n,o] * conv2d_resample(x[n] * styles[n,:], weight, f, up, padding, flip_weight)[o] + noise[n]
+ *   d[n,o] = rsqrt(sum_{i,k} (weight[o,i,k] * styles[n,i])^2 + 1e-8) if demodulate else 1
+ * x: [N,Cin,H,W] dense NCHW of `dtype`; weight [Cout,Cin,K,K], styles [N,Cin] (NULL = ones), resample_filter (4x4, needed
+ * for up = 2) float32; noise float32 or NULL, element (n,oy,ox) at noise[n*noise_sn + oy*OW + ox] (noise_sn = 0 broadcasts
+ * one map); y: [N,Cout,OH,OW] of `dtype`, OH = H + 2*padding - K + 1 (up = 1) or 2H + 2*padding - 2 (up = 2, K = 3).
+ * flip_weight != 0 = correlation (F.conv2d), 0 = true convolution (what the up-sampling SynthesisLayers pass).
+ * dtype NBE_BF16 / NBE_F16 with K = 3, Cout % 128 == 0, padding 1 (or 0 for up = 1): tensor cores -- pack to zero-gapped
+ *   NHWC bf16 with the modulation applied, nbe_conv3x3_flat_bf16 (up = 1) or nbe_convT3x3s2_flat_bf16 +
+ *   nbe_fir_act_nhwc_bf16 (up = 2, the transposed conv at 9 taps per input pixel), unpack; fp32 accumulation.
+ * dtype NBE_F32: true-FP32 direct convolution (nbe_conv2d_f32; up = 2 FIR-first through nbe_upfirdn2d).
+ * Other 16-bit shapes return NBE_EUNSUPPORTED (the caller converts to float32).
+ * workspace: caller-owned, 256-byte aligned, at least nbe_modulated_conv2d_workspace(...) bytes (that function returns
+ * -1 for an unsupported combination); nothing in it needs to be initialised or kept between calls. */
+int64_t nbe_modulated_conv2d_workspace(int dtype, int N, int Cin, int H, int W, int Cout, int K, int up, int padding);
+int nbe_modulated_conv2d(const void* x, int dtype, const float* weight, const float* styles,
+                         const float* noise, int64_t noise_sn, void* y,
+                         int N, int Cin, int H, int W, int Cout, int K, int up, int padding,
+                         const float* resample_filter, int demodulate, int flip_weight,
+                         void* workspace, int64_t workspace_bytes, nbe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Geometry encoder, tensor-core path (forger/experimental/autoenc/simple_autoencoder.py:95-126,155-199,251-261).

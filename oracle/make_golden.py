@@ -172,6 +172,54 @@ def golden_ops(out):
     save(out, 'modconv', **arrays)
 
 
+MODCONV_TC_CASES = {
+    # name: (N, Cin, Cout, H, W, up, demodulate, noise?)   -- shapes the tensor-core kernels take (Cout % 128 == 0, 3x3)
+    'c144_up1': (2, 144, 128, 8, 8, 1, True, True),
+    'c128_up2': (2, 128, 128, 8, 8, 2, True, True),
+    'c384_up2': (1, 384, 128, 5, 6, 2, True, True),
+    'c64_o256_up1': (2, 64, 256, 6, 9, 1, True, False),
+    'c128_up2_nodemod': (1, 128, 128, 4, 4, 2, False, True),
+    'c16_o256_up2': (2, 16, 256, 7, 5, 2, True, False),
+}
+
+
+def modconv_tc_inputs(name):
+    """Inputs of one MODCONV_TC_CASES entry from numpy's legacy MT19937 stream (stable across versions and machines), so the
+    fixture only has to store the reference's outputs."""
+    import zlib
+    N, cin, cout, H, W, up, demod, has_noise = MODCONV_TC_CASES[name]
+    rs = np.random.RandomState(zlib.crc32(name.encode()) % (2 ** 31))
+    x = torch.from_numpy(rs.randn(N, cin, H, W).astype(np.float32))
+    w = torch.from_numpy((rs.randn(cout, cin, 3, 3) / np.sqrt(cin * 9)).astype(np.float32))
+    s = torch.from_numpy((rs.randn(N, cin) * 0.5 + 1).astype(np.float32))
+    n = torch.from_numpy((rs.randn(N, 1, H * up, W * up) * 0.1).astype(np.float32)) if has_noise else None
+    return x, w, s, n
+
+
+def golden_modconv_tc(out):
+    """modulated_conv2d / conv2d_resample of the UNMODIFIED reference (CPU, float32) at tensor-core shapes: the
+    reference values for the bf16 / fp16 operator-surface path (tests/test_ops_gpu.py::test_modconv_tensor_core_golden)."""
+    import training.networks as rnet
+    import torch_utils.ops.conv2d_resample as rcr
+    f4 = O.setup_filter([1, 3, 3, 1])
+    arrays, worst = {}, 0.0
+    for name, (N, cin, cout, H, W, up, demod, has_noise) in MODCONV_TC_CASES.items():
+        x, w, s, n = modconv_tc_inputs(name)
+        fw = up == 1                                                     # SynthesisLayer: flip_weight = (up == 1), networks.py:384
+        y = rnet.modulated_conv2d(x, w, s, noise=n, up=up, padding=1, resample_filter=f4, demodulate=demod, flip_weight=fw)
+        arrays[f'{name}_mod'] = y
+        worst = max(worst, maxdiff(y, O.modulated_conv2d(x, w, s, noise=n, up=up, padding=1, resample_filter=f4,
+                                                         demodulate=demod, flip_weight=fw)))
+        # the signature's default flip_weight=True on an up-sampling layer (transposed conv with flipped taps), and plain conv2d_resample
+        if name in ('c128_up2', 'c64_o256_up1'):
+            arrays[f'{name}_mod_flip'] = rnet.modulated_conv2d(x, w, s, noise=n, up=up, padding=1, resample_filter=f4,
+                                                               demodulate=demod, flip_weight=not fw)
+            arrays[f'{name}_conv'] = rcr.conv2d_resample(x, w, f=(f4 if up > 1 else None), up=up, padding=1, flip_weight=fw)
+    print(f'modulated_conv2d (tensor-core shapes): oracle vs reference max diff {worst:.3e}')
+    assert worst < 5e-5
+    save(out, 'modconv_tc', **arrays)
+
+
 def golden_generator(out, G, enc, gp, ep, cfg, ecfg):
     z = torch.cat([P.style_z_from_seed(594), P.style_z_from_seed(7)])
     geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=3, radius=8),
@@ -349,10 +397,13 @@ def golden_canvas(out, ep, ecfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(REPO, 'tests', 'golden'))
+    ap.add_argument('--only', default=None, help="write one fixture only: 'modconv_tc'")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.set_grad_enabled(False)
     bootstrap_reference()
+    if args.only == 'modconv_tc':
+        return golden_modconv_tc(args.out)
     cfg, ecfg = P.GeneratorConfig(), P.EncoderConfig()
     gp = P.init_generator_params(cfg, seed=0, perturb=0.1)
     ep = P.init_encoder_params(ecfg, seed=1, perturb_bn=0.1)
@@ -361,6 +412,7 @@ def main():
     golden_generator(args.out, G, enc, gp, ep, cfg, ecfg)
     golden_engine(args.out, G, enc, enc_args, gp, ep, cfg, ecfg)
     golden_canvas(args.out, ep, ecfg)
+    golden_modconv_tc(args.out)
 
 
 if __name__ == '__main__':

@@ -163,6 +163,51 @@ def test_modconv_golden():
             assert md(y, g[f'{name}_mod_d{int(demod)}']) < 5e-5, (name, demod)
 
 
+@pytest.mark.parametrize('dtype,rel', [(torch.bfloat16, 2e-2), (torch.float16, 2e-2), (torch.float32, 2e-5)])
+def test_modconv_tensor_core_golden(dtype, rel):
+    """The operator-surface modulated_conv2d / conv2d_resample at tensor-core shapes (3x3, Cout % 128 == 0) against the
+    unmodified reference's float32 output (tests/golden/modconv_tc.npz): bf16 / fp16 activations run pack -> tcgen05 flat
+    kernels (+ FIR pass for up = 2) -> unpack through nbe_modulated_conv2d, within 2e-2 of the output's max-abs (bf16
+    operands, fp32 accumulation, bf16 result); float32 activations run the true-FP32 kernel through the same entry."""
+    from oracle.make_golden import MODCONV_TC_CASES, modconv_tc_inputs
+    from brushstroke_engine_b200.conv2d_resample import conv2d_resample
+    from brushstroke_engine_b200.modconv import modulated_conv2d
+    from brushstroke_engine_b200 import _lib
+    g = load_golden('modconv_tc')
+    f4 = O.setup_filter([1, 3, 3, 1]).to(DEV)
+    for name, (N, cin, cout, H, W, up, demod, has_noise) in MODCONV_TC_CASES.items():
+        x, w, s, n = modconv_tc_inputs(name)
+        xd = x.to(DEV).to(dtype)
+        nd = None if n is None else n.to(DEV)
+        ref = t(g[f'{name}_mod'])
+        scale = float(ref.abs().max())
+        n0 = _lib.launch_count()
+        y = modulated_conv2d(xd, w.to(DEV), s.to(DEV), noise=nd, up=up, padding=1, resample_filter=f4, demodulate=demod,
+                             flip_weight=(up == 1))
+        assert y.dtype == dtype and tuple(y.shape) == tuple(ref.shape), name
+        assert md(y, ref) < rel * scale, (name, md(y, ref), scale)
+        assert _lib.launch_count() > n0
+        if f'{name}_mod_flip' in g:
+            y = modulated_conv2d(xd, w.to(DEV), s.to(DEV), noise=nd, up=up, padding=1, resample_filter=f4, demodulate=demod,
+                                 flip_weight=(up != 1))
+            ref = t(g[f'{name}_mod_flip'])
+            assert md(y, ref) < rel * float(ref.abs().max()), (name, 'flip')
+            y = conv2d_resample(xd, w.to(DEV).to(dtype), f=(f4 if up > 1 else None), up=up, padding=1, flip_weight=(up == 1))
+            ref = t(g[f'{name}_conv'])
+            assert y.dtype == dtype and md(y, ref) < rel * float(ref.abs().max()), (name, 'conv')
+
+
+def test_modconv_16bit_takes_the_tensor_core_kernels():
+    """bf16 activations at a tensor-core shape must launch conv_tc_flat_kernel (not the FP32 SIMT kernel): checked through
+    the entry point's own refusal of the shapes it cannot take and the workspace it asks for."""
+    from brushstroke_engine_b200 import _lib
+    L = _lib.load()
+    assert L.nbe_modulated_conv2d_workspace(_lib.BF16, 2, 144, 8, 8, 128, 3, 1, 1) > 0
+    assert L.nbe_modulated_conv2d_workspace(_lib.BF16, 2, 128, 8, 8, 3, 1, 1, 0) < 0          # ToRGB 1x1: float32 kernel
+    assert L.nbe_modulated_conv2d_workspace(_lib.F32, 2, 128, 8, 8, 3, 1, 1, 0) > 0
+    assert L.nbe_modulated_conv2d_workspace(_lib.BF16, 2, 128, 8, 8, 96, 3, 1, 1) < 0
+
+
 @pytest.mark.parametrize('cin,cout,H,K,stride,groups', [(128, 128, 16, 3, 1, 1), (144, 128, 8, 3, 1, 1), (5, 70, 37, 3, 1, 1),
                                                          (64, 128, 16, 3, 2, 1), (1, 64, 20, 7, 1, 1), (128, 3, 16, 1, 1, 1),
                                                          (8, 12, 9, 3, 1, 4), (6, 6, 11, 5, 2, 1)])

@@ -146,3 +146,19 @@ def test_canvas_colour_format(bundles):
         assert md(rgba[:, :, ::2, ::2], g[f'rgba_{mode}_sub']) < 1e-4, mode
     with pytest.raises(RuntimeError):
         P.GeneratorConfig(color_format='bogus').torgb_out_channels
+
+
+def test_modconv_tensor_core_shapes():
+    """The oracle at the tensor-core shapes of tests/golden/modconv_tc.npz (inputs regenerated from numpy's MT19937 stream)."""
+    from oracle.make_golden import MODCONV_TC_CASES, modconv_tc_inputs
+    g = load_golden('modconv_tc')
+    f4 = O.setup_filter([1, 3, 3, 1])
+    for name, (N, cin, cout, H, W, up, demod, has_noise) in MODCONV_TC_CASES.items():
+        x, w, s, n = modconv_tc_inputs(name)
+        y = O.modulated_conv2d(x, w, s, noise=n, up=up, padding=1, resample_filter=f4, demodulate=demod, flip_weight=(up == 1))
+        assert md(y, g[f'{name}_mod']) < 5e-5, name
+        if f'{name}_conv' in g:
+            y = O.conv2d_resample(x, w, f=(f4 if up > 1 else None), up=up, padding=1, flip_weight=(up == 1))
+            assert md(y, g[f'{name}_conv']) < 5e-5, name
+            y = O.modulated_conv2d(x, w, s, noise=n, up=up, padding=1, resample_filter=f4, demodulate=demod, flip_weight=(up != 1))
+            assert md(y, g[f'{name}_mod_flip']) < 5e-5, name

@@ -1,0 +1,163 @@
+"""GPU: the branches round 1 left without a test -- truncation_psi / truncation_cutoff, encoder preproc_type, the
+``attach_fast_path`` / ``engine_from_reference`` hooks (through a stand-in reference engine), the band-sharded canvas against
+the single-GPU canvas, and (with >= 2 devices) the NCCL exchange under torchrun."""
+import dataclasses
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO, load_golden, t
+from oracle import neube_oracle as O
+from brushstroke_engine_b200 import params as P, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def md(a, b):
+    return float((torch.as_tensor(a).detach().cpu().double() - torch.as_tensor(b).detach().cpu().double()).abs().max())
+
+
+@pytest.mark.parametrize('psi,cutoff', [(0.7, None), (0.5, 8), (1.3, 3)])
+def test_truncation_psi_and_cutoff(bundles, psi, cutoff):
+    """MappingNetwork truncation (networks.py:283-289): ws = w_avg.lerp(ws, psi), optionally on the first `cutoff` layers
+    only -- with a non-zero w_avg (the constructor's zeros would hide a wrong branch)."""
+    from brushstroke_engine_b200.generator import Generator
+    cfg, ecfg, gp, ep = bundles
+    gp = dict(gp)
+    gp['mapping.w_avg'] = torch.randn(cfg.w_dim, generator=torch.Generator().manual_seed(5)) * 0.5
+    G = Generator(gp, cfg, DEV, mode='fp32')
+    z = torch.cat([P.style_z_from_seed(s) for s in (594, 7, 21)])
+    ws = G.mapping(z.to(DEV), None, truncation_psi=psi, truncation_cutoff=cutoff)
+    ref = O.mapping_network(gp, z, cfg.num_ws, cfg.mapping_layers, cfg.mapping_lr_multiplier, truncation_psi=psi, truncation_cutoff=cutoff)
+    assert ws.shape == ref.shape == (3, cfg.num_ws, cfg.w_dim)
+    assert md(ws, ref) < 1e-5
+    # and through the full call: psi changes the image, psi = 1 does not
+    g = load_golden('generator')
+    gf = [x.to(DEV) for x in O.geometry_encode(ep, ecfg, t(g['geom']))]
+    img1 = G(z[:2].to(DEV), None, gf, noise_mode='const', truncation_psi=1)
+    img2 = G(z[:2].to(DEV), None, gf, noise_mode='const', truncation_psi=psi, truncation_cutoff=cutoff)
+    gf_c = O.geometry_encode(ep, ecfg, t(g['geom']))
+    ref2, _ = O.generator_forward(gp, cfg, z[:2], gf_c, ws=ref[:2])
+    assert md(img2, ref2) < 1e-4 and md(img1, img2) > 1e-3
+
+
+@pytest.mark.parametrize('preproc', ['inverse', '-11inverse', 'none'])
+def test_encoder_preproc_types(bundles, preproc):
+    """BaseGeoEncoder preprocessing (base.py:32-58) in both precision modes against the oracle."""
+    from brushstroke_engine_b200.geo_encoder import GeometryEncoder
+    cfg, ecfg, gp, ep = bundles
+    e2 = dataclasses.replace(ecfg, preproc_type=preproc)
+    geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=3), synthetic.synthetic_patch(128, seed=9, radius=5)]))
+    ref = O.geometry_encode(ep, e2, geom)
+    if preproc != 'none':
+        assert md(ref[0], O.geometry_encode(ep, ecfg, geom)[0]) > 1e-3          # the flag matters for these weights
+    got = GeometryEncoder(ep, e2, DEV, mode='fp32').encode(geom.to(DEV))
+    for a, b in zip(got, ref):
+        assert md(a, b) < 5e-5, preproc
+    got = GeometryEncoder(ep, e2, DEV, mode='bf16').encode(geom.to(DEV))
+    for a, b in zip(got, ref):
+        assert md(a, b) < 0.03 * float(b.abs().max()), preproc
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
+def test_attach_fast_path_on_a_reference_shaped_engine(bundles, mode, tol):
+    """``attach_fast_path(engine)`` reads G / encoder through ``state_dict()`` and the module
+    attributes, builds the B200 engine and replaces ``_render_stroke_torch`` -- executed here on a stand-in engine whose
+    modules are laid out like the reference's (tests/standin.py), and compared with the oracle composite."""
+    from standin import standin_engine
+    from brushstroke_engine_b200 import install
+    from brushstroke_engine_b200.engine import GanBrushOptions, TriadPaintEngine
+    cfg, ecfg, gp, ep = bundles
+    ref_engine = standin_engine(cfg, ecfg, gp, ep, DEV, render_mode='full')
+    fast = install.attach_fast_path(ref_engine, mode=mode)
+    assert isinstance(fast, TriadPaintEngine) and ref_engine._nbe_fast is fast and fast.G.cfg == cfg and fast.encoder.cfg == ecfg
+    geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=3), synthetic.synthetic_patch(128, seed=4, radius=3)]))
+    z = torch.cat([P.style_z_from_seed(594), P.style_z_from_seed(7)])
+    pos = torch.tensor([[88, 176], [1144, 264]])
+    gf = O.geometry_encode(ep, ecfg, geom)
+    _, dbg = O.generator_forward(gp, cfg, z, gf, positions=pos)
+    for render_mode in ('full', 'clear'):
+        ref_engine.render_mode = render_mode                         # the hook follows the reference engine's mode
+        opts = GanBrushOptions()
+        opts.set_style(z.to(DEV))
+        opts.position = pos.to(DEV)
+        rgba, raw, dbg_img = ref_engine._render_stroke_torch(geom.to(DEV), None, opts)
+        assert md(rgba, O.triad_composite(dbg['uvs'], dbg['colors'], render_mode)) < tol, render_mode
+        assert set(('uvs', 'colors', 'ws')) <= set(raw.keys()) and dbg_img is None
+    # UVS mapping: the hook takes the reference mapper's factor (it depends on the reference's bundled geometry images)
+    ref_engine.uvs_mapper.get_sfactor = lambda o: torch.tensor(1.7)
+    opts = GanBrushOptions()
+    opts.set_style(z[:1].to(DEV), 'brush-1')
+    opts.enable_uvs_mapping = True
+    rgba, _, _ = ref_engine._render_stroke_torch(geom[:1].to(DEV), None, opts)
+    _, dbg1 = O.generator_forward(gp, cfg, z[:1], [x[:1] for x in gf])
+    assert md(rgba, O.triad_composite(dbg1['uvs'], dbg1['colors'], 'clear', sfactor=torch.tensor(1.7))) < tol
+    eng2 = install.engine_from_reference(ref_engine, mode=mode)
+    assert eng2.render_mode == ref_engine.render_mode
+
+
+def test_band_jobs_reassemble_the_single_gpu_canvas(bundles):
+    """The multi-GPU scheduler's per-rank work -- a row-window CanvasJob (partial guidance upload, global positions), its own
+    tiles placed into the canvas rows it owns -- executed for every 'rank' in turn on ONE device: the concatenated bands must
+    equal the canvas stylize() renders in one piece, bit for bit (the NCCL exchange itself only moves those bands)."""
+    from brushstroke_engine_b200 import stylizer
+    from brushstroke_engine_b200.engine import GanBrushOptions, TriadPaintEngine
+    cfg, ecfg, gp, ep = bundles
+    eng = TriadPaintEngine(gp, ep, DEV, mode='bf16')
+    guidance = synthetic.synthetic_guidance(700, 610, num_lines=24, seed=3)
+    opts = GanBrushOptions()
+    opts.set_style(P.style_z_from_seed(594).to(DEV), '594')
+    m = 10
+    nrows, ncols, rwidth, ph, pw = stylizer.crop_grid(700 + m, 610 + m, 128, 2 * m)
+    zpp = torch.cat([P.style_z_from_seed(i % 5) for i in range(nrows * ncols)]).to(DEV)
+    with torch.no_grad():
+        whole = stylizer.stylize(eng, guidance, opts, crop_margin=m, z_per_patch=zpp, to_host=False, distributed=False)
+        for world in (2, 3, nrows + 2):
+            canvas = torch.full((ph, pw, 4), 99, dtype=torch.uint8, device=DEV)
+            for rank, (r0, r1) in enumerate(stylizer.row_shards(nrows, world)):
+                job = stylizer.CanvasJob(eng, guidance if rank % 2 else torch.from_numpy(guidance).to(DEV), m, 'all', crop_rows=(r0, r1))
+                tiles = stylizer._render_job_tiles(eng, job, opts, zpp, r0 * ncols, 64, m)
+                lo, hi = job.band
+                band = canvas[lo:hi]
+                band.zero_()
+                job.place_band(band, tiles)
+            assert torch.equal(canvas[m:m + 700, m:m + 610], whole), world
+
+
+def test_multi_gpu_canvas_equals_single_gpu_under_torchrun(tmp_path):
+    """2 ranks over NCCL (skipped below 2 devices): stylize() sharded == stylize() on one GPU, dense and sparse grids."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    script = tmp_path / 'mg.py'
+    script.write_text('''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from brushstroke_engine_b200 import params as P, stylizer, synthetic
+from brushstroke_engine_b200.engine import GanBrushOptions, TriadPaintEngine
+rank = int(os.environ['LOCAL_RANK']); torch.cuda.set_device(rank)
+dev = torch.device('cuda', rank)
+dist.init_process_group('nccl', device_id=dev)
+cfg, ecfg = P.GeneratorConfig(), P.EncoderConfig()
+eng = TriadPaintEngine(P.init_generator_params(cfg, 0, 0.1), P.init_encoder_params(ecfg, 1, 0.1), dev, mode='bf16')
+guidance = synthetic.synthetic_guidance(900, 700, num_lines=30, seed=2)
+opts = GanBrushOptions(); opts.set_style(P.style_z_from_seed(594).to(dev), '594')
+ok = True
+with torch.no_grad():
+    for mode in ('all', 'full'):
+        out = stylizer.stylize(eng, guidance, opts, crop_margin=10, stitching_mode=mode, to_host=False)
+        if rank == 0:
+            solo = stylizer.stylize(eng, guidance, opts, crop_margin=10, stitching_mode=mode, to_host=False, distributed=False)
+            ok = ok and bool(torch.equal(out, solo))
+        dist.barrier()
+if rank == 0:
+    open(%r, 'w').write('OK' if ok else 'MISMATCH')
+dist.destroy_process_group()
+''' % (REPO, str(tmp_path / 'result.txt')))
+    subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+                    '--master-port', str(29700 + os.getpid() % 200), str(script)], check=True, timeout=600)
+    assert (tmp_path / 'result.txt').read_text() == 'OK'

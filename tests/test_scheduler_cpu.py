@@ -53,36 +53,78 @@ def test_style_seed_conventions():
 
 
 def _gloo_worker(rank, world, port, tmp):
+    """Runs the scheduler's own exchange functions (stylizer.row_shards / exchange_bands / shard_bounds / gather_tiles -- the
+    ones stylize() calls on NCCL) on gloo with CPU tensors; 'rendered' tiles are fakes whose pixels carry the tile's raster
+    index, placed on the CPU by the oracle's raster loop, so every placement or ownership error is visible."""
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     sys.path.insert(0, REPO)
+    m, T = 10, 108
     guidance = synthetic.synthetic_guidance(300, 260, num_lines=10, seed=5, radii=(1, 3, 9))
-    crops, padded = stylizer.generate_stitching_crops(stylizer.pad_geo(guidance, 10), 128, 'all', 20)
-    T = 108
-    s, e = stylizer.shard_crops(crops, world, rank)
-    # fake "rendered" tiles: every pixel carries its global raster index -> placement errors are visible
-    tiles = torch.stack([torch.full((T, T, 4), i % 251, dtype=torch.uint8) for i in range(s, e)]) if e > s else torch.zeros((0, T, T, 4), dtype=torch.uint8)
-    bounds = [stylizer.shard_crops(crops, world, r) for r in range(world)]
+    crops, padded = stylizer.generate_stitching_crops(stylizer.pad_geo(guidance, m), 128, 'all', 2 * m)
+    ph, pw = padded.shape[:2]
+    metas = [(c[0] + m, c[1] + m) for c in crops]
+    fake = lambda i: np.full((T, T, 4), i % 251, np.uint8)
+    ref = O.place_tiles((ph, pw), [fake(i) for i in range(len(crops))], metas)
+    ok = {}
+    # ---- dense grid: bands of owned canvas rows, one batched send/recv into the final canvas
+    nrows, ncols, rwidth, ph2, pw2 = stylizer.crop_grid(300 + m, 260 + m, 128, 2 * m)
+    assert (ph2, pw2) == (ph, pw) and nrows * ncols == len(crops)
+    shards = stylizer.row_shards(nrows, world)
+    bands = []
+    for (a, b) in shards:
+        lo = a * rwidth + m if a > 0 else 0
+        hi = b * rwidth + m if b < nrows else ph
+        bands.append((lo, max(lo, hi)))
+    assert bands[0][0] == 0 and bands[-1][1] == ph and all(x[1] == y[0] for x, y in zip(bands[:-1], bands[1:]))
+    r0, r1 = shards[rank]
+    mine = list(range(r0 * ncols, r1 * ncols))
+    own = O.place_tiles((ph, pw), [fake(i) for i in mine], [metas[i] for i in mine])     # this rank's tiles only
+    lo, hi = bands[rank]
+    canvas = torch.full((ph, pw, 4), 77, dtype=torch.uint8) if rank == 0 else None
+    if rank == 0:
+        canvas[lo:hi] = torch.from_numpy(own[lo:hi])
+        band = canvas[lo:hi]
+    else:
+        band = torch.from_numpy(np.ascontiguousarray(own[lo:hi]))
+    stylizer.exchange_bands(canvas, band, bands, rank)
+    if rank == 0:
+        ok['bands'] = bool(np.array_equal(canvas.numpy(), ref))
+    # ---- sparse lists: padded tile buffers gathered to rank 0, placed under global raster order
+    yx = np.array([(c[0], c[1]) for c in crops], dtype=np.int32)
+    bounds = stylizer.shard_bounds(yx, world)
+    assert bounds == [stylizer.shard_crops(crops, world, r) for r in range(world)]
+    s, e = bounds[rank]
     max_n = max(b - a for a, b in bounds)
     padded_t = torch.zeros((max_n, T, T, 4), dtype=torch.uint8)
-    padded_t[: e - s] = tiles
-    gathered = [torch.empty_like(padded_t) for _ in range(world)] if rank == 0 else None
-    dist.gather(padded_t, gathered, dst=0)
+    for k, i in enumerate(range(s, e)):
+        padded_t[k] = torch.from_numpy(fake(i))
+    gathered = stylizer.gather_tiles(padded_t, world, rank)
     if rank == 0:
         all_tiles = torch.cat([gathered[r][: b - a] for r, (a, b) in enumerate(bounds)]).numpy()
-        metas = [(c[0] + 10, c[1] + 10) for c in crops]
-        canvas = O.place_tiles(padded.shape[:2], list(all_tiles), metas)
-        ref = O.place_tiles(padded.shape[:2], [np.full((T, T, 4), i % 251, np.uint8) for i in range(len(crops))], metas)
-        np.save(os.path.join(tmp, 'ok.npy'), np.array([np.array_equal(canvas, ref)]))
+        ok['tiles'] = bool(np.array_equal(O.place_tiles((ph, pw), list(all_tiles), metas), ref))
+        np.save(os.path.join(tmp, 'ok.npy'), np.array([ok['bands'], ok['tiles']]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_gather_reassembles_canvas(tmp_path):
-    """world_size 2 on gloo: band sharding + tile gather + raster placement reproduce the single-process canvas."""
-    port = 29500 + (os.getpid() % 500)
-    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    assert bool(np.load(os.path.join(str(tmp_path), 'ok.npy'))[0])
+@pytest.mark.parametrize('world', [2, 3])
+def test_multi_rank_exchange_reassembles_canvas(tmp_path, world):
+    """world_size 2 and 3 on gloo: row sharding + band exchange (dense grid) and tile gather (sparse lists) both reproduce
+    the single-process raster-loop canvas bit for bit."""
+    port = 29500 + (os.getpid() % 500) + world
+    mp.spawn(_gloo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = np.load(os.path.join(str(tmp_path), 'ok.npy'))
+    assert bool(res[0]) and bool(res[1])
+
+
+def test_row_shards_match_shard_bounds_on_the_dense_grid():
+    ys, xs = np.meshgrid(np.arange(47) * 88, np.arange(47) * 88, indexing='ij')
+    yx = np.stack([ys.ravel(), xs.ravel()], axis=1).astype(np.int32)
+    for world in (1, 2, 4, 8, 64):
+        rows = stylizer.row_shards(47, world)
+        assert [(a * 47, b * 47) if b > a else (len(yx), len(yx)) for a, b in rows] == \
+            [(s, e) if e > s else (len(yx), len(yx)) for s, e in stylizer.shard_bounds(yx, world)]
 
 
 def test_blending_wavefronts_respect_raster_dependencies():
