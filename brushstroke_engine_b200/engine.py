@@ -225,6 +225,9 @@ class TriadPaintEngine:
         self.uvs_mapper = StyleUVSMapper(self)
         self._side_stream = None
         self._overlap_styles = os.environ.get('NBE_NO_STREAM_OVERLAP') is None
+        self._batch_sessions = {}
+        self._force_overlap = False
+        self.use_batch_graph = os.environ.get('NBE_NO_BATCH_GRAPH') is None      # A/B switch: eager launches for the batch step
 
     def set_render_mode(self, mode):
         if mode not in self.render_modes:
@@ -254,11 +257,12 @@ class TriadPaintEngine:
             # straight into the generator's concatenated, zero-gapped NHWC inputs
             extra = opts.custom_args if opts.style_ws is not None else {}
             positions = opts.get_position(self.device)
-            if self._overlap_styles and B >= 32 and not torch.cuda.is_current_stream_capturing():
+            if self._overlap_styles and (B >= 32 or self._force_overlap or torch.cuda.is_current_stream_capturing()):
                 # mapping network, per-layer styles / demodulation and the shifted noise maps are small latency-bound kernels
                 # that nothing in the encoder needs before its first feature map: they run on a side stream underneath the
                 # encoder's first layers (large batches only: at batch 1 the extra stream bookkeeping costs more host time than
-                # the overlap saves).  (Memory allocated there is only ever re-used by later side-stream work, which
+                # the overlap saves -- unless the step is being captured into a CUDA graph, where the fork / join becomes two
+                # branches of the graph at no host cost).  (Memory allocated there is only ever re-used by later side-stream work, which
                 # starts with wait_stream(main), so it cannot be recycled under a main-stream kernel that still reads it.)
                 with torch.cuda.device(self.device):
                     main = torch.cuda.current_stream()
@@ -335,6 +339,24 @@ class TriadPaintEngine:
         """CUDA-graph session for one-patch-at-a-time rendering with a fixed brush (see ``InteractiveSession``)."""
         return InteractiveSession(self, opts, crop_margin)
 
+    def batch_session(self, B: int, crop_margin: int = 10) -> 'BatchSession':
+        """The CUDA graph of one batch step (encoder -> mapping -> synthesis -> composite -> uint8 tiles) for ``B`` patches
+        styled by z, in the engine's current render mode; built on first use and kept per (B, crop_margin, render_mode)."""
+        key = (int(B), int(crop_margin), self.render_mode)
+        sess = self._batch_sessions.get(key)
+        if sess is None:
+            sess = self._batch_sessions[key] = BatchSession(self, int(B), int(crop_margin))
+            while len(self._batch_sessions) > 4:
+                self._batch_sessions.pop(next(iter(self._batch_sessions)))
+        return sess
+
+    def render_tiles_graph(self, geom: torch.Tensor, z: torch.Tensor, positions: torch.Tensor, crop_margin: int = 10) -> torch.Tensor:
+        """``render_tiles`` for a plain z-styled batch through the batch step's CUDA graph: three small device copies into the
+        graph's input buffers + ONE graph launch instead of ~55 kernel launches issued from Python.  Returns the graph's own
+        output buffer (valid until the next call with the same batch size; clone it to keep it)."""
+        sess = self.batch_session(geom.shape[0], crop_margin)
+        return sess.run(geom, z, positions)
+
     def render_patches_host(self, guidance_patches: torch.Tensor, z: torch.Tensor, positions: torch.Tensor,
                             crop_margin: int = 10, out: Optional[torch.Tensor] = None, wait: bool = True, **generator_kwargs):
         """End-to-end batched entry point with HOST buffers (the stylizer's per-batch work):
@@ -347,17 +369,23 @@ class TriadPaintEngine:
         B, W = guidance_patches.shape[0], self.patch_width
         assert guidance_patches.dtype == torch.uint8 and guidance_patches.shape == (B, W, W)
         dev = self.device
-        d_patches = guidance_patches.to(dev, non_blocking=True)
-        d_z = z.to(dev, non_blocking=True)
-        d_pos = positions.to(dev, non_blocking=True)
-        crops = torch.stack([torch.arange(B, dtype=torch.int32, device=dev) * W, torch.zeros(B, dtype=torch.int32, device=dev)], dim=1).contiguous()
-        geom = torch.empty((B, 1, W, W), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.call('nbe_gather_geom_patches', _lib.ptr(d_patches), B * W, W, _lib.ptr(crops), _lib.ptr(geom), B, W, _lib.stream())
-        opts = GanBrushOptions()
-        opts.set_style(d_z)
-        opts.position = d_pos
-        tiles, _ = self.render_tiles(geom, opts, crop_margin=crop_margin, **generator_kwargs)
+        if self.use_batch_graph and not generator_kwargs and self.G.flat_supported and self.encoder.mode == 'bf16' \
+                and z.dtype == torch.float64 and positions.dtype == torch.int64:
+            # the whole step as one CUDA-graph launch: the host buffers are copied straight into the graph's inputs
+            sess = self.batch_session(B, crop_margin)
+            tiles = sess.run_host(guidance_patches, z, positions).clone()     # the graph's output buffer is re-used by the next step
+        else:
+            d_patches = guidance_patches.to(dev, non_blocking=True)
+            d_z = z.to(dev, non_blocking=True)
+            d_pos = positions.to(dev, non_blocking=True)
+            crops = torch.stack([torch.arange(B, dtype=torch.int32, device=dev) * W, torch.zeros(B, dtype=torch.int32, device=dev)], dim=1).contiguous()
+            geom = torch.empty((B, 1, W, W), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.call('nbe_gather_geom_patches', _lib.ptr(d_patches), B * W, W, _lib.ptr(crops), _lib.ptr(geom), B, W, _lib.stream())
+            opts = GanBrushOptions()
+            opts.set_style(d_z)
+            opts.position = d_pos
+            tiles, _ = self.render_tiles(geom, opts, crop_margin=crop_margin, **generator_kwargs)
         if out is None:
             out = torch.empty(tiles.shape, dtype=torch.uint8, pin_memory=True)
         if wait:
@@ -375,6 +403,99 @@ class TriadPaintEngine:
                 done = torch.cuda.Event()
                 done.record(self._copy_stream)
         return out, done
+
+
+class BatchSession:
+    """One batch step -- geometry [B,1,W,W] + z [B,z_dim] + canvas positions [B,2] -> uint8 RGBA tiles [B,T,T,4] -- captured
+    ONCE into a CUDA graph (mapping / styles / noise as a parallel branch next to the encoder's first layers) and replayed per
+    batch.  The stylizer's batches, ``render_patches_host`` and the benchmark step go through it: the host issues three small
+    copies and one graph launch per batch instead of ~55 kernel launches, which is what bounds eight processes sharing one
+    host (8-GPU end-to-end) and removes the launch gaps between the step's small kernels.  Output bytes are identical to the
+    eager ``render_tiles`` (same kernels, same order).  The session owns the workspaces its kernels point into."""
+
+    def __init__(self, engine: 'TriadPaintEngine', B: int, crop_margin: int, split_last_layer: bool = False):
+        """``split_last_layer``: capture everything up to the last synthesis layer and launch that layer (the dominant kernel:
+        3x3 modconv @128^2 with ToRGB fused) and the composite eagerly after each replay, so that ``engine.G.probe`` can put
+        CUDA events around it inside a timed region (events cannot be timed inside a graph).  Same kernels, same bytes."""
+        self.engine, self.B, self.crop_margin = engine, B, crop_margin
+        self.split = bool(split_last_layer)
+        self._tail = None
+        dev, W = engine.device, engine.patch_width
+        self.render_mode = engine.render_mode
+        self._geom = torch.ones((B, 1, W, W), dtype=torch.float32, device=dev)
+        self._z = torch.zeros((B, engine.G.z_dim), dtype=torch.float64, device=dev)
+        self._pos = torch.zeros((B, 2), dtype=torch.int64, device=dev)
+        self._u8 = torch.full((B, W, W), 255, dtype=torch.uint8, device=dev)           # host-fed variant: uint8 guidance patches
+        self._crops = torch.stack([torch.arange(B, dtype=torch.int32, device=dev) * W, torch.zeros(B, dtype=torch.int32, device=dev)], dim=1).contiguous()
+        self._stream = torch.cuda.Stream(device=dev)
+        with torch.no_grad(), torch.cuda.device(dev):
+            self._stream.wait_stream(torch.cuda.current_stream())
+            engine._force_overlap = True                             # warm up the code path the capture takes (side-stream branch)
+            try:
+                with torch.cuda.stream(self._stream):
+                    for _ in range(2):                              # warm-up: workspaces, cudaFuncSetAttribute, lazy module loads
+                        engine.G._noise_cache = None
+                        self._forward()
+                        if self._tail is not None:
+                            self._tail()
+                self._stream.synchronize()
+                engine.G._noise_cache = None
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._stream):
+                    self._out = self._forward()
+            finally:
+                engine._force_overlap = False
+            engine.G._noise_cache = None
+            self._graph = g
+            self._workspaces = (engine.G._flat_ws.get(B), engine.encoder._ws.get((B, W)))
+            torch.cuda.current_stream().wait_stream(self._stream)
+
+    def _forward(self):
+        eng = self.engine
+        opts = GanBrushOptions()
+        opts.set_style(self._z)
+        opts.position = self._pos
+        if not self.split:
+            tiles, _ = eng.render_tiles(self._geom, opts, crop_margin=self.crop_margin)
+            return tiles
+        G = eng.G
+        G.defer_last_layer, G._deferred_last = True, None
+        try:
+            _, triad = eng._generate(self._geom, opts)
+        finally:
+            G.defer_last_layer = False
+        last = G._deferred_last
+        if last is None:
+            raise RuntimeError('BatchSession(split_last_layer=True) needs the flat tensor-core path of the stock configuration')
+        G._deferred_last = None
+
+        def tail():
+            _, uvs = last()
+            data = dict(triad)
+            data['uvs'] = uvs
+            return eng._composite(data, opts, self.B, want_f32=False, crop_margin=self.crop_margin)[1]
+        self._tail = tail
+        return None
+
+    def run(self, geom: torch.Tensor, z: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+        """Device-resident inputs -> the graph's output buffer (on the caller's current stream)."""
+        self._geom.copy_(geom, non_blocking=True)
+        self._z.copy_(z, non_blocking=True)
+        self._pos.copy_(positions, non_blocking=True)
+        self._graph.replay()
+        return self._tail() if self.split else self._out
+
+    def run_host(self, patches_u8: torch.Tensor, z: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+        """Pinned host inputs (uint8 guidance patches [B,W,W], z float64, positions int64) -> the graph's output buffer."""
+        eng, W = self.engine, self.engine.patch_width
+        self._u8.copy_(patches_u8, non_blocking=True)
+        self._z.copy_(z, non_blocking=True)
+        self._pos.copy_(positions, non_blocking=True)
+        with torch.cuda.device(eng.device):
+            _lib.call('nbe_gather_geom_patches', _lib.ptr(self._u8), self.B * W, W, _lib.ptr(self._crops), _lib.ptr(self._geom), self.B, W,
+                      _lib.stream())
+        self._graph.replay()
+        return self._tail() if self.split else self._out
 
 
 CANVAS_RENDER_MODES = {'clear': 0, 'stroke': 1, 'canvas': 2, 'full': 3}

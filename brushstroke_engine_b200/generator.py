@@ -147,6 +147,8 @@ class Generator:
         self.last_up_fir_first = os.environ.get('NBE_LAST_UP_FIR_FIRST') is not None   # A/B switch: 4x-FLOP FIR-first path at 128^2
         self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
         self.probe = None       # optional {layer_name: [(start_event, end_event), ...]} filled by _conv_tc (bench.py roofline)
+        self.defer_last_layer = False      # flat path: hand the last layer back as a closure instead of launching it (BatchSession)
+        self._deferred_last = None
 
     # ------------------------------------------------------------------------------------------ plan
     def _build(self, p: Bundle) -> None:
@@ -627,19 +629,32 @@ class Generator:
                     torch.cuda.nvtx.range_pop()
                 break
             if res == last:
-                ev = None
-                if self.probe is not None and conv1.name in self.probe:
-                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                    ev[0].record()
-                img = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
-                uvs = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
-                _lib.call('nbe_conv_tc_bf16_torgb', _lib.ptr(x1), _lib.ptr(conv1.wq), None, B, res, res, conv1.cin, conv1.cin,
-                          conv1.cout, conv1.cout, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
-                          _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(self._rgb_w), _lib.ptr(rgb_styles), _lib.ptr(self._rgb_b),
-                          _lib.ptr(colors.contiguous()), clamp, _lib.ptr(img), _lib.ptr(uvs), 0, st)
-                if ev is not None:
-                    ev[1].record()
-                    self.probe[conv1.name].append(ev)
+                colors_c = colors.contiguous()
+
+                def run_last(x1=x1, conv1=conv1, noise=noise, nsn=nsn, ngain=ngain, res=res):
+                    ev = None
+                    if self.probe is not None and conv1.name in self.probe:
+                        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                        ev[0].record()
+                    img = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
+                    uvs = torch.empty((B, 3, res, res), dtype=torch.float32, device=dev)
+                    with torch.cuda.device(dev):
+                        _lib.call('nbe_conv_tc_bf16_torgb', _lib.ptr(x1), _lib.ptr(conv1.wq), None, B, res, res, conv1.cin, conv1.cin,
+                                  conv1.cout, conv1.cout, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
+                                  _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(self._rgb_w), _lib.ptr(rgb_styles), _lib.ptr(self._rgb_b),
+                                  _lib.ptr(colors_c), clamp, _lib.ptr(img), _lib.ptr(uvs), 0, _lib.stream())
+                    if ev is not None:
+                        ev[1].record()
+                        self.probe[conv1.name].append(ev)
+                    return img, uvs
+
+                if self.defer_last_layer:
+                    # a CUDA-graph session that wants CUDA events around the dominant kernel captures everything up to here and
+                    # launches the last layer (conv + fused ToRGB) eagerly after every replay: see engine.BatchSession
+                    self._deferred_last = run_last
+                    img = uvs = None
+                else:
+                    img, uvs = run_last()
                 if nvtx:
                     torch.cuda.nvtx.range_pop()
                 break
