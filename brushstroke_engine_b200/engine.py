@@ -226,6 +226,7 @@ class TriadPaintEngine:
         self._side_stream = None
         self._overlap_styles = os.environ.get('NBE_NO_STREAM_OVERLAP') is None
         self._batch_sessions = {}
+        self._batch_hits = {}
         self._force_overlap = False
         self.use_batch_graph = os.environ.get('NBE_NO_BATCH_GRAPH') is None      # A/B switch: eager launches for the batch step
 
@@ -441,8 +442,10 @@ class BatchSession:
                 self._stream.synchronize()
                 engine.G._noise_cache = None
                 g = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
                 with torch.cuda.graph(g, stream=self._stream):
                     self._out = self._forward()
+                self.kernels_per_replay = _lib.launch_count() - n0   # libnbe_b200 kernels inside the graph (torch's own copies not counted)
             finally:
                 engine._force_overlap = False
             engine.G._noise_cache = None

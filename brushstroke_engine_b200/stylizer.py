@@ -362,6 +362,30 @@ def gather_tiles(tiles_local: torch.Tensor, world: int, rank: int, group=None):
     return gathered
 
 
+def _plain_z_style(opts: GanBrushOptions) -> bool:
+    """A brush the batch step's CUDA graph covers: styled by z, default colours, no UVS remapping, no custom noise."""
+    return opts.style_ws is None and opts.style_z is not None and opts.color0 is None and opts.color1 is None \
+        and opts.canvas_color is None and not opts.enable_uvs_mapping and not opts.custom_args
+
+
+def _render_batch(engine, geom, opts, z_per_patch, z0, z1, pos, crop_margin, repeats):
+    """One batch of a job -> uint8 tiles.  Batches whose size recurs (``repeats`` >= 2 in this job, or the engine has rendered a
+    batch of that size before) replay the batch step's CUDA graph: one launch from the host instead of ~55; a size seen for
+    the first time runs eagerly (capturing a graph costs more than one eager step)."""
+    n = geom.shape[0]
+    key = (n, int(crop_margin), engine.render_mode)
+    hits = engine._batch_hits[key] = engine._batch_hits.get(key, 0) + 1          # how often this engine has seen the batch size
+    if getattr(engine, 'use_batch_graph', False) and _plain_z_style(opts) and engine.G.flat_supported and engine.encoder.mode == 'bf16' \
+            and (repeats >= 2 or hits >= 2 or key in engine._batch_sessions):
+        z = z_per_patch[z0:z1] if z_per_patch is not None else opts.style_z
+        z = z.to(engine.device, torch.float64)
+        if z.shape[0] != n:
+            z = z.expand(n, -1)
+        return engine.render_tiles_graph(geom, z, pos, crop_margin)
+    tiles, _ = engine.render_tiles(geom, _batch_opts(opts, z_per_patch, z0, z1, pos), crop_margin=crop_margin)
+    return tiles
+
+
 def _render_job_tiles(engine, job, opts, z_per_patch, z_offset, batch_size, crop_margin, out=None):
     """All crops of ``job`` through encoder -> generator -> composite in even batches -> uint8 tiles [n, T, T, 4]."""
     n = len(job.crops_yx)
@@ -377,8 +401,7 @@ def _render_job_tiles(engine, job, opts, z_per_patch, z_offset, batch_size, crop
         b1 = min(b0 + bs, n)
         geom = job.gather(b0, b1)
         pos = job.d_crops[b0:b1].to(torch.int64)
-        tiles, _ = engine.render_tiles(geom, _batch_opts(opts, z_per_patch, z_offset + b0, z_offset + b1, pos), crop_margin=crop_margin)
-        tiles_all[b0:b1] = tiles
+        tiles_all[b0:b1] = _render_batch(engine, geom, opts, z_per_patch, z_offset + b0, z_offset + b1, pos, crop_margin, n // bs)
     return tiles_all
 
 
@@ -470,8 +493,7 @@ def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOption
         b1 = min(b0 + bs, end)
         geom = job.gather(b0, b1)
         pos = job.d_crops[b0:b1].to(torch.int64)
-        tiles, _ = engine.render_tiles(geom, _batch_opts(opts, z_per_patch, b0, b1, pos), crop_margin=crop_margin)
-        tiles_local[b0 - start:b1 - start] = tiles
+        tiles_local[b0 - start:b1 - start] = _render_batch(engine, geom, opts, z_per_patch, b0, b1, pos, crop_margin, (end - start) // bs)
     mark('render')
     if world == 1:
         canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)

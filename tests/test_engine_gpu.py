@@ -189,6 +189,39 @@ def test_interactive_graph_session_equals_render_stroke(engines):
     assert np.array_equal(sess.render_stroke(patch, (5, 7)), ref)
 
 
+@pytest.mark.parametrize('B', [3, 40])
+def test_batch_graph_session_equals_eager_render_tiles(engines, B):
+    """The CUDA graph of the batch step (whole, and split before the last layer for the benchmark's kernel probe) returns the
+    same bytes as the eager launch sequence, for changing inputs; so does render_patches_host, which feeds it from host buffers."""
+    from brushstroke_engine_b200.engine import BatchSession
+    eng = engines['bf16']
+    rng = np.random.RandomState(B)
+    whole = BatchSession(eng, B, 10)
+    split = BatchSession(eng, B, 10, split_last_layer=True)
+    assert whole.kernels_per_replay > split.kernels_per_replay > 20
+    for rep in range(3):
+        geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=100 * rep + i, radius=3 + (i % 4)) for i in range(B)])).to(eng.device)
+        z = torch.cat([P.style_z_from_seed(1000 * rep + i) for i in range(B)]).to(eng.device)
+        pos = torch.from_numpy(rng.randint(0, 4000, size=(B, 2))).to(eng.device)
+        o = _opts(z)
+        o.position = pos
+        ref, _ = eng.render_tiles(geom, o, crop_margin=10)
+        assert torch.equal(whole.run(geom, z, pos), ref), rep
+        eng.G.probe = {'b128.conv1': []}
+        got = split.run(geom, z, pos)
+        probe, eng.G.probe = eng.G.probe['b128.conv1'], None
+        assert torch.equal(got, ref) and len(probe) == 1
+        torch.cuda.synchronize()
+        assert probe[0][0].elapsed_time(probe[0][1]) > 0
+        assert torch.equal(eng.render_tiles_graph(geom, z, pos, 10), ref)
+        # host-fed: uint8 guidance patches (0 = stroke) -> pinned in, pinned out
+        patches = (geom[:, 0] * 255).round().to(torch.uint8).cpu()
+        g2 = (1 - (255 - patches.to(eng.device).float()) / 255.0)[:, None].contiguous()
+        ref2, _ = eng.render_tiles(g2, o, crop_margin=10)
+        out = eng.render_patches_host(patches.pin_memory(), z.cpu().pin_memory(), pos.cpu().pin_memory(), crop_margin=10)
+        assert np.array_equal(out.numpy(), ref2.cpu().numpy()), rep
+
+
 def test_interactive_graph_session_survives_other_batch_sizes(engines):
     """A graph session keeps replaying correctly while the same engine serves other batch sizes in between (the generator /
     encoder workspace caches are LRU: more distinct sizes than they hold evict the batch-1 buffers the graph points into,
