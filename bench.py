@@ -232,16 +232,16 @@ def main():
     # the step runs as ONE CUDA-graph replay (engine.BatchSession) + the last synthesis layer and the composite launched
     # eagerly after it, so that the dominant kernel can be bracketed by CUDA events inside the timed region; --eager issues
     # every launch from Python instead (A/B)
-    sess = None
+    bsess = None
     if not args.eager:
         from brushstroke_engine_b200.engine import BatchSession
         with torch.no_grad():
-            sess = BatchSession(engine, B, 10, split_last_layer=True)
+            bsess = BatchSession(engine, B, 10, split_last_layer=True)
 
     def step(i):
         g, z, pos = dsets[i % len(dsets)]
-        if sess is not None:
-            return sess.run(g, z, pos)
+        if bsess is not None:
+            return bsess.run(g, z, pos)
         opts = GanBrushOptions()
         opts.set_style(z)
         opts.position = pos
@@ -278,8 +278,8 @@ def main():
         e1.record()
         barrier()
         launches = _lib.launch_count() - launches0
-        if sess is not None:
-            launches += sess.kernels_per_replay * args.steps          # kernels inside the replayed graph + the eager tail counted above
+        if bsess is not None:
+            launches += bsess.kernels_per_replay * args.steps          # kernels inside the replayed graph + the eager tail counted above
         ms_total = e0.elapsed_time(e1)
         probe = engine.G.probe[DOM]
         engine.G.probe = None
@@ -473,8 +473,8 @@ def main():
                        'batch_per_gpu': B, 'parallelism': f'patch-sharded x{world} (no data-path collective)',
                        'l2': 'per-step working set ~6 GB >> 126 MB L2; inputs rotate over 8 distinct batches (8 x 16.8 MB)',
                        'mode': 'bf16 tensor-core (tcgen05), fp32 accumulate',
-                       'launch': 'eager launches from Python' if sess is None else
-                                 f'one CUDA-graph replay per step ({sess.kernels_per_replay} kernels) + last layer and composite eager (events around the dominant kernel)'},
+                       'launch': 'eager launches from Python' if bsess is None else
+                                 f'one CUDA-graph replay per step ({bsess.kernels_per_replay} kernels) + last layer and composite eager (events around the dominant kernel)'},
             'roofline': {'bound': 'tensor', 'kernel': f'conv_tc_row128_kernel @ {DOM} (3x3 modconv 128->128 @128^2 with ToRGB/triad fused in the epilogue, batch {B})',
                          'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                          'traffic': traffic, 'peak_source': peak_src, 'avg_launch_ms': dom_ms,

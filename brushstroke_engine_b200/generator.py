@@ -147,6 +147,9 @@ class Generator:
         self.last_up_fir_first = os.environ.get('NBE_LAST_UP_FIR_FIRST') is not None   # A/B switch: 4x-FLOP FIR-first path at 128^2
         self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
         self.probe = None       # optional {layer_name: [(start_event, end_event), ...]} filled by _conv_tc (bench.py roofline)
+        # bytes of the transposed-conv intermediate T that one chunk of an up-sampling layer may occupy (L2-resident hand-over
+        # between the transposed conv and the FIR pass); NBE_UP_CHUNK_MB=0 runs every layer over the whole batch at once
+        self.up_chunk_bytes = int(float(os.environ.get('NBE_UP_CHUNK_MB', '40')) * 2 ** 20)
         self.defer_last_layer = False      # flat path: hand the last layer back as a closure instead of launching it (BatchSession)
         self._deferred_last = None
 
@@ -227,7 +230,10 @@ class Generator:
                     ctot = cfg.block_in_channels(res * 2)
                     ws[f'out{res}'] = torch.zeros((B, res, res + 1, ctot), dtype=bf, device=dev)       # conv1 output = next conv0 input
                 if res > 4:
-                    ws[f't{res}'] = torch.zeros((B, res + 2, res + 2, cfg.channels(res)), dtype=bf, device=dev)  # transposed-conv output
+                    # transposed-conv output T of an up-sampling layer, for ONE chunk of the batch: the layer runs chunk by chunk
+                    # (transposed conv -> FIR pass) through this one buffer, sized to stay resident in L2 between the two
+                    # kernels, so T is neither written to nor re-read from HBM (see _up_chunk)
+                    ws[f't{res}'] = torch.zeros((self._up_chunk(B, res), res + 2, res + 2, cfg.channels(res)), dtype=bf, device=dev)
                     pitch = res if res == cfg.img_resolution else res + 1
                     ws[f'x{res}'] = torch.zeros((B, res, pitch, cfg.channels(res)), dtype=bf, device=dev)        # conv0 output = conv1 input
             ws['in4'] = torch.zeros((B, 4, 5, cfg.channels(4)), dtype=bf, device=dev)
@@ -247,6 +253,14 @@ class Generator:
         if ws.ndim != 3 or ws.shape[2] != self.w_dim or ws.shape[1] not in (1, self.num_ws):
             raise RuntimeError(f'w+ latents must be [B, {self.num_ws} or 1, {self.w_dim}], got {tuple(ws.shape)}')
         return ws.expand(-1, self.num_ws, -1) if ws.shape[1] == 1 else ws
+
+    def _up_chunk(self, B: int, res: int) -> int:
+        """Images per chunk of an up-sampling layer with output resolution ``res``: as many as keep the chunk's T tensor
+        ((res+2)^2 x C bf16 per image) under ``up_chunk_bytes`` (0 = the whole batch in one go)."""
+        if self.up_chunk_bytes <= 0:
+            return B
+        per_img = (res + 2) * (res + 2) * self.cfg.channels(res) * 2
+        return max(1, min(B, self.up_chunk_bytes // per_img))
 
     def alloc_injection(self, ws_latents: torch.Tensor):
         """Prepare the flat path for ``ws_latents`` [B, num_ws, w_dim]: computes all styles, and returns
@@ -609,12 +623,16 @@ class Generator:
                 else:
                     t = wsb[f't{res}']
                     TP = res + 2
-                    _lib.call('nbe_convT3x3s2_flat_bf16', _lib.ptr(xin), _lib.ptr(conv0.wqT), _lib.ptr(t), B, Rin, Rin, conv0.cin,
-                              xin.shape[3], xin_pitch, conv0.cout, conv0.cout, TP, TP * TP, None, st)
-                    _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(t), _lib.ptr(self._filter), _lib.ptr(x1), B, res, res, conv0.cout,
-                              res + 1, res + 1, 1, conv0.cout, TP, TP * TP, conv0.cout, x1_pitch, res * x1_pitch, 4.0,
-                              _lib.ptr(dcoefs[conv0.name]), _lib.ptr(noise), nsn, float(ngain), _lib.ptr(conv0.bias), 0.2, SQRT2, clamp,
-                              _lib.ptr(styles[conv1.name]), st)
+                    Bc = t.shape[0]
+                    dco, nsc = dcoefs[conv0.name], styles[conv1.name]
+                    for c0 in range(0, B, Bc):
+                        n = min(Bc, B - c0)
+                        _lib.call('nbe_convT3x3s2_flat_bf16', _lib.ptr(xin[c0:]), _lib.ptr(conv0.wqT), _lib.ptr(t), n, Rin, Rin, conv0.cin,
+                                  xin.shape[3], xin_pitch, conv0.cout, conv0.cout, TP, TP * TP, None, st)
+                        _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(t), _lib.ptr(self._filter), _lib.ptr(x1[c0:]), n, res, res, conv0.cout,
+                                  res + 1, res + 1, 1, conv0.cout, TP, TP * TP, conv0.cout, x1_pitch, res * x1_pitch, 4.0,
+                                  _lib.ptr(dco[c0:]), _lib.ptr(noise[c0:] if (noise is not None and nsn) else noise), nsn, float(ngain),
+                                  _lib.ptr(conv0.bias), 0.2, SQRT2, clamp, _lib.ptr(nsc[c0:]), st)
             else:
                 x1, x1_pitch = xin, xin_pitch
             noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp, noise_buffers.get(f'{conv1.name}.noise_const'))
