@@ -40,7 +40,7 @@
 
 namespace nbe {
 
-constexpr int F_MAX_ENT = 64;
+constexpr int F_MAX_ENT = 128;                                     // 9 taps x up to 14 K chunks (Cin <= 896)
 constexpr int F_MAX_CLASSES = 4;
 constexpr int F_THREADS = 320;                                     // TMA warp, MMA warp, 8 epilogue warps
 constexpr int F_EPI_WARPS = 8;

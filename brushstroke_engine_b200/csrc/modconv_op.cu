@@ -19,51 +19,123 @@ namespace nbe {
 
 static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
-// ---- NCHW (any supported dtype) -> zero-gapped NHWC bf16 ---------------------------------------------------------
+// ---- NCHW 16-bit -> zero-gapped NHWC bf16 -------------------------------------------------------------------------
 // dst[((n*H + h)*P + w)*cs + c] = src[n,c,h,w] * scale[n,c]   for w < W, c < C;   0 for gap columns W <= w < P and padding
-// channels C <= c < cs (so the buffer never has to be cleared).  One 32 (channels) x 32 (columns) tile per CTA through
-// shared memory: reads are contiguous along w, writes along c.
+// channels C <= c < cs (so the buffer never has to be cleared).  One 64 (channels) x 64 (columns) tile per CTA through
+// shared memory: global reads are 8-byte vectors along w (128 contiguous bytes per channel row), global writes 16-byte
+// vectors along c (128 contiguous bytes per pixel); the transposition itself is done with 2-byte shared-memory accesses
+// (33-word row pitch: at most 2-way bank conflicts).  HBM-bound: 2 bytes read + 2 bytes written per element.
+constexpr int PK_T = 64;                                            // tile edge
+constexpr int PK_PITCH = PK_T + 2;                                  // elements per shared-memory row (33 words)
+
+template <class T> struct Pair16;
+template <> struct Pair16<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 unpack(uint32_t w) { return bf16x2_to_f2(w); }
+    static __device__ __forceinline__ uint32_t pack(float a, float b) { const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); }
+};
+template <> struct Pair16<__half> {
+    static __device__ __forceinline__ float2 unpack(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+    static __device__ __forceinline__ uint32_t pack(float a, float b) { const __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); }
+};
+
 template <class T>
 __global__ void __launch_bounds__(256)
 pack_flat_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int H, int W, int P, int cs,
-                 const float* __restrict__ scale) {
-    __shared__ float tile[32][33];
+                 const float* __restrict__ scale, int vec_ok) {
+    __shared__ __nv_bfloat16 tile[PK_T][PK_PITCH];                  // [channel][column]
     const int nh = blockIdx.z, n = nh / H, h = nh - n * H;
-    const int c0 = blockIdx.y * 32, w0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) {
-        const int c = c0 + r, w = w0 + tx;
-        float v = 0.f;
-        if (c < C && w < W) {
-            v = Cvt<T>::ld(src[(((int64_t)n * C + c) * H + h) * W + w]);
-            if (scale) v *= scale[(int64_t)n * C + c];
+    const int c0 = blockIdx.y * PK_T, w0 = blockIdx.x * PK_T;
+    const int t = threadIdx.x;
+    {   // ---- load: thread = (channel row r of 16, group of 4 columns)
+        const int r = t >> 4, g = (t & 15) * 4;
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            const int cl = r + 16 * pass, c = c0 + cl, w = w0 + g;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (c < C && w < W) {
+                const T* sp = src + (((int64_t)n * C + c) * H + h) * W + w;
+                if (vec_ok && w + 3 < W) {
+                    const uint2 raw = *reinterpret_cast<const uint2*>(sp);
+                    const float2 a = Pair16<T>::unpack(raw.x), b = Pair16<T>::unpack(raw.y);
+                    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (w + k < W) v[k] = Cvt<T>::ld(sp[k]);
+                }
+                if (scale) {
+                    const float sc = scale[(int64_t)n * C + c];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] *= sc;
+                }
+            }
+            *reinterpret_cast<__nv_bfloat162*>(&tile[cl][g]) = __floats2bfloat162_rn(v[0], v[1]);
+            *reinterpret_cast<__nv_bfloat162*>(&tile[cl][g + 2]) = __floats2bfloat162_rn(v[2], v[3]);
         }
-        tile[r][tx] = v;
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int w = w0 + r, c = c0 + tx;
-        if (w < P && c < cs) dst[(((int64_t)n * H + h) * P + w) * cs + c] = __float2bfloat16_rn(tile[tx][r]);
+    {   // ---- store: thread = (column of 32, group of 8 channels) -> one 16-byte vector
+        const int cg = (t & 7) * 8, pl = t >> 3;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int wl = pl + 32 * pass, w = w0 + wl, c = c0 + cg;
+            if (w < P && c < cs) {
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned short lo = *reinterpret_cast<const unsigned short*>(&tile[cg + 2 * k][wl]);
+                    const unsigned short hi = *reinterpret_cast<const unsigned short*>(&tile[cg + 2 * k + 1][wl]);
+                    o[k] = (uint32_t)lo | ((uint32_t)hi << 16);
+                }
+                *reinterpret_cast<uint4*>(dst + (((int64_t)n * H + h) * P + w) * cs + c) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
     }
 }
 
-// ---- NHWC bf16 (row pitch P pixels, channel stride cs) -> NCHW T, optionally + noise (maps that do not fit the conv epilogue
-// are added by the caller) -------------------------------------------------------------------------------------------------
+// ---- NHWC bf16 (row pitch P pixels, channel stride cs) -> NCHW 16-bit: the same tile, the other way round -------------------
 template <class T>
 __global__ void __launch_bounds__(256)
-unpack_flat_kernel(const __nv_bfloat16* __restrict__ src, T* __restrict__ dst, int C, int H, int W, int P, int cs) {
-    __shared__ float tile[32][33];
+unpack_flat_kernel(const __nv_bfloat16* __restrict__ src, T* __restrict__ dst, int C, int H, int W, int P, int cs, int vec_ok) {
+    __shared__ __nv_bfloat16 tile[PK_T][PK_PITCH];                  // [channel][column]
     const int nh = blockIdx.z, n = nh / H, h = nh - n * H;
-    const int c0 = blockIdx.y * 32, w0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) {
-        const int w = w0 + r, c = c0 + tx;
-        tile[r][tx] = (w < W && c < C) ? __bfloat162float(src[(((int64_t)n * H + h) * P + w) * cs + c]) : 0.f;
+    const int c0 = blockIdx.y * PK_T, w0 = blockIdx.x * PK_T;
+    const int t = threadIdx.x;
+    {
+        const int cg = (t & 7) * 8, pl = t >> 3;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int wl = pl + 32 * pass, w = w0 + wl, c = c0 + cg;
+            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+            if (w < W && c < C) {                                   // C % 8 == 0 on this path: whole vectors
+                raw = *reinterpret_cast<const uint4*>(src + (((int64_t)n * H + h) * P + w) * cs + c);
+            }
+            const uint32_t o[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                *reinterpret_cast<unsigned short*>(&tile[cg + 2 * k][wl]) = (unsigned short)(o[k] & 0xffffu);
+                *reinterpret_cast<unsigned short*>(&tile[cg + 2 * k + 1][wl]) = (unsigned short)(o[k] >> 16);
+            }
+        }
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int c = c0 + r, w = w0 + tx;
-        if (c < C && w < W) dst[(((int64_t)n * C + c) * H + h) * W + w] = Cvt<T>::st(tile[tx][r]);
+    {
+        const int r = t >> 4, g = (t & 15) * 4;
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            const int cl = r + 16 * pass, c = c0 + cl, w = w0 + g;
+            if (c < C && w < W) {
+                const float2 a = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(&tile[cl][g]));
+                const float2 b = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(&tile[cl][g + 2]));
+                T* dp = dst + (((int64_t)n * C + c) * H + h) * W + w;
+                if (vec_ok && w + 3 < W) {
+                    *reinterpret_cast<uint2*>(dp) = make_uint2(Pair16<T>::pack(a.x, a.y), Pair16<T>::pack(b.x, b.y));
+                } else {
+                    const float v[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (w + k < W) dp[k] = Cvt<T>::st(v[k]);
+                }
+            }
+        }
     }
 }
 
@@ -74,9 +146,11 @@ static int launch_pack(const void* x, void* dst, int N, int C, int H, int W, int
     const int max_n = std::max(1, 65535 / H);
     for (int n0 = 0; n0 < N; n0 += max_n) {
         const int nn = std::min(max_n, N - n0);
-        dim3 grid((P + 31) / 32, (cs + 31) / 32, nn * H);
-        pack_flat_kernel<T><<<grid, 256, 0, s>>>((const T*)x + (int64_t)n0 * C * H * W, (__nv_bfloat16*)dst + (int64_t)n0 * H * P * cs,
-                                                  C, H, W, P, cs, scale ? scale + (int64_t)n0 * C : nullptr);
+        dim3 grid((P + PK_T - 1) / PK_T, (cs + PK_T - 1) / PK_T, nn * H);
+        const T* xp = (const T*)x + (int64_t)n0 * C * H * W;
+        const int vec_ok = (W % 4 == 0) && (((uintptr_t)xp & 7) == 0);
+        pack_flat_kernel<T><<<grid, 256, 0, s>>>(xp, (__nv_bfloat16*)dst + (int64_t)n0 * H * P * cs,
+                                                  C, H, W, P, cs, scale ? scale + (int64_t)n0 * C : nullptr, vec_ok);
         int st = launched("pack_flat_kernel");
         if (st) return st;
     }
@@ -88,9 +162,10 @@ static int launch_unpack(const void* src, void* y, int N, int C, int H, int W, i
     const int max_n = std::max(1, 65535 / H);
     for (int n0 = 0; n0 < N; n0 += max_n) {
         const int nn = std::min(max_n, N - n0);
-        dim3 grid((W + 31) / 32, (C + 31) / 32, nn * H);
-        unpack_flat_kernel<T><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src + (int64_t)n0 * H * P * cs, (T*)y + (int64_t)n0 * C * H * W,
-                                                    C, H, W, P, cs);
+        dim3 grid((W + PK_T - 1) / PK_T, (C + PK_T - 1) / PK_T, nn * H);
+        T* yp = (T*)y + (int64_t)n0 * C * H * W;
+        const int vec_ok = (W % 4 == 0) && (((uintptr_t)yp & 7) == 0);
+        unpack_flat_kernel<T><<<grid, 256, 0, s>>>((const __nv_bfloat16*)src + (int64_t)n0 * H * P * cs, yp, C, H, W, P, cs, vec_ok);
         int st = launched("unpack_flat_kernel");
         if (st) return st;
     }

@@ -147,9 +147,11 @@ class Generator:
         self.last_up_fir_first = os.environ.get('NBE_LAST_UP_FIR_FIRST') is not None   # A/B switch: 4x-FLOP FIR-first path at 128^2
         self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
         self.probe = None       # optional {layer_name: [(start_event, end_event), ...]} filled by _conv_tc (bench.py roofline)
-        # bytes of the transposed-conv intermediate T that one chunk of an up-sampling layer may occupy (L2-resident hand-over
-        # between the transposed conv and the FIR pass); NBE_UP_CHUNK_MB=0 runs every layer over the whole batch at once
-        self.up_chunk_bytes = int(float(os.environ.get('NBE_UP_CHUNK_MB', '40')) * 2 ** 20)
+        # A/B switch (default off): NBE_UP_CHUNK_MB=<n> runs every up-sampling layer chunk by chunk through a transposed-conv
+        # buffer of n MB, meant to keep T in L2 between the transposed conv and the FIR pass.  Measured (profiles/r02d_chunk_sweep.md):
+        # slower at every size -- 12 MB: generator 5.98 ms, 40 MB: 3.66, 96 MB: 3.13 against 2.80 ms unchunked; the per-launch
+        # floor of the persistent kernels (~20 us: resident weights, TMEM, tensor maps) outweighs what L2 residency returns.
+        self.up_chunk_bytes = int(float(os.environ.get('NBE_UP_CHUNK_MB', '0')) * 2 ** 20)
         self.defer_last_layer = False      # flat path: hand the last layer back as a closure instead of launching it (BatchSession)
         self._deferred_last = None
 
