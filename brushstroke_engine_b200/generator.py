@@ -152,6 +152,8 @@ class Generator:
         # slower at every size -- 12 MB: generator 5.98 ms, 40 MB: 3.66, 96 MB: 3.13 against 2.80 ms unchunked; the per-launch
         # floor of the persistent kernels (~20 us: resident weights, TMEM, tensor maps) outweighs what L2 residency returns.
         self.up_chunk_bytes = int(float(os.environ.get('NBE_UP_CHUNK_MB', '0')) * 2 ** 20)
+        self.use_up_fused = os.environ.get('NBE_NO_UP_FUSED') is None       # A/B switch: two kernels (transposed conv, FIR pass) per up layer
+        self._up_scratch_bufs = {}
         self.defer_last_layer = False      # flat path: hand the last layer back as a closure instead of launching it (BatchSession)
         self._deferred_last = None
 
@@ -255,6 +257,15 @@ class Generator:
         if ws.ndim != 3 or ws.shape[2] != self.w_dim or ws.shape[1] not in (1, self.num_ws):
             raise RuntimeError(f'w+ latents must be [B, {self.num_ws} or 1, {self.w_dim}], got {tuple(ws.shape)}')
         return ws.expand(-1, self.num_ws, -1) if ws.shape[1] == 1 else ws
+
+    def _up_scratch(self, W: int) -> torch.Tensor:
+        """Per-CTA rings of transposed-conv rows for ``nbe_up_layer_fused_bf16`` at input width ``W`` (zeroed once: the guard
+        columns must stay zero, everything else is rewritten by every launch)."""
+        t = self._up_scratch_bufs.get(W)
+        if t is None:
+            nbytes = int(_lib.load().nbe_up_layer_fused_scratch_bytes(int(W)))
+            t = self._up_scratch_bufs[W] = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)
+        return t
 
     def _up_chunk(self, B: int, res: int) -> int:
         """Images per chunk of an up-sampling layer with output resolution ``res``: as many as keep the chunk's T tensor
@@ -622,6 +633,12 @@ class Generator:
                     _lib.call('nbe_conv_tc_bf16', _lib.ptr(U), _lib.ptr(conv0.wq), _lib.ptr(x1), B, res, res, conv0.cin, conv0.cin,
                               conv0.cout, conv0.cout, 3, 1, _lib.ptr(dcoefs[conv0.name]), _lib.ptr(noise), nsn, float(ngain),
                               _lib.ptr(conv0.bias), 0.2, SQRT2, clamp, _lib.ptr(styles[conv1.name]), st)
+                elif self.use_up_fused and conv0.cout == 128 and conv0.cin <= 128 and Rin % 8 == 0 and Rin <= 120 and xin_pitch == Rin + 1:
+                    # the whole layer in one kernel: transposed conv -> L2-resident ring of T rows -> FIR + epilogue (csrc/up_fused.cu)
+                    _lib.call('nbe_up_layer_fused_bf16', _lib.ptr(xin), _lib.ptr(conv0.wqT), _lib.ptr(self._filter), _lib.ptr(x1),
+                              _lib.ptr(self._up_scratch(Rin)), self._up_scratch(Rin).numel(), B, Rin, Rin, conv0.cin, xin.shape[3], xin_pitch,
+                              conv0.cout, conv0.cout, x1_pitch, res * x1_pitch, 4.0, _lib.ptr(dcoefs[conv0.name]), _lib.ptr(noise), nsn,
+                              float(ngain), _lib.ptr(conv0.bias), 0.2, SQRT2, clamp, _lib.ptr(styles[conv1.name]), st)
                 else:
                     t = wsb[f't{res}']
                     TP = res + 2

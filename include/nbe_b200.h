@@ -221,6 +221,24 @@ int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int N, int OH,
                           const float* scale, const float* noise, int64_t noise_sn, float noise_gain, const float* bias,
                           float alpha, float gain, float clamp, const float* next_scale, nbe_stream_t stream);
 
+/* A whole up-sampling SynthesisLayer in ONE kernel: nbe_convT3x3s2_flat_bf16 followed by nbe_fir_act_nhwc_bf16 (pad 1) without
+ * the T tensor ever reaching HBM -- the transposed conv runs on tcgen05 CTA pairs, its bf16 result goes into a per-CTA ring of the
+ * last 16 T rows (`scratch`, L2-resident), and FIR warps of the same CTA filter the rows as they complete and apply
+ *   y = clamp(lrelu(fgain * FIR(T) * dcoef[n,c] + noise * noise_gain + bias[c]) * gain) * next_scale[n,c]      -> [N, 2H, 2W, Cout]
+ * Replaces: conv2d_resample's up-sampling path SG2/torch_utils/ops/conv2d_resample.py:124-142 (conv_transpose2d + upfirdn2d) and
+ * the SynthesisLayer epilogue SG2/training/networks.py:386-390.  Bit-identical to the two-kernel sequence.
+ * x: [N, H, x_pitch = W + 1, x_cs] zero-gapped, already modulated; wq: nbe_prepare_weights_bf16(flip = 0); f: 4x4 float32, must be
+ * separable (outer product).  Needs Cout == 128, Cin <= 128, W % 8 == 0, W <= 120, gain > 0, 0 <= alpha <= 1: NBE_EUNSUPPORTED
+ * otherwise (callers then run the two kernels).  scratch: nbe_up_layer_fused_scratch_bytes(W) bytes, zero-initialised ONCE by the
+ * caller (guard columns stay zero; everything else is rewritten), not shared between concurrently running launches. */
+int64_t nbe_up_layer_fused_scratch_bytes(int W);
+int nbe_up_layer_fused_bf16(const void* x, const void* wq, const float* f, void* y, void* scratch, int64_t scratch_bytes,
+                            int N, int H, int W, int Cin, int x_cs, int x_pitch, int Cout,
+                            int y_cs, int64_t y_row_pitch, int64_t y_img_pitch, float fgain,
+                            const float* dcoef, const float* noise, int64_t noise_sn, float noise_gain,
+                            const float* bias, float alpha, float gain, float clamp, const float* next_scale,
+                            nbe_stream_t stream);
+
 /* The last synthesis layer with ToRGB fused into its epilogue (SynthesisBlock.forward networks.py:663-672 for the last
  * block): the 3x3 modulated conv of nbe_conv_tc_bf16 followed, per pixel and still in registers, by the 1x1 modulated
  * ToRGB (rgb_w [3,Cout] * rgb_styles [N,Cout], no demodulation), bias, clamp, softmax over the three UVS logits and the
