@@ -12,12 +12,13 @@
 //     in shared memory), exactly the machinery of conv_flat.cu;
 //   * the four output-parity classes of an item are computed as two phases by ROW parity -- {(0,0),(0,1)} then {(1,0),(1,1)} --
 //     so that one phase's two accumulators are the two column parities of ONE T row: warps 2-9 ("writers") read them from
-//     TMEM, round to bf16 and store them into a per-CTA ring of the last 16 T rows in global memory, laid out
-//     [row % 16][channel quad][column parity][X + 1][4 channels] so that a warp's 32 positions are 256 contiguous bytes;
+//     TMEM, round to bf16 and store them into a per-CTA ring of the last R T rows in global memory (R = 16 at 64 -> 128), laid
+//     out [row % R][channel pair][column parity][X + 1][2 channels] so that a warp's 32 positions are 128 contiguous bytes;
 //   * warps 10-17 ("FIR") follow one item behind: as soon as the T rows oy-1 .. oy+2 of an output row are complete they
-//     read them back (L2 hits: the ring is 0.5 MB per CTA and is rewritten every 16 rows), filter them separably
-//     (horizontal neighbours come from warp shuffles, vertical ones from a register window), apply the SynthesisLayer
-//     epilogue and write y with whole 32-byte sectors through a small shared-memory transposition.
+//     read them back (L2 hits: the ring is 0.5 MB per CTA and is rewritten every R rows) -- ALL rows of a work unit are
+//     requested before the first one is used, so the L2 latency is paid once per unit --, filter them separably (horizontal
+//     neighbours come from warp shuffles, vertical ones from a register window), apply the SynthesisLayer epilogue and
+//     write y with whole 32-byte sectors through a small shared-memory transposition.
 //
 // The arithmetic (bf16 rounding of T, order of the FIR's fused multiply-adds, epilogue) is that of the two-kernel path, so
 // the two agree BIT FOR BIT -- which is how tests/test_up_fused_gpu.py checks this kernel.
@@ -31,12 +32,12 @@ namespace nbe {
 constexpr int U_THREADS = 576;                                       // warps: 0 TMA, 1 MMA, 2..9 T writers, 10..17 FIR
 constexpr int U_MAX_ENT = 18;                                        // 9 taps x <= 2 K chunks (Cin <= 128)
 constexpr int U_BHALF = 64 * 128;                                    // this CTA's half of a [128 Cout x 64 Cin] weight tile
-constexpr int U_RING = 16;                                           // T rows kept per CTA
-constexpr int U_STAGE = 512;                                         // per FIR warp: 16 pixels x 16 channels (32 bytes)
+constexpr int U_STAGE = 4 * 16 * 32;                                 // per FIR warp: 4 output rows x 16 pixels x 16 channels (32 bytes)
 
 struct UpParams {
     __nv_bfloat16* y; int y_cs; long long y_row_pitch, y_img_pitch;
     __nv_bfloat16* scratch; long long scratch_cta;                    // ring base, elements per CTA
+    int ring;                                                         // T rows kept per CTA (power of two)
     int N, H, W, P, positions, ipi, OH, OW, warm;
     int k_chunks, n_ent, ph_e0[2], ph_e1[2];
     uint32_t ent_w[U_MAX_ENT + 1];
@@ -55,13 +56,13 @@ __device__ __forceinline__ int rows_ready(int k, const UpParams& p) {
     return max(0, min(p.OH, 2 * yc - 2));
 }
 
-__device__ __forceinline__ uint2 ld_g8(const __nv_bfloat16* p) {
-    uint2 v;
-    asm volatile("ld.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+__device__ __forceinline__ uint32_t ld_g4(const __nv_bfloat16* p) {
+    uint32_t v;
+    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112)
 up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const UpParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -200,7 +201,8 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int qd = warp & 3, hsel = (warp - 2) >> 2;
         const int m = qd * 32 + lane;
         __nv_bfloat16* ring = p.scratch + (long long)blockIdx.x * p.scratch_cta;
-        const int plane = (p.W + 2) * 4;                               // elements of one [X + 1][4 ch] plane
+        const int plane = (p.W + 2) * 2;                               // elements of one [X + 1][2 ch] plane
+        const int rmask = p.ring - 1;
         uint32_t acc_phase[2] = {0, 0};
         for (int i = 0; i < n_items; ++i) {
             const int g = g_begin + i;
@@ -220,7 +222,7 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 const bool row_ok = q < p.positions && Y <= p.H - ph;
                 const bool ok0 = row_ok && X <= p.W, ok1 = row_ok && X < p.W;
                 const int t = 2 * Y + ph;
-                __nv_bfloat16* rowp = ring + ((long long)((tb + t) & (U_RING - 1)) * 32 * 2) * plane + (X + 1) * 4;
+                __nv_bfloat16* rowp = ring + ((long long)((tb + t) & rmask) * 64 * 2) * plane + (X + 1) * 2;
 #pragma unroll 1
                 for (int c32 = 0; c32 < 2; ++c32) {
                     uint32_t v0[32], v1[32];
@@ -229,19 +231,11 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     tmem_ld32_nowait(ta + 128, v1);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int ch4 = hsel * 16 + c32 * 8 + j;
-                        __nv_bfloat16* dst = rowp + (long long)ch4 * 2 * plane;
-                        if (ok0) {
-                            const __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1]));
-                            const __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3]));
-                            *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
-                        }
-                        if (ok1) {
-                            const __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1]));
-                            const __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3]));
-                            *reinterpret_cast<uint2*>(dst + plane) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
-                        }
+                    for (int j = 0; j < 16; ++j) {
+                        const int ch2 = hsel * 32 + c32 * 16 + j;
+                        __nv_bfloat16* dst = rowp + (long long)ch2 * 2 * plane;
+                        if (ok0) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+                        if (ok1) *reinterpret_cast<__nv_bfloat162*>(dst + plane) = __floats2bfloat162_rn(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
                     }
                 }
                 tcgen05_fence_before();
@@ -254,17 +248,16 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
     } else {
         // ============================== FIR + epilogue (warps 10..17, both CTAs) ==============================
-        // lane = (channel quad cq of 4, position xl of 8): a warp filters 8 input columns (16 output pixels) x 16 channels of the
-        // ready output rows with a vertical register window; units (segment of 8 columns, group of 16 channels) are dealt to the
-        // 8 warps round robin.
+        // lane = (channel pair cq of 4, position xl of 8): a warp filters 8 input columns (16 output pixels) x 8 channels at a time;
+        // two such passes fill the 16 channels (32 bytes) of its 16 pixels in the staging buffer, which is then written out as
+        // whole sectors.  Work units (segment of 8 columns, group of 16 channels) are dealt to the 8 warps round robin; a unit is
+        // processed in groups of <= 4 output rows whose <= 7 T rows are ALL requested before the first one is used.
         const int wf = warp - 10;
         const int xl = lane & 7, cq = lane >> 3;
         const __nv_bfloat16* ring = p.scratch + (long long)blockIdx.x * p.scratch_cta;
-        const int plane = (p.W + 2) * 4;
+        const int plane = (p.W + 2) * 2;
+        const int rmask = p.ring - 1;
         uint8_t* stg = smem_stage + wf * U_STAGE;
-        float fx[4], fy[4];
-#pragma unroll
-        for (int i2 = 0; i2 < 4; ++i2) { fx[i2] = s_f[i2]; fy[i2] = s_f[i2 * 4] / s_f[0]; }
         {   // the window arithmetic below is the rank-1 form f = fy (x) fx; anything else must take the two-kernel path
             bool sep = s_f[0] != 0.f;
             for (int a = 1; a < 4; ++a)
@@ -275,8 +268,9 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 __trap();
             }
         }
-        const float2 fx2[4] = {{fx[0], fx[0]}, {fx[1], fx[1]}, {fx[2], fx[2]}, {fx[3], fx[3]}};
-        const float2 fy2[4] = {{fy[0], fy[0]}, {fy[1], fy[1]}, {fy[2], fy[2]}, {fy[3], fy[3]}};
+        float2 fx2[4], fy2[4];
+#pragma unroll
+        for (int i2 = 0; i2 < 4; ++i2) { fx2[i2] = make_float2(s_f[i2], s_f[i2]); const float v = s_f[i2 * 4] / s_f[0]; fy2[i2] = make_float2(v, v); }
         const float g_pre = p.gain;                                     // lrelu(a) * gain == max(a*gain, a*gain*alpha): folded into scale / bias / noise
         const float clamp_hi = p.clamp >= 0.f ? p.clamp : INFINITY;
         const float ngain = p.noise_gain * g_pre;
@@ -302,91 +296,80 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     asm volatile("bar.sync 2, 256;" ::: "memory");
                     cur_n = n;
                 }
-                if (r_hi > r_lo) {
 #pragma unroll 1
-                    for (int u = wf; u < n_units; u += 8) {
-                        const int seg = u >> 3, cp = u & 7;
-                        const int ch4 = cp * 4 + cq;                     // channel quad of this lane
-                        const int X = seg * 8 + xl;
-                        float4 sc4 = *reinterpret_cast<const float4*>(s_vec + ch4 * 4);
-                        float4 bs4 = *reinterpret_cast<const float4*>(s_vec + 128 + ch4 * 4);
-                        float4 ns4 = *reinterpret_cast<const float4*>(s_vec + 256 + ch4 * 4);
-                        const float2 sc2[2] = {{sc4.x, sc4.y}, {sc4.z, sc4.w}}, bs2[2] = {{bs4.x, bs4.y}, {bs4.z, bs4.w}};
-                        const float2 ns2[2] = {{ns4.x, ns4.y}, {ns4.z, ns4.w}};
-                        const __nv_bfloat16* colp = ring + (long long)ch4 * 2 * plane + (X + 1) * 4;     // + slot * 64 * plane ; plane 1 at + plane
-                        __nv_bfloat16* yp = p.y + (((long long)n * p.y_img_pitch + (long long)r_lo * p.y_row_pitch + seg * 16) * p.y_cs + cp * 16);
-                        const float* nzp = p.noise ? p.noise + (long long)n * p.noise_sn + (long long)r_lo * p.OW + 2 * X : nullptr;
-                        float2 h[3][2][2];                               // [window row][pixel of the pair][channel pair]
-                        // T rows r_lo-1 .. r_hi+1 ; output row t-2 is complete when row t has been filtered horizontally
-                        for (int t = r_lo - 1; t <= r_hi + 1; ++t) {
-                            uint2 v0 = make_uint2(0u, 0u), v1 = v0, ea = v0, ed = v0, ee = v0;
-                            const bool row_ok = t >= 0 && t <= 2 * p.H;
-                            if (row_ok) {
-                                const __nv_bfloat16* rp = colp + (long long)((tb + t) & (U_RING - 1)) * 64 * plane;
-                                v0 = ld_g8(rp);
-                                v1 = ld_g8(rp + plane);
-                                if (xl == 0) ea = ld_g8(rp + plane - 4);                   // odd column of X - 1 (zero guard at X = -1)
-                                if (xl == 7) { ed = ld_g8(rp + 4); ee = ld_g8(rp + plane + 4); }   // columns of X + 1 (zero guard at X = W)
+                for (int u = wf; u < n_units && r_hi > r_lo; u += 8) {
+                    const int seg = u >> 3, cp = u & 7;
+                    const int X = seg * 8 + xl;
+#pragma unroll 1
+                    for (int r0 = r_lo; r0 < r_hi; r0 += 4) {
+                        const int nr = min(4, r_hi - r0);
+#pragma unroll 1
+                        for (int half = 0; half < 2; ++half) {
+                            const int ch2 = (cp * 2 + half) * 4 + cq;    // channel pair of this lane
+                            const __nv_bfloat16* colp = ring + (long long)ch2 * 2 * plane + (X + 1) * 2;   // + slot * 128 * plane ; odd columns at + plane
+                            // ---- every T row this group needs, requested at once: rows r0-1 .. r0+nr+1
+                            uint32_t v0[7], v1[7], ea[7], ed[7], ee[7];
+#pragma unroll
+                            for (int j = 0; j < 7; ++j) {
+                                const int t = r0 - 1 + j;
+                                v0[j] = v1[j] = ea[j] = ed[j] = ee[j] = 0u;
+                                if (j < nr + 3 && t >= 0 && t <= 2 * p.H) {
+                                    const __nv_bfloat16* rp = colp + (long long)((tb + t) & rmask) * 128 * plane;
+                                    v0[j] = ld_g4(rp);
+                                    v1[j] = ld_g4(rp + plane);
+                                    if (xl == 0) ea[j] = ld_g4(rp + plane - 2);                       // odd column of X - 1 (zero guard at X = -1)
+                                    if (xl == 7) { ed[j] = ld_g4(rp + 2); ee[j] = ld_g4(rp + plane + 2); }   // columns of X + 1 (zero guard at X = W)
+                                }
                             }
-                            uint2 a, d, e;
-                            a.x = __shfl_up_sync(0xffffffffu, v1.x, 1, 8); a.y = __shfl_up_sync(0xffffffffu, v1.y, 1, 8);
-                            d.x = __shfl_down_sync(0xffffffffu, v0.x, 1, 8); d.y = __shfl_down_sync(0xffffffffu, v0.y, 1, 8);
-                            e.x = __shfl_down_sync(0xffffffffu, v1.x, 1, 8); e.y = __shfl_down_sync(0xffffffffu, v1.y, 1, 8);
-                            if (xl == 0) a = ea;
-                            if (xl == 7) { d = ed; e = ee; }
-                            // T columns 2X-1 .. 2X+3 = a, v0, v1, d, e ; outputs 2X (a v0 v1 d) and 2X+1 (v0 v1 d e)
-                            const float2 c_[5][2] = {{bf16x2_to_f2(a.x), bf16x2_to_f2(a.y)}, {bf16x2_to_f2(v0.x), bf16x2_to_f2(v0.y)},
-                                                     {bf16x2_to_f2(v1.x), bf16x2_to_f2(v1.y)}, {bf16x2_to_f2(d.x), bf16x2_to_f2(d.y)},
-                                                     {bf16x2_to_f2(e.x), bf16x2_to_f2(e.y)}};
-                            float2 hn[2][2];
+                            const float2 sc2 = *reinterpret_cast<const float2*>(s_vec + ch2 * 2);
+                            const float2 bs2 = *reinterpret_cast<const float2*>(s_vec + 128 + ch2 * 2);
+                            const float2 ns2 = *reinterpret_cast<const float2*>(s_vec + 256 + ch2 * 2);
+                            const float* nzp = p.noise ? p.noise + (long long)n * p.noise_sn + (long long)r0 * p.OW + 2 * X : nullptr;
+                            float2 h[7][2];                              // horizontally filtered rows [T row][pixel of the pair], channel pair packed
 #pragma unroll
-                            for (int j = 0; j < 2; ++j)
+                            for (int j = 0; j < 7; ++j) {
+                                if (j < nr + 3) {
+                                    uint32_t a = __shfl_up_sync(0xffffffffu, v1[j], 1, 8);
+                                    uint32_t d = __shfl_down_sync(0xffffffffu, v0[j], 1, 8);
+                                    uint32_t e = __shfl_down_sync(0xffffffffu, v1[j], 1, 8);
+                                    if (xl == 0) a = ea[j];
+                                    if (xl == 7) { d = ed[j]; e = ee[j]; }
+                                    // T columns 2X-1 .. 2X+3 = a, v0, v1, d, e ; outputs 2X (a v0 v1 d) and 2X+1 (v0 v1 d e)
+                                    const float2 c_[5] = {bf16x2_to_f2(a), bf16x2_to_f2(v0[j]), bf16x2_to_f2(v1[j]), bf16x2_to_f2(d), bf16x2_to_f2(e)};
 #pragma unroll
-                                for (int q2 = 0; q2 < 2; ++q2)
-                                    hn[j][q2] = fma2(fx2[3], c_[j + 3][q2], fma2(fx2[2], c_[j + 2][q2], fma2(fx2[1], c_[j + 1][q2], mul2(fx2[0], c_[j][q2]))));
-                            if (t >= r_lo + 2) {
-                                const int r = t - 2 - r_lo;                  // output row r_lo + r
-                                float2 nz2 = {0.f, 0.f};
-                                if (nzp) nz2 = *reinterpret_cast<const float2*>(nzp + (long long)r * p.OW);
-                                uint2 outv[2];
+                                    for (int px = 0; px < 2; ++px)
+                                        h[j][px] = fma2(fx2[3], c_[px + 3], fma2(fx2[2], c_[px + 2], fma2(fx2[1], c_[px + 1], mul2(fx2[0], c_[px]))));
+                                }
+                                if (j >= 3 && j < nr + 3) {
+                                    const int r = j - 3;                     // output row r0 + r  (T rows r0+r-1 .. r0+r+2 = h[j-3 .. j])
+                                    float2 nz2 = {0.f, 0.f};
+                                    if (nzp) nz2 = *reinterpret_cast<const float2*>(nzp + (long long)r * p.OW);
 #pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const float nzg = (j ? nz2.y : nz2.x) * ngain;
-                                    const float2 nzv = {nzg, nzg};
-                                    float2 o[2];
-#pragma unroll
-                                    for (int q2 = 0; q2 < 2; ++q2) {
-                                        const float2 acc = fma2(fy2[3], hn[j][q2], fma2(fy2[2], h[2][j][q2], fma2(fy2[1], h[1][j][q2], mul2(fy2[0], h[0][j][q2]))));
-                                        float2 a2 = fma2(acc, sc2[q2], add2(nzv, bs2[q2]));
+                                    for (int px = 0; px < 2; ++px) {
+                                        const float nzg = (px ? nz2.y : nz2.x) * ngain;
+                                        const float2 nzv = {nzg, nzg};
+                                        const float2 acc = fma2(fy2[3], h[j][px], fma2(fy2[2], h[j - 1][px], fma2(fy2[1], h[j - 2][px], mul2(fy2[0], h[j - 3][px]))));
+                                        float2 a2 = fma2(acc, sc2, add2(nzv, bs2));
                                         const float2 m2 = mul2(a2, alpha2);
                                         a2.x = fmaxf(a2.x, m2.x); a2.y = fmaxf(a2.y, m2.y);
                                         a2.x = fminf(fmaxf(a2.x, -clamp_hi), clamp_hi); a2.y = fminf(fmaxf(a2.y, -clamp_hi), clamp_hi);
-                                        o[q2] = mul2(a2, ns2[q2]);
+                                        const float2 o = mul2(a2, ns2);
+                                        // staging: [row][pixel 2 xl + px of the segment][16 channels]: this lane's pair at channel (half*4 + cq) * 2
+                                        *reinterpret_cast<__nv_bfloat162*>(stg + r * 512 + (2 * xl + px) * 32 + (half * 4 + cq) * 4) = __floats2bfloat162_rn(o.x, o.y);
                                     }
-                                    const __nv_bfloat162 b0 = __floats2bfloat162_rn(o[0].x, o[0].y), b1 = __floats2bfloat162_rn(o[1].x, o[1].y);
-                                    outv[j] = make_uint2(*reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
                                 }
-                                // transposition: pixel 2 xl + j of the segment, 8-byte slot cq (swizzled) -> 16 pixels x 32 contiguous bytes
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const int px = 2 * xl + j;
-                                    *reinterpret_cast<uint2*>(stg + px * 32 + ((cq ^ ((px >> 2) & 3)) << 3)) = outv[j];
-                                }
-                                __syncwarp();
-                                {
-                                    const int px = lane >> 1, hf = lane & 1;
-                                    const int sw = (px >> 2) & 3;
-                                    const uint2 lo = *reinterpret_cast<const uint2*>(stg + px * 32 + (((2 * hf) ^ sw) << 3));
-                                    const uint2 hi = *reinterpret_cast<const uint2*>(stg + px * 32 + (((2 * hf + 1) ^ sw) << 3));
-                                    __stcs(reinterpret_cast<uint4*>(yp + ((long long)r * p.y_row_pitch + px) * p.y_cs + hf * 8), make_uint4(lo.x, lo.y, hi.x, hi.y));
-                                }
-                                __syncwarp();
                             }
-#pragma unroll
-                            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                                for (int q2 = 0; q2 < 2; ++q2) { h[0][j][q2] = h[1][j][q2]; h[1][j][q2] = h[2][j][q2]; h[2][j][q2] = hn[j][q2]; }
                         }
+                        __syncwarp();
+                        {   // 16 pixels x 32 bytes per row -> whole sectors: lane = (pixel, half sector)
+                            const int px = lane >> 1, hf = lane & 1;
+                            __nv_bfloat16* yp = p.y + (((long long)n * p.y_img_pitch + (long long)r0 * p.y_row_pitch + seg * 16 + px) * p.y_cs + cp * 16 + hf * 8);
+                            for (int r = 0; r < nr; ++r) {
+                                const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 512 + px * 32 + hf * 16);
+                                __stcs(reinterpret_cast<uint4*>(yp + (long long)r * p.y_row_pitch * p.y_cs), val);
+                            }
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -407,9 +390,18 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
 using namespace nbe;
 
+// T rows a CTA's ring must hold: the writers of item k+1 run while the FIR warps still read for item k and must not reach
+// the slots of item k-1's rows: 4 * ceil(128 / P) + 5 rows (an item spans up to ceil(128 / P) + 1 grid rows), rounded to 2^n
+static int ring_rows(int W) {
+    const int P = W + 1, need = 4 * ((128 + P - 1) / P) + 8;
+    int r = 16;
+    while (r < need) r *= 2;
+    return r;
+}
+
 extern "C" int64_t nbe_up_layer_fused_scratch_bytes(int W) {
     if (W < 8) return -1;
-    return (int64_t)kNumSMs * U_RING * 32 * 2 * (W + 2) * 4 * 2;
+    return (int64_t)kNumSMs * ring_rows(W) * 64 * 2 * (W + 2) * 2 * 2;
 }
 
 extern "C" int nbe_up_layer_fused_bf16(const void* x, const void* wq, const float* f, void* y, void* scratch, int64_t scratch_bytes,
@@ -434,7 +426,8 @@ extern "C" int nbe_up_layer_fused_bf16(const void* x, const void* wq, const floa
     // the FIR warps use the rank-1 form of the filter (fx = first row, fy = first column / corner), like fir_act_tiled_kernel
     UpParams p{};
     p.y = (__nv_bfloat16*)y; p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch;
-    p.scratch = (__nv_bfloat16*)scratch; p.scratch_cta = (long long)U_RING * 32 * 2 * (W + 2) * 4;
+    p.ring = ring_rows(W);
+    p.scratch = (__nv_bfloat16*)scratch; p.scratch_cta = (long long)p.ring * 64 * 2 * (W + 2) * 2;
     p.N = N; p.H = H; p.W = W; p.P = x_pitch; p.positions = (H + 1) * x_pitch; p.OH = 2 * H; p.OW = 2 * W;
     p.ipi = (p.positions + 127) / 128;
     p.warm = (3 * x_pitch + 127) / 128;
