@@ -11,10 +11,10 @@
 //     through its images; warp 0 = TMA, warp 1 = tcgen05 issuer (cta_group::2, all 9 x K-chunk weight half-tiles RESIDENT
 //     in shared memory), exactly the machinery of conv_flat.cu;
 //   * the four output-parity classes of an item are computed as two phases by ROW parity -- {(0,0),(0,1)} then {(1,0),(1,1)} --
-//     so that one phase's two accumulators are the two column parities of ONE T row: warps 2-9 ("writers") read them from
+//     so that one phase's two accumulators are the two column parities of ONE T row: warps 2-5 ("writers") read them from
 //     TMEM, round to bf16 and store them into a per-CTA ring of the last R T rows in global memory (R = 16 at 64 -> 128), laid
 //     out [row % R][channel pair][column parity][X + 1][2 channels] so that a warp's 32 positions are 128 contiguous bytes;
-//   * warps 10-17 ("FIR") follow one item behind: as soon as the T rows oy-1 .. oy+2 of an output row are complete they
+//   * warps 6-15 ("FIR") follow one item behind: as soon as the T rows oy-1 .. oy+2 of an output row are complete they
 //     read them back (L2 hits: the ring is 0.5 MB per CTA and is rewritten every R rows) -- ALL rows of a work unit are
 //     requested before the first one is used, so the L2 latency is paid once per unit --, filter them separably (horizontal
 //     neighbours come from warp shuffles, vertical ones from a register window), apply the SynthesisLayer epilogue and
@@ -29,7 +29,9 @@
 
 namespace nbe {
 
-constexpr int U_THREADS = 576;                                       // warps: 0 TMA, 1 MMA, 2..9 T writers, 10..17 FIR
+// 16 warps = 4 per SM sub-partition, whose 16 K registers then allow 128 per thread (a 17th warp would cap every thread at 96)
+constexpr int U_THREADS = 512;                                       // warps: 0 TMA, 1 MMA, 2..5 T writers, 6..15 FIR
+constexpr int U_FIR_WARPS = 10;
 constexpr int U_MAX_ENT = 18;                                        // 9 taps x <= 2 K chunks (Cin <= 128)
 constexpr int U_BHALF = 64 * 128;                                    // this CTA's half of a [128 Cout x 64 Cin] weight tile
 constexpr int U_STAGE = 4 * 16 * 32;                                 // per FIR warp: 4 output rows x 16 pixels x 16 channels (32 bytes)
@@ -62,7 +64,7 @@ __device__ __forceinline__ uint32_t ld_g4(const __nv_bfloat16* p) {
     return v;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(U_THREADS, 1)
 up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const UpParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,8 +75,8 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
     uint8_t* smem_a = smem;                                           // [2][window of one 64-channel chunk]
     uint8_t* smem_b = smem + 2 * p.a_bytes;                           // [n_ent][8 KiB] resident weights
-    uint8_t* smem_stage = smem_b + p.n_ent * U_BHALF;                 // [8 FIR warps][U_STAGE]
-    float* s_vec = reinterpret_cast<float*>(smem_stage + 8 * U_STAGE);   // [3][128]: scale, bias, next_scale of this CTA's image
+    uint8_t* smem_stage = smem_b + p.n_ent * U_BHALF;                 // [U_FIR_WARPS][U_STAGE]
+    float* s_vec = reinterpret_cast<float*>(smem_stage + U_FIR_WARPS * U_STAGE);   // [3][128]: scale, bias, next_scale of this CTA's image
     float* s_f = s_vec + 3 * 128;                                     // [16] flipped filter * fgain
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_f + 16);
     uint64_t* a_full = bars;                 // [2] (the leader's is the live one)
@@ -93,8 +95,8 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1);
-            mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 16);
-            mbar_init(smem_u32(&t_ready[i]), 8); mbar_init(smem_u32(&fir_done[i]), 8);
+            mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 8);
+            mbar_init(smem_u32(&t_ready[i]), 4); mbar_init(smem_u32(&fir_done[i]), U_FIR_WARPS);
         }
         mbar_init(smem_u32(res_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -194,11 +196,11 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (elect_one()) umma_commit_2sm(smem_u32(&acc_full[ab]));
             }
         }
-    } else if (warp < 10) {
-        // ============================== T writers (warps 2..9, both CTAs) ==============================
-        // TMEM lane quarter qd = warp % 4 (hardware rule) -> positions qd*32 + lane; channel half hsel = (warp - 2) / 4.
+    } else if (warp < 6) {
+        // ============================== T writers (warps 2..5, both CTAs) ==============================
+        // TMEM lane quarter qd = warp % 4 (hardware rule) -> positions qd*32 + lane; each warp stores all 128 channels of its positions.
         // Phase ph of an item holds T row 2Y + ph of every position: accumulator 0 = even columns (2X), 1 = odd columns (2X + 1).
-        const int qd = warp & 3, hsel = (warp - 2) >> 2;
+        const int qd = warp & 3;
         const int m = qd * 32 + lane;
         __nv_bfloat16* ring = p.scratch + (long long)blockIdx.x * p.scratch_cta;
         const int plane = (p.W + 2) * 2;                               // elements of one [X + 1][2 ch] plane
@@ -224,15 +226,15 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 const int t = 2 * Y + ph;
                 __nv_bfloat16* rowp = ring + ((long long)((tb + t) & rmask) * 64 * 2) * plane + (X + 1) * 2;
 #pragma unroll 1
-                for (int c32 = 0; c32 < 2; ++c32) {
+                for (int c32 = 0; c32 < 4; ++c32) {
                     uint32_t v0[32], v1[32];
-                    const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * 256 + hsel * 64 + c32 * 32);
+                    const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * 256 + c32 * 32);
                     tmem_ld32_nowait(ta, v0);
                     tmem_ld32_nowait(ta + 128, v1);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int ch2 = hsel * 32 + c32 * 16 + j;
+                        const int ch2 = c32 * 16 + j;
                         __nv_bfloat16* dst = rowp + (long long)ch2 * 2 * plane;
                         if (ok0) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
                         if (ok1) *reinterpret_cast<__nv_bfloat162*>(dst + plane) = __floats2bfloat162_rn(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
@@ -247,12 +249,12 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&t_ready[i & 1])) : "memory");
         }
     } else {
-        // ============================== FIR + epilogue (warps 10..17, both CTAs) ==============================
+        // ============================== FIR + epilogue (warps 6..15, both CTAs) ==============================
         // lane = (channel pair cq of 4, position xl of 8): a warp filters 8 input columns (16 output pixels) x 8 channels at a time;
         // two such passes fill the 16 channels (32 bytes) of its 16 pixels in the staging buffer, which is then written out as
-        // whole sectors.  Work units (segment of 8 columns, group of 16 channels) are dealt to the 8 warps round robin; a unit is
+        // whole sectors.  Work units (segment of 8 columns, group of 16 channels) are dealt to the FIR warps round robin; a unit is
         // processed in groups of <= 4 output rows whose <= 7 T rows are ALL requested before the first one is used.
-        const int wf = warp - 10;
+        const int wf = warp - 6;
         const int xl = lane & 7, cq = lane >> 3;
         const __nv_bfloat16* ring = p.scratch + (long long)blockIdx.x * p.scratch_cta;
         const int plane = (p.W + 2) * 2;
@@ -264,7 +266,7 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 for (int b = 1; b < 4; ++b)
                     sep = sep && fabsf(s_f[a * 4 + b] * s_f[0] - s_f[a * 4] * s_f[b]) <= 1e-6f * fabsf(s_f[a * 4 + b] * s_f[0]) + 1e-30f;
             if (!sep) {
-                if (threadIdx.x == 320 && blockIdx.x == 0) printf("nbe up_layer_fused: the resample filter is not separable\n");
+                if (threadIdx.x == 192 && blockIdx.x == 0) printf("nbe up_layer_fused: the resample filter is not separable\n");
                 __trap();
             }
         }
@@ -286,18 +288,18 @@ up_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             if (g >= g_own && n < p.N) {
                 const int r_lo = rows_ready(k - 1, p), r_hi = rows_ready(k, p);
                 if (n != cur_n) {
-                    asm volatile("bar.sync 2, 256;" ::: "memory");       // every FIR warp is done with the previous image's vectors
-                    const int et = threadIdx.x - 320;
+                    asm volatile("bar.sync 2, 320;" ::: "memory");       // every FIR warp is done with the previous image's vectors
+                    const int et = threadIdx.x - 192;
                     if (et < 128) {
                         s_vec[et] = (p.scale ? p.scale[(long long)n * 128 + et] : 1.f) * g_pre;
                         s_vec[128 + et] = (p.bias ? p.bias[et] : 0.f) * g_pre;
                         s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * 128 + et] : 1.f;
                     }
-                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    asm volatile("bar.sync 2, 320;" ::: "memory");
                     cur_n = n;
                 }
 #pragma unroll 1
-                for (int u = wf; u < n_units && r_hi > r_lo; u += 8) {
+                for (int u = wf; u < n_units && r_hi > r_lo; u += U_FIR_WARPS) {
                     const int seg = u >> 3, cp = u & 7;
                     const int X = seg * 8 + xl;
 #pragma unroll 1
@@ -468,7 +470,7 @@ extern "C" int nbe_up_layer_fused_bf16(const void* x, const void* wq, const floa
     p.f = f; p.fgain = fgain; p.scale = dcoef; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain; p.bias = bias;
     p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.next_scale = next_scale;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-    p.smem_need = (uint32_t)(2 * p.a_bytes + p.n_ent * U_BHALF + 8 * U_STAGE + (3 * 128 + 16) * sizeof(float) + 256);
+    p.smem_need = (uint32_t)(2 * p.a_bytes + p.n_ent * U_BHALF + U_FIR_WARPS * U_STAGE + (3 * 128 + 16) * sizeof(float) + 256);
     const size_t limit = 227 * 1024;
     if (p.smem_need + 1024 > limit) return fail(NBE_EUNSUPPORTED, "up_layer_fused: %u bytes of shared memory needed", p.smem_need);
     CUtensorMap ta, tb;
@@ -488,8 +490,16 @@ extern "C" int nbe_up_layer_fused_bf16(const void* x, const void* wq, const floa
     }
     static std::once_flag once;
     static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] { err = cudaFuncSetAttribute(up_layer_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    static int max_threads = 0, num_regs = 0;
+    std::call_once(once, [] {
+        err = cudaFuncSetAttribute(up_layer_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncAttributes at;
+        if (err == cudaSuccess) err = cudaFuncGetAttributes(&at, up_layer_fused_kernel);
+        if (err == cudaSuccess) { max_threads = at.maxThreadsPerBlock; num_regs = at.numRegs; }
+    });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "up_layer_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    if (max_threads < U_THREADS)
+        return fail(NBE_EUNSUPPORTED, "up_layer_fused: the kernel (%d registers / thread) can run %d threads per CTA, %d needed", num_regs, max_threads, U_THREADS);
     const int64_t G = (int64_t)((N + 1) / 2) * p.ipi;
     NBE_REQUIRE(G <= INT32_MAX / 2, "up_layer_fused: too many work items");
     const int grid = (int)std::min<int64_t>(kNumSMs / 2, G) * 2;

@@ -152,7 +152,8 @@ class Generator:
         # slower at every size -- 12 MB: generator 5.98 ms, 40 MB: 3.66, 96 MB: 3.13 against 2.80 ms unchunked; the per-launch
         # floor of the persistent kernels (~20 us: resident weights, TMEM, tensor maps) outweighs what L2 residency returns.
         self.up_chunk_bytes = int(float(os.environ.get('NBE_UP_CHUNK_MB', '0')) * 2 ** 20)
-        self.use_up_fused = os.environ.get('NBE_NO_UP_FUSED') is None       # A/B switch: two kernels (transposed conv, FIR pass) per up layer
+        self.use_up_fused = os.environ.get('NBE_UP_FUSED') == '1'      # A/B switch: one fused kernel per up layer (csrc/up_fused.cu) instead of transposed conv + FIR pass
+        self.up_fused_min_res = int(os.environ.get('NBE_UP_FUSED_MIN_RES', '8'))   # smallest input resolution that takes the fused kernel
         self._up_scratch_bufs = {}
         self.defer_last_layer = False      # flat path: hand the last layer back as a closure instead of launching it (BatchSession)
         self._deferred_last = None
@@ -633,7 +634,8 @@ class Generator:
                     _lib.call('nbe_conv_tc_bf16', _lib.ptr(U), _lib.ptr(conv0.wq), _lib.ptr(x1), B, res, res, conv0.cin, conv0.cin,
                               conv0.cout, conv0.cout, 3, 1, _lib.ptr(dcoefs[conv0.name]), _lib.ptr(noise), nsn, float(ngain),
                               _lib.ptr(conv0.bias), 0.2, SQRT2, clamp, _lib.ptr(styles[conv1.name]), st)
-                elif self.use_up_fused and conv0.cout == 128 and conv0.cin <= 128 and Rin % 8 == 0 and Rin <= 120 and xin_pitch == Rin + 1:
+                elif self.use_up_fused and Rin >= self.up_fused_min_res and conv0.cout == 128 and conv0.cin <= 128 and Rin % 8 == 0 \
+                        and Rin <= 120 and xin_pitch == Rin + 1:
                     # the whole layer in one kernel: transposed conv -> L2-resident ring of T rows -> FIR + epilogue (csrc/up_fused.cu)
                     _lib.call('nbe_up_layer_fused_bf16', _lib.ptr(xin), _lib.ptr(conv0.wqT), _lib.ptr(self._filter), _lib.ptr(x1),
                               _lib.ptr(self._up_scratch(Rin)), self._up_scratch(Rin).numel(), B, Rin, Rin, conv0.cin, xin.shape[3], xin_pitch,

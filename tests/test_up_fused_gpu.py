@@ -114,7 +114,7 @@ def test_generator_with_and_without_fused_up_layers_is_bit_identical(bundles):
     from brushstroke_engine_b200.engine import GanBrushOptions, TriadPaintEngine
     cfg, ecfg, gp, ep = bundles
     eng = TriadPaintEngine(gp, ep, DEV, mode='bf16')
-    assert eng.G.use_up_fused
+    eng.G.use_up_fused = True
     B = 21
     geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=40 + i, radius=2 + i % 5) for i in range(B)])).to(DEV)
     opts = GanBrushOptions()
@@ -127,5 +127,5 @@ def test_generator_with_and_without_fused_up_layers_is_bit_identical(bundles):
         try:
             b, rb = eng.render_tiles(geom, opts, crop_margin=10)
         finally:
-            eng.G.use_up_fused = True
+            eng.G.use_up_fused = False
     assert torch.equal(a, b) and torch.equal(uvs_a, rb['uvs'])
