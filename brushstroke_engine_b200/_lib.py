@@ -49,6 +49,8 @@ _SIGNATURES = {
     'nbe_conv_tc_bf16_torgb': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _F, _P, _F, _F, _F, _P, _P, _P, _P, _F, _P, _P, _I, _P],
     'nbe_enc_conv7x7_bf16': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     'nbe_enc_conv7x7_tc_bf16': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    'nbe_enc_conv7x7_toeplitz_weights': [_P, _P, _I, _P],
+    'nbe_enc_conv7x7_toeplitz_bf16': [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _F, _I, _P],
     'nbe_reflect_border_nhwc_bf16': [_P, _I, _I, _I, _I, _I, _P],
     'nbe_bilinear2x_pad_nhwc_bf16': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'nbe_torgb_triad': [_P, _I, _I, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P],
@@ -65,6 +67,7 @@ _SIGNATURES = {
 _OTHER = {
     'nbe_modulated_conv2d_workspace': (c_int64, [_I, _I, _I, _I, _I, _I, _I, _I, _I]),
     'nbe_up_layer_fused_scratch_bytes': (c_int64, [_I]),
+    'nbe_enc_conv7x7_toeplitz_scratch_bytes': (c_int64, [_I, _I, _I]),
 }
 
 _lib = None

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libnbe_b200.so')
-SOURCES = ['api.cu', 'bias_act.cu', 'upfirdn2d.cu', 'conv_f32.cu', 'small_ops.cu', 'canvas.cu', 'conv_tc.cu', 'encoder.cu', 'conv_flat.cu', 'fir_nhwc.cu', 'modconv_op.cu', 'up_fused.cu']
+SOURCES = ['api.cu', 'bias_act.cu', 'upfirdn2d.cu', 'conv_f32.cu', 'small_ops.cu', 'canvas.cu', 'conv_tc.cu', 'encoder.cu', 'conv_flat.cu', 'fir_nhwc.cu', 'modconv_op.cu', 'up_fused.cu', 'enc7x7_toeplitz.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

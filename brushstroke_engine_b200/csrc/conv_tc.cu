@@ -591,11 +591,16 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
               const cuuint32_t* box, const char* what, int spatial_stride, int swizzle128, int f32) {
+    const cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
+    return make_tmap_strided(map, base, rank, dims, strides_bytes, box, estr, what, swizzle128, f32);
+}
+
+int make_tmap_strided(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, const cuuint32_t* estr, const char* what, int swizzle128, int f32) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail(NBE_ECUDA, "conv_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
-    cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
     CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NBE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
     return NBE_OK;

@@ -85,7 +85,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box, const char* what, int spatial_stride = 1, int swizzle128 = 1, int f32 = 0);
+              const cuuint32_t* box, const char* what, int spatial_stride = 1, int swizzle128 = 1 /* 0 none, 1 128B, 32 32B */, int f32 = 0);
+// the same with one traversal (element) stride per dimension: box[i] is the extent walked in tensor coordinates, every
+// estr[i]-th element is transferred
+int make_tmap_strided(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, const cuuint32_t* estr, const char* what, int swizzle128 = 1, int f32 = 0);
 
 
 // ---- lean single-warp MMA issue ----------------------------------------------------------------------------

@@ -70,6 +70,12 @@ class GeometryEncoder:
                 self._w7q = torch.zeros((w0.shape[0], 64), dtype=torch.bfloat16, device=self.device)
                 self._w7q[:, :49] = self._w7.to(torch.bfloat16)
                 self._tc7 = w0.shape[0] % 16 == 0 and w0.shape[0] <= 64
+                # block-Toeplitz form of the same layer (csrc/enc7x7_toeplitz.cu): 64 output channels, NBE_ENC7_IM2COL keeps the
+                # im2col kernel for A/B
+                self._toep7 = w0.shape[0] == 64 and os.environ.get('NBE_ENC7_IM2COL') is None
+                if self._toep7:
+                    self._w7t = torch.empty((7, 512, 16), dtype=torch.bfloat16, device=self.device)
+                    _lib.call('nbe_enc_conv7x7_toeplitz_weights', _lib.ptr(self._w7), _lib.ptr(self._w7t), 64, _lib.stream())
                 self._wq = [None]
                 for (w, b, stride, pad, up) in self._layers[1:]:
                     cout, cin = w.shape[0], w.shape[1]
@@ -125,6 +131,8 @@ class GeometryEncoder:
                     h //= stride
                 # output of layer i, padded for the next conv
                 ws.append(torch.zeros((B, h + 2, h + 2, _cs(w.shape[0])), dtype=torch.bfloat16, device=self.device))
+            # last entry: the reflect-padded bf16 copy of the input the block-Toeplitz first layer reads ([B, H+6, W+16])
+            ws.append(torch.empty((B, H + 6, H + 16), dtype=torch.bfloat16, device=self.device))
             self._ws[key] = ws
             while len(self._ws) > self.max_cached_batch_sizes:     # least recently used first; a CUDA-graph session that
                 self._ws.pop(next(iter(self._ws)))                 # captured an evicted workspace keeps its own reference
@@ -155,13 +163,20 @@ class GeometryEncoder:
             wi = 0
             w, b, _, _, _ = self._layers[0]
             cur = ws[wi]; wi += 1
-            if self._tc7:
+            if self._toep7 and cur.shape[3] == 64 and H % 8 == 0 and W % 128 == 0:
+                nb = _lib.load().nbe_enc_conv7x7_toeplitz_scratch_bytes(B, H, W)
+                pad = ws[-1]
+                assert pad.numel() * 2 >= nb
+                _lib.call('nbe_enc_conv7x7_toeplitz_bf16', _lib.ptr(geom), _lib.ptr(self._w7t), _lib.ptr(b), _lib.ptr(cur), _lib.ptr(pad), nb,
+                          B, H, W, 64, 64, slope, PREPROC_CODE[self.cfg.preproc_type], st)
+            elif self._tc7:
                 _lib.call('nbe_enc_conv7x7_tc_bf16', _lib.ptr(geom), _lib.ptr(self._w7q), _lib.ptr(b), _lib.ptr(cur), B, H, W, w.shape[0],
                           cur.shape[3], slope, PREPROC_CODE[self.cfg.preproc_type], st)
             else:
                 _lib.call('nbe_enc_conv7x7_bf16', _lib.ptr(geom), _lib.ptr(self._w7), _lib.ptr(b), _lib.ptr(cur), B, H, W, w.shape[0],
                           cur.shape[3], slope, PREPROC_CODE[self.cfg.preproc_type], st)
-            _lib.call('nbe_reflect_border_nhwc_bf16', _lib.ptr(cur), B, H + 2, W + 2, w.shape[0], cur.shape[3], st)
+            if not (self._toep7 and cur.shape[3] == 64 and H % 8 == 0 and W % 128 == 0):      # (the Toeplitz kernel writes the border itself)
+                _lib.call('nbe_reflect_border_nhwc_bf16', _lib.ptr(cur), B, H + 2, W + 2, w.shape[0], cur.shape[3], st)
             h = H
             feat_dense = None          # latest feature map as a dense NHWC tensor [B,h,h,C] (input of the next ScaleUp)
             for i in range(1, n_layers):

@@ -303,6 +303,17 @@ int nbe_enc_conv7x7_bf16(const float* x, const float* w, const float* bias, void
 int nbe_enc_conv7x7_tc_bf16(const float* x, const void* wq, const float* bias, void* y, int N, int H, int W, int Cout,
                             int y_cs, float neg_slope, int preproc, nbe_stream_t stream);
 
+/* The same layer as a BLOCK-TOEPLITZ implicit GEMM (csrc/enc7x7_toeplitz.cu): a GEMM row is a group of 8 adjacent pixels, so the
+ * A operand is fetched by one overlapping 5-D TMA box per tile from a reflect-padded bf16 copy of the image (no im2col by
+ * threads), N = 8 px x 64 channels, K = 7 x 16.  Writes the interior AND the 1-pixel reflect border of y [N,H+2,W+2,64] bf16
+ * (no nbe_reflect_border_nhwc_bf16 pass needed).  Needs Cout == y_cs == 64, H % 8 == 0, W % 128 == 0 (NBE_EUNSUPPORTED otherwise:
+ * use nbe_enc_conv7x7_tc_bf16).  wt: [7][512][16] bf16 from nbe_enc_conv7x7_toeplitz_weights(w [Cout,49] float32, BN folded);
+ * scratch: nbe_enc_conv7x7_toeplitz_scratch_bytes(N, H, W) bytes (the padded image; contents need not be preserved). */
+int64_t nbe_enc_conv7x7_toeplitz_scratch_bytes(int N, int H, int W);
+int nbe_enc_conv7x7_toeplitz_weights(const float* w, void* wt, int Cout, nbe_stream_t stream);
+int nbe_enc_conv7x7_toeplitz_bf16(const float* x, const void* wt, const float* bias, void* y, void* scratch, int64_t scratch_bytes,
+                                  int N, int H, int W, int Cout, int y_cs, float neg_slope, int preproc, nbe_stream_t stream);
+
 /* Fill the 1-pixel border of buf [N,Hp,Wp,cs] (first C channels) by reflection of its interior (torch padding_mode='reflect'). */
 int nbe_reflect_border_nhwc_bf16(void* buf, int N, int Hp, int Wp, int C, int cs, nbe_stream_t stream);
 
