@@ -58,6 +58,7 @@ _SIGNATURES = {
     'nbe_gather_geom_patches': [_P, _I, _I, _P, _P, _I, _I, _P],
     'nbe_tile_owner_map': [_P, _I, _I, _P, _I, _I, _P],
     'nbe_place_tiles': [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P],
+    'nbe_blend_window_nhwc_bf16': [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _I, _P],
     'nbe_blend_features': [_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
     'nbe_up_layer_fused_bf16': [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _F, _P, _P, _L, _F, _P, _F, _F, _F, _P, _P],
     'nbe_modulated_conv2d': [_P, _I, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _L, _P],

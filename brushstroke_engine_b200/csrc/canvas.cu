@@ -1,5 +1,6 @@
 // Engine composite + canvas-side integer work of the patch scheduler (bit-exact index arithmetic).
 #include "common.cuh"
+#include <algorithm>
 
 namespace nbe {
 
@@ -147,6 +148,54 @@ place_tiles_kernel(const uint8_t* __restrict__ tiles, const int32_t* __restrict_
     reinterpret_cast<uchar4*>(canvas)[(int64_t)y * w + x] = reinterpret_cast<const uchar4*>(tiles)[idx];
 }
 
+
+// Feature blending of the painting helper (forger/ui/brush.py:190-242, forger/train/stitching.py:18-25) for a batch of
+// patches whose feature windows are DISJOINT (one wavefront of the crop grid), in one pass over the block output x:
+//   m      = the feature canvas already holds this pixel            alpha  = m ? base_alpha : 1
+//   x_b    = bf16((1 - alpha) * saved + alpha * x)                  (BlendedFeatures.blend with weight 1 - alpha)
+//   update = (base_alpha > 0.99 | (m & base_alpha > 0)) & inside the crop margin:  canvas <- x_b, mask <- 1
+//   x      = x_b * scale   (the consuming layer's styles; the un-blended flat path fuses this into the conv epilogue)
+// A pixel's C / 8 threads sit in one warp: all of them read the mask before the first one updates it.
+__global__ void __launch_bounds__(256)
+blend_window_kernel(__nv_bfloat16* __restrict__ x, int x_pitch, int x_cs, int R, int C, __nv_bfloat16* __restrict__ fcanvas,
+                    uint8_t* __restrict__ fmask, int FW, const int32_t* __restrict__ fyx, const float* __restrict__ base_alpha, int cm,
+                    const float* __restrict__ scale, int64_t total) {
+    const int vpp = C >> 3;                                           // 16-byte vectors per pixel
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vpp);
+        const int64_t pixn = i / vpp;
+        const int pix = (int)(pixn % (R * R));
+        const int n = (int)(pixn / (R * R));
+        const int r = pix / R, c = pix - r * R;
+        const int64_t fpix = (int64_t)(fyx[2 * n] + r) * FW + fyx[2 * n + 1] + c;
+        const bool m = fmask[fpix] != 0;
+        const float ab = base_alpha[pix];
+        const bool inner = r >= cm && r < R - cm && c >= cm && c < R - cm;
+        const bool update = (ab > 0.99f || (m && ab > 0.f)) && inner;
+        const float alpha = m ? ab : 1.f;
+        const float a = 1.f - alpha;                                  // weight of the saved features
+        __nv_bfloat16* xp = x + (((int64_t)n * R + r) * x_pitch + c) * x_cs + v * 8;
+        __nv_bfloat16* fp = fcanvas + fpix * C + v * 8;
+        int4 xv = *reinterpret_cast<const int4*>(xp);
+        const int4 sv = *reinterpret_cast<const int4*>(fp);
+        __nv_bfloat16* xe = reinterpret_cast<__nv_bfloat16*>(&xv);
+        const __nv_bfloat16* se = reinterpret_cast<const __nv_bfloat16*>(&sv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xe[e] = __float2bfloat16_rn(a * __bfloat162float(se[e]) + (1.f - a) * __bfloat162float(xe[e]));
+        __syncwarp();                                                 // every thread of the pixel has read the mask
+        if (update) {
+            *reinterpret_cast<int4*>(fp) = xv;
+            if (v == 0) fmask[fpix] = 1;
+        }
+        if (scale) {
+            const float* sc = scale + (int64_t)n * C + v * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xe[e] = __float2bfloat16_rn(__bfloat162float(xe[e]) * sc[e]);
+        }
+        *reinterpret_cast<int4*>(xp) = xv;
+    }
+}
+
 }  // namespace nbe
 
 using namespace nbe;
@@ -220,4 +269,21 @@ extern "C" int nbe_place_tiles(const uint8_t* tiles, const int32_t* tile_yx, con
     const int64_t total = (int64_t)N * T * T;
     place_tiles_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tiles, tile_yx, order, N, T, owner, canvas, canvas_h, canvas_w);
     return launched("place_tiles_kernel");
+}
+
+extern "C" int nbe_blend_window_nhwc_bf16(void* x, int x_pitch, int x_cs, int R, int C, void* fcanvas, uint8_t* fmask, int FH, int FW,
+                                          const int32_t* fyx, const float* base_alpha, int crop_margin, const float* scale, int N,
+                                          nbe_stream_t stream) {
+    NBE_REQUIRE(x && fcanvas && fmask && fyx && base_alpha && N >= 0 && R >= 1, "blend_window: bad arguments");
+    NBE_REQUIRE(C >= 8 && C % 8 == 0 && 32 % (C / 8) == 0, "blend_window: C / 8 must divide 32 (got C = %d)", C);
+    NBE_REQUIRE(x_pitch >= R && x_cs >= C && x_cs % 8 == 0 && FH >= R && FW >= R, "blend_window: bad pitches");
+    NBE_REQUIRE(((int64_t)R * R * (C / 8)) % 32 == 0, "blend_window: a patch must fill whole warps");
+    NBE_REQUIRE(crop_margin >= 0 && 2 * crop_margin < R, "blend_window: bad crop margin");
+    NBE_REQUIRE((((uintptr_t)x | (uintptr_t)fcanvas) & 15) == 0, "blend_window: tensors must be 16-byte aligned");
+    if (N == 0) return NBE_OK;
+    const int64_t total = (int64_t)N * R * R * (C / 8);
+    const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16);
+    blend_window_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, x_pitch, x_cs, R, C, (__nv_bfloat16*)fcanvas, fmask, FW,
+                                                                      fyx, base_alpha, crop_margin, scale, total);
+    return launched("blend_window_kernel");
 }

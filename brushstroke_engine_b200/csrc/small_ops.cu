@@ -559,13 +559,17 @@ styles_demod_kernel(const float* __restrict__ ws, int N, int num_ws, int w_dim, 
         for (int nb = 0; nb < SD_NB; ++nb) {
             const float a = acc[nb] + bias;
             s_s2[nb * cin + c] = a * a;
-            if (n0 + nb < N) tab.styles[l][(long long)(n0 + nb) * cin + c] = (c >= tab.post_from[l]) ? a * post : a;
+            if (n0 + nb < N && blockIdx.z == 0) tab.styles[l][(long long)(n0 + nb) * cin + c] = (c >= tab.post_from[l]) ? a * post : a;
         }
     }
     __syncthreads();
     if (tab.wsq[l] == nullptr || tab.dcoef[l] == nullptr) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int o = warp; o < cout; o += SD_THREADS / 32) {
+    // small batches have few (sample group, layer) blocks: the output channels are then split over gridDim.z blocks, each of
+    // which recomputes the (cheap) styles and reads only its slice of wsq
+    const int per_z = (cout + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int o_end = min(cout, ((int)blockIdx.z + 1) * per_z);
+    for (int o = (int)blockIdx.z * per_z + warp; o < o_end; o += SD_THREADS / 32) {
         const float* q = tab.wsq[l] + (long long)o * cin;
         float sm[SD_NB];
 #pragma unroll
@@ -681,7 +685,8 @@ extern "C" int nbe_styles_demod_f32(const float* ws, int N, int num_ws, int w_di
         tab.w_index[l] = w_index[l]; tab.post_scale[l] = post_scale[l]; tab.post_from[l] = post_from[l];
         if (cin[l] > max_cin) max_cin = cin[l];
     }
-    dim3 grid((N + SD_NB - 1) / SD_NB, n_layers);
+    const int groups = (N + SD_NB - 1) / SD_NB;
+    dim3 grid(groups, n_layers, groups * n_layers < 2 * kNumSMs ? 8 : 1);
     const size_t smem = (size_t)SD_NB * (w_dim + max_cin) * sizeof(float);
     NBE_REQUIRE(smem <= 48 * 1024, "styles_demod: layer too wide");
     styles_demod_kernel<<<grid, SD_THREADS, smem, (cudaStream_t)stream>>>(ws, N, num_ws, w_dim, tab);

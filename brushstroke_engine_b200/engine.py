@@ -224,6 +224,8 @@ class TriadPaintEngine:
         self.style_c = None
         self.uvs_mapper = StyleUVSMapper(self)
         self._side_stream = None
+        self._enc_stream = None
+        self._overlap_encoder = os.environ.get('NBE_NO_ENCODER_OVERLAP') is None     # A/B switch (graph-captured small batches)
         self._overlap_styles = os.environ.get('NBE_NO_STREAM_OVERLAP') is None
         self._batch_sessions = {}
         self._batch_hits = {}
@@ -279,7 +281,20 @@ class TriadPaintEngine:
                             G.prefetch_noise(B, positions)
                         ready = torch.cuda.Event()
                         ready.record(side)
-                    self.encoder.encode_into(geom, dests, scales, scales_ready=ready)
+                    if B < 32 and torch.cuda.is_current_stream_capturing() and self._overlap_encoder:
+                        # small batches inside a CUDA graph: every kernel occupies a few SMs for ~20 us, so the encoder becomes a
+                        # third branch of the graph next to the synthesis blocks that do not read its features yet (b4 .. b16);
+                        # the flat path joins it in front of b32.conv0 (generator.InjectedGeometry.ready_event)
+                        if self._enc_stream is None:
+                            self._enc_stream = torch.cuda.Stream(device=self.device)
+                        enc_s = self._enc_stream
+                        enc_s.wait_stream(main)
+                        with torch.cuda.stream(enc_s):
+                            self.encoder.encode_into(geom, dests, scales, scales_ready=ready)
+                            inj.ready_event = torch.cuda.Event()
+                            inj.ready_event.record(enc_s)
+                    else:
+                        self.encoder.encode_into(geom, dests, scales, scales_ready=ready)
                     main.wait_event(ready)
             else:
                 ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
@@ -414,12 +429,18 @@ class BatchSession:
     host (8-GPU end-to-end) and removes the launch gaps between the step's small kernels.  Output bytes are identical to the
     eager ``render_tiles`` (same kernels, same order).  The session owns the workspaces its kernels point into."""
 
-    def __init__(self, engine: 'TriadPaintEngine', B: int, crop_margin: int, split_last_layer: bool = False):
+    def __init__(self, engine: 'TriadPaintEngine', B: int, crop_margin: int, split_last_layer: bool = False, blend: Optional[dict] = None):
         """``split_last_layer``: capture everything up to the last synthesis layer and launch that layer (the dominant kernel:
         3x3 modconv @128^2 with ToRGB fused) and the composite eagerly after each replay, so that ``engine.G.probe`` can put
-        CUDA events around it inside a timed region (events cannot be timed inside a graph).  Same kernels, same bytes."""
+        CUDA events around it inside a timed region (events cannot be timed inside a graph).  Same kernels, same bytes.
+        ``blend``: ``dict(res, fcanvas, fmask, base_alpha, crop_margin)`` -- the step blends block ``res`` against that
+        persistent feature canvas (``generator.WindowBlend``); the window origins are the extra graph input ``_fyx`` [B,2]
+        int32.  The warm-up runs blend against a scratch canvas: only replays touch the real one."""
         self.engine, self.B, self.crop_margin = engine, B, crop_margin
         self.split = bool(split_last_layer)
+        self._blend = blend
+        self._fyx = torch.zeros((B, 2), dtype=torch.int32, device=engine.device)
+        assert not (blend and split_last_layer)
         self._tail = None
         dev, W = engine.device, engine.patch_width
         self.render_mode = engine.render_mode
@@ -434,17 +455,27 @@ class BatchSession:
             engine._force_overlap = True                             # warm up the code path the capture takes (side-stream branch)
             try:
                 with torch.cuda.stream(self._stream):
+                    scratch = None
+                    if blend is not None:
+                        from .generator import WindowBlend
+                        r = blend['res']
+                        scratch = WindowBlend(r, torch.zeros((r, r, blend['fcanvas'].shape[2]), dtype=torch.bfloat16, device=dev),
+                                              torch.zeros((r, r), dtype=torch.uint8, device=dev), self._fyx, blend['base_alpha'],
+                                              blend['crop_margin'])
                     for _ in range(2):                              # warm-up: workspaces, cudaFuncSetAttribute, lazy module loads
                         engine.G._noise_cache = None
-                        self._forward()
+                        self._forward(scratch)
                         if self._tail is not None:
                             self._tail()
                 self._stream.synchronize()
                 engine.G._noise_cache = None
                 g = torch.cuda.CUDAGraph()
                 n0 = _lib.launch_count()
+                real = None
+                if blend is not None:
+                    real = WindowBlend(blend['res'], blend['fcanvas'], blend['fmask'], self._fyx, blend['base_alpha'], blend['crop_margin'])
                 with torch.cuda.graph(g, stream=self._stream):
-                    self._out = self._forward()
+                    self._out = self._forward(real)
                 self.kernels_per_replay = _lib.launch_count() - n0   # libnbe_b200 kernels inside the graph (torch's own copies not counted)
             finally:
                 engine._force_overlap = False
@@ -453,13 +484,14 @@ class BatchSession:
             self._workspaces = (engine.G._flat_ws.get(B), engine.encoder._ws.get((B, W)))
             torch.cuda.current_stream().wait_stream(self._stream)
 
-    def _forward(self):
+    def _forward(self, window_blend=None):
         eng = self.engine
         opts = GanBrushOptions()
         opts.set_style(self._z)
         opts.position = self._pos
         if not self.split:
-            tiles, _ = eng.render_tiles(self._geom, opts, crop_margin=self.crop_margin)
+            kw = {'window_blend': window_blend} if window_blend is not None else {}
+            tiles, _ = eng.render_tiles(self._geom, opts, crop_margin=self.crop_margin, **kw)
             return tiles
         G = eng.G
         G.defer_last_layer, G._deferred_last = True, None

@@ -54,6 +54,22 @@ def fully_connected(x, weight, bias, activation=ACT_LINEAR, lr_multiplier=1.0, a
     return out
 
 
+class WindowBlend:
+    """Feature blending on the flat bf16 path (``nbe_blend_window_nhwc_bf16``): the output of block ``res`` is blended with a
+    persistent feature canvas and written back into it, per patch window -- the batched form of
+    ``PaintingHelper``'s feature canvas (forger/ui/brush.py:190-242) the wavefront scheduler of ``stylizer`` uses.
+    fcanvas: [FH, FW, C] bf16; fmask: [FH, FW] uint8; fyx: [B, 2] int32 window origins; base_alpha: [res, res] float32."""
+
+    def __init__(self, res, fcanvas, fmask, fyx, base_alpha, crop_margin):
+        self.res, self.fcanvas, self.fmask, self.fyx, self.base_alpha, self.crop_margin = res, fcanvas, fmask, fyx, base_alpha, crop_margin
+
+    def apply(self, x, x_pitch, C, scale, B):
+        assert self.fyx.shape == (B, 2) and self.fyx.dtype == torch.int32 and self.fcanvas.shape[2] == C
+        _lib.call('nbe_blend_window_nhwc_bf16', _lib.ptr(x), int(x_pitch), int(x.shape[3]), int(self.res), int(C), _lib.ptr(self.fcanvas),
+                  _lib.ptr(self.fmask), int(self.fcanvas.shape[0]), int(self.fcanvas.shape[1]), _lib.ptr(self.fyx),
+                  _lib.ptr(self.base_alpha), int(self.crop_margin), _lib.ptr(scale), int(B), _lib.stream())
+
+
 class InjectedGeometry:
     """Geometry features already resident in the generator's concatenated inputs (flat tensor-core path):
     ``buffers[res]`` is the zero-gapped NHWC bf16 tensor [B, res, res + 1, C_block + C_geo] that feeds ``b{2 res}.conv0``;
@@ -62,6 +78,9 @@ class InjectedGeometry:
     of networks_modified.py:219 and the ``x * styles`` of networks.py:68.  Tied to the ``ws`` it was prepared for."""
     def __init__(self, buffers: Dict[int, torch.Tensor], ws, prep):
         self.buffers, self.ws, self.prep = buffers, ws, prep
+        # CUDA event after which the geometry channels are in place, when the encoder runs on another stream: the flat path
+        # waits for it in front of the first layer that reads them (the blocks before it overlap the encoder)
+        self.ready_event = None
 
 
 class _Layer:
@@ -141,8 +160,10 @@ class Generator:
         self.mapping = MappingNetwork(self)
         self.synthesis = SynthesisNetwork(self)
         self._flat_ws = {}                 # batch size -> workspace, least recently used first
-        self.max_cached_batch_sizes = 4
+        self.max_cached_batch_sizes = 32   # workspaces kept (least recently used go first) ...
+        self.max_cached_patches = 1024     # ... as long as their batch sizes sum to no more than this (~23 MB per patch)
         self._noise_cache = None
+        self._window_blend = None          # WindowBlend of the running _synthesis call (flat path)
         self._noise_prefetched = None      # one-shot (positions, maps) computed ahead of _synthesis by prefetch_noise
         self.last_up_fir_first = os.environ.get('NBE_LAST_UP_FIR_FIRST') is not None   # A/B switch: 4x-FLOP FIR-first path at 128^2
         self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
@@ -243,7 +264,7 @@ class Generator:
                     ws[f'x{res}'] = torch.zeros((B, res, pitch, cfg.channels(res)), dtype=bf, device=dev)        # conv0 output = conv1 input
             ws['in4'] = torch.zeros((B, 4, 5, cfg.channels(4)), dtype=bf, device=dev)
             self._flat_ws[B] = ws
-            while len(self._flat_ws) > self.max_cached_batch_sizes:    # least recently used first; holders of an evicted
+            while len(self._flat_ws) > 1 and (len(self._flat_ws) > self.max_cached_batch_sizes or sum(self._flat_ws) > self.max_cached_patches):    # least recently used first; holders of an evicted
                 self._flat_ws.pop(next(iter(self._flat_ws)))           # workspace (CUDA-graph sessions) keep it alive themselves
         else:
             self._flat_ws[B] = self._flat_ws.pop(B)                    # most recently used last
@@ -403,7 +424,7 @@ class Generator:
 
     def _synthesis(self, ws, geom_feature, pos_encoding=None, return_debug_data=False, return_features=None,
                    blended_features=None, noise_buffers=None, positions=None, noise_mode='random', force_fp32=False,
-                   fused_modconv=None, norm_noise_positions=None, **unused):
+                   fused_modconv=None, norm_noise_positions=None, window_blend=None, **unused):
         if pos_encoding is not None:
             raise RuntimeError('synthesis: positional-encoding injection is not part of the style1/2 architecture')
         _lib.require_cuda(ws, 'synthesis')
@@ -419,6 +440,9 @@ class Generator:
         mode = 'fp32' if (force_fp32 or self.mode == 'fp32') else 'bf16'
         injected = isinstance(geom_feature, InjectedGeometry)
         flat = mode == 'bf16' and not return_features and not blended_features and self.flat_supported
+        if window_blend is not None and not flat:
+            raise RuntimeError('synthesis: window_blend needs the flat bf16 path (no force_fp32 / return_features / blended_features)')
+        self._window_blend = window_blend
         if injected and not flat:
             raise RuntimeError('synthesis: InjectedGeometry needs the flat bf16 path (no force_fp32 / return_features / blended_features)')
         with torch.cuda.device(self.device):
@@ -620,6 +644,9 @@ class Generator:
             if res > 4:
                 conv0 = self._layer_by_name[f'b{res}.conv0']
                 Rin = res // 2
+                if injected and geom_feature.ready_event is not None and Rin in cfg.geom_feature_resolutions:
+                    torch.cuda.current_stream().wait_event(geom_feature.ready_event)      # first consumer of the geometry channels
+                    geom_feature.ready_event = None
                 noise, nsn, ngain = self._noise_for(conv0, B, noise_mode, positions, nnp, noise_buffers.get(f'{conv0.name}.noise_const'))
                 x1 = wsb[f'x{res}']
                 x1_pitch = x1.shape[2]
@@ -657,12 +684,26 @@ class Generator:
             else:
                 x1, x1_pitch = xin, xin_pitch
             noise, nsn, ngain = self._noise_for(conv1, B, noise_mode, positions, nnp, noise_buffers.get(f'{conv1.name}.noise_const'))
+            if res == last and self._canvas_format and self._window_blend is not None and self._window_blend.res == res:
+                raise RuntimeError("synthesis: window_blend at the output resolution is not available in the 'canvas' colour format")
             if res == last and self._canvas_format:
                 # 'canvas' colour format: 8 ToRGB outputs do not fit the fused epilogue -- store the last feature map, then ToRGB
                 y = torch.empty((B, res, res, conv1.cout), dtype=torch.bfloat16, device=dev)
                 _lib.call('nbe_conv_tc_bf16', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(y), B, res, res, conv1.cin, x1.shape[3],
                           conv1.cout, conv1.cout, 3, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
                           _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, None, st)
+                img, uvs = self._torgb(y, True, conv1.cout, rgb_styles, colors, B)
+                if nvtx:
+                    torch.cuda.nvtx.range_pop()
+                break
+            wb = self._window_blend if (self._window_blend is not None and self._window_blend.res == res) else None
+            if res == last and wb is not None:
+                # blending at the output resolution: the last feature map must exist in memory, so ToRGB runs as its own kernel
+                y = torch.empty((B, res, res, conv1.cout), dtype=torch.bfloat16, device=dev)
+                _lib.call('nbe_conv_tc_bf16', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(y), B, res, res, conv1.cin, x1.shape[3],
+                          conv1.cout, conv1.cout, 3, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
+                          _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, None, st)
+                wb.apply(y, res, conv1.cout, None, B)
                 img, uvs = self._torgb(y, True, conv1.cout, rgb_styles, colors, B)
                 if nvtx:
                     torch.cuda.nvtx.range_pop()
@@ -703,7 +744,9 @@ class Generator:
             ns = styles[nxt.name][:, :conv1.cout].contiguous() if nxt.cin != conv1.cout else styles[nxt.name]
             _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(out), B, res, res, conv1.cin, x1.shape[3],
                       x1_pitch, 0, conv1.cout, out.shape[3], res + 1, res * (res + 1), _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn,
-                      float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(ns), st)
+                      float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(None if wb is not None else ns), st)
+            if wb is not None:
+                wb.apply(out, res + 1, conv1.cout, ns, B)             # blend, save, then the modulation the epilogue would have fused
             if res in cfg.geom_feature_resolutions:
                 extra = cfg.geom_feature_channels[list(cfg.geom_feature_resolutions).index(res)]
                 if not injected:

@@ -59,7 +59,8 @@ class GeometryEncoder:
             self._layers.append(self._fold(params, f'decoder.model.{i}.conv.conv') + (1, 1, True))
         self._n_enc = n_enc
         self._ws = {}                      # (batch, H) -> workspace, least recently used first
-        self.max_cached_batch_sizes = 4
+        self.max_cached_batch_sizes = 32
+        self.max_cached_patches = 1024      # ... and only while their batch sizes sum to no more than this
         self._flat_s2 = os.environ.get('NBE_ENC_PER_TAP') is None      # A/B switch: strided layers on the per-tap kernel
         if mode == 'bf16':
             if cfg.in_channels != 1 or cfg.pre_filters <= 0 or cfg.pre_filters % 8 or cfg.preproc_type not in PREPROC_CODE:
@@ -134,7 +135,7 @@ class GeometryEncoder:
             # last entry: the reflect-padded bf16 copy of the input the block-Toeplitz first layer reads ([B, H+6, W+16])
             ws.append(torch.empty((B, H + 6, H + 16), dtype=torch.bfloat16, device=self.device))
             self._ws[key] = ws
-            while len(self._ws) > self.max_cached_batch_sizes:     # least recently used first; a CUDA-graph session that
+            while len(self._ws) > 1 and (len(self._ws) > self.max_cached_batch_sizes or sum(k[0] for k in self._ws) > self.max_cached_patches):     # least recently used first; a CUDA-graph session that
                 self._ws.pop(next(iter(self._ws)))                 # captured an evicted workspace keeps its own reference
         else:
             self._ws[key] = self._ws.pop(key)

@@ -544,9 +544,127 @@ class _Blended:
         self.features, self.alpha = features, alpha
 
 
+def _flat_blend_ok(engine: TriadPaintEngine) -> bool:
+    """The flat tensor-core path can blend against a device-side feature canvas (generator.WindowBlend); FP32 engines and
+    non-stock configurations keep the generic path (``NBE_BLEND_GENERIC`` forces it for A/B)."""
+    return engine.G.flat_supported and engine.encoder.mode == 'bf16' and not engine.G._canvas_format \
+        and os.environ.get('NBE_BLEND_GENERIC') is None
+
+
+class _BlendContext:
+    """Device-side state of feature-blended canvases of one shape: the NHWC bf16 feature canvas + its mask (re-zeroed per
+    canvas), the dirty-area alpha, and one CUDA graph of the blended batch step per wavefront size (``engine.BatchSession``
+    with ``blend=``), captured the second time a size is seen.  Kept on the engine, most recent shapes only."""
+
+    def __init__(self, engine: TriadPaintEngine, fh: int, fw: int, res: int, margin: int, cm: int, crop_margin: int):
+        dev = engine.device
+        C = engine.G.cfg.channels(res)
+        self.engine, self.res, self.cm, self.crop_margin = engine, res, cm, crop_margin
+        self.base_alpha = dirty_area_alpha(res, margin, cm, dev).to(torch.float32).contiguous()
+        self.fcanvas = torch.zeros((fh + res, fw + res, C), dtype=torch.bfloat16, device=dev)      # + res: windows never leave the buffer
+        self.fmask = torch.zeros((fh + res, fw + res), dtype=torch.uint8, device=dev)
+        self.sessions, self.hits = {}, {}
+
+    def reset(self):
+        self.fcanvas.zero_()
+        self.fmask.zero_()
+
+    def session(self, n: int):
+        """The graph session for wavefronts of ``n`` patches, or None while the size has been seen only once."""
+        from .engine import BatchSession
+        sess = self.sessions.get(n)
+        if sess is None:
+            self.hits[n] = self.hits.get(n, 0) + 1
+            if self.hits[n] < 2:
+                return None
+            sess = self.sessions[n] = BatchSession(self.engine, n, self.crop_margin, blend=dict(
+                res=self.res, fcanvas=self.fcanvas, fmask=self.fmask, base_alpha=self.base_alpha, crop_margin=self.cm))
+        return sess
+
+
+def _blend_context(engine, fh, fw, res, margin, cm, crop_margin) -> _BlendContext:
+    cache = engine.__dict__.setdefault('_blend_contexts', {})
+    key = (fh, fw, res, margin, cm, crop_margin, engine.render_mode)
+    ctx = cache.pop(key, None)
+    if ctx is None:
+        while len(cache) >= 2:                               # a 4096^2 level-2 feature canvas is 1.1 GB
+            cache.pop(next(iter(cache)))
+        ctx = _BlendContext(engine, fh, fw, res, margin, cm, crop_margin)
+    cache[key] = ctx
+    return ctx
+
+
+def _stylize_blended_flat(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOptions, level: int, z_per_patch, sequential: bool):
+    """Feature blending on the flat bf16 path: the feature canvas is a device-side NHWC bf16 tensor, and look-up, blend,
+    core write-back and the next layer's modulation of a whole batch of windows are ONE kernel inside the generator
+    (``generator.WindowBlend`` -> ``nbe_blend_window_nhwc_bf16``) instead of indexed torch copies around it.
+    ``sequential``: one patch per generator call in raster order (the reference's loop, brush.py:190-242); otherwise one
+    anti-diagonal wavefront of mutually independent patches per call (``blending_wavefronts``) -- the two give the same bytes
+    because every kernel on the path is batch-invariant.  Wavefront sizes that recur (the second canvas of a shape onwards)
+    replay one CUDA graph each: gather + three small copies + one graph launch per wavefront."""
+    from .generator import WindowBlend
+    dev = engine.device
+    down = 2 ** (level - 1)
+    res = engine.patch_width // down
+    fh, fw = int(math.ceil(job.canvas_h / down)), int(math.ceil(job.canvas_w / down))
+    margin = 16 // down                                   # PaintingHelper.feature_blending_margin = 16
+    cm = job.crop_margin // down
+    ctx = _blend_context(engine, fh, fw, res, margin, cm, job.crop_margin)
+    ctx.reset()
+    snapped = (job.crops_yx // down) * down                                               # brush.py:253-258
+    tiles_yx = torch.from_numpy(np.ascontiguousarray(snapped + job.crop_margin).astype(np.int32)).to(dev)
+    n_crops = len(job.crops_yx)
+    tiles_all = torch.empty((n_crops, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
+    waves = [np.array([i], dtype=np.int64) for i in range(n_crops)] if sequential else blending_wavefronts(job.crops_yx, engine.patch_width)
+    # one upload for the whole schedule; the loop below never synchronises with the host
+    d_order = torch.from_numpy(np.concatenate(waves)).to(dev)
+    d_fyx = torch.from_numpy(np.ascontiguousarray(snapped // down).astype(np.int32)).to(dev)[d_order].contiguous()
+    d_pos = job.d_crops.to(torch.int64)[d_order]
+    d_cropsel = job.d_crops[d_order].contiguous()
+    z_sel = z_per_patch[d_order].to(dev, torch.float64) if z_per_patch is not None else None
+    graphs = getattr(engine, 'use_batch_graph', False) and _plain_z_style(opts) and not sequential
+    z_one = opts.style_z.to(dev, torch.float64) if graphs and z_sel is None else None
+    off = 0
+    with torch.cuda.device(dev):
+        for idx in waves:
+            n = len(idx)
+            sl = slice(off, off + n)
+            off += n
+            sess = ctx.session(n) if graphs else None
+            if sess is not None:
+                _lib.call('nbe_gather_geom_patches', _lib.ptr(job.d_geom), job.canvas_h, job.canvas_w, _lib.ptr(d_cropsel[sl]),
+                          _lib.ptr(sess._geom), n, job.patch, _lib.stream())
+                sess._z.copy_(z_sel[sl] if z_sel is not None else (z_one if z_one.shape[0] == n else z_one.expand(n, -1)), non_blocking=True)
+                sess._pos.copy_(d_pos[sl], non_blocking=True)
+                sess._fyx.copy_(d_fyx[sl], non_blocking=True)
+                sess._graph.replay()
+                tiles = sess._out
+            else:
+                geom = torch.empty((n, 1, job.patch, job.patch), dtype=torch.float32, device=dev)
+                _lib.call('nbe_gather_geom_patches', _lib.ptr(job.d_geom), job.canvas_h, job.canvas_w, _lib.ptr(d_cropsel[sl]), _lib.ptr(geom), n,
+                          job.patch, _lib.stream())
+                o = GanBrushOptions()
+                o.__dict__.update(opts.__dict__)
+                if z_sel is not None:
+                    o.style_z, o.style_ws = z_sel[sl], None
+                o.position = d_pos[sl]
+                wb = WindowBlend(res, ctx.fcanvas, ctx.fmask, d_fyx[sl], ctx.base_alpha, cm)
+                tiles, _ = engine.render_tiles(geom, o, crop_margin=job.crop_margin, window_blend=wb)
+            tiles_all[d_order[sl]] = tiles
+        canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
+        owner = torch.empty((job.canvas_h, job.canvas_w), dtype=torch.int32, device=dev)
+        _lib.call('nbe_tile_owner_map', _lib.ptr(tiles_yx), n_crops, job.tile, _lib.ptr(owner), job.canvas_h, job.canvas_w, _lib.stream())
+        order = torch.arange(n_crops, dtype=torch.int32, device=dev)
+        _lib.call('nbe_place_tiles', _lib.ptr(tiles_all), _lib.ptr(tiles_yx), _lib.ptr(order), n_crops, job.tile, _lib.ptr(owner),
+                  _lib.ptr(canvas), job.canvas_h, job.canvas_w, _lib.stream())
+    return canvas
+
+
 def _stylize_blended(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOptions, level: int, z_per_patch):
     """Raster-order execution with a feature canvas (brush.py:33-92, 190-242): patch n blends the features saved
     by earlier overlapping patches into its own post-b(128/2^(level-1)) activations, then saves its core."""
+    if _flat_blend_ok(engine):
+        return _stylize_blended_flat(engine, job, opts, level, z_per_patch, sequential=True)
     dev = engine.device
     down = 2 ** (level - 1)
     res = engine.patch_width // down
@@ -616,6 +734,8 @@ def _stylize_blended_wavefront(engine: TriadPaintEngine, job: CanvasJob, opts: G
     anti-diagonal wavefront of independent patches at a time (see ``blending_wavefronts``): ~2 rows + cols batched
     generator calls instead of rows x cols single-patch ones.  The feature canvas starts as zeros with an all-False
     mask (alpha = 1 wherever nothing was saved yet)."""
+    if _flat_blend_ok(engine):
+        return _stylize_blended_flat(engine, job, opts, level, z_per_patch, sequential=False)
     dev = engine.device
     down = 2 ** (level - 1)
     res = engine.patch_width // down

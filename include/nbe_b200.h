@@ -378,6 +378,17 @@ int nbe_tile_owner_map(const int32_t* tile_yx, int n_tiles, int T, int32_t* owne
 int nbe_place_tiles(const uint8_t* tiles, const int32_t* tile_yx, const int32_t* order, int N, int T,
                     const int32_t* owner, uint8_t* canvas, int canvas_h, int canvas_w, nbe_stream_t stream);
 
+/* Feature blending against a persistent feature canvas for a batch of patches with DISJOINT windows (one wavefront of the crop
+ * grid), on the flat generator path: brush.py:190-242 (saved-feature lookup, dirty-area alpha, core write-back) and
+ * stitching.py:18-25 (the blend) in one pass over the block output x [N, R, x_pitch, x_cs] bf16 (channels 0..C-1):
+ *   m = fmask[fy+r, fx+c];  alpha = m ? base_alpha[r,c] : 1;  x_b = bf16((1 - alpha) * fcanvas[fy+r, fx+c, :] + alpha * x)
+ *   if (base_alpha > 0.99 or (m and base_alpha > 0)) and crop_margin <= r, c < R - crop_margin:  fcanvas <- x_b, fmask <- 1
+ *   x <- bf16(x_b * scale[n, :])   (scale = the consuming layer's styles, or NULL)
+ * fcanvas: [FH, FW, C] bf16, fmask: [FH, FW] uint8, fyx: [N, 2] int32 window origins (windows must stay inside the canvas). */
+int nbe_blend_window_nhwc_bf16(void* x, int x_pitch, int x_cs, int R, int C, void* fcanvas, uint8_t* fmask, int FH, int FW,
+                               const int32_t* fyx, const float* base_alpha, int crop_margin, const float* scale, int N,
+                               nbe_stream_t stream);
+
 /* x = alpha * saved + (1 - alpha) * x on NCHW float32 or NHWC bf16 features (BlendedFeatures.blend,
  * forger/train/stitching.py:24-25), alpha [H,W] shared over channels, per patch n (alpha_sn = 0 broadcasts). */
 int nbe_blend_features(void* x, const void* saved, const float* alpha, int64_t alpha_sn, int N, int C, int H, int W,
