@@ -181,7 +181,8 @@ blend_window_kernel(__nv_bfloat16* __restrict__ x, int x_pitch, int x_cs, int R,
         __nv_bfloat16* xe = reinterpret_cast<__nv_bfloat16*>(&xv);
         const __nv_bfloat16* se = reinterpret_cast<const __nv_bfloat16*>(&sv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xe[e] = __float2bfloat16_rn(a * __bfloat162float(se[e]) + (1.f - a) * __bfloat162float(xe[e]));
+        for (int e = 0; e < 8; ++e)                                   // two roundings like torch's `alpha * features + (1 - alpha) * other` (stitching.py:24-25): no FMA contraction
+            xe[e] = __float2bfloat16_rn(__fadd_rn(__fmul_rn(a, __bfloat162float(se[e])), __fmul_rn(1.f - a, __bfloat162float(xe[e]))));
         __syncwarp();                                                 // every thread of the pixel has read the mask
         if (update) {
             *reinterpret_cast<int4*>(fp) = xv;

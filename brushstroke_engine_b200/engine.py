@@ -316,7 +316,9 @@ class TriadPaintEngine:
         default_colors = (triad_data['colors'] + 1) / 2.0
         sfactor = None
         if opts.enable_uvs_mapping:
-            sf = self.uvs_mapper.get_sfactor(opts)
+            sf = getattr(opts, 'sfactor', None)                 # per-patch factors of a multi-session batch (server.StrokeBatcher)
+            if sf is None:
+                sf = self.uvs_mapper.get_sfactor(opts)
             sfactor = sf.reshape(-1).to(self.device, torch.float32).expand(B).contiguous()
         colors = opts.prepare_colors(default_colors).contiguous()
         W = self.patch_width

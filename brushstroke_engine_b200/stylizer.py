@@ -660,6 +660,60 @@ def _stylize_blended_flat(engine: TriadPaintEngine, job: CanvasJob, opts: GanBru
     return canvas
 
 
+class RasterFeatureCanvas:
+    """``FeatureCanvas`` + ``PaintingHelper._get_blended_features`` / ``update_blended_features`` (brush.py:33-92, 190-242) on
+    the generic generator path (``return_features`` / ``blended_features``; FP32 engines and non-stock configurations): one
+    patch at a time, in the order the caller renders them.  The flat bf16 path keeps its feature canvas in NHWC bf16 and
+    blends inside the generator instead (``generator.WindowBlend``)."""
+
+    def __init__(self, engine: TriadPaintEngine, level: int, fh: int, fw: int, margin: int = 16):
+        self.engine = engine
+        self.down = 2 ** (level - 1)
+        self.res = engine.patch_width // self.down
+        self.fh, self.fw = int(fh), int(fw)
+        self.margin = margin // self.down                     # PaintingHelper.feature_blending_margin = 16
+        self.features, self.mask = None, None                 # allocated by the first patch (brush.py:48-57)
+        self._base = {}
+
+    def _alpha(self, cm: int):
+        b = self._base.get(cm)
+        if b is None:
+            a = dirty_area_alpha(self.res, self.margin, cm, self.engine.device)
+            b = self._base[cm] = (a, a > 0.99)
+        return b
+
+    def render(self, geom: torch.Tensor, opts: GanBrushOptions, y: int, x: int, crop_margin: int) -> torch.Tensor:
+        """Render the patch whose window starts at canvas (y, x) (already snapped to the feature grid), blended with what
+        earlier patches saved, and save its core -> uint8 tiles [1, T, T, 4] on the device."""
+        res, down = self.res, self.down
+        cm = crop_margin // down
+        ys, xs = y // down, x // down
+        alpha, update = self._alpha(cm)
+        blended = {}
+        if self.mask is not None:
+            m = self.mask[ys:ys + res, xs:xs + res]
+            update = update | (m & (alpha > 0))
+            alpha = alpha.clone()
+            alpha[~m] = 1
+            blended = {res: _Blended(self.features[..., ys:ys + res, xs:xs + res], (1 - alpha)[None, None])}
+        if cm > 0:
+            update = update.clone()
+            update[:cm, :] = False
+            update[-cm:, :] = False
+            update[:, :cm] = False
+            update[:, -cm:] = False
+        tiles, raw = self.engine.render_tiles(geom, opts, crop_margin=crop_margin, return_features=[res], blended_features=blended)
+        feat = raw[f'features{res}']
+        if self.features is None:
+            # + res: a window that starts inside the canvas never leaves the buffer
+            self.features = torch.zeros((1, feat.shape[1], self.fh + res, self.fw + res), dtype=feat.dtype, device=feat.device)
+            self.mask = torch.zeros((self.fh + res, self.fw + res), dtype=torch.bool, device=feat.device)
+        self.mask[ys:ys + res, xs:xs + res][update] = True
+        um = update[None, None].expand(-1, feat.shape[1], -1, -1)
+        self.features[..., ys:ys + res, xs:xs + res][um] = feat[um]
+        return tiles
+
+
 def _stylize_blended(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOptions, level: int, z_per_patch):
     """Raster-order execution with a feature canvas (brush.py:33-92, 190-242): patch n blends the features saved
     by earlier overlapping patches into its own post-b(128/2^(level-1)) activations, then saves its core."""
@@ -667,42 +721,15 @@ def _stylize_blended(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOpt
         return _stylize_blended_flat(engine, job, opts, level, z_per_patch, sequential=True)
     dev = engine.device
     down = 2 ** (level - 1)
-    res = engine.patch_width // down
     fh, fw = int(math.ceil(job.canvas_h / down)), int(math.ceil(job.canvas_w / down))
-    margin = 16 // down                                   # PaintingHelper.feature_blending_margin = 16
-    cm = job.crop_margin // down
-    base_alpha = dirty_area_alpha(res, margin, cm, dev)
-    base_update = base_alpha > 0.99
-    features, mask = None, None
+    fc = RasterFeatureCanvas(engine, level, fh, fw)
     canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
     for i, (y, x, _, _) in enumerate(job.crops):
-        ys, xs = (y // down * down) // down, (x // down * down) // down       # snap to the feature grid (brush.py:253-258)
-        alpha, update = base_alpha, base_update
-        blended = {}
-        if mask is not None:
-            m = mask[ys:ys + res, xs:xs + res]
-            update = update | (m & (alpha > 0))
-            alpha = alpha.clone()
-            alpha[~m] = 1
-            blended = {res: _Blended(features[..., ys:ys + res, xs:xs + res], (1 - alpha)[None, None])}
-        if cm > 0:
-            update = update.clone()
-            update[:cm, :] = False
-            update[-cm:, :] = False
-            update[:, :cm] = False
-            update[:, -cm:] = False
+        ys, xs = y // down * down, x // down * down                           # snap to the feature grid (brush.py:253-258)
         geom = job.gather(i, i + 1)
         pos = job.d_crops[i:i + 1].to(torch.int64)
-        tiles, raw = engine.render_tiles(geom, _batch_opts(opts, z_per_patch, i, i + 1, pos), crop_margin=job.crop_margin,
-                                         return_features=[res], blended_features=blended)
-        feat = raw[f'features{res}']
-        if features is None:
-            features = torch.zeros((1, feat.shape[1], fh, fw), dtype=feat.dtype, device=dev)
-            mask = torch.zeros((fh, fw), dtype=torch.bool, device=dev)
-        mask[ys:ys + res, xs:xs + res][update] = True
-        um = update[None, None].expand(-1, feat.shape[1], -1, -1)
-        features[..., ys:ys + res, xs:xs + res][um] = feat[um]
-        ty, tx = (y // down * down) + job.crop_margin, (x // down * down) + job.crop_margin
+        tiles = fc.render(geom, _batch_opts(opts, z_per_patch, i, i + 1, pos), ys, xs, job.crop_margin)
+        ty, tx = ys + job.crop_margin, xs + job.crop_margin
         canvas[ty:ty + job.tile, tx:tx + job.tile] = tiles[0]                 # raster order = last writer wins
     return canvas
 

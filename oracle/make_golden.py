@@ -260,10 +260,9 @@ def golden_generator(out, G, enc, gp, ep, cfg, ecfg):
     save(out, 'generator', **arrays)
 
 
-def golden_engine(out, G, enc, enc_args, gp, ep, cfg, ecfg):
-    """Engine composite + stylizer loop through the reference's own PaintingHelper."""
+def reference_engine(G, enc, enc_args, cfg):
+    """The reference's own ``PaintEngineFactory`` on a synthetic snapshot, CPU."""
     import forger.ui.brush as brush
-    import forger.viz.style_transfer as style_transfer
     snap = {'G': G, 'D': torch.nn.Identity(), 'G_ema': G, 'training_set_kwargs': None, 'augment_pipe': None,
             'args': argparse.Namespace(color_format='triad', geom_inject_resolutions=[0, 1]),
             'encoder': {'args': enc_args, 'model_state': enc.state_dict()}}
@@ -275,6 +274,96 @@ def golden_engine(out, G, enc, enc_args, gp, ep, cfg, ecfg):
     # make the engine run the fp32 path so the fixture pins exact semantics (the stock engine is mixed fp16)
     for res in cfg.block_resolutions:
         getattr(engine.G.synthesis, f'b{res}').use_fp16 = False
+    return engine
+
+
+def wire_script():
+    """The client side of the recorded session: JSON strings and binary render requests, in order (shared with the tests
+    only through the fixture it produces)."""
+    from brushstroke_engine_b200 import server
+
+    def stroke(seed, radius=6):
+        g = synthetic.synthetic_patch(128, seed=seed, radius=radius)[0, 0]              # float, 0 = stroke
+        rgba = np.zeros((128, 128, 4), dtype=np.uint8)
+        rgba[..., 3] = np.round((1 - g) * 255).astype(np.uint8)
+        rgba[..., 0] = 30                                                                # ignored by the server
+        return rgba
+    import json
+    msgs = [json.dumps({'type': 'set_brush', 'seed': 594}),
+            json.dumps({'type': 'new_canvas', 'rows': 300, 'cols': 420, 'feature_blending': 2}),
+            json.dumps({'type': 'set_option', 'option': 'positions', 'value': True}),
+            server.encode_render_request(stroke(21), 0, 0, 10),
+            server.encode_render_request(stroke(22), 89, 1, 10, colors=[(1, 255, 0, 128)], extra_data=5),    # snapped to (88, 0)
+            server.encode_render_request(stroke(23), 44, 61, 10, colors=[(0, 10, 200, 30), (2, 250, 250, 240)]),
+            server.encode_render_request(stroke(24), 176, 88, 0, debug=False),
+            json.dumps({'type': 'set_render_mode', 'mode': 'full'}),
+            server.encode_render_request(stroke(25), 130, 30, 10),
+            json.dumps({'type': 'set_render_mode', 'mode': 'clear'}),
+            json.dumps({'type': 'set_option', 'option': 'uvs_mapping', 'value': True}),
+            server.encode_render_request(stroke(26), 200, 120, 10),
+            json.dumps({'type': 'set_option', 'option': 'uvs_mapping', 'value': False}),
+            json.dumps({'type': 'set_option', 'option': 'positions', 'value': False}),
+            json.dumps({'type': 'new_canvas', 'rows': 300, 'cols': 420, 'feature_blending': 0}),
+            server.encode_render_request(stroke(27), 7, 9, 10, extra_data=3),
+            json.dumps({'type': 'set_brush'}),                                            # random seed from the session's rng
+            server.encode_render_request(stroke(28), 64, 64, 0),
+            b'\x00\x00',                                                               # undecodable: dropped without an answer
+            json.dumps({'type': 'bogus'})]
+    return msgs
+
+
+def golden_wire(out, G, enc, enc_args, cfg):
+    """A whole interactive session through the reference's own ``DrawingWebSocketHandler`` (forger/ui/util.py:107-245;
+    Tornado replaced by a stand-in base class -- the handler's logic is untouched): every message the client sends and
+    every message the handler writes back."""
+    wh = types.ModuleType('tornado.websocket')
+    wh.WebSocketHandler = type('WebSocketHandler', (), {})
+    gen = types.ModuleType('tornado.gen')
+    gen.coroutine = lambda f: f
+    tor = types.ModuleType('tornado')
+    tor.websocket, tor.gen = wh, gen
+    sys.modules.update({'tornado': tor, 'tornado.websocket': wh, 'tornado.gen': gen})
+    import forger.ui.util as ui_util
+    engine = reference_engine(G, enc, enc_args, cfg)
+    geo5 = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=10 + i, radius=8) for i in range(5)]))
+    geo5_thick = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=10 + i, radius=12) for i in range(5)]))
+    engine.uvs_mapper.geom_feature = engine.encoder.encode(geo5)
+    engine.uvs_mapper.fmask = geo5 < 0.01
+    engine.uvs_mapper.bmask = geo5_thick > 0.99
+    handler = ui_util.DrawingWebSocketHandler()
+    handler.initialize(engine, style_seed=3, debug_dir=None, saved_zs_filename=None, libraries={})
+    written = []
+    handler.write_message = lambda m, binary=False: written.append((m, binary))
+    arrays = {}
+
+    def record(tag):
+        for j, (m, binary) in enumerate(written):
+            import json
+            arrays[f'{tag}_out{j}'] = np.frombuffer(m if binary else json.dumps(m).encode(), dtype=np.uint8)
+            arrays[f'{tag}_out{j}_binary'] = np.uint8(binary)
+        arrays[f'{tag}_nout'] = np.int32(len(written))
+        written.clear()
+    with torch.no_grad():
+        handler.open()
+        record('open')
+        msgs = wire_script()
+        for i, m in enumerate(msgs):
+            handler.on_message(m)
+            arrays[f'm{i}_in'] = np.frombuffer(m if isinstance(m, bytes) else m.encode(), dtype=np.uint8)
+            arrays[f'm{i}_in_binary'] = np.uint8(isinstance(m, bytes))
+            record(f'm{i}')
+    arrays['n_msgs'] = np.int32(len(msgs))
+    n_bin = sum(int(arrays[f'm{i}_nout']) for i in range(len(msgs)) if arrays[f'm{i}_in_binary'])
+    print(f'wire: {len(msgs)} client messages, {n_bin} binary answers recorded')
+    assert n_bin == 8
+    save(out, 'wire', **arrays)
+
+
+def golden_engine(out, G, enc, enc_args, gp, ep, cfg, ecfg):
+    """Engine composite + stylizer loop through the reference's own PaintingHelper."""
+    import forger.ui.brush as brush
+    import forger.viz.style_transfer as style_transfer
+    engine = reference_engine(G, enc, enc_args, cfg)
 
     guidance = synthetic.synthetic_guidance(300, 260, num_lines=10, seed=5, radii=(1, 3, 9))
     crop_margin = 10
@@ -397,7 +486,7 @@ def golden_canvas(out, ep, ecfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(REPO, 'tests', 'golden'))
-    ap.add_argument('--only', default=None, help="write one fixture only: 'modconv_tc'")
+    ap.add_argument('--only', default=None, help="write one fixture only: 'modconv_tc' | 'wire'")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.set_grad_enabled(False)
@@ -408,11 +497,14 @@ def main():
     gp = P.init_generator_params(cfg, seed=0, perturb=0.1)
     ep = P.init_encoder_params(ecfg, seed=1, perturb_bn=0.1)
     G, enc, enc_args = build_reference_modules(gp, ep, cfg, ecfg)
+    if args.only == 'wire':
+        return golden_wire(args.out, G, enc, enc_args, cfg)
     golden_ops(args.out)
     golden_generator(args.out, G, enc, gp, ep, cfg, ecfg)
     golden_engine(args.out, G, enc, enc_args, gp, ep, cfg, ecfg)
     golden_canvas(args.out, ep, ecfg)
     golden_modconv_tc(args.out)
+    golden_wire(args.out, G, enc, enc_args, cfg)
 
 
 if __name__ == '__main__':
