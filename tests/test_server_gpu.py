@@ -113,7 +113,7 @@ def test_batched_sessions_equal_one_at_a_time(engines):
 def test_feature_pool_bands():
     cfg, ecfg = P.GeneratorConfig(), P.EncoderConfig()
     eng = TriadPaintEngine(P.init_generator_params(cfg, 0, 0.1), P.init_encoder_params(ecfg, 1, 0.1), DEV, mode='bf16')
-    eng.feature_pool_bytes = 64 << 20
+    eng.feature_pool_bytes = 256 << 20
     a, b = server.PaintingHelper(eng, 1), server.PaintingHelper(eng, 2)
     a.make_new_canvas(256, 256, feature_blending=2)
     b.make_new_canvas(512, 300, feature_blending=2)
