@@ -65,9 +65,11 @@ struct FlatParams {
     // resident: the weights of ONE phase stay in shared memory while the pair sweeps all of its items (phase-major order),
     // so that only the position windows stream from L2; otherwise weights stream through a F_BSTAGES ring (item-major)
     int resident, b_tiles, n_abuf;
+    int contiguous;                                                 // item pairs are dealt in contiguous runs (1) or round robin (0)
     int nbuf;                                                       // accumulator sets in TMEM: 2 (epilogue overlaps the next MMAs) or 1
     // planes: A chunks are 64 channels of one parity plane of a padded NHWC image (stride-2 convs); cpp = chunks per plane
     int planes, cpp, plane_C, plane_rows;
+    int last_steps;                                                 // K = 16 MMA steps of the last 64-channel chunk: ceil((Cin % 64 or 64) / 16)
     int cout_off;                                                   // first output channel of this launch within the weight tiles
     uint32_t smem_need;
     int y_cs; long long y_row_pitch, y_img_pitch; int noise_w;
@@ -130,7 +132,12 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // so both CTAs share q0 and with it every descriptor offset (the last image pair may hold a dummy).
     const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int pairs = ((p.N + 1) >> 1) * p.items_per_img;
-    const int n_local = (pairs - cid + n_clusters - 1) / n_clusters;
+    // every pair takes one CONTIGUOUS run of item pairs [j_first, j_first + n_local): the image -- and with it the per-image epilogue
+    // vectors, two named barriers and an exposed global-memory round trip -- changes once per items_per_img items instead of at
+    // every item (round-robin dealing put ~n_clusters / items_per_img images between two consecutive items of a pair)
+    const int j_first = p.contiguous ? (int)((long long)pairs * cid / n_clusters) : cid;
+    const int j_step = p.contiguous ? 1 : n_clusters;
+    const int n_local = p.contiguous ? (int)((long long)pairs * (cid + 1) / n_clusters) - j_first : (pairs - cid + n_clusters - 1) / n_clusters;
     const int n_steps = n_local * p.n_phases;
 
     if (warp == 0) {
@@ -139,7 +146,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t acnt = 0, bcnt = 0;
             int k = 0, ph = 0;
             for (int s = 0; s < n_steps; ++s) {
-                const int j = cid + k * n_clusters;
+                const int j = j_first + k * j_step;
                 const int np = j / p.items_per_img;
                 const int n = min(2 * np + rank, p.N - 1);                       // dummy: loads stay in range, nothing is stored
                 const int q0 = (j - np * p.items_per_img) * p.T * 128;
@@ -189,7 +196,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a)), b_lo0 = umma_desc_lo(smem_u32(smem_b));
             const uint32_t a_step = (uint32_t)a_bytes >> 4;
             const uint32_t idesc = p.idesc;
-            const int T = p.T, k_chunks = p.k_chunks, n_abuf = p.n_abuf;
+            const int T = p.T, k_chunks = p.k_chunks, n_abuf = p.n_abuf, cpp = p.cpp, last_steps = p.last_steps;
             const bool resident = p.resident != 0;
             uint32_t acc_par0 = 0, acc_par1 = 0;
             int slot = 0; uint32_t a_par = 0;
@@ -200,7 +207,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 // planes: the window starts at a plane-row boundary, q0 sits (q0 mod P) rows into it
                 uint32_t row0 = 0;
                 if (p.planes) {
-                    const int j = cid + k * n_clusters;
+                    const int j = j_first + k * j_step;
                     const int q0 = (j % p.items_per_img) * T * 128;
                     row0 = (uint32_t)(q0 % p.P);
                 }
@@ -213,10 +220,15 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t d_tile = (uint32_t)(G * 128);
                 int e = e0;
                 uint32_t w = p.ent_w[e0];
+                int c_in_plane = 0;
                 for (int c = 0; c < k_chunks; ++c) {
                     mbar_wait_fast(smem_u32(&a_full[slot]), a_par);
                     tcgen05_fence_after();
                     const uint32_t a_lo = a_lo0 + (uint32_t)slot * a_step + row0 * 8u;
+                    // K = 16 steps of this chunk: the last chunk of a (plane's) channel range holds Cin % 64 real channels, the
+                    // rest is zero padding on both operands -- MMAs over it would add exact zeros
+                    const int steps = (c_in_plane == cpp - 1) ? last_steps : 4;
+                    if (++c_in_plane == cpp) c_in_plane = 0;
                     while (e < e1 && (int)(w >> 27) == c) {
                         const uint32_t wn = p.ent_w[e + 1];          // next entry (the table has a sentinel), fetched ahead of the issue
                         uint32_t b_lo;
@@ -237,9 +249,9 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                     const uint32_t al = al0 + (uint32_t)(i * 1024);
                                     const uint32_t d = dd + (uint32_t)i * d_tile;
                                     umma_bf16_lo_2sm(d, al, b_lo, idesc, acc0);
-                                    umma_bf16_lo_2sm(d, al + 2, b_lo + 2, idesc, 1u);
-                                    umma_bf16_lo_2sm(d, al + 4, b_lo + 4, idesc, 1u);
-                                    umma_bf16_lo_2sm(d, al + 6, b_lo + 6, idesc, 1u);
+                                    if (steps > 1) umma_bf16_lo_2sm(d, al + 2, b_lo + 2, idesc, 1u);
+                                    if (steps > 2) umma_bf16_lo_2sm(d, al + 4, b_lo + 4, idesc, 1u);
+                                    if (steps > 3) umma_bf16_lo_2sm(d, al + 6, b_lo + 6, idesc, 1u);
                                 }
                             }
                             if (!resident) umma_commit_2sm(smem_u32(&b_empty[bs]));
@@ -273,9 +285,10 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t acc_phase[2] = {0, 0};
         int cur_n = -1;
         const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
+        const uint32_t s_vec_u32 = smem_u32(s_vec);
         int k = 0, ph = 0;
         for (int s = 0; s < n_steps; ++s) {
-            const int j = cid + k * n_clusters;
+            const int j = j_first + k * j_step;
             const int np = j / p.items_per_img;
             const bool dummy = 2 * np + rank >= p.N;
             const int n = min(2 * np + rank, p.N - 1);
@@ -327,6 +340,17 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                             for (int gg = 0; gg < 4; ++gg) {
                                 uint32_t o[4];
+                                // per-channel vectors: broadcast loads, 16 bytes at a time (the shared-memory data pipe also feeds the UMMAs)
+                                float dc[8], bs[8], ns[8];
+                                if (EPI == 1) {
+                                    const int ob = c0 + gg * 8;
+#pragma unroll
+                                    for (int h4 = 0; h4 < 2; ++h4) {
+                                        lds_f4(s_vec_u32 + (uint32_t)((ob + 4 * h4) * 4), dc + 4 * h4);
+                                        lds_f4(s_vec_u32 + (uint32_t)((128 + ob + 4 * h4) * 4), bs + 4 * h4);
+                                        lds_f4(s_vec_u32 + (uint32_t)((256 + ob + 4 * h4) * 4), ns + 4 * h4);
+                                    }
+                                }
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     float r0 = __uint_as_float(v[gg * 8 + e * 2]), r1 = __uint_as_float(v[gg * 8 + e * 2 + 1]);
@@ -334,13 +358,13 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                         float rr[2] = {r0, r1};
 #pragma unroll
                                         for (int h = 0; h < 2; ++h) {
-                                            const int oc = c0 + gg * 8 + e * 2 + h;
-                                            float a = rr[h] * s_vec[oc] + nz + s_vec[128 + oc];
+                                            const int k = e * 2 + h;
+                                            float a = rr[h] * dc[k] + nz + bs[k];
                                             if (p.act) {
                                                 a *= (a > 0.f) ? pos_gain : neg_gain;
                                                 if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
                                             }
-                                            rr[h] = a * s_vec[256 + oc];
+                                            rr[h] = a * ns[k];
                                         }
                                         r0 = rr[0]; r1 = rr[1];
                                     }
@@ -394,6 +418,8 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     const int cpp = Cin_pad / 64;
     p.planes = in.planes; p.cpp = cpp; p.plane_C = in.Cin;
     p.k_chunks = in.planes ? 4 * cpp : cpp;
+    static const bool full_k = getenv("NBE_FLAT_FULL_K") != nullptr;      // A/B switch: MMAs over the zero padding of the last chunk too
+    p.last_steps = full_k ? 4 : (in.Cin - (cpp - 1) * 64 + 15) / 16;
     // expand the tap program into entries sorted by chunk within each phase
     int ntaps = 0;
     for (int ph = 0; ph < p.n_phases; ++ph) ntaps += phase_ntaps[ph];
@@ -486,6 +512,8 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     const int64_t pairs = (int64_t)((in.N + 1) / 2) * p.items_per_img;
     const int grid = (int)std::min<int64_t>(kNumSMs / 2, pairs) * 2;
     // resident weights pay off when a pair sweeps several items per phase and the largest phase fits next to >= 3 windows
+    static const bool round_robin = getenv("NBE_FLAT_ROUND_ROBIN") != nullptr;      // A/B switch: the former item order
+    p.contiguous = round_robin ? 0 : 1;
     p.resident = !no_resident && pairs >= 2 * (int64_t)(grid / 2) && epi_bytes + (size_t)max_phase_tiles * F_BHALF + 3 * a_bytes <= limit;
     p.b_tiles = p.resident ? max_phase_tiles : F_BSTAGES;
     const size_t rest = epi_bytes + (size_t)p.b_tiles * F_BHALF;
@@ -559,6 +587,8 @@ extern "C" int nbe_conv3x3s2_flat_bf16(const void* xp, const void* wq, void* y,
         // two position tiles per item share every weight tile, unless the padding of the last item costs more than that saves
         const int tiles = (OH * P + 127) / 128;
         p.T = ((tiles + 1) / 2 * 2 * 100 > tiles * 115) ? 1 : 2;
+        static const int force_t = getenv("NBE_S2_T") ? atoi(getenv("NBE_S2_T")) : 0;      // A/B switch
+        if (force_t == 1 || force_t == 2) p.T = force_t;
         FlatTap taps[9];
         int t = 0;
         for (int pl = 0; pl < 4; ++pl)

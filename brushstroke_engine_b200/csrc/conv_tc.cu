@@ -319,6 +319,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         uint32_t acc_phase[2] = {0, 0};
         int it = 0, cur_n = -1;
         const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
+        const uint32_t s_vec_u32 = smem_u32(s_vec);
         for (int jp = cid; jp < pairs; jp += n_clusters, ++it) {
             const int ab = it & 1;
             const bool dummy = 2 * jp + rank >= p.total_items;
@@ -357,19 +358,35 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     for (int g = 0; g < 4; ++g) {
                         int4 out;
                         __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
+                        // the per-channel vectors are the same for all 32 lanes (broadcast loads): fetched 16 bytes at a time, they cost
+                        // 1.5 shared-memory wavefronts per channel instead of 6 -- the data pipe they ride on is the one the tensor
+                        // core reads its operands through (ncu: LSU 41 % + UMMA 45 % of the pipe with scalar loads)
+                        float dc[8], bs[8], ns[8], w0[8], w1[8], w2[8];
+                        const int ob = c0 + g * 8;
+#pragma unroll
+                        for (int h4 = 0; h4 < 2; ++h4) {
+                            lds_f4(s_vec_u32 + (uint32_t)((ob + 4 * h4) * 4), dc + 4 * h4);
+                            lds_f4(s_vec_u32 + (uint32_t)((128 + ob + 4 * h4) * 4), bs + 4 * h4);
+                            lds_f4(s_vec_u32 + (uint32_t)((256 + ob + 4 * h4) * 4), ns + 4 * h4);
+                            if (p.rgb_w) {
+                                lds_f4(s_vec_u32 + (uint32_t)((384 + ob + 4 * h4) * 4), w0 + 4 * h4);
+                                lds_f4(s_vec_u32 + (uint32_t)((512 + ob + 4 * h4) * 4), w1 + 4 * h4);
+                                lds_f4(s_vec_u32 + (uint32_t)((640 + ob + 4 * h4) * 4), w2 + 4 * h4);
+                            }
+                        }
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             float rr[2];
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
-                                const int o = c0 + g * 8 + e * 2 + h;
-                                float a = __uint_as_float(v[g * 8 + e * 2 + h]) * s_vec[o] + nz + s_vec[128 + o];
+                                const int k = e * 2 + h;
+                                float a = __uint_as_float(v[g * 8 + k]) * dc[k] + nz + bs[k];
                                 a *= (a > 0.f) ? pos_gain : neg_gain;
                                 if (p.clamp >= 0.f) a = fminf(fmaxf(a, -p.clamp), p.clamp);
                                 if (p.rgb_w) {
-                                    t0 = fmaf(a, s_vec[384 + o], t0); t1 = fmaf(a, s_vec[512 + o], t1); t2 = fmaf(a, s_vec[640 + o], t2);
+                                    t0 = fmaf(a, w0[k], t0); t1 = fmaf(a, w1[k], t1); t2 = fmaf(a, w2[k], t2);
                                 }
-                                rr[h] = a * s_vec[256 + o];
+                                rr[h] = a * ns[k];
                             }
                             o2[e] = __floats2bfloat162_rn(rr[0], rr[1]);
                         }

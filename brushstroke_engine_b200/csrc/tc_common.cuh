@@ -164,4 +164,10 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive o
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar & kPeerBitMask) : "memory");
 }
 
+// 16-byte shared-memory load through a 32-bit shared address (LDS.128; a generic pointer would make it LD.E.128 plus 64-bit
+// address arithmetic).  volatile: never moved across the named barriers that guard the buffer it reads.
+__device__ __forceinline__ void lds_f4(uint32_t addr, float* dst) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst[0]), "=f"(dst[1]), "=f"(dst[2]), "=f"(dst[3]) : "r"(addr));
+}
+
 }  // namespace nbe

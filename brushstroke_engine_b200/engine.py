@@ -227,6 +227,7 @@ class TriadPaintEngine:
         self._enc_stream = None
         self._overlap_encoder = os.environ.get('NBE_NO_ENCODER_OVERLAP') is None     # A/B switch (graph-captured small batches)
         self._overlap_styles = os.environ.get('NBE_NO_STREAM_OVERLAP') is None
+        self._overlap_encoder_all = os.environ.get('NBE_ENC_BRANCH_SMALL_ONLY') is None  # A/B switch: encoder as a graph branch below batch 32 only
         self._batch_sessions = {}
         self._batch_hits = {}
         self._force_overlap = False
@@ -281,10 +282,11 @@ class TriadPaintEngine:
                             G.prefetch_noise(B, positions)
                         ready = torch.cuda.Event()
                         ready.record(side)
-                    if B < 32 and torch.cuda.is_current_stream_capturing() and self._overlap_encoder:
-                        # small batches inside a CUDA graph: every kernel occupies a few SMs for ~20 us, so the encoder becomes a
-                        # third branch of the graph next to the synthesis blocks that do not read its features yet (b4 .. b16);
-                        # the flat path joins it in front of b32.conv0 (generator.InjectedGeometry.ready_event)
+                    if (B < 32 or self._overlap_encoder_all) and torch.cuda.is_current_stream_capturing() and self._overlap_encoder:
+                        # inside a CUDA graph the encoder becomes a third branch next to the synthesis blocks that do not read its
+                        # features yet (b4 .. b16: seven launches of ~20 us that occupy a few SMs each); the flat path joins it in
+                        # front of b32.conv0 (generator.InjectedGeometry.ready_event).  Batch 1: 0.40 -> 0.36 ms per stroke;
+                        # batch 256: 4.01 -> 3.92 ms per step (the small launches fill the tails of the encoder's kernels)
                         if self._enc_stream is None:
                             self._enc_stream = torch.cuda.Stream(device=self.device)
                         enc_s = self._enc_stream

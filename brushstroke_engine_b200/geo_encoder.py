@@ -62,6 +62,7 @@ class GeometryEncoder:
         self.max_cached_batch_sizes = 32
         self.max_cached_patches = 1024      # ... and only while their batch sizes sum to no more than this
         self._flat_s2 = os.environ.get('NBE_ENC_PER_TAP') is None      # A/B switch: strided layers on the per-tap kernel
+        self._flat_min = int(os.environ.get('NBE_ENC_FLAT_MIN', '32'))  # A/B switch: smallest output side of a strided layer on the flat kernel
         if mode == 'bf16':
             if cfg.in_channels != 1 or cfg.pre_filters <= 0 or cfg.pre_filters % 8 or cfg.preproc_type not in PREPROC_CODE:
                 raise RuntimeError('GeometryEncoder: the tensor-core path covers the sauto layout (1-channel input, 7x7 pre-layer)')
@@ -219,14 +220,14 @@ class GeometryEncoder:
                     y_ptr = nxt.data_ptr() + 2 * ((ho + 2) + 1) * y_cs
                     padded_out = nxt
                 cin = w.shape[1]
-                if stride == 2 and not up and self._flat_s2 and cin % 64 == 0 and cur.shape[3] == cin and cout % 128 == 0 and h % 2 == 0 and ho >= 32:
+                if stride == 2 and not up and self._flat_s2 and cin % 64 == 0 and cur.shape[3] == cin and cout % 128 == 0 and h % 2 == 0 and ho >= self._flat_min:
                     # down-sampling layer at its algorithmic cost: parity planes of the bordered input on the flat CTA-pair kernel
                     # (below 32^2 the per-image tiling pads too much; the per-tap kernel batches images into one tile)
                     _lib.call('nbe_conv3x3s2_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, h, h, cin, cout, y_cs, rp, ip,
                               _lib.ptr(b), slope, 1.0, -1.0, _lib.ptr(next_scale), st)
                 elif stride == 1 and self._flat_s2 and cout % 128 == 0 and ho >= 32:
                     # ScaleUp conv over the bordered bilinear map: 'valid' flat conv, one pass per 128 output channels
-                    _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cur.shape[3], cur.shape[3],
+                    _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cin, cur.shape[3],
                               cur.shape[2], 1, cout, y_cs, rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0, -1.0,
                               _lib.ptr(next_scale), st)
                 else:
