@@ -387,7 +387,9 @@ def main():
         # the reference's own stylization script runs with --feature_blending_level=2 (scripts/neube_stylize.sh): patches then
         # depend on their raster predecessors; wavefront-batched on one GPU (rank 0 only, the other ranks idle)
         blend_ms = None
-        if rank == 0 and not args.no_blend:
+        if not args.no_blend:
+            # the dependency chain (2 rows + cols wavefronts) is the critical path, so more GPUs do not shorten ONE blended canvas:
+            # with N ranks every rank renders its own canvas (replicas, no collective) and the line reports canvases per second
             btimes = []
             with torch.no_grad():
                 for rep in range(3):
@@ -398,7 +400,10 @@ def main():
                     torch.cuda.synchronize()
                     if rep > 0:
                         btimes.append((time.perf_counter() - t0) * 1e3)
-            blend_ms = float(np.median(btimes))
+            bt = torch.tensor([float(np.median(btimes))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+            blend_ms = float(bt[0])
         barrier()
         del d_guidance
         if size != 2000:
@@ -408,6 +413,7 @@ def main():
     #      (host uint8 patch in, host uint8 RGBA out; wall clock, rank 0) ----
     interactive_ms = None
     interactive_graph_ms = None
+    interactive_batched_ms = None
     if rank == 0 and not args.no_e2e:
         from brushstroke_engine_b200.engine import GanBrushOptions as _GBO
         patch = np.ascontiguousarray(((1.0 - synthetic.synthetic_patch(128, seed=5)[0, 0]) * 255).astype(np.uint8)[:, :, None])   # [W,W,1], 255 = stroke
@@ -431,6 +437,26 @@ def main():
             if i >= 10:
                 glat.append((time.perf_counter() - t0) * 1e3)
         interactive_graph_ms = float(np.median(glat))
+        # 32 concurrent sessions, one stroke each: one batched forward (server.StrokeBatcher) vs 32 single-patch calls
+        from brushstroke_engine_b200 import server
+        batcher = server.StrokeBatcher(engine)
+        sessions = [server.DrawingSession(engine, style_seed=k, batcher=batcher) for k in range(32)]
+        for s_ in sessions:
+            s_.on_message(json.dumps({'type': 'set_option', 'option': 'positions', 'value': True}))
+        rgba = np.zeros((128, 128, 4), dtype=np.uint8)
+        rgba[..., 3] = patch[..., 0]
+        blat = []
+        with torch.no_grad():
+            for i in range(25):
+                reqs = [server.encode_render_request(rgba, 64 + k, 32 + i, 10) for k in range(32)]
+                t0 = time.perf_counter()
+                for s_, m_ in zip(sessions, reqs):
+                    s_.on_message(m_)
+                answers = server.DrawingSession.flush_all(batcher, sessions)
+                if i >= 5:
+                    blat.append((time.perf_counter() - t0) * 1e3)
+                assert all(len(answers[s_]) == 1 for s_ in sessions)
+        interactive_batched_ms = float(np.median(blat))
     barrier()
     times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -490,10 +516,16 @@ def main():
         }
         if interactive_ms is not None:
             line['interactive'] = {'ms_per_stroke_patch': interactive_ms, 'ms_per_stroke_patch_cuda_graph': interactive_graph_ms,
+                                   'ms_per_32_sessions_batched': interactive_batched_ms,
+                                   'batched': '32 sessions x one binary render request each (wire decode -> ONE batched forward -> 32 encoded '
+                                              'responses), wall clock per round (server.StrokeBatcher)',
                                    'what': 'batch 1, host uint8 patch -> host uint8 RGBA, wall-clock median (rank 0): TriadPaintEngine.render_stroke (eager, ~60 launches) and InteractiveSession.render_stroke (one CUDA-graph replay)'}
         if canvas_ms is not None:
             line['canvas'] = dict(canvas_legs['main'])
             line['canvas'].update({'ms_feature_blending_level2_1gpu': blend_ms,
+                                   'blended_canvases_per_s': (world / (blend_ms * 1e-3)) if blend_ms else None,
+                                   'blended': 'feature_blending_level=2 (what scripts/neube_stylize.sh runs): one canvas per GPU, wavefront '
+                                              'schedule + one CUDA graph per wavefront size; max over ranks; canvases/s = n_gpus / that',
                                    'what': 'uint8 guidance on the device -> crops -> encoder+generator+composite (8-anchor z interpolation) -> '
                                            'every rank places its tiles into the canvas rows it owns -> one batched NCCL send/recv of those bands '
                                            'into the canvas on rank 0 (SURVEY 8d config 5); ms_host_to_host: host guidance in (each rank uploads '

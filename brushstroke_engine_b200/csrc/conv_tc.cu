@@ -181,6 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 //    but holds only HALF of every weight tile (64 of the 128 output channels), which halves the weight traffic per SM;
 //  * accumulators are double-buffered in TMEM (2 x 2 x 128 columns = all 512), so the epilogue of item i overlaps
 //    the MMAs of item i+1; per-image epilogue vectors (demod, bias, next-layer styles) are staged in smem.
+constexpr int R_THREADS = 320;                                      // TMA warp, MMA warp, 8 epilogue warps (4 per output row of the item)
 constexpr int R_ABUF = 17 * 1024;                                  // 130 px x 128 B = 16640 B, padded to a 1 KiB multiple
 constexpr int R_AROW_BYTES = 130 * 128;
 constexpr int R_BSTAGES = 8;
@@ -200,7 +201,7 @@ struct ConvRowParams {
     float* img; float* uvs; int write_y;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R_THREADS, 1)
 conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvRowParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -221,7 +222,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const bool leader = rank == 0;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1);
-                                      mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 8); }
+                                      mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 16); }
         for (int i = 0; i < R_BSTAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
@@ -312,10 +313,15 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
         }
     } else {
-        // ============================== epilogue (warps 2..5) ==============================
+        // ============================== epilogue (warps 2..9) ==============================
+        // One thread per output pixel and row: warps 2..5 take output row 0 of the item, warps 6..9 row 1 (TMEM lane quarter
+        // q = warp % 4, hardware rule).  With one epilogue warp per SM sub-partition (4 warps walking both rows in turn) the
+        // epilogue itself -- ~14 dependent instructions per channel value behind LDS / TMEM-load latencies nothing else covered --
+        // took longer per item than the MMAs and set the pace of the kernel; two warps per sub-partition hide each other's latencies.
         const int q = warp & 3;
+        const int er = (warp - 2) >> 2;                             // output row of the item this warp owns
         const int m = q * 32 + lane;                                // pixel x within the 128-px segment
-        const int et = threadIdx.x - 64;                            // 0..127
+        const int et = threadIdx.x - 64;                            // 0..255
         uint32_t acc_phase[2] = {0, 0};
         int it = 0, cur_n = -1;
         const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
@@ -329,22 +335,24 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const int yp = rem / p.items_per_row, xs = rem - yp * p.items_per_row;
             const int y0 = yp * 2, ox = xs * 128 + m;
             if (n != cur_n) {                                       // per-image epilogue vectors -> smem (epilogue warps only)
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone is done reading the previous image's vectors
-                s_vec[et] = p.dcoef ? p.dcoef[(long long)n * 128 + et] : 1.f;
-                s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
-                s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * 128 + et] : 1.f;
-                if (p.rgb_w) {
-                    const float st = p.rgb_styles[(long long)n * 128 + et];
-                    s_vec[384 + et] = p.rgb_w[et] * st; s_vec[512 + et] = p.rgb_w[128 + et] * st; s_vec[640 + et] = p.rgb_w[256 + et] * st;
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done reading the previous image's vectors
+                if (et < 128) {
+                    s_vec[et] = p.dcoef ? p.dcoef[(long long)n * 128 + et] : 1.f;
+                    s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
+                    s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * 128 + et] : 1.f;
+                } else if (p.rgb_w) {
+                    const int ec = et - 128;
+                    const float st = p.rgb_styles[(long long)n * 128 + ec];
+                    s_vec[384 + ec] = p.rgb_w[ec] * st; s_vec[512 + ec] = p.rgb_w[128 + ec] * st; s_vec[640 + ec] = p.rgb_w[256 + ec] * st;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_n = n;
             }
             mbar_wait(smem_u32(&acc_full[ab]), acc_phase[ab]);
             acc_phase[ab] ^= 1;
             tcgen05_fence_after();
-#pragma unroll 1
-            for (int r = 0; r < (dummy ? 0 : 2); ++r) {
+            if (!dummy) {
+                const int r = er;
                 const int oy = y0 + r;
                 float nz = 0.f;
                 if (p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
@@ -367,7 +375,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                         for (int h4 = 0; h4 < 2; ++h4) {
                             lds_f4(s_vec_u32 + (uint32_t)((ob + 4 * h4) * 4), dc + 4 * h4);
                             lds_f4(s_vec_u32 + (uint32_t)((128 + ob + 4 * h4) * 4), bs + 4 * h4);
-                            lds_f4(s_vec_u32 + (uint32_t)((256 + ob + 4 * h4) * 4), ns + 4 * h4);
+                            if (p.write_y) lds_f4(s_vec_u32 + (uint32_t)((256 + ob + 4 * h4) * 4), ns + 4 * h4);   // (the fused ToRGB launch does not store y)
                             if (p.rgb_w) {
                                 lds_f4(s_vec_u32 + (uint32_t)((384 + ob + 4 * h4) * 4), w0 + 4 * h4);
                                 lds_f4(s_vec_u32 + (uint32_t)((512 + ob + 4 * h4) * 4), w1 + 4 * h4);
@@ -386,7 +394,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                 if (p.rgb_w) {
                                     t0 = fmaf(a, w0[k], t0); t1 = fmaf(a, w1[k], t1); t2 = fmaf(a, w2[k], t2);
                                 }
-                                rr[h] = a * ns[k];
+                                rr[h] = p.write_y ? a * ns[k] : 0.f;
                             }
                             o2[e] = __floats2bfloat162_rn(rr[0], rr[1]);
                         }
@@ -730,7 +738,7 @@ static int conv_tc_impl(const void* x, const void* wq, void* y,
         });
         if (row_err != cudaSuccess) return fail(NBE_ECUDA, "conv_tc: cudaFuncSetAttribute(row128): %s", cudaGetErrorString(row_err));
         const int grid = (int)std::min<int64_t>(kNumSMs / 2, (total + 1) / 2) * 2;      // whole CTA pairs
-        conv_tc_row128_kernel<<<grid, TC_THREADS, rsmem, (cudaStream_t)stream>>>(ta, tb, r);
+        conv_tc_row128_kernel<<<grid, R_THREADS, rsmem, (cudaStream_t)stream>>>(ta, tb, r);
         return launched("conv_tc_row128_kernel");
     }
 
