@@ -42,8 +42,7 @@ namespace nbe {
 
 constexpr int F_MAX_ENT = 128;                                     // 9 taps x up to 14 K chunks (Cin <= 896)
 constexpr int F_MAX_CLASSES = 4;
-constexpr int F_THREADS = 320;                                     // TMA warp, MMA warp, 8 epilogue warps
-constexpr int F_EPI_WARPS = 8;
+constexpr int F_MAX_EPI_WARPS = 16;                                // TMA warp, MMA warp, EW = 8 or 16 epilogue warps (template parameter)
 constexpr int F_STAGE_BYTES = 32 * 64;                             // per epilogue warp: 32 positions x 32 channels
 constexpr int F_MAX_ABUF = 6;
 constexpr int F_BSTAGES = 6;
@@ -79,8 +78,8 @@ struct FlatParams {
     uint32_t idesc;
 };
 
-template <int EPI>   // 0: accumulators are stored as they are (bf16); 1: full SynthesisLayer epilogue
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
+template <int EPI, int EW>   // EPI 0: accumulators are stored as they are (bf16); 1: full SynthesisLayer epilogue.  EW: epilogue warps
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const FlatParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -92,8 +91,8 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int a_bytes = (p.n_boxes * p.box_rows * 128 + 1023) & ~1023;
     uint8_t* smem_a = smem;                                         // [n_abuf][window of one 64-channel chunk]
     uint8_t* smem_b = smem + p.n_abuf * a_bytes;                    // [b_tiles][8 KiB]: ring, or the resident phase weights
-    uint8_t* smem_stage = smem_b + p.b_tiles * F_BHALF;             // [F_EPI_WARPS][F_STAGE_BYTES] epilogue transposition buffers
-    float* s_vec = reinterpret_cast<float*>(smem_stage + F_EPI_WARPS * F_STAGE_BYTES);   // [3][128] (EPI == 1)
+    uint8_t* smem_stage = smem_b + p.b_tiles * F_BHALF;             // [EW][F_STAGE_BYTES] epilogue transposition buffers
+    float* s_vec = reinterpret_cast<float*>(smem_stage + EW * F_STAGE_BYTES);   // [3][128] (EPI == 1)
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + (EPI == 1 ? 3 * 128 : 0));
     uint64_t* a_full = bars;                            // [F_MAX_ABUF]  (the leader's is the live one)
     uint64_t* a_empty = a_full + F_MAX_ABUF;            // [F_MAX_ABUF]
@@ -112,7 +111,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (threadIdx.x == 0) {
         for (int i = 0; i < F_MAX_ABUF; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
         for (int i = 0; i < F_BSTAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 2 * F_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 2 * EW); }
         mbar_init(smem_u32(res_full), 1); mbar_init(smem_u32(res_free), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
@@ -177,8 +176,8 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     if (!p.resident)
                         for (; e < e1 && p.ent_c[e] == c; ++e) {
-                            const int bs = (int)(bcnt % F_BSTAGES);
-                            const uint32_t bpar = (bcnt / F_BSTAGES) & 1u;
+                            const int bs = (int)(bcnt % (uint32_t)p.b_tiles);
+                            const uint32_t bpar = (bcnt / (uint32_t)p.b_tiles) & 1u;
                             ++bcnt;
                             mbar_wait_fast(smem_u32(&b_empty[bs]), bpar ^ 1);
                             const uint32_t bf = smem_u32(&b_full[bs]);
@@ -198,6 +197,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t idesc = p.idesc;
             const int T = p.T, k_chunks = p.k_chunks, n_abuf = p.n_abuf, cpp = p.cpp, last_steps = p.last_steps;
             const bool resident = p.resident != 0;
+            const int b_ring = p.b_tiles;
             uint32_t acc_par0 = 0, acc_par1 = 0;
             int slot = 0; uint32_t a_par = 0;
             int bs = 0; uint32_t b_par = 0;
@@ -256,7 +256,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             }
                             if (!resident) umma_commit_2sm(smem_u32(&b_empty[bs]));
                         }
-                        if (!resident) { if (++bs == F_BSTAGES) { bs = 0; b_par ^= 1; } }
+                        if (!resident) { if (++bs == b_ring) { bs = 0; b_par ^= 1; } }
                         ++e; w = wn;
                     }
                     if (elect_one()) umma_commit_2sm(smem_u32(&a_empty[slot]));
@@ -269,12 +269,15 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else {
         // ============================== epilogue (warps 2..9, both CTAs) ==============================
-        // The epilogue has 4x less MMA time to hide behind than in an ordinary 3x3 conv (2.25 taps per class tile), so it
-        // runs on 8 warps: TMEM lane quarter qd = warp % 4 (hardware rule), channel half hsel = (warp - 2) / 4.
+        // The epilogue has 4x less MMA time to hide behind than in an ordinary 3x3 conv (2.25 taps per class tile), and even
+        // for ordinary convs it is what sets the pace when each SM sub-partition holds few epilogue warps (~14 dependent
+        // instructions per value behind TMEM-load / LDS latencies): it runs on EW = 8 or 16 warps: TMEM lane quarter
+        // qd = warp % 4 (hardware rule), channel slice hsel = (warp - 2) / 4 of 128 / (EW / 4) channels.
         // A TMEM lane (= position) is owned by one thread, but a position's channels are contiguous bytes of the output:
         // storing them straight from the owning lanes costs one wavefront per lane and instruction.  Each warp therefore
         // transposes 32 positions x 32 channels through a swizzled shared-memory buffer and writes 64-byte runs
         // (4 lanes per position, 8 positions per instruction).
+        constexpr int NC32 = 128 / (EW / 4) / 32;                       // 32-column TMEM chunks per warp and class tile: 2 (EW = 8) or 1 (EW = 16)
         const int qd = warp & 3, hsel = (warp - 2) >> 2;
         const int m = qd * 32 + lane;
         const int et = threadIdx.x - 64;
@@ -296,13 +299,13 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int G = p.ph_G[ph];
             const int ab = (p.nbuf == 2) ? (s & 1) : 0;
             if (EPI == 1 && n != cur_n) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" :: "n"(EW * 32) : "memory");
                 if (et < 128) {
                     s_vec[et] = p.dcoef ? p.dcoef[(long long)n * p.vec_stride + et] : 1.f;
                     s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
                     s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * p.vec_stride + et] : 1.f;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" :: "n"(EW * 32) : "memory");
                 cur_n = n;
             }
             mbar_wait(smem_u32(&acc_full[ab]), acc_phase[ab]);
@@ -326,16 +329,16 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int r8 = 0; r8 < 4; ++r8) rp[r8] = __shfl_sync(0xffffffffu, pix, r8 * 8 + rd_row0);
                         // both 32-column halves of this warp's 64 channels are requested before the one wait
-                        uint32_t vv[2][32];
+                        uint32_t vv[NC32][32];
                         {
-                            const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * set_cols + (i * G + gl) * 128 + hsel * 64);
+                            const uint32_t ta = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * set_cols + (i * G + gl) * 128 + hsel * (NC32 * 32));
                             tmem_ld32_nowait(ta, vv[0]);
-                            tmem_ld32_nowait(ta + 32, vv[1]);
+                            if (NC32 == 2) tmem_ld32_nowait(ta + 32, vv[NC32 - 1]);
                             tmem_ld_wait();
                         }
 #pragma unroll
-                        for (int c32 = 0; c32 < 2; ++c32) {
-                            const int c0 = hsel * 64 + c32 * 32;
+                        for (int c32 = 0; c32 < NC32; ++c32) {
+                            const int c0 = hsel * (NC32 * 32) + c32 * 32;
                             uint32_t (&v)[32] = vv[c32];
 #pragma unroll
                             for (int gg = 0; gg < 4; ++gg) {
@@ -478,7 +481,8 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     const size_t limit = 227 * 1024;
     static const bool no_resident = getenv("NBE_FLAT_NO_RESIDENT") != nullptr;
     const size_t a_bytes = ((size_t)p.n_boxes * p.box_rows * 128 + 1023) & ~(size_t)1023;
-    const size_t epi_bytes = F_EPI_WARPS * F_STAGE_BYTES + (raw ? 0 : 3 * 128 * sizeof(float)) + 256;
+    static const int epi_warps = (getenv("NBE_FLAT_EPI16") != nullptr) ? 16 : 8;      // A/B switch: 16 epilogue warps (measured 3-7 % slower: the windows lose a buffer)
+    const size_t epi_bytes = (size_t)epi_warps * F_STAGE_BYTES + (raw ? 0 : 3 * 128 * sizeof(float)) + 256;
     CUtensorMap ta, tb;
     if (in.planes) {
         // (pixel pair x channels, X', row parity, Y', image) over the padded NHWC image
@@ -505,8 +509,10 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     static std::once_flag once;
     static cudaError_t err = cudaSuccess;
     std::call_once(once, [] {
-        err = cudaFuncSetAttribute(conv_tc_flat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        err = cudaFuncSetAttribute(conv_tc_flat_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "conv_flat: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     const int64_t pairs = (int64_t)((in.N + 1) / 2) * p.items_per_img;
@@ -516,14 +522,22 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     p.contiguous = round_robin ? 0 : 1;
     p.resident = !no_resident && pairs >= 2 * (int64_t)(grid / 2) && epi_bytes + (size_t)max_phase_tiles * F_BHALF + 3 * a_bytes <= limit;
     p.b_tiles = p.resident ? max_phase_tiles : F_BSTAGES;
+    // streamed weights: a ring of 4 tiles instead of 6 when that buys one more window buffer (windows take longer to arrive)
+    if (!p.resident && (limit - epi_bytes - 4 * F_BHALF) / a_bytes > (limit - epi_bytes - (size_t)F_BSTAGES * F_BHALF) / a_bytes
+        && (limit - epi_bytes - (size_t)F_BSTAGES * F_BHALF) / a_bytes < F_MAX_ABUF) p.b_tiles = 4;
     const size_t rest = epi_bytes + (size_t)p.b_tiles * F_BHALF;
     if (rest + 2 * a_bytes > limit) return fail(NBE_EUNSUPPORTED, "conv_flat: window of %d rows does not fit in shared memory", win_rows);
     p.n_abuf = (int)std::min<size_t>(F_MAX_ABUF, (limit - rest) / a_bytes);
     p.smem_need = (uint32_t)(rest + (size_t)p.n_abuf * a_bytes);
     // the kernel aligns its base to 1 KiB; dynamic shared memory normally starts aligned, so the slack is only added when it fits
     const size_t smem = std::min(limit, (size_t)p.smem_need + 1024);
-    if (raw) conv_tc_flat_kernel<0><<<grid, F_THREADS, smem, stream>>>(ta, tb, p);
-    else     conv_tc_flat_kernel<1><<<grid, F_THREADS, smem, stream>>>(ta, tb, p);
+    if (epi_warps == 8) {
+        if (raw) conv_tc_flat_kernel<0, 8><<<grid, 64 + 8 * 32, smem, stream>>>(ta, tb, p);
+        else     conv_tc_flat_kernel<1, 8><<<grid, 64 + 8 * 32, smem, stream>>>(ta, tb, p);
+    } else {
+        if (raw) conv_tc_flat_kernel<0, 16><<<grid, 64 + 16 * 32, smem, stream>>>(ta, tb, p);
+        else     conv_tc_flat_kernel<1, 16><<<grid, 64 + 16 * 32, smem, stream>>>(ta, tb, p);
+    }
     return launched("conv_tc_flat_kernel");
 }
 
