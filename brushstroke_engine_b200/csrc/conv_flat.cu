@@ -68,7 +68,6 @@ struct FlatParams {
     int nbuf;                                                       // accumulator sets in TMEM: 2 (epilogue overlaps the next MMAs) or 1
     // planes: A chunks are 64 channels of one parity plane of a padded NHWC image (stride-2 convs); cpp = chunks per plane
     int planes, cpp, plane_C, plane_rows;
-    int last_steps;                                                 // K = 16 MMA steps of the last 64-channel chunk: ceil((Cin % 64 or 64) / 16)
     int cout_off;                                                   // first output channel of this launch within the weight tiles
     uint32_t smem_need;
     int y_cs; long long y_row_pitch, y_img_pitch; int noise_w;
@@ -78,7 +77,11 @@ struct FlatParams {
     uint32_t idesc;
 };
 
-template <int EPI, int EW>   // EPI 0: accumulators are stored as they are (bf16); 1: full SynthesisLayer epilogue.  EW: epilogue warps
+// EPI 0: accumulators are stored as they are (bf16); 1: full SynthesisLayer epilogue.  EW: epilogue warps.  RES: the phase
+// weights are resident in shared memory; TT: position tiles per item -- both compile-time because the single MMA-issuing
+// warp sets the pace of this kernel (ncu: ~600 cycles of issue loop per 4-MMA entry against 256 cycles of tensor work, no
+// barrier ever blocking it), so every runtime branch inside its loop costs throughput.
+template <int EPI, int EW, bool RES, int TT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const FlatParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -125,7 +128,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     cluster_sync_all();                                             // barriers of BOTH CTAs are initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
-    const int set_cols = p.T * p.Gmax * 128;                        // TMEM columns of one accumulator set
+    const int set_cols = TT * p.Gmax * 128;                           // TMEM columns of one accumulator set
     // schedule of this pair: n_local item pairs x n_phases, item-major (streamed weights) or phase-major (resident weights).
     // Pair j = (image pair j / items_per_img, tile j % items_per_img): CTA r takes that tile of image 2 * (j / items_per_img) + r,
     // so both CTAs share q0 and with it every descriptor offset (the last image pair may hold a dummy).
@@ -148,9 +151,9 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int j = j_first + k * j_step;
                 const int np = j / p.items_per_img;
                 const int n = min(2 * np + rank, p.N - 1);                       // dummy: loads stay in range, nothing is stored
-                const int q0 = (j - np * p.items_per_img) * p.T * 128;
+                const int q0 = (j - np * p.items_per_img) * TT * 128;
                 const int e0 = p.ph_e0[ph], e1 = p.ph_e1[ph];
-                if (p.resident && k == 0) {
+                if (RES && k == 0) {
                     if (ph > 0) mbar_wait(smem_u32(res_free), (uint32_t)((ph - 1) & 1));   // previous phase's MMAs are done with smem_b
                     const uint32_t rf = smem_u32(res_full);
                     if (leader) mbar_expect_tx(rf, 2u * (uint32_t)(e1 - e0) * F_BHALF);
@@ -174,7 +177,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             tma_load_3d_2sm(smem_u32(smem_a + slot * a_bytes + b * p.box_rows * 128), &tmap_a, full, c * 64,
                                             q0 + p.min_shift + b * p.box_rows, n);
                     }
-                    if (!p.resident)
+                    if (!RES)
                         for (; e < e1 && p.ent_c[e] == c; ++e) {
                             const int bs = (int)(bcnt % (uint32_t)p.b_tiles);
                             const uint32_t bpar = (bcnt / (uint32_t)p.b_tiles) & 1u;
@@ -185,7 +188,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             tma_load_3d_2sm(smem_u32(smem_b + bs * F_BHALF), &tmap_b, bf, p.ent_bk[e] * 64, p.cout_off + rank * 64, p.ent_btile[e]);
                         }
                 }
-                if (p.resident) { if (++k == n_local) { k = 0; ++ph; } }
+                if (RES) { if (++k == n_local) { k = 0; ++ph; } }
                 else            { if (++ph == p.n_phases) { ph = 0; ++k; } }
             }
         }
@@ -195,8 +198,9 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a)), b_lo0 = umma_desc_lo(smem_u32(smem_b));
             const uint32_t a_step = (uint32_t)a_bytes >> 4;
             const uint32_t idesc = p.idesc;
-            const int T = p.T, k_chunks = p.k_chunks, n_abuf = p.n_abuf, cpp = p.cpp, last_steps = p.last_steps;
-            const bool resident = p.resident != 0;
+            constexpr int T = TT;
+            const int k_chunks = p.k_chunks, n_abuf = p.n_abuf;
+            constexpr bool resident = RES;
             const int b_ring = p.b_tiles;
             uint32_t acc_par0 = 0, acc_par1 = 0;
             int slot = 0; uint32_t a_par = 0;
@@ -220,15 +224,10 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t d_tile = (uint32_t)(G * 128);
                 int e = e0;
                 uint32_t w = p.ent_w[e0];
-                int c_in_plane = 0;
                 for (int c = 0; c < k_chunks; ++c) {
                     mbar_wait_fast(smem_u32(&a_full[slot]), a_par);
                     tcgen05_fence_after();
                     const uint32_t a_lo = a_lo0 + (uint32_t)slot * a_step + row0 * 8u;
-                    // K = 16 steps of this chunk: the last chunk of a (plane's) channel range holds Cin % 64 real channels, the
-                    // rest is zero padding on both operands -- MMAs over it would add exact zeros
-                    const int steps = (c_in_plane == cpp - 1) ? last_steps : 4;
-                    if (++c_in_plane == cpp) c_in_plane = 0;
                     while (e < e1 && (int)(w >> 27) == c) {
                         const uint32_t wn = p.ent_w[e + 1];          // next entry (the table has a sentinel), fetched ahead of the issue
                         uint32_t b_lo;
@@ -249,9 +248,9 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                     const uint32_t al = al0 + (uint32_t)(i * 1024);
                                     const uint32_t d = dd + (uint32_t)i * d_tile;
                                     umma_bf16_lo_2sm(d, al, b_lo, idesc, acc0);
-                                    if (steps > 1) umma_bf16_lo_2sm(d, al + 2, b_lo + 2, idesc, 1u);
-                                    if (steps > 2) umma_bf16_lo_2sm(d, al + 4, b_lo + 4, idesc, 1u);
-                                    if (steps > 3) umma_bf16_lo_2sm(d, al + 6, b_lo + 6, idesc, 1u);
+                                    umma_bf16_lo_2sm(d, al + 2, b_lo + 2, idesc, 1u);
+                                    umma_bf16_lo_2sm(d, al + 4, b_lo + 4, idesc, 1u);
+                                    umma_bf16_lo_2sm(d, al + 6, b_lo + 6, idesc, 1u);
                                 }
                             }
                             if (!resident) umma_commit_2sm(smem_u32(&b_empty[bs]));
@@ -295,7 +294,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int np = j / p.items_per_img;
             const bool dummy = 2 * np + rank >= p.N;
             const int n = min(2 * np + rank, p.N - 1);
-            const int q0 = (j - np * p.items_per_img) * p.T * 128;
+            const int q0 = (j - np * p.items_per_img) * TT * 128;
             const int G = p.ph_G[ph];
             const int ab = (p.nbuf == 2) ? (s & 1) : 0;
             if (EPI == 1 && n != cur_n) {
@@ -313,7 +312,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tcgen05_fence_after();
             if (!dummy) {
 #pragma unroll 1
-                for (int i = 0; i < p.T; ++i) {
+                for (int i = 0; i < TT; ++i) {
                     const int q = q0 + i * 128 + m;
                     const int gy = q / p.P, gx = q - gy * p.P;
 #pragma unroll 1
@@ -393,7 +392,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(smem_u32(&acc_empty[ab]));
-            if (p.resident) { if (++k == n_local) { k = 0; ++ph; } }
+            if (RES) { if (++k == n_local) { k = 0; ++ph; } }
             else            { if (++ph == p.n_phases) { ph = 0; ++k; } }
         }
     }
@@ -421,8 +420,6 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     const int cpp = Cin_pad / 64;
     p.planes = in.planes; p.cpp = cpp; p.plane_C = in.Cin;
     p.k_chunks = in.planes ? 4 * cpp : cpp;
-    static const bool full_k = getenv("NBE_FLAT_FULL_K") != nullptr;      // A/B switch: MMAs over the zero padding of the last chunk too
-    p.last_steps = full_k ? 4 : (in.Cin - (cpp - 1) * 64 + 15) / 16;
     // expand the tap program into entries sorted by chunk within each phase
     int ntaps = 0;
     for (int ph = 0; ph < p.n_phases; ++ph) ntaps += phase_ntaps[ph];
@@ -481,7 +478,7 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     const size_t limit = 227 * 1024;
     static const bool no_resident = getenv("NBE_FLAT_NO_RESIDENT") != nullptr;
     const size_t a_bytes = ((size_t)p.n_boxes * p.box_rows * 128 + 1023) & ~(size_t)1023;
-    static const int epi_warps = (getenv("NBE_FLAT_EPI16") != nullptr) ? 16 : 8;      // A/B switch: 16 epilogue warps (measured 3-7 % slower: the windows lose a buffer)
+    constexpr int epi_warps = 8;                                    // (16 measured 3-7 % slower: the windows lose a buffer)
     const size_t epi_bytes = (size_t)epi_warps * F_STAGE_BYTES + (raw ? 0 : 3 * 128 * sizeof(float)) + 256;
     CUtensorMap ta, tb;
     if (in.planes) {
@@ -506,13 +503,15 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
         int st = make_tmap(&tb, wq, 3, dims, strides, box, "weights");
         if (st) return st;
     }
+    using KernelFn = void (*)(CUtensorMap, CUtensorMap, FlatParams);
+    static KernelFn kernels[2][2][2] = {       // [EPI][RES][T - 1]
+        {{conv_tc_flat_kernel<0, 8, false, 1>, conv_tc_flat_kernel<0, 8, false, 2>}, {conv_tc_flat_kernel<0, 8, true, 1>, conv_tc_flat_kernel<0, 8, true, 2>}},
+        {{conv_tc_flat_kernel<1, 8, false, 1>, conv_tc_flat_kernel<1, 8, false, 2>}, {conv_tc_flat_kernel<1, 8, true, 1>, conv_tc_flat_kernel<1, 8, true, 2>}}};
     static std::once_flag once;
     static cudaError_t err = cudaSuccess;
     std::call_once(once, [] {
-        err = cudaFuncSetAttribute(conv_tc_flat_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (err == cudaSuccess) err = cudaFuncSetAttribute(conv_tc_flat_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        for (int i = 0; i < 8 && err == cudaSuccess; ++i)
+            err = cudaFuncSetAttribute((const void*)kernels[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "conv_flat: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     const int64_t pairs = (int64_t)((in.N + 1) / 2) * p.items_per_img;
@@ -531,13 +530,8 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     p.smem_need = (uint32_t)(rest + (size_t)p.n_abuf * a_bytes);
     // the kernel aligns its base to 1 KiB; dynamic shared memory normally starts aligned, so the slack is only added when it fits
     const size_t smem = std::min(limit, (size_t)p.smem_need + 1024);
-    if (epi_warps == 8) {
-        if (raw) conv_tc_flat_kernel<0, 8><<<grid, 64 + 8 * 32, smem, stream>>>(ta, tb, p);
-        else     conv_tc_flat_kernel<1, 8><<<grid, 64 + 8 * 32, smem, stream>>>(ta, tb, p);
-    } else {
-        if (raw) conv_tc_flat_kernel<0, 16><<<grid, 64 + 16 * 32, smem, stream>>>(ta, tb, p);
-        else     conv_tc_flat_kernel<1, 16><<<grid, 64 + 16 * 32, smem, stream>>>(ta, tb, p);
-    }
+    if (p.T != 1 && p.T != 2) return fail(NBE_EUNSUPPORTED, "conv_flat: 1 or 2 tiles per item");
+    kernels[raw ? 0 : 1][p.resident ? 1 : 0][p.T - 1]<<<grid, 64 + epi_warps * 32, smem, stream>>>(ta, tb, p);
     return launched("conv_tc_flat_kernel");
 }
 
