@@ -42,7 +42,6 @@ namespace nbe {
 
 constexpr int F_MAX_ENT = 128;                                     // 9 taps x up to 14 K chunks (Cin <= 896)
 constexpr int F_MAX_CLASSES = 4;
-constexpr int F_MAX_EPI_WARPS = 16;                                // TMA warp, MMA warp, EW = 8 or 16 epilogue warps (template parameter)
 constexpr int F_STAGE_BYTES = 32 * 64;                             // per epilogue warp: 32 positions x 32 channels
 constexpr int F_MAX_ABUF = 6;
 constexpr int F_BSTAGES = 6;
@@ -77,11 +76,67 @@ struct FlatParams {
     uint32_t idesc;
 };
 
+// Compile-time tap programs of the two launches that dominate (PROG 1: 3x3 convolution, PROG 2: transposed 3x3 stride-2
+// convolution).  For them the MMA warp does not walk the entry table: its per-chunk loop is fully unrolled, every tap's row
+// shift is (ay * P + ax) rows with ay, ax known at compile time, accumulator column and the "first MMA of an accumulator"
+// flag are immediates -- the SASS is UTCHMMAs with a few uniform adds in between, as in conv_tc_row128_kernel.  The host
+// checks the entry table it built against these functions before it selects PROG != 0 (launch_flat).
+__host__ __device__ constexpr int prog_phases(int prog) { return prog == 2 ? 2 : 1; }
+__host__ __device__ constexpr int prog_ntaps(int prog, int ph) { return prog == 1 ? 9 : (ph == 0 ? 5 : 4); }
+__host__ __device__ constexpr int prog_G(int prog) { return prog == 2 ? 2 : 1; }
+// transposed conv: class (py, px) sums the taps kh = py, kw = px (mod 2) over x[Y - (kh - py) / 2, X - (kw - px) / 2]; the
+// window starts P + 1 rows before the tile, so a tap reads rows shifted by ((1 - dy) * P + (1 - dx))
+__host__ __device__ constexpr int prog_ay(int prog, int ph, int t) {
+    if (prog == 1) return t / 3;
+    if (ph == 0) return (t == 0 || t == 1 || t == 4) ? 1 : 0;       // (0,0): kh = 0,0,2,2 ; (1,1): kh = 1
+    return (t == 0 || t == 2 || t == 3) ? 1 : 0;                    // (0,1): kh = 0,2 ; (1,0): kh = 1,1
+}
+__host__ __device__ constexpr int prog_ax(int prog, int ph, int t) {
+    if (prog == 1) return t % 3;
+    if (ph == 0) return (t == 0 || t == 2 || t == 4) ? 1 : 0;       // (0,0): kw = 0,2,0,2 ; (1,1): kw = 1
+    return (t == 0 || t == 1 || t == 2) ? 1 : 0;                    // (0,1): kw = 1,1 ; (1,0): kw = 0,2
+}
+__host__ __device__ constexpr int prog_acc(int prog, int ph, int t) { return prog == 1 ? 0 : (ph == 0 ? (t == 4 ? 1 : 0) : (t >= 2 ? 1 : 0)); }
+__host__ __device__ constexpr int prog_first(int prog, int ph, int t) { return prog == 1 ? (t == 0) : (ph == 0 ? (t == 0 || t == 4) : (t == 0 || t == 2)); }
+
+// all taps of one 64-channel chunk of phase PH, issued by the elected lane of the MMA warp
+template <int PROG, int PH, bool RES, int TT>
+__device__ __forceinline__ void issue_chunk_prog(uint32_t a_lo, uint32_t row1, uint32_t row2, uint32_t b_lo0, uint32_t b_res, uint32_t d0, uint32_t idesc,
+                                                 bool later_chunk, int& bs, uint32_t& b_par, int b_ring, uint64_t* b_full, uint64_t* b_empty) {
+    constexpr int NT = prog_ntaps(PROG, PH), G = prog_G(PROG);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const int ay = prog_ay(PROG, PH, t), ax = prog_ax(PROG, PH, t), acc = prog_acc(PROG, PH, t), first = prog_first(PROG, PH, t);
+        uint32_t b_lo;
+        if (RES) b_lo = b_res + (uint32_t)(t * (F_BHALF >> 4));
+        else {
+            mbar_wait_fast(smem_u32(&b_full[bs]), b_par);
+            tcgen05_fence_after();
+            b_lo = b_lo0 + (uint32_t)bs * (F_BHALF >> 4);
+        }
+        const uint32_t al0 = a_lo + (ay == 0 ? 0u : (ay == 1 ? row1 : row2)) + (uint32_t)(ax * 8);
+        const uint32_t acc0 = first ? (later_chunk ? 1u : 0u) : 1u;
+        if (elect_one()) {
+#pragma unroll
+            for (int i = 0; i < TT; ++i) {
+                const uint32_t al = al0 + (uint32_t)(i * 1024);
+                const uint32_t d = d0 + (uint32_t)((i * G + acc) * 128);
+                umma_bf16_lo_2sm(d, al, b_lo, idesc, acc0);
+                umma_bf16_lo_2sm(d, al + 2, b_lo + 2, idesc, 1u);
+                umma_bf16_lo_2sm(d, al + 4, b_lo + 4, idesc, 1u);
+                umma_bf16_lo_2sm(d, al + 6, b_lo + 6, idesc, 1u);
+            }
+            if (!RES) umma_commit_2sm(smem_u32(&b_empty[bs]));
+        }
+        if (!RES) { if (++bs == b_ring) { bs = 0; b_par ^= 1; } }
+    }
+}
+
 // EPI 0: accumulators are stored as they are (bf16); 1: full SynthesisLayer epilogue.  EW: epilogue warps.  RES: the phase
 // weights are resident in shared memory; TT: position tiles per item -- both compile-time because the single MMA-issuing
 // warp sets the pace of this kernel (ncu: ~600 cycles of issue loop per 4-MMA entry against 256 cycles of tensor work, no
 // barrier ever blocking it), so every runtime branch inside its loop costs throughput.
-template <int EPI, int EW, bool RES, int TT>
+template <int EPI, int EW, bool RES, int TT, int PROG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const FlatParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -224,6 +279,25 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t d_tile = (uint32_t)(G * 128);
                 int e = e0;
                 uint32_t w = p.ent_w[e0];
+                if (PROG != 0) {
+                    // compile-time tap program: row shifts are (ay * P + ax) rows, ay, ax in {0, 1, 2}
+                    const uint32_t row1 = (uint32_t)p.P * 8u, row2 = (uint32_t)p.P * 16u;
+                    uint32_t b_res = b_lo0;
+                    for (int c = 0; c < k_chunks; ++c) {
+                        mbar_wait_fast(smem_u32(&a_full[slot]), a_par);
+                        tcgen05_fence_after();
+                        const uint32_t a_lo = a_lo0 + (uint32_t)slot * a_step;
+                        if (prog_phases(PROG) == 1 || ph == 0) {
+                            issue_chunk_prog<PROG, 0, RES, TT>(a_lo, row1, row2, b_lo0, b_res, d0, idesc, c != 0, bs, b_par, b_ring, b_full, b_empty);
+                            b_res += (uint32_t)(prog_ntaps(PROG, 0) * (F_BHALF >> 4));
+                        } else {
+                            issue_chunk_prog<PROG, 1, RES, TT>(a_lo, row1, row2, b_lo0, b_res, d0, idesc, c != 0, bs, b_par, b_ring, b_full, b_empty);
+                            b_res += (uint32_t)(prog_ntaps(PROG, 1) * (F_BHALF >> 4));
+                        }
+                        if (elect_one()) umma_commit_2sm(smem_u32(&a_empty[slot]));
+                        if (++slot == n_abuf) { slot = 0; a_par ^= 1; }
+                    }
+                } else
                 for (int c = 0; c < k_chunks; ++c) {
                     mbar_wait_fast(smem_u32(&a_full[slot]), a_par);
                     tcgen05_fence_after();
@@ -415,7 +489,7 @@ struct FlatInput {
 };
 
 static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_cout, FlatParams& p, const FlatTap* taps, const int* phase_ntaps,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int prog = 0) {
     const int Cin_pad = (in.Cin + 63) / 64 * 64;
     const int cpp = Cin_pad / 64;
     p.planes = in.planes; p.cpp = cpp; p.plane_C = in.Cin;
@@ -504,14 +578,22 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
         if (st) return st;
     }
     using KernelFn = void (*)(CUtensorMap, CUtensorMap, FlatParams);
-    static KernelFn kernels[2][2][2] = {       // [EPI][RES][T - 1]
-        {{conv_tc_flat_kernel<0, 8, false, 1>, conv_tc_flat_kernel<0, 8, false, 2>}, {conv_tc_flat_kernel<0, 8, true, 1>, conv_tc_flat_kernel<0, 8, true, 2>}},
-        {{conv_tc_flat_kernel<1, 8, false, 1>, conv_tc_flat_kernel<1, 8, false, 2>}, {conv_tc_flat_kernel<1, 8, true, 1>, conv_tc_flat_kernel<1, 8, true, 2>}}};
+    static KernelFn generic[2][2][2] = {       // [EPI][RES][T - 1], entry-table MMA loop
+        {{conv_tc_flat_kernel<0, 8, false, 1, 0>, conv_tc_flat_kernel<0, 8, false, 2, 0>}, {conv_tc_flat_kernel<0, 8, true, 1, 0>, conv_tc_flat_kernel<0, 8, true, 2, 0>}},
+        {{conv_tc_flat_kernel<1, 8, false, 1, 0>, conv_tc_flat_kernel<1, 8, false, 2, 0>}, {conv_tc_flat_kernel<1, 8, true, 1, 0>, conv_tc_flat_kernel<1, 8, true, 2, 0>}}};
+    static KernelFn conv_prog[2] = {conv_tc_flat_kernel<1, 8, false, 2, 1>, conv_tc_flat_kernel<1, 8, true, 2, 1>};          // [RES]: 3x3 conv, full epilogue, T = 2
+    static KernelFn convt_prog[2][2] = {{conv_tc_flat_kernel<0, 8, false, 1, 2>, conv_tc_flat_kernel<0, 8, false, 2, 2>},     // [RES][T - 1]: transposed conv, raw epilogue
+                                        {conv_tc_flat_kernel<0, 8, true, 1, 2>, conv_tc_flat_kernel<0, 8, true, 2, 2>}};
     static std::once_flag once;
     static cudaError_t err = cudaSuccess;
     std::call_once(once, [] {
-        for (int i = 0; i < 8 && err == cudaSuccess; ++i)
-            err = cudaFuncSetAttribute((const void*)kernels[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        KernelFn all[14];
+        int n = 0;
+        for (int i = 0; i < 8; ++i) all[n++] = generic[i >> 2][(i >> 1) & 1][i & 1];
+        all[n++] = conv_prog[0]; all[n++] = conv_prog[1];
+        for (int i = 0; i < 4; ++i) all[n++] = convt_prog[i >> 1][i & 1];
+        for (int i = 0; i < n && err == cudaSuccess; ++i)
+            err = cudaFuncSetAttribute((const void*)all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "conv_flat: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     const int64_t pairs = (int64_t)((in.N + 1) / 2) * p.items_per_img;
@@ -531,7 +613,26 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     // the kernel aligns its base to 1 KiB; dynamic shared memory normally starts aligned, so the slack is only added when it fits
     const size_t smem = std::min(limit, (size_t)p.smem_need + 1024);
     if (p.T != 1 && p.T != 2) return fail(NBE_EUNSUPPORTED, "conv_flat: 1 or 2 tiles per item");
-    kernels[raw ? 0 : 1][p.resident ? 1 : 0][p.T - 1]<<<grid, 64 + epi_warps * 32, smem, stream>>>(ta, tb, p);
+    // compile-time tap program, if the entry table is exactly what it encodes (and the epilogue / tile variant is instantiated)
+    static const bool table_only = getenv("NBE_FLAT_TABLE") != nullptr;          // A/B switch: always walk the entry table
+    int use_prog = table_only ? 0 : prog;
+    if (use_prog == 1 && (raw || p.T != 2)) use_prog = 0;
+    if (use_prog == 2 && !raw) use_prog = 0;
+    if (use_prog && (in.planes || p.n_phases != prog_phases(use_prog))) use_prog = 0;
+    for (int ph = 0; use_prog && ph < p.n_phases; ++ph) {
+        const int nt = use_prog == 1 ? prog_ntaps(1, 0) : prog_ntaps(2, ph);
+        if (p.ph_e1[ph] - p.ph_e0[ph] != nt * p.k_chunks || p.ph_G[ph] != prog_G(use_prog)) { use_prog = 0; break; }
+        for (int c = 0; use_prog && c < p.k_chunks; ++c)
+            for (int t = 0; t < nt; ++t) {
+                const int e_ = p.ph_e0[ph] + c * nt + t;
+                const int ay = prog_ay(use_prog, ph, t), ax = prog_ax(use_prog, ph, t);
+                if (p.ent_c[e_] != c || p.ent_shift[e_] - p.min_shift != ay * p.P + ax || p.ent_acc[e_] != prog_acc(use_prog, ph, t) ||
+                    p.ent_first[e_] != (c == 0 && prog_first(use_prog, ph, t) ? 1 : 0)) { use_prog = 0; break; }
+            }
+    }
+    KernelFn fn = use_prog == 1 ? conv_prog[p.resident ? 1 : 0] : use_prog == 2 ? convt_prog[p.resident ? 1 : 0][p.T - 1]
+                                : generic[raw ? 0 : 1][p.resident ? 1 : 0][p.T - 1];
+    fn<<<grid, 64 + epi_warps * 32, smem, stream>>>(ta, tb, p);
     return launched("conv_tc_flat_kernel");
 }
 
@@ -568,7 +669,7 @@ extern "C" int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
         p.next_scale = next_scale ? next_scale + co : nullptr;
         const int in_rows = valid ? OH + 2 : OH;
         FlatInput in{x, N, Cin, x_cs, in_rows * x_pitch, 0, 0, 0};
-        int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream);
+        int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream, 1);
         if (st) return st;
     }
     return NBE_OK;
@@ -659,7 +760,7 @@ extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_o
     p.dcoef = dcoef ? dcoef + co : nullptr; p.noise = nullptr; p.noise_sn = 0; p.noise_gain = 0.f;
     p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.gain = 1.f; p.clamp = -1.f; p.next_scale = nullptr;
     FlatInput in{x, N, Cin, x_cs, H * x_pitch, 0, 0, 0};
-    int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream);
+    int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream, 2);
     if (st) return st;
   }
     return NBE_OK;
