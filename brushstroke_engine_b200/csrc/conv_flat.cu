@@ -63,6 +63,7 @@ struct FlatParams {
     // resident: the weights of ONE phase stay in shared memory while the pair sweeps all of its items (phase-major order),
     // so that only the position windows stream from L2; otherwise weights stream through a F_BSTAGES ring (item-major)
     int resident, b_tiles, n_abuf;
+    int debug;                                                      // NBE_FLAT_DEBUG: 1 = epilogue skipped, 2 = epilogue without its global stores (WRONG results)
     int contiguous;                                                 // item pairs are dealt in contiguous runs (1) or round robin (0)
     int nbuf;                                                       // accumulator sets in TMEM: 2 (epilogue overlaps the next MMAs) or 1
     // planes: A chunks are 64 channels of one parity plane of a padded NHWC image (stride-2 convs); cpp = chunks per plane
@@ -82,21 +83,21 @@ struct FlatParams {
 // flag are immediates -- the SASS is UTCHMMAs with a few uniform adds in between, as in conv_tc_row128_kernel.  The host
 // checks the entry table it built against these functions before it selects PROG != 0 (launch_flat).
 __host__ __device__ constexpr int prog_phases(int prog) { return prog == 2 ? 2 : 1; }
-__host__ __device__ constexpr int prog_ntaps(int prog, int ph) { return prog == 1 ? 9 : (ph == 0 ? 5 : 4); }
+__host__ __device__ constexpr int prog_ntaps(int prog, int ph) { return prog == 1 ? 9 : (ph == 0 ? 6 : 3); }
 __host__ __device__ constexpr int prog_G(int prog) { return prog == 2 ? 2 : 1; }
 // transposed conv: class (py, px) sums the taps kh = py, kw = px (mod 2) over x[Y - (kh - py) / 2, X - (kw - px) / 2]; the
 // window starts P + 1 rows before the tile, so a tap reads rows shifted by ((1 - dy) * P + (1 - dx))
 __host__ __device__ constexpr int prog_ay(int prog, int ph, int t) {
     if (prog == 1) return t / 3;
-    if (ph == 0) return (t == 0 || t == 1 || t == 4) ? 1 : 0;       // (0,0): kh = 0,0,2,2 ; (1,1): kh = 1
-    return (t == 0 || t == 2 || t == 3) ? 1 : 0;                    // (0,1): kh = 0,2 ; (1,0): kh = 1,1
+    if (ph == 0) return (t == 0 || t == 1 || t == 4) ? 1 : 0;       // (0,0): kh = 0,0,2,2 ; (0,1): kh = 0,2
+    return 1;                                                       // (1,0): kh = 1,1 ; (1,1): kh = 1
 }
 __host__ __device__ constexpr int prog_ax(int prog, int ph, int t) {
     if (prog == 1) return t % 3;
-    if (ph == 0) return (t == 0 || t == 2 || t == 4) ? 1 : 0;       // (0,0): kw = 0,2,0,2 ; (1,1): kw = 1
-    return (t == 0 || t == 1 || t == 2) ? 1 : 0;                    // (0,1): kw = 1,1 ; (1,0): kw = 0,2
+    if (ph == 0) return (t == 0 || t == 2 || t >= 4) ? 1 : 0;       // (0,0): kw = 0,2,0,2 ; (0,1): kw = 1,1
+    return (t == 1) ? 0 : 1;                                        // (1,0): kw = 0,2 ; (1,1): kw = 1
 }
-__host__ __device__ constexpr int prog_acc(int prog, int ph, int t) { return prog == 1 ? 0 : (ph == 0 ? (t == 4 ? 1 : 0) : (t >= 2 ? 1 : 0)); }
+__host__ __device__ constexpr int prog_acc(int prog, int ph, int t) { return prog == 1 ? 0 : (ph == 0 ? (t >= 4 ? 1 : 0) : (t >= 2 ? 1 : 0)); }
 __host__ __device__ constexpr int prog_first(int prog, int ph, int t) { return prog == 1 ? (t == 0) : (ph == 0 ? (t == 0 || t == 4) : (t == 0 || t == 2)); }
 
 // all taps of one 64-channel chunk of phase PH, issued by the elected lane of the MMA warp
@@ -384,7 +385,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_wait(smem_u32(&acc_full[ab]), acc_phase[ab]);
             acc_phase[ab] ^= 1;
             tcgen05_fence_after();
-            if (!dummy) {
+            if (!dummy && p.debug != 1) {          // (p.debug: timing experiments only, see launch_flat)
 #pragma unroll 1
                 for (int i = 0; i < TT; ++i) {
                     const int q = q0 + i * 128 + m;
@@ -456,7 +457,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             for (int r8 = 0; r8 < 4; ++r8) {
                                 const int row = r8 * 8 + rd_row0;
                                 const int4 val = *reinterpret_cast<const int4*>(stg + row * 64 + ((rd_ch ^ ((row >> 1) & 3)) << 4));
-                                if (rp[r8] >= 0) *reinterpret_cast<int4*>(p.y + rp[r8] * p.y_cs + c0 + rd_ch * 8) = val;
+                                if (rp[r8] >= 0 && p.debug != 2) *reinterpret_cast<int4*>(p.y + rp[r8] * p.y_cs + c0 + rd_ch * 8) = val;
                             }
                             __syncwarp();
                         }
@@ -601,6 +602,8 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     // resident weights pay off when a pair sweeps several items per phase and the largest phase fits next to >= 3 windows
     static const bool round_robin = getenv("NBE_FLAT_ROUND_ROBIN") != nullptr;      // A/B switch: the former item order
     p.contiguous = round_robin ? 0 : 1;
+    static const int debug_mode = getenv("NBE_FLAT_DEBUG") ? atoi(getenv("NBE_FLAT_DEBUG")) : 0;
+    p.debug = debug_mode;
     p.resident = !no_resident && pairs >= 2 * (int64_t)(grid / 2) && epi_bytes + (size_t)max_phase_tiles * F_BHALF + 3 * a_bytes <= limit;
     p.b_tiles = p.resident ? max_phase_tiles : F_BSTAGES;
     // streamed weights: a ring of 4 tiles instead of 6 when that buys one more window buffer (windows take longer to arrive)
@@ -737,9 +740,13 @@ extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_o
     p.T = (Cin > 128 && !convt_t1 && (H + 1) * x_pitch >= 1024) ? 2 : 1;            // small maps: padding of the last item costs more
     // T[2Y+kh, 2X+kw] += W[kh,kw] x[Y,X]  (F.conv_transpose2d, SG2/torch_utils/ops/conv2d_resample.py:124-138):
     // class (py,px) at grid (Y',X') sums the taps with kh = py, kw = px (mod 2) over x[Y' - (kh-py)/2, X' - (kw-px)/2].
-    // Two phases of two classes each -- {(0,0): 4 taps, (1,1): 1 tap} and {(0,1): 2 taps, (1,0): 2 taps} -- so that a
-    // phase's two accumulators take 256 TMEM columns and the other 256 hold the previous phase while its epilogue runs.
-    const int phase_classes[2][2][2] = {{{0, 0}, {1, 1}}, {{0, 1}, {1, 0}}};
+    // Two phases of two classes each, split by ROW parity -- {(0,0): 4 taps, (0,1): 2 taps} and {(1,0): 2 taps, (1,1): 1 tap} --
+    // so that a phase's two accumulators take 256 TMEM columns and the other 256 hold the previous phase while its epilogue
+    // runs, and a phase writes whole T rows (its two classes are the even and the odd pixels of the same rows).  Measured
+    // against the tap-balanced split {(0,0),(1,1)} / {(0,1),(1,0)}: no difference (0.32 ms at 64 -> 128, batch 256).  What
+    // this launch waits for is its global stores: 0.18 ms with the stores removed, 0.17 ms without any epilogue
+    // (NBE_FLAT_DEBUG=2 / 1, timing experiments with wrong results).
+    const int phase_classes[2][2][2] = {{{0, 0}, {0, 1}}, {{1, 0}, {1, 1}}};
     FlatTap taps[9];
     int phase_ntaps[2] = {0, 0};
     int t = 0;
