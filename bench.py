@@ -181,7 +181,7 @@ def run_reference(args):
                              'config0_b1_ms': b1_ms,
                              'config0': 'BASELINE configs[0]: one 128x128 patch, batch 1, median of 20 after 3 warm-ups'},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -544,9 +544,13 @@ def main():
                                     'config0': 'BASELINE configs[0]: one 128x128 patch, batch 1, median of 20 after 3 warm-ups',
                                     'sample': f'{n} patches x {reps} reps of the same workload (fp32 oracle port, {threads} threads, median; '
                                               f'{sum(times_cpu):.1f} s of CPU work)'}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)                             # stdout is a block-buffered file under the driver: flush before any teardown
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:                                               # noqa: BLE001 -- the line is out; a teardown hiccup must not cost the run
+            pass
 
 
 if __name__ == '__main__':

@@ -357,6 +357,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int et = threadIdx.x - 64;
         uint8_t* stg = smem_stage + (warp - 2) * F_STAGE_BYTES;
         const uint32_t stg_wr = smem_u32(stg) + lane * 64;
+        const uint32_t stg_rd = smem_u32(stg);
         const int wr_sw = (lane >> 1) & 3;
         const int rd_row0 = lane >> 2, rd_ch = lane & 3;
         uint32_t acc_phase[2] = {0, 0};
@@ -456,8 +457,12 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                             for (int r8 = 0; r8 < 4; ++r8) {
                                 const int row = r8 * 8 + rd_row0;
-                                const int4 val = *reinterpret_cast<const int4*>(stg + row * 64 + ((rd_ch ^ ((row >> 1) & 3)) << 4));
-                                if (rp[r8] >= 0 && p.debug != 2) *reinterpret_cast<int4*>(p.y + rp[r8] * p.y_cs + c0 + rd_ch * 8) = val;
+                                int4 val;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                                             : "r"(stg_rd + (uint32_t)(row * 64 + ((rd_ch ^ ((row >> 1) & 3)) << 4))));
+                                long long pixel = rp[r8];
+                                if (p.debug == 3 && pixel >= 0) pixel &= 0xFFFF;              // timing experiment: all stores land in 16 MB (L2-resident)
+                                if (pixel >= 0 && p.debug != 2) *reinterpret_cast<int4*>(p.y + pixel * p.y_cs + c0 + rd_ch * 8) = val;
                             }
                             __syncwarp();
                         }
