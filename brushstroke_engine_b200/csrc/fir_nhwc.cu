@@ -27,6 +27,7 @@ struct FirParams {
     const float* scale; const float* noise; long long noise_sn; float noise_gain; const float* bias;
     float alpha, gain, clamp; const float* next_scale;
     int row_groups;
+    int debug;                                                      // NBE_FIR_DEBUG (timing experiments, WRONG results): 1 = no global stores, 2 = no arithmetic (first tile pixel stored)
 };
 
 constexpr int FIR_CPT = 4;                                          // channels per thread
@@ -288,7 +289,20 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
                 *reinterpret_cast<__nv_bfloat162*>(&outv.y) = __floats2bfloat162_rn(o[2], o[3]);
                 __stcs(reinterpret_cast<uint2*>(yrow + j * ycs), outv);
             };
-            if (PACKED && sep) {
+            if (PACKED && sep && p.debug == 2) {
+                // timing experiment: the tile is waited for and one vector per output is read and stored -- loads and stores, no FIR
+#pragma unroll
+                for (int r = 0; r < FT_OH; ++r) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        uint32_t x, y2;
+                        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y2) : "r"(tb + (uint32_t)(((r + 1) * FT_IW + j + 1) * 256)));
+                        uint2 outv; outv.x = x; outv.y = y2;
+                        __stcs(reinterpret_cast<uint2*>(yrow + j * ycs), outv);
+                    }
+                    yrow += yrow_step;
+                }
+            } else if (PACKED && sep) {
                 // the same arithmetic on register pairs: FFMA2 / FMUL2 / FADD2 halve the FP32-pipe instruction count
                 // (6.75 instead of 13.5 per output), which is what bounds this pass
                 const float2 fx2[4] = {{fx[0], fx[0]}, {fx[1], fx[1]}, {fx[2], fx[2]}, {fx[3], fx[3]}};
@@ -315,7 +329,7 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
                     uint2 outv;
                     *reinterpret_cast<__nv_bfloat162*>(&outv.x) = __floats2bfloat162_rn(o[0].x, o[0].y);
                     *reinterpret_cast<__nv_bfloat162*>(&outv.y) = __floats2bfloat162_rn(o[1].x, o[1].y);
-                    __stcs(reinterpret_cast<uint2*>(yrow + j * ycs), outv);
+                    if (p.debug != 1) __stcs(reinterpret_cast<uint2*>(yrow + j * ycs), outv);
                 };
                 float2 h[4][2][2];
                 auto hrow2 = [&](float2 (&dst)[2][2], int r) {
@@ -419,6 +433,8 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
     p.t_cs = t_cs; p.t_row_pitch = t_row_pitch; p.t_img_pitch = t_img_pitch; p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch;
     p.fgain = fgain; p.scale = scale; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain; p.bias = bias;
     p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.next_scale = next_scale;
+    static const int fir_debug = getenv("NBE_FIR_DEBUG") ? atoi(getenv("NBE_FIR_DEBUG")) : 0;
+    p.debug = fir_debug;
     static const bool force_simple = getenv("NBE_FIR_SIMPLE") != nullptr;
     if (C == 128 && t_cs == 128 && !force_simple) {
         // T is described to TMA with its VALID extent, so halo reads outside [0,TH) x [0,TW) come back as zeros
