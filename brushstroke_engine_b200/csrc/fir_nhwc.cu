@@ -164,8 +164,8 @@ constexpr int FT_TILE_BYTES = FT_IH * FT_IW * 256;                  // 128 bf16 
 
 template <bool PACKED>
 __global__ void __launch_bounds__(256, 2)
-fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_constant__ CUtensorMap tmap_nz, const FirParams p,
-                     int tiles_x, int tiles_y, int total_tiles, int noise_mode) {
+fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_constant__ CUtensorMap tmap_t8, const __grid_constant__ CUtensorMap tmap_nz,
+                     const FirParams p, int tiles_x, int tiles_y, int total_tiles, int noise_mode, int strip_ok) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     uint8_t* bufs = smem;                                           // [2][FT_TILE_BYTES]
@@ -209,28 +209,44 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
     const float ngain = p.noise_gain * g_pre;
     // noise_mode 1: the tile's 8 x 16 noise values arrive by TMA with the tile itself (same mbarrier; out-of-range elements are
     // zero-filled); 0: staged by the threads (noise tensors TMA cannot describe); 2: no noise
-    auto issue = [&](int tile, int b) {
-        int t = tile;
-        const int tx = t % tiles_x; t /= tiles_x;
-        const int ty = t % tiles_y; t /= tiles_y;
-        const uint32_t bar = smem_u32(&full[b]);
-        mbar_expect_tx(bar, FT_TILE_BYTES + (noise_mode == 1 ? FT_OH * FT_OW * 4 : 0));
-        tma_load_4d(smem_u32(bufs + b * BUF_STRIDE), &tmap_t, bar, 0, tx * FT_OW - p.pad, ty * FT_OH - p.pad, t);
-        if (noise_mode == 1) tma_load_3d(smem_u32(s_nz + b * FT_OH * FT_OW), &tmap_nz, bar, tx * FT_OW, ty * FT_OH, p.noise_sn ? t : 0);
-    };
     // every CTA takes one contiguous run of tiles: the image (and with it the per-channel epilogue vectors in s_epi) changes
     // once per 128 tiles instead of at every tile, so the loop has no exposed global-memory round trip and one barrier per tile
     const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int t_begin = blockIdx.x * per_cta, t_end = min(total_tiles, t_begin + per_cta);
+    // STRIP order (packed separable path): a run walks DOWN a 16-pixel-wide strip of its image, so the last three horizontally
+    // filtered rows of a tile are the first three of the next one and stay in REGISTERS: only the first tile of a strip (or of
+    // the run) loads its 3 halo rows, every other tile loads 8 rows instead of 11 -- the tile loads are what this pass waits for
+    // (0.44 of its 0.49 ms at 128^2 remain with the arithmetic compiled out), and they shrink by 27 %
+    if (PACKED && !sep) {                                          // the host routes rank-1 filters only to this instantiation (filter_is_rank1)
+        if (threadIdx.x == 0 && blockIdx.x == 0) printf("nbe fir_act_nhwc: packed kernel launched with a non-separable filter\n");
+        __trap();
+    }
+    const bool strip = PACKED && sep && strip_ok && p.debug != 2;
+    auto decode = [&](int tile, int& tx, int& ty, int& n) {
+        int t = tile;
+        if (strip) { ty = t % tiles_y; t /= tiles_y; tx = t % tiles_x; t /= tiles_x; }
+        else       { tx = t % tiles_x; t /= tiles_x; ty = t % tiles_y; t /= tiles_y; }
+        n = t;
+    };
+    auto issue = [&](int tile, int b) {
+        int tx, ty, t;
+        decode(tile, tx, ty, t);
+        const bool fresh = !strip || tile == t_begin || ty == 0;
+        const uint32_t bar = smem_u32(&full[b]);
+        mbar_expect_tx(bar, (fresh ? FT_TILE_BYTES : FT_OH * FT_IW * 256) + (noise_mode == 1 ? FT_OH * FT_OW * 4 : 0));
+        if (fresh) tma_load_4d(smem_u32(bufs + b * BUF_STRIDE), &tmap_t, bar, 0, tx * FT_OW - p.pad, ty * FT_OH - p.pad, t);
+        else       tma_load_4d(smem_u32(bufs + b * BUF_STRIDE + 3 * FT_IW * 256), &tmap_t8, bar, 0, tx * FT_OW - p.pad, ty * FT_OH - p.pad + 3, t);
+        if (noise_mode == 1) tma_load_3d(smem_u32(s_nz + b * FT_OH * FT_OW), &tmap_nz, bar, tx * FT_OW, ty * FT_OH, p.noise_sn ? t : 0);
+    };
     if (threadIdx.x == 0 && t_begin < t_end) issue(t_begin, 0);
     int it = 0, cur_n = -1;
+    float2 h[4][2][2];                                              // packed path: horizontally filtered rows, carried from tile to tile in strip order
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const int b = it & 1;
         if (threadIdx.x == 0 && tile + 1 < t_end) issue(tile + 1, b ^ 1);   // buffer b^1 was released by the __syncthreads of the previous iteration
-        int t = tile;
-        const int tx = t % tiles_x; t /= tiles_x;
-        const int ty = t % tiles_y; t /= tiles_y;
-        const int n = t;
+        int tx, ty, n;
+        decode(tile, tx, ty, n);
+        const bool fresh = !strip || tile == t_begin || ty == 0;
         if (n != cur_n) {
             for (int c = threadIdx.x; c < 128; c += 256) {
                 s_epi[c] = (p.scale ? p.scale[(long long)n * 128 + c] : 1.f) * g_pre;
@@ -331,7 +347,6 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
                     *reinterpret_cast<__nv_bfloat162*>(&outv.y) = __floats2bfloat162_rn(o[1].x, o[1].y);
                     if (p.debug != 1) __stcs(reinterpret_cast<uint2*>(yrow + j * ycs), outv);
                 };
-                float2 h[4][2][2];
                 auto hrow2 = [&](float2 (&dst)[2][2], int r) {
                     float2 v[5][2];
 #pragma unroll
@@ -346,7 +361,7 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
                         for (int q = 0; q < 2; ++q)
                             dst[j][q] = fma2(fx2[3], v[j + 3][q], fma2(fx2[2], v[j + 2][q], fma2(fx2[1], v[j + 1][q], mul2(fx2[0], v[j][q]))));
                 };
-                hrow2(h[0], 0); hrow2(h[1], 1); hrow2(h[2], 2);
+                if (fresh) { hrow2(h[0], 0); hrow2(h[1], 1); hrow2(h[2], 2); }      // else: rows 8, 9, 10 of the tile above, already in h[0..2]
 #pragma unroll
                 for (int r = 0; r < FT_OH; ++r) {
                     hrow2(h[(r + 3) & 3], r + 3);
@@ -361,7 +376,7 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
                     }
                     yrow += yrow_step;
                 }
-            } else if (sep) {
+            } else if (!PACKED && sep) {
                 float h[4][2][4];
                 auto hrow = [&](float (&dst)[2][4], int r) {
                     float v[5][4];
@@ -386,7 +401,7 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
                     }
                     yrow += yrow_step;
                 }
-            } else {
+            } else if (!PACKED) {
 #pragma unroll
                 for (int r = 0; r < FT_OH; ++r) {
 #pragma unroll
@@ -416,6 +431,31 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
 
 using namespace nbe;
 
+#include <map>
+// Is the 4x4 filter behind this device pointer rank-1 (f = fy (x) fx)?  The packed kernel holds only the separable arithmetic (the
+// other code paths cost it registers: 472 bytes of spills and 15 % of its speed), so the host classifies a filter the first time
+// it sees its pointer -- one synchronous 64-byte read, never during a stream capture -- and remembers the answer.  A pointer
+// whose contents change to a non-separable filter later is caught by the kernel itself (it traps).  -1: cannot tell now.
+static int filter_is_rank1(const float* f, cudaStream_t stream) {
+    static std::mutex mu;
+    static std::map<const float*, int> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = seen.find(f);
+    if (it != seen.end()) return it->second;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return -1;
+    float h[16];
+    if (cudaStreamSynchronize(stream) != cudaSuccess || cudaMemcpy(h, f, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+    float ft[16];
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) ft[a * 4 + b] = h[(3 - a) * 4 + (3 - b)];
+    bool sep = ft[0] != 0.f;
+    for (int a = 1; a < 4; ++a)
+        for (int b = 1; b < 4; ++b) sep = sep && fabsf(ft[a * 4 + b] * ft[0] - ft[a * 4] * ft[b]) <= 1e-6f * fabsf(ft[a * 4 + b] * ft[0]) + 1e-30f;
+    if (seen.size() > 64) seen.clear();
+    seen[f] = sep ? 1 : 0;
+    return sep ? 1 : 0;
+}
+
 extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int N, int OH, int OW, int C, int TH, int TW, int pad,
                                      int t_cs, int64_t t_row_pitch, int64_t t_img_pitch,
                                      int y_cs, int64_t y_row_pitch, int64_t y_img_pitch, float fgain,
@@ -444,6 +484,11 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
         cuuint32_t box[4] = {128, FT_IW, FT_IH, 1};
         int st = make_tmap(&tm, t, 4, dims, strides, box, "FIR input", 1, /*swizzle=*/0);
         if (st) return st;
+        CUtensorMap tm8;                                                // the same tensor, boxes of FT_OH rows: tiles that continue a strip
+        cuuint32_t box8[4] = {128, FT_IW, FT_OH, 1};
+        st = make_tmap(&tm8, t, 4, dims, strides, box8, "FIR input (strip)", 1, /*swizzle=*/0);
+        if (st) return st;
+        static const int strip_ok = getenv("NBE_FIR_NO_STRIP") == nullptr;              // A/B switch: every tile loads its own halo rows
         const int tiles_x = (OW + FT_OW - 1) / FT_OW, tiles_y = (OH + FT_OH - 1) / FT_OH;
         const int64_t total = (int64_t)tiles_x * tiles_y * N;
         NBE_REQUIRE(total <= INT32_MAX, "fir_act_nhwc: too many tiles");
@@ -471,8 +516,8 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
         int grid = kNumSMs * 2;
         if (total < grid) grid = (int)total;
         static const bool scalar_fp32 = getenv("NBE_FIR_SCALAR") != nullptr;      // A/B switch: the unpacked FP32 arithmetic
-        if (scalar_fp32) fir_act_tiled_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tn, p, tiles_x, tiles_y, (int)total, noise_mode);
-        else fir_act_tiled_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tn, p, tiles_x, tiles_y, (int)total, noise_mode);
+        if (scalar_fp32 || filter_is_rank1(f, (cudaStream_t)stream) != 1) fir_act_tiled_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tm8, tn, p, tiles_x, tiles_y, (int)total, noise_mode, strip_ok);
+        else fir_act_tiled_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tm8, tn, p, tiles_x, tiles_y, (int)total, noise_mode, strip_ok);
         return launched("fir_act_tiled_kernel");
     }
     p.row_groups = (OH + FIR_RPT - 1) / FIR_RPT;
