@@ -179,6 +179,8 @@ class CanvasJob:
         self.d_crops = d_yx if d_yx is not None else torch.from_numpy(self.crops_yx).to(dev)
         self.tiles_yx = self.crops_yx + m                                # meta: (y + m, x + m)  (brush.py:365-373)
         self.d_tiles_yx = self.d_crops + m
+        self.d_crops_local = self.d_crops
+        self.d_tiles_yx_band = None
 
     def _init_row_window(self, guidance, stitching_mode, crop_rows):
         if stitching_mode != 'all':
@@ -209,19 +211,33 @@ class CanvasJob:
                 assert guidance.dtype == torch.uint8
                 src = guidance[s0:s1, :, -1].to(dev)
             self.d_geom[s0 + m - g0:s1 + m - g0, m:m + W0] = src
-        gy = torch.arange(r0, r1, dtype=torch.int32, device=dev) * rwidth
-        gx = torch.arange(ncols, dtype=torch.int32, device=dev) * rwidth
-        n_r = r1 - r0
-        d_yx = torch.stack([gy[:, None].expand(n_r, ncols), gx[None, :].expand(n_r, ncols)], dim=2).reshape(-1, 2).contiguous()
-        ys, xs = np.meshgrid(np.arange(r0, r1) * rwidth, np.arange(ncols) * rwidth, indexing='ij')
-        self.crops_yx = np.stack([ys.ravel(), xs.ravel()], axis=1).astype(np.int32).reshape(-1, 2)
+        # the crop grid of a row window is pure arithmetic: built once per (shape, margin, rows) and kept on the engine -- a canvas
+        # that spans 8 GPUs spends ~4 ms per rank in its one batch, so every small launch of the set-up shows in its scaling
+        lo = r0 * rwidth + m if r0 > 0 else 0
+        cache = self.engine.__dict__.setdefault('_crop_grid_cache', {})
+        key = (H0, W0, m, r0, r1, self.patch)
+        ent = cache.get(key)
+        if ent is None:
+            gy = torch.arange(r0, r1, dtype=torch.int32, device=dev) * rwidth
+            gx = torch.arange(ncols, dtype=torch.int32, device=dev) * rwidth
+            n_r = r1 - r0
+            d_yx = torch.stack([gy[:, None].expand(n_r, ncols), gx[None, :].expand(n_r, ncols)], dim=2).reshape(-1, 2).contiguous()
+            ys, xs = np.meshgrid(np.arange(r0, r1) * rwidth, np.arange(ncols) * rwidth, indexing='ij')
+            crops_yx = np.stack([ys.ravel(), xs.ravel()], axis=1).astype(np.int32).reshape(-1, 2)
+            d_local = d_yx.clone()
+            d_local[:, 0] -= g0
+            d_tiles = d_yx + m
+            d_band = d_tiles.clone()
+            d_band[:, 0] -= lo
+            while len(cache) >= 16:
+                cache.pop(next(iter(cache)))
+            ent = cache[key] = (d_yx, crops_yx, d_local.contiguous(), d_tiles, d_band.contiguous())
+        d_yx, self.crops_yx, self.d_crops_local, self.d_tiles_yx, self.d_tiles_yx_band = ent
         self._crops = None
         self.d_crops = d_yx
         self.tiles_yx = self.crops_yx + m
-        self.d_tiles_yx = self.d_crops + m
         # canvas rows owned by these crop rows under last-writer-wins (closed form): [r0*rw + m, r1*rw + m), the
         # first band starts at row 0 (rows < m are never written), the last one runs to the end of the canvas
-        lo = r0 * rwidth + m if r0 > 0 else 0
         hi = r1 * rwidth + m if r1 < nrows else ph
         self.band = (lo, max(lo, hi))
 
@@ -240,9 +256,7 @@ class CanvasJob:
     def gather(self, start: int, end: int) -> torch.Tensor:
         n = end - start
         out = torch.empty((n, 1, self.patch, self.patch), dtype=torch.float32, device=self.engine.device)
-        crops = self.d_crops[start:end]
-        if self.geom_row0:
-            crops = crops - torch.tensor([self.geom_row0, 0], dtype=torch.int32, device=crops.device)
+        crops = self.d_crops_local[start:end]                            # window-relative rows (no host-to-device scalar copies here)
         with torch.cuda.device(self.engine.device):
             _lib.call('nbe_gather_geom_patches', _lib.ptr(self.d_geom), int(self.d_geom.shape[0]), self.canvas_w,
                       _lib.ptr(crops.contiguous()), _lib.ptr(out), n, self.patch, _lib.stream())
@@ -258,7 +272,10 @@ class CanvasJob:
         if rows <= 0 or n == 0:
             return
         dev = self.engine.device
-        yx = (self.d_tiles_yx - torch.tensor([lo, 0], dtype=torch.int32, device=dev)).contiguous()
+        yx = self.d_tiles_yx_band                                          # tile origins relative to the band (row-window jobs keep it ready)
+        if yx is None:
+            yx = self.d_tiles_yx.clone()
+            yx[:, 0] -= lo
         owner = torch.empty((rows, self.canvas_w), dtype=torch.int32, device=dev)
         order = torch.arange(n, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
