@@ -69,7 +69,11 @@ def test_encoder_bf16_tensor_core_path(bundles, golden_inputs):
     assert g0.shape == (2, 16, 16, 16) and g1.shape == (2, 256, 32, 32)
     for got, ref in ((g0, gf[0]), (g1, gf[1])):
         err = md(got, ref)
-        assert err < 0.03 * float(ref.abs().max()), (err, float(ref.abs().max()))
+        assert err < 0.01 * float(ref.abs().max()), (err, float(ref.abs().max()))      # measured: 0.58 % / 0.42 % of max |ref|
+        # as a kernel test: seven layers of bf16 activations (2^-9 relative rounding each) stay within 0.5 % RMS of the fp32 features
+        rms = float(((got.cpu().double() - ref.cpu().double()) ** 2).mean().sqrt() / (ref.cpu().double() ** 2).mean().sqrt())
+        print(f'bf16 encoder: max-abs error {err:.4g} (max |ref| {float(ref.abs().max()):.4g}), relative RMS error {rms:.3e}')
+        assert rms < 5e-3, rms
     # a second batch size re-plans the workspace; padding channels must stay zero
     geom5 = t(g['geom']).repeat(3, 1, 1, 1)[:5].to(DEV)
     h0, h1 = enc.encode(geom5)
