@@ -54,9 +54,12 @@ struct FlatParams {
     int n_ent;
     short ent_c[F_MAX_ENT], ent_shift[F_MAX_ENT];
     unsigned char ent_acc[F_MAX_ENT], ent_first[F_MAX_ENT], ent_btile[F_MAX_ENT], ent_bk[F_MAX_ENT];
+    unsigned char ent_co[F_MAX_ENT];                                // output-channel block (of 128) of the entry's weight tile: classes may be Cout slices
     // the same, packed for the MMA issuer: A start offset in 16-byte units [0,16) | accumulator column offset [16,26) | first [26] | chunk [27,32)
     uint32_t ent_w[F_MAX_ENT + 1];
     int cls_sy[F_MAX_CLASSES], cls_sx[F_MAX_CLASSES], cls_oy[F_MAX_CLASSES], cls_ox[F_MAX_CLASSES], cls_vy[F_MAX_CLASSES], cls_vx[F_MAX_CLASSES];
+    int cls_co[F_MAX_CLASSES];                                      // first output channel of the class (0, or 128 for the second Cout slice)
+    int n_vec;                                                      // per-channel epilogue vector length: 128, or 256 with two Cout slices
     int min_shift, n_boxes, box_rows, k_chunks;
     // phases: groups of classes whose accumulators fit in half of TMEM; each phase owns the entries [ph_e0, ph_e1)
     int n_phases, ph_e0[2], ph_e1[2], ph_G[2], ph_cls[2][F_MAX_CLASSES], Gmax;
@@ -151,8 +154,8 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t* smem_a = smem;                                         // [n_abuf][window of one 64-channel chunk]
     uint8_t* smem_b = smem + p.n_abuf * a_bytes;                    // [b_tiles][8 KiB]: ring, or the resident phase weights
     uint8_t* smem_stage = smem_b + p.b_tiles * F_BHALF;             // [EW][F_STAGE_BYTES] epilogue transposition buffers
-    float* s_vec = reinterpret_cast<float*>(smem_stage + EW * F_STAGE_BYTES);   // [3][128] (EPI == 1)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + (EPI == 1 ? 3 * 128 : 0));
+    float* s_vec = reinterpret_cast<float*>(smem_stage + EW * F_STAGE_BYTES);   // [3][256] (EPI == 1)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_vec + (EPI == 1 ? 3 * 256 : 0));
     uint64_t* a_full = bars;                            // [F_MAX_ABUF]  (the leader's is the live one)
     uint64_t* a_empty = a_full + F_MAX_ABUF;            // [F_MAX_ABUF]
     uint64_t* b_full = a_empty + F_MAX_ABUF;            // [F_BSTAGES]
@@ -214,7 +217,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t rf = smem_u32(res_full);
                     if (leader) mbar_expect_tx(rf, 2u * (uint32_t)(e1 - e0) * F_BHALF);
                     for (int e = e0; e < e1; ++e)
-                        tma_load_3d_2sm(smem_u32(smem_b + (e - e0) * F_BHALF), &tmap_b, rf, p.ent_bk[e] * 64, p.cout_off + rank * 64, p.ent_btile[e]);
+                        tma_load_3d_2sm(smem_u32(smem_b + (e - e0) * F_BHALF), &tmap_b, rf, p.ent_bk[e] * 64, p.cout_off + p.ent_co[e] * 128 + rank * 64, p.ent_btile[e]);
                 }
                 int e = e0;
                 const int wrow0 = p.planes ? q0 / p.P : 0;                        // first plane row of the window
@@ -241,7 +244,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             mbar_wait_fast(smem_u32(&b_empty[bs]), bpar ^ 1);
                             const uint32_t bf = smem_u32(&b_full[bs]);
                             if (leader) mbar_expect_tx(bf, 2u * F_BHALF);
-                            tma_load_3d_2sm(smem_u32(smem_b + bs * F_BHALF), &tmap_b, bf, p.ent_bk[e] * 64, p.cout_off + rank * 64, p.ent_btile[e]);
+                            tma_load_3d_2sm(smem_u32(smem_b + bs * F_BHALF), &tmap_b, bf, p.ent_bk[e] * 64, p.cout_off + p.ent_co[e] * 128 + rank * 64, p.ent_btile[e]);
                         }
                 }
                 if (RES) { if (++k == n_local) { k = 0; ++ph; } }
@@ -375,10 +378,10 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int ab = (p.nbuf == 2) ? (s & 1) : 0;
             if (EPI == 1 && n != cur_n) {
                 asm volatile("bar.sync 1, %0;" :: "n"(EW * 32) : "memory");
-                if (et < 128) {
+                if (et < p.n_vec) {
                     s_vec[et] = p.dcoef ? p.dcoef[(long long)n * p.vec_stride + et] : 1.f;
-                    s_vec[128 + et] = p.bias ? p.bias[et] : 0.f;
-                    s_vec[256 + et] = p.next_scale ? p.next_scale[(long long)n * p.vec_stride + et] : 1.f;
+                    s_vec[256 + et] = p.bias ? p.bias[et] : 0.f;
+                    s_vec[512 + et] = p.next_scale ? p.next_scale[(long long)n * p.vec_stride + et] : 1.f;
                 }
                 asm volatile("bar.sync 1, %0;" :: "n"(EW * 32) : "memory");
                 cur_n = n;
@@ -394,6 +397,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
                     for (int gl = 0; gl < G; ++gl) {
                         const int g = p.ph_cls[ph][gl];              // global class (output mapping) of local accumulator gl
+                        const int cco = p.cls_co[g];
                         const bool valid = q < p.positions && gy < p.cls_vy[g] && gx < p.cls_vx[g];
                         const int oy = gy * p.cls_sy[g] + p.cls_oy[g], ox = gx * p.cls_sx[g] + p.cls_ox[g];
                         float nz = 0.f;
@@ -424,9 +428,9 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                     const int ob = c0 + gg * 8;
 #pragma unroll
                                     for (int h4 = 0; h4 < 2; ++h4) {
-                                        lds_f4(s_vec_u32 + (uint32_t)((ob + 4 * h4) * 4), dc + 4 * h4);
-                                        lds_f4(s_vec_u32 + (uint32_t)((128 + ob + 4 * h4) * 4), bs + 4 * h4);
-                                        lds_f4(s_vec_u32 + (uint32_t)((256 + ob + 4 * h4) * 4), ns + 4 * h4);
+                                        lds_f4(s_vec_u32 + (uint32_t)((cco + ob + 4 * h4) * 4), dc + 4 * h4);
+                                        lds_f4(s_vec_u32 + (uint32_t)((256 + cco + ob + 4 * h4) * 4), bs + 4 * h4);
+                                        lds_f4(s_vec_u32 + (uint32_t)((512 + cco + ob + 4 * h4) * 4), ns + 4 * h4);
                                     }
                                 }
 #pragma unroll
@@ -462,7 +466,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                              : "r"(stg_rd + (uint32_t)(row * 64 + ((rd_ch ^ ((row >> 1) & 3)) << 4))));
                                 long long pixel = rp[r8];
                                 if (p.debug == 3 && pixel >= 0) pixel &= 0xFFFF;              // timing experiment: all stores land in 16 MB (L2-resident)
-                                if (pixel >= 0 && p.debug != 2) *reinterpret_cast<int4*>(p.y + pixel * p.y_cs + c0 + rd_ch * 8) = val;
+                                if (pixel >= 0 && p.debug != 2) *reinterpret_cast<int4*>(p.y + pixel * p.y_cs + cco + c0 + rd_ch * 8) = val;
                             }
                             __syncwarp();
                         }
@@ -486,7 +490,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
 // ---- host ----------------------------------------------------------------------------------------
 // One tap of a launch's program, before expansion into entries
-struct FlatTap { int shift, acc, btile, plane; };                   // plane: parity plane the tap reads (-1: all chunks)
+struct FlatTap { int shift, acc, btile, plane, co; };               // plane: parity plane the tap reads (-1: all chunks); co: Cout block of 128
 
 struct FlatInput {
     const void* x; int N, Cin, x_cs;
@@ -498,6 +502,7 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
                        cudaStream_t stream, int prog = 0) {
     const int Cin_pad = (in.Cin + 63) / 64 * 64;
     const int cpp = Cin_pad / 64;
+    if (p.n_vec == 0) p.n_vec = 128;
     p.planes = in.planes; p.cpp = cpp; p.plane_C = in.Cin;
     p.k_chunks = in.planes ? 4 * cpp : cpp;
     // expand the tap program into entries sorted by chunk within each phase
@@ -516,6 +521,7 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
                 if (e >= F_MAX_ENT) return fail(NBE_EUNSUPPORTED, "conv_flat: tap program too long (%d chunks x %d taps)", p.k_chunks, ntaps);
                 p.ent_c[e] = (short)c; p.ent_shift[e] = (short)taps[t].shift; p.ent_acc[e] = (unsigned char)taps[t].acc;
                 p.ent_btile[e] = (unsigned char)taps[t].btile; p.ent_bk[e] = (unsigned char)(in.planes ? c % cpp : c);
+                p.ent_co[e] = (unsigned char)taps[t].co;
                 p.ent_first[e] = seen[taps[t].acc] ? 0 : 1; seen[taps[t].acc] = true;
                 ++e;
             }
@@ -559,7 +565,7 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     static const bool no_resident = getenv("NBE_FLAT_NO_RESIDENT") != nullptr;
     const size_t a_bytes = ((size_t)p.n_boxes * p.box_rows * 128 + 1023) & ~(size_t)1023;
     constexpr int epi_warps = 8;                                    // (16 measured 3-7 % slower: the windows lose a buffer)
-    const size_t epi_bytes = (size_t)epi_warps * F_STAGE_BYTES + (raw ? 0 : 3 * 128 * sizeof(float)) + 256;
+    const size_t epi_bytes = (size_t)epi_warps * F_STAGE_BYTES + (raw ? 0 : 3 * 256 * sizeof(float)) + 256;
     CUtensorMap ta, tb;
     if (in.planes) {
         // (pixel pair x channels, X', row parity, Y', image) over the padded NHWC image
@@ -661,23 +667,31 @@ extern "C" int nbe_conv3x3_flat_bf16(const void* x, const void* wq, void* y,
     NBE_REQUIRE((((uintptr_t)x | (uintptr_t)wq | (uintptr_t)y) & 15) == 0, "conv3x3_flat: tensors must be 16-byte aligned");
     NBE_REQUIRE(y_row_pitch >= OW && y_img_pitch >= y_row_pitch * OH, "conv3x3_flat: bad output pitches");
     if (N == 0) return NBE_OK;
-    for (int co = 0; co < Cout; co += 128) {
+    // 256 output channels per launch as TWO accumulator classes (Cout slices of 128) over the same position windows: the windows
+    // are loaded once instead of once per 128-channel pass and one launch floor disappears; the accumulators then fill TMEM
+    // (2 tiles x 2 slices x 128 columns), so the epilogue is not overlapped -- which costs what the saved window loads buy
+    static const bool one_pass_256 = getenv("NBE_FLAT_ONE_PASS_256") != nullptr;     // A/B switch, off: measured equal (stride-2 128->256: 0.199 vs 0.201 ms) or slower (ScaleUp conv: 0.121 vs 0.099 ms)
+    const int nh = (one_pass_256 && Cout % 256 == 0) ? 2 : 1;
+    for (int co = 0; co < Cout; co += 128 * nh) {
         FlatParams p{};
         p.y = (__nv_bfloat16*)y + co; p.P = x_pitch; p.positions = OH * x_pitch; p.T = 2;
-        FlatTap taps[9];
+        FlatTap taps[18];
         const int off = valid ? 0 : -1;
-        for (int kh = 0; kh < 3; ++kh)
-            for (int kw = 0; kw < 3; ++kw) taps[kh * 3 + kw] = {(kh + off) * x_pitch + (kw + off), 0, kh * 3 + kw, -1};
-        p.cls_sy[0] = 1; p.cls_sx[0] = 1; p.cls_oy[0] = 0; p.cls_ox[0] = 0; p.cls_vy[0] = OH; p.cls_vx[0] = OW;
-        p.n_phases = 1; p.ph_G[0] = 1; p.ph_cls[0][0] = 0; p.Gmax = 1;
-        const int phase_ntaps[2] = {9, 0};
+        for (int half = 0; half < nh; ++half) {
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) taps[half * 9 + kh * 3 + kw] = {(kh + off) * x_pitch + (kw + off), half, kh * 3 + kw, -1, half};
+            p.cls_sy[half] = 1; p.cls_sx[half] = 1; p.cls_oy[half] = 0; p.cls_ox[half] = 0; p.cls_vy[half] = OH; p.cls_vx[half] = OW;
+            p.cls_co[half] = half * 128; p.ph_cls[0][half] = half;
+        }
+        p.n_phases = 1; p.ph_G[0] = nh; p.Gmax = nh; p.n_vec = 128 * nh;
+        const int phase_ntaps[2] = {9 * nh, 0};
         p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch; p.noise_w = OW; p.vec_stride = Cout; p.cout_off = co;
         p.dcoef = dcoef ? dcoef + co : nullptr; p.noise = noise; p.noise_sn = noise_sn; p.noise_gain = noise_gain;
         p.bias = bias ? bias + co : nullptr; p.act = 1; p.alpha = alpha; p.gain = gain; p.clamp = clamp;
         p.next_scale = next_scale ? next_scale + co : nullptr;
         const int in_rows = valid ? OH + 2 : OH;
         FlatInput in{x, N, Cin, x_cs, in_rows * x_pitch, 0, 0, 0};
-        int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream, 1);
+        int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream, nh == 1 ? 1 : 0);
         if (st) return st;
     }
     return NBE_OK;
@@ -698,7 +712,9 @@ extern "C" int nbe_conv3x3s2_flat_bf16(const void* xp, const void* wq, void* y,
     // out[Y, X] = sum_{kh,kw} W[kh,kw] xp[2Y + kh, 2X + kw]  (xp = the input with its 1-pixel border, (H+2) x (W+2)):
     // tap (kh, kw) reads parity plane (kh & 1, kw & 1) at plane position (Y + (kh >> 1), X + (kw >> 1))
     const int P = (W + 2) / 2;
-    for (int co = 0; co < Cout; co += 128) {
+    static const bool one_pass_256 = getenv("NBE_FLAT_ONE_PASS_256") != nullptr;     // A/B switch, off (see nbe_conv3x3_flat_bf16)
+    const int nh = (one_pass_256 && Cout % 256 == 0) ? 2 : 1;
+    for (int co = 0; co < Cout; co += 128 * nh) {
         FlatParams p{};
         p.y = (__nv_bfloat16*)y + co; p.P = P; p.positions = OH * P;
         // two position tiles per item share every weight tile, unless the padding of the last item costs more than that saves
@@ -706,14 +722,17 @@ extern "C" int nbe_conv3x3s2_flat_bf16(const void* xp, const void* wq, void* y,
         p.T = ((tiles + 1) / 2 * 2 * 100 > tiles * 115) ? 1 : 2;
         static const int force_t = getenv("NBE_S2_T") ? atoi(getenv("NBE_S2_T")) : 0;      // A/B switch
         if (force_t == 1 || force_t == 2) p.T = force_t;
-        FlatTap taps[9];
+        FlatTap taps[18];
         int t = 0;
-        for (int pl = 0; pl < 4; ++pl)
-            for (int kh = (pl >> 1); kh < 3; kh += 2)
-                for (int kw = (pl & 1); kw < 3; kw += 2) taps[t++] = {(kh >> 1) * P + (kw >> 1), 0, kh * 3 + kw, pl};
-        p.cls_sy[0] = 1; p.cls_sx[0] = 1; p.cls_oy[0] = 0; p.cls_ox[0] = 0; p.cls_vy[0] = OH; p.cls_vx[0] = OW;
-        p.n_phases = 1; p.ph_G[0] = 1; p.ph_cls[0][0] = 0; p.Gmax = 1;
-        const int phase_ntaps[2] = {9, 0};
+        for (int half = 0; half < nh; ++half) {
+            for (int pl = 0; pl < 4; ++pl)
+                for (int kh = (pl >> 1); kh < 3; kh += 2)
+                    for (int kw = (pl & 1); kw < 3; kw += 2) taps[t++] = {(kh >> 1) * P + (kw >> 1), half, kh * 3 + kw, pl, half};
+            p.cls_sy[half] = 1; p.cls_sx[half] = 1; p.cls_oy[half] = 0; p.cls_ox[half] = 0; p.cls_vy[half] = OH; p.cls_vx[half] = OW;
+            p.cls_co[half] = half * 128; p.ph_cls[0][half] = half;
+        }
+        p.n_phases = 1; p.ph_G[0] = nh; p.Gmax = nh; p.n_vec = 128 * nh;
+        const int phase_ntaps[2] = {9 * nh, 0};
         p.y_cs = y_cs; p.y_row_pitch = y_row_pitch; p.y_img_pitch = y_img_pitch; p.noise_w = OW; p.vec_stride = Cout; p.cout_off = co;
         p.dcoef = nullptr; p.noise = nullptr; p.noise_sn = 0; p.noise_gain = 0.f;
         p.bias = bias ? bias + co : nullptr; p.act = 1; p.alpha = alpha; p.gain = gain; p.clamp = clamp;
