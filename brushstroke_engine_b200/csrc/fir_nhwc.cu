@@ -163,9 +163,8 @@ constexpr int FT_IW = FT_OW + 3, FT_IH = FT_OH + 3;
 constexpr int FT_TILE_BYTES = FT_IH * FT_IW * 256;                  // 128 bf16 channels per pixel
 
 template <bool PACKED>
-__global__ void __launch_bounds__(256, 2)
-fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_constant__ CUtensorMap tmap_t8, const __grid_constant__ CUtensorMap tmap_nz,
-                     const FirParams p, int tiles_x, int tiles_y, int total_tiles, int noise_mode, int strip_ok) {
+__device__ __forceinline__ void fir_tiled_body(const CUtensorMap& tmap_t, const CUtensorMap& tmap_t8, const CUtensorMap& tmap_nz,
+                                               const FirParams& p, int tiles_x, int tiles_y, int total_tiles, int noise_mode, int strip_ok) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     uint8_t* bufs = smem;                                           // [2][FT_TILE_BYTES]
@@ -217,10 +216,7 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
     // filtered rows of a tile are the first three of the next one and stay in REGISTERS: only the first tile of a strip (or of
     // the run) loads its 3 halo rows, every other tile loads 8 rows instead of 11 -- the tile loads are what this pass waits for
     // (0.44 of its 0.49 ms at 128^2 remain with the arithmetic compiled out), and they shrink by 27 %
-    if (PACKED && !sep) {                                          // the host routes rank-1 filters only to this instantiation (filter_is_rank1)
-        if (threadIdx.x == 0 && blockIdx.x == 0) printf("nbe fir_act_nhwc: packed kernel launched with a non-separable filter\n");
-        __trap();
-    }
+    if (PACKED && !sep) __trap();                                   // unreachable: the kernel sends other filters to fir_tiled_generic
     const bool strip = PACKED && sep && strip_ok && p.debug != 2;
     auto decode = [&](int tile, int& tx, int& ty, int& n) {
         int t = tile;
@@ -427,34 +423,40 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
     }
 }
 
+// the general path (scalar arithmetic, any 4x4 filter) as an out-of-line function: the packed kernel falls back to it for a
+// filter that is not rank-1 without paying for its code paths in registers (inlined next to the packed path they cost it
+// 472 bytes of spills and 15 % of its speed)
+__device__ __noinline__ void fir_tiled_generic(const CUtensorMap& tmap_t, const CUtensorMap& tmap_t8, const CUtensorMap& tmap_nz,
+                                               const FirParams& p, int tiles_x, int tiles_y, int total_tiles, int noise_mode) {
+    fir_tiled_body<false>(tmap_t, tmap_t8, tmap_nz, p, tiles_x, tiles_y, total_tiles, noise_mode, 0);
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(256, 2)
+fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_constant__ CUtensorMap tmap_t8, const __grid_constant__ CUtensorMap tmap_nz,
+                     const FirParams p, int tiles_x, int tiles_y, int total_tiles, int noise_mode, int strip_ok) {
+    if (PACKED) {
+        // rank-1 test on the flipped, scaled filter (the same test the body repeats): decided before anything is set up
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __ldg(p.f + (15 - i)) * p.fgain;
+        bool sep = f[0] != 0.f;
+#pragma unroll
+        for (int a = 1; a < 4; ++a)
+#pragma unroll
+            for (int b = 1; b < 4; ++b) sep = sep && fabsf(f[a * 4 + b] * f[0] - f[a * 4] * f[b]) <= 1e-6f * fabsf(f[a * 4 + b] * f[0]) + 1e-30f;
+        if (!sep) {
+            fir_tiled_generic(tmap_t, tmap_t8, tmap_nz, p, tiles_x, tiles_y, total_tiles, noise_mode);
+            return;
+        }
+    }
+    fir_tiled_body<PACKED>(tmap_t, tmap_t8, tmap_nz, p, tiles_x, tiles_y, total_tiles, noise_mode, strip_ok);
+}
+
+
 }  // namespace nbe
 
 using namespace nbe;
-
-#include <map>
-// Is the 4x4 filter behind this device pointer rank-1 (f = fy (x) fx)?  The packed kernel holds only the separable arithmetic (the
-// other code paths cost it registers: 472 bytes of spills and 15 % of its speed), so the host classifies a filter the first time
-// it sees its pointer -- one synchronous 64-byte read, never during a stream capture -- and remembers the answer.  A pointer
-// whose contents change to a non-separable filter later is caught by the kernel itself (it traps).  -1: cannot tell now.
-static int filter_is_rank1(const float* f, cudaStream_t stream) {
-    static std::mutex mu;
-    static std::map<const float*, int> seen;
-    std::lock_guard<std::mutex> lock(mu);
-    auto it = seen.find(f);
-    if (it != seen.end()) return it->second;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return -1;
-    float h[16];
-    if (cudaStreamSynchronize(stream) != cudaSuccess || cudaMemcpy(h, f, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
-    float ft[16];
-    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) ft[a * 4 + b] = h[(3 - a) * 4 + (3 - b)];
-    bool sep = ft[0] != 0.f;
-    for (int a = 1; a < 4; ++a)
-        for (int b = 1; b < 4; ++b) sep = sep && fabsf(ft[a * 4 + b] * ft[0] - ft[a * 4] * ft[b]) <= 1e-6f * fabsf(ft[a * 4 + b] * ft[0]) + 1e-30f;
-    if (seen.size() > 64) seen.clear();
-    seen[f] = sep ? 1 : 0;
-    return sep ? 1 : 0;
-}
 
 extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int N, int OH, int OW, int C, int TH, int TW, int pad,
                                      int t_cs, int64_t t_row_pitch, int64_t t_img_pitch,
@@ -516,7 +518,7 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
         int grid = kNumSMs * 2;
         if (total < grid) grid = (int)total;
         static const bool scalar_fp32 = getenv("NBE_FIR_SCALAR") != nullptr;      // A/B switch: the unpacked FP32 arithmetic
-        if (scalar_fp32 || filter_is_rank1(f, (cudaStream_t)stream) != 1) fir_act_tiled_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tm8, tn, p, tiles_x, tiles_y, (int)total, noise_mode, strip_ok);
+        if (scalar_fp32) fir_act_tiled_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tm8, tn, p, tiles_x, tiles_y, (int)total, noise_mode, strip_ok);
         else fir_act_tiled_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tm8, tn, p, tiles_x, tiles_y, (int)total, noise_mode, strip_ok);
         return launched("fir_act_tiled_kernel");
     }
