@@ -41,24 +41,31 @@ constexpr int TC_STAGES = 3;
 constexpr int TC_A_BYTES = 128 * 128;                               // 128 pixels x 64 bf16
 constexpr int TC_THREADS = 192;
 
+// TPC = position tiles per CTA: with 2, every weight tile that streams in feeds two accumulators -- the wide small-map layers
+// (encoder 256 -> 256 @16^2: 32 KiB of weights per 16 KiB of activations and K block) are bound by that L2 -> SM traffic
+template <int TPC>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = p.Cout * 128;
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + TC_STAGES * TC_A_BYTES;
+    uint8_t* smem_a = smem;                                         // [TC_STAGES][TPC][TC_A_BYTES]
+    uint8_t* smem_b = smem + TC_STAGES * TPC * TC_A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + TC_STAGES * b_bytes);
     // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full ; then the TMEM base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
 
     const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
 
-    // tile -> (n0, y0, x0)
-    int tile = blockIdx.x;
-    const int txi = tile % p.tiles_x; tile /= p.tiles_x;
-    const int tyi = tile % p.tiles_y; tile /= p.tiles_y;
-    const int n0 = tile * p.bn, y0 = tyi * p.bh, x0 = txi * p.bw;
+    // tile -> (n0, y0, x0); a tile past the end (odd tile count, TPC = 2) loads zeros (n0 >= N) and stores nothing
+    int n0s[TPC], y0s[TPC], x0s[TPC];
+#pragma unroll
+    for (int i = 0; i < TPC; ++i) {
+        int tile = blockIdx.x * TPC + i;
+        const int txi = tile % p.tiles_x; tile /= p.tiles_x;
+        const int tyi = tile % p.tiles_y; tile /= p.tiles_y;
+        n0s[i] = tile * p.bn; y0s[i] = tyi * p.bh; x0s[i] = txi * p.bw;
+    }
     const int num_kb = p.KK * p.k_chunks;
 
     if (threadIdx.x == 0) {
@@ -86,8 +93,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int kh = tap / p.K, kw = tap - kh * p.K;
                 mbar_wait(smem_u32(&bars[TC_STAGES + stage]), phase ^ 1);
                 const uint32_t full = smem_u32(&bars[stage]);
-                mbar_expect_tx(full, TC_A_BYTES + b_bytes);
-                tma_load_4d(smem_u32(smem_a + stage * TC_A_BYTES), &tmap_a, full, cc * 64, x0 * p.in_stride + kw + p.pad_off, y0 * p.in_stride + kh + p.pad_off, n0);
+                mbar_expect_tx(full, TPC * TC_A_BYTES + b_bytes);
+#pragma unroll
+                for (int i = 0; i < TPC; ++i)
+                    tma_load_4d(smem_u32(smem_a + (stage * TPC + i) * TC_A_BYTES), &tmap_a, full, cc * 64, x0s[i] * p.in_stride + kw + p.pad_off,
+                                y0s[i] * p.in_stride + kh + p.pad_off, n0s[i]);
                 tma_load_3d(smem_u32(smem_b + stage * b_bytes), &tmap_b, full, cc * 64, 0, tap);
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -102,10 +112,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 mbar_wait_fast(smem_u32(&bars[stage]), phase);
                 tcgen05_fence_after();
                 if (elect_one()) {
-                    const uint32_t a_lo = a_lo0 + (uint32_t)stage * (TC_A_BYTES >> 4), b_lo = b_lo0 + (uint32_t)stage * b_step;
+                    const uint32_t b_lo = b_lo0 + (uint32_t)stage * b_step;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)                     // 4 x (K = 16) per 64-channel block: +32 B inside the swizzle atom
-                        umma_bf16_lo(tmem_base, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (kb | k) != 0);
+                    for (int i = 0; i < TPC; ++i) {
+                        const uint32_t a_lo = a_lo0 + (uint32_t)(stage * TPC + i) * (TC_A_BYTES >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)                 // 4 x (K = 16) per 64-channel block: +32 B inside the swizzle atom
+                            umma_bf16_lo(tmem_base + (uint32_t)(i * p.Cout), a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (kb | k) != 0);
+                    }
                     umma_commit(smem_u32(&bars[TC_STAGES + stage]));    // frees the smem stage when these MMAs retire
                 }
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -119,16 +133,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int wi = m % p.bw;
         const int hi = (m / p.bw) % p.bh;
         const int ni = m / (p.bw * p.bh);
-        const int n = n0 + ni, oy = y0 + hi, ox = x0 + wi;
-        const bool valid = n < p.N;
         mbar_wait(smem_u32(&bars[2 * TC_STAGES]), 0);
         tcgen05_fence_after();
+#pragma unroll
+      for (int ti = 0; ti < TPC; ++ti) {
+        const int n = n0s[ti] + ni, oy = y0s[ti] + hi, ox = x0s[ti] + wi;
+        const bool valid = n < p.N;
         float nz = 0.f;
         if (valid && p.noise) nz = p.noise[(long long)n * p.noise_sn + (long long)oy * p.OW + ox] * p.noise_gain;
         const float pos_gain = p.gain, neg_gain = p.gain * p.alpha;
         for (int c0 = 0; c0 < p.Cout; c0 += 32) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ti * p.Cout + c0), v);
             if (valid) {
                 __nv_bfloat16* yp = p.y + ((long long)n * p.y_img_pitch + (long long)oy * p.y_row_pitch + ox) * p.y_cs + c0;
 #pragma unroll
@@ -157,6 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
         }
+      }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -761,14 +778,20 @@ static int conv_tc_impl(const void* x, const void* wq, void* y,
     }
     const int64_t tiles = (int64_t)p.tiles_x * p.tiles_y * ((N + p.bn - 1) / p.bn);
     NBE_REQUIRE(tiles <= INT32_MAX, "conv_tc: too many tiles");
-    const size_t smem = 1024 + (size_t)TC_STAGES * (TC_A_BYTES + Cout * 128) + 128;
+    // two tiles per CTA when the weight tile is at least as large as an activation tile and both accumulators fit in TMEM
+    static const bool one_tile = getenv("NBE_CONV_TC_ONE_TILE") != nullptr;          // A/B switch
+    const int tpc = (!one_tile && Cout >= 128 && 2 * Cout <= 512 && tiles >= 2 * kNumSMs) ? 2 : 1;
+    if (tpc == 2) { uint32_t c = 32; while (c < (uint32_t)(2 * Cout)) c <<= 1; p.tmem_cols = c; }
+    const size_t smem = 1024 + (size_t)TC_STAGES * (tpc * TC_A_BYTES + Cout * 128) + 128;
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_err = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return fail(NBE_ECUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    conv_tc_kernel<<<(int)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, p);
+    if (tpc == 2) conv_tc_kernel<2><<<(int)((tiles + 1) / 2), TC_THREADS, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, p);
+    else          conv_tc_kernel<1><<<(int)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, p);
     return launched("conv_tc_kernel");
 }
 
