@@ -28,7 +28,6 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import _lib
 from .engine import GanBrushOptions, TriadPaintEngine
 from .stylizer import RasterFeatureCanvas, dirty_area_alpha, _flat_blend_ok
 
@@ -252,7 +251,7 @@ class PaintingHelper:
         y, x, crop_margin = self.snap(meta)
         self._check_window(y, x)
         geom = self.engine.prepare_geom_input(stroke_patch)
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(self.engine.device):
             if self._raster is not None:
                 tiles = self._raster.render(geom, opts, y, x, crop_margin)
             elif self._band is not None:
