@@ -454,6 +454,14 @@ class BatchSession:
         self._u8 = torch.full((B, W, W), 255, dtype=torch.uint8, device=dev)           # host-fed variant: uint8 guidance patches
         self._crops = torch.stack([torch.arange(B, dtype=torch.int32, device=dev) * W, torch.zeros(B, dtype=torch.int32, device=dev)], dim=1).contiguous()
         self._stream = torch.cuda.Stream(device=dev)
+        # host-fed variant: two staging sets (uint8 patches, z, positions) filled on a copy-in stream + the event that frees each
+        self._in_stream = torch.cuda.Stream(device=dev)
+        self._in_flip = 0
+        self._in_sets = []
+        for _ in range(2):
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._in_sets.append((torch.empty_like(self._u8), torch.empty_like(self._z), torch.empty_like(self._pos), ev))
         with torch.no_grad(), torch.cuda.device(dev):
             self._stream.wait_stream(torch.cuda.current_stream())
             engine._force_overlap = True                             # warm up the code path the capture takes (side-stream branch)
@@ -525,14 +533,35 @@ class BatchSession:
         return self._tail() if self.split else self._out
 
     def run_host(self, patches_u8: torch.Tensor, z: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
-        """Pinned host inputs (uint8 guidance patches [B,W,W], z float64, positions int64) -> the graph's output buffer."""
+        """Pinned host inputs (uint8 guidance patches [B,W,W], z float64, positions int64) -> the graph's output buffer.
+        The uploads go through two staging sets on a copy-in stream, so the inputs of step i+1 cross PCIe while step i computes
+        (the graph's own input buffers are still being read then); the main stream only waits for the upload's event."""
         eng, W = self.engine, self.engine.patch_width
-        self._u8.copy_(patches_u8, non_blocking=True)
-        self._z.copy_(z, non_blocking=True)
-        self._pos.copy_(positions, non_blocking=True)
         with torch.cuda.device(eng.device):
-            _lib.call('nbe_gather_geom_patches', _lib.ptr(self._u8), self.B * W, W, _lib.ptr(self._crops), _lib.ptr(self._geom), self.B, W,
+            main = torch.cuda.current_stream()
+            if self._in_stream is None or os.environ.get('NBE_E2E_SINGLE_STREAM') is not None:      # A/B switch: uploads on the main stream
+                u8 = self._u8
+                u8.copy_(patches_u8, non_blocking=True)
+                self._z.copy_(z, non_blocking=True)
+                self._pos.copy_(positions, non_blocking=True)
+            else:
+                k = self._in_flip
+                self._in_flip ^= 1
+                u8, zs, ps, free = self._in_sets[k]
+                with torch.cuda.stream(self._in_stream):
+                    self._in_stream.wait_event(free)                 # the gather of two steps ago is done with this set
+                    u8.copy_(patches_u8, non_blocking=True)
+                    zs.copy_(z, non_blocking=True)
+                    ps.copy_(positions, non_blocking=True)
+                    up = torch.cuda.Event()
+                    up.record(self._in_stream)
+                main.wait_event(up)
+                self._z.copy_(zs, non_blocking=True)
+                self._pos.copy_(ps, non_blocking=True)
+            _lib.call('nbe_gather_geom_patches', _lib.ptr(u8), self.B * W, W, _lib.ptr(self._crops), _lib.ptr(self._geom), self.B, W,
                       _lib.stream())
+            if u8 is not self._u8:
+                free.record(main)
         self._graph.replay()
         return self._tail() if self.split else self._out
 
