@@ -40,6 +40,8 @@ _SIGNATURES = {
     'nbe_conv_tc_bf16_ex': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P, _P, _L, _F, _P, _F, _F, _F, _P, _P],
     'nbe_conv3x3_flat_bf16': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _P, _P, _L, _F, _P, _F, _F, _F, _P, _P],
     'nbe_reflect_pad_nchw_f32': [_P, _P, _L, _I, _I, _I, _I, _P],
+    'nbe_affine_nhwc_bf16': [_P, _I, _L, _L, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P],
+    'nbe_affine_nchw_f32': [_P, _P, _I, _I, _I, _P, _P, _P],
     'nbe_count_stroke_pixels': [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     'nbe_torgb_canvas': [_P, _I, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     'nbe_canvas_composite': [_P, _P, _P, _L, _P, _I, _P, _P, _I, _I, _I, _I, _P],

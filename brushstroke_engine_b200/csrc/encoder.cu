@@ -6,6 +6,7 @@
 //   * bilinear2x_pad_kernel   : bilinear x2 (align_corners = True) + reflect pad 1 in one pass
 // Reference: forger/experimental/autoenc/simple_autoencoder.py:95-126 (SingleConvolution / ScaleUp), 155-199, 251-261.
 #include "common.cuh"
+#include <algorithm>
 
 namespace nbe {
 
@@ -173,6 +174,44 @@ reflect_pad_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, long
     }
 }
 
+// y[n, p, c] = (x[n, p, c] * scale[c] + shift[c]) * next_scale[n, c]: eval-mode BatchNorm AFTER the activation
+// (simple_autoencoder.py:100-103, the --neg_slope variant) for the feature maps that leave the encoder, optionally times the
+// consuming generator layer's styles.  8 channels (16 bytes) per thread; source and destination have their own pitches.
+__global__ void __launch_bounds__(256)
+affine_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, long long x_row_pitch, long long x_img_pitch,
+                   __nv_bfloat16* __restrict__ y, int y_cs, long long y_row_pitch, long long y_img_pitch,
+                   int N, int H, int W, int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                   const float* __restrict__ next_scale) {
+    const int CV = C / 8;
+    const long long total = (long long)N * H * W * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long t = idx / CV;
+        const int px = (int)(t % W); t /= W;
+        const int py = (int)(t % H);
+        const int n = (int)(t / H);
+        int4 v = *reinterpret_cast<const int4*>(x + ((long long)n * x_img_pitch + (long long)py * x_row_pitch + px) * x_cs + cv * 8);
+        __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = cv * 8 + k;
+            float a = fmaf(__bfloat162float(e[k]), scale[c], shift[c]);
+            if (next_scale) a *= next_scale[(long long)n * C + c];
+            e[k] = __float2bfloat16_rn(a);
+        }
+        *reinterpret_cast<int4*>(y + ((long long)n * y_img_pitch + (long long)py * y_row_pitch + px) * y_cs + cv * 8) = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+affine_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long total, int C, int HW,
+                       const float* __restrict__ scale, const float* __restrict__ shift) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((idx / HW) % C);
+        y[idx] = x[idx] * scale[c] + shift[c];                    // two roundings, like torch's batch_norm in eval mode restated as scale / shift
+    }
+}
+
 }  // namespace nbe
 
 using namespace nbe;
@@ -224,4 +263,30 @@ extern "C" int nbe_reflect_pad_nchw_f32(const float* x, float* y, int64_t NC, in
     if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
     reflect_pad_nchw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, NC, H, W, pad, upsample2x ? 1 : 0);
     return launched("reflect_pad_nchw_kernel");
+}
+
+extern "C" int nbe_affine_nhwc_bf16(const void* x, int x_cs, int64_t x_row_pitch, int64_t x_img_pitch,
+                                    void* y, int y_cs, int64_t y_row_pitch, int64_t y_img_pitch,
+                                    int N, int H, int W, int C, const float* scale, const float* shift, const float* next_scale,
+                                    nbe_stream_t stream) {
+    NBE_REQUIRE(x && y && scale && shift && N >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "affine_nhwc: bad arguments");
+    NBE_REQUIRE(x_cs % 8 == 0 && x_cs >= C && y_cs % 8 == 0 && y_cs >= C, "affine_nhwc: channel strides must be multiples of 8");
+    NBE_REQUIRE(x_row_pitch >= W && x_img_pitch >= x_row_pitch * H && y_row_pitch >= W && y_img_pitch >= y_row_pitch * H, "affine_nhwc: bad pitches");
+    NBE_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "affine_nhwc: tensors must be 16-byte aligned");
+    if (N == 0) return NBE_OK;
+    const long long total = (long long)N * H * W * (C / 8);
+    const long long blocks = std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+    affine_nhwc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_cs, x_row_pitch, x_img_pitch,
+        (__nv_bfloat16*)y, y_cs, y_row_pitch, y_img_pitch, N, H, W, C, scale, shift, next_scale);
+    return launched("affine_nhwc_kernel");
+}
+
+extern "C" int nbe_affine_nchw_f32(const float* x, float* y, int N, int C, int HW, const float* scale, const float* shift,
+                                   nbe_stream_t stream) {
+    NBE_REQUIRE(x && y && scale && shift && N >= 0 && C >= 1 && HW >= 1, "affine_nchw: bad arguments");
+    if (N == 0) return NBE_OK;
+    const long long total = (long long)N * C * HW;
+    const long long blocks = std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+    affine_nchw_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, total, C, HW, scale, shift);
+    return launched("affine_nchw_f32_kernel");
 }

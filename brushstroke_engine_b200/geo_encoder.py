@@ -53,10 +53,16 @@ class GeometryEncoder:
         n_enc = 1 + len(cfg.down_filters) + len(cfg.post_filters)
         strides = [1] + [2] * len(cfg.down_filters) + [1] * len(cfg.post_filters)
         pads = [3] + [1] * (n_enc - 1)
-        for i in range(n_enc):
-            self._layers.append(self._fold(params, f'encoder.model.{i}.conv') + (strides[i], pads[i], False))
-        for i in range(max(self.res)):
-            self._layers.append(self._fold(params, f'decoder.model.{i}.conv.conv') + (1, 1, True))
+        self._v2 = bool(getattr(cfg, 'bn_after_activation', False))
+        self._slopes = []                  # LeakyReLU slope per entry of self._layers
+        if self._v2:
+            self._build_v2(params, n_enc, strides, pads)
+        else:
+            for i in range(n_enc):
+                self._layers.append(self._fold(params, f'encoder.model.{i}.conv') + (strides[i], pads[i], False))
+            for i in range(max(self.res)):
+                self._layers.append(self._fold(params, f'decoder.model.{i}.conv.conv') + (1, 1, True))
+            self._slopes = [float(cfg.neg_slope)] * len(self._layers)
         self._n_enc = n_enc
         self._ws = {}                      # (batch, H) -> workspace, least recently used first
         self.max_cached_batch_sizes = 32
@@ -86,6 +92,55 @@ class GeometryEncoder:
                     wq = torch.empty((9, cout, _cs(cin)), dtype=torch.bfloat16, device=self.device)
                     _lib.call('nbe_prepare_weights_bf16', _lib.ptr(w), _lib.ptr(wq), cout, cin, 3, 0, _lib.stream())
                     self._wq.append(wq)
+                if self._v2:
+                    self._dec_wq = []
+                    for (w_conv, w_tr, b) in self._dec:
+                        cout, cin = w_tr.shape[0], w_tr.shape[1]
+                        if cout % 128 or max(self.res) > 1:
+                            raise RuntimeError('GeometryEncoder: the tensor-core path of the --neg_slope variant covers one ScaleUpV2 stage with a '
+                                               'multiple of 128 output channels')
+                        wq = torch.empty((9, cout, _cs(cin)), dtype=torch.bfloat16, device=self.device)
+                        _lib.call('nbe_prepare_weights_bf16', _lib.ptr(w_tr), _lib.ptr(wq), cout, cin, 3, 0, _lib.stream())
+                        self._dec_wq.append(wq)
+                    f = torch.zeros((4, 4), dtype=torch.float32, device=self.device)
+                    f[1, 1] = 1.0               # the FIR pass as a crop: y[oy, ox] = T[oy + 1, ox + 1] (ConvTranspose2d padding 1, output_padding 1)
+                    self._f_crop = f
+                    self._v2_ws = {}
+
+    def _bn_scale_shift(self, p, prefix):
+        g, beta = p[f'{prefix}.weight'].double(), p[f'{prefix}.bias'].double()
+        m, v = p[f'{prefix}.running_mean'].double(), p[f'{prefix}.running_var'].double()
+        scale = g / torch.sqrt(v + self.cfg.bn_eps)
+        return scale, beta - m * scale
+
+    def _build_v2(self, p, n_enc, strides, pads):
+        """The ``--neg_slope`` variant: every stage is conv -> LeakyReLU -> eval BatchNorm (simple_autoencoder.py:100-103) and
+        the decoder stages are ``ScaleUpV2`` (ConvTranspose2d 3x3 stride 2 -> LeakyReLU -> BatchNorm, :128-148).  The BatchNorm
+        of stage k, y = s * a + t, is folded FORWARD into the convolution of stage k+1 -- conv(y) = conv_{w * s}(a) + sum_i t_i
+        sum_taps w[o, i], exact because a reflect-padded constant field is constant -- so every stage stays one
+        conv + bias + LeakyReLU launch; only the feature maps that leave the encoder (g0, and every ScaleUpV2 output) get
+        their BatchNorm as an explicit per-channel scale / shift (``nbe_affine_*``), and the transposed convolutions read those."""
+        cfg, dev = self.cfg, self.device
+        n_pre_down = 1 + len(cfg.down_filters)
+        prev = None
+        for i in range(n_enc):
+            prefix = f'encoder.model.{i}.conv'
+            w, b = p[f'{prefix}.0.weight'].double(), p[f'{prefix}.0.bias'].double()
+            if prev is not None:
+                b = b + (w.sum(dim=(2, 3)) * prev[1][None, :]).sum(dim=1)
+                w = w * prev[0][None, :, None, None]
+            self._layers.append((w.to(dev, torch.float32).contiguous(), b.to(dev, torch.float32).contiguous(), strides[i], pads[i], False))
+            self._slopes.append(float(cfg.neg_slope if i < n_pre_down else cfg.post_neg_slope))
+            prev = self._bn_scale_shift(p, f'{prefix}.2')
+        self._feat_affine = [tuple(t.to(dev, torch.float32).contiguous() for t in prev)]      # BatchNorm of g0, then of every ScaleUpV2
+        self._dec = []                      # ScaleUpV2 stages: (conv-form weight [Cout,Cin,3,3], ConvTranspose2d weight as [Cout,Cin,3,3], bias)
+        for i in range(max(self.res)):
+            prefix = f'decoder.model.{i}.conv'
+            wt = p[f'{prefix}.0.weight'].to(dev, torch.float32)                       # [Cin, Cout, 3, 3]
+            w_tr = wt.permute(1, 0, 2, 3).contiguous()                                 # T[2Y+kh, 2X+kw] += w_tr[o, i, kh, kw] x[Y, X]
+            w_conv = w_tr.flip([2, 3]).contiguous()                                    # the same as a correlation over the zero-stuffed input
+            self._dec.append((w_conv, w_tr, p[f'{prefix}.0.bias'].to(dev, torch.float32).contiguous()))
+            self._feat_affine.append(tuple(t.to(dev, torch.float32).contiguous() for t in self._bn_scale_shift(p, f'{prefix}.2')))
 
     def _fold(self, p, prefix):
         """conv -> eval BatchNorm  ==  conv with w' = w * g/sqrt(v+eps), b' = (b - m) * g/sqrt(v+eps) + beta."""
@@ -142,6 +197,27 @@ class GeometryEncoder:
             self._ws[key] = self._ws.pop(key)
         return ws
 
+    def _launch_conv(self, i, cur, B, h, ho, y_ptr, y_cs, rp, ip, next_scale, st):
+        """3x3 layer ``i`` (folded weights + bias + LeakyReLU) from the bordered NHWC buffer ``cur`` ([B, h+2, h+2, cs]) to the
+        NHWC destination (y_ptr, channel stride y_cs, row / image pitches rp / ip in pixels), on the kernel that suits its shape."""
+        w, b, stride, pad, up = self._layers[i]
+        cout, cin = w.shape[0], w.shape[1]
+        slope = self._slopes[i]
+        if stride == 2 and not up and self._flat_s2 and cin % 64 == 0 and cur.shape[3] == cin and cout % 128 == 0 and h % 2 == 0 and ho >= self._flat_min:
+            # down-sampling layer at its algorithmic cost: parity planes of the bordered input on the flat CTA-pair kernel
+            # (below 32^2 the per-image tiling pads too much; the per-tap kernel batches images into one tile)
+            _lib.call('nbe_conv3x3s2_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, h, h, cin, cout, y_cs, rp, ip,
+                      _lib.ptr(b), slope, 1.0, -1.0, _lib.ptr(next_scale), st)
+        elif stride == 1 and self._flat_s2 and cout % 128 == 0 and ho >= 32:
+            # ScaleUp conv over the bordered bilinear map: 'valid' flat conv, one pass per 128 output channels
+            _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cin, cur.shape[3],
+                      cur.shape[2], 1, cout, y_cs, rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0, -1.0,
+                      _lib.ptr(next_scale), st)
+        else:
+            _lib.call('nbe_conv_tc_bf16_ex', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cur.shape[3], cur.shape[3],
+                      cout, y_cs, 3, 1, stride, cur.shape[1], cur.shape[2], rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0,
+                      -1.0, _lib.ptr(next_scale), st)
+
     @_lib.profiled('encode')
     def encode_into(self, geom, dests, scales=None, scales_ready=None):
         """Run the bf16 encoder and write feature map ``r`` (index into ``self.res``) into ``dests[r] = (tensor, c_off)``:
@@ -158,8 +234,8 @@ class GeometryEncoder:
         res = self.res if isinstance(self.res, (list, tuple)) else [self.res]
         max_res = max(res)
         ws = self._workspace(B, H)
-        slope = float(self.cfg.neg_slope)
-        n_layers = self._n_enc + max_res
+        slope = self._slopes[0]
+        n_layers = self._n_enc + (0 if self._v2 else max_res)
         with torch.cuda.device(self.device):
             st = _lib.stream()
             wi = 0
@@ -195,10 +271,20 @@ class GeometryEncoder:
                 ho = h // stride
                 feat_idx = i - (self._n_enc - 1)            # >= 0: this layer's output is feature map `feat_idx`
                 nxt = ws[wi]; wi += 1
-                is_feat = feat_idx >= 0 and feat_idx in res
+                is_feat = feat_idx >= 0 and feat_idx in res and not self._v2
                 last_layer = i == n_layers - 1
                 next_scale = None
                 direct = is_feat and last_layer             # nothing else consumes it: write (pre-scaled) straight into the destination
+                if self._v2 and last_layer:
+                    # --neg_slope variant: the last stage's activation goes to a dense map; its BatchNorm, the hand-over to the
+                    # generator and the ScaleUpV2 stage follow in _finish_v2
+                    a_last = torch.empty((B, ho, ho, cout), dtype=torch.bfloat16, device=self.device)
+                    self._launch_conv(i, cur, B, h, ho, a_last.data_ptr(), cout, ho, ho * ho, None, st)
+                    if scales_ready is not None:
+                        torch.cuda.current_stream().wait_event(scales_ready)
+                        scales_ready = None
+                    self._finish_v2(a_last, B, ho, res, dests, scales, st)
+                    break
                 if is_feat and scales_ready is not None:
                     torch.cuda.current_stream().wait_event(scales_ready)      # first consumer of the styles / destination buffers
                     scales_ready = None
@@ -219,21 +305,7 @@ class GeometryEncoder:
                     y_cs, rp, ip = nxt.shape[3], ho + 2, (ho + 2) * (ho + 2)
                     y_ptr = nxt.data_ptr() + 2 * ((ho + 2) + 1) * y_cs
                     padded_out = nxt
-                cin = w.shape[1]
-                if stride == 2 and not up and self._flat_s2 and cin % 64 == 0 and cur.shape[3] == cin and cout % 128 == 0 and h % 2 == 0 and ho >= self._flat_min:
-                    # down-sampling layer at its algorithmic cost: parity planes of the bordered input on the flat CTA-pair kernel
-                    # (below 32^2 the per-image tiling pads too much; the per-tap kernel batches images into one tile)
-                    _lib.call('nbe_conv3x3s2_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, h, h, cin, cout, y_cs, rp, ip,
-                              _lib.ptr(b), slope, 1.0, -1.0, _lib.ptr(next_scale), st)
-                elif stride == 1 and self._flat_s2 and cout % 128 == 0 and ho >= 32:
-                    # ScaleUp conv over the bordered bilinear map: 'valid' flat conv, one pass per 128 output channels
-                    _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cin, cur.shape[3],
-                              cur.shape[2], 1, cout, y_cs, rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0, -1.0,
-                              _lib.ptr(next_scale), st)
-                else:
-                    _lib.call('nbe_conv_tc_bf16_ex', _lib.ptr(cur), _lib.ptr(self._wq[i]), y_ptr, B, ho, ho, cur.shape[3], cur.shape[3],
-                              cout, y_cs, 3, 1, stride, cur.shape[1], cur.shape[2], rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0,
-                              -1.0, _lib.ptr(next_scale), st)
+                self._launch_conv(i, cur, B, h, ho, y_ptr, y_cs, rp, ip, next_scale, st)
                 h = ho
                 if padded_out is not None:
                     _lib.call('nbe_reflect_border_nhwc_bf16', _lib.ptr(padded_out), B, h + 2, h + 2, cout, padded_out.shape[3], st)
@@ -246,6 +318,80 @@ class GeometryEncoder:
                     src = feat_dense if sc is None else (feat_dense.float() * sc.to(self.device)[:, None, None, :]).to(torch.bfloat16)
                     dst[:, :, :ho, c_off:c_off + cout] = src
         return dests
+
+    def _affine_f32(self, x, affine):
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.call('nbe_affine_nchw_f32', _lib.ptr(x), _lib.ptr(y), x.shape[0], x.shape[1], x.shape[2] * x.shape[3],
+                      _lib.ptr(affine[0]), _lib.ptr(affine[1]), _lib.stream())
+        return y
+
+    def _encode_f32_v2(self, x, res, max_res):
+        """FP32 parity mode of the --neg_slope variant (see ``_build_v2``): folded conv + LeakyReLU per stage, explicit BatchNorm on
+        g0 and on every ScaleUpV2 output; ConvTranspose2d(3, stride 2, padding 1, output_padding 1) = zero-stuffing
+        (``upfirdn2d`` with a 1x1 filter, up = 2, padding 1) followed by a valid correlation with the flipped kernel."""
+        from .upfirdn2d import upfirdn2d
+        for i, (w, b, stride, pad, up) in enumerate(self._layers):
+            x = x.contiguous()
+            xp = torch.empty((x.shape[0], x.shape[1], x.shape[2] + 2 * pad, x.shape[3] + 2 * pad), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                _lib.call('nbe_reflect_pad_nchw_f32', _lib.ptr(x), _lib.ptr(xp), x.shape[0] * x.shape[1], x.shape[2], x.shape[3], pad, 0,
+                          _lib.stream())
+            x = conv2d_f32(xp, w, padding=0, stride=stride, bias=b, act=ACT_LRELU, alpha=self._slopes[i], gain=1.0)
+        x = self._affine_f32(x, self._feat_affine[0])
+        results = [x]
+        one = torch.ones((1, 1), dtype=torch.float32, device=x.device)
+        for j in range(max_res):
+            w_conv, _, b = self._dec[j]
+            u = upfirdn2d(x, one, up=2, padding=[1, 1, 1, 1])                   # [B, C, 2h + 2, 2h + 2]: x at odd positions, zeros elsewhere
+            a = conv2d_f32(u, w_conv, padding=0, stride=1, bias=b, act=ACT_LRELU, alpha=float(self.cfg.neg_slope), gain=1.0)
+            x = self._affine_f32(a, self._feat_affine[j + 1])
+            results.append(x)
+        if not isinstance(res, (list, tuple)):
+            res = [res]
+        return [results[r] for r in res]
+
+    def _finish_v2(self, a_last, B, h, res, dests, scales, st):
+        """Tail of the --neg_slope variant on the bf16 path: g0 = BN(a_last) into its destination (times the consuming layer's
+        styles) and, for feature 1, ScaleUpV2: g0 in the zero-gapped flat layout -> transposed conv on tcgen05
+        (``nbe_convT3x3s2_flat_bf16``, full (2h+1)^2 result) -> crop to [1, 2h] x [1, 2h] + bias + LeakyReLU (the FIR pass with a
+        one-tap filter) -> BatchNorm (+ styles) into the destination."""
+        dev = self.device
+        C0 = a_last.shape[3]
+
+        def hand_over(src, src_cs, src_rp, src_ip, R, C, affine, feat):
+            dst, c_off = dests[res.index(feat)]
+            assert dst.dtype == torch.bfloat16 and dst.shape[0] == B and dst.shape[1] == R and dst.shape[2] >= R and dst.shape[3] >= c_off + C
+            sc = None
+            if scales is not None and scales[res.index(feat)] is not None:
+                sc = scales[res.index(feat)].to(dev, torch.float32).contiguous()
+                assert sc.shape == (B, C)
+            _lib.call('nbe_affine_nhwc_bf16', src, src_cs, src_rp, src_ip, dst.data_ptr() + 2 * c_off, dst.shape[3], dst.shape[2],
+                      R * dst.shape[2], B, R, R, C, _lib.ptr(affine[0]), _lib.ptr(affine[1]), _lib.ptr(sc), st)
+
+        if 0 in res:
+            hand_over(a_last.data_ptr(), C0, h, h * h, h, C0, self._feat_affine[0], 0)
+        if max(res) >= 1:
+            key = (B, h)
+            wsv = self._v2_ws.get(key)
+            if wsv is None:
+                cout = self._dec[0][1].shape[0]
+                wsv = self._v2_ws[key] = (torch.zeros((B, h, h + 1, _cs(C0)), dtype=torch.bfloat16, device=dev),          # g0, zero-gapped
+                                          torch.empty((B, 2 * h + 2, 2 * h + 2, cout), dtype=torch.bfloat16, device=dev),  # T
+                                          torch.empty((B, 2 * h, 2 * h, cout), dtype=torch.bfloat16, device=dev))         # lrelu(crop(T) + b)
+                while len(self._v2_ws) > 4:
+                    self._v2_ws.pop(next(iter(self._v2_ws)))
+            xg, T, a1 = wsv
+            cout = T.shape[3]
+            _lib.call('nbe_affine_nhwc_bf16', a_last.data_ptr(), C0, h, h * h, xg.data_ptr(), xg.shape[3], h + 1, h * (h + 1),
+                      B, h, h, C0, _lib.ptr(self._feat_affine[0][0]), _lib.ptr(self._feat_affine[0][1]), None, st)
+            _lib.call('nbe_convT3x3s2_flat_bf16', _lib.ptr(xg), _lib.ptr(self._dec_wq[0]), _lib.ptr(T), B, h, h, C0, xg.shape[3], h + 1,
+                      cout, cout, 2 * h + 2, (2 * h + 2) * (2 * h + 2), None, st)
+            _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(T), _lib.ptr(self._f_crop), _lib.ptr(a1), B, 2 * h, 2 * h, cout, 2 * h + 1, 2 * h + 1, 1,
+                      cout, 2 * h + 2, (2 * h + 2) * (2 * h + 2), cout, 2 * h, 4 * h * h, 1.0, None, None, 0, 0.0, _lib.ptr(self._dec[0][2]),
+                      float(self.cfg.neg_slope), 1.0, -1.0, None, st)
+            if 1 in res:
+                hand_over(a1.data_ptr(), cout, 2 * h, 4 * h * h, 2 * h, cout, self._feat_affine[1], 1)
 
     def _encode_bf16(self, geom, res) -> List[torch.Tensor]:
         B, H = geom.shape[0], geom.shape[2]
@@ -274,6 +420,8 @@ class GeometryEncoder:
         x = self.preprocess(geom.to(torch.float32))
         results = []
         max_res = res if not isinstance(res, (list, tuple)) else max(res)
+        if self._v2:
+            return self._encode_f32_v2(x, res, max_res)
         for i, (w, b, stride, pad, up) in enumerate(self._layers[: self._n_enc + max_res]):
             # reflect padding (of the bilinear x2 map for ScaleUp layers) in one kernel: no torch compute on this path
             x = x.contiguous()

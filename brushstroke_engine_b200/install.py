@@ -72,46 +72,66 @@ def generator_config_from_reference(G) -> GeneratorConfig:
                            color_format=getattr(last.torgb, 'color_format', 'triad'))
 
 
-def _check_encoder_layer_order(enc) -> float:
-    """The B200 encoder folds eval-mode BatchNorm into the preceding convolution, which is exact only for the default layer
-    order conv -> BatchNorm -> LeakyReLU (simple_autoencoder.py:102-105) with bilinear ``ScaleUp`` decoder stages.  The
-    ``--neg_slope`` variant (``batchnorm_after_activation=True`` + ``ScaleUpV2``, simple_autoencoder.py:48-53,130-145) has
-    conv -> LeakyReLU -> BatchNorm and transposed-conv up-sampling: refuse it by name instead of producing wrong features.
-    Returns the (single) LeakyReLU slope of the checked layers."""
+def _encoder_layer_order(enc) -> dict:
+    """Read the stage layout of a reference ``sauto`` autoencoder.  Two layouts exist (simple_autoencoder.py:48-53):
+      * default: every stage conv -> BatchNorm -> LeakyReLU with one slope, bilinear ``ScaleUp`` decoder stages (eval-mode
+        BatchNorm folds into the preceding convolution);
+      * ``--neg_slope``: conv -> LeakyReLU -> BatchNorm (``batchnorm_after_activation=True``), the pre / down stages and the
+        ``ScaleUpV2`` (ConvTranspose2d) decoder stages with the flag's slope, the post stages with LeakyReLU's default
+        (simple_autoencoder.py:180-185) -- BatchNorm folds FORWARD into the next convolution (``GeometryEncoder._build_v2``).
+    Anything else (mixed orders, a decoder ``first`` layer, unknown stage modules) is refused by name instead of producing
+    wrong features.  Returns the EncoderConfig fields that describe the layout."""
     import torch.nn as nn
-    slopes = set()
-    stages = list(enc.encoder.model) + [m for m in enc.decoder.model if hasattr(m, 'conv')]
-    for m in stages:
-        if type(m).__name__ == 'ScaleUpV2' or (hasattr(m, 'conv') and isinstance(m.conv, nn.Sequential)
-                                                and isinstance(m.conv[0], nn.ConvTranspose2d)):
-            raise RuntimeError('encoder_config_from_reference: unsupported geometry encoder: ScaleUpV2 (transposed-conv up-sampling of '
-                               'the --neg_slope variant, simple_autoencoder.py:130-145); only the default sauto layout is built')
+    if getattr(enc.decoder, 'first', None) is not None:
+        raise RuntimeError('encoder_config_from_reference: unsupported geometry encoder: decoder pre layer (--decoder_pre_filters > 0, '
+                           'simple_autoencoder.py:217-231)')
+    n_down = enc.encoder.num_down_layers
+    n_feat = max(enc.res) if isinstance(enc.res, (list, tuple)) else int(enc.res)
+    dec_stages = [m for m in enc.decoder.model if hasattr(m, 'conv')][:max(n_feat, 0)]
+    orders, slopes = [], []
+    for m in list(enc.encoder.model) + dec_stages:
+        transposed = isinstance(m.conv, nn.Sequential) and isinstance(m.conv[0], nn.ConvTranspose2d)        # ScaleUpV2
         single = m.conv if isinstance(m.conv, nn.Sequential) else m.conv.conv       # SingleConvolution / ScaleUp(SingleConvolution)
         kinds = [type(x) for x in single]
-        if len(kinds) != 3 or not issubclass(kinds[0], nn.Conv2d):
+        if len(kinds) != 3 or not issubclass(kinds[0], (nn.Conv2d, nn.ConvTranspose2d)):
             raise RuntimeError(f'encoder_config_from_reference: unsupported encoder stage {[k.__name__ for k in kinds]}')
-        if issubclass(kinds[1], nn.LeakyReLU) and issubclass(kinds[2], nn.BatchNorm2d):
-            raise RuntimeError('encoder_config_from_reference: unsupported geometry encoder: layer order conv -> LeakyReLU -> BatchNorm '
-                               '(batchnorm_after_activation=True, the --neg_slope variant, simple_autoencoder.py:48-53,102-105); '
-                               'BatchNorm cannot be folded into the preceding convolution in that order')
-        if not (issubclass(kinds[1], nn.BatchNorm2d) and issubclass(kinds[2], nn.LeakyReLU)):
+        if issubclass(kinds[1], nn.BatchNorm2d) and issubclass(kinds[2], nn.LeakyReLU) and not transposed:
+            orders.append('bn_act'); slopes.append(float(single[2].negative_slope))
+        elif issubclass(kinds[1], nn.LeakyReLU) and issubclass(kinds[2], nn.BatchNorm2d):
+            orders.append('act_bn_T' if transposed else 'act_bn'); slopes.append(float(single[1].negative_slope))
+            if transposed:
+                c = single[0]
+                if (tuple(c.kernel_size), tuple(c.stride), tuple(c.padding), tuple(c.output_padding), tuple(c.dilation)) != \
+                        ((3, 3), (2, 2), (1, 1), (1, 1), (1, 1)):
+                    raise RuntimeError('encoder_config_from_reference: unsupported ScaleUpV2 geometry (expected ConvTranspose2d 3x3, stride 2, '
+                                       'padding 1, output_padding 1, simple_autoencoder.py:133-141)')
+        else:
             raise RuntimeError(f'encoder_config_from_reference: unsupported encoder stage {[k.__name__ for k in kinds]}')
-        slopes.add(float(single[2].negative_slope))
-    if len(slopes) != 1:
-        raise RuntimeError(f'encoder_config_from_reference: layers use different LeakyReLU slopes {sorted(slopes)}')
-    return slopes.pop()
+    n_enc = len(enc.encoder.model)
+    if all(o == 'bn_act' for o in orders):
+        if len(set(slopes)) != 1:
+            raise RuntimeError(f'encoder_config_from_reference: layers use different LeakyReLU slopes {sorted(set(slopes))}')
+        return dict(neg_slope=slopes[0])
+    if all(o == 'act_bn' for o in orders[:n_enc]) and all(o == 'act_bn_T' for o in orders[n_enc:]):
+        main, post = set(slopes[:1 + n_down] + slopes[n_enc:]), set(slopes[1 + n_down:n_enc])
+        if len(main) != 1 or len(post) > 1:
+            raise RuntimeError(f'encoder_config_from_reference: layers use different LeakyReLU slopes {sorted(main)} / {sorted(post)}')
+        return dict(neg_slope=main.pop(), bn_after_activation=True, post_neg_slope=post.pop() if post else 0.01)
+    raise RuntimeError(f'encoder_config_from_reference: unsupported geometry encoder: mixed stage layouts {orders} (expected the default '
+                       'sauto layout or the --neg_slope variant with batchnorm_after_activation=True and ScaleUpV2, '
+                       'simple_autoencoder.py:48-53)')
 
 
 def encoder_config_from_reference(enc) -> EncoderConfig:
     e, d = enc.encoder, enc.decoder
-    slope = _check_encoder_layer_order(enc)
+    layout = _encoder_layer_order(enc)
     convs = [m.conv[0] for m in e.model]
     n_down = e.num_down_layers
     return EncoderConfig(in_channels=e.in_channels, pre_filters=convs[0].out_channels,
                          down_filters=tuple(c.out_channels for c in convs[1:1 + n_down]),
                          post_filters=tuple(c.out_channels for c in convs[1 + n_down:]),
                          up_filters=tuple(d.up_layer_filters), encode_resolutions=tuple(enc.res),
-                         preproc_type=enc.preproc_name, neg_slope=slope)
+                         preproc_type=enc.preproc_name, **layout)
 
 
 def engine_from_reference(ref_engine, mode: str = 'bf16'):

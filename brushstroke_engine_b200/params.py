@@ -98,8 +98,11 @@ class GeneratorConfig:
 
 @dataclasses.dataclass(frozen=True)
 class EncoderConfig:
-    """Default-flag ``sauto`` geometry autoencoder (simple_autoencoder.py:155-199,
-    model_from_flags).  Only the encode path is described."""
+    """``sauto`` geometry autoencoder (simple_autoencoder.py:155-199, model_from_flags); only the encode path is described.
+    Default flags: every stage is conv -> BatchNorm -> LeakyReLU(0.01) and the decoder up-samples bilinearly (``ScaleUp``).
+    ``bn_after_activation=True`` is the ``--neg_slope`` variant (simple_autoencoder.py:48-53): conv -> LeakyReLU -> BatchNorm,
+    the pre / down layers and the decoder use ``neg_slope``, the post layers keep ``post_neg_slope`` (their constructor gets no
+    slope, :180-185), and the decoder stages are ``ScaleUpV2`` (ConvTranspose2d 3x3 stride 2, :128-148)."""
     in_channels: int = 1
     pre_filters: int = 64
     down_filters: Sequence[int] = (128, 256, 256)
@@ -109,6 +112,8 @@ class EncoderConfig:
     preproc_type: str | None = None
     bn_eps: float = 1e-5
     neg_slope: float = 0.01
+    bn_after_activation: bool = False
+    post_neg_slope: float = 0.01
 
     def feature_channels(self, res: int) -> int:
         return ([self.post_filters[-1]] + list(self.up_filters))[res]
@@ -170,20 +175,23 @@ def init_encoder_params(cfg: EncoderConfig = EncoderConfig(), seed: int = 1, per
     that eval-BN folding is exercised."""
     g = torch.Generator().manual_seed(seed)
     p: Bundle = {}
+    bn = 2 if cfg.bn_after_activation else 1          # index of the BatchNorm inside the stage's nn.Sequential
 
-    def conv(prefix, cin, cout, k):
+    def conv(prefix, cin, cout, k, transposed=False):
         std = math.sqrt(2.0 / ((cin + cout) * k * k))
-        p[f'{prefix}.0.weight'] = _randn(g, cout, cin, k, k) * std
+        p[f'{prefix}.0.weight'] = (_randn(g, cin, cout, k, k) if transposed else _randn(g, cout, cin, k, k)) * std
         p[f'{prefix}.0.bias'] = torch.zeros(cout)
-        p[f'{prefix}.1.weight'] = torch.ones(cout)
-        p[f'{prefix}.1.bias'] = torch.zeros(cout)
-        p[f'{prefix}.1.running_mean'] = torch.zeros(cout)
-        p[f'{prefix}.1.running_var'] = torch.ones(cout)
+        if perturb_bn > 0 and cfg.bn_after_activation:
+            p[f'{prefix}.0.bias'] += perturb_bn * _randn(g, cout)      # (in this order the bias does not fold into the BatchNorm shift)
+        p[f'{prefix}.{bn}.weight'] = torch.ones(cout)
+        p[f'{prefix}.{bn}.bias'] = torch.zeros(cout)
+        p[f'{prefix}.{bn}.running_mean'] = torch.zeros(cout)
+        p[f'{prefix}.{bn}.running_var'] = torch.ones(cout)
         if perturb_bn > 0:
-            p[f'{prefix}.1.weight'] += perturb_bn * _randn(g, cout)
-            p[f'{prefix}.1.bias'] += perturb_bn * _randn(g, cout)
-            p[f'{prefix}.1.running_mean'] += perturb_bn * _randn(g, cout)
-            p[f'{prefix}.1.running_var'] += perturb_bn * torch.rand(cout, generator=g)
+            p[f'{prefix}.{bn}.weight'] += perturb_bn * _randn(g, cout)
+            p[f'{prefix}.{bn}.bias'] += perturb_bn * _randn(g, cout)
+            p[f'{prefix}.{bn}.running_mean'] += perturb_bn * _randn(g, cout)
+            p[f'{prefix}.{bn}.running_var'] += perturb_bn * torch.rand(cout, generator=g)
 
     filters = [cfg.pre_filters] + list(cfg.down_filters)
     conv('encoder.model.0.conv', cfg.in_channels, filters[0], 7)
@@ -197,7 +205,10 @@ def init_encoder_params(cfg: EncoderConfig = EncoderConfig(), seed: int = 1, per
         idx += 1
     filters = [cfg.post_filters[-1]] + list(cfg.up_filters)
     for i in range(1, max(cfg.encode_resolutions) + 1):
-        conv(f'decoder.model.{i - 1}.conv.conv', filters[i - 1], filters[i], 3)
+        if cfg.bn_after_activation:
+            conv(f'decoder.model.{i - 1}.conv', filters[i - 1], filters[i], 3, transposed=True)      # ScaleUpV2: ConvTranspose2d [in, out, 3, 3]
+        else:
+            conv(f'decoder.model.{i - 1}.conv.conv', filters[i - 1], filters[i], 3)
     return p
 
 

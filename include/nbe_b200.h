@@ -321,6 +321,15 @@ int nbe_reflect_border_nhwc_bf16(void* buf, int N, int Hp, int Wp, int C, int cs
 int nbe_bilinear2x_pad_nhwc_bf16(const void* x, void* out, int N, int h, int w, int C, int xs_c, int out_cs,
                                  nbe_stream_t stream);
 
+/* Eval-mode BatchNorm AFTER the activation (the encoder's --neg_slope variant, simple_autoencoder.py:100-103,128-148), for the
+ * feature maps that leave the encoder: y[n,py,px,c] = (x[n,py,px,c] * scale[c] + shift[c]) * next_scale[n,c] (next_scale may be
+ * NULL) on NHWC bf16 with independent pitches (in pixels) and channel strides, C % 8 == 0; and the same on dense NCHW float32. */
+int nbe_affine_nhwc_bf16(const void* x, int x_cs, int64_t x_row_pitch, int64_t x_img_pitch,
+                         void* y, int y_cs, int64_t y_row_pitch, int64_t y_img_pitch,
+                         int N, int H, int W, int C, const float* scale, const float* shift, const float* next_scale,
+                         nbe_stream_t stream);
+int nbe_affine_nchw_f32(const float* x, float* y, int N, int C, int HW, const float* scale, const float* shift, nbe_stream_t stream);
+
 /* FP32 parity mode of the same two steps on NCHW float32: y = reflect_pad(x, pad) (padding_mode='reflect',
  * simple_autoencoder.py:98), or, with upsample2x != 0, y = reflect_pad(bilinear_x2(x), pad) with align_corners=True
  * (ScaleUp, simple_autoencoder.py:117) without materialising the up-sampled map.

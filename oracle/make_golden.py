@@ -483,16 +483,45 @@ def golden_canvas(out, ep, ecfg):
     save(out, 'canvas', **arrays)
 
 
+def golden_encoder_v2(out):
+    """The ``--neg_slope`` autoencoder (simple_autoencoder.py:48-53: conv -> LeakyReLU -> BatchNorm stages, ``ScaleUpV2``
+    transposed-conv decoder) built by the reference's own factory with neg_slope = 0.2; oracle restatement checked on the way."""
+    import forger.experimental.autoenc.factory as factory
+    ecfg = P.EncoderConfig(bn_after_activation=True, neg_slope=0.2)
+    ep = P.init_encoder_params(ecfg, seed=5, perturb_bn=0.1)
+    enc_args = argparse.Namespace(model_name='sauto', encoder_in_channels=1, decoder_out_channels=1,
+                                  encoder_pre_filters=64, encoder_down_filters='128,256,256',
+                                  encoder_post_filters='32,16', decoder_up_filters='256,128,64', neg_slope=0.2,
+                                  decoder_pre_filters=-1, widths='256,128,64', preproc_type=None)
+    enc, _ = factory.create_autoencoder(enc_args)
+    missing, unexpected = enc.load_state_dict(ep, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith('decoder.model.') and int(k.split('.')[2]) >= 1 or 'num_batches_tracked' in k for k in missing), missing
+    enc.eval().requires_grad_(False)
+    enc.set_default_encode_resolutions([0, 1])
+    geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=3, radius=8),
+                                            synthetic.synthetic_patch(128, seed=4, radius=3)]))
+    gf = enc.encode(geom)
+    gfo = O.geometry_encode(ep, ecfg, geom)
+    d_enc = max(maxdiff(a, b) for a, b in zip(gf, gfo))
+    print(f'encoder (--neg_slope variant): oracle vs reference max diff {d_enc:.3e}')
+    assert d_enc < 2e-5
+    save(out, 'encoder_v2', geom=geom, g0=gf[0], g1_sub=gf[1][:, ::8],
+         enc_digest=np.frombuffer(P.bundle_digest(ep).encode(), dtype=np.uint8))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(REPO, 'tests', 'golden'))
-    ap.add_argument('--only', default=None, help="write one fixture only: 'modconv_tc' | 'wire'")
+    ap.add_argument('--only', default=None, help="write one fixture only: 'modconv_tc' | 'wire' | 'encoder_v2'")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.set_grad_enabled(False)
     bootstrap_reference()
     if args.only == 'modconv_tc':
         return golden_modconv_tc(args.out)
+    if args.only == 'encoder_v2':
+        return golden_encoder_v2(args.out)
     cfg, ecfg = P.GeneratorConfig(), P.EncoderConfig()
     gp = P.init_generator_params(cfg, seed=0, perturb=0.1)
     ep = P.init_encoder_params(ecfg, seed=1, perturb_bn=0.1)
@@ -505,6 +534,7 @@ def main():
     golden_canvas(args.out, ep, ecfg)
     golden_modconv_tc(args.out)
     golden_wire(args.out, G, enc, enc_args, cfg)
+    golden_encoder_v2(args.out)
 
 
 if __name__ == '__main__':

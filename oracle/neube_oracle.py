@@ -516,6 +516,26 @@ def _single_convolution(p: Bundle, prefix: str, x, stride: int, pad: int, neg_sl
     return F.leaky_relu(x, neg_slope)
 
 
+def _bn_eval(p: Bundle, prefix: str, x, eps):
+    g, b = p[f'{prefix}.weight'].to(x.dtype), p[f'{prefix}.bias'].to(x.dtype)
+    m, v = p[f'{prefix}.running_mean'].to(x.dtype), p[f'{prefix}.running_var'].to(x.dtype)
+    return (x - m[None, :, None, None]) / torch.sqrt(v[None, :, None, None] + eps) * g[None, :, None, None] + b[None, :, None, None]
+
+
+def _single_convolution_bn_last(p: Bundle, prefix: str, x, stride: int, pad: int, neg_slope, eps=1e-5):
+    """``batchnorm_after_activation=True``: conv(reflect) -> LeakyReLU -> eval BatchNorm (simple_autoencoder.py:100-103)."""
+    x = F.pad(x, (pad, pad, pad, pad), mode='reflect')
+    x = F.conv2d(x, p[f'{prefix}.0.weight'].to(x.dtype), p[f'{prefix}.0.bias'].to(x.dtype), stride=stride)
+    return _bn_eval(p, f'{prefix}.2', F.leaky_relu(x, neg_slope), eps)
+
+
+def _scale_up_v2(p: Bundle, prefix: str, x, neg_slope, eps=1e-5):
+    """``ScaleUpV2``: ConvTranspose2d(3, stride 2, padding 1, output_padding 1) -> LeakyReLU -> eval BatchNorm
+    (simple_autoencoder.py:128-148)."""
+    x = F.conv_transpose2d(x, p[f'{prefix}.0.weight'].to(x.dtype), p[f'{prefix}.0.bias'].to(x.dtype), stride=2, padding=1, output_padding=1)
+    return _bn_eval(p, f'{prefix}.2', F.leaky_relu(x, neg_slope), eps)
+
+
 def encoder_preprocess(geom, preproc_type=None):
     """base.py:32-58."""
     if preproc_type in (None, 'none'):
@@ -531,6 +551,22 @@ def geometry_encode(p: Bundle, ecfg, geom, dtype=torch.float32) -> List[torch.Te
     """``BaseGeoEncoder.encode`` -> ``AutoEncoder._encode`` for res list [0, 1]:
     returns ``[g0 [B,16,16,16], g1 [B,256,32,32]]`` for 128x128 input."""
     x = encoder_preprocess(geom.to(dtype), ecfg.preproc_type)
+    if getattr(ecfg, 'bn_after_activation', False):
+        # the --neg_slope variant (simple_autoencoder.py:48-53): BatchNorm after the activation, ScaleUpV2 decoder stages; the
+        # post layers are built without a slope (:180-185) and keep LeakyReLU's default
+        x = _single_convolution_bn_last(p, 'encoder.model.0.conv', x, 1, 3, ecfg.neg_slope, ecfg.bn_eps)
+        idx = 1
+        for _ in ecfg.down_filters:
+            x = _single_convolution_bn_last(p, f'encoder.model.{idx}.conv', x, 2, 1, ecfg.neg_slope, ecfg.bn_eps)
+            idx += 1
+        for _ in ecfg.post_filters:
+            x = _single_convolution_bn_last(p, f'encoder.model.{idx}.conv', x, 1, 1, ecfg.post_neg_slope, ecfg.bn_eps)
+            idx += 1
+        results = [x]
+        for i in range(max(ecfg.encode_resolutions)):
+            x = _scale_up_v2(p, f'decoder.model.{i}.conv', x, ecfg.neg_slope, ecfg.bn_eps)
+            results.append(x)
+        return [results[r] for r in ecfg.encode_resolutions]
     x = _single_convolution(p, 'encoder.model.0.conv', x, 1, 3, ecfg.neg_slope, ecfg.bn_eps)
     idx = 1
     for _ in ecfg.down_filters:

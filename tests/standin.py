@@ -23,19 +23,30 @@ class ScaleUp(nn.Module):                                    # simple_autoencode
         self.conv = Single(cin, cout, **kw)
 
 
+class ScaleUpV2(nn.Module):                                  # simple_autoencoder.py:128-148
+    def __init__(self, cin, cout, neg_slope):
+        super().__init__()
+        self.conv = nn.Sequential(nn.ConvTranspose2d(cin, cout, 3, stride=2, padding=1, output_padding=1), nn.LeakyReLU(neg_slope),
+                                  nn.BatchNorm2d(cout))
+
+
 class StandInAutoEncoder(nn.Module):
-    def __init__(self, ecfg, ep=None, **kw):
+    """``neg_slope`` + ``bn_after_act=True`` + ``scale_up_v2=True`` is what the reference's ``--neg_slope`` flag builds
+    (model_from_flags, simple_autoencoder.py:44-55): the post stages then keep LeakyReLU's default slope (:180-185)."""
+    def __init__(self, ecfg, ep=None, scale_up_v2=False, **kw):
         super().__init__()
         enc, dec = nn.Module(), nn.Module()
         chans = [ecfg.pre_filters] + list(ecfg.down_filters) + list(ecfg.post_filters)
         layers = [Single(ecfg.in_channels, ecfg.pre_filters, 7, 3, 1, **kw)]
         for i, c in enumerate(chans[1:]):
-            layers.append(Single(chans[i], c, 3, 1, 2 if i < len(ecfg.down_filters) else 1, **kw))
+            down = i < len(ecfg.down_filters)
+            kw_i = kw if down or not scale_up_v2 else {k: v for k, v in kw.items() if k != 'neg_slope'}
+            layers.append(Single(chans[i], c, 3, 1, 2 if down else 1, **kw_i))
         enc.model = nn.ModuleList(layers)
         enc.in_channels, enc.num_down_layers = ecfg.in_channels, len(ecfg.down_filters)
         ups, c = [], chans[-1]
         for f in ecfg.up_filters:
-            ups.append(ScaleUp(c, f, **kw))
+            ups.append(ScaleUpV2(c, f, kw.get('neg_slope')) if scale_up_v2 else ScaleUp(c, f, **kw))
             c = f
         dec.model = nn.ModuleList(ups)
         dec.up_layer_filters = list(ecfg.up_filters)

@@ -86,6 +86,18 @@ def test_generator_and_encoder(bundles):
     assert md(O.shifted_noise_closed_form(nc, npos), g['noise16_pos']) < 1e-5
 
 
+def test_encoder_neg_slope_variant():
+    """--neg_slope autoencoder (conv -> LeakyReLU -> BatchNorm, ScaleUpV2; simple_autoencoder.py:48-53,128-148): the oracle's
+    restatement against features produced by the reference's own factory-built model (oracle/make_golden.py --only encoder_v2)."""
+    g = load_golden('encoder_v2')
+    ecfg = P.EncoderConfig(bn_after_activation=True, neg_slope=0.2)
+    ep = P.init_encoder_params(ecfg, seed=5, perturb_bn=0.1)
+    assert bytes(g['enc_digest']).decode() == P.bundle_digest(ep)
+    gf = O.geometry_encode(ep, ecfg, t(g['geom']))
+    assert md(gf[0], g['g0']) < 2e-5
+    assert md(gf[1][:, ::8], g['g1_sub']) < 2e-5
+
+
 def test_stylizer_engine(bundles):
     cfg, ecfg, gp, ep = bundles
     g = load_golden('engine')

@@ -101,6 +101,79 @@ def test_attach_fast_path_on_a_reference_shaped_engine(bundles, mode, tol):
     assert eng2.render_mode == ref_engine.render_mode
 
 
+@pytest.fixture(scope='module')
+def v2_bundle():
+    ecfg2 = P.EncoderConfig(bn_after_activation=True, neg_slope=0.2)
+    ep2 = P.init_encoder_params(ecfg2, seed=5, perturb_bn=0.1)
+    g = load_golden('encoder_v2')
+    assert bytes(g['enc_digest']).decode() == P.bundle_digest(ep2), 'encoder weights differ from the golden run'
+    return ecfg2, ep2, g
+
+
+def test_encoder_neg_slope_variant_fp32(v2_bundle):
+    """The --neg_slope autoencoder (conv -> LeakyReLU -> BatchNorm, ScaleUpV2; simple_autoencoder.py:48-53,128-148) in FP32
+    parity mode against the features of the reference's own factory-built model (tests/golden/encoder_v2.npz)."""
+    from brushstroke_engine_b200.geo_encoder import GeometryEncoder
+    ecfg2, ep2, g = v2_bundle
+    enc = GeometryEncoder(ep2, ecfg2, DEV, mode='fp32')
+    g0, g1 = enc.encode(t(g['geom']).to(DEV))
+    assert g0.shape == (2, 16, 16, 16) and g1.shape == (2, 256, 32, 32)
+    assert md(g0, g['g0']) < 5e-5
+    assert md(g1[:, ::8], g['g1_sub']) < 5e-5
+    # one resolution only, and another input size (the fold of BatchNorm into the next conv relies on reflect padding only)
+    only0 = enc.encode(t(g['geom']).to(DEV), res=0)
+    assert md(only0[0] if isinstance(only0, (list, tuple)) else only0, g['g0']) < 5e-5
+    geom64 = t(g['geom'])[:, :, 32:96, 32:96].contiguous()
+    ref = O.geometry_encode(ep2, ecfg2, geom64)
+    got = enc.encode(geom64.to(DEV))
+    for a, b in zip(got, ref):
+        assert md(a, b) < 5e-5
+
+
+def test_encoder_neg_slope_variant_bf16(v2_bundle):
+    """The same on the tensor-core path: folded-forward BatchNorm, ScaleUpV2 as transposed conv on tcgen05 + crop / bias /
+    LeakyReLU + BatchNorm; within bf16 rounding of the reference features, like the default layout's test."""
+    from brushstroke_engine_b200.geo_encoder import GeometryEncoder
+    ecfg2, ep2, g = v2_bundle
+    ref = O.geometry_encode(ep2, ecfg2, t(g['geom']))
+    enc = GeometryEncoder(ep2, ecfg2, DEV, mode='bf16')
+    got = enc.encode(t(g['geom']).to(DEV))
+    assert got[0].shape == (2, 16, 16, 16) and got[1].shape == (2, 256, 32, 32)
+    for a, b in zip(got, ref):
+        err = md(a, b)
+        rms = float(((a.cpu().double() - b.double()) ** 2).mean().sqrt() / (b.double() ** 2).mean().sqrt())
+        print(f'bf16 --neg_slope encoder: max-abs error {err:.4g} (max |ref| {float(b.abs().max()):.4g}), relative RMS error {rms:.3e}')
+        assert err < 0.02 * float(b.abs().max()) and rms < 1e-2, (err, rms)
+    geom5 = t(g['geom']).repeat(3, 1, 1, 1)[:5].to(DEV)
+    h = enc.encode(geom5)
+    assert md(h[0][:2], got[0]) == 0 and md(h[1][:2], got[1]) == 0
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
+def test_engine_with_neg_slope_encoder_through_the_hook(bundles, v2_bundle, mode, tol):
+    """A reference-shaped engine whose encoder is the --neg_slope variant goes through ``attach_fast_path``: the hook reads the
+    layout from the modules and the rendered stroke matches the oracle (generator fed with the oracle's v2 features)."""
+    from standin import standin_engine, StandInAutoEncoder
+    from brushstroke_engine_b200 import install
+    from brushstroke_engine_b200.engine import GanBrushOptions
+    cfg, ecfg, gp, ep = bundles
+    ecfg2, ep2, g = v2_bundle
+    ref_engine = standin_engine(cfg, ecfg, gp, ep, DEV)
+    ref_engine.encoder = StandInAutoEncoder(ecfg2, ep2, scale_up_v2=True, neg_slope=0.2, bn_after_act=True)
+    fast = install.attach_fast_path(ref_engine, mode=mode)
+    assert fast.encoder.cfg == ecfg2
+    geom = t(g['geom'])
+    z = torch.cat([P.style_z_from_seed(594), P.style_z_from_seed(7)])
+    pos = torch.tensor([[88, 176], [1144, 264]])
+    gf = O.geometry_encode(ep2, ecfg2, geom)
+    _, dbg = O.generator_forward(gp, cfg, z, gf, positions=pos)
+    opts = GanBrushOptions()
+    opts.set_style(z.to(DEV))
+    opts.position = pos.to(DEV)
+    rgba, raw, _ = ref_engine._render_stroke_torch(geom.to(DEV), None, opts)
+    assert md(rgba, O.triad_composite(dbg['uvs'], dbg['colors'], 'clear')) < tol
+
+
 def test_band_jobs_reassemble_the_single_gpu_canvas(bundles):
     """The multi-GPU scheduler's per-rank work -- a row-window CanvasJob (partial guidance upload, global positions), its own
     tiles placed into the canvas rows it owns -- executed for every 'rank' in turn on ONE device: the concatenated bands must
