@@ -1,9 +1,14 @@
 // Library-wide state of libnbe_b200.so: error string, launch counter, ABI version.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace nbe {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+bool pdl_enabled() {
+    static const bool on = getenv("NBE_NO_PDL") == nullptr;
+    return on;
+}
 }  // namespace nbe
 
 extern "C" int nbe_abi_version(void) { return NBE_ABI_VERSION; }

@@ -8,6 +8,8 @@ namespace nbe {
 __global__ void __launch_bounds__(256)
 triad_composite_kernel(const float* __restrict__ uvs, const float* __restrict__ colors01, const float* __restrict__ sfactor,
                        int mode, float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, int N, int H, int W, int m) {
+    pdl_trigger();
+    pdl_wait();
     const int HW = H * W;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * HW) return;
@@ -210,8 +212,8 @@ extern "C" int nbe_triad_composite(const float* uvs, const float* colors01, cons
     if (N == 0) return NBE_OK;
     const int64_t total = (int64_t)N * H * W;
     NBE_REQUIRE(total <= INT32_MAX, "triad_composite: too large");
-    triad_composite_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        uvs, colors01, sfactor, mode, out_f32, out_u8, N, H, W, crop_margin);
+    launch_pdl(triad_composite_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+               uvs, colors01, sfactor, mode, out_f32, out_u8, N, H, W, crop_margin);
     return launched("triad_composite_kernel");
 }
 

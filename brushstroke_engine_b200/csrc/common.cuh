@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <utility>
 #include "../../include/nbe_b200.h"
 
 namespace nbe {
@@ -28,6 +29,28 @@ inline int launched(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(NBE_ECUDA, "%s: %s", what, cudaGetErrorString(e));
     return NBE_OK;
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The batch step is a chain of ~35 kernels, most of them persistent with a per-launch prologue (barrier init, TMEM allocation,
+// cluster sync, tensor-map prefetch, resident weights).  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, a
+// kernel's CTAs may become resident while the tail of its predecessor is still running: every kernel of the chain calls
+// pdl_trigger() first (its dependents may start launching once all of its CTAs have started) and pdl_wait() after its prologue,
+// BEFORE the first access to global memory another kernel may have written or may still be reading (the wait returns when every
+// prerequisite grid has completed and its memory is visible).  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();                                                // NBE_NO_PDL=1: plain stream-ordered launches (A/B switch)
+
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);       // errors surface through launched()
 }
 
 #define NBE_REQUIRE(cond, ...) do { if (!(cond)) return nbe::fail(NBE_EINVAL, __VA_ARGS__); } while (0)

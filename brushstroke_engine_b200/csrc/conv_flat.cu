@@ -144,6 +144,7 @@ template <int EPI, int EW, bool RES, int TT, int PROG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const FlatParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_trigger();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     {
         uint32_t dyn;
@@ -206,18 +207,26 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             uint32_t acnt = 0, bcnt = 0;
             int k = 0, ph = 0;
+            auto load_resident = [&](int ph_) {
+                const int e0 = p.ph_e0[ph_], e1 = p.ph_e1[ph_];
+                const uint32_t rf = smem_u32(res_full);
+                if (leader) mbar_expect_tx(rf, 2u * (uint32_t)(e1 - e0) * F_BHALF);
+                for (int e = e0; e < e1; ++e)
+                    tma_load_3d_2sm(smem_u32(smem_b + (e - e0) * F_BHALF), &tmap_b, rf, p.ent_bk[e] * 64, p.cout_off + p.ent_co[e] * 128 + rank * 64, p.ent_btile[e]);
+            };
+            // the first phase's resident weights are parameters, not another kernel's output: they cross L2 -> shared memory
+            // while the predecessor's tail is still running; everything else waits for it
+            if (RES && n_steps > 0) load_resident(0);
+            pdl_wait();
             for (int s = 0; s < n_steps; ++s) {
                 const int j = j_first + k * j_step;
                 const int np = j / p.items_per_img;
                 const int n = min(2 * np + rank, p.N - 1);                       // dummy: loads stay in range, nothing is stored
                 const int q0 = (j - np * p.items_per_img) * TT * 128;
                 const int e0 = p.ph_e0[ph], e1 = p.ph_e1[ph];
-                if (RES && k == 0) {
-                    if (ph > 0) mbar_wait(smem_u32(res_free), (uint32_t)((ph - 1) & 1));   // previous phase's MMAs are done with smem_b
-                    const uint32_t rf = smem_u32(res_full);
-                    if (leader) mbar_expect_tx(rf, 2u * (uint32_t)(e1 - e0) * F_BHALF);
-                    for (int e = e0; e < e1; ++e)
-                        tma_load_3d_2sm(smem_u32(smem_b + (e - e0) * F_BHALF), &tmap_b, rf, p.ent_bk[e] * 64, p.cout_off + p.ent_co[e] * 128 + rank * 64, p.ent_btile[e]);
+                if (RES && k == 0 && ph > 0) {
+                    mbar_wait(smem_u32(res_free), (uint32_t)((ph - 1) & 1));   // previous phase's MMAs are done with smem_b
+                    load_resident(ph);
                 }
                 int e = e0;
                 const int wrow0 = p.planes ? q0 / p.P : 0;                        // first plane row of the window
@@ -355,6 +364,7 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // transposes 32 positions x 32 channels through a swizzled shared-memory buffer and writes 64-byte runs
         // (4 lanes per position, 8 positions per instruction).
         constexpr int NC32 = 128 / (EW / 4) / 32;                       // 32-column TMEM chunks per warp and class tile: 2 (EW = 8) or 1 (EW = 16)
+        pdl_wait();
         const int qd = warp & 3, hsel = (warp - 2) >> 2;
         const int m = qd * 32 + lane;
         const int et = threadIdx.x - 64;
@@ -609,7 +619,8 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "conv_flat: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     const int64_t pairs = (int64_t)((in.N + 1) / 2) * p.items_per_img;
-    const int grid = (int)std::min<int64_t>(kNumSMs / 2, pairs) * 2;
+    static const int grid_pairs_env = getenv("NBE_FLAT_GRID_PAIRS") ? atoi(getenv("NBE_FLAT_GRID_PAIRS")) : 0;   // timing experiment: fewer CTA pairs
+    const int grid = (int)std::min<int64_t>(grid_pairs_env > 0 ? std::min(grid_pairs_env, kNumSMs / 2) : kNumSMs / 2, pairs) * 2;
     // resident weights pay off when a pair sweeps several items per phase and the largest phase fits next to >= 3 windows
     static const bool round_robin = getenv("NBE_FLAT_ROUND_ROBIN") != nullptr;      // A/B switch: the former item order
     p.contiguous = round_robin ? 0 : 1;
@@ -646,7 +657,7 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     }
     KernelFn fn = use_prog == 1 ? conv_prog[p.resident ? 1 : 0] : use_prog == 2 ? convt_prog[p.resident ? 1 : 0][p.T - 1]
                                 : generic[raw ? 0 : 1][p.resident ? 1 : 0][p.T - 1];
-    fn<<<grid, 64 + epi_warps * 32, smem, stream>>>(ta, tb, p);
+    launch_pdl(fn, dim3(grid), dim3(64 + epi_warps * 32), smem, stream, ta, tb, p);
     return launched("conv_tc_flat_kernel");
 }
 

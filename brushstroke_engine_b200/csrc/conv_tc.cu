@@ -47,6 +47,7 @@ template <int TPC>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = p.Cout * 128;
     uint8_t* smem_a = smem;                                         // [TC_STAGES][TPC][TC_A_BYTES]
@@ -83,6 +84,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    pdl_wait();
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -221,6 +223,7 @@ struct ConvRowParams {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R_THREADS, 1)
 conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvRowParams p) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                         // [2 chunks][4 rows][R_ABUF]
     uint8_t* smem_b = smem + 8 * R_ABUF;                            // [R_BSTAGES][R_BBYTES]
@@ -253,6 +256,7 @@ conv_tc_row128_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     cluster_sync_all();                                             // barriers of BOTH CTAs are initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    pdl_wait();
     // pair jp of the cluster: CTA r takes item 2 jp + r (the last pair may hold a dummy item: loaded, computed, never stored)
     const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int pairs = (p.total_items + 1) >> 1;
@@ -755,7 +759,7 @@ static int conv_tc_impl(const void* x, const void* wq, void* y,
         });
         if (row_err != cudaSuccess) return fail(NBE_ECUDA, "conv_tc: cudaFuncSetAttribute(row128): %s", cudaGetErrorString(row_err));
         const int grid = (int)std::min<int64_t>(kNumSMs / 2, (total + 1) / 2) * 2;      // whole CTA pairs
-        conv_tc_row128_kernel<<<grid, R_THREADS, rsmem, (cudaStream_t)stream>>>(ta, tb, r);
+        launch_pdl(conv_tc_row128_kernel, dim3(grid), dim3(R_THREADS), rsmem, (cudaStream_t)stream, ta, tb, r);
         return launched("conv_tc_row128_kernel");
     }
 
@@ -790,8 +794,8 @@ static int conv_tc_impl(const void* x, const void* wq, void* y,
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return fail(NBE_ECUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    if (tpc == 2) conv_tc_kernel<2><<<(int)((tiles + 1) / 2), TC_THREADS, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, p);
-    else          conv_tc_kernel<1><<<(int)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, p);
+    if (tpc == 2) launch_pdl(conv_tc_kernel<2>, dim3((int)((tiles + 1) / 2)), dim3(TC_THREADS), smem, (cudaStream_t)stream, tmap_a, tmap_b, p);
+    else          launch_pdl(conv_tc_kernel<1>, dim3((int)tiles), dim3(TC_THREADS), smem, (cudaStream_t)stream, tmap_a, tmap_b, p);
     return launched("conv_tc_kernel");
 }
 

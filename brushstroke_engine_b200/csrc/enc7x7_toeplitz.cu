@@ -66,6 +66,8 @@ __device__ __forceinline__ void st_global_32B(void* p, const uint32_t (&v)[8]) {
 
 // x [N,H,W] float32 -> P [N,H+6,Wp] bf16: reflect padding by 3, BaseGeoEncoder preprocessing (base.py:32-58), zeros beyond W+6
 __global__ void enc7_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ P, int N, int H, int W, int Wp, int preproc) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = (int64_t)N * (H + 6) * Wp;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % Wp);
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1)
 enc7_toeplitz_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_y, const ToepParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_trigger();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_b = smem;                                           // [7 kh][512][32 B]
     uint8_t* smem_a = smem + TP_B_BYTES;                              // [TP_ASTAGES][7 kh][128][32 B]
@@ -142,6 +145,7 @@ enc7_toeplitz_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
     tcgen05_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
     const int n_local = (p.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    pdl_wait();
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -342,7 +346,7 @@ extern "C" int nbe_enc_conv7x7_toeplitz_bf16(const float* x, const void* wt, con
     {
         const int64_t total = (int64_t)N * (H + 6) * Wp;
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16);
-        enc7_pad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)scratch, N, H, W, Wp, preproc);
+        launch_pdl(enc7_pad_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)scratch, N, H, W, Wp, preproc);
         int st = launched("enc7_pad_kernel");
         if (st) return st;
     }
@@ -382,6 +386,6 @@ extern "C" int nbe_enc_conv7x7_toeplitz_bf16(const float* x, const void* wt, con
     std::call_once(once, [&] { err = cudaFuncSetAttribute(enc7_toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     if (err != cudaSuccess) return fail(NBE_ECUDA, "enc_conv7x7_toeplitz: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     const int grid = (int)std::min<int64_t>(kNumSMs, total);
-    enc7_toeplitz_kernel<<<grid, TP_THREADS, smem, (cudaStream_t)stream>>>(tp, tw, ty, p);
+    launch_pdl(enc7_toeplitz_kernel, dim3(grid), dim3(TP_THREADS), smem, (cudaStream_t)stream, tp, tw, ty, p);
     return launched("enc7_toeplitz_kernel");
 }

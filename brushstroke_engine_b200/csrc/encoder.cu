@@ -78,6 +78,8 @@ enc_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 // One thread per (border pixel, 8-channel vector).  Border pixels of an Hp x Wp image: 2*Wp + 2*(Hp-2).
 __global__ void __launch_bounds__(256)
 reflect_border_kernel(__nv_bfloat16* __restrict__ buf, int N, int Hp, int Wp, int C, int cs) {
+    pdl_trigger();
+    pdl_wait();
     const int CV = C / 8;
     const int nb = 2 * Wp + 2 * (Hp - 2);
     const long long total = (long long)N * nb * CV;
@@ -101,6 +103,8 @@ reflect_border_kernel(__nv_bfloat16* __restrict__ buf, int N, int Hp, int Wp, in
 __global__ void __launch_bounds__(256)
 bilinear2x_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int h, int w, int C,
                       int xs_c, int out_cs) {
+    pdl_trigger();
+    pdl_wait();
     const int CV = C / 8;
     const int Hp = 2 * h + 2, Wp = 2 * w + 2;
     const long long total = (long long)N * Hp * Wp * CV;
@@ -235,7 +239,7 @@ extern "C" int nbe_reflect_border_nhwc_bf16(void* buf, int N, int Hp, int Wp, in
     const long long total = (long long)N * (2 * Wp + 2 * (Hp - 2)) * (C / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-    reflect_border_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, N, Hp, Wp, C, cs);
+    launch_pdl(reflect_border_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, (__nv_bfloat16*)buf, N, Hp, Wp, C, cs);
     return launched("reflect_border_kernel");
 }
 
@@ -248,7 +252,7 @@ extern "C" int nbe_bilinear2x_pad_nhwc_bf16(const void* x, void* out, int N, int
     const long long total = (long long)N * (2 * h + 2) * (2 * w + 2) * (C / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-    bilinear2x_pad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, h, w, C, xs_c, out_cs);
+    launch_pdl(bilinear2x_pad_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, h, w, C, xs_c, out_cs);
     return launched("bilinear2x_pad_kernel");
 }
 

@@ -12,6 +12,7 @@
 #include "tc_common.cuh"
 #include <mutex>
 #include <type_traits>
+#include <algorithm>
 #include <cstdlib>
 
 namespace nbe {
@@ -166,6 +167,7 @@ template <bool PACKED>
 __device__ __forceinline__ void fir_tiled_body(const CUtensorMap& tmap_t, const CUtensorMap& tmap_t8, const CUtensorMap& tmap_nz,
                                                const FirParams& p, int tiles_x, int tiles_y, int total_tiles, int noise_mode, int strip_ok) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     uint8_t* bufs = smem;                                           // [2][FT_TILE_BYTES]
     constexpr int BUF_STRIDE = (FT_TILE_BYTES + 127) & ~127;
@@ -186,6 +188,7 @@ __device__ __forceinline__ void fir_tiled_body(const CUtensorMap& tmap_t, const 
     }
     if (noise_mode == 2) s_nz[threadIdx.x] = 0.f;                   // no noise input: both tiles stay zero (2 x 128 floats)
     __syncthreads();
+    pdl_wait();                                                     // T, the epilogue vectors and y belong to other kernels of the chain
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = s_f[i];
@@ -515,11 +518,12 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
             if (st) return st;
             noise_mode = 1;
         }
-        int grid = kNumSMs * 2;
+        static const int grid_env = getenv("NBE_FIR_GRID") ? atoi(getenv("NBE_FIR_GRID")) : 0;     // timing experiment: fewer CTAs
+        int grid = grid_env > 0 ? std::min(grid_env, kNumSMs * 2) : kNumSMs * 2;
         if (total < grid) grid = (int)total;
         static const bool scalar_fp32 = getenv("NBE_FIR_SCALAR") != nullptr;      // A/B switch: the unpacked FP32 arithmetic
-        if (scalar_fp32) fir_act_tiled_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tm8, tn, p, tiles_x, tiles_y, (int)total, noise_mode, strip_ok);
-        else fir_act_tiled_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(tm, tm8, tn, p, tiles_x, tiles_y, (int)total, noise_mode, strip_ok);
+        if (scalar_fp32) launch_pdl(fir_act_tiled_kernel<false>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, tm, tm8, tn, p, tiles_x, tiles_y, (int)total, noise_mode, strip_ok);
+        else launch_pdl(fir_act_tiled_kernel<true>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, tm, tm8, tn, p, tiles_x, tiles_y, (int)total, noise_mode, strip_ok);
         return launched("fir_act_tiled_kernel");
     }
     p.row_groups = (OH + FIR_RPT - 1) / FIR_RPT;
