@@ -118,7 +118,12 @@ struct StagedGeom {
     int buf_bytes;      // smem_bytes rounded up to 128
     int lds32;          // 16-bit types on the packed path: aligned 32-bit shared-memory loads + funnel shift
     int packed;         // up = 1, windows hang at most 3 elements over a row end, OW % VPT == 0: FFMA2 path with mask fix-ups
+    int cg_sh, rg_sh, strips_sh;   // log2 of cg / rg / strips when they are powers of two (-1 otherwise): the per-thread index
+                                   // arithmetic was a third of this kernel's instructions while its divisors were runtime values
 };
+__device__ __forceinline__ void divmod_sh(int v, int d, int sh, int& q, int& r) {
+    if (sh >= 0) { q = v >> sh; r = v & (d - 1); } else { q = v / d; r = v - q * d; }
+}
 
 template <int VPT, int WIN, int PI>
 __device__ __forceinline__ void up2_row(float (&acc)[VPT], const float (&rowA)[WIN], const float (&rowB)[WIN], const float (&f)[16], int a0) {
@@ -142,6 +147,7 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
     // cp.async.bulk -> mbarrier) while the current one is filtered, so no thread ever waits on a global load of its own.
     extern __shared__ __align__(128) uint8_t st_smem[];                 // [2][g.buf_bytes] input buffers, then 2 mbarriers
     __shared__ float s_f[16];
+    __shared__ __align__(16) uint32_t s_zero[8];                        // up = 2: what a window row outside the staged range reads
     uint64_t* bars = reinterpret_cast<uint64_t*>(st_smem + 2 * (size_t)g.buf_bytes);
     const T* xbase = (const T*)p.x;
     const long long plane_elems = (long long)p.H * p.W;
@@ -151,7 +157,7 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
     auto item_geom = [&](int item, Item& I) {
         // ---- which planes / rows does this item cover
         if (g.ppc > 1) { I.plane0 = item * g.ppc; I.oy0 = 0; I.rows = p.OH; }
-        else { I.plane0 = item / g.strips; I.oy0 = (item % g.strips) * g.strip; I.rows = min(g.strip, p.OH - I.oy0); }
+        else { int si; divmod_sh(item, g.strips, g.strips_sh, I.plane0, si); I.oy0 = si * g.strip; I.rows = min(g.strip, p.OH - I.oy0); }
         I.planes = min(g.ppc, n_planes - I.plane0);
         // ---- input rows needed (per plane): UP=1: [oy0 - pad, oy0 - pad + rows + 3) ; UP=2: [(oy0 - pad) >> 1, ((oy0 + rows + 2 - pad) >> 1) + 1)
         int r_lo, r_hi;
@@ -171,8 +177,7 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
     };
     // all threads call this: thread 0 issues the bulk copy of the chunks that lie completely inside the tensor, the (at most
     // two) chunks straddling its first / last bytes are assembled element by element with zeros outside
-    auto stage = [&](int item, int b) {
-        Item I;
+    auto stage = [&](int item, int b, Item& I) {
         item_geom(item, I);
         uint8_t* buf = st_smem + (size_t)b * g.buf_bytes;
         int c0 = 0, c1 = I.n_chunks;
@@ -207,8 +212,10 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
         int a = threadIdx.x >> 2, b = threadIdx.x & 3;
         s_f[threadIdx.x] = (p.flip ? p.f[a * 4 + b] : p.f[(3 - a) * 4 + (3 - b)]) * p.gain;
     }
+    if (threadIdx.x < 8) s_zero[threadIdx.x] = 0u;
     __syncthreads();
-    if ((int)blockIdx.x < n_items) stage(blockIdx.x, 0);
+    Item I_next{};
+    if ((int)blockIdx.x < n_items) stage(blockIdx.x, 0, I_next);
     // the (at most two) edge chunks of the first item are written by threads 0 / 1 with ordinary stores: the mbarrier only
     // covers the bulk copy, so the other threads need this barrier before they read them (later items are staged one
     // iteration ahead and ordered by the barrier that ends every iteration).  Found by compute-sanitizer (round 2):
@@ -234,10 +241,9 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
     const T* sx = reinterpret_cast<const T*>(buf + 16 + (I.gb_lo - I.a_lo));                             // smem view of element e_lo
 
     // ---- thread -> (plane_local, row group, column group)
-    int t = threadIdx.x;
-    const int cgi = t % g.cg; t /= g.cg;
-    const int rgi = t % g.rg; t /= g.rg;
-    const int pl = t;
+    int t, cgi, rgi, pl;
+    divmod_sh((int)threadIdx.x, g.cg, g.cg_sh, t, cgi);
+    divmod_sh(t, g.rg, g.rg_sh, pl, rgi);
     if (pl >= planes) return;
     const int ox0 = cgi * VPT;
     const int ry0 = oy0 + rgi * ST_RPT;
@@ -401,20 +407,42 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
         const int jl = ixb < 0 ? -ixb : 0;
         const int jh = ixb + WIN > W ? W - ixb : WIN;
         float rows[NR][WIN];
+        // Window loads without branches (ncu, round 2: this path was ISSUE-bound -- 17 instructions per output, two thirds of
+        // them compares / selects / branches around the loads and stores): a row outside the staged range reads the zero
+        // words in s_zero instead, window slots outside the row are cleared by row-invariant AND masks on the raw bits, and
+        // 16-bit types read aligned 32-bit words (a window of 6 halfwords = 4 words) realigned by a funnel shift.
+        uint32_t mk[WIN];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) mk[j] = (j >= jl && j < jh) ? ~0u : 0u;
+        const uint32_t zero_a = (uint32_t)__cvta_generic_to_shared(s_zero);
 #pragma unroll
         for (int q = 0; q < NR; ++q) {
             const int iy = iy_first + q;
-            if (iy >= r_lo && iy < r_hi) {
-                const T* rp = sp + (long long)iy * W + ixb;
+            const bool ok = iy >= r_lo && iy < r_hi;
+            const uint32_t a_row = (uint32_t)__cvta_generic_to_shared(sp + (long long)(ok ? iy : r_lo) * W + ixb);
+            if (sizeof(T) == 2) {
+                constexpr int NW = WIN / 2 + 1;
+                const uint32_t sh = (a_row & 2u) ? 16u : 0u;
+                const uint32_t wa = ok ? (a_row & ~3u) : zero_a;
+                uint32_t w[NW];
 #pragma unroll
-                for (int j = 0; j < WIN; ++j) rows[q][j] = Cvt<T>::ld(rp[j]);
-                if (jl > 0 || jh < WIN) {
+                for (int k = 0; k < NW; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[k]) : "r"(wa + 4u * k));
 #pragma unroll
-                    for (int j = 0; j < WIN; ++j) if (j < jl || j >= jh) rows[q][j] = 0.f;
+                for (int k = 0; k < WIN / 2; ++k) {
+                    const uint32_t v = __funnelshift_r(w[k], w[k + 1], sh);      // elements 2k (low half), 2k + 1 (high half)
+                    float lo, hi;
+                    Raw<T>::unpack2(v, lo, hi);
+                    rows[q][2 * k] = __uint_as_float(__float_as_uint(lo) & mk[2 * k]);
+                    rows[q][2 * k + 1] = __uint_as_float(__float_as_uint(hi) & mk[2 * k + 1]);
                 }
             } else {
+                const uint32_t wa = ok ? a_row : zero_a;
 #pragma unroll
-                for (int j = 0; j < WIN; ++j) rows[q][j] = 0.f;
+                for (int j = 0; j < WIN; ++j) {
+                    uint32_t v;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(wa + 4u * j));
+                    rows[q][j] = __uint_as_float(v & mk[j]);
+                }
             }
         }
         // column parity pi = (ox0 - padx0) & 1 is uniform across the CTA (ox0 is a multiple of VPT): with it fixed,
@@ -422,23 +450,43 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
         const int pi = (ox0 - p.padx0) & 1;
         const int par0 = u00 & 1;                                          // row parity of the first output row (uniform per launch)
         T* yrow = yp + (long long)ry0 * p.OW + ox0;
+        // whole row groups of whole, 16-byte aligned column groups (every thread at the generator's sizes) store without the
+        // per-row bounds / alignment checks
+        const bool fast = ry0 + ST_RPT <= row_end && n_valid == VPT && (reinterpret_cast<uintptr_t>(yrow) & 15) == 0 &&
+                          (((size_t)p.OW * sizeof(T)) & 15) == 0;
+        auto out_rows = [&](auto par0_c, auto pi_c, auto fast_c) {
+            constexpr int PAR0 = decltype(par0_c)::value, PI = decltype(pi_c)::value;
+            constexpr bool FAST = decltype(fast_c)::value;
 #pragma unroll
-        for (int r = 0; r < ST_RPT; ++r) {
-            if (ry0 + r >= row_end) break;
-            float acc[VPT];
-            // q = (u0 + a0) / 2 - iy_first with u0 = u00 + r, a0 = u0 & 1: compile-time per (r, par0)
-            if (par0 == 0) {
-                constexpr int dummy = 0; (void)dummy;
-                const int a0 = r & 1, q = (r + a0) >> 1;
-                if (pi == 0) up2_row<VPT, WIN, 0>(acc, rows[q], rows[q + 1], f, a0);
-                else         up2_row<VPT, WIN, 1>(acc, rows[q], rows[q + 1], f, a0);
-            } else {
-                const int a0 = (r + 1) & 1, q = (r + 1 + a0) / 2 - 1;
-                if (pi == 0) up2_row<VPT, WIN, 0>(acc, rows[q], rows[q + 1], f, a0);
-                else         up2_row<VPT, WIN, 1>(acc, rows[q], rows[q + 1], f, a0);
+            for (int r = 0; r < ST_RPT; ++r) {
+                if (!FAST && ry0 + r >= row_end) break;
+                float acc[VPT];
+                // q = (u0 + a0) / 2 - iy_first with u0 = u00 + r, a0 = u0 & 1: compile-time per (r, par0)
+                const int a0 = (r + PAR0) & 1, q = PAR0 == 0 ? (r + a0) >> 1 : (r + 1 + a0) / 2 - 1;
+                up2_row<VPT, WIN, PI>(acc, rows[q], rows[q + 1], f, a0);
+                if (FAST) {
+                    constexpr int PER16 = 16 / (int)sizeof(T);
+#pragma unroll
+                    for (int v0 = 0; v0 < VPT; v0 += PER16) {
+                        int4 v;
+                        T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+                        for (int k = 0; k < PER16; ++k) e[k] = Cvt<T>::st(acc[v0 + k]);
+                        st_stream16(yrow + v0, v);
+                    }
+                } else {
+                    store_row<T, VPT>(yrow, acc, n_valid);
+                }
+                yrow += p.OW;
             }
-            store_row<T, VPT>(yrow, acc, n_valid);
-            yrow += p.OW;
+        };
+        using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
+        if (fast) {
+            if (par0 == 0) { if (pi == 0) out_rows(I0{}, I0{}, std::true_type{}); else out_rows(I0{}, I1{}, std::true_type{}); }
+            else           { if (pi == 0) out_rows(I1{}, I0{}, std::true_type{}); else out_rows(I1{}, I1{}, std::true_type{}); }
+        } else {
+            if (par0 == 0) { if (pi == 0) out_rows(I0{}, I0{}, std::false_type{}); else out_rows(I0{}, I1{}, std::false_type{}); }
+            else           { if (pi == 0) out_rows(I1{}, I0{}, std::false_type{}); else out_rows(I1{}, I1{}, std::false_type{}); }
         }
     }
     };   // compute
@@ -446,9 +494,8 @@ upfirdn2d_staged_kernel(UpfirdnParams p, StagedGeom g, int n_planes, int n_items
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int b = it & 1;
-        if (item + (int)gridDim.x < n_items) stage(item + gridDim.x, b ^ 1);   // buffer b^1 was released by the barrier that ended the previous iteration
-        Item I;
-        item_geom(item, I);
+        const Item I = I_next;                                            // (computed when the item was staged)
+        if (item + (int)gridDim.x < n_items) stage(item + gridDim.x, b ^ 1, I_next);   // buffer b^1 was released by the barrier that ended the previous iteration
         {   // bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU
             const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[b]), parity = (uint32_t)((it >> 1) & 1);
             uint32_t done = 0;
@@ -486,6 +533,8 @@ static bool staged_geometry(const UpfirdnParams& p, StagedGeom& g, int VPT) {
         g.smem_bytes = (int)((long long)in_rows * p.W * es + 80);
     }
     g.buf_bytes = (g.smem_bytes + 127) & ~127;
+    auto lg = [](int v) { int sh = 0; while ((1 << sh) < v) ++sh; return (1 << sh) == v ? sh : -1; };
+    g.cg_sh = lg(g.cg); g.rg_sh = lg(g.rg); g.strips_sh = lg(g.strips);
     return g.smem_bytes <= 48 * 1024;                                  // two buffers per CTA
 }
 
@@ -515,16 +564,19 @@ static int run_typed(const UpfirdnParams& p, bool tiled_ok, cudaStream_t s) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
                 if (e != cudaSuccess) return fail(NBE_ECUDA, "upfirdn2d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             }
-            // persistent grid: as many CTAs as fit an SM (shared memory; at most 6), each keeps its next item in flight
+            // persistent grid: as many CTAs as fit an SM (shared memory; at most 6, 12 for 16-bit up = 2), each keeps its next item in flight
             int per_sm = (227 * 1024) / (dyn + 1024);
-            const char* cap_env = getenv("NBE_UPF_PER_SM");                 // A/B: persistent CTAs per SM (default cap 6)
-            const int cap = cap_env ? atoi(cap_env) : 6;
+            const char* cap_env = getenv("NBE_UPF_PER_SM");                 // A/B: persistent CTAs per SM
+            const int cap = cap_env ? atoi(cap_env) : ((p.upx == 2 && sizeof(T) == 2) ? 12 : 6);
             per_sm = per_sm < 1 ? 1 : (per_sm > cap ? cap : per_sm);
-            // one item per CTA (the loop runs once; residency is then set by registers / shared memory only): up = 2 writes 4x what
-            // it reads, so it gains nothing from prefetching its small input and loses residency to the persistent grid
-            // (tools/ab_up2.py: fp32 0.63 -> 0.57 ms, bf16 0.41 -> 0.38 ms at 64^2 -> 128^2).  NBE_UPF_ONESHOT=0/1 overrides.
+            // one item per CTA (the loop runs once; residency is then set by registers / shared memory only): FP32 up = 2 writes 4x
+            // what it reads, gains nothing from prefetching its small input and loses residency to the persistent grid
+            // (tools/ab_up2.py, 64^2 -> 128^2, batch 256 x 128: 0.565 ms one-shot vs 0.62-0.66 ms persistent).  The 16-bit types were
+            // ISSUE-bound (ncu: 17 instructions per output, ALU pipe 71 %); with the branch-free window loads and shift / mask
+            // index arithmetic the persistent grid is the faster one for them (bf16: 0.258 ms persistent x12 vs 0.314 ms one-shot;
+            // 0.382 ms before).  NBE_UPF_ONESHOT=0/1 overrides.
             const char* one_env = getenv("NBE_UPF_ONESHOT");
-            const bool oneshot = one_env ? atoi(one_env) != 0 : (p.upx == 2);
+            const bool oneshot = one_env ? atoi(one_env) != 0 : (p.upx == 2 && sizeof(T) == 4);
             const int grid = (int)(oneshot || blocks < (int64_t)kNumSMs * per_sm ? blocks : (int64_t)kNumSMs * per_sm);
             kern<<<grid, ST_THREADS, dyn, s>>>(p, g, n_planes, (int)blocks);
             return launched("upfirdn2d_staged_kernel");
