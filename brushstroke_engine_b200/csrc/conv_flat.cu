@@ -626,7 +626,8 @@ static int launch_flat(const FlatInput& in, const void* wq, int n_wtiles, int w_
     p.contiguous = round_robin ? 0 : 1;
     static const int debug_mode = getenv("NBE_FLAT_DEBUG") ? atoi(getenv("NBE_FLAT_DEBUG")) : 0;
     p.debug = debug_mode;
-    p.resident = !no_resident && pairs >= 2 * (int64_t)(grid / 2) && epi_bytes + (size_t)max_phase_tiles * F_BHALF + 3 * a_bytes <= limit;
+    static const int res_min_abuf = getenv("NBE_FLAT_RES_MIN_ABUF") ? atoi(getenv("NBE_FLAT_RES_MIN_ABUF")) : 3;   // experiment: resident weights next to fewer windows
+    p.resident = !no_resident && pairs >= 2 * (int64_t)(grid / 2) && epi_bytes + (size_t)max_phase_tiles * F_BHALF + (size_t)res_min_abuf * a_bytes <= limit;
     p.b_tiles = p.resident ? max_phase_tiles : F_BSTAGES;
     // streamed weights: a ring of 4 tiles instead of 6 when that buys one more window buffer (windows take longer to arrive)
     if (!p.resident && (limit - epi_bytes - 4 * F_BHALF) / a_bytes > (limit - epi_bytes - (size_t)F_BSTAGES * F_BHALF) / a_bytes
@@ -781,28 +782,31 @@ extern "C" int nbe_convT3x3s2_flat_bf16(const void* x, const void* wq, void* t_o
     // against the tap-balanced split {(0,0),(1,1)} / {(0,1),(1,0)}: no difference (0.32 ms at 64 -> 128, batch 256).  What
     // this launch waits for is its global stores: 0.18 ms with the stores removed, 0.17 ms without any epilogue
     // (NBE_FLAT_DEBUG=2 / 1, timing experiments with wrong results).
-    const int phase_classes[2][2][2] = {{{0, 0}, {0, 1}}, {{1, 0}, {1, 1}}};
+    // NBE_CONVT_ONE_PHASE (experiment): all four classes in ONE phase -- every item is finished in one visit (images complete in
+    // order), all nine taps stay resident, the four accumulators fill TMEM (the epilogue is not overlapped)
+    static const bool one_phase = getenv("NBE_CONVT_ONE_PHASE") != nullptr;
+    const int n_ph = (one_phase && p.T == 1) ? 1 : 2, cls_per_ph = 4 / n_ph;
     FlatTap taps[9];
     int phase_ntaps[2] = {0, 0};
     int t = 0;
-    for (int ph = 0; ph < 2; ++ph) {
-        for (int gl = 0; gl < 2; ++gl) {
-            const int py = phase_classes[ph][gl][0], px = phase_classes[ph][gl][1];
-            const int g = py * 2 + px;
+    for (int ph = 0; ph < n_ph; ++ph) {
+        for (int gl = 0; gl < cls_per_ph; ++gl) {
+            const int g = ph * cls_per_ph + gl;                     // class (py, px) = (g >> 1, g & 1): a phase holds whole row parities
+            const int py = g >> 1, px = g & 1;
             p.ph_cls[ph][gl] = g;
             for (int kh = py; kh < 3; kh += 2)
                 for (int kw = px; kw < 3; kw += 2) { taps[t++] = {-((kh - py) / 2) * x_pitch - (kw - px) / 2, gl, kh * 3 + kw, -1}; ++phase_ntaps[ph]; }
             p.cls_sy[g] = 2; p.cls_sx[g] = 2; p.cls_oy[g] = py; p.cls_ox[g] = px;
             p.cls_vy[g] = py ? H : H + 1; p.cls_vx[g] = px ? W : W + 1;
         }
-        p.ph_G[ph] = 2;
+        p.ph_G[ph] = cls_per_ph;
     }
-    p.n_phases = 2; p.Gmax = 2;
+    p.n_phases = n_ph; p.Gmax = cls_per_ph;
     p.y_cs = t_cs; p.y_row_pitch = t_row_pitch; p.y_img_pitch = t_img_pitch; p.noise_w = 0; p.vec_stride = Cout; p.cout_off = co;
     p.dcoef = dcoef ? dcoef + co : nullptr; p.noise = nullptr; p.noise_sn = 0; p.noise_gain = 0.f;
     p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.gain = 1.f; p.clamp = -1.f; p.next_scale = nullptr;
     FlatInput in{x, N, Cin, x_cs, H * x_pitch, 0, 0, 0};
-    int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream, 2);
+    int st = launch_flat(in, wq, 9, Cout, p, taps, phase_ntaps, (cudaStream_t)stream, n_ph == 2 ? 2 : 0);
     if (st) return st;
   }
     return NBE_OK;
