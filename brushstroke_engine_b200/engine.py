@@ -493,7 +493,7 @@ class BatchSession:
                 engine._force_overlap = False
             engine.G._noise_cache = None
             self._graph = g
-            self._workspaces = (engine.G._flat_ws.get(B), engine.encoder._ws.get((B, W)))
+            self._workspaces = (engine.G._flat_ws.get(B), engine.encoder._ws.get((B, W)), engine.encoder.graph_workspaces(B, W))
             torch.cuda.current_stream().wait_stream(self._stream)
 
     def _forward(self, window_blend=None):
@@ -665,7 +665,7 @@ class InteractiveSession:
             # the captured kernels hold raw pointers into the batch-1 workspaces of the generator and the encoder: keep them
             # alive (and out of reach of a re-allocation) for as long as the graph exists, whatever other batch sizes the
             # engine serves in between
-            self._workspaces = (eng.G._flat_ws.get(1), eng.encoder._ws.get((1, eng.patch_width)))
+            self._workspaces = (eng.G._flat_ws.get(1), eng.encoder._ws.get((1, eng.patch_width)), eng.encoder.graph_workspaces(1, eng.patch_width))
 
     def render_stroke(self, stroke_patch: np.ndarray, position_yx=None) -> np.ndarray:
         """[W,W,C] uint8 stroke patch (last channel: 255 = stroke), optional canvas position (y, x) -> [T,T,4] uint8 RGBA."""

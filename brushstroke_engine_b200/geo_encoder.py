@@ -218,6 +218,17 @@ class GeometryEncoder:
                       cout, y_cs, 3, 1, stride, cur.shape[1], cur.shape[2], rp, ip, None, None, 0, 0.0, _lib.ptr(b), slope, 1.0,
                       -1.0, _lib.ptr(next_scale), st)
 
+    def graph_workspaces(self, B: int, H: int):
+        """Every cached buffer a CUDA graph captured at (batch B, input H) points into besides ``_workspace(B, H)``: a session keeps
+        the returned objects alive, because the caches are least-recently-used and may drop them (the --neg_slope layout's
+        zero-gapped g0 / transposed-conv buffers are keyed by the feature-map size)."""
+        if not self._v2 or self.mode != 'bf16':
+            return None
+        h = H
+        for (_, _, stride, _, _) in self._layers:
+            h //= stride
+        return self._v2_ws.get((B, h))
+
     @_lib.profiled('encode')
     def encode_into(self, geom, dests, scales=None, scales_ready=None):
         """Run the bf16 encoder and write feature map ``r`` (index into ``self.res``) into ``dests[r] = (tensor, c_off)``:

@@ -174,6 +174,29 @@ def test_engine_with_neg_slope_encoder_through_the_hook(bundles, v2_bundle, mode
     assert md(rgba, O.triad_composite(dbg['uvs'], dbg['colors'], 'clear')) < tol
 
 
+def test_neg_slope_encoder_in_the_batch_graph(bundles, v2_bundle):
+    """The batch step as a CUDA graph (what stylize / render_patches_host replay) with the --neg_slope encoder: same bytes as the
+    eager launch sequence for changing inputs -- the variant's extra buffers (dense last activation, zero-gapped g0, transposed-conv
+    result) live in the graph's pool / the encoder's workspace cache."""
+    from brushstroke_engine_b200.engine import BatchSession, GanBrushOptions, TriadPaintEngine
+    cfg, ecfg, gp, ep = bundles
+    ecfg2, ep2, g = v2_bundle
+    eng = TriadPaintEngine(gp, ep2, DEV, mode='bf16', enc_cfg=ecfg2)
+    B = 5
+    sess = BatchSession(eng, B, 10)
+    rng = np.random.RandomState(7)
+    for rep in range(3):
+        geom = torch.from_numpy(np.concatenate([synthetic.synthetic_patch(128, seed=50 * rep + i, radius=3 + (i % 4)) for i in range(B)])).to(DEV)
+        z = torch.cat([P.style_z_from_seed(100 * rep + i) for i in range(B)]).to(DEV)
+        pos = torch.from_numpy(rng.randint(0, 4000, size=(B, 2))).to(DEV)
+        o = GanBrushOptions()
+        o.set_style(z)
+        o.position = pos
+        ref, _ = eng.render_tiles(geom, o, crop_margin=10)
+        assert torch.equal(sess.run(geom, z, pos), ref), rep
+    assert int(ref.max()) > 0
+
+
 def test_band_jobs_reassemble_the_single_gpu_canvas(bundles):
     """The multi-GPU scheduler's per-rank work -- a row-window CanvasJob (partial guidance upload, global positions), its own
     tiles placed into the canvas rows it owns -- executed for every 'rank' in turn on ONE device: the concatenated bands must
