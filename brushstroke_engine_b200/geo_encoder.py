@@ -326,9 +326,20 @@ class GeometryEncoder:
                     dst, c_off = dests[res.index(feat_idx)]
                     assert dst.shape[0] == B and dst.shape[1] == ho and dst.shape[2] >= ho and dst.shape[3] >= c_off + cout
                     sc = scales[res.index(feat_idx)] if scales is not None else None
-                    src = feat_dense if sc is None else (feat_dense.float() * sc.to(self.device)[:, None, None, :]).to(torch.bfloat16)
-                    dst[:, :, :ho, c_off:c_off + cout] = src
+                    if sc is not None:
+                        sc = sc.to(self.device, torch.float32).contiguous()
+                        assert sc.shape == (B, cout)
+                    one, zero = self._identity_affine(cout)
+                    # one strided copy (times the consuming layer's styles) instead of a chain of torch element-wise kernels
+                    _lib.call('nbe_affine_nhwc_bf16', feat_dense.data_ptr(), cout, ho, ho * ho, dst.data_ptr() + 2 * c_off, dst.shape[3],
+                              dst.shape[2], ho * dst.shape[2], B, ho, ho, cout, _lib.ptr(one), _lib.ptr(zero), _lib.ptr(sc), st)
         return dests
+
+    def _identity_affine(self, C):
+        cache = self.__dict__.setdefault('_id_affine', {})
+        if C not in cache:
+            cache[C] = (torch.ones(C, dtype=torch.float32, device=self.device), torch.zeros(C, dtype=torch.float32, device=self.device))
+        return cache[C]
 
     def _affine_f32(self, x, affine):
         y = torch.empty_like(x)
