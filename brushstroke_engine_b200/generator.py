@@ -173,6 +173,7 @@ class Generator:
         # slower at every size -- 12 MB: generator 5.98 ms, 40 MB: 3.66, 96 MB: 3.13 against 2.80 ms unchunked; the per-launch
         # floor of the persistent kernels (~20 us: resident weights, TMEM, tensor maps) outweighs what L2 residency returns.
         self.up_chunk_bytes = int(float(os.environ.get('NBE_UP_CHUNK_MB', '0')) * 2 ** 20)
+        self.small_pertap_max = int(os.environ.get('NBE_SMALL_PERTAP_MAX', '0'))   # A/B switch: conv1 of blocks up to this resolution on the per-tap kernel (images batched into a tile)
         self.use_up_fused = os.environ.get('NBE_UP_FUSED') == '1'      # A/B switch: one fused kernel per up layer (csrc/up_fused.cu) instead of transposed conv + FIR pass
         self.up_fused_min_res = int(os.environ.get('NBE_UP_FUSED_MIN_RES', '8'))   # smallest input resolution that takes the fused kernel
         self._up_scratch_bufs = {}
@@ -742,9 +743,18 @@ class Generator:
             nxt = self._layer_by_name[f'b{res * 2}.conv0']
             out = geom_feature.buffers[res] if (injected and res in cfg.geom_feature_resolutions) else wsb[f'out{res}']
             ns = styles[nxt.name][:, :conv1.cout].contiguous() if nxt.cin != conv1.cout else styles[nxt.name]
-            _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(out), B, res, res, conv1.cin, x1.shape[3],
-                      x1_pitch, 0, conv1.cout, out.shape[3], res + 1, res * (res + 1), _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn,
-                      float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(None if wb is not None else ns), st)
+            if res <= self.small_pertap_max and x1_pitch == res + 1 and x1.shape[1] == res:
+                # small maps: the flat kernel tiles every image by itself (a 4x4 map fills 20 of a tile's 256 positions); the per-tap
+                # kernel packs 128 / res^2 images into one position tile and reads the same zero-gapped layout as a 'same'
+                # convolution over a (res) x (res + 1) image whose last column is the zero gap
+                _lib.call('nbe_conv_tc_bf16_ex', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(out), B, res, res, conv1.cin, x1.shape[3],
+                          conv1.cout, out.shape[3], 3, 0, 1, res, res + 1, res + 1, res * (res + 1), _lib.ptr(dcoefs[conv1.name]),
+                          _lib.ptr(noise), nsn, float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp,
+                          _lib.ptr(None if wb is not None else ns), st)
+            else:
+                _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(out), B, res, res, conv1.cin, x1.shape[3],
+                          x1_pitch, 0, conv1.cout, out.shape[3], res + 1, res * (res + 1), _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn,
+                          float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(None if wb is not None else ns), st)
             if wb is not None:
                 wb.apply(out, res + 1, conv1.cout, ns, B)             # blend, save, then the modulation the epilogue would have fused
             if res in cfg.geom_feature_resolutions:
