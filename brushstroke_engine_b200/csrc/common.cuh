@@ -33,7 +33,7 @@ inline int launched(const char* what) {
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
 // The batch step is a chain of ~35 kernels, most of them persistent with a per-launch prologue (barrier init, TMEM allocation,
-// cluster sync, tensor-map prefetch, resident weights).  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, a
+// cluster sync, tensor-map prefetch).  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, a
 // kernel's CTAs may become resident while the tail of its predecessor is still running: every kernel of the chain calls
 // pdl_trigger() first (its dependents may start launching once all of its CTAs have started) and pdl_wait() after its prologue,
 // BEFORE the first access to global memory another kernel may have written or may still be reading (the wait returns when every

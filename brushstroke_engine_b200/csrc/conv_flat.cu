@@ -214,10 +214,10 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int e = e0; e < e1; ++e)
                     tma_load_3d_2sm(smem_u32(smem_b + (e - e0) * F_BHALF), &tmap_b, rf, p.ent_bk[e] * 64, p.cout_off + p.ent_co[e] * 128 + rank * 64, p.ent_btile[e]);
             };
-            // the first phase's resident weights are parameters, not another kernel's output: they cross L2 -> shared memory
-            // while the predecessor's tail is still running; everything else waits for it
-            if (RES && n_steps > 0) load_resident(0);
+            // everything this warp reads may be another kernel's output -- the activations, and the weights too when a caller
+            // prepares them right before the launch (nbe_modulated_conv2d does): nothing is fetched ahead of the wait
             pdl_wait();
+            if (RES && n_steps > 0) load_resident(0);
             for (int s = 0; s < n_steps; ++s) {
                 const int j = j_first + k * j_step;
                 const int np = j / p.items_per_img;

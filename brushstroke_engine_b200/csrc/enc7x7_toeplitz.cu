@@ -149,7 +149,6 @@ enc7_toeplitz_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_y) : "memory");
     }
-    if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -160,6 +159,8 @@ enc7_toeplitz_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
     const int n_local = (p.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     pdl_wait();
+    if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+    __syncthreads();
 
     if (warp == 0) {
         // ============================== TMA producer ==============================

@@ -176,10 +176,6 @@ __device__ __forceinline__ void fir_tiled_body(const CUtensorMap& tmap_t, const 
     float* s_f = s_epi + 3 * 128;                                   // [16]
     uint64_t* full = reinterpret_cast<uint64_t*>(s_f + 16);         // [2]
 
-    if (threadIdx.x < 16) {
-        const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
-        s_f[threadIdx.x] = p.f[(3 - a) * 4 + (3 - b)] * p.fgain;
-    }
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&full[0]), 1); mbar_init(smem_u32(&full[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -187,8 +183,12 @@ __device__ __forceinline__ void fir_tiled_body(const CUtensorMap& tmap_t, const 
         if (noise_mode == 1) asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_nz) : "memory");
     }
     if (noise_mode == 2) s_nz[threadIdx.x] = 0.f;                   // no noise input: both tiles stay zero (2 x 128 floats)
+    pdl_wait();                                                     // T, the filter, the epilogue vectors and y belong to other kernels of the chain
+    if (threadIdx.x < 16) {
+        const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
+        s_f[threadIdx.x] = p.f[(3 - a) * 4 + (3 - b)] * p.fgain;
+    }
     __syncthreads();
-    pdl_wait();                                                     // T, the epilogue vectors and y belong to other kernels of the chain
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = s_f[i];
@@ -440,6 +440,8 @@ fir_act_tiled_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_co
                      const FirParams p, int tiles_x, int tiles_y, int total_tiles, int noise_mode, int strip_ok) {
     if (PACKED) {
         // rank-1 test on the flipped, scaled filter (the same test the body repeats): decided before anything is set up
+        pdl_trigger();
+        pdl_wait();                                                 // (the filter may be the output of the kernel before this one)
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = __ldg(p.f + (15 - i)) * p.fgain;
