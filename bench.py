@@ -387,6 +387,7 @@ def main():
         # the reference's own stylization script runs with --feature_blending_level=2 (scripts/neube_stylize.sh): patches then
         # depend on their raster predecessors; wavefront-batched on one GPU (rank 0 only, the other ranks idle)
         blend_ms = None
+        blend_sharded_ms, blend_equal = None, None
         if not args.no_blend:
             # the dependency chain (2 rows + cols wavefronts) is the critical path, so more GPUs do not shorten ONE blended canvas:
             # with N ranks every rank renders its own canvas (replicas, no collective) and the line reports canvases per second
@@ -404,6 +405,27 @@ def main():
             if world > 1:
                 dist.all_reduce(bt, op=dist.ReduceOp.MAX)
             blend_ms = float(bt[0])
+            # ONE blended canvas on all ranks: the layers before / after the blend point sharded over the ranks, the blend on rank 0
+            # (stylizer._stylize_blended_phased); rank 0 compares the bytes with its own single-GPU canvas
+            if world > 1:
+                stimes = []
+                with torch.no_grad():
+                    for rep in range(3):
+                        barrier()
+                        t0 = time.perf_counter()
+                        shard_canvas = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, feature_blending_level=2, z_per_patch=z_pp,
+                                                        to_host=False)
+                        barrier()
+                        if rep > 0:
+                            stimes.append((time.perf_counter() - t0) * 1e3)
+                    if rank == 0:
+                        solo = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, feature_blending_level=2, z_per_patch=z_pp,
+                                                to_host=False, distributed=False)
+                        blend_equal = bool(torch.equal(shard_canvas, solo))
+                        del solo
+                st_ = torch.tensor([float(np.median(stimes))], dtype=torch.float64, device=dev)
+                dist.all_reduce(st_, op=dist.ReduceOp.MAX)
+                blend_sharded_ms = float(st_[0])
         barrier()
         del d_guidance
         if size != 2000:
@@ -524,8 +546,13 @@ def main():
             line['canvas'] = dict(canvas_legs['main'])
             line['canvas'].update({'ms_feature_blending_level2_1gpu': blend_ms,
                                    'blended_canvases_per_s': (world / (blend_ms * 1e-3)) if blend_ms else None,
-                                   'blended': 'feature_blending_level=2 (what scripts/neube_stylize.sh runs): one canvas per GPU, wavefront '
-                                              'schedule + one CUDA graph per wavefront size; max over ranks; canvases/s = n_gpus / that',
+                                   'ms_feature_blending_level2_sharded': blend_sharded_ms,
+                                   'blended_sharded_equals_1gpu': blend_equal,
+                                   'blended': 'feature_blending_level=2 (what scripts/neube_stylize.sh runs): every patch\'s layers before / '
+                                              'after the blend point at batch 256, only the blend kernel in wavefront order '
+                                              '(stylizer._stylize_blended_phased). _1gpu: one canvas per GPU (max over ranks; canvases/s = '
+                                              'n_gpus / that); _sharded (n_gpus > 1): ONE canvas, those layers sharded over the ranks, the '
+                                              'blend on rank 0, wall clock between barriers',
                                    'what': 'uint8 guidance on the device -> crops -> encoder+generator+composite (8-anchor z interpolation) -> '
                                            'every rank places its tiles into the canvas rows it owns -> one batched NCCL send/recv of those bands '
                                            'into the canvas on rank 0 (SURVEY 8d config 5); ms_host_to_host: host guidance in (each rank uploads '

@@ -349,6 +349,29 @@ class TriadPaintEngine:
         _, out_u8 = self._composite(triad_data, opts, geom.shape[0], want_f32=False, crop_margin=crop_margin)
         return out_u8, triad_data
 
+    def render_split_pre(self, geom, opts, res: int, out: torch.Tensor) -> torch.Tensor:
+        """First half of ``render_tiles`` for the stylizer's phased feature blending: encoder, mapping and the synthesis blocks
+        up to ``conv1`` of block ``res``, whose un-modulated bf16 output lands in ``out`` [B, res, res + 1, C] (zero gap column).
+        Returns the styles [B, C] the consumer of that feature map is modulated with (applied after the blend)."""
+        _lib.require_cuda(geom, 'render_split_pre')
+        _, raw = self._generate(geom, opts, split=('pre', int(res), out))
+        return raw['split_next_scale']
+
+    def render_split_post(self, xin: torch.Tensor, opts, res: int, crop_margin: int = 0) -> torch.Tensor:
+        """Second half: the synthesis blocks above ``res`` from ``xin`` [B, res, res + 1, C] (the blended feature map, already
+        multiplied by the next layer's styles), ToRGB and the composite -> uint8 tiles [B, W-2m, W-2m, 4] on the device."""
+        _lib.require_cuda(xin, 'render_split_post')
+        B, G = xin.shape[0], self.G
+        opts.to(self.device)
+        opts.prepare_style(B, self.device)
+        extra = opts.custom_args if opts.style_ws is not None else {}
+        ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
+        ws = G.expand_ws(ws).to(self.device, torch.float32).contiguous()
+        _, triad_data = G.forward_pre_mapped(ws=ws, positions=opts.get_position(self.device), geom_feature=None, return_debug_data=True,
+                                             noise_mode='const', split=('post', int(res), xin), **extra)
+        _, out_u8 = self._composite(triad_data, opts, B, want_f32=False, crop_margin=crop_margin)
+        return out_u8
+
     def render_stroke(self, stroke_patch, canvas_patch, opts, **generator_kwargs):
         """[W,W,C] uint8 stroke patch -> ([W,W,4] uint8, None) (brush.py:683-701)."""
         geom = self.prepare_geom_input(stroke_patch)

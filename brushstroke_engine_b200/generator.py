@@ -164,6 +164,7 @@ class Generator:
         self.max_cached_patches = 1024     # ... as long as their batch sizes sum to no more than this (~23 MB per patch)
         self._noise_cache = None
         self._window_blend = None          # WindowBlend of the running _synthesis call (flat path)
+        self._split = None                 # ('pre' | 'post', res, tensor) of the running _synthesis call (flat path)
         self._noise_prefetched = None      # one-shot (positions, maps) computed ahead of _synthesis by prefetch_noise
         self.last_up_fir_first = os.environ.get('NBE_LAST_UP_FIR_FIRST') is not None   # A/B switch: 4x-FLOP FIR-first path at 128^2
         self.use_flat = os.environ.get('NBE_GEN_V1') is None      # flat shifted-window kernels + algorithmic-cost up-sampling
@@ -425,7 +426,7 @@ class Generator:
 
     def _synthesis(self, ws, geom_feature, pos_encoding=None, return_debug_data=False, return_features=None,
                    blended_features=None, noise_buffers=None, positions=None, noise_mode='random', force_fp32=False,
-                   fused_modconv=None, norm_noise_positions=None, window_blend=None, **unused):
+                   fused_modconv=None, norm_noise_positions=None, window_blend=None, split=None, **unused):
         if pos_encoding is not None:
             raise RuntimeError('synthesis: positional-encoding injection is not part of the style1/2 architecture')
         _lib.require_cuda(ws, 'synthesis')
@@ -444,6 +445,18 @@ class Generator:
         if window_blend is not None and not flat:
             raise RuntimeError('synthesis: window_blend needs the flat bf16 path (no force_fp32 / return_features / blended_features)')
         self._window_blend = window_blend
+        # split = ('pre', res, out): run up to conv1 of block `res`, whose un-modulated output goes to `out` ([B, res, res + 1, C] bf16,
+        # zero gap column), and stop; ('post', res, xin): start at block 2 * res from `xin`, the (blended, modulated) input of its
+        # conv0.  The stylizer's phased feature blending runs every patch's layers before / after the blend point at full batch
+        # size and only the blend itself in dependency order (stylizer._stylize_blended_phased).
+        if split is not None:
+            if not flat or window_blend is not None:
+                raise RuntimeError('synthesis: split needs the flat bf16 path without window_blend')
+            if split[0] not in ('pre', 'post') or split[1] not in cfg.block_resolutions or split[1] >= cfg.img_resolution \
+                    or any(r >= split[1] for r in cfg.geom_feature_resolutions):
+                raise RuntimeError(f'synthesis: cannot split at block {split[1]} (needs a block below the output resolution and above '
+                                   'every geometry-feature injection)')
+        self._split = split
         if injected and not flat:
             raise RuntimeError('synthesis: InjectedGeometry needs the flat bf16 path (no force_fp32 / return_features / blended_features)')
         with torch.cuda.device(self.device):
@@ -632,13 +645,21 @@ class Generator:
         geo_idx = 0
         img = uvs = None
         last = cfg.img_resolution
-        # b4 input: const * styles(b4.conv1), zero-gapped [B,4,5,C]
-        c4 = self._layer_by_name['b4.conv1']
-        xin = wsb['in4']
-        xin[:, :, :4, :] = (self._const_nhwc.unsqueeze(0) * styles[c4.name][:, None, None, :]).to(torch.bfloat16)
-        xin_pitch = 5
+        split = self._split
+        skip_to = split[1] if (split is not None and split[0] == 'post') else 0
+        if skip_to:
+            xin, xin_pitch = split[2], skip_to + 1
+            assert xin.dtype == torch.bfloat16 and xin.is_contiguous() and tuple(xin.shape[:3]) == (B, skip_to, skip_to + 1)
+        else:
+            # b4 input: const * styles(b4.conv1), zero-gapped [B,4,5,C]
+            c4 = self._layer_by_name['b4.conv1']
+            xin = wsb['in4']
+            xin[:, :, :4, :] = (self._const_nhwc.unsqueeze(0) * styles[c4.name][:, None, None, :]).to(torch.bfloat16)
+            xin_pitch = 5
         nvtx = _lib.NVTX
         for res in cfg.block_resolutions:
+            if res <= skip_to:
+                continue
             conv1 = self._layer_by_name[f'b{res}.conv1']
             if nvtx:
                 torch.cuda.nvtx.range_push(f'b{res}: modulated_conv2d + bias_act')
@@ -743,6 +764,10 @@ class Generator:
             nxt = self._layer_by_name[f'b{res * 2}.conv0']
             out = geom_feature.buffers[res] if (injected and res in cfg.geom_feature_resolutions) else wsb[f'out{res}']
             ns = styles[nxt.name][:, :conv1.cout].contiguous() if nxt.cin != conv1.cout else styles[nxt.name]
+            pre_split = split is not None and split[0] == 'pre' and split[1] == res
+            if pre_split:
+                out = split[2]
+                assert out.dtype == torch.bfloat16 and out.is_contiguous() and tuple(out.shape[:3]) == (B, res, res + 1) and out.shape[3] >= conv1.cout
             if res <= self.small_pertap_max and x1_pitch == res + 1 and x1.shape[1] == res:
                 # small maps: the flat kernel tiles every image by itself (a 4x4 map fills 20 of a tile's 256 positions); the per-tap
                 # kernel packs 128 / res^2 images into one position tile and reads the same zero-gapped layout as a 'same'
@@ -750,11 +775,15 @@ class Generator:
                 _lib.call('nbe_conv_tc_bf16_ex', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(out), B, res, res, conv1.cin, x1.shape[3],
                           conv1.cout, out.shape[3], 3, 0, 1, res, res + 1, res + 1, res * (res + 1), _lib.ptr(dcoefs[conv1.name]),
                           _lib.ptr(noise), nsn, float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp,
-                          _lib.ptr(None if wb is not None else ns), st)
+                          _lib.ptr(None if (wb is not None or pre_split) else ns), st)
             else:
                 _lib.call('nbe_conv3x3_flat_bf16', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(out), B, res, res, conv1.cin, x1.shape[3],
                           x1_pitch, 0, conv1.cout, out.shape[3], res + 1, res * (res + 1), _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn,
-                          float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(None if wb is not None else ns), st)
+                          float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(None if (wb is not None or pre_split) else ns), st)
+            if pre_split:
+                if nvtx:
+                    torch.cuda.nvtx.range_pop()
+                return None, None, {'split_next_scale': ns}
             if wb is not None:
                 wb.apply(out, res + 1, conv1.cout, ns, B)             # blend, save, then the modulation the epilogue would have fused
             if res in cfg.geom_feature_resolutions:

@@ -453,10 +453,18 @@ def stylize(engine: TriadPaintEngine, guidance: np.ndarray, opts: GanBrushOption
     if feature_blending_level > 0:
         job = CanvasJob(engine, guidance, crop_margin, stitching_mode)
         if world > 1:
-            raise RuntimeError('stylize: feature blending makes patches raster-dependent; one canvas runs on one GPU '
-                               '(pass distributed=False and give every rank its own canvas)')
-        blend = _stylize_blended if os.environ.get('NBE_BLEND_SEQUENTIAL') else _stylize_blended_wavefront
-        canvas = blend(engine, job, opts, feature_blending_level, z_per_patch)
+            # several GPUs: the layers before and after the blend point are sharded, the blend itself runs on rank 0
+            # (_stylize_blended_phased); levels whose blend point the generator cannot be split at stay on one GPU
+            res = engine.patch_width // 2 ** (feature_blending_level - 1)
+            if not (_flat_blend_ok(engine) and _phased_blend_ok(engine, res, len(job.crops_yx))):
+                raise RuntimeError('stylize: this feature-blending level / engine cannot be split at the blend point, so one canvas runs on '
+                                   'one GPU (pass distributed=False and give every rank its own canvas)')
+            canvas = _stylize_blended_phased(engine, job, opts, feature_blending_level, z_per_patch, batch_size, group, world, rank)
+            if rank != 0:
+                return (None, job) if return_job else None
+        else:
+            blend = _stylize_blended if os.environ.get('NBE_BLEND_SEQUENTIAL') else _stylize_blended_wavefront
+            canvas = blend(engine, job, opts, feature_blending_level, z_per_patch)
         out = job.finish(canvas, on_white, to_host)
         return (out, job) if return_job else out
 
@@ -609,6 +617,130 @@ def _blend_context(engine, fh, fw, res, margin, cm, crop_margin) -> _BlendContex
         ctx = _BlendContext(engine, fh, fw, res, margin, cm, crop_margin)
     cache[key] = ctx
     return ctx
+
+
+PHASED_BLEND_MAX_BYTES = 16 << 30          # budget for the per-canvas buffer of pre-blend feature maps (2.35 GB for 4096^2, level 2)
+
+
+def _phased_blend_ok(engine: TriadPaintEngine, res: int, n_crops: int) -> bool:
+    cfg = engine.G.cfg
+    if os.environ.get('NBE_BLEND_WAVEFRONT_GRAPHS') is not None:                      # A/B switch: one whole forward per wavefront
+        return False
+    return res < cfg.img_resolution and res in cfg.block_resolutions and all(r < res for r in cfg.geom_feature_resolutions) \
+        and n_crops * res * (res + 1) * cfg.channels(res) * 2 <= PHASED_BLEND_MAX_BYTES
+
+
+def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOptions, level: int, z_per_patch, batch_size: int = 256,
+                            group=None, world: int = 1, rank: int = 0):
+    """Feature blending with the work split at the blend point.  Patch n's layers BEFORE the blend (encoder, mapping, blocks up to
+    conv1 of the blended block) depend on nothing another patch computes, and its layers AFTER the blend only on its own blended
+    feature map: the raster dependency of brush.py:190-242 runs through the blend alone (look up what earlier patches saved,
+    blend, save the core).  So: (1) every patch's first half at full batch size, un-modulated feature maps into one buffer in
+    wavefront order; (2) ``nbe_blend_window_nhwc_bf16`` wavefront by wavefront over slices of that buffer -- the only sequential
+    part, ~140 launches of a few microseconds for a 4096^2 canvas; (3) every patch's second half at full batch size.  Same kernels
+    on the same per-patch inputs as the wavefront schedule, hence the same bytes (every kernel is batch-invariant); 4096^2, level 2:
+    the generator runs 2 x 9 batches of 256 instead of 141 of <= 24.
+
+    Several GPUs (``world`` > 1, one process per GPU): phases (1) and (3) are sharded -- rank r takes the r-th contiguous share of
+    the wavefront-ordered patch list -- and the blend runs on rank 0 over the gathered feature maps: one batched NCCL send/recv of
+    the shares to rank 0, the ~140 blend launches there, one send/recv back, and the finished tiles gathered on rank 0, which
+    places them.  Every patch still goes through the same kernels in the same blend order: the canvas equals the single-GPU one
+    bit for bit.  Returns the canvas on rank 0, None elsewhere."""
+    import torch.distributed as dist
+    from .generator import WindowBlend
+    dev = engine.device
+    down = 2 ** (level - 1)
+    res = engine.patch_width // down
+    C = engine.G.cfg.channels(res)
+    fh, fw = int(math.ceil(job.canvas_h / down)), int(math.ceil(job.canvas_w / down))
+    margin = 16 // down                                   # PaintingHelper.feature_blending_margin = 16
+    cm = job.crop_margin // down
+    snapped = (job.crops_yx // down) * down                                               # brush.py:253-258
+    n_crops = len(job.crops_yx)
+    waves = blending_wavefronts(job.crops_yx, engine.patch_width)
+    d_order = torch.from_numpy(np.concatenate(waves)).to(dev)
+    d_pos = job.d_crops.to(torch.int64)[d_order]
+    d_cropsel = job.d_crops[d_order].contiguous()
+    z_sel = z_per_patch[d_order] if z_per_patch is not None else None
+    shares = [(n_crops * r // world, n_crops * (r + 1) // world) for r in range(world)]
+    s0, s1 = shares[rank]
+    # rank 0 holds every patch's feature map (it blends them); the other ranks only their own share
+    n_buf, b0 = (n_crops, 0) if rank == 0 else (s1 - s0, s0)
+    key = (n_buf, res, C)
+    buf = engine.__dict__.get('_phased_blend_buf')
+    if buf is None or buf[0] != key:
+        buf = engine.__dict__['_phased_blend_buf'] = (key, torch.zeros((n_buf, res, res + 1, C), dtype=torch.bfloat16, device=dev),
+                                                      torch.empty((n_buf, C), dtype=torch.float32, device=dev))
+    _, X, NS = buf                                         # (the gap column of X is never written: zero from the allocation on)
+    tiles_all = torch.empty((n_buf, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
+
+    def chunk_opts(sl):
+        o = GanBrushOptions()
+        o.__dict__.update(opts.__dict__)
+        if z_sel is not None:
+            o.style_z, o.style_ws = z_sel[sl], None
+        o.position = d_pos[sl]
+        return o
+
+    def exchange(tensors, to_root: bool):
+        """rank r's share of every tensor in ``tensors`` (rank 0: full-length, others: share-length) to rank 0 or back."""
+        if world == 1:
+            return
+        ops = []
+        for t in tensors:
+            if rank == 0:
+                for r in range(1, world):
+                    a, b = shares[r]
+                    if b > a:
+                        ops.append(dist.P2POp(dist.irecv if to_root else dist.isend, t[a:b], dist.get_global_rank(group, r) if group is not None else r, group))
+            elif s1 > s0:
+                ops.append(dist.P2POp(dist.isend if to_root else dist.irecv, t[:s1 - s0], dist.get_global_rank(group, 0) if group is not None else 0, group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    # even batches, like _render_job_tiles: a short tail batch costs almost a full launch sequence (276 patches -> 1 x 276)
+    n_own = s1 - s0
+    n_batches = 1 if n_own <= batch_size * 5 // 4 else -(-n_own // batch_size)
+    batch_size = max(1, -(-n_own // n_batches)) if n_own else batch_size
+    with torch.cuda.device(dev):
+        for c0 in range(s0, s1, batch_size):                                              # (1) everything before the blend
+            sl = slice(c0, min(s1, c0 + batch_size))
+            loc = slice(sl.start - b0, sl.stop - b0)
+            n = sl.stop - sl.start
+            geom = torch.empty((n, 1, job.patch, job.patch), dtype=torch.float32, device=dev)
+            _lib.call('nbe_gather_geom_patches', _lib.ptr(job.d_geom), job.canvas_h, job.canvas_w, _lib.ptr(d_cropsel[sl]), _lib.ptr(geom), n,
+                      job.patch, _lib.stream())
+            NS[loc] = engine.render_split_pre(geom, chunk_opts(sl), res, X[loc])
+        exchange([X, NS], to_root=True)
+        if rank == 0:                                                                     # (2) the blend, in dependency order
+            ctx = _blend_context(engine, fh, fw, res, margin, cm, job.crop_margin)
+            ctx.reset()
+            d_fyx = torch.from_numpy(np.ascontiguousarray(snapped // down).astype(np.int32)).to(dev)[d_order].contiguous()
+            off = 0
+            for idx in waves:
+                sl = slice(off, off + len(idx))
+                off += len(idx)
+                WindowBlend(res, ctx.fcanvas, ctx.fmask, d_fyx[sl], ctx.base_alpha, cm).apply(X[sl], res + 1, C, NS[sl], len(idx))
+        exchange([X], to_root=False)
+        for c0 in range(s0, s1, batch_size):                                              # (3) everything after it
+            sl = slice(c0, min(s1, c0 + batch_size))
+            loc = slice(sl.start - b0, sl.stop - b0)
+            tiles_all[loc] = engine.render_split_post(X[loc], chunk_opts(sl), res, crop_margin=job.crop_margin)
+        exchange([tiles_all], to_root=True)
+        if rank != 0:
+            return None
+        canvas = torch.zeros((job.canvas_h, job.canvas_w, 4), dtype=torch.uint8, device=dev)
+        owner = torch.empty((job.canvas_h, job.canvas_w), dtype=torch.int32, device=dev)
+        # last writer wins in RASTER order: tile k of the wavefront-ordered list is crop d_order[k]
+        raster_yx = torch.from_numpy(np.ascontiguousarray(snapped + job.crop_margin).astype(np.int32)).to(dev)
+        _lib.call('nbe_tile_owner_map', _lib.ptr(raster_yx), n_crops, job.tile, _lib.ptr(owner), job.canvas_h, job.canvas_w, _lib.stream())
+        raster_tiles = torch.empty_like(tiles_all)
+        raster_tiles[d_order] = tiles_all
+        order = torch.arange(n_crops, dtype=torch.int32, device=dev)
+        _lib.call('nbe_place_tiles', _lib.ptr(raster_tiles), _lib.ptr(raster_yx), _lib.ptr(order), n_crops, job.tile, _lib.ptr(owner),
+                  _lib.ptr(canvas), job.canvas_h, job.canvas_w, _lib.stream())
+    return canvas
 
 
 def _stylize_blended_flat(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOptions, level: int, z_per_patch, sequential: bool):
@@ -779,6 +911,8 @@ def _stylize_blended_wavefront(engine: TriadPaintEngine, job: CanvasJob, opts: G
     generator calls instead of rows x cols single-patch ones.  The feature canvas starts as zeros with an all-False
     mask (alpha = 1 wherever nothing was saved yet)."""
     if _flat_blend_ok(engine):
+        if _phased_blend_ok(engine, engine.patch_width // 2 ** (level - 1), len(job.crops_yx)):
+            return _stylize_blended_phased(engine, job, opts, level, z_per_patch)
         return _stylize_blended_flat(engine, job, opts, level, z_per_patch, sequential=False)
     dev = engine.device
     down = 2 ** (level - 1)

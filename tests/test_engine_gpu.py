@@ -164,6 +164,28 @@ def test_blending_wavefronts_equal_raster_loop(engines, mode, level):
     assert int((wav[..., 3] > 0).sum()) > 1000                                       # something was painted
 
 
+def test_phased_blending_equals_wavefronts_and_raster_loop(engines):
+    """Feature blending split at the blend point (every patch's layers before / after it at full batch size, only the blend kernel
+    in wavefront order; stylizer._stylize_blended_phased) gives the bytes of the wavefront schedule and of the raster loop -- with a
+    distinct style per patch and chunks smaller than the canvas, so that chunk and wavefront boundaries do not coincide."""
+    from brushstroke_engine_b200 import stylizer
+    eng = engines['bf16']
+    guidance = synthetic.synthetic_guidance(450, 560, num_lines=24, seed=5)          # 5 x 6 crops
+    opts = _opts(P.style_z_from_seed(17), '17')
+    job = stylizer.CanvasJob(eng, guidance, 10, 'all')
+    n = len(job.crops)
+    zpp = torch.cat([P.style_z_from_seed(100 + i % 7) for i in range(n)]).to(eng.device)
+    assert stylizer._phased_blend_ok(eng, 64, n) and not stylizer._phased_blend_ok(eng, 32, n) and not stylizer._phased_blend_ok(eng, 128, n)
+    with torch.no_grad():
+        for z in (None, zpp):
+            seq = stylizer._stylize_blended_flat(eng, job, opts, 2, z, sequential=True)
+            wav = stylizer._stylize_blended_flat(eng, job, opts, 2, z, sequential=False)
+            for bs in (7, 256):
+                ph = stylizer._stylize_blended_phased(eng, job, opts, 2, z, batch_size=bs)
+                assert torch.equal(ph, wav) and torch.equal(ph, seq), (z is None, bs)
+    assert int((ph[..., 3] > 0).sum()) > 1000
+
+
 def test_interactive_graph_session_equals_render_stroke(engines):
     """The CUDA-graph replay of the batch-1 forward gives the same bytes as the eager call, for changing stroke patches
     and canvas positions (the shifted noise depends on the position and must be recomputed inside the graph)."""

@@ -226,7 +226,8 @@ def test_band_jobs_reassemble_the_single_gpu_canvas(bundles):
 
 
 def test_multi_gpu_canvas_equals_single_gpu_under_torchrun(tmp_path):
-    """2 ranks over NCCL (skipped below 2 devices): stylize() sharded == stylize() on one GPU, dense and sparse grids."""
+    """2 ranks over NCCL (skipped below 2 devices): stylize() sharded == stylize() on one GPU, dense and sparse grids, and a
+    feature-blended canvas whose layers around the blend point are sharded (one style, then a style per patch)."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     script = tmp_path / 'mg.py'
@@ -250,6 +251,18 @@ with torch.no_grad():
             solo = stylizer.stylize(eng, guidance, opts, crop_margin=10, stitching_mode=mode, to_host=False, distributed=False)
             ok = ok and bool(torch.equal(out, solo))
         dist.barrier()
+    # one feature-blended canvas (level 2) over both ranks: layers before / after the blend point sharded, the blend on rank 0
+    zpp = None
+    for rep in range(2):
+        out = stylizer.stylize(eng, guidance, opts, crop_margin=10, feature_blending_level=2, z_per_patch=zpp, to_host=False, batch_size=16)
+        if rank == 0:
+            solo = stylizer.stylize(eng, guidance, opts, crop_margin=10, feature_blending_level=2, z_per_patch=zpp, to_host=False, distributed=False)
+            ok = ok and bool(torch.equal(out, solo)) and int((out[..., 3] > 0).sum()) > 1000
+        else:
+            ok = ok and out is None
+        dist.barrier()
+        n = len(stylizer.CanvasJob(eng, guidance, 10, 'all').crops)
+        zpp = torch.cat([P.style_z_from_seed(i %% 5) for i in range(n)]).to(dev)
 if rank == 0:
     open(%r, 'w').write('OK' if ok else 'MISMATCH')
 dist.destroy_process_group()
