@@ -619,6 +619,36 @@ def _blend_context(engine, fh, fw, res, margin, cm, crop_margin) -> _BlendContex
     return ctx
 
 
+def phased_shares(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous shares [a, b) of a list of ``n`` (wavefront-ordered) patches, one per rank."""
+    return [(n * r // world, n * (r + 1) // world) for r in range(world)]
+
+
+def exchange_shares(tensors: Sequence[torch.Tensor], shares: Sequence[Tuple[int, int]], rank: int, to_root: bool, group=None) -> None:
+    """Move every rank's share of each tensor in ``tensors`` to rank 0 (``to_root``) or back, in ONE batched send/recv.  On
+    rank 0 the tensors are full-length (its own share is already in place, share r lives at [a_r, b_r)); on rank r > 0 they hold
+    that rank's share in their first b_r - a_r entries.  Device-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    world = len(shares)
+    if world == 1:
+        return
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    ops = []
+    for t in tensors:
+        if rank == 0:
+            for r in range(1, world):
+                a, b = shares[r]
+                if b > a:
+                    ops.append(dist.P2POp(dist.irecv if to_root else dist.isend, t[a:b], peer(r), group))
+        else:
+            a, b = shares[rank]
+            if b > a:
+                ops.append(dist.P2POp(dist.isend if to_root else dist.irecv, t[:b - a], peer(0), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
 PHASED_BLEND_MAX_BYTES = 16 << 30          # budget for the per-canvas buffer of pre-blend feature maps (2.35 GB for 4096^2, level 2)
 
 
@@ -662,7 +692,7 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
     d_pos = job.d_crops.to(torch.int64)[d_order]
     d_cropsel = job.d_crops[d_order].contiguous()
     z_sel = z_per_patch[d_order] if z_per_patch is not None else None
-    shares = [(n_crops * r // world, n_crops * (r + 1) // world) for r in range(world)]
+    shares = phased_shares(n_crops, world)
     s0, s1 = shares[rank]
     # rank 0 holds every patch's feature map (it blends them); the other ranks only their own share
     n_buf, b0 = (n_crops, 0) if rank == 0 else (s1 - s0, s0)
@@ -683,21 +713,7 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
         return o
 
     def exchange(tensors, to_root: bool):
-        """rank r's share of every tensor in ``tensors`` (rank 0: full-length, others: share-length) to rank 0 or back."""
-        if world == 1:
-            return
-        ops = []
-        for t in tensors:
-            if rank == 0:
-                for r in range(1, world):
-                    a, b = shares[r]
-                    if b > a:
-                        ops.append(dist.P2POp(dist.irecv if to_root else dist.isend, t[a:b], dist.get_global_rank(group, r) if group is not None else r, group))
-            elif s1 > s0:
-                ops.append(dist.P2POp(dist.isend if to_root else dist.irecv, t[:s1 - s0], dist.get_global_rank(group, 0) if group is not None else 0, group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        exchange_shares(tensors, shares, rank, to_root, group)
 
     # even batches, like _render_job_tiles: a short tail batch costs almost a full launch sequence (276 patches -> 1 x 276)
     n_own = s1 - s0

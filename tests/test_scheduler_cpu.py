@@ -118,6 +118,47 @@ def test_multi_rank_exchange_reassembles_canvas(tmp_path, world):
     assert bool(res[0]) and bool(res[1])
 
 
+def _gloo_share_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    n = 11                                                     # 11 patches over 2 / 3 / 4 ranks: uneven shares, an empty one never
+    shares = stylizer.phased_shares(n, world)
+    a, b = shares[rank]
+    full = torch.arange(n * 6, dtype=torch.float32).reshape(n, 2, 3)
+    aux = torch.arange(n, dtype=torch.int64) * 10
+    if rank == 0:
+        x, y = torch.full_like(full, -1.0), torch.full_like(aux, -1)
+        x[a:b], y[a:b] = full[a:b], aux[a:b]
+    else:
+        x, y = full[a:b].clone(), aux[a:b].clone()
+    stylizer.exchange_shares([x, y], shares, rank, to_root=True)                     # what the phased feature blending gathers
+    ok = True
+    if rank == 0:
+        ok = bool(torch.equal(x, full) and torch.equal(y, aux))
+        x = x * 2                                                                    # "blend" on rank 0 ...
+    else:
+        x = torch.zeros_like(x)
+    stylizer.exchange_shares([x], shares, rank, to_root=False)                       # ... and every share travels back
+    ok = ok and bool(torch.equal(x[a:b] if rank == 0 else x, full[a:b] * 2))
+    res = torch.tensor([1 if ok else 0])
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.save(os.path.join(tmp, 'ok_shares.npy'), np.array([int(res[0])]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_phased_blend_share_exchange(tmp_path, world):
+    """world_size 2 and 3 on gloo: the share exchange of the phased feature blending (stylizer.exchange_shares -- every rank's
+    contiguous share of the wavefront-ordered patch list to rank 0 and back) reassembles and returns the data exactly."""
+    assert stylizer.phased_shares(2209, 8)[0] == (0, 276) and stylizer.phased_shares(2209, 8)[-1][1] == 2209
+    assert all(b >= a for a, b in stylizer.phased_shares(3, 8)) and sum(b - a for a, b in stylizer.phased_shares(3, 8)) == 3
+    port = 29000 + (os.getpid() % 400) + world
+    mp.spawn(_gloo_share_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert int(np.load(os.path.join(str(tmp_path), 'ok_shares.npy'))[0]) == 1
+
+
 def test_row_shards_match_shard_bounds_on_the_dense_grid():
     ys, xs = np.meshgrid(np.arange(47) * 88, np.arange(47) * 88, indexing='ij')
     yx = np.stack([ys.ravel(), xs.ravel()], axis=1).astype(np.int32)
