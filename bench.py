@@ -321,7 +321,7 @@ def main():
     if not args.no_canvas:
         from brushstroke_engine_b200 import stylizer
 
-        def canvas_leg(size, interpolate):
+        def canvas_leg(size, interpolate, blended_too=False):
             guidance = synthetic.synthetic_guidance(size, size, num_lines=256 if size >= 4096 else 64, seed=0)
             job_crops, _ = stylizer.generate_stitching_crops(stylizer.pad_geo(guidance, 10), 128, 'all', 20)
             copts = GanBrushOptions()
@@ -376,6 +376,30 @@ def main():
                    'style': '8-anchor z interpolation along x' if interpolate else 'one style (seed 594)'}
             if equal is not None:
                 leg['canvas_equals_1gpu'] = equal
+            if blended_too and not args.no_blend:
+                # the same drawing the way scripts/neube_stylize.sh renders it: --feature_blending_level=2 (one canvas over all ranks)
+                btimes_, bout = [], None
+                with torch.no_grad():
+                    for rep in range(3):
+                        barrier()
+                        t0 = time.perf_counter()
+                        bout = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, batch_size=B, z_per_patch=z_pp, to_host=False,
+                                                feature_blending_level=2)
+                        barrier()
+                        if rep > 0:
+                            btimes_.append((time.perf_counter() - t0) * 1e3)
+                    beq = None
+                    if world > 1 and rank == 0:
+                        solo = stylizer.stylize(engine, d_guidance, copts, crop_margin=10, batch_size=B, z_per_patch=z_pp, to_host=False,
+                                                feature_blending_level=2, distributed=False)
+                        beq = bool(torch.equal(solo, bout))
+                    barrier()
+                bt_ = torch.tensor([float(np.median(btimes_))], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(bt_, op=dist.ReduceOp.MAX)
+                leg['ms_feature_blending_level2'] = float(bt_[0])
+                if beq is not None:
+                    leg['blended_equals_1gpu'] = beq
             return leg, d_guidance, copts, z_pp
 
         size = args.canvas
@@ -429,7 +453,7 @@ def main():
         barrier()
         del d_guidance
         if size != 2000:
-            canvas_legs['config3_2000'] = canvas_leg(2000, False)[0]          # BASELINE configs[3]
+            canvas_legs['config3_2000'] = canvas_leg(2000, False, blended_too=True)[0]          # BASELINE configs[3]
 
     # ---- interactive use: one 128^2 stroke patch per call through the reference-facing render_stroke
     #      (host uint8 patch in, host uint8 RGBA out; wall clock, rank 0) ----
