@@ -453,9 +453,10 @@ class Generator:
             if not flat or window_blend is not None:
                 raise RuntimeError('synthesis: split needs the flat bf16 path without window_blend')
             if split[0] not in ('pre', 'post') or split[1] not in cfg.block_resolutions or split[1] >= cfg.img_resolution \
-                    or any(r >= split[1] for r in cfg.geom_feature_resolutions):
-                raise RuntimeError(f'synthesis: cannot split at block {split[1]} (needs a block below the output resolution and above '
-                                   'every geometry-feature injection)')
+                    or any(r > split[1] for r in cfg.geom_feature_resolutions) \
+                    or (split[0] == 'pre' and split[1] in cfg.geom_feature_resolutions and not injected):
+                raise RuntimeError(f'synthesis: cannot split at block {split[1]} (needs a block below the output resolution, at or above '
+                                   'every geometry-feature injection, and geometry injected by the encoder when it happens at that block)')
         self._split = split
         if injected and not flat:
             raise RuntimeError('synthesis: InjectedGeometry needs the flat bf16 path (no force_fp32 / return_features / blended_features)')
@@ -766,8 +767,13 @@ class Generator:
             ns = styles[nxt.name][:, :conv1.cout].contiguous() if nxt.cin != conv1.cout else styles[nxt.name]
             pre_split = split is not None and split[0] == 'pre' and split[1] == res
             if pre_split:
-                out = split[2]
-                assert out.dtype == torch.bfloat16 and out.is_contiguous() and tuple(out.shape[:3]) == (B, res, res + 1) and out.shape[3] >= conv1.cout
+                # a block whose output buffer also holds injected geometry channels keeps writing there (the encoder's share is
+                # already in it) and the whole buffer is copied out afterwards; otherwise conv1 writes straight into the caller's
+                copy_out = res in cfg.geom_feature_resolutions
+                if not copy_out:
+                    out = split[2]
+                assert split[2].dtype == torch.bfloat16 and split[2].is_contiguous() and tuple(split[2].shape) == tuple(out.shape) \
+                    and out.shape[3] >= conv1.cout
             if res <= self.small_pertap_max and x1_pitch == res + 1 and x1.shape[1] == res:
                 # small maps: the flat kernel tiles every image by itself (a 4x4 map fills 20 of a tile's 256 positions); the per-tap
                 # kernel packs 128 / res^2 images into one position tile and reads the same zero-gapped layout as a 'same'
@@ -781,6 +787,11 @@ class Generator:
                           x1_pitch, 0, conv1.cout, out.shape[3], res + 1, res * (res + 1), _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn,
                           float(ngain), _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, _lib.ptr(None if (wb is not None or pre_split) else ns), st)
             if pre_split:
+                if copy_out:
+                    if geom_feature.ready_event is not None:
+                        torch.cuda.current_stream().wait_event(geom_feature.ready_event)      # the encoder's channels are in place
+                        geom_feature.ready_event = None
+                    split[2].copy_(out)
                 if nvtx:
                     torch.cuda.nvtx.range_pop()
                 return None, None, {'split_next_scale': ns}

@@ -656,8 +656,8 @@ def _phased_blend_ok(engine: TriadPaintEngine, res: int, n_crops: int) -> bool:
     cfg = engine.G.cfg
     if os.environ.get('NBE_BLEND_WAVEFRONT_GRAPHS') is not None:                      # A/B switch: one whole forward per wavefront
         return False
-    return res < cfg.img_resolution and res in cfg.block_resolutions and all(r < res for r in cfg.geom_feature_resolutions) \
-        and n_crops * res * (res + 1) * cfg.channels(res) * 2 <= PHASED_BLEND_MAX_BYTES
+    return res < cfg.img_resolution and res in cfg.block_resolutions and all(r <= res for r in cfg.geom_feature_resolutions) \
+        and n_crops * res * (res + 1) * cfg.block_in_channels(res * 2) * 2 <= PHASED_BLEND_MAX_BYTES
 
 
 def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOptions, level: int, z_per_patch, batch_size: int = 256,
@@ -681,7 +681,8 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
     dev = engine.device
     down = 2 ** (level - 1)
     res = engine.patch_width // down
-    C = engine.G.cfg.channels(res)
+    C = engine.G.cfg.channels(res)                        # blended channels
+    Cbuf = engine.G.cfg.block_in_channels(res * 2)        # channels of the buffer that feeds the next block (+ injected geometry at 32^2)
     fh, fw = int(math.ceil(job.canvas_h / down)), int(math.ceil(job.canvas_w / down))
     margin = 16 // down                                   # PaintingHelper.feature_blending_margin = 16
     cm = job.crop_margin // down
@@ -696,10 +697,10 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
     s0, s1 = shares[rank]
     # rank 0 holds every patch's feature map (it blends them); the other ranks only their own share
     n_buf, b0 = (n_crops, 0) if rank == 0 else (s1 - s0, s0)
-    key = (n_buf, res, C)
+    key = (n_buf, res, Cbuf)
     buf = engine.__dict__.get('_phased_blend_buf')
     if buf is None or buf[0] != key:
-        buf = engine.__dict__['_phased_blend_buf'] = (key, torch.zeros((n_buf, res, res + 1, C), dtype=torch.bfloat16, device=dev),
+        buf = engine.__dict__['_phased_blend_buf'] = (key, torch.zeros((n_buf, res, res + 1, Cbuf), dtype=torch.bfloat16, device=dev),
                                                       torch.empty((n_buf, C), dtype=torch.float32, device=dev))
     _, X, NS = buf                                         # (the gap column of X is never written: zero from the allocation on)
     tiles_all = torch.empty((n_buf, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)

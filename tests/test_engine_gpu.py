@@ -175,14 +175,16 @@ def test_phased_blending_equals_wavefronts_and_raster_loop(engines):
     job = stylizer.CanvasJob(eng, guidance, 10, 'all')
     n = len(job.crops)
     zpp = torch.cat([P.style_z_from_seed(100 + i % 7) for i in range(n)]).to(eng.device)
-    assert stylizer._phased_blend_ok(eng, 64, n) and not stylizer._phased_blend_ok(eng, 32, n) and not stylizer._phased_blend_ok(eng, 128, n)
+    # level 2 blends at 64^2, level 3 at 32^2 (the block whose output buffer also carries the encoder's 256 injected channels);
+    # level 1 blends at the output resolution, where the generator is not split
+    assert stylizer._phased_blend_ok(eng, 64, n) and stylizer._phased_blend_ok(eng, 32, n) and not stylizer._phased_blend_ok(eng, 128, n)
     with torch.no_grad():
-        for z in (None, zpp):
-            seq = stylizer._stylize_blended_flat(eng, job, opts, 2, z, sequential=True)
-            wav = stylizer._stylize_blended_flat(eng, job, opts, 2, z, sequential=False)
+        for level, z in ((2, None), (2, zpp), (3, zpp)):
+            seq = stylizer._stylize_blended_flat(eng, job, opts, level, z, sequential=True)
+            wav = stylizer._stylize_blended_flat(eng, job, opts, level, z, sequential=False)
             for bs in (7, 256):
-                ph = stylizer._stylize_blended_phased(eng, job, opts, 2, z, batch_size=bs)
-                assert torch.equal(ph, wav) and torch.equal(ph, seq), (z is None, bs)
+                ph = stylizer._stylize_blended_phased(eng, job, opts, level, z, batch_size=bs)
+                assert torch.equal(ph, wav) and torch.equal(ph, seq), (level, z is None, bs)
     assert int((ph[..., 3] > 0).sum()) > 1000
 
 
