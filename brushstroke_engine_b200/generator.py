@@ -452,10 +452,11 @@ class Generator:
         if split is not None:
             if not flat or window_blend is not None:
                 raise RuntimeError('synthesis: split needs the flat bf16 path without window_blend')
-            if split[0] not in ('pre', 'post') or split[1] not in cfg.block_resolutions or split[1] >= cfg.img_resolution \
+            if split[0] not in ('pre', 'post') or split[1] not in cfg.block_resolutions or split[1] > cfg.img_resolution \
+                    or (split[1] == cfg.img_resolution and self._canvas_format) \
                     or any(r > split[1] for r in cfg.geom_feature_resolutions) \
                     or (split[0] == 'pre' and split[1] in cfg.geom_feature_resolutions and not injected):
-                raise RuntimeError(f'synthesis: cannot split at block {split[1]} (needs a block below the output resolution, at or above '
+                raise RuntimeError(f'synthesis: cannot split at block {split[1]} (needs a block at or above '
                                    'every geometry-feature injection, and geometry injected by the encoder when it happens at that block)')
         self._split = split
         if injected and not flat:
@@ -648,6 +649,12 @@ class Generator:
         last = cfg.img_resolution
         split = self._split
         skip_to = split[1] if (split is not None and split[0] == 'post') else 0
+        if skip_to == last:
+            # split at the output resolution: only ToRGB is left (the last feature map is dense, without a gap column)
+            y = split[2]
+            assert y.dtype == torch.bfloat16 and y.is_contiguous() and tuple(y.shape[:3]) == (B, last, last)
+            img, uvs = self._torgb(y, True, y.shape[3], rgb_styles, colors, B)
+            return img, uvs, {}
         if skip_to:
             xin, xin_pitch = split[2], skip_to + 1
             assert xin.dtype == torch.bfloat16 and xin.is_contiguous() and tuple(xin.shape[:3]) == (B, skip_to, skip_to + 1)
@@ -720,12 +727,21 @@ class Generator:
                     torch.cuda.nvtx.range_pop()
                 break
             wb = self._window_blend if (self._window_blend is not None and self._window_blend.res == res) else None
-            if res == last and wb is not None:
+            pre_last = res == last and split is not None and split[0] == 'pre' and split[1] == res
+            if res == last and (wb is not None or pre_last):
                 # blending at the output resolution: the last feature map must exist in memory, so ToRGB runs as its own kernel
-                y = torch.empty((B, res, res, conv1.cout), dtype=torch.bfloat16, device=dev)
+                if pre_last:
+                    y = split[2]
+                    assert y.dtype == torch.bfloat16 and y.is_contiguous() and tuple(y.shape) == (B, res, res, conv1.cout)
+                else:
+                    y = torch.empty((B, res, res, conv1.cout), dtype=torch.bfloat16, device=dev)
                 _lib.call('nbe_conv_tc_bf16', _lib.ptr(x1), _lib.ptr(conv1.wq), _lib.ptr(y), B, res, res, conv1.cin, x1.shape[3],
                           conv1.cout, conv1.cout, 3, 0, _lib.ptr(dcoefs[conv1.name]), _lib.ptr(noise), nsn, float(ngain),
                           _lib.ptr(conv1.bias), 0.2, SQRT2, clamp, None, st)
+                if pre_last:
+                    if nvtx:
+                        torch.cuda.nvtx.range_pop()
+                    return None, None, {'split_next_scale': None}
                 wb.apply(y, res, conv1.cout, None, B)
                 img, uvs = self._torgb(y, True, conv1.cout, rgb_styles, colors, B)
                 if nvtx:

@@ -656,8 +656,9 @@ def _phased_blend_ok(engine: TriadPaintEngine, res: int, n_crops: int) -> bool:
     cfg = engine.G.cfg
     if os.environ.get('NBE_BLEND_WAVEFRONT_GRAPHS') is not None:                      # A/B switch: one whole forward per wavefront
         return False
-    return res < cfg.img_resolution and res in cfg.block_resolutions and all(r <= res for r in cfg.geom_feature_resolutions) \
-        and n_crops * res * (res + 1) * cfg.block_in_channels(res * 2) * 2 <= PHASED_BLEND_MAX_BYTES
+    cbuf = cfg.channels(res) if res == cfg.img_resolution else cfg.block_in_channels(res * 2)
+    return res <= cfg.img_resolution and res in cfg.block_resolutions and all(r <= res for r in cfg.geom_feature_resolutions) \
+        and n_crops * res * (res + 1) * cbuf * 2 <= PHASED_BLEND_MAX_BYTES
 
 
 def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanBrushOptions, level: int, z_per_patch, batch_size: int = 256,
@@ -682,7 +683,9 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
     down = 2 ** (level - 1)
     res = engine.patch_width // down
     C = engine.G.cfg.channels(res)                        # blended channels
-    Cbuf = engine.G.cfg.block_in_channels(res * 2)        # channels of the buffer that feeds the next block (+ injected geometry at 32^2)
+    last = res == engine.G.cfg.img_resolution             # level 1: the blended map is the dense last feature map (no gap column, ToRGB follows)
+    Cbuf = C if last else engine.G.cfg.block_in_channels(res * 2)   # channels of the buffer that feeds the next block (+ injected geometry at 32^2)
+    pitch = res if last else res + 1
     fh, fw = int(math.ceil(job.canvas_h / down)), int(math.ceil(job.canvas_w / down))
     margin = 16 // down                                   # PaintingHelper.feature_blending_margin = 16
     cm = job.crop_margin // down
@@ -700,7 +703,7 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
     key = (n_buf, res, Cbuf)
     buf = engine.__dict__.get('_phased_blend_buf')
     if buf is None or buf[0] != key:
-        buf = engine.__dict__['_phased_blend_buf'] = (key, torch.zeros((n_buf, res, res + 1, Cbuf), dtype=torch.bfloat16, device=dev),
+        buf = engine.__dict__['_phased_blend_buf'] = (key, torch.zeros((n_buf, res, pitch, Cbuf), dtype=torch.bfloat16, device=dev),
                                                       torch.empty((n_buf, C), dtype=torch.float32, device=dev))
     _, X, NS = buf                                         # (the gap column of X is never written: zero from the allocation on)
     tiles_all = torch.empty((n_buf, job.tile, job.tile, 4), dtype=torch.uint8, device=dev)
@@ -728,8 +731,10 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
             geom = torch.empty((n, 1, job.patch, job.patch), dtype=torch.float32, device=dev)
             _lib.call('nbe_gather_geom_patches', _lib.ptr(job.d_geom), job.canvas_h, job.canvas_w, _lib.ptr(d_cropsel[sl]), _lib.ptr(geom), n,
                       job.patch, _lib.stream())
-            NS[loc] = engine.render_split_pre(geom, chunk_opts(sl), res, X[loc])
-        exchange([X, NS], to_root=True)
+            ns_ = engine.render_split_pre(geom, chunk_opts(sl), res, X[loc])
+            if ns_ is not None:
+                NS[loc] = ns_
+        exchange([X] if last else [X, NS], to_root=True)
         if rank == 0:                                                                     # (2) the blend, in dependency order
             ctx = _blend_context(engine, fh, fw, res, margin, cm, job.crop_margin)
             ctx.reset()
@@ -738,7 +743,7 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
             for idx in waves:
                 sl = slice(off, off + len(idx))
                 off += len(idx)
-                WindowBlend(res, ctx.fcanvas, ctx.fmask, d_fyx[sl], ctx.base_alpha, cm).apply(X[sl], res + 1, C, NS[sl], len(idx))
+                WindowBlend(res, ctx.fcanvas, ctx.fmask, d_fyx[sl], ctx.base_alpha, cm).apply(X[sl], pitch, C, None if last else NS[sl], len(idx))
         exchange([X], to_root=False)
         for c0 in range(s0, s1, batch_size):                                              # (3) everything after it
             sl = slice(c0, min(s1, c0 + batch_size))
