@@ -695,7 +695,7 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
     d_order = torch.from_numpy(np.concatenate(waves)).to(dev)
     d_pos = job.d_crops.to(torch.int64)[d_order]
     d_cropsel = job.d_crops[d_order].contiguous()
-    z_sel = z_per_patch[d_order] if z_per_patch is not None else None
+    z_sel = z_per_patch.to(dev)[d_order] if z_per_patch is not None else None          # (a host tensor is uploaded once)
     shares = phased_shares(n_crops, world)
     s0, s1 = shares[rank]
     # rank 0 holds every patch's feature map (it blends them); the other ranks only their own share
@@ -792,7 +792,7 @@ def _stylize_blended_flat(engine: TriadPaintEngine, job: CanvasJob, opts: GanBru
     d_fyx = torch.from_numpy(np.ascontiguousarray(snapped // down).astype(np.int32)).to(dev)[d_order].contiguous()
     d_pos = job.d_crops.to(torch.int64)[d_order]
     d_cropsel = job.d_crops[d_order].contiguous()
-    z_sel = z_per_patch[d_order].to(dev, torch.float64) if z_per_patch is not None else None
+    z_sel = z_per_patch.to(dev)[d_order].to(torch.float64) if z_per_patch is not None else None
     graphs = getattr(engine, 'use_batch_graph', False) and _plain_z_style(opts) and not sequential
     z_one = opts.style_z.to(dev, torch.float64) if graphs and z_sel is None else None
     off = 0
