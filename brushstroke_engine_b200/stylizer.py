@@ -649,6 +649,22 @@ def exchange_shares(tensors: Sequence[torch.Tensor], shares: Sequence[Tuple[int,
             req.wait()
 
 
+_RETURN_GROUPS = {}
+
+
+def _return_group(group, world: int):
+    """A second process group over the same ranks (its own NCCL communicator and stream), created once per main group: the
+    blended feature maps travel back on it while the main communicator is still receiving.  Collective: every rank of ``group``
+    reaches this call at the same point of ``_stylize_blended_phased``."""
+    import torch.distributed as dist
+    key = id(group) if group is not None else None
+    g = _RETURN_GROUPS.get(key)
+    if g is None:
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+        g = _RETURN_GROUPS[key] = dist.new_group(ranks=ranks)
+    return g
+
+
 PHASED_BLEND_MAX_BYTES = 16 << 30          # budget for the per-canvas buffer of pre-blend feature maps (2.35 GB for 4096^2, level 2)
 
 
@@ -734,17 +750,50 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
             ns_ = engine.render_split_pre(geom, chunk_opts(sl), res, X[loc])
             if ns_ is not None:
                 NS[loc] = ns_
-        exchange([X] if last else [X, NS], to_root=True)
-        if rank == 0:                                                                     # (2) the blend, in dependency order
+        # (2) the blend, in dependency order.  Several GPUs: the shares arrive one after the other (per-share receives in rank order on
+        # the main communicator) while rank 0 already blends the wavefronts whose patches are complete, and a share travels back -- on a
+        # SECOND communicator, so that returns are not queued behind the receives -- as soon as the last wavefront that touches it is done:
+        # of the 2 x 2 GB through rank 0's links only the first share in and the last share out are not hidden behind the blend.
+        # (a sub-group of the world keeps the two batched exchanges: creating the second communicator is collective over ALL ranks)
+        overlap = world > 1 and dev.type == 'cuda' and group is None and os.environ.get('NBE_BLEND_NO_EXCHANGE_OVERLAP') is None
+        back = _return_group(group, world) if overlap else None
+        peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+        feats = [X] if last else [X, NS]
+        if not overlap:
+            exchange(feats, to_root=True)
+        elif rank != 0 and s1 > s0:
+            out_reqs = [dist.isend(t[:s1 - s0], peer(0), group) for t in feats]
+        if rank == 0:
+            recv = {}
+            if overlap:
+                for r in range(1, world):
+                    a, b = shares[r]
+                    recv[r] = [dist.irecv(t[a:b], peer(r), group) for t in feats] if b > a else []
             ctx = _blend_context(engine, fh, fw, res, margin, cm, job.crop_margin)
             ctx.reset()
             d_fyx = torch.from_numpy(np.ascontiguousarray(snapped // down).astype(np.int32)).to(dev)[d_order].contiguous()
-            off = 0
+            off, arrived, returned, sends = 0, 0, 0, []
             for idx in waves:
                 sl = slice(off, off + len(idx))
                 off += len(idx)
+                while overlap and arrived + 1 < world and shares[arrived + 1][0] < off:    # this wavefront reaches into the next share(s)
+                    arrived += 1
+                    for q in recv[arrived]:
+                        q.wait()                                                          # (the compute stream waits, not the host)
                 WindowBlend(res, ctx.fcanvas, ctx.fmask, d_fyx[sl], ctx.base_alpha, cm).apply(X[sl], pitch, C, None if last else NS[sl], len(idx))
-        exchange([X], to_root=False)
+                while overlap and returned + 1 < world and shares[returned + 1][1] <= off:  # share complete: send it home
+                    returned += 1
+                    a, b = shares[returned]
+                    if b > a:
+                        sends.append(dist.isend(X[a:b], peer(returned), back))
+            for q in sends:
+                q.wait()
+        elif overlap and s1 > s0:
+            dist.irecv(X[:s1 - s0], peer(0), back).wait()
+            for q in out_reqs:
+                q.wait()
+        if not overlap:
+            exchange([X], to_root=False)
         for c0 in range(s0, s1, batch_size):                                              # (3) everything after it
             sl = slice(c0, min(s1, c0 + batch_size))
             loc = slice(sl.start - b0, sl.stop - b0)
