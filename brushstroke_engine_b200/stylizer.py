@@ -689,10 +689,11 @@ def _stylize_blended_phased(engine: TriadPaintEngine, job: CanvasJob, opts: GanB
     the generator runs 2 x 9 batches of 256 instead of 141 of <= 24.
 
     Several GPUs (``world`` > 1, one process per GPU): phases (1) and (3) are sharded -- rank r takes the r-th contiguous share of
-    the wavefront-ordered patch list -- and the blend runs on rank 0 over the gathered feature maps: one batched NCCL send/recv of
-    the shares to rank 0, the ~140 blend launches there, one send/recv back, and the finished tiles gathered on rank 0, which
-    places them.  Every patch still goes through the same kernels in the same blend order: the canvas equals the single-GPU one
-    bit for bit.  Returns the canvas on rank 0, None elsewhere."""
+    the wavefront-ordered patch list -- and the blend runs on rank 0 over the gathered feature maps: the shares travel to rank 0,
+    the ~140 blend launches run there (overlapped with the arrival of later shares and the return of finished ones, see below),
+    the blended maps travel back, and the finished tiles are gathered on rank 0, which places them.  Every patch still goes through
+    the same kernels in the same blend order: the canvas equals the single-GPU one bit for bit.  Returns the canvas on rank 0, None
+    elsewhere."""
     import torch.distributed as dist
     from .generator import WindowBlend
     dev = engine.device
