@@ -409,12 +409,11 @@ def main():
         canvas_host_ms = leg['ms_host_to_host']
         n_canvas_patches = leg['patches']
         # the reference's own stylization script runs with --feature_blending_level=2 (scripts/neube_stylize.sh): patches then
-        # depend on their raster predecessors; wavefront-batched on one GPU (rank 0 only, the other ranks idle)
+        # depend on their raster predecessors through the blend at 64^2 (stylizer._stylize_blended_phased)
         blend_ms = None
         blend_sharded_ms, blend_equal = None, None
         if not args.no_blend:
-            # the dependency chain (2 rows + cols wavefronts) is the critical path, so more GPUs do not shorten ONE blended canvas:
-            # with N ranks every rank renders its own canvas (replicas, no collective) and the line reports canvases per second
+            # first with N ranks rendering N canvases (replicas, no collective: canvases per second), then ONE canvas over all ranks
             btimes = []
             with torch.no_grad():
                 for rep in range(3):
