@@ -89,6 +89,14 @@ pack_flat_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int
                 *reinterpret_cast<uint4*>(dst + (((int64_t)n * H + h) * P + w) * cs + c) = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
+        // the tiles cover the W image columns; gap columns the last tile does not reach (W a multiple of 64: the gap would otherwise
+        // cost a whole extra tile per row -- a third of all CTAs at 128^2) are zeroed by the last tile's threads
+        if (blockIdx.x == gridDim.x - 1) {
+            const int g0 = w0 + PK_T;                                // first column this tile's 64 columns do not cover
+            const int wz = g0 + (t >> 3), c = c0 + cg;
+            if (wz < P && c < cs)
+                *reinterpret_cast<uint4*>(dst + (((int64_t)n * H + h) * P + wz) * cs + c) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
 }
 
@@ -146,7 +154,8 @@ static int launch_pack(const void* x, void* dst, int N, int C, int H, int W, int
     const int max_n = std::max(1, 65535 / H);
     for (int n0 = 0; n0 < N; n0 += max_n) {
         const int nn = std::min(max_n, N - n0);
-        dim3 grid((P + PK_T - 1) / PK_T, (cs + PK_T - 1) / PK_T, nn * H);
+        NBE_REQUIRE(P - (W + PK_T - 1) / PK_T * PK_T <= 32, "modulated_conv2d: row pitch too large for the packing kernel");
+        dim3 grid((W + PK_T - 1) / PK_T, (cs + PK_T - 1) / PK_T, nn * H);
         const T* xp = (const T*)x + (int64_t)n0 * C * H * W;
         const int vec_ok = (W % 4 == 0) && (((uintptr_t)xp & 7) == 0);
         pack_flat_kernel<T><<<grid, 256, 0, s>>>(xp, (__nv_bfloat16*)dst + (int64_t)n0 * H * P * cs,
