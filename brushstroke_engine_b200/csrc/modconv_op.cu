@@ -47,13 +47,18 @@ pack_flat_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int
     const int c0 = blockIdx.y * PK_T, w0 = blockIdx.x * PK_T;
     const int t = threadIdx.x;
     {   // ---- load: thread = (channel row r of 16, group of 4 columns)
+        // (pointers advance by constant strides: the 64-bit index arithmetic per pass was a quarter of this kernel's instructions,
+        // ncu: 24 instructions per element, issue slots 64 % busy at 46 % of the DRAM throughput)
         const int r = t >> 4, g = (t & 15) * 4;
+        const int w = w0 + g;
+        const T* sp = src + (((int64_t)n * C + c0 + r) * H + h) * W + w;
+        const int64_t sp_step = (int64_t)16 * H * W;
+        const float* scp = scale ? scale + (int64_t)n * C + c0 + r : nullptr;
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-            const int cl = r + 16 * pass, c = c0 + cl, w = w0 + g;
+        for (int pass = 0; pass < 4; ++pass, sp += sp_step) {
+            const int cl = r + 16 * pass, c = c0 + cl;
             float v[4] = {0.f, 0.f, 0.f, 0.f};
             if (c < C && w < W) {
-                const T* sp = src + (((int64_t)n * C + c) * H + h) * W + w;
                 if (vec_ok && w + 3 < W) {
                     const uint2 raw = *reinterpret_cast<const uint2*>(sp);
                     const float2 a = Pair16<T>::unpack(raw.x), b = Pair16<T>::unpack(raw.y);
@@ -63,7 +68,7 @@ pack_flat_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int
                     for (int k = 0; k < 4; ++k) if (w + k < W) v[k] = Cvt<T>::ld(sp[k]);
                 }
                 if (scale) {
-                    const float sc = scale[(int64_t)n * C + c];
+                    const float sc = scp[16 * pass];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) v[k] *= sc;
                 }
@@ -75,9 +80,11 @@ pack_flat_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int
     __syncthreads();
     {   // ---- store: thread = (column of 32, group of 8 channels) -> one 16-byte vector
         const int cg = (t & 7) * 8, pl = t >> 3;
+        const int c = c0 + cg;
+        __nv_bfloat16* dp = dst + (((int64_t)n * H + h) * P + w0 + pl) * cs + c;
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int wl = pl + 32 * pass, w = w0 + wl, c = c0 + cg;
+        for (int pass = 0; pass < 2; ++pass, dp += 32 * cs) {
+            const int wl = pl + 32 * pass, w = w0 + wl;
             if (w < P && c < cs) {
                 uint32_t o[4];
 #pragma unroll
@@ -86,14 +93,14 @@ pack_flat_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int
                     const unsigned short hi = *reinterpret_cast<const unsigned short*>(&tile[cg + 2 * k + 1][wl]);
                     o[k] = (uint32_t)lo | ((uint32_t)hi << 16);
                 }
-                *reinterpret_cast<uint4*>(dst + (((int64_t)n * H + h) * P + w) * cs + c) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(dp) = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
         // the tiles cover the W image columns; gap columns the last tile does not reach (W a multiple of 64: the gap would otherwise
         // cost a whole extra tile per row -- a third of all CTAs at 128^2) are zeroed by the last tile's threads
         if (blockIdx.x == gridDim.x - 1) {
             const int g0 = w0 + PK_T;                                // first column this tile's 64 columns do not cover
-            const int wz = g0 + (t >> 3), c = c0 + cg;
+            const int wz = g0 + (t >> 3);
             if (wz < P && c < cs)
                 *reinterpret_cast<uint4*>(dst + (((int64_t)n * H + h) * P + wz) * cs + c) = make_uint4(0u, 0u, 0u, 0u);
         }
@@ -110,12 +117,14 @@ unpack_flat_kernel(const __nv_bfloat16* __restrict__ src, T* __restrict__ dst, i
     const int t = threadIdx.x;
     {
         const int cg = (t & 7) * 8, pl = t >> 3;
+        const int c = c0 + cg;
+        const __nv_bfloat16* sp = src + (((int64_t)n * H + h) * P + w0 + pl) * cs + c;
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int wl = pl + 32 * pass, w = w0 + wl, c = c0 + cg;
+        for (int pass = 0; pass < 2; ++pass, sp += 32 * cs) {
+            const int wl = pl + 32 * pass, w = w0 + wl;
             uint4 raw = make_uint4(0u, 0u, 0u, 0u);
             if (w < W && c < C) {                                   // C % 8 == 0 on this path: whole vectors
-                raw = *reinterpret_cast<const uint4*>(src + (((int64_t)n * H + h) * P + w) * cs + c);
+                raw = *reinterpret_cast<const uint4*>(sp);
             }
             const uint32_t o[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
@@ -128,13 +137,15 @@ unpack_flat_kernel(const __nv_bfloat16* __restrict__ src, T* __restrict__ dst, i
     __syncthreads();
     {
         const int r = t >> 4, g = (t & 15) * 4;
+        const int w = w0 + g;
+        T* dp = dst + (((int64_t)n * C + c0 + r) * H + h) * W + w;
+        const int64_t dp_step = (int64_t)16 * H * W;
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-            const int cl = r + 16 * pass, c = c0 + cl, w = w0 + g;
+        for (int pass = 0; pass < 4; ++pass, dp += dp_step) {
+            const int cl = r + 16 * pass, c = c0 + cl;
             if (c < C && w < W) {
                 const float2 a = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(&tile[cl][g]));
                 const float2 b = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(&tile[cl][g + 2]));
-                T* dp = dst + (((int64_t)n * C + c) * H + h) * W + w;
                 if (vec_ok && w + 3 < W) {
                     *reinterpret_cast<uint2*>(dp) = make_uint2(Pair16<T>::pack(a.x, a.y), Pair16<T>::pack(b.x, b.y));
                 } else {
