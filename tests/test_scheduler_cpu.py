@@ -159,6 +159,26 @@ def test_phased_blend_share_exchange(tmp_path, world):
     assert int(np.load(os.path.join(str(tmp_path), 'ok_shares.npy'))[0]) == 1
 
 
+def test_phased_blend_eligibility():
+    """Which feature-blending levels the stylizer splits at the blend point (stylizer._phased_blend_ok): a block of the generator at
+    or above every geometry injection, with the per-canvas buffer of pre-blend feature maps inside its memory budget."""
+    import types
+    from brushstroke_engine_b200 import params as P
+    cfg = P.GeneratorConfig()
+    eng = types.SimpleNamespace(G=types.SimpleNamespace(cfg=cfg))
+    assert stylizer._phased_blend_ok(eng, 64, 2209) and stylizer._phased_blend_ok(eng, 32, 2209) and stylizer._phased_blend_ok(eng, 128, 2209)
+    assert not stylizer._phased_blend_ok(eng, 16, 2209)                      # below the 32^2 injection: the encoder still has to write into it
+    assert not stylizer._phased_blend_ok(eng, 48, 2209)                      # not a block resolution
+    assert not stylizer._phased_blend_ok(eng, 128, 10 ** 5)                  # 4.2 MB per patch: over the 16 GB budget
+    # bytes of the buffer: 64 x 65 x 128 channels at level 2, 32 x 33 x (128 + 256 injected) at level 3
+    assert cfg.block_in_channels(128) == 128 and cfg.block_in_channels(64) == 384
+    os.environ['NBE_BLEND_WAVEFRONT_GRAPHS'] = '1'
+    try:
+        assert not stylizer._phased_blend_ok(eng, 64, 2209)
+    finally:
+        del os.environ['NBE_BLEND_WAVEFRONT_GRAPHS']
+
+
 def test_row_shards_match_shard_bounds_on_the_dense_grid():
     ys, xs = np.meshgrid(np.arange(47) * 88, np.arange(47) * 88, indexing='ij')
     yx = np.stack([ys.ravel(), xs.ravel()], axis=1).astype(np.int32)
