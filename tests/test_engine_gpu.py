@@ -186,6 +186,14 @@ def test_phased_blending_equals_wavefronts_and_raster_loop(engines):
                 ph = stylizer._stylize_blended_phased(eng, job, opts, level, z, batch_size=bs)
                 assert torch.equal(ph, wav) and torch.equal(ph, seq), (level, z is None, bs)
     assert int((ph[..., 3] > 0).sum()) > 1000
+    # a sparse crop list (crops without strokes are dropped: irregular wavefronts, fewer patches than grid cells)
+    sparse = synthetic.synthetic_guidance(700, 610, num_lines=5, seed=11, radii=(3, 9))
+    job2 = stylizer.CanvasJob(eng, sparse, 10, 'full')
+    assert 2 <= len(job2.crops) < len(stylizer.CanvasJob(eng, sparse, 10, 'all').crops)
+    with torch.no_grad():
+        seq = stylizer._stylize_blended_flat(eng, job2, opts, 2, None, sequential=True)
+        ph = stylizer._stylize_blended_phased(eng, job2, opts, 2, None, batch_size=4)
+    assert torch.equal(ph, seq)
 
 
 def test_interactive_graph_session_equals_render_stroke(engines):
