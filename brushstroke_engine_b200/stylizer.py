@@ -657,7 +657,8 @@ def _return_group(group, world: int):
     blended feature maps travel back on it while the main communicator is still receiving.  Collective: every rank of ``group``
     reaches this call at the same point of ``_stylize_blended_phased``."""
     import torch.distributed as dist
-    key = id(group) if group is not None else None
+    main = group if group is not None else dist.distributed_c10d._get_default_group()
+    key = id(main)                                       # (a re-initialised default group is a new object: no stale communicator)
     g = _RETURN_GROUPS.get(key)
     if g is None:
         ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
