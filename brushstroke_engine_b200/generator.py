@@ -230,16 +230,30 @@ class Generator:
         self._layer_by_name = {L.name: L for L in self._layers}
         # static halves of the fused styles/demod and shifted-noise launch tables (host arrays of device pointers)
         nl = len(self._layers) + 1
-        VP, IA, FA = ctypes.c_void_p * nl, ctypes.c_int * nl, ctypes.c_float * nl
-        self._tab_n = nl
-        self._tab_aw = VP(*([L.affine_w.data_ptr() for L in self._layers] + [self._rgb_affine_w.data_ptr()]))
-        self._tab_ab = VP(*([L.affine_b.data_ptr() for L in self._layers] + [self._rgb_affine_b.data_ptr()]))
-        self._tab_wsq = VP(*([L.wsq.data_ptr() for L in self._layers] + [None]))
-        self._tab_cin = IA(*([L.cin for L in self._layers] + [self._rgb_affine_w.shape[0]]))
-        self._tab_cout = IA(*([L.cout for L in self._layers] + [0]))
-        self._tab_widx = IA(*list(range(nl)))                       # layer l reads ws[:, l] (networks_modified.py:144-151)
-        self._tab_pscale = FA(*([1.0] * (nl - 1) + [1.0 / math.sqrt(self._rgb_w.shape[1])]))
-        self._tab_pfrom = IA(*([0] * (nl - 1) + [9]))
+        # "virtual" entries: row ranges of a layer's affine whose styles the flat path needs as their own contiguous [B, rows]
+        # tensors -- the block channels (':head') and the injected geometry channels (':geo') of the layers that read a concat
+        # buffer -- written by the same launch instead of sliced + copied by torch kernels in every forward pass
+        self._virt = []                                             # (key, layer index, first row, rows)
+        for li, L in enumerate(self._layers):
+            if L.name.endswith('.conv0') and (L.res // 2) in cfg.geom_feature_resolutions:
+                cb = cfg.channels(L.res // 2)
+                self._virt += [(f'{L.name}:head', li, 0, cb), (f'{L.name}:geo', li, cb, L.cin - cb)]
+        if nl + len(self._virt) > 16:                               # (the launch table of nbe_styles_demod_f32 holds 16 entries)
+            self._virt = []
+        nv = len(self._virt)
+        VP, IA, FA = ctypes.c_void_p * (nl + nv), ctypes.c_int * (nl + nv), ctypes.c_float * (nl + nv)
+        self._tab_n = nl + nv
+        wd = self.w_dim
+        self._tab_aw = VP(*([L.affine_w.data_ptr() for L in self._layers] + [self._rgb_affine_w.data_ptr()] +
+                            [self._layers[li].affine_w.data_ptr() + 4 * r0 * wd for _, li, r0, _ in self._virt]))
+        self._tab_ab = VP(*([L.affine_b.data_ptr() for L in self._layers] + [self._rgb_affine_b.data_ptr()] +
+                            [self._layers[li].affine_b.data_ptr() + 4 * r0 for _, li, r0, _ in self._virt]))
+        self._tab_wsq = VP(*([L.wsq.data_ptr() for L in self._layers] + [None] + [None] * nv))
+        self._tab_cin = IA(*([L.cin for L in self._layers] + [self._rgb_affine_w.shape[0]] + [rows for _, _, _, rows in self._virt]))
+        self._tab_cout = IA(*([L.cout for L in self._layers] + [0] + [0] * nv))
+        self._tab_widx = IA(*(list(range(nl)) + [li for _, li, _, _ in self._virt]))   # layer l reads ws[:, l] (networks_modified.py:144-151)
+        self._tab_pscale = FA(*([1.0] * (nl - 1) + [1.0 / math.sqrt(self._rgb_w.shape[1])] + [1.0] * nv))
+        self._tab_pfrom = IA(*([0] * (nl - 1) + [9] + [0] * nv))
         self._VP = VP
         nn = len(self._layers)
         self._ntab_nc = (ctypes.c_void_p * nn)(*[L.noise_const.data_ptr() for L in self._layers])
@@ -316,7 +330,8 @@ class Generator:
             t = wsb[f'out{res}']
             bufs[res] = t
             dests.append((t, cb))
-            scales.append(prep[0][f'b{res * 2}.conv0'][:, cb:cb + cg].contiguous())
+            geo = prep[0].get(f'b{res * 2}.conv0:geo')
+            scales.append(geo if geo is not None else prep[0][f'b{res * 2}.conv0'][:, cb:cb + cg].contiguous())
         return InjectedGeometry(bufs, ws_latents, prep), dests, scales
 
     @property
@@ -388,12 +403,14 @@ class Generator:
         st_t = [torch.empty((B, L.cin), dtype=torch.float32, device=dev) for L in self._layers]
         dc_t = [torch.empty((B, L.cout), dtype=torch.float32, device=dev) for L in self._layers]
         scaled = torch.empty((B, self._rgb_affine_w.shape[0]), dtype=torch.float32, device=dev)
-        tab_st = self._VP(*([t.data_ptr() for t in st_t] + [scaled.data_ptr()]))
-        tab_dc = self._VP(*([t.data_ptr() for t in dc_t] + [None]))
+        virt_t = [torch.empty((B, rows), dtype=torch.float32, device=dev) for _, _, _, rows in self._virt]
+        tab_st = self._VP(*([t.data_ptr() for t in st_t] + [scaled.data_ptr()] + [t.data_ptr() for t in virt_t]))
+        tab_dc = self._VP(*([t.data_ptr() for t in dc_t] + [None] + [None] * len(virt_t)))
         _lib.call('nbe_styles_demod_f32', _lib.ptr(ws), B, self.num_ws, self.w_dim, self._tab_n, self._tab_aw, self._tab_ab,
                   self._tab_wsq, tab_st, tab_dc, self._tab_cin, self._tab_cout, self._tab_widx, self._tab_pscale, self._tab_pfrom,
                   _lib.stream())
         styles = {L.name: t for L, t in zip(self._layers, st_t)}
+        styles.update({key: t for (key, _, _, _), t in zip(self._virt, virt_t)})
         dcoefs = {L.name: t for L, t in zip(self._layers, dc_t)}
         # ToRGB: affine -> [colors(9) | styles(C) / sqrt(C)] (networks.py:455-462)
         from .bias_act import bias_act
@@ -780,7 +797,12 @@ class Generator:
             # conv1 -> next block's (pre-modulated, concatenated, zero-gapped) input
             nxt = self._layer_by_name[f'b{res * 2}.conv0']
             out = geom_feature.buffers[res] if (injected and res in cfg.geom_feature_resolutions) else wsb[f'out{res}']
-            ns = styles[nxt.name][:, :conv1.cout].contiguous() if nxt.cin != conv1.cout else styles[nxt.name]
+            if nxt.cin != conv1.cout:
+                ns = styles.get(f'{nxt.name}:head')
+                if ns is None:
+                    ns = styles[nxt.name][:, :conv1.cout].contiguous()
+            else:
+                ns = styles[nxt.name]
             pre_split = split is not None and split[0] == 'pre' and split[1] == res
             if pre_split:
                 # a block whose output buffer also holds injected geometry channels keeps writing there (the encoder's share is
