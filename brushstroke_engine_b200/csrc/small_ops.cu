@@ -497,7 +497,7 @@ extern "C" int nbe_blend_features(void* x, const void* saved, const float* alpha
 // ---------------------------------------------------------------------------------------------
 namespace nbe {
 
-constexpr int SD_MAX_LAYERS = 16;
+constexpr int SD_MAX_LAYERS = 24;
 
 struct StylesTable {
     int n_layers;

@@ -275,8 +275,8 @@ class TriadPaintEngine:
                     side = self._side_stream
                     side.wait_stream(main)
                     with torch.cuda.stream(side):
-                        ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
-                        ws = G.expand_ws(ws).to(self.device, torch.float32).contiguous()
+                        ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c, broadcast_view=True)
+                        ws = G.expand_ws(ws).to(self.device, torch.float32)   # (a single w per patch stays a stride-0 view)
                         inj, dests, scales = G.alloc_injection(ws)
                         if extra.get('noise_buffers') is None:
                             G.prefetch_noise(B, positions)
@@ -299,8 +299,8 @@ class TriadPaintEngine:
                         self.encoder.encode_into(geom, dests, scales, scales_ready=ready)
                     main.wait_event(ready)
             else:
-                ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c)
-                ws = G.expand_ws(ws).to(self.device, torch.float32).contiguous()
+                ws = opts.style_ws if opts.style_ws is not None else G.mapping(opts.style_z, self.style_c, broadcast_view=True)
+                ws = G.expand_ws(ws).to(self.device, torch.float32)
                 inj, dests, scales = G.alloc_injection(ws)
                 self.encoder.encode_into(geom, dests, scales)
             return G.forward_pre_mapped(ws=ws, positions=positions, geom_feature=inj,

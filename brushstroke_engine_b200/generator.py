@@ -96,7 +96,9 @@ class MappingNetwork:
         self.z_dim, self.c_dim, self.w_dim, self.num_ws = G.z_dim, 0, G.w_dim, G.num_ws
         self.num_layers = G.cfg.mapping_layers
 
-    def __call__(self, z, c=None, truncation_psi=1, truncation_cutoff=None, skip_w_avg_update=False):
+    def __call__(self, z, c=None, truncation_psi=1, truncation_cutoff=None, skip_w_avg_update=False, broadcast_view=False):
+        """``broadcast_view`` (not a reference argument): return the per-layer broadcast as a stride-0 view instead of the
+        reference's materialised ``repeat`` -- for callers that only read ws (the engine's fused step)."""
         G = self._G
         _lib.require_cuda(z, 'mapping')
         assert z.ndim == 2 and z.shape[1] == self.z_dim
@@ -107,7 +109,8 @@ class MappingNetwork:
                 x = fully_connected(x, G._map_w[i], G._map_b[i], ACT_LRELU, G.cfg.mapping_lr_multiplier, SQRT2, 0.2,
                                     normalize=(i == 0))
         with _lib.nvtx_range('broadcast'):
-            ws = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+            ws = x.unsqueeze(1).expand(-1, self.num_ws, -1) if (broadcast_view and truncation_cutoff is None) \
+                else x.unsqueeze(1).repeat([1, self.num_ws, 1])
         if truncation_psi != 1:
             with _lib.nvtx_range('truncate'):
                 if truncation_cutoff is None:
@@ -229,31 +232,43 @@ class Generator:
             self._rgb_affine_b = f32(p[f'{k}.affine.bias'])
         self._layer_by_name = {L.name: L for L in self._layers}
         # static halves of the fused styles/demod and shifted-noise launch tables (host arrays of device pointers)
-        nl = len(self._layers) + 1
-        # "virtual" entries: row ranges of a layer's affine whose styles the flat path needs as their own contiguous [B, rows]
-        # tensors -- the block channels (':head') and the injected geometry channels (':geo') of the layers that read a concat
-        # buffer -- written by the same launch instead of sliced + copied by torch kernels in every forward pass
-        self._virt = []                                             # (key, layer index, first row, rows)
+        # one table entry = one row range of an affine layer, written as its own contiguous [B, rows] tensor:
+        #   every layer's styles (+ demodulation coefficients), the ToRGB affine as its two halves -- 9 colour outputs and the C
+        #   styles / sqrt(C) (networks.py:455-462) --, and the block-channel (':head') / injected-geometry-channel (':geo') halves of
+        #   the layers that read a concat buffer: nothing is sliced + copied by torch kernels in a forward pass
+        wd = self.w_dim
+        nl = len(self._layers)
+        ent = [dict(key=L.name, aw=L.affine_w.data_ptr(), ab=L.affine_b.data_ptr(), wsq=L.wsq.data_ptr(), cin=L.cin, cout=L.cout,
+                    widx=li, pscale=1.0) for li, L in enumerate(self._layers)]   # layer l reads ws[:, l] (networks_modified.py:144-151)
+        rows_rgb = self._rgb_affine_w.shape[0]
+        rgb_aw, rgb_ab = self._rgb_affine_w.data_ptr(), self._rgb_affine_b.data_ptr()
+        ent.append(dict(key='rgb:colors', aw=rgb_aw, ab=rgb_ab, wsq=None, cin=9, cout=0, widx=nl, pscale=1.0))
+        ent.append(dict(key='rgb:styles', aw=rgb_aw + 4 * 9 * wd, ab=rgb_ab + 4 * 9, wsq=None, cin=rows_rgb - 9, cout=0, widx=nl,
+                        pscale=1.0 / math.sqrt(self._rgb_w.shape[1])))
+        self._virt = []
         for li, L in enumerate(self._layers):
             if L.name.endswith('.conv0') and (L.res // 2) in cfg.geom_feature_resolutions:
                 cb = cfg.channels(L.res // 2)
                 self._virt += [(f'{L.name}:head', li, 0, cb), (f'{L.name}:geo', li, cb, L.cin - cb)]
-        if nl + len(self._virt) > 16:                               # (the launch table of nbe_styles_demod_f32 holds 16 entries)
+        if len(ent) + len(self._virt) > 24:                         # (the launch table of nbe_styles_demod_f32 holds 24 entries)
             self._virt = []
-        nv = len(self._virt)
-        VP, IA, FA = ctypes.c_void_p * (nl + nv), ctypes.c_int * (nl + nv), ctypes.c_float * (nl + nv)
-        self._tab_n = nl + nv
-        wd = self.w_dim
-        self._tab_aw = VP(*([L.affine_w.data_ptr() for L in self._layers] + [self._rgb_affine_w.data_ptr()] +
-                            [self._layers[li].affine_w.data_ptr() + 4 * r0 * wd for _, li, r0, _ in self._virt]))
-        self._tab_ab = VP(*([L.affine_b.data_ptr() for L in self._layers] + [self._rgb_affine_b.data_ptr()] +
-                            [self._layers[li].affine_b.data_ptr() + 4 * r0 for _, li, r0, _ in self._virt]))
-        self._tab_wsq = VP(*([L.wsq.data_ptr() for L in self._layers] + [None] + [None] * nv))
-        self._tab_cin = IA(*([L.cin for L in self._layers] + [self._rgb_affine_w.shape[0]] + [rows for _, _, _, rows in self._virt]))
-        self._tab_cout = IA(*([L.cout for L in self._layers] + [0] + [0] * nv))
-        self._tab_widx = IA(*(list(range(nl)) + [li for _, li, _, _ in self._virt]))   # layer l reads ws[:, l] (networks_modified.py:144-151)
-        self._tab_pscale = FA(*([1.0] * (nl - 1) + [1.0 / math.sqrt(self._rgb_w.shape[1])] + [1.0] * nv))
-        self._tab_pfrom = IA(*([0] * (nl - 1) + [9] + [0] * nv))
+        for key, li, r0, rows in self._virt:
+            L = self._layers[li]
+            ent.append(dict(key=key, aw=L.affine_w.data_ptr() + 4 * r0 * wd, ab=L.affine_b.data_ptr() + 4 * r0, wsq=None, cin=rows,
+                            cout=0, widx=li, pscale=1.0))
+        ne = len(ent)
+        VP, IA, FA = ctypes.c_void_p * ne, ctypes.c_int * ne, ctypes.c_float * ne
+        self._tab_ent = ent
+        self._tab_n = ne
+        self._tab_aw = VP(*[e['aw'] for e in ent])
+        self._tab_ab = VP(*[e['ab'] for e in ent])
+        self._tab_wsq = VP(*[e['wsq'] for e in ent])
+        self._tab_cin = IA(*[e['cin'] for e in ent])
+        self._tab_cout = IA(*[e['cout'] for e in ent])
+        self._tab_widx = IA(*[e['widx'] for e in ent])
+        self._tab_widx0 = IA(*([0] * ne))                           # a single w repeated for every layer: ws passed as [B, 1, w]
+        self._tab_pscale = FA(*[e['pscale'] for e in ent])
+        self._tab_pfrom = IA(*([0] * ne))
         self._VP = VP
         nn = len(self._layers)
         self._ntab_nc = (ctypes.c_void_p * nn)(*[L.noise_const.data_ptr() for L in self._layers])
@@ -398,24 +413,25 @@ class Generator:
     def _styles(self, ws: torch.Tensor):
         """All affine layers + demodulation coefficients in one launch (they depend on ws only)."""
         B = ws.shape[0]
-        ws = ws.contiguous()
+        num_ws, widx = self.num_ws, self._tab_widx
+        if ws.shape[1] == self.num_ws and ws.stride(1) == 0 and ws.stride(2) == 1 and ws.stride(0) == self.w_dim:
+            num_ws, widx = 1, self._tab_widx0                       # the mapping network's broadcast view: never materialised
+        else:
+            ws = ws.contiguous()
         dev = self.device
-        st_t = [torch.empty((B, L.cin), dtype=torch.float32, device=dev) for L in self._layers]
-        dc_t = [torch.empty((B, L.cout), dtype=torch.float32, device=dev) for L in self._layers]
-        scaled = torch.empty((B, self._rgb_affine_w.shape[0]), dtype=torch.float32, device=dev)
-        virt_t = [torch.empty((B, rows), dtype=torch.float32, device=dev) for _, _, _, rows in self._virt]
-        tab_st = self._VP(*([t.data_ptr() for t in st_t] + [scaled.data_ptr()] + [t.data_ptr() for t in virt_t]))
-        tab_dc = self._VP(*([t.data_ptr() for t in dc_t] + [None] + [None] * len(virt_t)))
-        _lib.call('nbe_styles_demod_f32', _lib.ptr(ws), B, self.num_ws, self.w_dim, self._tab_n, self._tab_aw, self._tab_ab,
-                  self._tab_wsq, tab_st, tab_dc, self._tab_cin, self._tab_cout, self._tab_widx, self._tab_pscale, self._tab_pfrom,
+        out_t = [torch.empty((B, e['cin']), dtype=torch.float32, device=dev) for e in self._tab_ent]
+        dc_t = [torch.empty((B, e['cout']), dtype=torch.float32, device=dev) if e['cout'] else None for e in self._tab_ent]
+        tab_st = self._VP(*[t.data_ptr() for t in out_t])
+        tab_dc = self._VP(*[t.data_ptr() if t is not None else None for t in dc_t])
+        _lib.call('nbe_styles_demod_f32', _lib.ptr(ws), B, num_ws, self.w_dim, self._tab_n, self._tab_aw, self._tab_ab,
+                  self._tab_wsq, tab_st, tab_dc, self._tab_cin, self._tab_cout, widx, self._tab_pscale, self._tab_pfrom,
                   _lib.stream())
-        styles = {L.name: t for L, t in zip(self._layers, st_t)}
-        styles.update({key: t for (key, _, _, _), t in zip(self._virt, virt_t)})
-        dcoefs = {L.name: t for L, t in zip(self._layers, dc_t)}
+        styles = {e['key']: t for e, t in zip(self._tab_ent, out_t)}
+        dcoefs = {e['key']: t for e, t in zip(self._tab_ent, dc_t) if t is not None}
         # ToRGB: affine -> [colors(9) | styles(C) / sqrt(C)] (networks.py:455-462)
         from .bias_act import bias_act
-        colors = bias_act(scaled[:, :9].contiguous(), self._rgb_color_bias, dim=1, act='tanh').reshape(-1, 3, 3)
-        rgb_styles = scaled[:, 9:].contiguous()
+        colors = bias_act(styles.pop('rgb:colors'), self._rgb_color_bias, dim=1, act='tanh').reshape(-1, 3, 3)
+        rgb_styles = styles.pop('rgb:styles')
         return styles, dcoefs, colors, rgb_styles
 
     def _noise_all(self, B: int, positions):
