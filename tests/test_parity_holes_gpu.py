@@ -270,3 +270,41 @@ dist.destroy_process_group()
     subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
                     '--master-port', str(29700 + os.getpid() % 200), str(script)], check=True, timeout=600)
     assert (tmp_path / 'result.txt').read_text() == 'OK'
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_styles_table_broadcast_view_and_row_ranges(bundles, mode):
+    """The single styles launch (``nbe_styles_demod_f32``): a w repeated for every layer read through a stride-0 view gives the
+    same bits as the reference's materialised ``repeat`` (networks.py:281), and every row-range entry (ToRGB colours / styles,
+    ':head' / ':geo' halves of the concat layers) equals the slice of the whole layer's styles (networks.py:109-122, 455-462)."""
+    from brushstroke_engine_b200.generator import Generator
+    cfg, ecfg, gp, ep = bundles
+    G = Generator(gp, cfg, DEV, mode=mode)
+    z = torch.cat([P.style_z_from_seed(s) for s in range(11)]).to(DEV)
+    ws_rep = G.mapping(z, None)
+    ws_view = G.mapping(z, None, broadcast_view=True)
+    assert ws_rep.is_contiguous() and ws_view.stride(1) == 0 and torch.equal(ws_rep, ws_view)
+    assert G.mapping(z, None, truncation_psi=0.5, truncation_cutoff=4, broadcast_view=True).is_contiguous()   # written in place: materialised
+    s_rep, d_rep, c_rep, r_rep = G._styles(ws_rep)
+    s_view, d_view, c_view, r_view = G._styles(ws_view)
+    assert set(s_rep) == set(s_view) and set(d_rep) == set(d_view)
+    for k in s_rep:
+        assert torch.equal(s_rep[k], s_view[k]), k
+    for k in d_rep:
+        assert torch.equal(d_rep[k], d_view[k]), k
+    assert torch.equal(c_rep, c_view) and torch.equal(r_rep, r_view)
+    # a genuinely per-layer w+ (every layer its own latent) through the same launch, against the oracle's affine layers
+    wp = torch.randn(5, cfg.num_ws, cfg.w_dim, generator=torch.Generator().manual_seed(2)).to(DEV)
+    s_wp, _, c_wp, r_wp = G._styles(wp)
+    names = [k for k in s_wp if ':' not in k]
+    for li, k in enumerate(names):
+        ref = O.fully_connected(wp[:, li].cpu(), gp[f'synthesis.{k}.affine.weight'], gp[f'synthesis.{k}.affine.bias'])
+        assert md(s_wp[k], ref) < 1e-4, k
+    for k in s_wp:
+        if k.endswith(':head'):
+            base = s_wp[k.split(':')[0]]
+            assert torch.equal(s_wp[k], base[:, :s_wp[k].shape[1]]), k
+        if k.endswith(':geo'):
+            base = s_wp[k.split(':')[0]]
+            assert torch.equal(s_wp[k], base[:, base.shape[1] - s_wp[k].shape[1]:]), k
+    assert c_wp.shape == (5, 3, 3) and r_wp.shape[0] == 5 and float(c_wp.abs().max()) <= 1.0
