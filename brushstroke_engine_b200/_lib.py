@@ -30,6 +30,7 @@ _SIGNATURES = {
     'nbe_fc_f32': [_P, _I, _P, _P, _P, _I, _I, _I, _L, _L, _F, _F, _I, _F, _F, _I, _P],
     'nbe_shifted_noise_f32': [_P, _P, _P, _P, _I, _I, _I, _P],
     'nbe_styles_demod_f32': [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'nbe_styles_demod_input_f32': [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
     'nbe_shifted_noise_all_f32': [_P, _I, _I, _I, _P, _P, _P, _P, _P],
     'nbe_pack_nhwc_bf16': [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     'nbe_unpack_nchw_f32': [_P, _P, _I, _I, _I, _I, _I, _P],

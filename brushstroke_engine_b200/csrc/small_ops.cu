@@ -509,6 +509,12 @@ struct StylesTable {
     int cin[SD_MAX_LAYERS], cout[SD_MAX_LAYERS], w_index[SD_MAX_LAYERS];
     float post_scale[SD_MAX_LAYERS];          // styles *= post_scale for channels >= post_from (ToRGB: 1/sqrt(C) after the 9 colour outputs)
     int post_from[SD_MAX_LAYERS];
+    // optional: the blocks of layer in_layer also write the first block's modulated constant input,
+    // in_out[n, y, x, c] = bf16(in_const[y, x, c] * styles[n, c]) (networks.py:642-643 `const` + networks.py:68 `x * styles`)
+    int in_layer;                             // -1: none
+    const float* in_const;                    // [in_h, in_w, cin]
+    __nv_bfloat16* in_out;                    // [N, in_h, in_pitch, cin], columns >= in_w are left alone (the zero gap)
+    int in_h, in_w, in_pitch;
 };
 
 // grid = (ceil(N / SD_NB), n_layers); block = SD_THREADS threads.  styles = affine(w) (FullyConnectedLayer, lr 1, bias_init 1:
@@ -560,6 +566,16 @@ styles_demod_kernel(const float* __restrict__ ws, int N, int num_ws, int w_dim, 
             const float a = acc[nb] + bias;
             s_s2[nb * cin + c] = a * a;
             if (n0 + nb < N && blockIdx.z == 0) tab.styles[l][(long long)(n0 + nb) * cin + c] = (c >= tab.post_from[l]) ? a * post : a;
+        }
+        if (l == tab.in_layer && blockIdx.z == 0) {
+            for (int y = 0; y < tab.in_h; ++y)
+                for (int x = 0; x < tab.in_w; ++x) {
+                    const float cv = tab.in_const[(y * tab.in_w + x) * cin + c];
+#pragma unroll
+                    for (int nb = 0; nb < SD_NB; ++nb)
+                        if (n0 + nb < N)
+                            tab.in_out[(((long long)(n0 + nb) * tab.in_h + y) * tab.in_pitch + x) * cin + c] = __float2bfloat16_rn(cv * (acc[nb] + bias));
+                }
         }
     }
     __syncthreads();
@@ -671,6 +687,16 @@ extern "C" int nbe_styles_demod_f32(const float* ws, int N, int num_ws, int w_di
                                     const void* const* affine_w, const void* const* affine_b, const void* const* wsq,
                                     void* const* styles, void* const* dcoef, const int* cin, const int* cout, const int* w_index,
                                     const float* post_scale, const int* post_from, nbe_stream_t stream) {
+    return nbe_styles_demod_input_f32(ws, N, num_ws, w_dim, n_layers, affine_w, affine_b, wsq, styles, dcoef, cin, cout, w_index,
+                                      post_scale, post_from, -1, nullptr, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int nbe_styles_demod_input_f32(const float* ws, int N, int num_ws, int w_dim, int n_layers,
+                                          const void* const* affine_w, const void* const* affine_b, const void* const* wsq,
+                                          void* const* styles, void* const* dcoef, const int* cin, const int* cout, const int* w_index,
+                                          const float* post_scale, const int* post_from,
+                                          int in_layer, const float* in_const, void* in_out, int in_h, int in_w, int in_pitch,
+                                          nbe_stream_t stream) {
     NBE_REQUIRE(ws && N >= 0 && n_layers >= 1 && n_layers <= SD_MAX_LAYERS && w_dim >= 1 && num_ws >= 1, "styles_demod: bad arguments");
     NBE_REQUIRE(affine_w && affine_b && wsq && styles && dcoef && cin && cout && w_index && post_scale && post_from, "styles_demod: null table");
     if (N == 0) return NBE_OK;
@@ -684,6 +710,13 @@ extern "C" int nbe_styles_demod_f32(const float* ws, int N, int num_ws, int w_di
         tab.styles[l] = (float*)styles[l]; tab.dcoef[l] = (float*)dcoef[l]; tab.cin[l] = cin[l]; tab.cout[l] = cout[l];
         tab.w_index[l] = w_index[l]; tab.post_scale[l] = post_scale[l]; tab.post_from[l] = post_from[l];
         if (cin[l] > max_cin) max_cin = cin[l];
+    }
+    tab.in_layer = -1; tab.in_const = nullptr; tab.in_out = nullptr; tab.in_h = tab.in_w = tab.in_pitch = 0;
+    if (in_layer >= 0) {
+        NBE_REQUIRE(in_layer < n_layers && in_const && in_out && in_h >= 1 && in_w >= 1 && in_pitch >= in_w && ((uintptr_t)in_out & 1) == 0,
+                    "styles_demod: bad constant-input arguments");
+        NBE_REQUIRE(post_scale[in_layer] == 1.f || post_from[in_layer] >= cin[in_layer], "styles_demod: the constant input is modulated by un-scaled styles (layer %d has a post scale)", in_layer);
+        tab.in_layer = in_layer; tab.in_const = in_const; tab.in_out = (__nv_bfloat16*)in_out; tab.in_h = in_h; tab.in_w = in_w; tab.in_pitch = in_pitch;
     }
     const int groups = (N + SD_NB - 1) / SD_NB;
     dim3 grid(groups, n_layers, groups * n_layers < 2 * kNumSMs ? 8 : 1);

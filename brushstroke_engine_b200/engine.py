@@ -21,6 +21,7 @@ import torch
 
 from . import _lib
 from . import synthetic
+from .bias_act import bias_act
 from .generator import Generator
 from .geo_encoder import GeometryEncoder
 from .params import Bundle, EncoderConfig, GeneratorConfig, style_z_from_seed
@@ -99,13 +100,29 @@ class GanBrushOptions:
         self.style_z = prep(self.style_z)
         self.style_ws = prep(self.style_ws)
 
-    def prepare_colors(self, default_colors):
-        """[B,3,ncolors] in [0,1]; user colours override columns (brush.py:514-527)."""
-        out = default_colors.clone()
+    def prepare_colors(self, default_colors, owned=False):
+        """[B,3,ncolors] in [0,1]; user colours override columns (brush.py:514-527).  ``owned``: the caller made
+        ``default_colors`` for this call alone, so it is modified in place instead of cloned."""
+        out = default_colors if owned else default_colors.clone()
         for idx, col in enumerate((self.color0, self.color1, self.canvas_color)):
             if col is not None:
                 out[:, :, idx] = col.to(out.device)
         return out
+
+
+_ONES3 = {}
+_TORCH_COLORS = os.environ.get('NBE_TORCH_COLORS') is not None      # A/B switch: (colors + 1) / 2 as two torch kernels
+
+
+def _unit_range_colors(colors: torch.Tensor) -> torch.Tensor:
+    """``(colors + 1) / 2`` of the generator's tanh colours (brush.py:770,913) as ONE ``nbe_bias_act`` launch -- bias 1, linear,
+    gain 0.5: the same float32 add followed by an exact halving -- instead of two torch kernels."""
+    if _TORCH_COLORS or colors.dtype != torch.float32 or colors.ndim != 3 or colors.shape[1] != 3 or not colors.is_cuda:
+        return (colors + 1) / 2.0
+    one = _ONES3.get(colors.device)
+    if one is None:
+        one = _ONES3[colors.device] = torch.ones(3, dtype=torch.float32, device=colors.device)
+    return bias_act(colors.contiguous(), one, dim=1, act='linear', gain=0.5)
 
 
 class StyleUVSMapper:
@@ -315,14 +332,14 @@ class TriadPaintEngine:
 
     def _composite(self, triad_data, opts, B, want_f32=True, crop_margin=None):
         uvs = triad_data['uvs'].contiguous()
-        default_colors = (triad_data['colors'] + 1) / 2.0
+        default_colors = _unit_range_colors(triad_data['colors'])
         sfactor = None
         if opts.enable_uvs_mapping:
             sf = getattr(opts, 'sfactor', None)                 # per-patch factors of a multi-session batch (server.StrokeBatcher)
             if sf is None:
                 sf = self.uvs_mapper.get_sfactor(opts)
             sfactor = sf.reshape(-1).to(self.device, torch.float32).expand(B).contiguous()
-        colors = opts.prepare_colors(default_colors).contiguous()
+        colors = opts.prepare_colors(default_colors, owned=True).contiguous()
         W = self.patch_width
         out_f32 = torch.empty((B, 4, W, W), dtype=torch.float32, device=self.device) if want_f32 else None
         out_u8 = None
@@ -607,8 +624,8 @@ class CanvasPaintEngine(TriadPaintEngine):
 
     def _composite(self, triad_data, opts, B, want_f32=True, crop_margin=None):
         uvs = triad_data['uvs'].contiguous()
-        default_colors = (triad_data['colors'] + 1) / 2.0
-        colors = opts.prepare_colors(default_colors).contiguous()
+        default_colors = _unit_range_colors(triad_data['colors'])
+        colors = opts.prepare_colors(default_colors, owned=True).contiguous()
         alpha = triad_data['alpha'].contiguous()                     # [B,2,W,W]; channel 0 is alpha_fg
         gen_canvas = triad_data['canvas'].contiguous()
         W = self.patch_width

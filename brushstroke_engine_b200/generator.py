@@ -32,6 +32,8 @@ from .conv2d_resample import conv2d_f32
 from .modconv import demod_coefs, weight_sqsum
 from .params import Bundle, GeneratorConfig
 
+_NO_STYLES_IN4 = os.environ.get('NBE_NO_STYLES_IN4') is not None      # A/B switch: b4 input by the torch expression
+
 SQRT2 = math.sqrt(2.0)
 ACT_LINEAR, ACT_LRELU, ACT_TANH = 1, 3, 4
 
@@ -269,6 +271,8 @@ class Generator:
         self._tab_widx0 = IA(*([0] * ne))                           # a single w repeated for every layer: ws passed as [B, 1, w]
         self._tab_pscale = FA(*[e['pscale'] for e in ent])
         self._tab_pfrom = IA(*([0] * ne))
+        self._tab_in4_layer = [e['key'] for e in ent].index('b4.conv1')
+        self._in4_filled = None                                     # (styles of b4.conv1, in4 tensor) of the last _styles(ws, in4) launch
         self._VP = VP
         nn = len(self._layers)
         self._ntab_nc = (ctypes.c_void_p * nn)(*[L.noise_const.data_ptr() for L in self._layers])
@@ -337,8 +341,8 @@ class Generator:
         if tuple(ws_latents.shape[1:]) != (self.num_ws, self.w_dim):
             raise RuntimeError(f'alloc_injection: ws must be [B, {self.num_ws}, {self.w_dim}] (see expand_ws), got {tuple(ws_latents.shape)}')
         with torch.cuda.device(self.device):
-            prep = self._styles(ws_latents.to(torch.float32))
-        wsb = self._workspace(B)
+            wsb = self._workspace(B)
+            prep = self._styles(ws_latents.to(torch.float32), in4=wsb['in4'])
         bufs, dests, scales = {}, [], []
         for res, cg in zip(cfg.geom_feature_resolutions, cfg.geom_feature_channels):
             cb = cfg.channels(res)
@@ -410,8 +414,10 @@ class Generator:
                                'norm_noise_positions itself, networks_modified.py:351-353)')
         return nc, 0, L.noise_strength
 
-    def _styles(self, ws: torch.Tensor):
-        """All affine layers + demodulation coefficients in one launch (they depend on ws only)."""
+    def _styles(self, ws: torch.Tensor, in4: Optional[torch.Tensor] = None):
+        """All affine layers + demodulation coefficients in one launch (they depend on ws only).  ``in4`` (the flat path's
+        zero-gapped b4 input [B, 4, 5, C] bf16): the same launch also writes ``const * styles(b4.conv1)`` into it
+        (networks.py:642-643 + :68); ``_run_bf16_flat`` recognises the pair by identity and skips its own torch expression."""
         B = ws.shape[0]
         num_ws, widx = self.num_ws, self._tab_widx
         if ws.shape[1] == self.num_ws and ws.stride(1) == 0 and ws.stride(2) == 1 and ws.stride(0) == self.w_dim:
@@ -423,10 +429,19 @@ class Generator:
         dc_t = [torch.empty((B, e['cout']), dtype=torch.float32, device=dev) if e['cout'] else None for e in self._tab_ent]
         tab_st = self._VP(*[t.data_ptr() for t in out_t])
         tab_dc = self._VP(*[t.data_ptr() if t is not None else None for t in dc_t])
-        _lib.call('nbe_styles_demod_f32', _lib.ptr(ws), B, num_ws, self.w_dim, self._tab_n, self._tab_aw, self._tab_ab,
+        in_layer = -1
+        if _NO_STYLES_IN4:                                          # A/B switch: the torch expression in _run_bf16_flat
+            in4 = None
+        if in4 is not None:
+            in_layer = self._tab_in4_layer
+            assert in4.dtype == torch.bfloat16 and in4.is_contiguous() and tuple(in4.shape) == (B,) + tuple(self._const_nhwc.shape[:1]) \
+                + (self._const_nhwc.shape[1] + 1, self._const_nhwc.shape[2])
+        _lib.call('nbe_styles_demod_input_f32', _lib.ptr(ws), B, num_ws, self.w_dim, self._tab_n, self._tab_aw, self._tab_ab,
                   self._tab_wsq, tab_st, tab_dc, self._tab_cin, self._tab_cout, widx, self._tab_pscale, self._tab_pfrom,
-                  _lib.stream())
+                  in_layer, _lib.ptr(self._const_nhwc) if in4 is not None else None, _lib.ptr(in4), self._const_nhwc.shape[0],
+                  self._const_nhwc.shape[1], self._const_nhwc.shape[1] + 1, _lib.stream())
         styles = {e['key']: t for e, t in zip(self._tab_ent, out_t)}
+        self._in4_filled = (styles['b4.conv1'], in4) if in4 is not None else None
         dcoefs = {e['key']: t for e, t in zip(self._tab_ent, dc_t) if t is not None}
         # ToRGB: affine -> [colors(9) | styles(C) / sqrt(C)] (networks.py:455-462)
         from .bias_act import bias_act
@@ -500,7 +515,7 @@ class Generator:
             else:
                 if injected:
                     raise RuntimeError('synthesis: InjectedGeometry was prepared for a different ws tensor')
-                styles, dcoefs, colors, rgb_styles = self._styles(ws)
+                styles, dcoefs, colors, rgb_styles = self._styles(ws, in4=self._workspace(B)['in4'] if (flat and not (split and split[0] == 'post')) else None)
             run = self._run_fp32 if mode == 'fp32' else (self._run_bf16_flat if flat else self._run_bf16)
             pre, self._noise_prefetched = self._noise_prefetched, None
             if positions is not None and noise_mode == 'const':
@@ -695,7 +710,9 @@ class Generator:
             # b4 input: const * styles(b4.conv1), zero-gapped [B,4,5,C]
             c4 = self._layer_by_name['b4.conv1']
             xin = wsb['in4']
-            xin[:, :, :4, :] = (self._const_nhwc.unsqueeze(0) * styles[c4.name][:, None, None, :]).to(torch.bfloat16)
+            filled, self._in4_filled = self._in4_filled, None
+            if filled is None or filled[0] is not styles[c4.name] or filled[1] is not xin:   # (styles from somewhere else: torch expression)
+                xin[:, :, :4, :] = (self._const_nhwc.unsqueeze(0) * styles[c4.name][:, None, None, :]).to(torch.bfloat16)
             xin_pitch = 5
         nvtx = _lib.NVTX
         for res in cfg.block_resolutions:

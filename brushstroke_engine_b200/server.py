@@ -278,9 +278,9 @@ class _BatchOptions(GanBrushOptions):
         self.color_vals = None          # [B, 3 (rgb), 3 (idx)]
         self.sfactor = None             # [B] float32 (UVS mapping on) or None
 
-    def prepare_colors(self, default_colors):
+    def prepare_colors(self, default_colors, owned=False):
         if self.color_mask is None:
-            return default_colors.clone()
+            return default_colors if owned else default_colors.clone()
         return torch.where(self.color_mask[:, None, :], self.color_vals, default_colors)
 
 

@@ -111,6 +111,18 @@ int nbe_styles_demod_f32(const float* ws, int N, int num_ws, int w_dim, int n_la
                          void* const* styles, void* const* dcoef, const int* cin, const int* cout, const int* w_index,
                          const float* post_scale, const int* post_from, nbe_stream_t stream);
 
+/* nbe_styles_demod_f32 that also writes the modulated constant input of the first synthesis block in the same launch
+ * (in_layer >= 0): in_out[n, y, x, c] = bf16(in_const[y, x, c] * styles_{in_layer}[n, c]) for y < in_h, x < in_w, with in_const
+ * float32 [in_h, in_w, cin] and in_out bf16 [N, in_h, in_pitch, cin] (columns >= in_w -- the zero gap of the flat layout -- are not
+ * touched).  Replaces: `x = self.const ... repeat` (SG2/training/networks.py:642-643) followed by the `x * styles` of the
+ * first modulated_conv2d (SG2/training/networks.py:68).  in_layer = -1: identical to nbe_styles_demod_f32. */
+int nbe_styles_demod_input_f32(const float* ws, int N, int num_ws, int w_dim, int n_layers,
+                               const void* const* affine_w, const void* const* affine_b, const void* const* wsq,
+                               void* const* styles, void* const* dcoef, const int* cin, const int* cout, const int* w_index,
+                               const float* post_scale, const int* post_from,
+                               int in_layer, const float* in_const, void* in_out, int in_h, int in_w, int in_pitch,
+                               nbe_stream_t stream);
+
 /* nbe_shifted_noise_f32 for n_layers noise buffers at once (HOST arrays of device pointers; out_l is [N, res_l, res_l]). */
 int nbe_shifted_noise_all_f32(const int64_t* positions, int N, int mod, int n_layers,
                               const void* const* noise_const, const void* const* lin, void* const* out, const int* res,

@@ -308,3 +308,37 @@ def test_styles_table_broadcast_view_and_row_ranges(bundles, mode):
             base = s_wp[k.split(':')[0]]
             assert torch.equal(s_wp[k], base[:, base.shape[1] - s_wp[k].shape[1]:]), k
     assert c_wp.shape == (5, 3, 3) and r_wp.shape[0] == 5 and float(c_wp.abs().max()) <= 1.0
+
+
+@pytest.mark.parametrize('B', [1, 11, 64])
+def test_styles_launch_writes_the_modulated_constant_input(bundles, B):
+    """``nbe_styles_demod_input_f32``: the b4 input ``const * styles(b4.conv1)`` (networks.py:642-643 + :68) written by the styles
+    launch equals the torch expression bit for bit, the gap column stays untouched, and the flat path picks it up only for the
+    very styles / buffer pair it was written for (full images equal with and without it)."""
+    from brushstroke_engine_b200.generator import Generator
+    cfg, ecfg, gp, ep = bundles
+    G = Generator(gp, cfg, DEV, mode='bf16')
+    ws = torch.randn(B, cfg.num_ws, cfg.w_dim, generator=torch.Generator().manual_seed(B)).to(DEV)
+    in4 = torch.full((B, 4, 5, cfg.channels(4)), 7.0, dtype=torch.bfloat16, device=DEV)
+    styles, _, _, _ = G._styles(ws, in4=in4)
+    assert G._in4_filled is not None and G._in4_filled[0] is styles['b4.conv1'] and G._in4_filled[1] is in4
+    ref = (G._const_nhwc.unsqueeze(0) * styles['b4.conv1'][:, None, None, :]).to(torch.bfloat16)
+    assert torch.equal(in4[:, :, :4, :], ref)
+    assert bool((in4[:, :, 4, :] == 7.0).all())
+    plain, _, _, _ = G._styles(ws)
+    assert G._in4_filled is None and torch.equal(plain['b4.conv1'], styles['b4.conv1'])
+    if G.flat_supported:
+        geom = [torch.randn(B, c, r, r, generator=torch.Generator().manual_seed(r)).to(DEV)
+                for r, c in zip(cfg.geom_feature_resolutions, cfg.geom_feature_channels)]
+        pos = torch.randint(0, 4096, (B, 2), generator=torch.Generator().manual_seed(3)).to(DEV)
+        img_a = G.forward_pre_mapped(ws, geom, positions=pos, noise_mode='const')           # styles launch fills in4
+        G._styles(ws, in4=G._workspace(B)['in4'])                                            # stale pair: other styles object
+        real = G._styles
+        G._styles = lambda w, in4=None: real(w)                                              # torch expression
+        try:
+            img_b = G.forward_pre_mapped(ws, geom, positions=pos, noise_mode='const')
+        finally:
+            G._styles = real
+        img_a = img_a[0] if isinstance(img_a, tuple) else img_a
+        img_b = img_b[0] if isinstance(img_b, tuple) else img_b
+        assert torch.equal(img_a, img_b)
