@@ -214,7 +214,13 @@ __device__ __forceinline__ void fir_tiled_body(const CUtensorMap& tmap_t, const 
     // every CTA takes one contiguous run of tiles: the image (and with it the per-channel epilogue vectors in s_epi) changes
     // once per 128 tiles instead of at every tile, so the loop has no exposed global-memory round trip and one barrier per tile
     const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int t_begin = blockIdx.x * per_cta, t_end = min(total_tiles, t_begin + per_cta);
+    // strip_ok == 2, CYCLIC strip order: CTA k takes the strips k, k + grid, k + 2 grid, ... -- neighbouring CTAs then filter
+    // neighbouring strips of one image at the same time, and the 3 halo columns two strips share are read from DRAM once and from
+    // L2 the second time (in contiguous runs the two strips are ~40 MB of traffic apart).  `tile` is then a CTA-local counter.
+    const bool cyclic = PACKED && strip_ok == 2 && p.debug != 2;
+    const int total_strips = tiles_x * (total_tiles / (tiles_x * tiles_y));
+    const int my_strips = cyclic ? (total_strips - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int t_begin = cyclic ? 0 : blockIdx.x * per_cta, t_end = cyclic ? my_strips * tiles_y : min(total_tiles, t_begin + per_cta);
     // STRIP order (packed separable path): a run walks DOWN a 16-pixel-wide strip of its image, so the last three horizontally
     // filtered rows of a tile are the first three of the next one and stay in REGISTERS: only the first tile of a strip (or of
     // the run) loads its 3 halo rows, every other tile loads 8 rows instead of 11 -- the tile loads are what this pass waits for
@@ -223,7 +229,8 @@ __device__ __forceinline__ void fir_tiled_body(const CUtensorMap& tmap_t, const 
     const bool strip = PACKED && sep && strip_ok && p.debug != 2;
     auto decode = [&](int tile, int& tx, int& ty, int& n) {
         int t = tile;
-        if (strip) { ty = t % tiles_y; t /= tiles_y; tx = t % tiles_x; t /= tiles_x; }
+        if (cyclic) { ty = t % tiles_y; t = (int)blockIdx.x + (t / tiles_y) * (int)gridDim.x; tx = t % tiles_x; t /= tiles_x; }
+        else if (strip) { ty = t % tiles_y; t /= tiles_y; tx = t % tiles_x; t /= tiles_x; }
         else       { tx = t % tiles_x; t /= tiles_x; ty = t % tiles_y; t /= tiles_y; }
         n = t;
     };
@@ -495,9 +502,16 @@ extern "C" int nbe_fir_act_nhwc_bf16(const void* t, const float* f, void* y, int
         cuuint32_t box8[4] = {128, FT_IW, FT_OH, 1};
         st = make_tmap(&tm8, t, 4, dims, strides, box8, "FIR input (strip)", 1, /*swizzle=*/0);
         if (st) return st;
-        static const int strip_ok = getenv("NBE_FIR_NO_STRIP") == nullptr;              // A/B switch: every tile loads its own halo rows
+        static const int strip_env = getenv("NBE_FIR_NO_STRIP") == nullptr;              // A/B switch: every tile loads its own halo rows
+        static const int cyclic_env = getenv("NBE_FIR_CYCLIC") ? atoi(getenv("NBE_FIR_CYCLIC")) : 1;   // A/B switch: 0 = contiguous runs only
         const int tiles_x = (OW + FT_OW - 1) / FT_OW, tiles_y = (OH + FT_OH - 1) / FT_OH;
         const int64_t total = (int64_t)tiles_x * tiles_y * N;
+        int strip_ok = strip_env;
+        {   // cyclic strip order where whole strips balance as well as tile runs do (128^2 at batch 256: 7 strips = 112 tiles vs 111)
+            const int64_t g = std::min<int64_t>(total, (int64_t)kNumSMs * 2), strips = (int64_t)tiles_x * N;
+            const int64_t run = (total + g - 1) / g, cyc = (strips + g - 1) / g * tiles_y;
+            if (strip_env && cyclic_env && tiles_x > 1 && strips >= g && cyc * 50 <= run * 51) strip_ok = 2;
+        }
         NBE_REQUIRE(total <= INT32_MAX, "fir_act_nhwc: too many tiles");
         const size_t smem = 128 + 2 * ((FT_TILE_BYTES + 127) & ~127) + (2 * FT_OH * FT_OW + 3 * 128 + 16) * sizeof(float) + 64;
         static std::once_flag once;

@@ -205,3 +205,32 @@ def test_random_shape_sweep():
     r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fuzz_flat.py'), '40', '7'], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert 'worst relative error' in r.stdout
+
+
+def test_fir_act_nhwc_cyclic_strip_order_equals_contiguous_runs():
+    """At large batches the FIR pass hands out whole 16-px strips round-robin (neighbouring CTAs share halo columns through L2);
+    40 images at 128^2 (320 strips >= 296 CTAs: cyclic) must give the bits of the same images filtered 20 at a time (contiguous
+    tile runs) -- the arithmetic per output does not depend on the order.  Reference semantics: upfirdn2d.py:168-208."""
+    B, R, C = 40, 128, 128
+    g = torch.Generator().manual_seed(11)
+    TP = R + 2
+    T = torch.randn(B, TP, TP, C, generator=g).to(torch.bfloat16).to(DEV)
+    f4 = O.setup_filter([1, 3, 3, 1]).to(DEV)
+    sc = (torch.rand(B, C, generator=g) + 0.5).to(DEV)
+    ns = (torch.rand(B, C, generator=g) + 0.5).to(DEV)
+    noise = torch.randn(B, R, R, generator=g).to(DEV)
+    bias = (torch.randn(C, generator=g) * 0.1).to(DEV)
+
+    def run(lo, hi):
+        n = hi - lo
+        y = torch.zeros(n, R, R, C, dtype=torch.bfloat16, device=DEV)
+        t, s, z, nz = T[lo:hi].contiguous(), sc[lo:hi].contiguous(), ns[lo:hi].contiguous(), noise[lo:hi].contiguous()
+        _lib.call('nbe_fir_act_nhwc_bf16', _lib.ptr(t), _lib.ptr(f4), _lib.ptr(y), n, R, R, C, R + 1, R + 1, 1, C, TP, TP * TP,
+                  C, R, R * R, 4.0, _lib.ptr(s), _lib.ptr(nz), R * R, 0.3, _lib.ptr(bias), 0.2, SQ2, 256.0, _lib.ptr(z), _lib.stream())
+        torch.cuda.synchronize()
+        return y
+
+    whole = run(0, B)
+    halves = torch.cat([run(0, 20), run(20, 40)])
+    assert torch.equal(whole, halves)
+    assert float(whole.float().abs().max()) > 0.1
