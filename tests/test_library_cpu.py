@@ -120,3 +120,25 @@ def test_matches_reference_library(tmp_path):
         rr.set_style('rand0', r)
         assert torch.equal(o.style_z, r.style_z)
     assert L.interp_style_id('a', 7, 0.5) == RL._interp_style_id('a', 7, 0.5)
+
+
+def test_prepare_colors_owned_and_default_colour_range():
+    """``GanBrushOptions.prepare_colors`` (brush.py:514-527): user colours override columns of the default table; the caller's table
+    is cloned unless the caller says it owns it.  ``_unit_range_colors`` is ``(colors + 1) / 2`` (brush.py:770,913); on a CPU tensor
+    it is the torch expression itself (the one-launch form needs a CUDA tensor)."""
+    import torch
+    from brushstroke_engine_b200 import engine as E
+    colors = torch.tensor([[[-1.0, 0.0, 1.0], [0.5, -0.5, 0.25], [1.0, 1.0, -1.0]]]).repeat(4, 1, 1)
+    unit = E._unit_range_colors(colors)
+    assert torch.equal(unit, (colors + 1) / 2.0) and float(unit.min()) >= 0.0 and float(unit.max()) <= 1.0
+    opts = E.GanBrushOptions()
+    kept = unit.clone()
+    out = opts.prepare_colors(unit)
+    assert out is not unit and torch.equal(out, kept)
+    assert opts.prepare_colors(unit, owned=True) is unit
+    opts.color1 = torch.tensor([0.1, 0.2, 0.3])
+    out = opts.prepare_colors(unit)
+    assert torch.equal(unit, kept)                                  # the caller's table is untouched
+    assert torch.equal(out[:, :, 1], torch.tensor([0.1, 0.2, 0.3]).expand(4, 3)) and torch.equal(out[:, :, 0], kept[:, :, 0])
+    out2 = opts.prepare_colors(unit, owned=True)
+    assert out2 is unit and torch.equal(out2, out)
